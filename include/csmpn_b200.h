@@ -1,0 +1,153 @@
+/*
+ * csmpn_b200 -- C ABI of the B200-native CSMPN hot path (libcsmpn_b200.so, sm_100a).
+ *
+ * The reference (congliuUvA/Clifford-Group-Equivariant-Simplicial-Message-Passing-Networks) is pure
+ * Python; its seam for this path is the class API of csmpn/algebra/cliffordalgebra.py and
+ * csmpn/models/cegnn_utils.py.  Every entry point below replaces the body of one reference method
+ * (cited per function as file:line, relative to the reference root) and is what a ctypes binding of
+ * that method would call; INTEGRATION.md shows the binding.
+ *
+ * Conventions
+ *  - All float tensors are fp32, contiguous, laid out [rows, channels, B] with the B = 2^dim blades
+ *    innermost in grade-major ("short-lex") blade order (metric.py:18-29).
+ *  - All pointers except `metric` / `*_host` and the params structs themselves are DEVICE pointers that the
+ *    caller owns; nothing returned is allocated by the library.  Work is enqueued on `stream`
+ *    (a cudaStream_t passed as void*); the call returns without synchronising.
+ *  - `metric` is a HOST array of `dim` floats (the diagonal metric handed to CliffordAlgebra(metric),
+ *    cliffordalgebra.py:11-25).  dim in 1..5.
+ *  - Return value: 0 on success, a negative csmpn_status otherwise.  No exceptions cross the ABI.
+ *  - Re-entrant; no global state besides immutable function attributes set on first use.
+ */
+#ifndef CSMPN_B200_H_
+#define CSMPN_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* csmpn_stream_t; /* cudaStream_t */
+
+enum csmpn_status {
+  CSMPN_OK = 0,
+  CSMPN_ERR_BAD_DIM = -1,       /* dim outside 1..5 */
+  CSMPN_ERR_BAD_ARG = -2,       /* null pointer / negative size / inconsistent sizes */
+  CSMPN_ERR_UNSUPPORTED = -3,   /* configuration not built (e.g. fused path with a non-Euclidean metric) */
+  CSMPN_ERR_CUDA = -4,          /* a CUDA runtime call failed; see csmpn_last_cuda_error() */
+  CSMPN_ERR_WORKSPACE = -5      /* workspace too small */
+};
+
+int csmpn_version(void);
+const char* csmpn_status_string(int status);
+const char* csmpn_last_cuda_error(void);
+/* number of SMs of the current device (grid sizing is a multiple of this) */
+int csmpn_sm_count(void);
+
+/* ---- algebra tables (host side; metric.py:18-120, cliffordalgebra.py:27-42,238-252) ------------------
+ * out_idx[B*B]  : blade index j of e_i e_k            coef[B*B] : c[i, j(i,k), k]
+ * grades[B]     : grade of each blade                 paths[G*G*G] : 1 where (g_i, g_j, g_k) occurs
+ * All outputs are HOST arrays; any may be NULL. */
+int csmpn_algebra_tables(int dim, const float* metric, int32_t* out_idx, float* coef, int32_t* grades,
+                         uint8_t* paths);
+
+/* ---- geometric product  (CliffordAlgebra.geometric_product, cliffordalgebra.py:44-54) ----------------
+ * out[r, j] = sum_{i,k} a[r,i] c[i,j,k] b[r,k]      a, b, out: [n_mv, B]
+ * a_stride_zero / b_stride_zero: 1 broadcasts a single multivector over all rows (einsum "...").   */
+int csmpn_gp_fwd(int dim, const float* metric, const float* a, const float* b, float* out, int64_t n_mv,
+                 int a_bcast, int b_bcast, csmpn_stream_t stream);
+/* grad_a, grad_b: [n_mv, B] (per-row gradients even for a broadcast operand; the caller reduces). */
+int csmpn_gp_bwd(int dim, const float* metric, const float* a, const float* b, const float* grad_out,
+                 float* grad_a, float* grad_b, int64_t n_mv, int a_bcast, int b_bcast, csmpn_stream_t stream);
+
+/* ---- per-grade quadratic forms  (CliffordAlgebra.qs / norms, cliffordalgebra.py:143-168) -------------
+ * q[r, g] = sum_{i in grade g} qsign_i x[r,i]^2 ;  mode 0: q, mode 1: norm = (q^2 + 1e-16)^(1/4)  */
+int csmpn_grade_forms_fwd(int dim, const float* metric, const float* x, float* out, int64_t n_mv, int mode,
+                          csmpn_stream_t stream);
+int csmpn_grade_forms_bwd(int dim, const float* metric, const float* x, const float* grad_out, float* grad_x,
+                          int64_t n_mv, int mode, csmpn_stream_t stream);
+
+/* ---- MVLinear  (cegnn_utils.py:287-338) ---------------------------------------------------------------
+ * y[r,n,i] = sum_m x[r,m,i] W[n,m,g(i)] (+ bias[n] on blade 0)
+ * weight: [Cout, Cin, G] if subspaces else [Cout, Cin]; bias: [Cout] or NULL.                          */
+int csmpn_mvlinear_fwd(int dim, const float* x, const float* weight, const float* bias, float* y, int64_t rows,
+                       int c_in, int c_out, int subspaces, csmpn_stream_t stream);
+/* grad_x = grad_y . W  (same contraction with the roles of n and m swapped) */
+int csmpn_mvlinear_bwd_input(int dim, const float* grad_y, const float* weight, float* grad_x, int64_t rows,
+                             int c_in, int c_out, int subspaces, csmpn_stream_t stream);
+/* grad_w[n,m,g] = sum_{r, i in g} grad_y[r,n,i] x[r,m,i] ; grad_bias[n] = sum_r grad_y[r,n,0] (NULL to skip).
+ * Deterministic two-pass reduction; workspace (device) must hold csmpn_mvlinear_bwd_weight_workspace() bytes. */
+int64_t csmpn_mvlinear_bwd_weight_workspace(int dim, int64_t rows, int c_in, int c_out);
+int csmpn_mvlinear_bwd_weight(int dim, const float* x, const float* grad_y, float* grad_w, float* grad_bias,
+                              int64_t rows, int c_in, int c_out, int subspaces, void* workspace,
+                              int64_t workspace_bytes, csmpn_stream_t stream);
+
+/* ---- MVSiLU (invariant="mag2")  (cegnn_utils.py:53-83) -----------------------------------------------
+ * y_i = sigmoid(a[n,g(i)] * inv_g + b[n,g(i)]) x_i ; inv_0 = x_0, inv_g = q_g(x).   a, b: [C, G]        */
+int csmpn_mvsilu_fwd(int dim, const float* metric, const float* x, const float* a, const float* b, float* y,
+                     int64_t rows, int channels, csmpn_stream_t stream);
+/* grad_a, grad_b: [C, G] (overwritten).  workspace: csmpn_param_grad_workspace(channels * G * 2) bytes. */
+int csmpn_mvsilu_bwd(int dim, const float* metric, const float* x, const float* a, const float* b,
+                     const float* grad_y, float* grad_x, float* grad_a, float* grad_b, int64_t rows, int channels,
+                     void* workspace, int64_t workspace_bytes, csmpn_stream_t stream);
+
+/* ---- NormalizationLayer  (cegnn_utils.py:34-51) -------------------------------------------------------
+ * y_i = x_i / (sigmoid(a[n,g]) (norm_g(x) - 1) + 1 + 1e-6)      a: [C, G]                              */
+int csmpn_mvnorm_fwd(int dim, const float* metric, const float* x, const float* a, float* y, int64_t rows,
+                     int channels, csmpn_stream_t stream);
+int csmpn_mvnorm_bwd(int dim, const float* metric, const float* x, const float* a, const float* grad_y,
+                     float* grad_x, float* grad_a, int64_t rows, int channels, void* workspace,
+                     int64_t workspace_bytes, csmpn_stream_t stream);
+
+/* ---- MVLayerNorm  (cegnn_utils.py:86-96) --------------------------------------------------------------
+ * y = a[n] x / (mean_n (Q(x[r,n])^2 + 1e-16)^(1/4) + 1e-6),  Q = sum_i qsign_i x_i^2     a: [C]        */
+int csmpn_mvlayernorm_fwd(int dim, const float* metric, const float* x, const float* a, float* y, int64_t rows,
+                          int channels, csmpn_stream_t stream);
+int csmpn_mvlayernorm_bwd(int dim, const float* metric, const float* x, const float* a, const float* grad_y,
+                          float* grad_x, float* grad_a, int64_t rows, int channels, void* workspace,
+                          int64_t workspace_bytes, csmpn_stream_t stream);
+
+/* ---- weighted geometric product of SteerableGeometricProductLayer  (cegnn_utils.py:126-155) ----------
+ * z[r,n,j] = sum_{i,k} x[r,n,i] c[i,j,k] w[n, path(g_i,g_j,g_k)] r[r,n,k]
+ * out = (left + z) * scale   when `left` != NULL (include_first_order: scale = 1/sqrt 2), else z * scale.
+ * w: [C, P] with P = number of non-zero grade paths in row-major (g_i, g_j, g_k) order.                */
+int csmpn_wgp_fwd(int dim, const float* metric, const float* x, const float* r, const float* w, const float* left,
+                  float scale, float* out, int64_t rows, int channels, csmpn_stream_t stream);
+/* grad_x, grad_r: [rows, C, B]; grad_w: [C, P]; grad_left = scale * grad_out is left to the caller.     */
+int csmpn_wgp_bwd(int dim, const float* metric, const float* x, const float* r, const float* w,
+                  const float* grad_out, float scale, float* grad_x, float* grad_r, float* grad_w, int64_t rows,
+                  int channels, void* workspace, int64_t workspace_bytes, csmpn_stream_t stream);
+
+/* bytes of workspace needed by the *_bwd calls above that reduce `n_params` parameter gradients over rows */
+int64_t csmpn_param_grad_workspace(int64_t n_params);
+
+/* ---- graph plumbing for EGCL / PyG MessagePassing.propagate  (cegnn_utils.py:277-284) ----------------
+ * csr_build: stable counting sort of the E adjacency pairs by key (receiver = edge_index[1], or sender).
+ *   keys      [E] int64 (row of edge_index)      n_nodes: number of simplices
+ *   rowptr    [n_nodes + 1] int32 (out)          perm [E] int32 (out): perm[p] = original pair id of the
+ *   p-th pair in key-sorted order; pairs with equal key keep their original relative order.
+ *   workspace: csmpn_csr_workspace(E, n_nodes) bytes.                                                   */
+int64_t csmpn_csr_workspace(int64_t n_pairs, int64_t n_nodes);
+int csmpn_csr_build(const int64_t* keys, int64_t n_pairs, int64_t n_nodes, int32_t* rowptr, int32_t* perm,
+                    void* workspace, int64_t workspace_bytes, csmpn_stream_t stream);
+/* out[p, :] = h[dst[p], :] - h[src[p], :]  for width floats per row (C*B); src/dst int64 [E].          */
+int csmpn_gather_diff(const float* h, const int64_t* src, const int64_t* dst, float* out, int64_t n_pairs,
+                      int64_t width, csmpn_stream_t stream);
+/* Deterministic segment reduce (aggr "sum" | "mean", PyG scatter semantics: mean divides by
+ * max(count,1), empty receivers get 0):   out[n,:] = sum_{p in rowptr[n]..rowptr[n+1]} msg[perm[p], :]
+ * scaled by 1/max(deg,1) when mean != 0.   msg rows are in ORIGINAL pair order.                       */
+int csmpn_segment_reduce(const float* msg, const int32_t* rowptr, const int32_t* perm, float* out,
+                         int64_t n_nodes, int64_t width, int mean, csmpn_stream_t stream);
+/* Adjoint of gather_diff, deterministic:  grad_h[n,:] (+)= sum_{p: dst[p]=n} g[p,:] - sum_{p: src[p]=n} g[p,:]
+ * using the two CSR orderings (by receiver and by sender).  accumulate != 0 adds to grad_h.           */
+int csmpn_scatter_diff(const float* g, const int32_t* rowptr_dst, const int32_t* perm_dst,
+                       const int32_t* rowptr_src, const int32_t* perm_src, float* grad_h, int64_t n_nodes,
+                       int64_t width, int accumulate, csmpn_stream_t stream);
+/* Adjoint of segment_reduce: grad_msg[p,:] = grad_out[dst[p],:] * (mean ? 1/max(deg[dst[p]],1) : 1).   */
+int csmpn_segment_expand(const float* grad_out, const int64_t* dst, const int32_t* rowptr, float* grad_msg,
+                         int64_t n_pairs, int64_t width, int mean, csmpn_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CSMPN_B200_H_ */

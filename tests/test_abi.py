@@ -1,0 +1,73 @@
+"""The C-ABI library builds, loads and exports every symbol include/csmpn_b200.h declares (no GPU needed)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from conftest import ROOT
+
+
+@pytest.fixture(scope="module")
+def built_lib():
+    import __graft_entry__ as g
+
+    g.build()
+    from csmpn_b200 import _lib
+
+    return _lib
+
+
+def header_symbols():
+    text = open(os.path.join(ROOT, "include", "csmpn_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(csmpn_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_symbols_exported(built_lib):
+    lib = ctypes.CDLL(built_lib.LIB_PATH)
+    names = header_symbols()
+    assert len(names) >= 25
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, f"declared in the header but not exported: {missing}"
+
+
+def test_bindings_cover_header(built_lib):
+    built_lib.lib()
+    bound = set(built_lib.EXPORTED)
+    assert set(header_symbols()) <= bound, sorted(set(header_symbols()) - bound)
+
+
+def test_host_only_entry_points(built_lib):
+    lib = built_lib.lib()
+    assert lib.csmpn_version() >= 100
+    assert lib.csmpn_status_string(0) == b"ok"
+    assert b"workspace" in lib.csmpn_status_string(-5)
+    # algebra tables on the host: Cl(3,0) multiplication table known answers
+    B = 8
+    out = (ctypes.c_int32 * (B * B))()
+    coef = (ctypes.c_float * (B * B))()
+    grades = (ctypes.c_int32 * B)()
+    paths = (ctypes.c_uint8 * 64)()
+    metric = (ctypes.c_float * 3)(1, 1, 1)
+    assert lib.csmpn_algebra_tables(3, metric, out, coef, grades, paths) == 0
+    assert list(grades) == [0, 1, 1, 1, 2, 2, 2, 3]
+    row2 = [(out[2 * B + k], coef[2 * B + k]) for k in range(B)]
+    assert row2 == [(2, 1), (4, -1), (0, 1), (6, 1), (1, -1), (7, -1), (3, 1), (5, -1)]
+    assert sum(paths) == 20
+    assert sum(1 for c in coef if c < 0) == 24
+    assert lib.csmpn_algebra_tables(7, metric, out, coef, grades, paths) == -1
+    assert lib.csmpn_param_grad_workspace(10) == 1024 * 10 * 4
+
+
+def test_product_refuses_cpu_tensors(built_lib):
+    import torch
+
+    from csmpn_b200.algebra.cliffordalgebra import CliffordAlgebra
+    from csmpn_b200.models.cegnn_utils import MVLinear
+
+    alg = CliffordAlgebra((1, 1, 1))
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        alg.geometric_product(torch.randn(2, 8), torch.randn(2, 8))
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        MVLinear(alg, 4, 4)(torch.randn(3, 4, 8))
