@@ -30,6 +30,7 @@ def _declare(lib):
         "csmpn_status_string": (c_char_p, [i32]),
         "csmpn_last_cuda_error": (c_char_p, []),
         "csmpn_sm_count": (c_int, []),
+        "csmpn_launch_count": (i64, []),
         "csmpn_algebra_tables": (c_int, [i32, P, P, P, P, P]),
         "csmpn_gp_fwd": (c_int, [i32, P, P, P, P, i64, i32, i32, P]),
         "csmpn_gp_bwd": (c_int, [i32, P, P, P, P, P, P, i64, i32, i32, P]),

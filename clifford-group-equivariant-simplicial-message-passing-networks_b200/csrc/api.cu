@@ -1,6 +1,13 @@
 // Host-only entry points: version, status strings, algebra tables.
 #include "common.cuh"
 
+namespace csmpn {
+unsigned long long& launch_counter() {
+  static unsigned long long n = 0;
+  return n;
+}
+}  // namespace csmpn
+
 using namespace csmpn;
 
 extern "C" {
@@ -22,6 +29,8 @@ const char* csmpn_status_string(int status) {
 const char* csmpn_last_cuda_error(void) { return last_error_buf(); }
 
 int csmpn_sm_count(void) { return sm_count_cached(); }
+
+int64_t csmpn_launch_count(void) { return (int64_t)launch_counter(); }
 
 // metric.py:18-120 / cliffordalgebra.py:27-42,238-252 restated with bit arithmetic.
 int csmpn_algebra_tables(int dim, const float* metric, int32_t* out_idx, float* coef, int32_t* grades, uint8_t* paths) {

@@ -19,6 +19,9 @@ inline char* last_error_buf() {
   return buf;
 }
 
+// process-wide count of kernels launched by this library (bench.py reports it as gpu_launches)
+unsigned long long& launch_counter();
+
 inline int cuda_fail(cudaError_t e, const char* what) {
   snprintf(last_error_buf(), 256, "%s: %s", what, cudaGetErrorString(e));
   return CSMPN_ERR_CUDA;
@@ -30,8 +33,10 @@ inline int cuda_fail(cudaError_t e, const char* what) {
     if (_e != cudaSuccess) return ::csmpn::cuda_fail(_e, #expr); \
   } while (0)
 
+// every kernel launch is followed by this macro: it also counts launches (csmpn_launch_count())
 #define CSMPN_LAUNCH_CHECK(name)                              \
   do {                                                        \
+    ++::csmpn::launch_counter();                              \
     cudaError_t _e = cudaGetLastError();                      \
     if (_e != cudaSuccess) return ::csmpn::cuda_fail(_e, name); \
   } while (0)

@@ -280,7 +280,7 @@ class EGCL(nn.Module):
         else:
             input = torch.cat([h_i - h_j, edge_attr], dim=1)
         h_msg = self.edge_model(input)
-        return self.algebra.flatten(h_msg)
+        return h_msg.reshape(h_msg.shape[0], self.out_features * self.algebra.n_blades)
 
     def update(self, h_agg, h, node_attr):
         h_agg, h = self.algebra.split(h_agg), self.algebra.split(h)
@@ -297,9 +297,9 @@ class EGCL(nn.Module):
         graph = get_csr(edge_index, h.shape[0])
         B = self.algebra.n_blades
         diff = ops.GatherDiffFn.apply(h, graph)                      # h_i - h_j, [E, C*B]
-        diff = diff.reshape(graph.n_pairs, -1, B)
+        diff = diff.reshape(graph.n_pairs, h.shape[1] // B, B)
         inp = diff if edge_attr is None else torch.cat([diff, edge_attr], dim=1)
-        msg = self.algebra.flatten(self.edge_model(inp))
+        msg = self.edge_model(inp).reshape(graph.n_pairs, self.out_features * B)
         agg = ops.SegmentReduceFn.apply(msg, graph, self.aggr == "mean")
         return self.update(agg, h, node_attr)
 

@@ -43,6 +43,8 @@ const char* csmpn_status_string(int status);
 const char* csmpn_last_cuda_error(void);
 /* number of SMs of the current device (grid sizing is a multiple of this) */
 int csmpn_sm_count(void);
+/* number of CUDA kernels this library has launched in this process (monotonic; not thread-safe accounting) */
+int64_t csmpn_launch_count(void);
 
 /* ---- algebra tables (host side; metric.py:18-120, cliffordalgebra.py:27-42,238-252) ------------------
  * out_idx[B*B]  : blade index j of e_i e_k            coef[B*B] : c[i, j(i,k), k]

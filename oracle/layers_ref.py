@@ -126,8 +126,8 @@ def mvlayernorm(alg, x, a):
     return a.reshape(1, -1, 1) * x / mu
 
 
-def weighted_gp(alg, x, r, w):
-    """z[r,n,j] = sum_{i,k} x_i c[i,j,k] w[n, path(g_i,g_j,g_k)] r_k   (cegnn_utils.py:126-140,151)"""
+def weighted_gp_tables(alg, x, r, w):
+    """z[r,n,j] = sum_{i,k} x_i c[i,j,k] w[n, path(g_i,g_j,g_k)] r_k   (cegnn_utils.py:126-140,151) -- term by term"""
     coef = alg.C.to(x.dtype)
     keep = alg.path_of_term >= 0
     I, J, K = alg.I[keep], alg.J[keep], alg.K[keep]
@@ -135,6 +135,16 @@ def weighted_gp(alg, x, r, w):
     terms = x[..., I] * r[..., K] * wt.unsqueeze(0)
     out = torch.zeros_like(x)
     return out.index_add(-1, J, terms)
+
+
+def weighted_gp(alg, x, r, w):
+    """Same contraction evaluated the way the reference does it on CPU: scatter the path weights into a dense
+    [C,B,B,B] tensor and einsum (cegnn_utils.py:126-140,151).  Used by the timed CPU baseline so that the baseline
+    runs the reference's algorithm, not a slower table walk; tests check it equals ``weighted_gp_tables``."""
+    keep = alg.path_of_term >= 0
+    dense = torch.zeros(w.shape[0], alg.B, alg.B, alg.B, dtype=x.dtype)
+    dense[:, alg.I[keep], alg.J[keep], alg.K[keep]] = w[:, alg.path_of_term[keep]] * alg.C.to(x.dtype)[keep]
+    return torch.einsum("bni,nijk,bnk->bnj", x, dense, r)
 
 
 def sgp(alg, x, p, prefix):

@@ -149,3 +149,13 @@ def test_oracle_fp64_agrees_with_fp32():
     y32 = R.egcl(alg, h, ei, ea, na, p32, "sum")
     y64 = R.egcl(alg, h.double(), ei, ea.double(), na.double(), p64, "sum")
     assert_close(y32, y64.float(), 5e-5, "fp32 vs fp64 oracle")
+
+
+def test_dense_and_table_weighted_product_agree():
+    for metric in ((1, 1), (1, 1, 1), (1, -1, 1), (0, 1, 1)):
+        alg = R.RefAlgebra(metric)
+        gen = torch.Generator().manual_seed(1)
+        x = torch.randn(7, 5, alg.B, generator=gen, dtype=torch.float64)
+        r = torch.randn(7, 5, alg.B, generator=gen, dtype=torch.float64)
+        w = torch.randn(5, alg.n_paths, generator=gen, dtype=torch.float64)
+        assert_close(R.weighted_gp(alg, x, r, w), R.weighted_gp_tables(alg, x, r, w), 1e-12, str(metric))
