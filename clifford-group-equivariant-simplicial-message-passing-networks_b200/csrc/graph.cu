@@ -235,6 +235,90 @@ __global__ void segment_expand_kernel(const float* __restrict__ go, const int64_
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------
+// receiver-sorted helpers for the fused EGCL path
+__global__ void sorted_indices_kernel(const int64_t* __restrict__ src, const int64_t* __restrict__ dst,
+                                      const int32_t* __restrict__ perm, int32_t* __restrict__ ss, int32_t* __restrict__ ds,
+                                      int32_t* __restrict__ rank, int64_t n) {
+  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < n; p += (int64_t)gridDim.x * blockDim.x) {
+    const int32_t e = perm[p];
+    ss[p] = (int32_t)src[e];
+    ds[p] = (int32_t)dst[e];
+    if (rank) rank[e] = (int32_t)p;
+  }
+}
+
+__global__ void rank_kernel(const int32_t* __restrict__ perm, int32_t* __restrict__ rank, int64_t n) {
+  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < n; p += (int64_t)gridDim.x * blockDim.x) rank[perm[p]] = (int32_t)p;
+}
+
+__global__ void segment_reduce_sorted_kernel(const float4* __restrict__ msg, const int32_t* __restrict__ rowptr,
+                                             float4* __restrict__ out, int64_t n_nodes, int64_t vpr, int mean) {
+  const int64_t total = n_nodes * vpr;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t n = idx / vpr, v = idx - n * vpr;
+    const int32_t b = rowptr[n], e = rowptr[n + 1];
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int32_t p = b; p < e; ++p) {
+      const float4 t = msg[(int64_t)p * vpr + v];
+      acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+    }
+    if (mean) {
+      const float d = (float)(e - b > 1 ? e - b : 1);
+      acc.x /= d; acc.y /= d; acc.z /= d; acc.w /= d;
+    }
+    out[idx] = acc;
+  }
+}
+
+__global__ void segment_expand_sorted_kernel(const float4* __restrict__ go, const int32_t* __restrict__ dst_sorted,
+                                             const int32_t* __restrict__ rowptr, float4* __restrict__ gm, int64_t n_pairs,
+                                             int64_t vpr, int mean) {
+  const int64_t total = n_pairs * vpr;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t p = idx / vpr, v = idx - p * vpr;
+    const int32_t n = dst_sorted[p];
+    float sc = 1.f;
+    if (mean) { const int32_t d = rowptr[n + 1] - rowptr[n]; sc = 1.f / (float)(d > 1 ? d : 1); }
+    float4 t = go[(int64_t)n * vpr + v];
+    t.x *= sc; t.y *= sc; t.z *= sc; t.w *= sc;
+    gm[idx] = t;
+  }
+}
+
+__global__ void scatter_diff_sorted_kernel(const float* __restrict__ g, int64_t ld, const int32_t* __restrict__ rp_dst,
+                                           const int32_t* __restrict__ rp_src, const int32_t* __restrict__ pm_src,
+                                           const int32_t* __restrict__ rank, float* __restrict__ gh, int64_t n_nodes,
+                                           int64_t width, int accumulate) {
+  const int64_t vpr = width / 4, total = n_nodes * vpr;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t n = idx / vpr, v = idx - n * vpr;
+    float4* o = reinterpret_cast<float4*>(gh + n * width) + v;
+    float4 acc = accumulate ? *o : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int32_t p = rp_dst[n]; p < rp_dst[n + 1]; ++p) {
+      const float4 t = *(reinterpret_cast<const float4*>(g + (int64_t)p * ld) + v);
+      acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+    }
+    for (int32_t q = rp_src[n]; q < rp_src[n + 1]; ++q) {
+      const int64_t p = rank[pm_src[q]];
+      const float4 t = *(reinterpret_cast<const float4*>(g + p * ld) + v);
+      acc.x -= t.x; acc.y -= t.y; acc.z -= t.z; acc.w -= t.w;
+    }
+    *o = acc;
+  }
+}
+
+__global__ void scatter_rows_kernel(const float* __restrict__ g, int64_t ld, int64_t col0, const int32_t* __restrict__ eid,
+                                    float* __restrict__ out, int64_t n_rows, int64_t width) {
+  const int64_t vpr = width / 4, total = n_rows * vpr;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t p = idx / vpr, v = idx - p * vpr;
+    const float4 t = *(reinterpret_cast<const float4*>(g + p * ld + col0) + v);
+    *(reinterpret_cast<float4*>(out + (int64_t)eid[p] * width) + v) = t;
+  }
+}
+
 inline int grid_for(int64_t total, int threads) {
   int64_t b = (total + threads - 1) / threads;
   int64_t cap = (int64_t)sm_count_cached() * 16;
@@ -336,6 +420,76 @@ int csmpn_segment_expand(const float* grad_out, const int64_t* dst, const int32_
   cudaStream_t s = (cudaStream_t)stream;
   CSMPN_VEC_DISPATCH(width, segment_expand_kernel, n_pairs * width, grad_out, dst, rowptr, grad_msg, n_pairs, width, mean);
   CSMPN_LAUNCH_CHECK("segment_expand");
+  return CSMPN_OK;
+}
+
+int csmpn_csr_sorted_indices(const int64_t* src, const int64_t* dst, const int32_t* perm, int32_t* src_sorted,
+                             int32_t* dst_sorted, int64_t n_pairs, csmpn_stream_t stream) {
+  if (n_pairs < 0) return CSMPN_ERR_BAD_ARG;
+  if (n_pairs == 0) return CSMPN_OK;
+  if (!src || !dst || !perm || !src_sorted || !dst_sorted) return CSMPN_ERR_BAD_ARG;
+  cudaStream_t s = (cudaStream_t)stream;
+  sorted_indices_kernel<<<grid_for(n_pairs, 256), 256, 0, s>>>(src, dst, perm, src_sorted, dst_sorted, nullptr, n_pairs);
+  CSMPN_LAUNCH_CHECK("csr_sorted_indices");
+  return CSMPN_OK;
+}
+
+int csmpn_segment_reduce_sorted(const float* msg, const int32_t* rowptr, float* out, int64_t n_nodes, int64_t width,
+                                int mean, csmpn_stream_t stream) {
+  if (n_nodes < 0 || width <= 0 || width % 4) return CSMPN_ERR_BAD_ARG;
+  if (n_nodes == 0) return CSMPN_OK;
+  if (!rowptr || !out) return CSMPN_ERR_BAD_ARG;
+  cudaStream_t s = (cudaStream_t)stream;
+  segment_reduce_sorted_kernel<<<grid_for(n_nodes * width / 4, 256), 256, 0, s>>>(
+      reinterpret_cast<const float4*>(msg), rowptr, reinterpret_cast<float4*>(out), n_nodes, width / 4, mean);
+  CSMPN_LAUNCH_CHECK("segment_reduce_sorted");
+  return CSMPN_OK;
+}
+
+int csmpn_segment_expand_sorted(const float* grad_out, const int32_t* dst_sorted, const int32_t* rowptr, float* grad_msg,
+                                int64_t n_pairs, int64_t width, int mean, csmpn_stream_t stream) {
+  if (n_pairs < 0 || width <= 0 || width % 4) return CSMPN_ERR_BAD_ARG;
+  if (n_pairs == 0) return CSMPN_OK;
+  if (!grad_out || !dst_sorted || !rowptr || !grad_msg) return CSMPN_ERR_BAD_ARG;
+  cudaStream_t s = (cudaStream_t)stream;
+  segment_expand_sorted_kernel<<<grid_for(n_pairs * width / 4, 256), 256, 0, s>>>(
+      reinterpret_cast<const float4*>(grad_out), dst_sorted, rowptr, reinterpret_cast<float4*>(grad_msg), n_pairs,
+      width / 4, mean);
+  CSMPN_LAUNCH_CHECK("segment_expand_sorted");
+  return CSMPN_OK;
+}
+
+int csmpn_scatter_diff_sorted(const float* g, int64_t ld, const int32_t* rowptr_dst, const int32_t* rowptr_src,
+                              const int32_t* perm_src, const int32_t* rank, float* grad_h, int64_t n_nodes,
+                              int64_t width, int accumulate, csmpn_stream_t stream) {
+  if (n_nodes < 0 || width <= 0 || width % 4 || ld % 4 || ld < width) return CSMPN_ERR_BAD_ARG;
+  if (n_nodes == 0) return CSMPN_OK;
+  if (!rowptr_dst || !rowptr_src || !grad_h) return CSMPN_ERR_BAD_ARG;
+  cudaStream_t s = (cudaStream_t)stream;
+  scatter_diff_sorted_kernel<<<grid_for(n_nodes * width / 4, 256), 256, 0, s>>>(g, ld, rowptr_dst, rowptr_src, perm_src,
+                                                                                  rank, grad_h, n_nodes, width, accumulate);
+  CSMPN_LAUNCH_CHECK("scatter_diff_sorted");
+  return CSMPN_OK;
+}
+
+int csmpn_scatter_rows(const float* g, int64_t ld, int64_t col0, const int32_t* eid, float* out, int64_t n_rows,
+                       int64_t width, csmpn_stream_t stream) {
+  if (n_rows < 0 || width <= 0 || width % 4 || ld % 4 || col0 % 4) return CSMPN_ERR_BAD_ARG;
+  if (n_rows == 0) return CSMPN_OK;
+  if (!g || !eid || !out) return CSMPN_ERR_BAD_ARG;
+  cudaStream_t s = (cudaStream_t)stream;
+  scatter_rows_kernel<<<grid_for(n_rows * width / 4, 256), 256, 0, s>>>(g, ld, col0, eid, out, n_rows, width);
+  CSMPN_LAUNCH_CHECK("scatter_rows");
+  return CSMPN_OK;
+}
+
+int csmpn_csr_rank(const int32_t* perm, int32_t* rank, int64_t n_pairs, csmpn_stream_t stream) {
+  if (n_pairs < 0) return CSMPN_ERR_BAD_ARG;
+  if (n_pairs == 0) return CSMPN_OK;
+  if (!perm || !rank) return CSMPN_ERR_BAD_ARG;
+  cudaStream_t s = (cudaStream_t)stream;
+  rank_kernel<<<grid_for(n_pairs, 256), 256, 0, s>>>(perm, rank, n_pairs);
+  CSMPN_LAUNCH_CHECK("csr_rank");
   return CSMPN_OK;
 }
 

@@ -1,6 +1,371 @@
-"""Fused CEMLP-block / EGCL path (csrc/block_fused.cu).  Placeholder switch until the kernels land."""
+"""Fused CEMLP-block / EGCL path: Python side of csrc/block_fused.cu (C ABI: csmpn_block_fwd / csmpn_block_bwd).
+
+One autograd node per CEMLP block.  The EGCL layer becomes
+
+    block(gather: h[dst]-h[src] | edge_attr)  ->  block(dense)  ->  CSR segment reduce (contiguous rows)
+    block(concat: h | agg | node_attr)        ->  block(dense, + residual)
+
+with every per-pair tensor kept in receiver-sorted order so the reduce reads contiguous rows and is
+deterministic.  Enabled for Euclidean algebras of dimension 2, 3 and 5 (the reference's models); other
+algebras use the unit kernels.  ``CSMPN_FUSED=0`` forces the unit-kernel composition (used by tests to
+cross-check the two paths).
+"""
+from __future__ import annotations
+
+import ctypes
 import os
+from ctypes import POINTER, c_float, c_int32, c_int64, c_void_p
+
+import torch
+
+from .. import _lib
+from .._lib import check, f32c, lib, ptr, require_cuda, stream_ptr, workspace
+from . import ops
+
+
+class BlockDesc(ctypes.Structure):
+    _fields_ = [
+        ("mode", c_int32), ("c0", c_int32), ("c1", c_int32), ("c2", c_int32), ("c", c_int32), ("has_b1", c_int32),
+        ("rows", c_int64),
+        ("p0", c_void_p), ("p1", c_void_p), ("p2", c_void_p),
+        ("src", c_void_p), ("dst", c_void_p), ("eid", c_void_p),
+        ("w1", c_void_p), ("b1", c_void_p), ("sa", c_void_p), ("sb", c_void_p), ("wr", c_void_p), ("na", c_void_p),
+        ("wl", c_void_p), ("bl", c_void_p), ("wp", c_void_p), ("la", c_void_p),
+        ("y", c_void_p), ("res", c_void_p), ("save_y1", c_void_p), ("save_xr", c_void_p), ("save_o", c_void_p),
+    ]
+
+
+class BlockGrads(ctypes.Structure):
+    _fields_ = [
+        ("grad_y", c_void_p), ("grad_x", c_void_p),
+        ("g_w1", c_void_p), ("g_b1", c_void_p), ("g_sa", c_void_p), ("g_sb", c_void_p), ("g_wr", c_void_p),
+        ("g_na", c_void_p), ("g_wl", c_void_p), ("g_bl", c_void_p), ("g_wp", c_void_p), ("g_la", c_void_p),
+    ]
+
+
+_declared = False
+
+
+def _declare():
+    global _declared
+    if _declared:
+        return
+    l = lib()
+    P, i64, i32 = c_void_p, c_int64, ctypes.c_int
+    l.csmpn_block_fwd.restype = ctypes.c_int
+    l.csmpn_block_fwd.argtypes = [i32, POINTER(BlockDesc), P]
+    l.csmpn_block_bwd_workspace.restype = i64
+    l.csmpn_block_bwd_workspace.argtypes = [i32, POINTER(BlockDesc)]
+    l.csmpn_block_bwd.restype = ctypes.c_int
+    l.csmpn_block_bwd.argtypes = [i32, POINTER(BlockDesc), POINTER(BlockGrads), P, i64, P]
+    l.csmpn_csr_sorted_indices.restype = ctypes.c_int
+    l.csmpn_csr_sorted_indices.argtypes = [P, P, P, P, P, i64, P]
+    l.csmpn_csr_rank.restype = ctypes.c_int
+    l.csmpn_csr_rank.argtypes = [P, P, i64, P]
+    l.csmpn_segment_reduce_sorted.restype = ctypes.c_int
+    l.csmpn_segment_reduce_sorted.argtypes = [P, P, P, i64, i64, i32, P]
+    l.csmpn_segment_expand_sorted.restype = ctypes.c_int
+    l.csmpn_segment_expand_sorted.argtypes = [P, P, P, P, i64, i64, i32, P]
+    l.csmpn_scatter_diff_sorted.restype = ctypes.c_int
+    l.csmpn_scatter_diff_sorted.argtypes = [P, i64, P, P, P, P, P, i64, i64, i32, P]
+    l.csmpn_scatter_rows.restype = ctypes.c_int
+    l.csmpn_scatter_rows.argtypes = [P, i64, i64, P, P, i64, i64, P]
+    for name in ("csmpn_block_fwd", "csmpn_block_bwd_workspace", "csmpn_block_bwd", "csmpn_csr_sorted_indices", "csmpn_csr_rank",
+                 "csmpn_segment_reduce_sorted", "csmpn_segment_expand_sorted", "csmpn_scatter_diff_sorted", "csmpn_scatter_rows"):
+        _lib.EXPORTED[name] = True
+    _declared = True
+
+
+FUSED_DIMS = (2, 3, 5)
+
+
+def available() -> bool:
+    try:
+        _declare()
+        return True
+    except Exception:
+        return False
 
 
 def enabled(algebra) -> bool:
-    return False
+    if os.environ.get("CSMPN_FUSED", "1") == "0":
+        return False
+    return bool(getattr(algebra, "is_euclidean", False)) and algebra.dim in FUSED_DIMS
+
+
+def _block_supported(layer) -> bool:
+    from .cegnn_utils import MVLayerNorm, MVLinear, MVSiLU, NormalizationLayer, SteerableGeometricProductLayer
+
+    if len(layer) != 4:
+        return False
+    lin, act, sgp, ln = layer[0], layer[1], layer[2], layer[3]
+    return (isinstance(lin, MVLinear) and lin.subspaces and isinstance(act, MVSiLU) and act.invariant == "mag2"
+            and isinstance(sgp, SteerableGeometricProductLayer) and sgp.include_first_order
+            and isinstance(sgp.normalization, NormalizationLayer) and isinstance(ln, MVLayerNorm)
+            and lin.out_features <= 128)
+
+
+def _block_params(layer):
+    lin, act, sgp, ln = layer[0], layer[1], layer[2], layer[3]
+    return (lin.weight, lin.bias, act.a, act.b, sgp.linear_right.weight, sgp.normalization.a, sgp.linear_left.weight,
+            sgp.linear_left.bias, sgp.weight, ln.a)
+
+
+class SortedGraph:
+    """Receiver-sorted int32 views of a CSRGraph for the fused kernels (built once per batch)."""
+
+    def __init__(self, g: ops.CSRGraph):
+        _declare()
+        self.csr = g
+        dev = g.edge_index.device
+        E = g.n_pairs
+        self.src_sorted = torch.empty(max(E, 1), dtype=torch.int32, device=dev)
+        self.dst_sorted = torch.empty(max(E, 1), dtype=torch.int32, device=dev)
+        self.rank = torch.empty(max(E, 1), dtype=torch.int32, device=dev)
+        s = stream_ptr(dev)
+        check(lib().csmpn_csr_sorted_indices(ptr(g.src), ptr(g.dst), ptr(g.perm_dst), ptr(self.src_sorted),
+                                             ptr(self.dst_sorted), E, s), "csr_sorted_indices")
+        check(lib().csmpn_csr_rank(ptr(g.perm_dst), ptr(self.rank), E, s), "csr_rank")
+
+
+def sorted_graph(g: ops.CSRGraph) -> SortedGraph:
+    sg = getattr(g, "_sorted", None)
+    if sg is None:
+        sg = SortedGraph(g)
+        g._sorted = sg
+    return sg
+
+
+def _fill_desc(dim, mode, srcs, chans, rows, c, params, sgraph, y, res, saves):
+    w1, b1, sa, sb, wr, na, wl, bl, wp, la = params
+    d = BlockDesc()
+    d.mode, d.c0, d.c1, d.c2, d.c = mode, chans[0], chans[1], chans[2], c
+    d.has_b1 = int(b1 is not None)
+    d.rows = rows
+    d.p0, d.p1, d.p2 = (None if t is None else t.data_ptr() for t in srcs)
+    if mode == 1:
+        d.src, d.dst = sgraph.src_sorted.data_ptr(), sgraph.dst_sorted.data_ptr()
+        d.eid = sgraph.csr.perm_dst.data_ptr()
+    d.w1, d.sa, d.sb, d.wr, d.na = w1.data_ptr(), sa.data_ptr(), sb.data_ptr(), wr.data_ptr(), na.data_ptr()
+    d.b1 = None if b1 is None else b1.data_ptr()
+    d.wl, d.bl, d.wp, d.la = wl.data_ptr(), bl.data_ptr(), wp.data_ptr(), la.data_ptr()
+    d.y = y.data_ptr()
+    d.res = None if res is None else res.data_ptr()
+    if saves is not None:
+        d.save_y1, d.save_xr, d.save_o = (t.data_ptr() for t in saves)
+    return d
+
+
+class FusedBlockFn(torch.autograd.Function):
+    """One CEMLP block.  inputs: p0, p1, p2 (sources), res, then the ten parameters."""
+
+    @staticmethod
+    def forward(ctx, cfg, p0, p1, p2, res, w1, b1, sa, sb, wr, na, wl, bl, wp, la):
+        _declare()
+        dim, mode, sgraph = cfg["dim"], cfg["mode"], cfg.get("sgraph")
+        srcs = [None if t is None else f32c(t) for t in (p0, p1, p2)]
+        require_cuda(*srcs, what="fused block")
+        B = 1 << dim
+        chans = [0 if t is None else t.shape[1] for t in srcs]
+        c = w1.shape[0]
+        if sum(chans) != w1.shape[1]:
+            raise ValueError(f"fused block: input channels {chans} do not match weight {tuple(w1.shape)}")
+        rows = sgraph.csr.n_pairs if mode == 1 else srcs[0].shape[0]
+        params = tuple(None if t is None else f32c(t) for t in (w1, b1, sa, sb, wr, na, wl, bl, wp, la))
+        dev = srcs[0].device
+        y = torch.empty((rows, c, B), dtype=torch.float32, device=dev)
+        need_grad = cfg["need_grad"]
+        saves = tuple(torch.empty((rows, c, B), dtype=torch.float32, device=dev) for _ in range(3)) if need_grad else None
+        resc = None if res is None else f32c(res)
+        d = _fill_desc(dim, mode, srcs, chans, rows, c, params, sgraph, y, resc, saves)
+        check(lib().csmpn_block_fwd(dim, ctypes.byref(d), stream_ptr(dev)), "block_fwd")
+        if need_grad:
+            ctx.save_for_backward(*[t for t in srcs if t is not None], *[t for t in params if t is not None], *saves)
+            ctx.meta = (dim, mode, sgraph, chans, c, rows, [t is not None for t in srcs], [t is not None for t in params],
+                        res is not None, [None if t is None else t.shape for t in (w1, b1, sa, sb, wr, na, wl, bl, wp, la)],
+                        [None if t is None else t.shape for t in (p0, p1, p2)])
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        dim, mode, sgraph, chans, c, rows, src_mask, par_mask, has_res, pshapes, sshapes = ctx.meta
+        saved = list(ctx.saved_tensors)
+        srcs = [saved.pop(0) if m else None for m in src_mask]
+        params = [saved.pop(0) if m else None for m in par_mask]
+        saves = tuple(saved)
+        gy = f32c(gy)
+        dev = gy.device
+        B = 1 << dim
+        cin = sum(chans)
+        y_dummy = gy  # desc.y is not written by the backward
+        d = _fill_desc(dim, mode, srcs, chans, rows, c, params, sgraph, y_dummy, None, saves)
+        gx = torch.empty((rows, cin, B), dtype=torch.float32, device=dev)
+        pg = [None if t is None else torch.empty_like(t) for t in params]
+        g = BlockGrads()
+        g.grad_y, g.grad_x = gy.data_ptr(), gx.data_ptr()
+        names = ("g_w1", "g_b1", "g_sa", "g_sb", "g_wr", "g_na", "g_wl", "g_bl", "g_wp", "g_la")
+        for n, t in zip(names, pg):
+            setattr(g, n, None if t is None else t.data_ptr())
+        nbytes = lib().csmpn_block_bwd_workspace(dim, ctypes.byref(d))
+        if nbytes < 0:
+            raise _lib.CsmpnError("fused block backward: unsupported configuration")
+        ws = workspace(nbytes, dev)
+        check(lib().csmpn_block_bwd(dim, ctypes.byref(d), ctypes.byref(g), ptr(ws), ws.numel(), stream_ptr(dev)), "block_bwd")
+        # split the gradient of the assembled input row back onto the sources
+        gsrc = [None, None, None]
+        if mode == 0:
+            off = 0
+            for k in range(3):
+                if srcs[k] is not None:
+                    gsrc[k] = gx[:, off:off + chans[k]] if (chans[k] != cin) else gx
+                    off += chans[k]
+        else:
+            csr = sgraph.csr
+            n_nodes, width = srcs[0].shape[0], chans[0] * B
+            gh = torch.empty((n_nodes, chans[0], B), dtype=torch.float32, device=dev)
+            check(lib().csmpn_scatter_diff_sorted(ptr(gx), cin * B, ptr(csr.rowptr_dst), ptr(csr.rowptr_src), ptr(csr.perm_src),
+                                                  ptr(sgraph.rank), ptr(gh), n_nodes, width, 0, stream_ptr(dev)),
+                  "scatter_diff_sorted")
+            gsrc[0] = gh
+            if srcs[1] is not None:
+                ge = torch.empty((rows, chans[1], B), dtype=torch.float32, device=dev)
+                check(lib().csmpn_scatter_rows(ptr(gx), cin * B, chans[0] * B, ptr(csr.perm_dst), ptr(ge), rows, chans[1] * B,
+                                               stream_ptr(dev)), "scatter_rows")
+                gsrc[1] = ge
+        gsrc = [None if t is None else t.reshape(s) for t, s in zip(gsrc, sshapes)]
+        gres = gy if has_res else None
+        pgr = [None if t is None else t.reshape(s) for t, s in zip(pg, pshapes)]
+        return (None, gsrc[0], gsrc[1], gsrc[2], gres, *pgr)
+
+
+class SegmentReduceSortedFn(torch.autograd.Function):
+    """[E_sorted, W] -> [N, W]; rows of a receiver are contiguous (deterministic, fixed order)."""
+
+    @staticmethod
+    def forward(ctx, msg, sgraph: SortedGraph, mean: bool):
+        _declare()
+        msg = f32c(msg)
+        csr = sgraph.csr
+        out = torch.empty((csr.n_nodes, msg.shape[1]), dtype=torch.float32, device=msg.device)
+        check(lib().csmpn_segment_reduce_sorted(ptr(msg), ptr(csr.rowptr_dst), ptr(out), csr.n_nodes, msg.shape[1], int(mean),
+                                                stream_ptr(msg.device)), "segment_reduce_sorted")
+        ctx.sgraph, ctx.mean = sgraph, mean
+        return out
+
+    @staticmethod
+    def backward(ctx, go):
+        go = f32c(go)
+        sg = ctx.sgraph
+        gm = torch.empty((sg.csr.n_pairs, go.shape[1]), dtype=torch.float32, device=go.device)
+        check(lib().csmpn_segment_expand_sorted(ptr(go), ptr(sg.dst_sorted), ptr(sg.csr.rowptr_dst), ptr(gm), sg.csr.n_pairs,
+                                                go.shape[1], int(ctx.mean), stream_ptr(go.device)), "segment_expand_sorted")
+        return gm, None, None
+
+
+def _need_grad(*tensors_and_params):
+    return torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors_and_params)
+
+
+def block_forward(algebra, layer, x, p1=None, p2=None, res=None, mode=0, sgraph=None):
+    """Run one CEMLP block (nn.Sequential of the four sub-layers) through the fused kernel."""
+    if not _block_supported(layer) or (x is not None and x.dim() != 3):
+        y = x if p1 is None else torch.cat([t for t in (x, p1, p2) if t is not None], dim=1)
+        y = layer(y)
+        return y if res is None else res + y
+    params = _block_params(layer)
+    cfg = {"dim": algebra.dim, "mode": mode, "sgraph": sgraph, "need_grad": _need_grad(x, p1, p2, res, *params)}
+    return FusedBlockFn.apply(cfg, x, p1, p2, res, *params)
+
+
+def egcl_forward(egcl, h, edge_index, edge_attr=None, node_attr=None):
+    """EGCL.forward (cegnn_utils.py:277-284) on the fused path."""
+    alg = egcl.algebra
+    blocks_e, blocks_n = list(egcl.edge_model.layers), list(egcl.node_model.layers)
+    if not all(_block_supported(b) for b in blocks_e + blocks_n) or h.dim() != 3:
+        hf = alg.flatten(h)
+        return alg.split(egcl.propagate(edge_index, h=hf, edge_attr=edge_attr, node_attr=node_attr))
+    require_cuda(h, what="EGCL")
+    B = alg.n_blades
+    N = h.shape[0]
+    csr = ops.get_csr(edge_index, N)
+    sg = sorted_graph(csr)
+    h = f32c(h)
+    if csr.n_pairs > 0:
+        m = block_forward(alg, blocks_e[0], h, edge_attr, None, None, mode=1, sgraph=sg)
+        for blk in blocks_e[1:]:
+            m = block_forward(alg, blk, m)
+        agg = SegmentReduceSortedFn.apply(m.reshape(csr.n_pairs, -1), sg, egcl.aggr == "mean").reshape(N, -1, B)
+    else:
+        agg = h.new_zeros((N, egcl.out_features, B))
+    u = block_forward(alg, blocks_n[0], h, agg, node_attr)
+    for k, blk in enumerate(blocks_n[1:]):
+        last = k == len(blocks_n) - 2
+        u = block_forward(alg, blk, u, res=h if (last and egcl.residual) else None)
+    if len(blocks_n) == 1 and egcl.residual:
+        u = h + u
+    return u
+
+
+# ------------------------------------------------------------------------------------------------- bench helper
+def bench_dominant_kernel(layer, d, graph, hbm_peak, peak_src, iters=10):
+    """Time the dominant kernel (backward of the first edge block: gather prologue, 3 transposed GEMMs, 3 weight-gradient
+    GEMMs) alone with CUDA events on the launching stream, L2 flushed between launches."""
+    alg = layer.algebra
+    B = alg.n_blades
+    csr = ops.get_csr(graph, d["h"].shape[0])
+    sg = sorted_graph(csr)
+    blk = layer.edge_model.layers[0]
+    params = tuple(None if t is None else f32c(t.detach()) for t in _block_params(blk))
+    h, ea = f32c(d["h"]), f32c(d["edge_attr"])
+    E, C = csr.n_pairs, params[0].shape[0]
+    c0, c1 = h.shape[1], ea.shape[1]
+    dev = h.device
+    y = torch.empty((E, C, B), device=dev)
+    saves = tuple(torch.empty((E, C, B), device=dev) for _ in range(3))
+    desc = _fill_desc(alg.dim, 1, [h, ea, None], [c0, c1, 0], E, C, params, sg, y, None, saves)
+    s = stream_ptr(dev)
+    check(lib().csmpn_block_fwd(alg.dim, ctypes.byref(desc), s), "block_fwd")
+    gy = torch.randn_like(y)
+    gx = torch.empty((E, c0 + c1, B), device=dev)
+    pg = [None if t is None else torch.empty_like(t) for t in params]
+    g = BlockGrads()
+    g.grad_y, g.grad_x = gy.data_ptr(), gx.data_ptr()
+    for n, t in zip(("g_w1", "g_b1", "g_sa", "g_sb", "g_wr", "g_na", "g_wl", "g_bl", "g_wp", "g_la"), pg):
+        setattr(g, n, None if t is None else t.data_ptr())
+    ws = workspace(lib().csmpn_block_bwd_workspace(alg.dim, ctypes.byref(desc)), dev)
+    flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)
+    times = {"fwd": [], "bwd": []}
+    for it in range(iters + 3):
+        for which in ("fwd", "bwd"):
+            flush.fill_(0.0)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            if which == "fwd":
+                check(lib().csmpn_block_fwd(alg.dim, ctypes.byref(desc), s), "block_fwd")
+            else:
+                check(lib().csmpn_block_bwd(alg.dim, ctypes.byref(desc), ctypes.byref(g), ptr(ws), ws.numel(), s), "block_bwd")
+            e1.record()
+            torch.cuda.synchronize()
+            if it >= 3:
+                times[which].append(e0.elapsed_time(e1))
+    t_bwd = sum(times["bwd"]) / len(times["bwd"]) * 1e-3
+    t_fwd = sum(times["fwd"]) / len(times["fwd"]) * 1e-3
+    cin = c0 + c1
+    G = alg.dim + 1
+    # algorithmic bytes of the backward launch: read grad_y, o, y1, xr ([E,C,B] each), gather h twice per pair for the
+    # weight gradient (2 x [E,c0,B]) + edge_attr, write grad_x [E,cin,B]; indices 12 B per pair
+    bytes_bwd = 4 * B * E * (4 * C + 2 * c0 + c1 + cin) + 12 * E
+    bytes_fwd = 4 * B * E * (2 * c0 + c1 + 4 * C) + 12 * E
+    # FLOPs: transposed GEMMs + weight-gradient GEMMs (2 per linear) + products
+    fl_lin = 2 * B * C * (cin + 2 * C)
+    flops_bwd = E * (2 * fl_lin + 6 * B * B * C + 40 * B * C)
+    flops_fwd = E * (fl_lin + 3 * B * B * C + 18 * B * C)
+    return {
+        "bound": "hbm", "achieved": bytes_bwd / t_bwd / 1e9, "peak": hbm_peak, "unit": "GB/s",
+        "frac": bytes_bwd / t_bwd / 1e9 / hbm_peak, "traffic": None, "peak_source": peak_src,
+        "kernel": "block_bwd_kernel<3> (first edge block: gather prologue + 3 transposed GEMMs + 3 weight-gradient GEMMs)",
+        "launch_ms": t_bwd * 1e3, "algorithmic_bytes_per_launch": bytes_bwd, "rows_per_launch": E,
+        "fp32": {"achieved_tflops": flops_bwd / t_bwd / 1e12, "peak_tflops": 74.4, "frac": flops_bwd / t_bwd / 1e12 / 74.4,
+                 "note": "binding roof: FP32 FMA pipe (148 SM x 128 lanes x 2 x 1.965 GHz); ~110 FLOP/B vs ridge 11"},
+        "fwd_kernel": {"launch_ms": t_fwd * 1e3, "hbm_gbs": bytes_fwd / t_fwd / 1e9, "fp32_tflops": flops_fwd / t_fwd / 1e12},
+    }

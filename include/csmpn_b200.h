@@ -149,6 +149,79 @@ int csmpn_scatter_diff(const float* g, const int32_t* rowptr_dst, const int32_t*
 int csmpn_segment_expand(const float* grad_out, const int64_t* dst, const int32_t* rowptr, float* grad_msg,
                          int64_t n_pairs, int64_t width, int mean, csmpn_stream_t stream);
 
+/* ---- fused CEMLP block  (one [MVLinear, MVSiLU, SteerableGeometricProductLayer, MVLayerNorm] block of CEMLP,
+ *      cegnn_utils.py:180-207; with the gather of EGCL.message :254-262 or the concat of EGCL.update :264-275
+ *      folded into its prologue and the residual of :272-273 into its epilogue) --------------------------------
+ * Euclidean metrics, dim in {2,3,5}.  Rows are processed in tiles held in shared memory; the three per-grade
+ * channel GEMMs, the gates, norms and the weighted geometric product of a block never leave the SM.
+ *
+ * Input row r (c_in = c0 + c1 + c2 channels):
+ *   mode 0 (concat):  [ p0[r, 0:c0] | p1[r, 0:c1] | p2[r, 0:c2] ]                (p1 / p2 may be NULL with c = 0)
+ *   mode 1 (gather):  [ p0[dst[r], 0:c0] - p0[src[r], 0:c0] | p1[eid[r], 0:c1] ]  rows = adjacency pairs in
+ *                     receiver-sorted order; src/dst/eid are int32 [rows] (eid = original pair id)
+ * Forward output y[r, 0:c] (+ res[r] when res != NULL).  When save_* are non-NULL the forward also stores the three
+ * [rows, c, B] intermediates the backward needs (pre-SiLU y1, pre-normalisation right input xr, pre-LayerNorm o).  */
+typedef struct csmpn_block_desc {
+  int32_t mode, c0, c1, c2, c;          /* c = block width (hidden/out features) */
+  int32_t has_b1;                       /* MVLinear bias present */
+  int64_t rows;
+  const float *p0, *p1, *p2;
+  const int32_t *src, *dst, *eid;
+  /* parameters, reference state_dict names in brackets (layer prefix "layers.k.") */
+  const float* w1;  /* [c, c_in, G]  0.weight */
+  const float* b1;  /* [c]           0.bias */
+  const float* sa;  /* [c, G]        1.a */
+  const float* sb;  /* [c, G]        1.b */
+  const float* wr;  /* [c, c, G]     2.linear_right.weight */
+  const float* na;  /* [c, G]        2.normalization.a */
+  const float* wl;  /* [c, c, G]     2.linear_left.weight */
+  const float* bl;  /* [c]           2.linear_left.bias */
+  const float* wp;  /* [c, P]        2.weight */
+  const float* la;  /* [c]           3.a */
+  /* forward outputs */
+  float* y;         /* [rows, c, B] */
+  const float* res; /* [rows, c, B] or NULL */
+  float *save_y1, *save_xr, *save_o;    /* [rows, c, B] each, or all NULL (inference) */
+} csmpn_block_desc;
+
+/* gradients produced by csmpn_block_bwd (all overwritten; parameter gradients reduced deterministically) */
+typedef struct csmpn_block_grads {
+  const float* grad_y;   /* [rows, c, B] (the residual branch, if any, is the caller's: grad_res = grad_y) */
+  float* grad_x;         /* [rows, c_in, B] gradient of the assembled input row (mode 1: w.r.t. the difference and the
+                            gathered extra channels, in sorted-row order; scatter with csmpn_scatter_rows) */
+  float *g_w1, *g_b1, *g_sa, *g_sb, *g_wr, *g_na, *g_wl, *g_bl, *g_wp, *g_la;
+} csmpn_block_grads;
+
+int csmpn_block_fwd(int dim, const csmpn_block_desc* desc, csmpn_stream_t stream);
+/* workspace for csmpn_block_bwd (device bytes; zero-initialised by the call itself) */
+int64_t csmpn_block_bwd_workspace(int dim, const csmpn_block_desc* desc);
+int csmpn_block_bwd(int dim, const csmpn_block_desc* desc, const csmpn_block_grads* grads, void* workspace,
+                    int64_t workspace_bytes, csmpn_stream_t stream);
+
+/* Sorted-order helpers for the fused EGCL path.
+ * csr_sorted_indices: src_sorted[p] = (int32) src[perm[p]], dst_sorted[p] = (int32) dst[perm[p]].            */
+int csmpn_csr_sorted_indices(const int64_t* src, const int64_t* dst, const int32_t* perm, int32_t* src_sorted,
+                             int32_t* dst_sorted, int64_t n_pairs, csmpn_stream_t stream);
+/* rank[perm[p]] = p : position of every original pair in the sorted order (inverse permutation) */
+int csmpn_csr_rank(const int32_t* perm, int32_t* rank, int64_t n_pairs, csmpn_stream_t stream);
+/* segment reduce over CONTIGUOUS rows (messages already in receiver-sorted order):
+ *   out[n,:] = sum_{p in [rowptr[n], rowptr[n+1])} msg[p,:]   (/ max(deg,1) when mean)                        */
+int csmpn_segment_reduce_sorted(const float* msg, const int32_t* rowptr, float* out, int64_t n_nodes, int64_t width,
+                                int mean, csmpn_stream_t stream);
+/* its adjoint: grad_msg[p,:] = grad_out[dst_sorted[p],:] * (mean ? 1/max(deg,1) : 1)                           */
+int csmpn_segment_expand_sorted(const float* grad_out, const int32_t* dst_sorted, const int32_t* rowptr,
+                                float* grad_msg, int64_t n_pairs, int64_t width, int mean, csmpn_stream_t stream);
+/* adjoint of the gather prologue, deterministic.  g: [E, ld] rows in receiver-sorted order; the first `width`
+ * floats of each row are the gradient of (h[dst] - h[src]):
+ *   grad_h[n,:] (+)= sum_{p in rowptr_dst[n]..} g[p, 0:width] - sum_{q in rowptr_src[n]..} g[rank[perm_src[q]], 0:width]
+ * rank[e] = position of pair e in receiver-sorted order (inverse of perm_dst).                                 */
+int csmpn_scatter_diff_sorted(const float* g, int64_t ld, const int32_t* rowptr_dst, const int32_t* rowptr_src,
+                              const int32_t* perm_src, const int32_t* rank, float* grad_h, int64_t n_nodes,
+                              int64_t width, int accumulate, csmpn_stream_t stream);
+/* out[eid[p], 0:width] = g[p, col0 : col0 + width]   (un-permute the gathered extra channels' gradient)        */
+int csmpn_scatter_rows(const float* g, int64_t ld, int64_t col0, const int32_t* eid, float* out, int64_t n_rows,
+                       int64_t width, csmpn_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

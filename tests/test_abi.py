@@ -34,6 +34,9 @@ def test_header_symbols_exported(built_lib):
 
 def test_bindings_cover_header(built_lib):
     built_lib.lib()
+    from csmpn_b200.models import fused
+
+    assert fused.available()
     bound = set(built_lib.EXPORTED)
     assert set(header_symbols()) <= bound, sorted(set(header_symbols()) - bound)
 

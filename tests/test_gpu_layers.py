@@ -13,6 +13,13 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda"
 
 
+@pytest.fixture(params=["fused", "unit"])
+def path(request, monkeypatch):
+    """run the CEMLP / EGCL tests through both the fused block kernels and the unit-kernel composition"""
+    monkeypatch.setenv("CSMPN_FUSED", "1" if request.param == "fused" else "0")
+    return request.param
+
+
 def _mods():
     from csmpn_b200.algebra.cliffordalgebra import CliffordAlgebra
     from csmpn_b200.models import cegnn_utils as M
@@ -164,7 +171,7 @@ def test_sgp(fx):
         assert_close(gi, g["grads"][n], GRAD, n)
 
 
-def test_cemlp(fx):
+def test_cemlp(fx, path):
     FWD, GRAD = tols(fx)
     _, M = _mods()
     alg, g = fx["alg"], fx["cemlp"]
@@ -182,7 +189,7 @@ def test_cemlp(fx):
 
 
 @pytest.mark.parametrize("aggr", ["sum", "mean"])
-def test_egcl(fx, aggr):
+def test_egcl(fx, aggr, path):
     FWD, GRAD = tols(fx)
     _, M = _mods()
     alg, g = fx["alg"], fx[f"egcl_{aggr}"]
@@ -221,7 +228,7 @@ def _block_diag_graph(n_cplx, n, e, gen):
 
 
 @pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
-def test_egcl_vs_oracle(case):
+def test_egcl_vs_oracle(case, path):
     name, metric, C, T, ncx, n, e, aggr = case
     CliffordAlgebra, M = _mods()
     gen = torch.Generator().manual_seed(hash(name) % 1000)
@@ -257,7 +264,7 @@ def test_egcl_vs_oracle(case):
         assert_close(a, b, 1e-4, f"{name} {k}")
 
 
-def test_egcl_empty_and_ragged():
+def test_egcl_empty_and_ragged(path):
     """no pairs at all; a receiver with hundreds of pairs; N not a multiple of any tile."""
     CliffordAlgebra, M = _mods()
     gen = torch.Generator().manual_seed(9)
