@@ -2,7 +2,9 @@
 //
 // One block = MVLinear -> MVSiLU -> SteerableGeometricProductLayer -> MVLayerNorm  (cegnn_utils.py:180-207).
 //
-// Execution model (B200): persistent CTAs, one per SM, each looping over tiles of TR rows.
+// Execution model (B200): persistent CTAs, one per SM, each looping over tiles of TR rows.  Every stage reads and
+// writes shared-memory tiles (no register-resident state crosses a stage), which keeps the instruction footprint
+// small enough for the instruction cache and lets the elementwise stages use a thread-per-(row, channel) mapping:
 //  * The three weight matrices of the block stay RESIDENT in shared memory for the life of the CTA (natural
 //    [n][m][g] layout, row stride = 4 mod 32 words, which serves both the forward and the transposed GEMMs
 //    conflict-free).  When they do not fit (wide layers) they are staged per GEMM in K-chunks instead.
@@ -25,9 +27,16 @@ namespace csmpn {
 constexpr float kInvSqrt2 = 0.70710678118654752440f;
 constexpr int kMaxSmem = 220 * 1024;
 
+// fused-kernel GEMM thread tile: RB rows x NCH channels x B blades = 32 accumulators
+template <int DIM> struct FCfg;
+template <> struct FCfg<2> { static constexpr int RB = 2, NCH = 4; };
+template <> struct FCfg<3> { static constexpr int RB = 1, NCH = 4; };
+template <> struct FCfg<5> { static constexpr int RB = 1, NCH = 1; };
+
 struct FusedPlan {
-  int tr, rg, nc, threads, nwarps;
-  int sa, sb;          // row strides (words) of bufA (max(c_in, c) channels) and bufB
+  int tr, rg, nc, threads;
+  int ew_rows;         // rows handled per elementwise pass (= threads / C); thread t owns channel t % C
+  int s1, s2, s3;      // tile row strides (words): s1 = pad(max(C, gathered c0) B), s2 = pad(C B), s3 = pad(max(c_in, C) B)
   int resident;        // weights resident in shared memory
   int sw1, swc;        // resident row strides: pad(c_in*GP), pad(c*GP)
   int off_w1, off_wr, off_wl;  // word offsets of the resident weights inside the weight area
@@ -38,29 +47,34 @@ struct FusedPlan {
   int ks;              // max row splits of the weight-gradient GEMMs
 };
 
+// Shared-memory layout (words):  forward  [A: tr*s3][B: tr*s1][C: tr*s2][weights][nu: tr*c][mu: 2*tr][barriers]
+//                                backward [T1: tr*s1][T2: tr*s2][T3: tr*s3][T4: tr*s2][weights][nu][dt][mu: 2*tr][barriers]
 template <int DIM>
-inline int make_fused_plan(const csmpn_block_desc& d, FusedPlan* out) {
-  using Cfg = GemmCfg<DIM>;
-  constexpr int B = Alg<DIM>::B, GP = Cfg::GP;
+inline int make_fused_plan(const csmpn_block_desc& d, bool backward, FusedPlan* out) {
+  using Cfg = FCfg<DIM>;
+  constexpr int B = Alg<DIM>::B, GP = GemmCfg<DIM>::GP;
   FusedPlan p;
   memset(&p, 0, sizeof(p));
   const int c = d.c, cin = d.c0 + d.c1 + d.c2;
+  if (c > 256) return CSMPN_ERR_UNSUPPORTED;
   p.nc = (c + Cfg::NCH - 1) / Cfg::NCH;
-  if (p.nc > 256) return CSMPN_ERR_UNSUPPORTED;
   const int wide = cin > c ? cin : c;
   const int bwide = (d.mode == 1 && d.c0 > c) ? d.c0 : c;
-  p.sa = pad_stride(wide * B);
-  p.sb = pad_stride(bwide * B);
+  p.s1 = pad_stride(bwide * B);
+  p.s2 = pad_stride(c * B);
+  p.s3 = pad_stride(wide * B);
   p.sw1 = pad_stride(cin * GP);
   p.swc = pad_stride(c * GP);
   const int res_words = c * p.sw1 + 2 * c * p.swc;
-  auto tile_words = [&](int tr) { return (size_t)tr * (p.sa + p.sb) + 2 * (size_t)tr * p.nc + 16; };
-  // largest tile (<= 256 threads) that fits next to the resident weights
+  auto tile_words = [&](int tr) {
+    size_t t = backward ? (size_t)tr * (p.s1 + 2 * p.s2 + p.s3) : (size_t)tr * (p.s1 + p.s2 + p.s3);
+    return t + 2 * (size_t)tr * c + 2 * tr + 16;
+  };
+  auto threads_for = [&](int tr) { return (((tr / Cfg::RB) * p.nc + 31) / 32) * 32; };
+  static const int cand[] = {64, 48, 32, 24, 16, 12, 8, 6, 4, 2, 1};
   int best = 0;
-  for (int tr = 64; tr >= Cfg::RB; tr >>= 1) {
-    if (tr % Cfg::RB) continue;
-    const int rg = tr / Cfg::RB;
-    if (((rg * p.nc + 31) / 32) * 32 > 256) continue;
+  for (int tr : cand) {
+    if (tr % Cfg::RB || threads_for(tr) > 256) continue;
     if ((tile_words(tr) + res_words) * 4 <= (size_t)kMaxSmem) { best = tr; break; }
   }
   if (best) {
@@ -71,14 +85,14 @@ inline int make_fused_plan(const csmpn_block_desc& d, FusedPlan* out) {
     p.off_wl = p.off_wr + c * p.swc;
     p.wbuf = res_words;
   } else {
-    // staged weights: 22 KB staging area, ~128-thread tiles
     p.resident = 0;
-    const int wb_words = 5632;
-    int rg = 128 / p.nc;
-    if (rg < 1) rg = 1;
-    int max_rg = (DIM <= 3 ? 32 : 8) / Cfg::RB;
-    if (rg > max_rg) rg = max_rg;
-    p.tr = rg * Cfg::RB;
+    const int wb_words = 5632;  // 22 KB staging area
+    for (int tr : cand) {
+      if (tr % Cfg::RB || threads_for(tr) > 256) continue;
+      if ((tile_words(tr) + wb_words) * 4 <= (size_t)kMaxSmem) { best = tr; break; }
+    }
+    if (!best) return CSMPN_ERR_UNSUPPORTED;
+    p.tr = best;
     auto fit_fwd = [&](int odim, int kdim) {
       int kc = (wb_words / odim - 4) / GP;
       if (kc > kdim) kc = kdim;
@@ -98,13 +112,15 @@ inline int make_fused_plan(const csmpn_block_desc& d, FusedPlan* out) {
     p.wbuf = w1 > w2 ? w1 : w2;
     if (w3 > p.wbuf) p.wbuf = w3;
     if (w4 > p.wbuf) p.wbuf = w4;
+    if ((tile_words(p.tr) + p.wbuf) * 4 > (size_t)kMaxSmem) return CSMPN_ERR_UNSUPPORTED;
   }
   p.rg = p.tr / Cfg::RB;
-  p.threads = ((p.rg * p.nc + 31) / 32) * 32;
+  p.threads = threads_for(p.tr);
+  if (p.threads < c) p.threads = ((c + 31) / 32) * 32;  // the elementwise stages need one thread per channel
   if (p.threads > 256) return CSMPN_ERR_UNSUPPORTED;
-  p.nwarps = p.threads / 32;
+  p.ew_rows = p.threads / c;
+  if (p.ew_rows > p.tr) p.ew_rows = p.tr;
   p.smem = (tile_words(p.tr) + p.wbuf) * sizeof(float);
-  if (p.smem > (size_t)kMaxSmem) return CSMPN_ERR_UNSUPPORTED;
   int64_t tiles = (d.rows + p.tr - 1) / p.tr;
   int per_sm = (int)((size_t)(226 * 1024) / (p.smem + 1024));
   if (per_sm < 1) per_sm = 1;
@@ -112,7 +128,6 @@ inline int make_fused_plan(const csmpn_block_desc& d, FusedPlan* out) {
   if (per_sm * p.threads > 512) per_sm = 512 / p.threads > 0 ? 512 / p.threads : 1;
   int64_t cap = (int64_t)sm_count_cached() * per_sm;
   p.grid = (int)(tiles < cap ? (tiles > 0 ? tiles : 1) : cap);
-  // weight-gradient GEMMs: thread tiles of NA x 4 channels; rows of a tile split ks ways
   const int NA = Alg<DIM>::G <= 4 ? 4 : 2;
   int tc = ((c + NA - 1) / NA) * ((c + 3) / 4);
   p.ks = p.threads / tc > 0 ? p.threads / tc : 1;
@@ -188,57 +203,84 @@ __device__ __forceinline__ float mv_sumsq(const float* x) {
 }
 
 // ---------------------------------------------------------------------------------------------------
-// Tile input: TMA row copies (issued by warp 0) + one shared-memory pass.
-//   mode 0:  bufA[r] = [ p0[row] | p1[row] | p2[row] ]
-//   mode 1:  bufA[r] = [ p0[dst[row]] - p0[src[row]] | p1[eid[row]] ]     (sender rows pass through bufB)
-// Caller guarantees every thread has executed fence_proxy_async() + __syncthreads() since the last generic access to
-// bufA / bufB.  On return bufA is complete for the calling thread's own writes; a barrier must follow before other
-// threads read it.
+// TMA row loaders (executed by warp 0; every lane issues the copies of the rows r = lane, lane + 32, ... and then
+// arrives on the mbarrier with the byte count it issued; the barrier is initialised with 32 arrivals).
+
+// dense rows [row0 + r] of a [rows, ch, B] tensor into tile columns [col, col + ch*B)
 template <int DIM>
-__device__ __forceinline__ void load_input_tile(float* __restrict__ bufA, int sa, float* __restrict__ bufB, int sb,
-                                                const csmpn_block_desc& d, int64_t row0, int tr, uint64_t* bar,
-                                                uint32_t parity) {
+__device__ __forceinline__ uint32_t tma_dense_rows(float* tile, int stride, int col, const float* src, int ch, int64_t row0,
+                                                   int valid, uint64_t* bar) {
   constexpr int B = Alg<DIM>::B;
-  const uint32_t b0 = d.c0 * B * 4, b1 = d.c1 * B * 4, b2 = d.c2 * B * 4;
-  if (threadIdx.x < 32) {
-    uint32_t bytes = 0;
-    for (int r = threadIdx.x; r < tr; r += 32)
-      if (row0 + r < d.rows) bytes += (d.mode == 1 ? 2 * b0 : b0) + b1 + b2;
-    mbar_arrive_expect_tx(bar, bytes);
-    for (int r = threadIdx.x; r < tr; r += 32) {
-      const int64_t gr = row0 + r;
-      if (gr >= d.rows) continue;
-      float* ra = bufA + r * sa;
-      if (d.mode == 0) {
-        tma_row_g2s(ra, d.p0 + gr * (int64_t)d.c0 * B, b0, bar);
-        if (b1) tma_row_g2s(ra + d.c0 * B, d.p1 + gr * (int64_t)d.c1 * B, b1, bar);
-        if (b2) tma_row_g2s(ra + (d.c0 + d.c1) * B, d.p2 + gr * (int64_t)d.c2 * B, b2, bar);
-      } else {
-        const int64_t ri = __ldg(d.dst + gr), rj = __ldg(d.src + gr);
-        tma_row_g2s(ra, d.p0 + ri * (int64_t)d.c0 * B, b0, bar);
-        tma_row_g2s(bufB + r * sb, d.p0 + rj * (int64_t)d.c0 * B, b0, bar);
-        if (b1) tma_row_g2s(ra + d.c0 * B, d.p1 + (int64_t)__ldg(d.eid + gr) * d.c1 * B, b1, bar);
-      }
-    }
+  const uint32_t rb = (uint32_t)ch * B * 4;
+  uint32_t bytes = 0;
+  for (int r = threadIdx.x; r < valid; r += 32) {
+    tma_row_g2s(tile + r * stride + col, src + (row0 + r) * (int64_t)ch * B, rb, bar);
+    bytes += rb;
   }
-  mbar_wait(bar, parity);
-  const int valid = (d.rows - row0) < tr ? (int)(d.rows - row0) : tr;
+  return bytes;
+}
+
+// rows idx[row0 + r] of a [*, ch, B] tensor
+template <int DIM>
+__device__ __forceinline__ uint32_t tma_indexed_rows(float* tile, int stride, int col, const float* src, int ch,
+                                                     const int32_t* __restrict__ idx, int64_t row0, int valid, uint64_t* bar) {
+  constexpr int B = Alg<DIM>::B;
+  const uint32_t rb = (uint32_t)ch * B * 4;
+  uint32_t bytes = 0;
+  for (int r = threadIdx.x; r < valid; r += 32) {
+    tma_row_g2s(tile + r * stride + col, src + (int64_t)__ldg(idx + row0 + r) * ch * B, rb, bar);
+    bytes += rb;
+  }
+  return bytes;
+}
+
+// the assembled input row of the block into `tile` (stride s3); sender rows of the gather mode go to `tmp` (stride s1)
+template <int DIM>
+__device__ __forceinline__ uint32_t tma_input_rows(float* tile, int s3, float* tmp, int s1, const csmpn_block_desc& d,
+                                                   int64_t row0, int valid, uint64_t* bar) {
+  constexpr int B = Alg<DIM>::B;
+  uint32_t bytes = 0;
+  if (d.mode == 0) {
+    bytes += tma_dense_rows<DIM>(tile, s3, 0, d.p0, d.c0, row0, valid, bar);
+    if (d.c1) bytes += tma_dense_rows<DIM>(tile, s3, d.c0 * B, d.p1, d.c1, row0, valid, bar);
+    if (d.c2) bytes += tma_dense_rows<DIM>(tile, s3, (d.c0 + d.c1) * B, d.p2, d.c2, row0, valid, bar);
+  } else {
+    bytes += tma_indexed_rows<DIM>(tile, s3, 0, d.p0, d.c0, d.dst, row0, valid, bar);
+    bytes += tma_indexed_rows<DIM>(tmp, s1, 0, d.p0, d.c0, d.src, row0, valid, bar);
+    if (d.c1) bytes += tma_indexed_rows<DIM>(tile, s3, d.c0 * B, d.p1, d.c1, d.eid, row0, valid, bar);
+  }
+  return bytes;
+}
+
+// after the wait: gather mode forms h[dst] - h[src]; missing rows of a tail tile are zeroed
+template <int DIM>
+__device__ __forceinline__ void finish_input_rows(float* tile, int s3, const float* tmp, int s1, const csmpn_block_desc& d,
+                                                  int tr, int valid) {
+  constexpr int B = Alg<DIM>::B;
   if (d.mode == 1) {
     const int v0 = d.c0 * B / 4;
     for (int idx = threadIdx.x; idx < valid * v0; idx += blockDim.x) {
       const int r = idx / v0, v = idx - r * v0;
-      float4 a = *reinterpret_cast<const float4*>(bufA + r * sa + 4 * v);
-      const float4 b = *reinterpret_cast<const float4*>(bufB + r * sb + 4 * v);
+      float4 a = *reinterpret_cast<const float4*>(tile + r * s3 + 4 * v);
+      const float4 b = *reinterpret_cast<const float4*>(tmp + r * s1 + 4 * v);
       a.x -= b.x; a.y -= b.y; a.z -= b.z; a.w -= b.w;
-      *reinterpret_cast<float4*>(bufA + r * sa + 4 * v) = a;
+      *reinterpret_cast<float4*>(tile + r * s3 + 4 * v) = a;
     }
   }
-  if (valid < tr) {  // tail tile: zero the missing rows
+  if (valid < tr) {
     const int vpr = (d.c0 + d.c1 + d.c2) * B / 4;
     for (int idx = threadIdx.x; idx < (tr - valid) * vpr; idx += blockDim.x) {
       const int r = valid + idx / vpr, v = idx % vpr;
-      *reinterpret_cast<float4*>(bufA + r * sa + 4 * v) = make_float4(0.f, 0.f, 0.f, 0.f);
+      *reinterpret_cast<float4*>(tile + r * s3 + 4 * v) = make_float4(0.f, 0.f, 0.f, 0.f);
     }
+  }
+}
+
+__device__ __forceinline__ void zero_tail_rows(float* tile, int stride, int words, int tr, int valid) {
+  const int vpr = words / 4;
+  for (int idx = threadIdx.x; idx < (tr - valid) * vpr; idx += blockDim.x) {
+    const int r = valid + idx / vpr, v = idx % vpr;
+    *reinterpret_cast<float4*>(tile + r * stride + 4 * v) = make_float4(0.f, 0.f, 0.f, 0.f);
   }
 }
 
@@ -255,15 +297,14 @@ struct WRef {
 // acc += buf[:, 0:kdim] * W   for output channels  obase + c + a * nco  (a < NCHT), masked by owidth.
 // The leading barrier publishes the shared-memory writes of the previous stage.
 template <int DIM, bool TRANS, int NCHT>
-__device__ __forceinline__ void gemm_run(float (&acc)[GemmCfg<DIM>::RB][NCHT][Alg<DIM>::B],
+__device__ __forceinline__ void gemm_run(float (&acc)[FCfg<DIM>::RB][NCHT][Alg<DIM>::B],
                                          const float* __restrict__ buf_rows, int stride, const WRef& w, bool active, int c,
-                                         int nco, int obase, int owidth) {
-  using Cfg = GemmCfg<DIM>;
-  constexpr int B = Alg<DIM>::B, GP = Cfg::GP;
+                                         int nco, int obase, int owidth, bool lead_sync = true) {
+  constexpr int B = Alg<DIM>::B, GP = GemmCfg<DIM>::GP, RB = FCfg<DIM>::RB;
   const int kdim = TRANS ? w.c_out : w.c_in;
   const int odim = TRANS ? w.c_in : w.c_out;
   if (w.resident) {
-    __syncthreads();
+    if (lead_sync) __syncthreads();
     if (active) {
       const float* wp[NCHT];
 #pragma unroll
@@ -272,7 +313,7 @@ __device__ __forceinline__ void gemm_run(float (&acc)[GemmCfg<DIM>::RB][NCHT][Al
         int o = obase + (ol < owidth ? ol : 0);
         wp[a] = TRANS ? w.s + o * GP : w.s + o * w.sw;
       }
-      gemm_accumulate<DIM, NCHT>(acc, buf_rows, stride, wp, TRANS ? w.sw : GP, kdim);
+      gemm_accumulate<DIM, NCHT, RB>(acc, buf_rows, stride, wp, TRANS ? w.sw : GP, kdim);
     }
     return;
   }
@@ -290,7 +331,7 @@ __device__ __forceinline__ void gemm_run(float (&acc)[GemmCfg<DIM>::RB][NCHT][Al
         int o = obase + (ol < owidth ? ol : 0);
         wp[a] = TRANS ? w.s + o * GP : w.s + o * sw;
       }
-      gemm_accumulate<DIM, NCHT>(acc, buf_rows + k0 * B, stride, wp, TRANS ? sw : GP, kc);
+      gemm_accumulate<DIM, NCHT, RB>(acc, buf_rows + k0 * B, stride, wp, TRANS ? sw : GP, kc);
     }
   }
 }
@@ -309,156 +350,164 @@ __device__ __forceinline__ void setup_weights(const csmpn_block_desc& d, const F
   }
 }
 
+// dst[r][o] (+)= sum_k src[r][k] W(k, o) for all C output channels of the block; shared-memory to shared-memory.
+template <int DIM, bool TRANS, bool ACCUM>
+__device__ __forceinline__ void gemm_tile(float* __restrict__ dst, int dstride, const float* __restrict__ src, int sstride,
+                                          const WRef& w, const FusedPlan& p, int C, bool active, int c, int rg,
+                                          bool lead_sync = true) {
+  constexpr int B = Alg<DIM>::B, RB = FCfg<DIM>::RB, NCH = FCfg<DIM>::NCH;
+  float acc[RB][NCH][B];
+#pragma unroll
+  for (int j = 0; j < RB; ++j)
+#pragma unroll
+    for (int a = 0; a < NCH; ++a)
+#pragma unroll
+      for (int i = 0; i < B; ++i) acc[j][a][i] = 0.f;
+  gemm_run<DIM, TRANS, NCH>(acc, src + rg * RB * sstride, sstride, w, active, c, p.nc, 0, C, lead_sync);
+  if (active) {
+#pragma unroll
+    for (int a = 0; a < NCH; ++a) {
+      const int o = c + a * p.nc;
+      if (o >= C) continue;
+#pragma unroll
+      for (int j = 0; j < RB; ++j) {
+        float* q = dst + (rg * RB + j) * dstride + o * B;
+        if (ACCUM) {
+          float old[B];
+          load_vec<B>(old, q);
+#pragma unroll
+          for (int i = 0; i < B; ++i) acc[j][a][i] += old[i];
+        }
+        store_vec<B>(q, acc[j][a]);
+      }
+    }
+  }
+}
+
+// per-thread parameters of the channel a thread owns in the elementwise stages
+template <int DIM>
+struct ChanParams {
+  float sa[Alg<DIM>::G], sb[Alg<DIM>::G], sn[Alg<DIM>::G], wv[Alg<DIM>::P], b1, bl, la;
+  __device__ __forceinline__ void load(const csmpn_block_desc& d, int n, bool ok) {
+    constexpr int G = Alg<DIM>::G, P = Alg<DIM>::P;
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      sa[g] = ok ? d.sa[n * G + g] : 0.f;
+      sb[g] = ok ? d.sb[n * G + g] : 0.f;
+      sn[g] = ok ? sigmoidf_(d.na[n * G + g]) : 0.f;
+    }
+#pragma unroll
+    for (int q = 0; q < P; ++q) wv[q] = ok ? d.wp[n * P + q] : 0.f;
+    b1 = (ok && d.has_b1) ? d.b1[n] : 0.f;
+    bl = ok ? d.bl[n] : 0.f;
+    la = ok ? d.la[n] : 0.f;
+  }
+};
+
 // ===================================================================================================
 // forward
 template <int DIM>
 __global__ void __launch_bounds__(256, 1) block_fwd_kernel(csmpn_block_desc d, FusedPlan p) {
   using A = Alg<DIM>;
-  using Cfg = GemmCfg<DIM>;
-  constexpr int B = A::B, G = A::G, P = A::P, RB = Cfg::RB, NCH = Cfg::NCH;
+  constexpr int B = A::B, G = A::G;
   extern __shared__ __align__(128) float smem[];
-  float* bufA = smem;
-  float* bufB = bufA + p.tr * p.sa;
-  float* wsm = bufB + p.tr * p.sb;
-  float* part = wsm + p.wbuf;  // [tr][nc] layer-norm partials
-  uint64_t* bar = reinterpret_cast<uint64_t*>(part + 2 * p.tr * p.nc);
+  float* tA = smem;                       // input row (wide) -> xr
+  float* tB = tA + p.tr * p.s3;           // sender rows (gather) -> y1 -> y2
+  float* tC = tB + p.tr * p.s1;           // xl -> o
+  float* wsm = tC + p.tr * p.s2;
+  float* nu_s = wsm + p.wbuf;             // [tr][C]
+  float* mu_s = nu_s + 2 * p.tr * d.c;    // [tr]
+  uint64_t* bar = reinterpret_cast<uint64_t*>(mu_s + 2 * p.tr);
   const int C = d.c;
   const int c = threadIdx.x % p.nc, rg = threadIdx.x / p.nc;
   const bool active = rg < p.rg;
-  int och[NCH];
-  bool ov[NCH];
-#pragma unroll
-  for (int a = 0; a < NCH; ++a) { och[a] = c + a * p.nc; ov[a] = active && och[a] < C; if (!ov[a]) och[a] = 0; }
+  const int n_e = threadIdx.x % C, rl = threadIdx.x / C;  // elementwise mapping: channel n_e, rows rl, rl + ew_rows, ...
+  const bool ew = rl < p.ew_rows;
   const int64_t tiles = (d.rows + p.tr - 1) / p.tr;
   WRef w1, wr, wl;
   setup_weights<DIM>(d, p, wsm, w1, wr, wl);
   if (!p.resident) { w1.kchunk = p.kc1; wr.kchunk = p.kcc; wl.kchunk = p.kcc; }
   if (threadIdx.x == 0) mbar_init(bar, 32);
+  ChanParams<DIM> cp;
+  cp.load(d, n_e, ew);
   uint32_t phase = 0;
 
   for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
     const int64_t row0 = tile * p.tr;
-    const int lr0 = rg * RB;  // first local row of this thread
+    const int valid = (d.rows - row0) < p.tr ? (int)(d.rows - row0) : p.tr;
     fence_proxy_async();
-    __syncthreads();  // previous tile's generic accesses to bufA / bufB / part are done (and the barrier is initialised)
-    load_input_tile<DIM>(bufA, p.sa, bufB, p.sb, d, row0, p.tr, bar, phase);
+    __syncthreads();  // previous tile's generic accesses are done; barrier initialised
+    if (threadIdx.x < 32) {
+      uint32_t bytes = tma_input_rows<DIM>(tA, p.s3, tB, p.s1, d, row0, valid, bar);
+      mbar_arrive_expect_tx(bar, bytes);
+    }
+    mbar_wait(bar, phase);
     phase ^= 1;
-
-    float acc[RB][NCH][B];
-    // ---- GEMM1 + bias + MVSiLU  -> y2 in bufB
+    finish_input_rows<DIM>(tA, p.s3, tB, p.s1, d, p.tr, valid);
+    // ---- GEMM1: y1 (without bias) -> tB
+    gemm_tile<DIM, false, false>(tB, p.s1, tA, p.s3, w1, p, C, active, c, rg);
+    __syncthreads();
+    // ---- bias + MVSiLU (in place): tB = y2
+    if (ew) {
+      for (int r = rl; r < p.tr; r += p.ew_rows) {
+        float y1[B], sg[G], inv[G];
+        float* q = tB + r * p.s1 + n_e * B;
+        load_vec<B>(y1, q);
+        y1[0] += cp.b1;
+        if (d.save_y1 && r < valid) store_vec<B>(d.save_y1 + ((row0 + r) * C + n_e) * B, y1);
+        silu_gates<DIM>(y1, cp.sa, cp.sb, sg, inv);
 #pragma unroll
-    for (int j = 0; j < RB; ++j)
-#pragma unroll
-      for (int a = 0; a < NCH; ++a)
-#pragma unroll
-        for (int i = 0; i < B; ++i) acc[j][a][i] = 0.f;
-    gemm_run<DIM, false, NCH>(acc, bufA + lr0 * p.sa, p.sa, w1, active, c, p.nc, 0, C);
-#pragma unroll
-    for (int a = 0; a < NCH; ++a) {
-      if (!ov[a]) continue;
-      const int n = och[a];
-      float sa_[G], sb_[G];
-#pragma unroll
-      for (int g = 0; g < G; ++g) { sa_[g] = d.sa[n * G + g]; sb_[g] = d.sb[n * G + g]; }
-      const float b1 = d.has_b1 ? d.b1[n] : 0.f;
-#pragma unroll
-      for (int j = 0; j < RB; ++j) {
-        acc[j][a][0] += b1;
-        const int64_t r = row0 + lr0 + j;
-        if (d.save_y1 && r < d.rows) store_vec<B>(d.save_y1 + (r * C + n) * B, acc[j][a]);
-        float sg[G], inv[G];
-        silu_gates<DIM>(acc[j][a], sa_, sb_, sg, inv);
-        float y2[B];
-#pragma unroll
-        for (int i = 0; i < B; ++i) y2[i] = acc[j][a][i] * sg[A::grade_of(i)];
-        store_vec<B>(bufB + (lr0 + j) * p.sb + n * B, y2);
+        for (int i = 0; i < B; ++i) y1[i] *= sg[A::grade_of(i)];
+        store_vec<B>(q, y1);
       }
     }
-    // ---- GEMM-R -> xr (own slot of bufA)
-#pragma unroll
-    for (int j = 0; j < RB; ++j)
-#pragma unroll
-      for (int a = 0; a < NCH; ++a)
-#pragma unroll
-        for (int i = 0; i < B; ++i) acc[j][a][i] = 0.f;
-    gemm_run<DIM, false, NCH>(acc, bufB + lr0 * p.sb, p.sb, wr, active, c, p.nc, 0, C);
-#pragma unroll
-    for (int a = 0; a < NCH; ++a) {
-      if (!ov[a]) continue;
-#pragma unroll
-      for (int j = 0; j < RB; ++j) {
-        const int64_t r = row0 + lr0 + j;
-        if (d.save_xr && r < d.rows) store_vec<B>(d.save_xr + (r * C + och[a]) * B, acc[j][a]);
-        store_vec<B>(bufA + (lr0 + j) * p.sa + och[a] * B, acc[j][a]);
-      }
-    }
-    // ---- GEMM-L + bias, normalisation of xr, weighted geometric product, 1/sqrt2  -> o (registers)
-#pragma unroll
-    for (int j = 0; j < RB; ++j)
-#pragma unroll
-      for (int a = 0; a < NCH; ++a)
-#pragma unroll
-        for (int i = 0; i < B; ++i) acc[j][a][i] = 0.f;
-    gemm_run<DIM, false, NCH>(acc, bufB + lr0 * p.sb, p.sb, wl, active, c, p.nc, 0, C);
-    float nu_sum[RB];
-#pragma unroll
-    for (int j = 0; j < RB; ++j) nu_sum[j] = 0.f;
-#pragma unroll
-    for (int a = 0; a < NCH; ++a) {
-      if (!ov[a]) continue;
-      const int n = och[a];
-      float s[G], wv[P];
-#pragma unroll
-      for (int g = 0; g < G; ++g) s[g] = sigmoidf_(d.na[n * G + g]);
-#pragma unroll
-      for (int q = 0; q < P; ++q) wv[q] = d.wp[n * P + q];
-      const float bl = d.bl[n];
-#pragma unroll
-      for (int j = 0; j < RB; ++j) {
-        float xr[B], y2[B], q[G], nrm[G], rinv[G];
-        load_vec<B>(xr, bufA + (lr0 + j) * p.sa + n * B);
-        load_vec<B>(y2, bufB + (lr0 + j) * p.sb + n * B);
-        norm_factors<DIM>(xr, s, q, nrm, rinv);
+    // ---- GEMM-R: xr -> tA ; GEMM-L: xl -> tC   (the leading barrier of the first publishes y2)
+    gemm_tile<DIM, false, false>(tA, p.s3, tB, p.s1, wr, p, C, active, c, rg);
+    gemm_tile<DIM, false, false>(tC, p.s2, tB, p.s1, wl, p, C, active, c, rg, !p.resident);
+    __syncthreads();
+    // ---- normalisation, weighted geometric product, 1/sqrt2: tC = o ; norms for the layer norm
+    if (ew) {
+      for (int r = rl; r < p.tr; r += p.ew_rows) {
+        float xr[B], y2[B], o[B], q[G], nrm[G], rinv[G];
+        load_vec<B>(xr, tA + r * p.s3 + n_e * B);
+        load_vec<B>(y2, tB + r * p.s1 + n_e * B);
+        load_vec<B>(o, tC + r * p.s2 + n_e * B);
+        if (d.save_xr && r < valid) store_vec<B>(d.save_xr + ((row0 + r) * C + n_e) * B, xr);
+        norm_factors<DIM>(xr, cp.sn, q, nrm, rinv);
 #pragma unroll
         for (int i = 0; i < B; ++i) xr[i] *= rinv[A::grade_of(i)];
-        acc[j][a][0] += bl;
-        A::template wgp<false>(y2, xr, wv, nullptr, acc[j][a]);
+        o[0] += cp.bl;
+        A::template wgp<false>(y2, xr, cp.wv, nullptr, o);
 #pragma unroll
-        for (int i = 0; i < B; ++i) acc[j][a][i] *= kInvSqrt2;
-        const int64_t r = row0 + lr0 + j;
-        if (d.save_o && r < d.rows) store_vec<B>(d.save_o + (r * C + n) * B, acc[j][a]);
-        nu_sum[j] += smooth_abs_sqrt(mv_sumsq<DIM>(acc[j][a]));
+        for (int i = 0; i < B; ++i) o[i] *= kInvSqrt2;
+        if (d.save_o && r < valid) store_vec<B>(d.save_o + ((row0 + r) * C + n_e) * B, o);
+        store_vec<B>(tC + r * p.s2 + n_e * B, o);
+        nu_s[r * C + n_e] = smooth_abs_sqrt(mv_sumsq<DIM>(o));
       }
     }
-    // ---- MVLayerNorm: mean over channels of the norms (fixed-order sum of the per-thread partials)
-    if (active) {
-#pragma unroll
-      for (int j = 0; j < RB; ++j) part[(lr0 + j) * p.nc + c] = nu_sum[j];
+    __syncthreads();
+    if (threadIdx.x < p.tr) {  // fixed-order channel sum per row
+      float s = 0.f;
+      for (int n = 0; n < C; ++n) s += nu_s[threadIdx.x * C + n];
+      mu_s[threadIdx.x] = 1.f / (s / (float)C + kEps);
     }
     __syncthreads();
-    if (active) {
+    // ---- MVLayerNorm scale (+ residual) -> global
+    if (ew) {
+      for (int r = rl; r < valid; r += p.ew_rows) {
+        float o[B];
+        load_vec<B>(o, tC + r * p.s2 + n_e * B);
+        const float sc = cp.la * mu_s[r];
 #pragma unroll
-      for (int j = 0; j < RB; ++j) {
-        float sum = 0.f;
-        for (int cc = 0; cc < p.nc; ++cc) sum += part[(lr0 + j) * p.nc + cc];
-        const float inv_mu = 1.f / (sum / (float)C + kEps);
-        const int64_t r = row0 + lr0 + j;
-        if (r >= d.rows) continue;
+        for (int i = 0; i < B; ++i) o[i] *= sc;
+        const int64_t off = ((row0 + r) * C + n_e) * B;
+        if (d.res) {
+          float rv[B];
+          load_vec<B>(rv, d.res + off);
 #pragma unroll
-        for (int a = 0; a < NCH; ++a) {
-          if (!ov[a]) continue;
-          const float sc = d.la[och[a]] * inv_mu;
-          float y[B];
-#pragma unroll
-          for (int i = 0; i < B; ++i) y[i] = acc[j][a][i] * sc;
-          if (d.res) {
-            float rv[B];
-            load_vec<B>(rv, d.res + (r * C + och[a]) * B);
-#pragma unroll
-            for (int i = 0; i < B; ++i) y[i] += rv[i];
-          }
-          store_vec<B>(d.y + (r * C + och[a]) * B, y);
+          for (int i = 0; i < B; ++i) o[i] += rv[i];
         }
+        store_vec<B>(d.y + off, o);
       }
     }
   }
@@ -466,35 +515,6 @@ __global__ void __launch_bounds__(256, 1) block_fwd_kernel(csmpn_block_desc d, F
 
 // ===================================================================================================
 // backward helpers
-
-// Fixed-order reduction over the lanes of a warp that own the same channel group, then accumulation into this
-// warp's private global accumulators.  vals[a][q]: contribution of this thread to parameter q of channel och[a].
-// Threads are numbered t = rg * nc + c, so the lanes sharing c inside a warp are lane, lane + nc, lane + 2 nc, ...
-template <int NCH, int Q>
-__device__ __forceinline__ void warp_reduce_store(float (&vals)[NCH][Q], float* __restrict__ dest, const int (&och)[NCH],
-                                                  const bool (&ov)[NCH], int nc) {
-  const int lane = threadIdx.x & 31;
-#pragma unroll
-  for (int a = 0; a < NCH; ++a)
-#pragma unroll
-    for (int q = 0; q < Q; ++q) {
-      const float v = vals[a][q];
-      float s = v;
-      for (int off = nc; off < 32; off += nc) {
-        const float t = __shfl_down_sync(0xffffffffu, v, off);
-        if (lane + off < 32) s += t;
-      }
-      vals[a][q] = s;
-    }
-  if (lane < nc) {  // chain heads: the first lane of the warp holding each channel group
-#pragma unroll
-    for (int a = 0; a < NCH; ++a) {
-      if (!ov[a]) continue;
-#pragma unroll
-      for (int q = 0; q < Q; ++q) dest[och[a] * Q + q] += vals[a][q];
-    }
-  }
-}
 
 // Tile-local weight-gradient GEMM over one column block of the m operand:
 //   gacc[split][n][m_off + m][g] += sum_{r in split} sum_{i in g} nbuf[r][n][i] * mbuf[r][m][i],  m < cm_block
@@ -568,15 +588,15 @@ struct BwdWorkspace {
   float* dw1;    // [grid][ks][c][cin][G]
   float* dwr;    // [grid][ks][c][c][G]
   float* dwl;    // [grid][ks][c][c][G]
-  float* small;  // [grid][nwarps][c * (P + 3G + 3)]:  dw[c][P] | dna[c][G] | dsa[c][G] | dsb[c][G] | dla[c] | db1[c] | dbl[c]
+  float* small;  // [grid][c * (P + 3G + 3)]:  dw[c][P] | dna[c][G] | dsa[c][G] | dsb[c][G] | dla[c] | db1[c] | dbl[c]
 };
 
-// one pass of the transposed W1 GEMM over output channels [ob, ob + width) with NCHT channels per thread
+// one pass of the transposed W1 GEMM over output channels [ob, ob + width) with NCHT channels per thread -> global
 template <int DIM, int NCHT>
-__device__ __forceinline__ void dx_pass(const float* __restrict__ bufB, const FusedPlan& p, const WRef& w1, float* grad_x,
-                                        int64_t row0, int64_t rows, int cin, int ob, int width, int c, int rg, bool active) {
-  using Cfg = GemmCfg<DIM>;
-  constexpr int B = Alg<DIM>::B, RB = Cfg::RB;
+__device__ __forceinline__ void dx_pass(const float* __restrict__ tD, int sD, const FusedPlan& p, const WRef& w1,
+                                        float* grad_x, int64_t row0, int valid, int cin, int ob, int width, int c, int rg,
+                                        bool active) {
+  constexpr int B = Alg<DIM>::B, RB = FCfg<DIM>::RB;
   float acc[RB][NCHT][B];
 #pragma unroll
   for (int j = 0; j < RB; ++j)
@@ -585,16 +605,16 @@ __device__ __forceinline__ void dx_pass(const float* __restrict__ bufB, const Fu
 #pragma unroll
       for (int i = 0; i < B; ++i) acc[j][a][i] = 0.f;
   const bool act = active && c < width;
-  gemm_run<DIM, true, NCHT>(acc, bufB + rg * RB * p.sb, p.sb, w1, act, c, p.nc, ob, width);
+  gemm_run<DIM, true, NCHT>(acc, tD + rg * RB * sD, sD, w1, act, c, p.nc, ob, width);
   if (act && grad_x) {
 #pragma unroll
     for (int j = 0; j < RB; ++j) {
-      const int64_t r = row0 + rg * RB + j;
-      if (r >= rows) continue;
+      const int r = rg * RB + j;
+      if (r >= valid) continue;
 #pragma unroll
       for (int a = 0; a < NCHT; ++a) {
         const int ol = c + a * p.nc;
-        if (ol < width) store_vec<B>(grad_x + (r * cin + ob + ol) * B, acc[j][a]);
+        if (ol < width) store_vec<B>(grad_x + ((row0 + r) * cin + ob + ol) * B, acc[j][a]);
       }
     }
   }
@@ -606,256 +626,257 @@ template <int DIM>
 __global__ void __launch_bounds__(256, 1) block_bwd_kernel(csmpn_block_desc d, csmpn_block_grads gr, FusedPlan p,
                                                            BwdWorkspace ws) {
   using A = Alg<DIM>;
-  using Cfg = GemmCfg<DIM>;
-  constexpr int B = A::B, G = A::G, P = A::P, RB = Cfg::RB, NCH = Cfg::NCH;
+  constexpr int B = A::B, G = A::G, P = A::P, NCH = FCfg<DIM>::NCH;
   extern __shared__ __align__(128) float smem[];
-  float* bufA = smem;
-  float* bufB = bufA + p.tr * p.sa;
-  float* wsm = bufB + p.tr * p.sb;
-  float* part = wsm + p.wbuf;            // [tr][nc] sum of norms
-  float* part2 = part + p.tr * p.nc;     // [tr][nc] sum of a_n <dy, o>
-  uint64_t* bar = reinterpret_cast<uint64_t*>(part2 + p.tr * p.nc);
+  float* t1 = smem;                       // o -> y2 ; later sender rows of the gather
+  float* t2 = t1 + p.tr * p.s1;           // dy -> d ; later y1 again
+  float* t3 = t2 + p.tr * p.s2;           // xr -> dxr ; later the input row x0 (wide)
+  float* t4 = t3 + p.tr * p.s3;           // y1 -> dy2 -> dy1
+  float* wsm = t4 + p.tr * p.s2;
+  float* nu_s = wsm + p.wbuf;             // [tr][C]
+  float* dt_s = nu_s + p.tr * d.c;        // [tr][C]
+  float* mu_s = dt_s + p.tr * d.c;        // [tr] 1/mu
+  float* dmu_s = mu_s + p.tr;             // [tr] d loss / d mu / C
+  uint64_t* bar = reinterpret_cast<uint64_t*>(dmu_s + p.tr);  // bar[0]: tile inputs, bar[1]: y1 + x0 reload
   const int C = d.c, cin = d.c0 + d.c1 + d.c2;
   const int c = threadIdx.x % p.nc, rg = threadIdx.x / p.nc;
   const bool active = rg < p.rg;
-  const int warp = threadIdx.x >> 5;
-  int och[NCH];
-  bool ov[NCH];
-#pragma unroll
-  for (int a = 0; a < NCH; ++a) { och[a] = c + a * p.nc; ov[a] = active && och[a] < C; if (!ov[a]) och[a] = 0; }
+  const int n_e = threadIdx.x % C, rl = threadIdx.x / C;
+  const bool ew = rl < p.ew_rows;
   const int64_t tiles = (d.rows + p.tr - 1) / p.tr;
-  const int small_words = C * (P + 3 * G + 3);
-  float* my_small = ws.small + ((size_t)blockIdx.x * p.nwarps + warp) * small_words;
-  float* s_dw = my_small;
-  float* s_dna = s_dw + C * P;
-  float* s_dsa = s_dna + C * G;
-  float* s_dsb = s_dsa + C * G;
-  float* s_dla = s_dsb + C * G;
-  float* s_db1 = s_dla + C;
-  float* s_dbl = s_db1 + C;
   float* my_dw1 = ws.dw1 + (size_t)blockIdx.x * p.ks * C * cin * G;
   float* my_dwr = ws.dwr + (size_t)blockIdx.x * p.ks * C * C * G;
   float* my_dwl = ws.dwl + (size_t)blockIdx.x * p.ks * C * C * G;
   WRef w1, wr, wl;
   setup_weights<DIM>(d, p, wsm, w1, wr, wl);
   if (!p.resident) { w1.kchunk = p.kt1; wr.kchunk = p.ktc; wl.kchunk = p.ktc; }
-  if (threadIdx.x == 0) mbar_init(bar, 32);
+  if (threadIdx.x == 0) { mbar_init(bar, 32); mbar_init(bar + 1, 32); }
+  ChanParams<DIM> cp;
+  cp.load(d, n_e, ew);
+  // parameter-gradient accumulators of the channel this thread owns (registers, whole kernel)
+  float g_w[P], g_na[G], g_sa[G], g_sb[G], g_la = 0.f, g_b1 = 0.f, g_bl = 0.f;
+#pragma unroll
+  for (int q = 0; q < P; ++q) g_w[q] = 0.f;
+#pragma unroll
+  for (int g = 0; g < G; ++g) { g_na[g] = 0.f; g_sa[g] = 0.f; g_sb[g] = 0.f; }
   uint32_t phase = 0;
+  const size_t rowsz = (size_t)C * B;
 
   for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
     const int64_t row0 = tile * p.tr;
-    const int lr0 = rg * RB;
-    float dd[RB][NCH][B];   // running gradient held by this thread (dy -> d = do / sqrt2)
-    float nu_sum[RB], dot_sum[RB];
-    // ---- B0: load o, dy; layer-norm statistics
-    {
-      float oo[RB][NCH][B];
+    const int valid = (d.rows - row0) < p.tr ? (int)(d.rows - row0) : p.tr;
+    fence_proxy_async();
+    __syncthreads();
+    // ---- TMA: o -> t1, dy -> t2, xr -> t3, y1 -> t4
+    if (threadIdx.x < 32) {
+      uint32_t bytes = tma_dense_rows<DIM>(t1, p.s1, 0, d.save_o, C, row0, valid, bar);
+      bytes += tma_dense_rows<DIM>(t2, p.s2, 0, gr.grad_y, C, row0, valid, bar);
+      bytes += tma_dense_rows<DIM>(t3, p.s3, 0, d.save_xr, C, row0, valid, bar);
+      bytes += tma_dense_rows<DIM>(t4, p.s2, 0, d.save_y1, C, row0, valid, bar);
+      mbar_arrive_expect_tx(bar, bytes);
+    }
+    mbar_wait(bar, phase);
+    if (valid < p.tr) {
+      zero_tail_rows(t1, p.s1, (int)rowsz, p.tr, valid);
+      zero_tail_rows(t2, p.s2, (int)rowsz, p.tr, valid);
+      zero_tail_rows(t3, p.s3, (int)rowsz, p.tr, valid);
+      zero_tail_rows(t4, p.s2, (int)rowsz, p.tr, valid);
+      __syncthreads();
+    }
+    // ---- layer-norm statistics
+    if (ew) {
+      for (int r = rl; r < p.tr; r += p.ew_rows) {
+        float o[B], dy[B];
+        load_vec<B>(o, t1 + r * p.s1 + n_e * B);
+        load_vec<B>(dy, t2 + r * p.s2 + n_e * B);
+        float dot = 0.f;
 #pragma unroll
-      for (int j = 0; j < RB; ++j) {
-        nu_sum[j] = 0.f; dot_sum[j] = 0.f;
-        const int64_t r = row0 + lr0 + j;
+        for (int i = 0; i < B; ++i) dot = fmaf(dy[i], o[i], dot);
+        nu_s[r * C + n_e] = smooth_abs_sqrt(mv_sumsq<DIM>(o));
+        dt_s[r * C + n_e] = cp.la * dot;
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x < p.tr) {
+      float s1 = 0.f, s2 = 0.f;
+      for (int n = 0; n < C; ++n) { s1 += nu_s[threadIdx.x * C + n]; s2 += dt_s[threadIdx.x * C + n]; }
+      const float inv_mu = 1.f / (s1 / (float)C + kEps);
+      mu_s[threadIdx.x] = inv_mu;
+      dmu_s[threadIdx.x] = -s2 * inv_mu * inv_mu / (float)C;
+    }
+    __syncthreads();
+    // ---- layer-norm backward -> d (t2); y2 (t1); product + normalisation backward -> dxr (t3), dy2 partial (t4)
+    if (ew) {
+      for (int r = rl; r < p.tr; r += p.ew_rows) {
+        float o[B], dd[B];
+        load_vec<B>(o, t1 + r * p.s1 + n_e * B);
+        load_vec<B>(dd, t2 + r * p.s2 + n_e * B);
+        {
+          const float inv_mu = mu_s[r];
+          float dot = 0.f;
+#pragma unroll
+          for (int i = 0; i < B; ++i) dot = fmaf(dd[i], o[i], dot);
+          g_la = fmaf(dot, inv_mu, g_la);
+          const float Q = mv_sumsq<DIM>(o);
+          const float nu = smooth_abs_sqrt(Q);
+          const float k1 = cp.la * inv_mu * kInvSqrt2;
+          const float k2 = dmu_s[r] * Q / (nu * nu * nu) * kInvSqrt2;
+#pragma unroll
+          for (int i = 0; i < B; ++i) dd[i] = fmaf(k1, dd[i], k2 * o[i]);  // d = do / sqrt2
+        }
+        store_vec<B>(t2 + r * p.s2 + n_e * B, dd);
+        g_bl += dd[0];
+        float y2[B], xr[B];
+        {
+          float sg[G], inv[G];
+          load_vec<B>(y2, t4 + r * p.s2 + n_e * B);  // y1
+          silu_gates<DIM>(y2, cp.sa, cp.sb, sg, inv);
+#pragma unroll
+          for (int i = 0; i < B; ++i) y2[i] *= sg[A::grade_of(i)];
+        }
+        store_vec<B>(t1 + r * p.s1 + n_e * B, y2);
+        load_vec<B>(xr, t3 + r * p.s3 + n_e * B);
+        float q[G], nrm[G], rinv[G], xn[B], dxn[B], dy2[B];
+        norm_factors<DIM>(xr, cp.sn, q, nrm, rinv);
+#pragma unroll
+        for (int i = 0; i < B; ++i) { xn[i] = xr[i] * rinv[A::grade_of(i)]; dy2[i] = 0.f; dxn[i] = 0.f; }
+        A::template wgp_bwd<false>(y2, xn, cp.wv, dd, nullptr, dy2, dxn, g_w);
+        store_vec<B>(t4 + r * p.s2 + n_e * B, dy2);
+        float t[G];
+#pragma unroll
+        for (int g = 0; g < G; ++g) t[g] = 0.f;
+#pragma unroll
+        for (int i = 0; i < B; ++i) t[A::grade_of(i)] = fmaf(dxn[i], xr[i], t[A::grade_of(i)]);
+        float coef[G];
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+          const float ddn = -t[g] * rinv[g] * rinv[g];  // d loss / d denominator
+          g_na[g] = fmaf(ddn * (nrm[g] - 1.f), cp.sn[g] * (1.f - cp.sn[g]), g_na[g]);
+          coef[g] = ddn * cp.sn[g] * q[g] / (nrm[g] * nrm[g] * nrm[g]);
+        }
+#pragma unroll
+        for (int i = 0; i < B; ++i) dxn[i] = fmaf(dxn[i], rinv[A::grade_of(i)], coef[A::grade_of(i)] * xr[i]);
+        store_vec<B>(t3 + r * p.s3 + n_e * B, dxn);  // dxr
+      }
+    }
+    // ---- dy2 (t4) += D * WL + DXR * WR ;  dWL += D^T Y2 ; dWR += DXR^T Y2
+    {
+      constexpr int RB = FCfg<DIM>::RB;
+      float acc[RB][NCH][B];
+#pragma unroll
+      for (int j = 0; j < RB; ++j)
+#pragma unroll
+        for (int a = 0; a < NCH; ++a)
+#pragma unroll
+          for (int i = 0; i < B; ++i) acc[j][a][i] = 0.f;
+      gemm_run<DIM, true, NCH>(acc, t2 + rg * RB * p.s2, p.s2, wl, active, c, p.nc, 0, C);
+      gemm_run<DIM, true, NCH>(acc, t3 + rg * RB * p.s3, p.s3, wr, active, c, p.nc, 0, C, !p.resident);
+      if (active) {
 #pragma unroll
         for (int a = 0; a < NCH; ++a) {
-          if (ov[a] && r < d.rows) {
-            load_vec<B>(oo[j][a], d.save_o + (r * C + och[a]) * B);
-            load_vec<B>(dd[j][a], gr.grad_y + (r * C + och[a]) * B);
-            float dot = 0.f;
+          const int o = c + a * p.nc;
+          if (o >= C) continue;
 #pragma unroll
-            for (int i = 0; i < B; ++i) dot = fmaf(dd[j][a][i], oo[j][a][i], dot);
-            nu_sum[j] += smooth_abs_sqrt(mv_sumsq<DIM>(oo[j][a]));
-            dot_sum[j] = fmaf(d.la[och[a]], dot, dot_sum[j]);
-          } else {
+          for (int j = 0; j < RB; ++j) {
+            float* q = t4 + (rg * RB + j) * p.s2 + o * B;
+            float old[B];
+            load_vec<B>(old, q);
 #pragma unroll
-            for (int i = 0; i < B; ++i) { oo[j][a][i] = 0.f; dd[j][a][i] = 0.f; }
+            for (int i = 0; i < B; ++i) old[i] += acc[j][a][i];
+            store_vec<B>(q, old);
           }
         }
       }
-      __syncthreads();  // previous tile's readers of part / part2 / bufA / bufB are done
-      if (active) {
-#pragma unroll
-        for (int j = 0; j < RB; ++j) { part[(lr0 + j) * p.nc + c] = nu_sum[j]; part2[(lr0 + j) * p.nc + c] = dot_sum[j]; }
-      }
-      __syncthreads();
-      float g_la[NCH][1];
-#pragma unroll
-      for (int a = 0; a < NCH; ++a) g_la[a][0] = 0.f;
-      if (active) {
-#pragma unroll
-        for (int j = 0; j < RB; ++j) {
-          float s1 = 0.f, s2 = 0.f;
-          for (int cc = 0; cc < p.nc; ++cc) { s1 += part[(lr0 + j) * p.nc + cc]; s2 += part2[(lr0 + j) * p.nc + cc]; }
-          const float mu = s1 / (float)C + kEps;
-          const float inv_mu = 1.f / mu;
-          const float dmu_c = -s2 * inv_mu * inv_mu / (float)C;  // d loss / d mu, divided by C
-#pragma unroll
-          for (int a = 0; a < NCH; ++a) {
-            if (!ov[a]) continue;
-            float dot = 0.f;
-#pragma unroll
-            for (int i = 0; i < B; ++i) dot = fmaf(dd[j][a][i], oo[j][a][i], dot);
-            g_la[a][0] = fmaf(dot, inv_mu, g_la[a][0]);
-            const float Q = mv_sumsq<DIM>(oo[j][a]);
-            const float nu = smooth_abs_sqrt(Q);
-            const float k1 = d.la[och[a]] * inv_mu * kInvSqrt2;
-            const float k2 = dmu_c * Q / (nu * nu * nu) * kInvSqrt2;
-            // d = do / sqrt2  (gradient of both the left branch xl and the product z)
-#pragma unroll
-            for (int i = 0; i < B; ++i) dd[j][a][i] = fmaf(k1, dd[j][a][i], k2 * oo[j][a][i]);
-          }
-        }
-      }
-      warp_reduce_store<NCH, 1>(g_la, s_dla, och, ov, p.nc);
     }
-    // ---- B1: y2 = silu(y1) -> bufB; product / normalisation backward; d -> bufA
-    float dy2[RB][NCH][B];  // gradient w.r.t. y2 (starts with the product's left-operand term)
-    float dxr[RB][NCH][B];
-    {
-      float g_w[NCH][P], g_na[NCH][G], g_bl[NCH][1];
-#pragma unroll
-      for (int a = 0; a < NCH; ++a) {
-        g_bl[a][0] = 0.f;
-#pragma unroll
-        for (int q = 0; q < P; ++q) g_w[a][q] = 0.f;
-#pragma unroll
-        for (int g = 0; g < G; ++g) g_na[a][g] = 0.f;
-      }
-#pragma unroll
-      for (int a = 0; a < NCH; ++a) {
-        const int n = och[a];
-        float sa_[G], sb_[G], s[G], wv[P];
-#pragma unroll
-        for (int g = 0; g < G; ++g) { sa_[g] = d.sa[n * G + g]; sb_[g] = d.sb[n * G + g]; s[g] = sigmoidf_(d.na[n * G + g]); }
-#pragma unroll
-        for (int q = 0; q < P; ++q) wv[q] = d.wp[n * P + q];
-#pragma unroll
-        for (int j = 0; j < RB; ++j) {
-          const int64_t r = row0 + lr0 + j;
-          float y2[B], xr[B];
-          if (ov[a] && r < d.rows) {
-            float y1[B], sg[G], inv[G];
-            load_vec<B>(y1, d.save_y1 + (r * C + n) * B);
-            load_vec<B>(xr, d.save_xr + (r * C + n) * B);
-            silu_gates<DIM>(y1, sa_, sb_, sg, inv);
-#pragma unroll
-            for (int i = 0; i < B; ++i) y2[i] = y1[i] * sg[A::grade_of(i)];
-          } else {
-#pragma unroll
-            for (int i = 0; i < B; ++i) { y2[i] = 0.f; xr[i] = 0.f; }
-          }
-          if (ov[a]) store_vec<B>(bufB + (lr0 + j) * p.sb + n * B, y2);
-          float q[G], nrm[G], rinv[G], xn[B], dxn[B];
-          norm_factors<DIM>(xr, s, q, nrm, rinv);
-#pragma unroll
-          for (int i = 0; i < B; ++i) { xn[i] = xr[i] * rinv[A::grade_of(i)]; dy2[j][a][i] = 0.f; dxn[i] = 0.f; }
-          A::template wgp_bwd<false>(y2, xn, wv, dd[j][a], nullptr, dy2[j][a], dxn, g_w[a]);
-          // normalisation backward: xn_i = xr_i * rinv_g
-          float t[G];
-#pragma unroll
-          for (int g = 0; g < G; ++g) t[g] = 0.f;
-#pragma unroll
-          for (int i = 0; i < B; ++i) t[A::grade_of(i)] = fmaf(dxn[i], xr[i], t[A::grade_of(i)]);
-          float coef[G];
-#pragma unroll
-          for (int g = 0; g < G; ++g) {
-            const float ddn = -t[g] * rinv[g] * rinv[g];  // d loss / d denominator
-            g_na[a][g] = fmaf(ddn * (nrm[g] - 1.f), s[g] * (1.f - s[g]), g_na[a][g]);
-            coef[g] = ddn * s[g] * q[g] / (nrm[g] * nrm[g] * nrm[g]);
-          }
-#pragma unroll
-          for (int i = 0; i < B; ++i) dxr[j][a][i] = fmaf(dxn[i], rinv[A::grade_of(i)], coef[A::grade_of(i)] * xr[i]);
-          g_bl[a][0] += dd[j][a][0];
-          if (ov[a]) store_vec<B>(bufA + (lr0 + j) * p.sa + n * B, dd[j][a]);
-        }
-      }
-      warp_reduce_store<NCH, P>(g_w, s_dw, och, ov, p.nc);
-      warp_reduce_store<NCH, G>(g_na, s_dna, och, ov, p.nc);
-      warp_reduce_store<NCH, 1>(g_bl, s_dbl, och, ov, p.nc);
-    }
-    // ---- B2: dy2 += D * WL ; dWL += D^T Y2
-    gemm_run<DIM, true, NCH>(dy2, bufA + lr0 * p.sa, p.sa, wl, active, c, p.nc, 0, C);
-    dw_tile<DIM>(bufA, p.sa, C, bufB, p.sb, C, 0, C, p.tr, p.ks, my_dwl);
-    __syncthreads();  // all readers of D (bufA) are done
-#pragma unroll
-    for (int a = 0; a < NCH; ++a) {
-      if (!ov[a]) continue;
-#pragma unroll
-      for (int j = 0; j < RB; ++j) store_vec<B>(bufA + (lr0 + j) * p.sa + och[a] * B, dxr[j][a]);
-    }
-    // ---- B3: dy2 += DXR * WR ; dWR += DXR^T Y2
-    gemm_run<DIM, true, NCH>(dy2, bufA + lr0 * p.sa, p.sa, wr, active, c, p.nc, 0, C);
-    dw_tile<DIM>(bufA, p.sa, C, bufB, p.sb, C, 0, C, p.tr, p.ks, my_dwr);
-    // ---- B4: MVSiLU backward -> dy1 (registers, reuse dy2)
-    {
-      float g_sa[NCH][G], g_sb[NCH][G], g_b1[NCH][1];
-#pragma unroll
-      for (int a = 0; a < NCH; ++a) {
-        g_b1[a][0] = 0.f;
-#pragma unroll
-        for (int g = 0; g < G; ++g) { g_sa[a][g] = 0.f; g_sb[a][g] = 0.f; }
-      }
-#pragma unroll
-      for (int a = 0; a < NCH; ++a) {
-        const int n = och[a];
-        float sa_[G], sb_[G];
-#pragma unroll
-        for (int g = 0; g < G; ++g) { sa_[g] = d.sa[n * G + g]; sb_[g] = d.sb[n * G + g]; }
-#pragma unroll
-        for (int j = 0; j < RB; ++j) {
-          const int64_t r = row0 + lr0 + j;
-          if (!(ov[a] && r < d.rows)) {
-#pragma unroll
-            for (int i = 0; i < B; ++i) dy2[j][a][i] = 0.f;
-            continue;
-          }
-          float y1[B], sg[G], inv[G], t[G];
-          load_vec<B>(y1, d.save_y1 + (r * C + n) * B);
-          silu_gates<DIM>(y1, sa_, sb_, sg, inv);
-#pragma unroll
-          for (int g = 0; g < G; ++g) t[g] = 0.f;
-#pragma unroll
-          for (int i = 0; i < B; ++i) t[A::grade_of(i)] = fmaf(dy2[j][a][i], y1[i], t[A::grade_of(i)]);
-          float ds[G];
-#pragma unroll
-          for (int g = 0; g < G; ++g) {
-            ds[g] = t[g] * sg[g] * (1.f - sg[g]);
-            g_sa[a][g] = fmaf(ds[g], inv[g], g_sa[a][g]);
-            g_sb[a][g] += ds[g];
-          }
-#pragma unroll
-          for (int i = 0; i < B; ++i) {
-            const int g = A::grade_of(i);
-            const float dinv = (g == 0) ? 1.f : 2.f * y1[i];
-            dy2[j][a][i] = fmaf(sg[g], dy2[j][a][i], ds[g] * sa_[g] * dinv);
-          }
-          g_b1[a][0] += dy2[j][a][0];
-        }
-      }
-      warp_reduce_store<NCH, G>(g_sa, s_dsa, och, ov, p.nc);
-      warp_reduce_store<NCH, G>(g_sb, s_dsb, och, ov, p.nc);
-      warp_reduce_store<NCH, 1>(g_b1, s_db1, och, ov, p.nc);
-    }
-    // ---- B4.5: the input rows again (TMA, L2-resident) for dW1; then dy1 -> bufB
+    dw_tile<DIM>(t2, p.s2, C, t1, p.s1, C, 0, C, p.tr, p.ks, my_dwl);
+    dw_tile<DIM>(t3, p.s3, C, t1, p.s1, C, 0, C, p.tr, p.ks, my_dwr);
+    // ---- TMA: y1 -> t2 again, the input row x0 -> t3 (sender rows through t1)
     fence_proxy_async();
-    __syncthreads();  // generic readers of bufB (Y2) and bufA (DXR) are done
-    load_input_tile<DIM>(bufA, p.sa, bufB, p.sb, d, row0, p.tr, bar, phase);
-    phase ^= 1;
-    __syncthreads();  // the input pass has finished reading the sender rows in bufB
-#pragma unroll
-    for (int a = 0; a < NCH; ++a) {
-      if (!ov[a]) continue;
-#pragma unroll
-      for (int j = 0; j < RB; ++j) store_vec<B>(bufB + (lr0 + j) * p.sb + och[a] * B, dy2[j][a]);
+    __syncthreads();  // generic accesses to t1, t2, t3 are done
+    if (threadIdx.x < 32) {
+      uint32_t bytes = tma_dense_rows<DIM>(t2, p.s2, 0, d.save_y1, C, row0, valid, bar + 1);
+      bytes += tma_input_rows<DIM>(t3, p.s3, t1, p.s1, d, row0, valid, bar + 1);
+      mbar_arrive_expect_tx(bar + 1, bytes);
     }
-    // ---- B5: dx0 = DY1 * W1 in column blocks of C channels (written straight to global);  dW1 += DY1^T X0
+    mbar_wait(bar + 1, phase);
+    phase ^= 1;
+    finish_input_rows<DIM>(t3, p.s3, t1, p.s1, d, p.tr, valid);
+    if (valid < p.tr) zero_tail_rows(t2, p.s2, (int)rowsz, p.tr, valid);
+    __syncthreads();
+    // ---- MVSiLU backward: dy1 -> t4
+    if (ew) {
+      for (int r = rl; r < p.tr; r += p.ew_rows) {
+        float y1[B], dy[B], sg[G], inv[G], t[G];
+        load_vec<B>(y1, t2 + r * p.s2 + n_e * B);
+        load_vec<B>(dy, t4 + r * p.s2 + n_e * B);
+        silu_gates<DIM>(y1, cp.sa, cp.sb, sg, inv);
+#pragma unroll
+        for (int g = 0; g < G; ++g) t[g] = 0.f;
+#pragma unroll
+        for (int i = 0; i < B; ++i) t[A::grade_of(i)] = fmaf(dy[i], y1[i], t[A::grade_of(i)]);
+        float ds[G];
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+          ds[g] = t[g] * sg[g] * (1.f - sg[g]);
+          g_sa[g] = fmaf(ds[g], inv[g], g_sa[g]);
+          g_sb[g] += ds[g];
+        }
+#pragma unroll
+        for (int i = 0; i < B; ++i) {
+          const int g = A::grade_of(i);
+          const float dinv = (g == 0) ? 1.f : 2.f * y1[i];
+          dy[i] = fmaf(sg[g], dy[i], ds[g] * cp.sa[g] * dinv);
+        }
+        g_b1 += dy[0];
+        store_vec<B>(t4 + r * p.s2 + n_e * B, dy);
+      }
+    }
+    // ---- dx0 = DY1 * W1 in column blocks of C channels (straight to global);  dW1 += DY1^T X0
     for (int ob = 0; ob < cin; ob += C) {
       const int width = (cin - ob) < C ? (cin - ob) : C;
-      const int ncht = (width + p.nc - 1) / p.nc;  // channels per thread in this block
-      if (ncht >= NCH) dx_pass<DIM, NCH>(bufB, p, w1, gr.grad_x, row0, d.rows, cin, ob, width, c, rg, active);
-      else if (ncht == 1) dx_pass<DIM, 1>(bufB, p, w1, gr.grad_x, row0, d.rows, cin, ob, width, c, rg, active);
-      else if (ncht == 2) dx_pass<DIM, (NCH > 2 ? 2 : NCH)>(bufB, p, w1, gr.grad_x, row0, d.rows, cin, ob, width, c, rg, active);
-      else dx_pass<DIM, (NCH > 3 ? 3 : NCH)>(bufB, p, w1, gr.grad_x, row0, d.rows, cin, ob, width, c, rg, active);
-      dw_tile<DIM>(bufB, p.sb, C, bufA + ob * B, p.sa, width, ob, cin, p.tr, p.ks, my_dw1);
+      if (width > (NCH - 1) * p.nc) {
+        dx_pass<DIM, NCH>(t4, p.s2, p, w1, gr.grad_x, row0, valid, cin, ob, width, c, rg, active);
+      } else {
+        for (int o2 = 0; o2 < width; o2 += p.nc)
+          dx_pass<DIM, 1>(t4, p.s2, p, w1, gr.grad_x, row0, valid, cin, ob + o2, (width - o2) < p.nc ? (width - o2) : p.nc, c,
+                          rg, active);
+      }
+      dw_tile<DIM>(t4, p.s2, C, t3 + ob * B, p.s3, width, ob, cin, p.tr, p.ks, my_dw1);
     }
+  }
+  // ---- fixed-order reduction of the per-thread parameter gradients over the row lanes of the CTA
+  {
+    __syncthreads();
+    float* red = smem;  // [threads]
+    float* out = ws.small + (size_t)blockIdx.x * C * (P + 3 * G + 3);
+    auto reduce_one = [&](float v, int offset, int Q, int q) {
+      red[threadIdx.x] = v;
+      __syncthreads();
+      if (rl == 0 && ew) {
+        float s = 0.f;
+        for (int k = 0; k < p.ew_rows; ++k) s += red[k * C + n_e];
+        out[offset + n_e * Q + q] = s;
+      }
+      __syncthreads();
+    };
+    int off = 0;
+#pragma unroll
+    for (int q = 0; q < P; ++q) reduce_one(g_w[q], off, P, q);
+    off += C * P;
+#pragma unroll
+    for (int g = 0; g < G; ++g) reduce_one(g_na[g], off, G, g);
+    off += C * G;
+#pragma unroll
+    for (int g = 0; g < G; ++g) reduce_one(g_sa[g], off, G, g);
+    off += C * G;
+#pragma unroll
+    for (int g = 0; g < G; ++g) reduce_one(g_sb[g], off, G, g);
+    off += C * G;
+    reduce_one(g_la, off, 1, 0);
+    off += C;
+    reduce_one(g_b1, off, 1, 0);
+    off += C;
+    reduce_one(g_bl, off, 1, 0);
   }
 }
 
@@ -882,7 +903,7 @@ __global__ void __launch_bounds__(256) block_bwd_final_kernel(FinalSegs segs) {
 template <int DIM>
 int launch_block_fwd(const csmpn_block_desc& d, cudaStream_t s) {
   FusedPlan p;
-  int st = make_fused_plan<DIM>(d, &p);
+  int st = make_fused_plan<DIM>(d, false, &p);
   if (st) return st;
   static bool attr_set = false;
   if (!attr_set) {
@@ -897,11 +918,11 @@ int launch_block_fwd(const csmpn_block_desc& d, cudaStream_t s) {
 template <int DIM>
 int64_t block_bwd_ws_bytes(const csmpn_block_desc& d, FusedPlan* pp) {
   FusedPlan p;
-  if (make_fused_plan<DIM>(d, &p)) return -1;
+  if (make_fused_plan<DIM>(d, true, &p)) return -1;
   if (pp) *pp = p;
   constexpr int G = Alg<DIM>::G, P = Alg<DIM>::P;
   const int64_t c = d.c, cin = d.c0 + d.c1 + d.c2;
-  int64_t words = (int64_t)p.grid * ((int64_t)p.ks * (c * cin * G + 2 * c * c * G) + (int64_t)p.nwarps * c * (P + 3 * G + 3));
+  int64_t words = (int64_t)p.grid * ((int64_t)p.ks * (c * cin * G + 2 * c * c * G) + c * (P + 3 * G + 3));
   return words * 4;
 }
 
@@ -918,7 +939,8 @@ int launch_block_bwd(const csmpn_block_desc& d, const csmpn_block_grads& g, void
   ws.dwr = ws.dw1 + (size_t)p.grid * p.ks * c * cin * G;
   ws.dwl = ws.dwr + (size_t)p.grid * p.ks * c * c * G;
   ws.small = ws.dwl + (size_t)p.grid * p.ks * c * c * G;
-  CSMPN_CUDA_TRY(cudaMemsetAsync(workspace, 0, (size_t)need, s));
+  const size_t dw_bytes = (size_t)((char*)ws.small - (char*)workspace);
+  CSMPN_CUDA_TRY(cudaMemsetAsync(workspace, 0, dw_bytes, s));  // the small partials are written, not accumulated
   static bool attr_set = false;
   if (!attr_set) {
     CSMPN_CUDA_TRY(cudaFuncSetAttribute(block_bwd_kernel<DIM>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem + 1024));
@@ -927,7 +949,6 @@ int launch_block_bwd(const csmpn_block_desc& d, const csmpn_block_grads& g, void
   block_bwd_kernel<DIM><<<p.grid, p.threads, p.smem, s>>>(d, g, p, ws);
   CSMPN_LAUNCH_CHECK("block_bwd");
   const int small_words = c * (P + 3 * G + 3);
-  const int sparts = p.grid * p.nwarps;
   FinalSegs fs;
   int k = 0;
   auto add = [&](const float* in, float* out, int n, int parts, int64_t stride) {
@@ -937,13 +958,13 @@ int launch_block_bwd(const csmpn_block_desc& d, const csmpn_block_grads& g, void
   add(ws.dwr, g.g_wr, c * c * G, p.grid * p.ks, (int64_t)c * c * G);
   add(ws.dwl, g.g_wl, c * c * G, p.grid * p.ks, (int64_t)c * c * G);
   const float* sm = ws.small;
-  add(sm, g.g_wp, c * P, sparts, small_words); sm += c * P;
-  add(sm, g.g_na, c * G, sparts, small_words); sm += c * G;
-  add(sm, g.g_sa, c * G, sparts, small_words); sm += c * G;
-  add(sm, g.g_sb, c * G, sparts, small_words); sm += c * G;
-  add(sm, g.g_la, c, sparts, small_words); sm += c;
-  add(sm, d.has_b1 ? g.g_b1 : nullptr, c, sparts, small_words); sm += c;
-  add(sm, g.g_bl, c, sparts, small_words);
+  add(sm, g.g_wp, c * P, p.grid, small_words); sm += c * P;
+  add(sm, g.g_na, c * G, p.grid, small_words); sm += c * G;
+  add(sm, g.g_sa, c * G, p.grid, small_words); sm += c * G;
+  add(sm, g.g_sb, c * G, p.grid, small_words); sm += c * G;
+  add(sm, g.g_la, c, p.grid, small_words); sm += c;
+  add(sm, d.has_b1 ? g.g_b1 : nullptr, c, p.grid, small_words); sm += c;
+  add(sm, g.g_bl, c, p.grid, small_words);
   fs.count = k;
   fs.total = 0;
   for (int i = 0; i < k; ++i) fs.total += fs.s[i].n;

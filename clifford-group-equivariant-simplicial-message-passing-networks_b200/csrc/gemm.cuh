@@ -25,13 +25,13 @@ template <> struct GemmCfg<5> { static constexpr int RB = 1, NCH = 2, GP = 8; };
 __host__ __device__ inline int pad_stride(int n) { return n + ((4 - (n % 32)) + 32) % 32; }
 
 // acc[j][a][i] += sum_{k < K} xs[j*xstride + k*B + i] * wp[a][k*wk_stride + grade(i)]
-template <int DIM, int NCH = GemmCfg<DIM>::NCH>
-__device__ __forceinline__ void gemm_accumulate(float (&acc)[GemmCfg<DIM>::RB][NCH][Alg<DIM>::B],
+template <int DIM, int NCH = GemmCfg<DIM>::NCH, int RB = GemmCfg<DIM>::RB>
+__device__ __forceinline__ void gemm_accumulate(float (&acc)[RB][NCH][Alg<DIM>::B],
                                                 const float* __restrict__ xs, int xstride,
                                                 const float* const (&wp)[NCH], int wk_stride, int K) {
   using A = Alg<DIM>;
   using Cfg = GemmCfg<DIM>;
-  constexpr int B = A::B, RB = Cfg::RB, GP = Cfg::GP;
+  constexpr int B = A::B, GP = Cfg::GP;
 #pragma unroll 2
   for (int k = 0; k < K; ++k) {
     float xv[RB][B], wv[NCH][GP];
