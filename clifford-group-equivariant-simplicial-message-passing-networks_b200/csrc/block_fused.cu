@@ -203,53 +203,47 @@ __device__ __forceinline__ float mv_sumsq(const float* x) {
 }
 
 // ---------------------------------------------------------------------------------------------------
-// TMA row loaders (executed by warp 0; every lane issues the copies of the rows r = lane, lane + 32, ... and then
-// arrives on the mbarrier with the byte count it issued; the barrier is initialised with 32 arrivals).
+// TMA row loaders.  Every thread of the CTA issues at most a few cp.async.bulk row copies (one per (row, piece)
+// item, so the dependent index loads of the gather are spread over all threads); thread 0 arrives on the mbarrier
+// (initialised with one arrival) with the total byte count, which is known arithmetically.
+struct RowPiece {
+  float* tile; int stride; int col;   // destination: tile row r, word offset col
+  const float* src; int ch;           // source tensor [*, ch, B]
+  const int32_t* idx;                 // row index array (NULL: dense rows row0 + r)
+};
 
-// dense rows [row0 + r] of a [rows, ch, B] tensor into tile columns [col, col + ch*B)
-template <int DIM>
-__device__ __forceinline__ uint32_t tma_dense_rows(float* tile, int stride, int col, const float* src, int ch, int64_t row0,
-                                                   int valid, uint64_t* bar) {
+template <int DIM, int NP>
+__device__ __forceinline__ void tma_issue_pieces(const RowPiece (&pc)[NP], int npieces, int64_t row0, int valid,
+                                                 uint64_t* bar) {
   constexpr int B = Alg<DIM>::B;
-  const uint32_t rb = (uint32_t)ch * B * 4;
-  uint32_t bytes = 0;
-  for (int r = threadIdx.x; r < valid; r += 32) {
-    tma_row_g2s(tile + r * stride + col, src + (row0 + r) * (int64_t)ch * B, rb, bar);
-    bytes += rb;
+  if (threadIdx.x == 0) {
+    uint32_t per_row = 0;
+    for (int k = 0; k < npieces; ++k) per_row += (uint32_t)pc[k].ch * B * 4;
+    mbar_arrive_expect_tx(bar, per_row * (uint32_t)valid);
   }
-  return bytes;
+  for (int item = threadIdx.x; item < valid * npieces; item += blockDim.x) {
+    const int r = item / npieces, k = item - r * npieces;
+    const RowPiece& q = pc[k];
+    const int64_t srow = q.idx ? (int64_t)__ldg(q.idx + row0 + r) : row0 + r;
+    tma_row_g2s(q.tile + r * q.stride + q.col, q.src + srow * (int64_t)q.ch * B, (uint32_t)q.ch * B * 4, bar);
+  }
 }
 
-// rows idx[row0 + r] of a [*, ch, B] tensor
+// pieces of the assembled input row of the block into `tile` (stride s3); sender rows of the gather go to `tmp`
 template <int DIM>
-__device__ __forceinline__ uint32_t tma_indexed_rows(float* tile, int stride, int col, const float* src, int ch,
-                                                     const int32_t* __restrict__ idx, int64_t row0, int valid, uint64_t* bar) {
+__device__ __forceinline__ int input_pieces(RowPiece* pc, float* tile, int s3, float* tmp, int s1, const csmpn_block_desc& d) {
   constexpr int B = Alg<DIM>::B;
-  const uint32_t rb = (uint32_t)ch * B * 4;
-  uint32_t bytes = 0;
-  for (int r = threadIdx.x; r < valid; r += 32) {
-    tma_row_g2s(tile + r * stride + col, src + (int64_t)__ldg(idx + row0 + r) * ch * B, rb, bar);
-    bytes += rb;
-  }
-  return bytes;
-}
-
-// the assembled input row of the block into `tile` (stride s3); sender rows of the gather mode go to `tmp` (stride s1)
-template <int DIM>
-__device__ __forceinline__ uint32_t tma_input_rows(float* tile, int s3, float* tmp, int s1, const csmpn_block_desc& d,
-                                                   int64_t row0, int valid, uint64_t* bar) {
-  constexpr int B = Alg<DIM>::B;
-  uint32_t bytes = 0;
+  int n = 0;
   if (d.mode == 0) {
-    bytes += tma_dense_rows<DIM>(tile, s3, 0, d.p0, d.c0, row0, valid, bar);
-    if (d.c1) bytes += tma_dense_rows<DIM>(tile, s3, d.c0 * B, d.p1, d.c1, row0, valid, bar);
-    if (d.c2) bytes += tma_dense_rows<DIM>(tile, s3, (d.c0 + d.c1) * B, d.p2, d.c2, row0, valid, bar);
+    pc[n++] = RowPiece{tile, s3, 0, d.p0, d.c0, nullptr};
+    if (d.c1) pc[n++] = RowPiece{tile, s3, d.c0 * B, d.p1, d.c1, nullptr};
+    if (d.c2) pc[n++] = RowPiece{tile, s3, (d.c0 + d.c1) * B, d.p2, d.c2, nullptr};
   } else {
-    bytes += tma_indexed_rows<DIM>(tile, s3, 0, d.p0, d.c0, d.dst, row0, valid, bar);
-    bytes += tma_indexed_rows<DIM>(tmp, s1, 0, d.p0, d.c0, d.src, row0, valid, bar);
-    if (d.c1) bytes += tma_indexed_rows<DIM>(tile, s3, d.c0 * B, d.p1, d.c1, d.eid, row0, valid, bar);
+    pc[n++] = RowPiece{tile, s3, 0, d.p0, d.c0, d.dst};
+    pc[n++] = RowPiece{tmp, s1, 0, d.p0, d.c0, d.src};
+    if (d.c1) pc[n++] = RowPiece{tile, s3, d.c0 * B, d.p1, d.c1, d.eid};
   }
-  return bytes;
+  return n;
 }
 
 // after the wait: gather mode forms h[dst] - h[src]; missing rows of a tail tile are zeroed
@@ -427,7 +421,7 @@ __global__ void __launch_bounds__(256, 1) block_fwd_kernel(csmpn_block_desc d, F
   WRef w1, wr, wl;
   setup_weights<DIM>(d, p, wsm, w1, wr, wl);
   if (!p.resident) { w1.kchunk = p.kc1; wr.kchunk = p.kcc; wl.kchunk = p.kcc; }
-  if (threadIdx.x == 0) mbar_init(bar, 32);
+  if (threadIdx.x == 0) mbar_init(bar, 1);
   ChanParams<DIM> cp;
   cp.load(d, n_e, ew);
   uint32_t phase = 0;
@@ -437,9 +431,10 @@ __global__ void __launch_bounds__(256, 1) block_fwd_kernel(csmpn_block_desc d, F
     const int valid = (d.rows - row0) < p.tr ? (int)(d.rows - row0) : p.tr;
     fence_proxy_async();
     __syncthreads();  // previous tile's generic accesses are done; barrier initialised
-    if (threadIdx.x < 32) {
-      uint32_t bytes = tma_input_rows<DIM>(tA, p.s3, tB, p.s1, d, row0, valid, bar);
-      mbar_arrive_expect_tx(bar, bytes);
+    {
+      RowPiece pc[4];
+      const int np = input_pieces<DIM>(pc, tA, p.s3, tB, p.s1, d);
+      tma_issue_pieces<DIM, 4>(pc, np, row0, valid, bar);
     }
     mbar_wait(bar, phase);
     phase ^= 1;
@@ -486,10 +481,12 @@ __global__ void __launch_bounds__(256, 1) block_fwd_kernel(csmpn_block_desc d, F
       }
     }
     __syncthreads();
-    if (threadIdx.x < p.tr) {  // fixed-order channel sum per row
+    for (int r = threadIdx.x >> 5; r < p.tr; r += (int)(blockDim.x >> 5)) {  // one warp per row, fixed-order tree
       float s = 0.f;
-      for (int n = 0; n < C; ++n) s += nu_s[threadIdx.x * C + n];
-      mu_s[threadIdx.x] = 1.f / (s / (float)C + kEps);
+      for (int n = threadIdx.x & 31; n < C; n += 32) s += nu_s[r * C + n];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      if ((threadIdx.x & 31) == 0) mu_s[r] = 1.f / (s / (float)C + kEps);
     }
     __syncthreads();
     // ---- MVLayerNorm scale (+ residual) -> global
@@ -564,18 +561,32 @@ __device__ __forceinline__ void dw_tile(const float* __restrict__ nbuf, int nstr
           for (int i = 0; i < B; ++i) acc[a][b][A::grade_of(i)] = fmaf(dv[a][i], xv[b][i], acc[a][b][A::grade_of(i)]);
     }
     float* out = gacc + (size_t)split * cn_total * m_ld * G;
+    if constexpr (G == 4) {
+      // issue every load of the read-modify-write before the first dependent add (one L2 round trip, not 16)
+      float4 old[NA][MA];
 #pragma unroll
-    for (int a = 0; a < NA; ++a) {
-      if (!nv[a]) continue;
+      for (int a = 0; a < NA; ++a)
 #pragma unroll
-      for (int b = 0; b < MA; ++b) {
-        if (!mv[b]) continue;
-        float* o = out + ((size_t)nl[a] * m_ld + m_off + ml[b]) * G;
-        if constexpr (G == 4) {
-          float4 t = *reinterpret_cast<float4*>(o);
+        for (int b = 0; b < MA; ++b)
+          old[a][b] = (nv[a] && mv[b]) ? __ldcg(reinterpret_cast<const float4*>(out + ((size_t)nl[a] * m_ld + m_off + ml[b]) * G))
+                                       : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int a = 0; a < NA; ++a)
+#pragma unroll
+        for (int b = 0; b < MA; ++b) {
+          if (!(nv[a] && mv[b])) continue;
+          float4 t = old[a][b];
           t.x += acc[a][b][0]; t.y += acc[a][b][1]; t.z += acc[a][b][2]; t.w += acc[a][b][3];
-          *reinterpret_cast<float4*>(o) = t;
-        } else {
+          __stcg(reinterpret_cast<float4*>(out + ((size_t)nl[a] * m_ld + m_off + ml[b]) * G), t);
+        }
+    } else {
+#pragma unroll
+      for (int a = 0; a < NA; ++a) {
+        if (!nv[a]) continue;
+#pragma unroll
+        for (int b = 0; b < MA; ++b) {
+          if (!mv[b]) continue;
+          float* o = out + ((size_t)nl[a] * m_ld + m_off + ml[b]) * G;
 #pragma unroll
           for (int g = 0; g < G; ++g) o[g] += acc[a][b][g];
         }
@@ -650,7 +661,7 @@ __global__ void __launch_bounds__(256, 1) block_bwd_kernel(csmpn_block_desc d, c
   WRef w1, wr, wl;
   setup_weights<DIM>(d, p, wsm, w1, wr, wl);
   if (!p.resident) { w1.kchunk = p.kt1; wr.kchunk = p.ktc; wl.kchunk = p.ktc; }
-  if (threadIdx.x == 0) { mbar_init(bar, 32); mbar_init(bar + 1, 32); }
+  if (threadIdx.x == 0) { mbar_init(bar, 1); mbar_init(bar + 1, 1); }
   ChanParams<DIM> cp;
   cp.load(d, n_e, ew);
   // parameter-gradient accumulators of the channel this thread owns (registers, whole kernel)
@@ -668,12 +679,10 @@ __global__ void __launch_bounds__(256, 1) block_bwd_kernel(csmpn_block_desc d, c
     fence_proxy_async();
     __syncthreads();
     // ---- TMA: o -> t1, dy -> t2, xr -> t3, y1 -> t4
-    if (threadIdx.x < 32) {
-      uint32_t bytes = tma_dense_rows<DIM>(t1, p.s1, 0, d.save_o, C, row0, valid, bar);
-      bytes += tma_dense_rows<DIM>(t2, p.s2, 0, gr.grad_y, C, row0, valid, bar);
-      bytes += tma_dense_rows<DIM>(t3, p.s3, 0, d.save_xr, C, row0, valid, bar);
-      bytes += tma_dense_rows<DIM>(t4, p.s2, 0, d.save_y1, C, row0, valid, bar);
-      mbar_arrive_expect_tx(bar, bytes);
+    {
+      RowPiece pc[4] = {RowPiece{t1, p.s1, 0, d.save_o, C, nullptr}, RowPiece{t2, p.s2, 0, gr.grad_y, C, nullptr},
+                        RowPiece{t3, p.s3, 0, d.save_xr, C, nullptr}, RowPiece{t4, p.s2, 0, d.save_y1, C, nullptr}};
+      tma_issue_pieces<DIM, 4>(pc, 4, row0, valid, bar);
     }
     mbar_wait(bar, phase);
     if (valid < p.tr) {
@@ -697,12 +706,16 @@ __global__ void __launch_bounds__(256, 1) block_bwd_kernel(csmpn_block_desc d, c
       }
     }
     __syncthreads();
-    if (threadIdx.x < p.tr) {
+    for (int r = threadIdx.x >> 5; r < p.tr; r += (int)(blockDim.x >> 5)) {
       float s1 = 0.f, s2 = 0.f;
-      for (int n = 0; n < C; ++n) { s1 += nu_s[threadIdx.x * C + n]; s2 += dt_s[threadIdx.x * C + n]; }
-      const float inv_mu = 1.f / (s1 / (float)C + kEps);
-      mu_s[threadIdx.x] = inv_mu;
-      dmu_s[threadIdx.x] = -s2 * inv_mu * inv_mu / (float)C;
+      for (int n = threadIdx.x & 31; n < C; n += 32) { s1 += nu_s[r * C + n]; s2 += dt_s[r * C + n]; }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
+      if ((threadIdx.x & 31) == 0) {
+        const float inv_mu = 1.f / (s1 / (float)C + kEps);
+        mu_s[r] = inv_mu;
+        dmu_s[r] = -s2 * inv_mu * inv_mu / (float)C;
+      }
     }
     __syncthreads();
     // ---- layer-norm backward -> d (t2); y2 (t1); product + normalisation backward -> dxr (t3), dy2 partial (t4)
@@ -793,10 +806,11 @@ __global__ void __launch_bounds__(256, 1) block_bwd_kernel(csmpn_block_desc d, c
     // ---- TMA: y1 -> t2 again, the input row x0 -> t3 (sender rows through t1)
     fence_proxy_async();
     __syncthreads();  // generic accesses to t1, t2, t3 are done
-    if (threadIdx.x < 32) {
-      uint32_t bytes = tma_dense_rows<DIM>(t2, p.s2, 0, d.save_y1, C, row0, valid, bar + 1);
-      bytes += tma_input_rows<DIM>(t3, p.s3, t1, p.s1, d, row0, valid, bar + 1);
-      mbar_arrive_expect_tx(bar + 1, bytes);
+    {
+      RowPiece pc[4];
+      pc[0] = RowPiece{t2, p.s2, 0, d.save_y1, C, nullptr};
+      const int np = 1 + input_pieces<DIM>(pc + 1, t3, p.s3, t1, p.s1, d);
+      tma_issue_pieces<DIM, 4>(pc, np, row0, valid, bar + 1);
     }
     mbar_wait(bar + 1, phase);
     phase ^= 1;

@@ -79,6 +79,17 @@ template <int DIM, bool TRANS>
 __device__ __forceinline__ void stage_weights(float* __restrict__ ws, int sw, const float* __restrict__ w, int c_out,
                                               int c_in, int gw, int k0, int kc) {
   constexpr int G = Alg<DIM>::G, GP = GemmCfg<DIM>::GP;
+  if constexpr (G == 4 && GP == 4) {
+    if (gw == G) {  // one 128-bit copy per (n, m): coalesced along m
+      const int rows = TRANS ? kc : c_out, cols = TRANS ? c_in : kc;
+      for (int idx = threadIdx.x; idx < rows * cols; idx += blockDim.x) {
+        const int n = idx / cols, m = idx - n * cols;
+        const int gn = TRANS ? k0 + n : n, gm = TRANS ? m : k0 + m;
+        *reinterpret_cast<float4*>(ws + n * sw + m * 4) = *reinterpret_cast<const float4*>(w + ((int64_t)gn * c_in + gm) * 4);
+      }
+      return;
+    }
+  }
   if constexpr (!TRANS) {
     const int per_n = kc * G;
     for (int idx = threadIdx.x; idx < c_out * per_n; idx += blockDim.x) {
