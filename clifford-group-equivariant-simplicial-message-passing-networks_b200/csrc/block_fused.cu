@@ -34,7 +34,9 @@ template <> struct FCfg<3> { static constexpr int RB = 1, NCH = 4; };
 template <> struct FCfg<5> { static constexpr int RB = 1, NCH = 1; };
 
 struct FusedPlan {
-  int tr, rg, nc, threads;
+  int tr, rg, nc, threads;   // per group
+  int ng;                    // thread groups per CTA (1 or 2); CTA size = ng * threads
+  int tile_words;            // shared-memory words owned by one group (tiles + statistics)
   int ew_rows;         // rows handled per elementwise pass (= threads / C); thread t owns channel t % C
   int s1, s2, s3;      // tile row strides (words): s1 = pad(max(C, gathered c0) B), s2 = pad(C B), s3 = pad(max(c_in, C) B)
   int resident;        // weights resident in shared memory
@@ -70,6 +72,8 @@ inline int make_fused_plan(const csmpn_block_desc& d, bool backward, FusedPlan* 
     size_t t = backward ? (size_t)tr * (p.s1 + 2 * p.s2 + p.s3) : (size_t)tr * (p.s1 + p.s2 + p.s3);
     return t + 2 * (size_t)tr * c + 2 * tr + 16;
   };
+  // two half-size groups (same shared memory as one tile twice the size) when the whole CTA fits 256 threads
+  auto two_groups = [&](int tr) { return (tr % (2 * Cfg::RB) == 0) && tr >= 16; };
   auto threads_for = [&](int tr) { return (((tr / Cfg::RB) * p.nc + 31) / 32) * 32; };
   static const int cand[] = {64, 48, 32, 24, 16, 12, 8, 6, 4, 2, 1};
   int best = 0;
@@ -114,23 +118,30 @@ inline int make_fused_plan(const csmpn_block_desc& d, bool backward, FusedPlan* 
     if (w4 > p.wbuf) p.wbuf = w4;
     if ((tile_words(p.tr) + p.wbuf) * 4 > (size_t)kMaxSmem) return CSMPN_ERR_UNSUPPORTED;
   }
+  p.ng = 1;
+  if (p.resident && two_groups(p.tr) && threads_for(p.tr / 2) >= c && threads_for(p.tr / 2) * 2 <= 256 &&
+      (2 * tile_words(p.tr / 2) + res_words) * 4 <= (size_t)kMaxSmem) {
+    p.ng = 2;
+    p.tr /= 2;
+  }
   p.rg = p.tr / Cfg::RB;
   p.threads = threads_for(p.tr);
   if (p.threads < c) p.threads = ((c + 31) / 32) * 32;  // the elementwise stages need one thread per channel
-  if (p.threads > 256) return CSMPN_ERR_UNSUPPORTED;
+  if (p.threads * p.ng > 256) return CSMPN_ERR_UNSUPPORTED;
   p.ew_rows = p.threads / c;
   if (p.ew_rows > p.tr) p.ew_rows = p.tr;
-  p.smem = (tile_words(p.tr) + p.wbuf) * sizeof(float);
-  int64_t tiles = (d.rows + p.tr - 1) / p.tr;
+  p.tile_words = (int)tile_words(p.tr);
+  p.smem = ((size_t)p.ng * tile_words(p.tr) + p.wbuf) * sizeof(float);
+  int64_t tiles = (d.rows + (int64_t)p.tr * p.ng - 1) / ((int64_t)p.tr * p.ng);
   int per_sm = (int)((size_t)(226 * 1024) / (p.smem + 1024));
   if (per_sm < 1) per_sm = 1;
   if (per_sm > 4) per_sm = 4;
-  if (per_sm * p.threads > 512) per_sm = 512 / p.threads > 0 ? 512 / p.threads : 1;
+  if (per_sm * p.threads * p.ng > 512) per_sm = 512 / (p.threads * p.ng) > 0 ? 512 / (p.threads * p.ng) : 1;
   int64_t cap = (int64_t)sm_count_cached() * per_sm;
   p.grid = (int)(tiles < cap ? (tiles > 0 ? tiles : 1) : cap);
   const int NA = Alg<DIM>::G <= 4 ? 4 : 2;
   int tc = ((c + NA - 1) / NA) * ((c + 3) / 4);
-  p.ks = p.threads / tc > 0 ? p.threads / tc : 1;
+  p.ks = p.threads / tc > 0 ? p.threads / tc : 1;  // per group
   if (p.ks > 16) p.ks = 16;
   while (p.ks > 1 && p.tr % p.ks) --p.ks;
   *out = p;
@@ -203,6 +214,15 @@ __device__ __forceinline__ float mv_sumsq(const float* x) {
 }
 
 // ---------------------------------------------------------------------------------------------------
+// A CTA runs NG (1 or 2) independent thread groups.  Each group owns its own tiles in shared memory, its own
+// mbarriers and its own stream of row tiles, and synchronises with a named barrier, so one group's TMA waits,
+// barriers and elementwise stages overlap the other group's GEMMs while both share the resident weights.
+struct Grp {
+  int tid, nthr, id;
+  __device__ __forceinline__ void sync() const { asm volatile("bar.sync %0, %1;" ::"r"(id + 1), "r"(nthr) : "memory"); }
+};
+
+// ---------------------------------------------------------------------------------------------------
 // TMA row loaders.  Every thread of the CTA issues at most a few cp.async.bulk row copies (one per (row, piece)
 // item, so the dependent index loads of the gather are spread over all threads); thread 0 arrives on the mbarrier
 // (initialised with one arrival) with the total byte count, which is known arithmetically.
@@ -213,15 +233,15 @@ struct RowPiece {
 };
 
 template <int DIM, int NP>
-__device__ __forceinline__ void tma_issue_pieces(const RowPiece (&pc)[NP], int npieces, int64_t row0, int valid,
-                                                 uint64_t* bar) {
+__device__ __forceinline__ void tma_issue_pieces(const Grp& g, const RowPiece (&pc)[NP], int npieces, int64_t row0,
+                                                 int valid, uint64_t* bar) {
   constexpr int B = Alg<DIM>::B;
-  if (threadIdx.x == 0) {
+  if (g.tid == 0) {
     uint32_t per_row = 0;
     for (int k = 0; k < npieces; ++k) per_row += (uint32_t)pc[k].ch * B * 4;
     mbar_arrive_expect_tx(bar, per_row * (uint32_t)valid);
   }
-  for (int item = threadIdx.x; item < valid * npieces; item += blockDim.x) {
+  for (int item = g.tid; item < valid * npieces; item += g.nthr) {
     const int r = item / npieces, k = item - r * npieces;
     const RowPiece& q = pc[k];
     const int64_t srow = q.idx ? (int64_t)__ldg(q.idx + row0 + r) : row0 + r;
@@ -248,12 +268,12 @@ __device__ __forceinline__ int input_pieces(RowPiece* pc, float* tile, int s3, f
 
 // after the wait: gather mode forms h[dst] - h[src]; missing rows of a tail tile are zeroed
 template <int DIM>
-__device__ __forceinline__ void finish_input_rows(float* tile, int s3, const float* tmp, int s1, const csmpn_block_desc& d,
-                                                  int tr, int valid) {
+__device__ __forceinline__ void finish_input_rows(const Grp& g, float* tile, int s3, const float* tmp, int s1,
+                                                  const csmpn_block_desc& d, int tr, int valid) {
   constexpr int B = Alg<DIM>::B;
   if (d.mode == 1) {
     const int v0 = d.c0 * B / 4;
-    for (int idx = threadIdx.x; idx < valid * v0; idx += blockDim.x) {
+    for (int idx = g.tid; idx < valid * v0; idx += g.nthr) {
       const int r = idx / v0, v = idx - r * v0;
       float4 a = *reinterpret_cast<const float4*>(tile + r * s3 + 4 * v);
       const float4 b = *reinterpret_cast<const float4*>(tmp + r * s1 + 4 * v);
@@ -263,16 +283,16 @@ __device__ __forceinline__ void finish_input_rows(float* tile, int s3, const flo
   }
   if (valid < tr) {
     const int vpr = (d.c0 + d.c1 + d.c2) * B / 4;
-    for (int idx = threadIdx.x; idx < (tr - valid) * vpr; idx += blockDim.x) {
+    for (int idx = g.tid; idx < (tr - valid) * vpr; idx += g.nthr) {
       const int r = valid + idx / vpr, v = idx % vpr;
       *reinterpret_cast<float4*>(tile + r * s3 + 4 * v) = make_float4(0.f, 0.f, 0.f, 0.f);
     }
   }
 }
 
-__device__ __forceinline__ void zero_tail_rows(float* tile, int stride, int words, int tr, int valid) {
+__device__ __forceinline__ void zero_tail_rows(const Grp& g, float* tile, int stride, int words, int tr, int valid) {
   const int vpr = words / 4;
-  for (int idx = threadIdx.x; idx < (tr - valid) * vpr; idx += blockDim.x) {
+  for (int idx = g.tid; idx < (tr - valid) * vpr; idx += g.nthr) {
     const int r = valid + idx / vpr, v = idx % vpr;
     *reinterpret_cast<float4*>(tile + r * stride + 4 * v) = make_float4(0.f, 0.f, 0.f, 0.f);
   }
@@ -291,14 +311,14 @@ struct WRef {
 // acc += buf[:, 0:kdim] * W   for output channels  obase + c + a * nco  (a < NCHT), masked by owidth.
 // The leading barrier publishes the shared-memory writes of the previous stage.
 template <int DIM, bool TRANS, int NCHT>
-__device__ __forceinline__ void gemm_run(float (&acc)[FCfg<DIM>::RB][NCHT][Alg<DIM>::B],
+__device__ __forceinline__ void gemm_run(const Grp& g, float (&acc)[FCfg<DIM>::RB][NCHT][Alg<DIM>::B],
                                          const float* __restrict__ buf_rows, int stride, const WRef& w, bool active, int c,
                                          int nco, int obase, int owidth, bool lead_sync = true) {
   constexpr int B = Alg<DIM>::B, GP = GemmCfg<DIM>::GP, RB = FCfg<DIM>::RB;
   const int kdim = TRANS ? w.c_out : w.c_in;
   const int odim = TRANS ? w.c_in : w.c_out;
   if (w.resident) {
-    if (lead_sync) __syncthreads();
+    if (lead_sync) g.sync();
     if (active) {
       const float* wp[NCHT];
 #pragma unroll
@@ -314,9 +334,9 @@ __device__ __forceinline__ void gemm_run(float (&acc)[FCfg<DIM>::RB][NCHT][Alg<D
   for (int k0 = 0; k0 < kdim; k0 += w.kchunk) {
     const int kc = (kdim - k0) < w.kchunk ? (kdim - k0) : w.kchunk;
     const int sw = TRANS ? pad_stride(odim * GP) : pad_stride(kc * GP);
-    __syncthreads();
+    g.sync();
     stage_weights<DIM, TRANS>(w.s, sw, w.g, w.c_out, w.c_in, Alg<DIM>::G, k0, kc);
-    __syncthreads();
+    g.sync();
     if (active) {
       const float* wp[NCHT];
 #pragma unroll
@@ -346,8 +366,8 @@ __device__ __forceinline__ void setup_weights(const csmpn_block_desc& d, const F
 
 // dst[r][o] (+)= sum_k src[r][k] W(k, o) for all C output channels of the block; shared-memory to shared-memory.
 template <int DIM, bool TRANS, bool ACCUM>
-__device__ __forceinline__ void gemm_tile(float* __restrict__ dst, int dstride, const float* __restrict__ src, int sstride,
-                                          const WRef& w, const FusedPlan& p, int C, bool active, int c, int rg,
+__device__ __forceinline__ void gemm_tile(const Grp& g, float* __restrict__ dst, int dstride, const float* __restrict__ src,
+                                          int sstride, const WRef& w, const FusedPlan& p, int C, bool active, int c, int rg,
                                           bool lead_sync = true) {
   constexpr int B = Alg<DIM>::B, RB = FCfg<DIM>::RB, NCH = FCfg<DIM>::NCH;
   float acc[RB][NCH][B];
@@ -357,7 +377,7 @@ __device__ __forceinline__ void gemm_tile(float* __restrict__ dst, int dstride, 
     for (int a = 0; a < NCH; ++a)
 #pragma unroll
       for (int i = 0; i < B; ++i) acc[j][a][i] = 0.f;
-  gemm_run<DIM, TRANS, NCH>(acc, src + rg * RB * sstride, sstride, w, active, c, p.nc, 0, C, lead_sync);
+  gemm_run<DIM, TRANS, NCH>(g, acc, src + rg * RB * sstride, sstride, w, active, c, p.nc, 0, C, lead_sync);
   if (active) {
 #pragma unroll
     for (int a = 0; a < NCH; ++a) {
@@ -405,43 +425,48 @@ __global__ void __launch_bounds__(256, 1) block_fwd_kernel(csmpn_block_desc d, F
   using A = Alg<DIM>;
   constexpr int B = A::B, G = A::G;
   extern __shared__ __align__(128) float smem[];
-  float* tA = smem;                       // input row (wide) -> xr
-  float* tB = tA + p.tr * p.s3;           // sender rows (gather) -> y1 -> y2
-  float* tC = tB + p.tr * p.s1;           // xl -> o
-  float* wsm = tC + p.tr * p.s2;
-  float* nu_s = wsm + p.wbuf;             // [tr][C]
-  float* mu_s = nu_s + 2 * p.tr * d.c;    // [tr]
+  Grp g;
+  g.id = threadIdx.x / p.threads;
+  g.tid = threadIdx.x - g.id * p.threads;
+  g.nthr = p.threads;
+  float* wsm = smem;                                  // weights (shared by the groups)
+  float* tA = smem + p.wbuf + g.id * p.tile_words;    // input row (wide) -> xr
+  float* tB = tA + p.tr * p.s3;                       // sender rows (gather) -> y1 -> y2
+  float* tC = tB + p.tr * p.s1;                       // xl -> o
+  float* nu_s = tC + p.tr * p.s2;                     // [tr][C]
+  float* mu_s = nu_s + 2 * p.tr * d.c;                // [tr]
   uint64_t* bar = reinterpret_cast<uint64_t*>(mu_s + 2 * p.tr);
   const int C = d.c;
-  const int c = threadIdx.x % p.nc, rg = threadIdx.x / p.nc;
+  const int c = g.tid % p.nc, rg = g.tid / p.nc;
   const bool active = rg < p.rg;
-  const int n_e = threadIdx.x % C, rl = threadIdx.x / C;  // elementwise mapping: channel n_e, rows rl, rl + ew_rows, ...
+  const int n_e = g.tid % C, rl = g.tid / C;  // elementwise mapping: channel n_e, rows rl, rl + ew_rows, ...
   const bool ew = rl < p.ew_rows;
   const int64_t tiles = (d.rows + p.tr - 1) / p.tr;
   WRef w1, wr, wl;
   setup_weights<DIM>(d, p, wsm, w1, wr, wl);
   if (!p.resident) { w1.kchunk = p.kc1; wr.kchunk = p.kcc; wl.kchunk = p.kcc; }
-  if (threadIdx.x == 0) mbar_init(bar, 1);
+  if (g.tid == 0) mbar_init(bar, 1);
   ChanParams<DIM> cp;
   cp.load(d, n_e, ew);
   uint32_t phase = 0;
+  __syncthreads();  // resident weights staged, barriers initialised
 
-  for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+  for (int64_t tile = (int64_t)blockIdx.x * p.ng + g.id; tile < tiles; tile += (int64_t)gridDim.x * p.ng) {
     const int64_t row0 = tile * p.tr;
     const int valid = (d.rows - row0) < p.tr ? (int)(d.rows - row0) : p.tr;
     fence_proxy_async();
-    __syncthreads();  // previous tile's generic accesses are done; barrier initialised
+    g.sync();  // previous tile's generic accesses are done
     {
       RowPiece pc[4];
       const int np = input_pieces<DIM>(pc, tA, p.s3, tB, p.s1, d);
-      tma_issue_pieces<DIM, 4>(pc, np, row0, valid, bar);
+      tma_issue_pieces<DIM, 4>(g, pc, np, row0, valid, bar);
     }
     mbar_wait(bar, phase);
     phase ^= 1;
-    finish_input_rows<DIM>(tA, p.s3, tB, p.s1, d, p.tr, valid);
+    finish_input_rows<DIM>(g, tA, p.s3, tB, p.s1, d, p.tr, valid);
     // ---- GEMM1: y1 (without bias) -> tB
-    gemm_tile<DIM, false, false>(tB, p.s1, tA, p.s3, w1, p, C, active, c, rg);
-    __syncthreads();
+    gemm_tile<DIM, false, false>(g, tB, p.s1, tA, p.s3, w1, p, C, active, c, rg);
+    g.sync();
     // ---- bias + MVSiLU (in place): tB = y2
     if (ew) {
       for (int r = rl; r < p.tr; r += p.ew_rows) {
@@ -457,9 +482,9 @@ __global__ void __launch_bounds__(256, 1) block_fwd_kernel(csmpn_block_desc d, F
       }
     }
     // ---- GEMM-R: xr -> tA ; GEMM-L: xl -> tC   (the leading barrier of the first publishes y2)
-    gemm_tile<DIM, false, false>(tA, p.s3, tB, p.s1, wr, p, C, active, c, rg);
-    gemm_tile<DIM, false, false>(tC, p.s2, tB, p.s1, wl, p, C, active, c, rg, !p.resident);
-    __syncthreads();
+    gemm_tile<DIM, false, false>(g, tA, p.s3, tB, p.s1, wr, p, C, active, c, rg);
+    gemm_tile<DIM, false, false>(g, tC, p.s2, tB, p.s1, wl, p, C, active, c, rg, !p.resident);
+    g.sync();
     // ---- normalisation, weighted geometric product, 1/sqrt2: tC = o ; norms for the layer norm
     if (ew) {
       for (int r = rl; r < p.tr; r += p.ew_rows) {
@@ -480,15 +505,15 @@ __global__ void __launch_bounds__(256, 1) block_fwd_kernel(csmpn_block_desc d, F
         nu_s[r * C + n_e] = smooth_abs_sqrt(mv_sumsq<DIM>(o));
       }
     }
-    __syncthreads();
-    for (int r = threadIdx.x >> 5; r < p.tr; r += (int)(blockDim.x >> 5)) {  // one warp per row, fixed-order tree
+    g.sync();
+    for (int r = g.tid >> 5; r < p.tr; r += (g.nthr >> 5)) {  // one warp per row, fixed-order tree
       float s = 0.f;
-      for (int n = threadIdx.x & 31; n < C; n += 32) s += nu_s[r * C + n];
+      for (int n = g.tid & 31; n < C; n += 32) s += nu_s[r * C + n];
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-      if ((threadIdx.x & 31) == 0) mu_s[r] = 1.f / (s / (float)C + kEps);
+      if ((g.tid & 31) == 0) mu_s[r] = 1.f / (s / (float)C + kEps);
     }
-    __syncthreads();
+    g.sync();
     // ---- MVLayerNorm scale (+ residual) -> global
     if (ew) {
       for (int r = rl; r < valid; r += p.ew_rows) {
@@ -516,7 +541,7 @@ __global__ void __launch_bounds__(256, 1) block_fwd_kernel(csmpn_block_desc d, F
 // Tile-local weight-gradient GEMM over one column block of the m operand:
 //   gacc[split][n][m_off + m][g] += sum_{r in split} sum_{i in g} nbuf[r][n][i] * mbuf[r][m][i],  m < cm_block
 template <int DIM>
-__device__ __forceinline__ void dw_tile(const float* __restrict__ nbuf, int nstride, int cn_total,
+__device__ __forceinline__ void dw_tile(const Grp& g, const float* __restrict__ nbuf, int nstride, int cn_total,
                                         const float* __restrict__ mbuf, int mstride, int cm_block, int m_off, int m_ld,
                                         int tr, int ks_max, float* __restrict__ gacc) {
   using A = Alg<DIM>;
@@ -524,12 +549,12 @@ __device__ __forceinline__ void dw_tile(const float* __restrict__ nbuf, int nstr
   constexpr int NA = (G <= 4) ? 4 : 2, MA = 4;
   const int ncn = (cn_total + NA - 1) / NA, ncm = (cm_block + MA - 1) / MA;
   const int tiles = ncn * ncm;
-  int ks = (int)blockDim.x / tiles;
+  int ks = g.nthr / tiles;
   if (ks < 1) ks = 1;
   if (ks > ks_max) ks = ks_max;
   while (ks > 1 && tr % ks) --ks;
   const int rows_per = tr / ks;
-  for (int item = threadIdx.x; item < tiles * ks; item += blockDim.x) {
+  for (int item = g.tid; item < tiles * ks; item += g.nthr) {
     const int split = item / tiles, tt = item - split * tiles;
     const int cm = tt % ncm, cn = tt / ncm;
     int nl[NA], ml[MA];
@@ -604,7 +629,7 @@ struct BwdWorkspace {
 
 // one pass of the transposed W1 GEMM over output channels [ob, ob + width) with NCHT channels per thread -> global
 template <int DIM, int NCHT>
-__device__ __forceinline__ void dx_pass(const float* __restrict__ tD, int sD, const FusedPlan& p, const WRef& w1,
+__device__ __forceinline__ void dx_pass(const Grp& g, const float* __restrict__ tD, int sD, const FusedPlan& p, const WRef& w1,
                                         float* grad_x, int64_t row0, int valid, int cin, int ob, int width, int c, int rg,
                                         bool active) {
   constexpr int B = Alg<DIM>::B, RB = FCfg<DIM>::RB;
@@ -616,7 +641,7 @@ __device__ __forceinline__ void dx_pass(const float* __restrict__ tD, int sD, co
 #pragma unroll
       for (int i = 0; i < B; ++i) acc[j][a][i] = 0.f;
   const bool act = active && c < width;
-  gemm_run<DIM, true, NCHT>(acc, tD + rg * RB * sD, sD, w1, act, c, p.nc, ob, width);
+  gemm_run<DIM, true, NCHT>(g, acc, tD + rg * RB * sD, sD, w1, act, c, p.nc, ob, width);
   if (act && grad_x) {
 #pragma unroll
     for (int j = 0; j < RB; ++j) {
@@ -639,29 +664,34 @@ __global__ void __launch_bounds__(256, 1) block_bwd_kernel(csmpn_block_desc d, c
   using A = Alg<DIM>;
   constexpr int B = A::B, G = A::G, P = A::P, NCH = FCfg<DIM>::NCH;
   extern __shared__ __align__(128) float smem[];
-  float* t1 = smem;                       // o -> y2 ; later sender rows of the gather
+  Grp g;
+  g.id = threadIdx.x / p.threads;
+  g.tid = threadIdx.x - g.id * p.threads;
+  g.nthr = p.threads;
+  float* wsm = smem;                                  // weights (shared by the groups)
+  float* t1 = smem + p.wbuf + g.id * p.tile_words;    // o -> y2 ; later sender rows of the gather
   float* t2 = t1 + p.tr * p.s1;           // dy -> d ; later y1 again
   float* t3 = t2 + p.tr * p.s2;           // xr -> dxr ; later the input row x0 (wide)
   float* t4 = t3 + p.tr * p.s3;           // y1 -> dy2 -> dy1
-  float* wsm = t4 + p.tr * p.s2;
-  float* nu_s = wsm + p.wbuf;             // [tr][C]
+  float* nu_s = t4 + p.tr * p.s2;         // [tr][C]
   float* dt_s = nu_s + p.tr * d.c;        // [tr][C]
   float* mu_s = dt_s + p.tr * d.c;        // [tr] 1/mu
   float* dmu_s = mu_s + p.tr;             // [tr] d loss / d mu / C
   uint64_t* bar = reinterpret_cast<uint64_t*>(dmu_s + p.tr);  // bar[0]: tile inputs, bar[1]: y1 + x0 reload
   const int C = d.c, cin = d.c0 + d.c1 + d.c2;
-  const int c = threadIdx.x % p.nc, rg = threadIdx.x / p.nc;
+  const int c = g.tid % p.nc, rg = g.tid / p.nc;
   const bool active = rg < p.rg;
-  const int n_e = threadIdx.x % C, rl = threadIdx.x / C;
+  const int n_e = g.tid % C, rl = g.tid / C;
   const bool ew = rl < p.ew_rows;
   const int64_t tiles = (d.rows + p.tr - 1) / p.tr;
-  float* my_dw1 = ws.dw1 + (size_t)blockIdx.x * p.ks * C * cin * G;
-  float* my_dwr = ws.dwr + (size_t)blockIdx.x * p.ks * C * C * G;
-  float* my_dwl = ws.dwl + (size_t)blockIdx.x * p.ks * C * C * G;
+  const size_t slot = (size_t)blockIdx.x * p.ng + g.id;  // private weight-gradient accumulators of this group
+  float* my_dw1 = ws.dw1 + slot * p.ks * C * cin * G;
+  float* my_dwr = ws.dwr + slot * p.ks * C * C * G;
+  float* my_dwl = ws.dwl + slot * p.ks * C * C * G;
   WRef w1, wr, wl;
   setup_weights<DIM>(d, p, wsm, w1, wr, wl);
   if (!p.resident) { w1.kchunk = p.kt1; wr.kchunk = p.ktc; wl.kchunk = p.ktc; }
-  if (threadIdx.x == 0) { mbar_init(bar, 1); mbar_init(bar + 1, 1); }
+  if (g.tid == 0) { mbar_init(bar, 1); mbar_init(bar + 1, 1); }
   ChanParams<DIM> cp;
   cp.load(d, n_e, ew);
   // parameter-gradient accumulators of the channel this thread owns (registers, whole kernel)
@@ -672,25 +702,26 @@ __global__ void __launch_bounds__(256, 1) block_bwd_kernel(csmpn_block_desc d, c
   for (int g = 0; g < G; ++g) { g_na[g] = 0.f; g_sa[g] = 0.f; g_sb[g] = 0.f; }
   uint32_t phase = 0;
   const size_t rowsz = (size_t)C * B;
+  __syncthreads();  // resident weights staged, barriers initialised
 
-  for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+  for (int64_t tile = (int64_t)blockIdx.x * p.ng + g.id; tile < tiles; tile += (int64_t)gridDim.x * p.ng) {
     const int64_t row0 = tile * p.tr;
     const int valid = (d.rows - row0) < p.tr ? (int)(d.rows - row0) : p.tr;
     fence_proxy_async();
-    __syncthreads();
+    g.sync();
     // ---- TMA: o -> t1, dy -> t2, xr -> t3, y1 -> t4
     {
       RowPiece pc[4] = {RowPiece{t1, p.s1, 0, d.save_o, C, nullptr}, RowPiece{t2, p.s2, 0, gr.grad_y, C, nullptr},
                         RowPiece{t3, p.s3, 0, d.save_xr, C, nullptr}, RowPiece{t4, p.s2, 0, d.save_y1, C, nullptr}};
-      tma_issue_pieces<DIM, 4>(pc, 4, row0, valid, bar);
+      tma_issue_pieces<DIM, 4>(g, pc, 4, row0, valid, bar);
     }
     mbar_wait(bar, phase);
     if (valid < p.tr) {
-      zero_tail_rows(t1, p.s1, (int)rowsz, p.tr, valid);
-      zero_tail_rows(t2, p.s2, (int)rowsz, p.tr, valid);
-      zero_tail_rows(t3, p.s3, (int)rowsz, p.tr, valid);
-      zero_tail_rows(t4, p.s2, (int)rowsz, p.tr, valid);
-      __syncthreads();
+      zero_tail_rows(g, t1, p.s1, (int)rowsz, p.tr, valid);
+      zero_tail_rows(g, t2, p.s2, (int)rowsz, p.tr, valid);
+      zero_tail_rows(g, t3, p.s3, (int)rowsz, p.tr, valid);
+      zero_tail_rows(g, t4, p.s2, (int)rowsz, p.tr, valid);
+      g.sync();
     }
     // ---- layer-norm statistics
     if (ew) {
@@ -705,19 +736,19 @@ __global__ void __launch_bounds__(256, 1) block_bwd_kernel(csmpn_block_desc d, c
         dt_s[r * C + n_e] = cp.la * dot;
       }
     }
-    __syncthreads();
-    for (int r = threadIdx.x >> 5; r < p.tr; r += (int)(blockDim.x >> 5)) {
+    g.sync();
+    for (int r = g.tid >> 5; r < p.tr; r += (g.nthr >> 5)) {
       float s1 = 0.f, s2 = 0.f;
-      for (int n = threadIdx.x & 31; n < C; n += 32) { s1 += nu_s[r * C + n]; s2 += dt_s[r * C + n]; }
+      for (int n = g.tid & 31; n < C; n += 32) { s1 += nu_s[r * C + n]; s2 += dt_s[r * C + n]; }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
-      if ((threadIdx.x & 31) == 0) {
+      if ((g.tid & 31) == 0) {
         const float inv_mu = 1.f / (s1 / (float)C + kEps);
         mu_s[r] = inv_mu;
         dmu_s[r] = -s2 * inv_mu * inv_mu / (float)C;
       }
     }
-    __syncthreads();
+    g.sync();
     // ---- layer-norm backward -> d (t2); y2 (t1); product + normalisation backward -> dxr (t3), dy2 partial (t4)
     if (ew) {
       for (int r = rl; r < p.tr; r += p.ew_rows) {
@@ -782,8 +813,8 @@ __global__ void __launch_bounds__(256, 1) block_bwd_kernel(csmpn_block_desc d, c
         for (int a = 0; a < NCH; ++a)
 #pragma unroll
           for (int i = 0; i < B; ++i) acc[j][a][i] = 0.f;
-      gemm_run<DIM, true, NCH>(acc, t2 + rg * RB * p.s2, p.s2, wl, active, c, p.nc, 0, C);
-      gemm_run<DIM, true, NCH>(acc, t3 + rg * RB * p.s3, p.s3, wr, active, c, p.nc, 0, C, !p.resident);
+      gemm_run<DIM, true, NCH>(g, acc, t2 + rg * RB * p.s2, p.s2, wl, active, c, p.nc, 0, C);
+      gemm_run<DIM, true, NCH>(g, acc, t3 + rg * RB * p.s3, p.s3, wr, active, c, p.nc, 0, C, !p.resident);
       if (active) {
 #pragma unroll
         for (int a = 0; a < NCH; ++a) {
@@ -801,22 +832,22 @@ __global__ void __launch_bounds__(256, 1) block_bwd_kernel(csmpn_block_desc d, c
         }
       }
     }
-    dw_tile<DIM>(t2, p.s2, C, t1, p.s1, C, 0, C, p.tr, p.ks, my_dwl);
-    dw_tile<DIM>(t3, p.s3, C, t1, p.s1, C, 0, C, p.tr, p.ks, my_dwr);
+    dw_tile<DIM>(g, t2, p.s2, C, t1, p.s1, C, 0, C, p.tr, p.ks, my_dwl);
+    dw_tile<DIM>(g, t3, p.s3, C, t1, p.s1, C, 0, C, p.tr, p.ks, my_dwr);
     // ---- TMA: y1 -> t2 again, the input row x0 -> t3 (sender rows through t1)
     fence_proxy_async();
-    __syncthreads();  // generic accesses to t1, t2, t3 are done
+    g.sync();  // generic accesses to t1, t2, t3 are done
     {
       RowPiece pc[4];
       pc[0] = RowPiece{t2, p.s2, 0, d.save_y1, C, nullptr};
       const int np = 1 + input_pieces<DIM>(pc + 1, t3, p.s3, t1, p.s1, d);
-      tma_issue_pieces<DIM, 4>(pc, np, row0, valid, bar + 1);
+      tma_issue_pieces<DIM, 4>(g, pc, np, row0, valid, bar + 1);
     }
     mbar_wait(bar + 1, phase);
     phase ^= 1;
-    finish_input_rows<DIM>(t3, p.s3, t1, p.s1, d, p.tr, valid);
-    if (valid < p.tr) zero_tail_rows(t2, p.s2, (int)rowsz, p.tr, valid);
-    __syncthreads();
+    finish_input_rows<DIM>(g, t3, p.s3, t1, p.s1, d, p.tr, valid);
+    if (valid < p.tr) zero_tail_rows(g, t2, p.s2, (int)rowsz, p.tr, valid);
+    g.sync();
     // ---- MVSiLU backward: dy1 -> t4
     if (ew) {
       for (int r = rl; r < p.tr; r += p.ew_rows) {
@@ -849,13 +880,13 @@ __global__ void __launch_bounds__(256, 1) block_bwd_kernel(csmpn_block_desc d, c
     for (int ob = 0; ob < cin; ob += C) {
       const int width = (cin - ob) < C ? (cin - ob) : C;
       if (width > (NCH - 1) * p.nc) {
-        dx_pass<DIM, NCH>(t4, p.s2, p, w1, gr.grad_x, row0, valid, cin, ob, width, c, rg, active);
+        dx_pass<DIM, NCH>(g, t4, p.s2, p, w1, gr.grad_x, row0, valid, cin, ob, width, c, rg, active);
       } else {
         for (int o2 = 0; o2 < width; o2 += p.nc)
-          dx_pass<DIM, 1>(t4, p.s2, p, w1, gr.grad_x, row0, valid, cin, ob + o2, (width - o2) < p.nc ? (width - o2) : p.nc, c,
+          dx_pass<DIM, 1>(g, t4, p.s2, p, w1, gr.grad_x, row0, valid, cin, ob + o2, (width - o2) < p.nc ? (width - o2) : p.nc, c,
                           rg, active);
       }
-      dw_tile<DIM>(t4, p.s2, C, t3 + ob * B, p.s3, width, ob, cin, p.tr, p.ks, my_dw1);
+      dw_tile<DIM>(g, t4, p.s2, C, t3 + ob * B, p.s3, width, ob, cin, p.tr, p.ks, my_dw1);
     }
   }
   // ---- fixed-order reduction of the per-thread parameter gradients over the row lanes of the CTA
@@ -864,12 +895,13 @@ __global__ void __launch_bounds__(256, 1) block_bwd_kernel(csmpn_block_desc d, c
     float* red = smem;  // [threads]
     float* out = ws.small + (size_t)blockIdx.x * C * (P + 3 * G + 3);
     auto reduce_one = [&](float v, int offset, int Q, int q) {
-      red[threadIdx.x] = v;
+      red[threadIdx.x] = ew ? v : 0.f;
       __syncthreads();
-      if (rl == 0 && ew) {
+      if (threadIdx.x < C) {  // thread n sums the row lanes of every group in a fixed order
         float s = 0.f;
-        for (int k = 0; k < p.ew_rows; ++k) s += red[k * C + n_e];
-        out[offset + n_e * Q + q] = s;
+        for (int gi = 0; gi < p.ng; ++gi)
+          for (int k = 0; k < p.ew_rows; ++k) s += red[gi * p.threads + k * C + threadIdx.x];
+        out[offset + threadIdx.x * Q + q] = s;
       }
       __syncthreads();
     };
@@ -924,7 +956,7 @@ int launch_block_fwd(const csmpn_block_desc& d, cudaStream_t s) {
     CSMPN_CUDA_TRY(cudaFuncSetAttribute(block_fwd_kernel<DIM>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem + 1024));
     attr_set = true;
   }
-  block_fwd_kernel<DIM><<<p.grid, p.threads, p.smem, s>>>(d, p);
+  block_fwd_kernel<DIM><<<p.grid, p.threads * p.ng, p.smem, s>>>(d, p);
   CSMPN_LAUNCH_CHECK("block_fwd");
   return CSMPN_OK;
 }
@@ -936,7 +968,7 @@ int64_t block_bwd_ws_bytes(const csmpn_block_desc& d, FusedPlan* pp) {
   if (pp) *pp = p;
   constexpr int G = Alg<DIM>::G, P = Alg<DIM>::P;
   const int64_t c = d.c, cin = d.c0 + d.c1 + d.c2;
-  int64_t words = (int64_t)p.grid * ((int64_t)p.ks * (c * cin * G + 2 * c * c * G) + c * (P + 3 * G + 3));
+  int64_t words = (int64_t)p.grid * ((int64_t)p.ng * p.ks * (c * cin * G + 2 * c * c * G) + c * (P + 3 * G + 3));
   return words * 4;
 }
 
@@ -950,9 +982,10 @@ int launch_block_bwd(const csmpn_block_desc& d, const csmpn_block_grads& g, void
   const int c = d.c, cin = d.c0 + d.c1 + d.c2;
   BwdWorkspace ws;
   ws.dw1 = (float*)workspace;
-  ws.dwr = ws.dw1 + (size_t)p.grid * p.ks * c * cin * G;
-  ws.dwl = ws.dwr + (size_t)p.grid * p.ks * c * c * G;
-  ws.small = ws.dwl + (size_t)p.grid * p.ks * c * c * G;
+  const size_t slots = (size_t)p.grid * p.ng * p.ks;
+  ws.dwr = ws.dw1 + slots * c * cin * G;
+  ws.dwl = ws.dwr + slots * c * c * G;
+  ws.small = ws.dwl + slots * c * c * G;
   const size_t dw_bytes = (size_t)((char*)ws.small - (char*)workspace);
   CSMPN_CUDA_TRY(cudaMemsetAsync(workspace, 0, dw_bytes, s));  // the small partials are written, not accumulated
   static bool attr_set = false;
@@ -960,7 +993,7 @@ int launch_block_bwd(const csmpn_block_desc& d, const csmpn_block_grads& g, void
     CSMPN_CUDA_TRY(cudaFuncSetAttribute(block_bwd_kernel<DIM>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem + 1024));
     attr_set = true;
   }
-  block_bwd_kernel<DIM><<<p.grid, p.threads, p.smem, s>>>(d, g, p, ws);
+  block_bwd_kernel<DIM><<<p.grid, p.threads * p.ng, p.smem, s>>>(d, g, p, ws);
   CSMPN_LAUNCH_CHECK("block_bwd");
   const int small_words = c * (P + 3 * G + 3);
   FinalSegs fs;
@@ -968,9 +1001,9 @@ int launch_block_bwd(const csmpn_block_desc& d, const csmpn_block_grads& g, void
   auto add = [&](const float* in, float* out, int n, int parts, int64_t stride) {
     fs.s[k].in = in; fs.s[k].out = out; fs.s[k].n = n; fs.s[k].parts = parts; fs.s[k].stride = stride; ++k;
   };
-  add(ws.dw1, g.g_w1, c * cin * G, p.grid * p.ks, (int64_t)c * cin * G);
-  add(ws.dwr, g.g_wr, c * c * G, p.grid * p.ks, (int64_t)c * c * G);
-  add(ws.dwl, g.g_wl, c * c * G, p.grid * p.ks, (int64_t)c * c * G);
+  add(ws.dw1, g.g_w1, c * cin * G, (int)slots, (int64_t)c * cin * G);
+  add(ws.dwr, g.g_wr, c * c * G, (int)slots, (int64_t)c * c * G);
+  add(ws.dwl, g.g_wl, c * c * G, (int)slots, (int64_t)c * c * G);
   const float* sm = ws.small;
   add(sm, g.g_wp, c * P, p.grid, small_words); sm += c * P;
   add(sm, g.g_na, c * G, p.grid, small_words); sm += c * G;
