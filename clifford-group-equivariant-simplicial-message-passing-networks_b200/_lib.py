@@ -55,6 +55,19 @@ def _declare(lib):
         "csmpn_segment_reduce": (c_int, [P, P, P, P, i64, i64, i32, P]),
         "csmpn_scatter_diff": (c_int, [P, P, P, P, P, P, i64, i64, i32, P]),
         "csmpn_segment_expand": (c_int, [P, P, P, P, i64, i64, i32, P]),
+        # fused CEMLP block / sorted-order EGCL helpers (descriptor structs are passed by reference)
+        "csmpn_block_fwd": (c_int, [i32, P, P]),
+        "csmpn_block_bwd_workspace": (i64, [i32, P]),
+        "csmpn_block_bwd": (c_int, [i32, P, P, P, i64, P]),
+        "csmpn_csr_sorted_indices": (c_int, [P, P, P, P, P, i64, P]),
+        "csmpn_csr_rank": (c_int, [P, P, i64, P]),
+        "csmpn_segment_reduce_sorted": (c_int, [P, P, P, i64, i64, i32, P]),
+        "csmpn_segment_expand_sorted": (c_int, [P, P, P, P, i64, i64, i32, P]),
+        "csmpn_scatter_diff_sorted": (c_int, [P, i64, P, P, P, P, P, i64, i64, i32, P]),
+        "csmpn_scatter_rows": (c_int, [P, i64, i64, P, P, i64, i64, P]),
+        # simplicial lifting
+        "csmpn_lift_count": (c_int, [P, P, P, P, P, P]),
+        "csmpn_lift_fill": (c_int, [P, P, P, i64, P, P, P, P, P]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(lib, name)

@@ -1,0 +1,135 @@
+"""Batched simplicial lifting on the GPU: Python side of csrc/lift.cu (C ABI: csmpn_lift_count / csmpn_lift_fill).
+
+One call lifts a whole batch of complexes and returns them already collated (node offsets added, ``edge_index``
+concatenated) -- what the reference obtains by running ``SimplicialTransform`` per sample on the CPU
+(csmpn/data/modules/simplicial_data.py:40-103) and collating with PyG's DataLoader.  No CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes
+from ctypes import c_double, c_int32, c_int64, c_void_p
+
+import torch
+
+from ..._lib import CsmpnError, check, lib, ptr, require_cuda, stream_ptr
+
+LIFT_RIPS, LIFT_CLIQUE, LIFT_FACETS, LIFT_MOTION = 0, 1, 2, 3
+MAX_VERTICES = 32
+
+
+class LiftDesc(ctypes.Structure):
+    _fields_ = [
+        ("mode", c_int32), ("n_complexes", c_int32), ("max_dim", c_int32), ("point_dim", c_int32),
+        ("facet_size", c_int32), ("reserved", c_int32),
+        ("max_edge_length", c_double), ("n_pairs", c_int64),
+        ("vptr", c_void_p), ("points", c_void_p), ("pairs", c_void_p), ("pptr", c_void_p), ("facets", c_void_p),
+        ("fptr", c_void_p),
+    ]
+
+
+class LiftedBatch:
+    """Collated lift of ``n_complexes`` complexes.
+
+    edge_index [2, E] int64 (global simplex ids; per complex the blocks 0_0,0_1,1_0,1_1,1_2,2_1 in that order),
+    x_ind [N, 3] float32 (LOCAL vertex ids, zero padded), node_types [N] int64, batch [N] int64 (complex id per
+    simplex = PyG's ``x_ind_batch`` / ``batch``), node_ptr / pair_ptr [n_complexes + 1] int64 (``ptr`` vectors),
+    counts [n_complexes, 2] int32 (edges, triangles), n_vertices [n_complexes] int32.
+    """
+
+    def __init__(self, **kw):
+        self.__dict__.update(kw)
+
+    @property
+    def num_nodes(self):
+        return int(self.x_ind.shape[0])
+
+    def block_sizes(self, c: int, single: bool):
+        """pair counts of the six adjacency blocks of complex c (host ints)."""
+        n = int(self.n_vertices_host[c])
+        ne, nt = (int(v) for v in self.counts_host[c])
+        b00 = 2 * ne + ((n * (n - 1) - ne) if single else 0)
+        return {"0_0": b00, "0_1": 2 * ne, "1_0": 2 * ne, "1_1": 6 * nt, "1_2": 3 * nt, "2_1": 3 * nt}
+
+
+def _i32(t, device):
+    return t.to(device=device, dtype=torch.int32).contiguous()
+
+
+def lift_batch(mode: int, n_vertices, *, points=None, max_edge_length=0.0, pairs=None, pairs_per_complex=None, facets=None,
+               facets_per_complex=None, dim: int = 2, device=None) -> LiftedBatch:
+    """Lift a batch.  ``n_vertices``: int tensor / list [n_complexes].  mode RIPS: ``points`` [sum n, D] fp32.
+    mode CLIQUE / MOTION: ``pairs`` [2, P] int64 local ids concatenated over complexes + ``pairs_per_complex``.
+    mode FACETS: ``facets`` [F, k] int64 local ids + ``facets_per_complex``."""
+    anchor = points if points is not None else (pairs if pairs is not None else facets)
+    if device is None:
+        device = anchor.device
+    device = torch.device(device)
+    if device.type != "cuda":
+        raise CsmpnError(f"csmpn_b200.lift_batch: expected a CUDA device (got {device}); this package has no CPU path")
+    nv = torch.as_tensor(n_vertices, dtype=torch.int64)
+    ncx = int(nv.numel())
+    if ncx and int(nv.max()) > MAX_VERTICES:
+        raise ValueError(f"lift_batch supports at most {MAX_VERTICES} vertices per complex (got {int(nv.max())})")
+
+    def make_ptr(counts):
+        c = torch.as_tensor(counts, dtype=torch.int64)
+        return _i32(torch.cat([torch.zeros(1, dtype=torch.int64), torch.cumsum(c, 0)]), device)
+
+    d = LiftDesc()
+    d.mode, d.n_complexes, d.max_dim = mode, ncx, dim
+    vptr = make_ptr(nv)
+    d.vptr = vptr.data_ptr()
+    keep = [vptr]
+    if mode == LIFT_RIPS:
+        pts = points.to(device=device, dtype=torch.float32).contiguous()
+        if pts.dim() != 2 or pts.shape[0] != int(nv.sum()):
+            raise ValueError(f"points must be [sum(n_vertices), D]; got {tuple(pts.shape)} for {int(nv.sum())} vertices")
+        d.points, d.point_dim, d.max_edge_length = pts.data_ptr(), pts.shape[1], float(max_edge_length)
+        keep.append(pts)
+    elif mode in (LIFT_CLIQUE, LIFT_MOTION):
+        pr = pairs.to(device=device, dtype=torch.int64).contiguous()
+        if pr.dim() != 2 or pr.shape[0] != 2:
+            raise ValueError(f"pairs must be [2, P]; got {tuple(pr.shape)}")
+        pptr = make_ptr(pairs_per_complex)
+        d.pairs, d.n_pairs, d.pptr = pr.data_ptr(), pr.shape[1], pptr.data_ptr()
+        keep += [pr, pptr]
+        if mode == LIFT_MOTION and ncx and not bool((nv == 31).all()):
+            raise ValueError("the motion template (ManualTransform) has exactly 31 vertices per complex")
+    elif mode == LIFT_FACETS:
+        fc = facets.to(device=device, dtype=torch.int64).contiguous()
+        fptr = make_ptr(facets_per_complex)
+        d.facets, d.facet_size, d.fptr = fc.data_ptr(), fc.shape[1], fptr.data_ptr()
+        keep += [fc, fptr]
+    else:
+        raise ValueError(f"unknown lifting mode {mode}")
+
+    counts = torch.empty((ncx, 2), dtype=torch.int32, device=device)
+    node_ptr = torch.empty(ncx + 1, dtype=torch.int64, device=device)
+    pair_ptr = torch.empty(ncx + 1, dtype=torch.int64, device=device)
+    status = torch.empty(1, dtype=torch.int32, device=device)
+    s = stream_ptr(device)
+    check(lib().csmpn_lift_count(ctypes.byref(d), ptr(counts), ptr(node_ptr), ptr(pair_ptr), ptr(status), s), "lift_count")
+    totals = torch.stack([node_ptr[-1], pair_ptr[-1], status[0].long()]).cpu()  # the one host sync: output sizes
+    n_total, e_total, bad = (int(v) for v in totals)
+    if bad:
+        raise ValueError("lift_batch: a complex has an unsupported vertex count")
+    edge_index = torch.empty((2, e_total), dtype=torch.int64, device=device)
+    x_ind = torch.empty((n_total, 3), dtype=torch.float32, device=device)
+    node_types = torch.empty(n_total, dtype=torch.int64, device=device)
+    batch = torch.empty(n_total, dtype=torch.int64, device=device)
+    check(lib().csmpn_lift_fill(ctypes.byref(d), ptr(node_ptr), ptr(pair_ptr), e_total, ptr(edge_index), ptr(x_ind),
+                                ptr(node_types), ptr(batch), s), "lift_fill")
+    out = LiftedBatch(edge_index=edge_index, x_ind=x_ind, node_types=node_types, batch=batch, node_ptr=node_ptr,
+                      pair_ptr=pair_ptr, counts=counts, n_vertices=vptr[1:] - vptr[:-1], mode=mode, _keep=keep)
+    out.n_vertices_host = nv
+    out._counts_host = None
+    return out
+
+
+def _counts_host(self):
+    if self._counts_host is None:
+        self._counts_host = self.counts.cpu()
+    return self._counts_host
+
+
+LiftedBatch.counts_host = property(_counts_host)

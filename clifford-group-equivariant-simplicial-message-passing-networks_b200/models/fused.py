@@ -43,37 +43,9 @@ class BlockGrads(ctypes.Structure):
     ]
 
 
-_declared = False
-
-
 def _declare():
-    global _declared
-    if _declared:
-        return
-    l = lib()
-    P, i64, i32 = c_void_p, c_int64, ctypes.c_int
-    l.csmpn_block_fwd.restype = ctypes.c_int
-    l.csmpn_block_fwd.argtypes = [i32, POINTER(BlockDesc), P]
-    l.csmpn_block_bwd_workspace.restype = i64
-    l.csmpn_block_bwd_workspace.argtypes = [i32, POINTER(BlockDesc)]
-    l.csmpn_block_bwd.restype = ctypes.c_int
-    l.csmpn_block_bwd.argtypes = [i32, POINTER(BlockDesc), POINTER(BlockGrads), P, i64, P]
-    l.csmpn_csr_sorted_indices.restype = ctypes.c_int
-    l.csmpn_csr_sorted_indices.argtypes = [P, P, P, P, P, i64, P]
-    l.csmpn_csr_rank.restype = ctypes.c_int
-    l.csmpn_csr_rank.argtypes = [P, P, i64, P]
-    l.csmpn_segment_reduce_sorted.restype = ctypes.c_int
-    l.csmpn_segment_reduce_sorted.argtypes = [P, P, P, i64, i64, i32, P]
-    l.csmpn_segment_expand_sorted.restype = ctypes.c_int
-    l.csmpn_segment_expand_sorted.argtypes = [P, P, P, P, i64, i64, i32, P]
-    l.csmpn_scatter_diff_sorted.restype = ctypes.c_int
-    l.csmpn_scatter_diff_sorted.argtypes = [P, i64, P, P, P, P, P, i64, i64, i32, P]
-    l.csmpn_scatter_rows.restype = ctypes.c_int
-    l.csmpn_scatter_rows.argtypes = [P, i64, i64, P, P, i64, i64, P]
-    for name in ("csmpn_block_fwd", "csmpn_block_bwd_workspace", "csmpn_block_bwd", "csmpn_csr_sorted_indices", "csmpn_csr_rank",
-                 "csmpn_segment_reduce_sorted", "csmpn_segment_expand_sorted", "csmpn_scatter_diff_sorted", "csmpn_scatter_rows"):
-        _lib.EXPORTED[name] = True
-    _declared = True
+    """All C entry points are declared in _lib._declare; loading the library is all that is left to do."""
+    lib()
 
 
 FUSED_DIMS = (2, 3, 5)

@@ -222,6 +222,49 @@ int csmpn_scatter_diff_sorted(const float* g, int64_t ld, const int32_t* rowptr_
 int csmpn_scatter_rows(const float* g, int64_t ld, int64_t col0, const int32_t* eid, float* out, int64_t n_rows,
                        int64_t width, csmpn_stream_t stream);
 
+/* ---- simplicial lifting on the GPU ------------------------------------------------------------------------------
+ * Replaces, for a whole batch of complexes in one launch, the reference's per-sample CPU pipeline
+ *   rips_lift (utils.py:106-136) | simplicial_lift (utils.py:151-207) | simplicial_lift_hulls (utils.py:210-248)
+ *   -> generate_indices / generate_features / generate_adjacencies[_single] (utils.py:37-103, 285-388)
+ *   -> SimplicialTransform.add_missing_adj / get_edge / x_ind / node_types (simplicial_data.py:105-175, 218-222)
+ *   and ManualTransform (simplicial_data.py:254-302) for the fixed CMU-motion complex,
+ * followed by the PyG collation of the batch (node offsets added to edge_index, SimplicialComplexData.__cat_dim__,
+ * simplicial_data.py:14-25).  Outputs are bit-exact to the reference, order included.  At most 32 vertices per
+ * complex; complexes of dimension <= 2.
+ *
+ *   mode RIPS    points [n_vertices_total, point_dim] fp32; edge iff Euclidean distance (double) <= max_edge_length;
+ *                clique complex up to max_dim; adjacency of generate_adjacencies_single (extra 0_0 pairs)
+ *   mode CLIQUE  pairs [2, n_pairs] int64 LOCAL vertex ids of an (un)directed graph, pptr [n_complexes+1]; clique
+ *                complex up to triangles; adjacency of generate_adjacencies (no extra pairs)
+ *   mode FACETS  facets [n_facets_total, facet_size] int64 local vertex ids (Qhull simplices), fptr [n_complexes+1];
+ *                every <= max_dim face of every facet; adjacency of generate_adjacencies_single
+ *   mode MOTION  pairs = the skeleton 0-0 pairs of every complex (31 vertices each); 12 edges, 4 triangles and the
+ *                96 literal pairs of ManualTransform are appended
+ * vptr [n_complexes+1]: first vertex of each complex (vertex counts).  All pointers are device pointers.           */
+enum csmpn_lift_mode { CSMPN_LIFT_RIPS = 0, CSMPN_LIFT_CLIQUE = 1, CSMPN_LIFT_FACETS = 2, CSMPN_LIFT_MOTION = 3 };
+
+typedef struct csmpn_lift_desc {
+  int32_t mode, n_complexes, max_dim, point_dim, facet_size, reserved;
+  double max_edge_length;
+  int64_t n_pairs;
+  const int32_t* vptr;
+  const float* points;
+  const int64_t* pairs;
+  const int32_t* pptr;
+  const int64_t* facets;
+  const int32_t* fptr;
+} csmpn_lift_desc;
+
+/* Pass 1: counts [n_complexes, 2] = (edges, triangles) of every complex; node_ptr / pair_ptr [n_complexes+1] =
+ * exclusive prefix sums of simplices / adjacency pairs (last entry = batch totals, which the caller reads back to
+ * size the outputs); *status (device int32) is set non-zero if a complex has more than 32 vertices.               */
+int csmpn_lift_count(const csmpn_lift_desc* desc, int32_t* counts, int64_t* node_ptr, int64_t* pair_ptr, int32_t* status,
+                     csmpn_stream_t stream);
+/* Pass 2: edge_index [2, n_pairs_total] int64 (global ids), x_ind [N, 3] fp32 (local vertex ids, CPython frozenset
+ * order, zero padded), node_types [N] int64 (simplex dimension), batch [N] int64 (complex id).                     */
+int csmpn_lift_fill(const csmpn_lift_desc* desc, const int64_t* node_ptr, const int64_t* pair_ptr, int64_t n_pairs_total,
+                    int64_t* edge_index, float* x_ind, int64_t* node_types, int64_t* batch, csmpn_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

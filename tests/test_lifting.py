@@ -1,0 +1,193 @@
+"""Simplicial lifting: (1) the CPU oracle (oracle/lift_ref.py) against the fixtures produced by the reference's own
+utils.py / simplicial_data.py (tests/golden/lifting.pt, made by tests/golden/make_golden.py), (2) the GPU lifter
+(csrc/lift.cu through the C ABI) against both.  Bit-exact: values AND order of every output."""
+import itertools
+
+import pytest
+import torch
+
+from conftest import load_golden
+from oracle import lift_ref as L
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return load_golden("lifting.pt")
+
+
+def oracle_case(name, g):
+    if name in ("nba6", "nba11", "rips9_sparse"):
+        x, adj = L.rips_lift_ref(g["points"].tolist(), 2, g["dis"])
+    elif name.startswith("md17"):
+        x, adj = L.clique_lift_ref(g["points"].shape[0], g["knn_edge_index"])
+    elif name == "hulls8":
+        x, adj = L.hull_faces_lift_ref(8, g["facets"].tolist(), 2)
+    else:
+        return L.motion_manual_ref(g["base_edge_index"])
+    return L.merge_ref(x, adj)
+
+
+CASES = ["nba6", "nba11", "rips9_sparse", "md17_13", "md17_21", "hulls8", "motion"]
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_oracle_matches_reference_fixture(gold, name):
+    ei, x_ind, nt = oracle_case(name, gold[name])
+    assert torch.equal(ei, gold[name]["edge_index"])
+    assert torch.equal(x_ind, gold[name]["x_ind"]) and x_ind.dtype == torch.float32
+    assert torch.equal(nt, gold[name]["node_types"])
+
+
+def test_frozenset_order_known_answers():
+    # not sorted once an id >= 8 appears
+    assert list(frozenset([6, 8])) == [8, 6]
+    assert list(frozenset([7, 8, 9])) == [8, 9, 7]
+
+
+# ------------------------------------------------------------------------------------------------ GPU
+def gpu_lift(name, g, dev):
+    from csmpn_b200.data.modules import lifting as G
+
+    if name in ("nba6", "nba11", "rips9_sparse"):
+        return G.lift_batch(G.LIFT_RIPS, [g["points"].shape[0]], points=g["points"].to(dev), max_edge_length=g["dis"])
+    if name.startswith("md17"):
+        ei = g["knn_edge_index"].to(dev)
+        return G.lift_batch(G.LIFT_CLIQUE, [g["points"].shape[0]], pairs=ei, pairs_per_complex=[ei.shape[1]])
+    if name == "hulls8":
+        f = g["facets"].to(dev)
+        return G.lift_batch(G.LIFT_FACETS, [8], facets=f, facets_per_complex=[f.shape[0]])
+    b = g["base_edge_index"].to(dev)
+    return G.lift_batch(G.LIFT_MOTION, [31], pairs=b, pairs_per_complex=[b.shape[1]])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", CASES)
+def test_gpu_lift_matches_reference_fixture(gold, name):
+    dev = torch.device("cuda:0")
+    lb = gpu_lift(name, gold[name], dev)
+    assert torch.equal(lb.edge_index.cpu(), gold[name]["edge_index"])
+    assert torch.equal(lb.x_ind.cpu(), gold[name]["x_ind"]) and lb.x_ind.dtype == torch.float32
+    assert torch.equal(lb.node_types.cpu(), gold[name]["node_types"])
+    assert int(lb.batch.max()) == 0
+
+
+def _collate_ref(parts):
+    eis, xs, nts, off = [], [], [], 0
+    for ei, x_ind, nt in parts:
+        eis.append(ei + off), xs.append(x_ind), nts.append(nt)
+        off += x_ind.shape[0]
+    return torch.cat(eis, 1), torch.cat(xs, 0), torch.cat(nts, 0)
+
+
+@pytest.mark.gpu
+def test_gpu_lift_batched_ragged_rips_vs_oracle():
+    """100 ragged point clouds (1..32 vertices, radius from 'no edge' to 'complete') in one launch vs the oracle."""
+    from csmpn_b200.data.modules import lifting as G
+
+    dev = torch.device("cuda:0")
+    gen = torch.Generator().manual_seed(3)
+    sizes = [1, 2, 3, 32, 31, 17] + [int(v) for v in torch.randint(4, 14, (58,), generator=gen)]
+    for dis in (0.0, 0.9, 1e4):
+        pts = [torch.randn(n, 3, generator=gen) for n in sizes]
+        if dis == 1e4:   # keep the complete complexes small enough for the pure-Python oracle
+            pts = [p[:12] for p in pts]
+        nv = [p.shape[0] for p in pts]
+        lb = G.lift_batch(G.LIFT_RIPS, nv, points=torch.cat(pts).to(dev), max_edge_length=dis)
+        ref = _collate_ref([L.merge_ref(*L.rips_lift_ref(p.tolist(), 2, dis)) if _has_edges(p, dis)
+                            else _no_edge_ref(p.shape[0]) for p in pts])
+        assert torch.equal(lb.edge_index.cpu(), ref[0]), dis
+        assert torch.equal(lb.x_ind.cpu(), ref[1])
+        assert torch.equal(lb.node_types.cpu(), ref[2])
+        assert lb.node_ptr.cpu().tolist() == [0] + list(itertools.accumulate(int(c[0] + c[1]) + n for c, n in zip(lb.counts.cpu().tolist(), nv)))
+
+
+def _has_edges(p, dis):
+    return p.shape[0] > 1
+
+
+def _no_edge_ref(n):
+    """a single vertex: no adjacency at all (merge_ref cannot concatenate zero blocks)"""
+    x_ind = torch.zeros((n, 3))
+    x_ind[:, 0] = torch.arange(n).float()
+    return torch.zeros((2, 0), dtype=torch.long), x_ind, torch.zeros(n, dtype=torch.long)
+
+
+@pytest.mark.gpu
+def test_gpu_lift_full_32_vertex_complex_properties():
+    """maximum size: complete complex on 32 vertices (496 edges, 4960 triangles) -- closed-form counts, every block
+    sorted the way the reference emits it, incidences consistent with x_ind."""
+    from csmpn_b200.data.modules import lifting as G
+
+    dev = torch.device("cuda:0")
+    pts = torch.randn(32, 2, generator=torch.Generator().manual_seed(0))
+    lb = G.lift_batch(G.LIFT_RIPS, [32], points=pts.to(dev), max_edge_length=1e9)
+    n, ne, nt = 32, 496, 4960
+    assert lb.counts.cpu().tolist() == [[ne, nt]]
+    assert lb.x_ind.shape[0] == n + ne + nt
+    E = 2 * ne + (n * (n - 1) - ne) + 4 * ne + 12 * nt
+    assert lb.edge_index.shape[1] == E
+    ei, x = lb.edge_index.cpu(), lb.x_ind.cpu().long()
+    # block 1_2: each triangle receives its three faces; the face vertex sets are subsets of the triangle's
+    p = 2 * ne + (n * (n - 1) - ne) + 4 * ne + 6 * nt
+    blk = ei[:, p:p + 3 * nt]
+    assert torch.equal(blk[1], (n + ne + torch.arange(nt)).repeat_interleave(3))
+    tri_sets = [set(r.tolist()) for r in x[n + ne:]]
+    for col in range(0, 3 * nt, 97):
+        e, t = int(blk[0, col]), int(blk[1, col]) - n - ne
+        assert set(x[e, :2].tolist()) < tri_sets[t]
+    # block 2_1 is block 1_2 reversed
+    assert torch.equal(ei[:, p + 3 * nt:p + 6 * nt], blk[[1, 0]])
+
+
+@pytest.mark.gpu
+def test_gpu_lift_clique_and_facets_batched_vs_oracle():
+    from csmpn_b200.data.modules import lifting as G
+
+    dev = torch.device("cuda:0")
+    gen = torch.Generator().manual_seed(5)
+    # clique: kNN graphs of 40 random molecules of 5..21 atoms
+    parts, pairs, nv, pp = [], [], [], []
+    for _ in range(40):
+        n = int(torch.randint(5, 22, (1,), generator=gen))
+        ei = L.knn_graph(torch.randn(n, 3, generator=gen), 3)
+        parts.append(L.merge_ref(*L.clique_lift_ref(n, ei)))
+        pairs.append(ei), nv.append(n), pp.append(ei.shape[1])
+    lb = G.lift_batch(G.LIFT_CLIQUE, nv, pairs=torch.cat(pairs, 1).to(dev), pairs_per_complex=pp)
+    ref = _collate_ref(parts)
+    assert torch.equal(lb.edge_index.cpu(), ref[0]) and torch.equal(lb.x_ind.cpu(), ref[1]) and torch.equal(lb.node_types.cpu(), ref[2])
+    assert torch.equal(lb.batch.cpu(), torch.repeat_interleave(torch.arange(40), torch.tensor([p[1].shape[0] for p in parts])))
+    # facets: convex hulls of 8 points in R^5 (Qhull on the host supplies the facets, as in the reference)
+    from scipy.spatial import ConvexHull
+    parts, facets, fp = [], [], []
+    for _ in range(12):
+        f = torch.as_tensor(ConvexHull(torch.randn(8, 5, generator=gen).numpy()).simplices).long()
+        parts.append(L.merge_ref(*L.hull_faces_lift_ref(8, f.tolist(), 2)))
+        facets.append(f), fp.append(f.shape[0])
+    lb = G.lift_batch(G.LIFT_FACETS, [8] * 12, facets=torch.cat(facets).to(dev), facets_per_complex=fp)
+    ref = _collate_ref(parts)
+    assert torch.equal(lb.edge_index.cpu(), ref[0]) and torch.equal(lb.x_ind.cpu(), ref[1]) and torch.equal(lb.node_types.cpu(), ref[2])
+
+
+@pytest.mark.gpu
+def test_gpu_transform_api_matches_reference_fixture(gold):
+    """the reference-facing classes: SimplicialTransform / ManualTransform / rips_lift on single samples"""
+    from csmpn_b200.data.modules import utils as U
+    from csmpn_b200.data.modules.simplicial_data import Data, ManualTransform, SimplicialTransform
+
+    dev = torch.device("cuda:0")
+    g = gold["nba6"]
+    pos = torch.zeros(6, 4, 2)
+    pos[:, 0] = g["points"]
+    d = SimplicialTransform(dim=2, dis=g["dis"], label="nba")(Data(pos=pos.to(dev), vel=torch.randn(6, 4, 2).to(dev),
+                                                                   init_pos=g["points"].to(dev), y=torch.zeros(5, 2, 2)))
+    assert torch.equal(d.edge_index.cpu(), g["edge_index"]) and torch.equal(d.x_ind.cpu(), g["x_ind"])
+    assert d.pos.shape == (41, 4, 2) and torch.equal(d.pos[:6].cpu(), pos) and float(d.pos[6:].abs().max()) == 0.0
+    x_dict, adj = U.rips_lift(Data(init_pos=g["points"].to(dev)), 2, g["dis"])
+    xr, ar = L.rips_lift_ref(g["points"].tolist(), 2, g["dis"])
+    assert all(torch.equal(x_dict[k].cpu(), xr[k]) for k in xr) and set(adj) == set(ar)
+    assert all(torch.equal(adj[k].cpu(), ar[k]) for k in ar)
+    m = gold["motion"]
+    d = ManualTransform()(Data(loc=torch.randn(31, 3).to(dev), vel=torch.randn(31, 3).to(dev), edge_index=m["base_edge_index"].to(dev),
+                               y=torch.zeros(31, 3)))
+    assert torch.equal(d.edge_index.cpu(), m["edge_index"]) and torch.equal(d.x_ind.cpu(), m["x_ind"])
+    assert torch.equal(d.node_types.cpu(), m["node_types"])
