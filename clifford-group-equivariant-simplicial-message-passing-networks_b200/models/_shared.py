@@ -1,0 +1,138 @@
+"""What the four task models of the reference share (csmpn/models/{md17,motion,nba,hulls}_cssmpnn.py), written once.
+
+The reference repeats the same three steps in every model file:
+  embed_simplex_types       simplex dimension -> T-channel scalar multivector per simplex (``node_attr``) and the
+                            concatenated (sender ‖ receiver) version per adjacency pair (``edge_attr``)
+                            (md17_cssmpnn.py:122-133, motion :125-136, nba :113-124, hulls :127-140)
+  embed_simplicial_complex  for every d-simplex: the features of its d+1 vertices under ALL (d+1)! vertex orders,
+                            embedded as grade-1 / grade-0 multivectors, pushed through cl_feature_embedding[d] and
+                            summed over the orders (md17 :85-120, motion :90-123, nba :126-157, hulls :96-125)
+  the layer loop            num_layers x EGCL on ONE graph whose nodes are all simplices (md17 :162-163 ...)
+Here they live in ``SharedSimplicialBase``; the task models only declare their parameters (same names and shapes as
+the reference, so its checkpoints load) and their feature lists / losses.  All heavy lifting runs in the sm_100a
+kernels behind MVLinear / CEMLP / EGCL; the gathers and reductions around them are plain device-side torch indexing.
+"""
+from __future__ import annotations
+
+import itertools
+import math
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+
+class Loss:
+    """Stand-in for engineer.metrics.Loss (engineer/metrics/metrics.py:142-145): mean of the collected values."""
+
+    def __init__(self):
+        self.values = []
+
+    def update(self, v):
+        self.values.append(v.detach())
+
+    def compute(self):
+        return torch.cat([v.reshape(-1) for v in self.values]).mean() if self.values else torch.tensor(float("nan"))
+
+    def reset(self):
+        self.values = []
+
+
+class MetricCollection:
+    """Stand-in for engineer.metrics.MetricCollection (engineer/metrics/metrics.py:92-139)."""
+
+    def __init__(self, metrics):
+        self.metrics = dict(metrics)
+
+    def update(self, **kw):
+        for k, v in kw.items():
+            if k in self.metrics:
+                self.metrics[k].update(v)
+
+    def compute(self):
+        return {k: m.compute() for k, m in self.metrics.items()}
+
+    def reset(self):
+        for m in self.metrics.values():
+            m.reset()
+
+
+def global_mean_pool(x, batch, size=None):
+    """per-graph mean (PyG ``global_mean_pool``: count clamped to >= 1)."""
+    size = int(batch.max()) + 1 if size is None else size
+    out = x.new_zeros((size,) + tuple(x.shape[1:]))
+    out.index_add_(0, batch, x)
+    cnt = torch.bincount(batch, minlength=size).clamp(min=1).to(x.dtype)
+    return out / cnt.reshape((-1,) + (1,) * (x.dim() - 1))
+
+
+_PERMS = {}
+
+
+def vertex_orders(k: int, device):
+    """[(k)!, k] all orders of k vertices, in itertools.permutations order (the order the reference sums over)."""
+    key = (k, str(device))
+    if key not in _PERMS:
+        _PERMS[key] = torch.tensor(list(itertools.permutations(range(k))), device=device)
+    return _PERMS[key]
+
+
+class SharedSimplicialBase(nn.Module):
+    """Shared machinery; subclasses set ``self.algebra, self.max_dim, self.num_node_type, self.layers,
+    self.cl_feature_embedding`` and implement ``vertex_features``."""
+
+    learned_type_embedding = True
+
+    # ---- per-batch index cache (one nonzero per simplex dimension, reused by every step of the forward) ----------
+    def simplex_rows(self, graph):
+        cached = getattr(graph, "_csmpn_rows", None)
+        if cached is None:
+            cached = [torch.nonzero(graph.node_types == d).squeeze(1) for d in range(self.max_dim + 1)]
+            try:
+                graph._csmpn_rows = cached
+            except Exception:
+                pass
+        return cached
+
+    def embed_simplex_types(self, graph):
+        B = self.algebra.n_blades
+        if self.learned_type_embedding:
+            table = self.sim_type_embedding.weight            # [T, T]
+        else:
+            table = torch.eye(self.num_node_type, device=graph.node_types.device)
+        node_attr = torch.zeros((graph.node_types.shape[0], table.shape[1], B), device=table.device, dtype=table.dtype)
+        node_attr[..., 0] = table[graph.node_types]
+        ei = graph.edge_index
+        edge_attr = torch.cat((node_attr[ei[0]], node_attr[ei[1]]), dim=1)
+        return node_attr, edge_attr
+
+    def vertex_features(self, graph, verts):
+        """[rows, k] global vertex ids -> [rows, k * F, B] multivector features (vertex-major channels)."""
+        raise NotImplementedError
+
+    def embed_simplicial_complex(self, graph, out_channels=None):
+        B = self.algebra.n_blades
+        start = graph.x_ind_ptr[:-1][graph.x_ind_batch]
+        simplex_vertices = graph.x_ind.long() + start.unsqueeze(-1)
+        rows = self.simplex_rows(graph)
+        n_out = out_channels if out_channels is not None else self.num_hidden
+        x = torch.zeros((graph.x_ind.shape[0], n_out, B), device=graph.x_ind.device)
+        for d in range(self.max_dim + 1):
+            idx = rows[d]
+            if idx.numel() == 0:
+                continue
+            orders = vertex_orders(d + 1, idx.device)
+            verts = simplex_vertices[idx, : d + 1][:, orders].reshape(-1, d + 1)          # [n_d * (d+1)!, d+1]
+            emb = self.cl_feature_embedding[d](self.vertex_features(graph, verts))
+            emb = emb.reshape(idx.shape[0], math.factorial(d + 1), -1, B).sum(dim=1)
+            x = x.index_copy(0, idx, emb)
+        return x
+
+    def grade1(self, t):
+        """[..., dim] vectors -> grade-1 multivectors"""
+        return self.algebra.embed_grade(t, 1)
+
+    def run_layers(self, x, graph, edge_attr, node_attr):
+        for layer in self.layers:
+            x = layer(x, graph.edge_index, edge_attr, node_attr)
+        return x
