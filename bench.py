@@ -243,6 +243,72 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+
+# ----------------------------------------------------------------------------------------------- full-model train step
+def make_md17_graphs(n_complexes, seed, dev, frames=10, atoms=21):
+    """synthetic MD17-aspirin-shaped samples: positions ~ N(0, 1.5^2), kNN(k=3) graph"""
+    from csmpn_b200.data.modules.simplicial_data import Data
+
+    g = torch.Generator().manual_seed(seed)
+    graphs = []
+    for _ in range(n_complexes):
+        loc = torch.randn(atoms, frames, 3, generator=g) * 1.5
+        d = torch.cdist(loc[:, 0].double(), loc[:, 0].double())
+        d.fill_diagonal_(float("inf"))
+        nbr = torch.argsort(d, dim=1, stable=True)[:, :3]
+        ei = torch.stack([nbr.reshape(-1), torch.arange(atoms).repeat_interleave(3)])
+        graphs.append(Data(loc=loc, vel=torch.randn(atoms, frames, 3, generator=g), edge_index=ei,
+                           charges=torch.randint(1, 9, (atoms,), generator=g).float(),
+                           y=loc + 0.1 * torch.randn(atoms, frames, 3, generator=g)))
+    return graphs
+
+
+def train_leg(dev, world, rank, steps, warmup, lib):
+    """train complexes/s: the md17 model (C=32, 5 layers, 10 frames) on 100 complexes per GPU -- GPU lifting once, then
+    per step forward + backward + flat-bucket gradient all-reduce + Adam."""
+    import torch.distributed as dist
+
+    from csmpn_b200.data.modules.simplicial_data import SimplicialTransform
+    from csmpn_b200.models.md17_cssmpnn import CliffordSharedSimplicialMPNN_md17
+    from csmpn_b200.train_step import DataParallelStep
+
+    ncx = 100
+    graphs = make_md17_graphs(ncx, 2000 + rank, dev)
+    batch = SimplicialTransform(dim=2, dis=2.5, label="md17", molecule_type="aspirin").lift(graphs, device=dev)
+    torch.manual_seed(0)
+    model = CliffordSharedSimplicialMPNN_md17().to(dev)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3, fused=True)
+    step = DataParallelStep(model, opt)
+    loc0 = batch.loc.clone()
+
+    def one():
+        batch.loc = loc0
+        loss, _ = step(batch)
+        return loss
+
+    for _ in range(warmup):
+        one()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    l0 = lib.csmpn_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        loss = one()
+    e1.record()
+    torch.cuda.synchronize()
+    launches = lib.csmpn_launch_count() - l0
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item()) / steps
+    return {"metric": "train complexes/sec (md17 model: Cl(3,0), C=32, 5 layers, 10 frames, Adam)", "value": ncx * world / (ms * 1e-3),
+            "unit": "complexes/s", "ms_per_step": ms, "complexes_per_step_per_gpu": ncx, "simplices_per_gpu": int(batch.x_ind.shape[0]),
+            "pairs_per_gpu": int(batch.edge_index.shape[1]), "params": sum(p.numel() for p in model.parameters()),
+            "gpu_launches_per_step": launches / steps, "final_loss": float(loss)}
+
 # ----------------------------------------------------------------------------------------------- GPU arm
 def run_ours(args):
     import torch.distributed as dist
@@ -335,6 +401,7 @@ def run_ours(args):
     total_ms, launches = timed(step_resident, args.steps, args.warmup)
     clocks = sampler.stop() if rank == 0 else None
     e2e_ms, _ = timed(step_e2e, args.steps, max(3, args.warmup // 2))
+    train = None if args.no_train else train_leg(dev, world, rank, max(3, args.steps // 2), 3, lib)
 
     ms_per_step = total_ms / args.steps
     n_total = N * world  # every rank holds a batch of the same shape (weak scaling); N differs by a few per rank
@@ -376,7 +443,7 @@ def run_ours(args):
                        "parallelism": f"dp{world}" if world > 1 else "single", "path": fused_path_name()},
             "e2e": {"value": e2e_value, "unit": "simplices/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                     "ms_per_step": e2e_ms / args.steps},
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "train": train,
         }
         print(json.dumps(line))
     if world > 1:
@@ -415,6 +482,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="md17", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the full-model train-step leg")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

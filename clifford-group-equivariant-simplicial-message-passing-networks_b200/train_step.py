@@ -1,0 +1,74 @@
+"""Data-parallel train step for the shared simplicial models.
+
+The reference wraps its models in ``DistributedDataParallel`` (csmpn/md17.py:15-20, csmpn/nba.py:15-20) and shards
+samples with ``DistributedSampler`` (csmpn/data/md17.py:143-150); the step order is the trainer's
+(engineer/trainer/trainer.py:204-216): forward -> zero_grad -> backward -> optimizer step.  Complexes are independent,
+so the only exchange is ONE gradient all-reduce (mean) per step.  All parameters of these models together are
+0.8-1.5 MB, i.e. a latency-bound collective: the gradients live in ONE flat fp32 bucket (every ``p.grad`` is a view
+into it), the backward kernels accumulate straight into it, and a single NCCL all-reduce over NVLink covers the model.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+
+def shard_indices(n_samples: int, rank: int, world: int, drop_last: bool = False):
+    """Sample ids of ``rank`` -- DistributedSampler semantics without shuffling: ids rank, rank + world, ...; when
+    ``n_samples`` is not a multiple of ``world`` the list is padded by wrapping around (or truncated with drop_last)
+    so every rank gets the same count (equal counts make the mean of per-rank mean losses the global mean)."""
+    if world <= 0 or not 0 <= rank < world:
+        raise ValueError(f"bad rank/world {rank}/{world}")
+    ids = list(range(n_samples))
+    if drop_last:
+        total = (n_samples // world) * world
+        ids = ids[:total]
+    else:
+        total = -(-n_samples // world) * world
+        if n_samples:
+            while len(ids) < total:
+                ids += ids[: total - len(ids)]
+    return ids[rank:total:world]
+
+
+class FlatGradBucket:
+    """One contiguous fp32 buffer holding every parameter gradient; ``p.grad`` are views into it."""
+
+    def __init__(self, params):
+        self.params = [p for p in params if p.requires_grad]
+        if not self.params:
+            raise ValueError("no trainable parameters")
+        dev, dt = self.params[0].device, self.params[0].dtype
+        if any(p.device != dev or p.dtype != dt for p in self.params):
+            raise ValueError("FlatGradBucket needs all parameters on one device with one dtype")
+        self.numel = sum(p.numel() for p in self.params)
+        self.flat = torch.zeros(self.numel, dtype=dt, device=dev)
+        off = 0
+        for p in self.params:
+            p.grad = self.flat[off: off + p.numel()].view_as(p)
+            off += p.numel()
+
+    def zero(self):
+        self.flat.zero_()
+
+    def all_reduce_mean(self, group=None):
+        """sum over ranks, then divide by the world size (what DDP does)"""
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
+            self.flat.div_(dist.get_world_size(group))
+
+
+class DataParallelStep:
+    """forward -> zero -> backward -> all-reduce(mean) -> optimizer step, on this rank's shard of the batch."""
+
+    def __init__(self, model, optimizer, group=None):
+        self.model, self.optimizer, self.group = model, optimizer, group
+        self.bucket = FlatGradBucket(model.parameters())
+
+    def __call__(self, batch, step: int = 0):
+        loss, out = self.model(batch, step, "train")
+        self.bucket.zero()
+        loss.backward()
+        self.bucket.all_reduce_mean(self.group)
+        self.optimizer.step()
+        return loss, out
