@@ -68,6 +68,9 @@ def _declare(lib):
         # simplicial lifting
         "csmpn_lift_count": (c_int, [P, P, P, P, P, P]),
         "csmpn_lift_fill": (c_int, [P, P, P, i64, P, P, P, P, P]),
+        # tensor-core diagnostics
+        "csmpn_tc_probe": (c_int, [i32, i32, i32, i32, i32, P, P, P, P]),
+        "csmpn_tc_probe_raw": (c_int, [P, i32, P, i32, P, P, P]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(lib, name)

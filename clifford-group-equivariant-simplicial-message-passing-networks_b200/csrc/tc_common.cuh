@@ -1,0 +1,152 @@
+// tcgen05 / TMEM / mbarrier helpers for the tensor-core kernels (sm_100a only; inline PTX, no CUTLASS).
+//
+// Operand layout used by every tensor-core kernel of this library ("plane" layout, no swizzle):
+//   a plane holds a [R rows x Cc channels] fp32 matrix as 16-byte units of 4 consecutive channels,
+//       byte offset of (r, c) = ((c / 4) * R + r) * 16 + (c % 4) * 4
+//   i.e. [Cc/4][R][4].  Eight consecutive rows of one unit column are 128 contiguous bytes = one UMMA core matrix.
+//   The same plane serves
+//     * as a K-major operand (MMA rows = plane rows, K = channels): one K=8 step is two unit columns,
+//       LBO (K direction) = R*16 bytes, SBO (8-row groups) = 128 bytes, start = base + 2*ks*R*16;
+//     * as an MN-major operand (MMA rows = channels, K = plane rows): one K=8 step is eight plane rows,
+//       SBO (groups of 4 channels) = R*16 bytes, LBO (K groups) = 128 bytes, start = base + ks*128.
+//   (canonical SWIZZLE_NONE layouts: K-major ((8,n),2):((1,SBO),LBO), MN-major ((1,n),(8,k)):((X,SBO),(1,LBO)) in
+//   16-byte units.)
+// fp32 accuracy on the TF32 pipe comes from the usual error-compensated split  x = hi + lo  with hi = x with the low
+// 13 mantissa bits cleared (exactly representable in TF32) and three MMAs per product: hi*hi + hi*lo + lo*hi.
+#pragma once
+#include "common.cuh"
+
+namespace csmpn {
+namespace tc {
+
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// ------------------------------------------------------------------------------------------------ mbarrier
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_addr(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+// bulk async copy global -> shared, completion counted on an mbarrier (bytes % 16 == 0, 16-byte aligned both sides)
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_addr(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_addr(bar))
+               : "memory");
+}
+// generic-proxy writes to shared memory -> visible to the async proxy (UMMA operand reads, bulk copies)
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// ------------------------------------------------------------------------------------------------ TMEM
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {  // one full warp; cols = 2^k >= 32
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(dst_smem)), "r"(cols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {  // the allocating warp
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// warp-collective loads: lane l of the warp reads TMEM lane (taddr.lane + l), N consecutive 32-bit columns
+__device__ __forceinline__ void tmem_ld1(uint32_t taddr, float& v) {
+  uint32_t r;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr));
+  v = __uint_as_float(r);
+}
+__device__ __forceinline__ void tmem_ld2(uint32_t taddr, float* v) {
+  uint32_t r0, r1;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(taddr));
+  v[0] = __uint_as_float(r0); v[1] = __uint_as_float(r1);
+}
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, float* v) {
+  uint32_t r0, r1, r2, r3;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+               : "r"(taddr));
+  v[0] = __uint_as_float(r0); v[1] = __uint_as_float(r1); v[2] = __uint_as_float(r2); v[3] = __uint_as_float(r3);
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, const float* v) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(__float_as_uint(v[0])),
+               "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3]))
+               : "memory");
+}
+// TMEM address of (lane, column) relative to an allocation base
+__device__ __forceinline__ uint32_t tmem_at(uint32_t base, uint32_t lane, uint32_t col) { return base + (lane << 16) + col; }
+
+// ------------------------------------------------------------------------------------------------ UMMA descriptors
+// shared-memory matrix descriptor, SWIZZLE_NONE, Blackwell version field = 1
+__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  return d;
+}
+// K-major view of a plane with R rows: K step ks (8 channels)
+__device__ __forceinline__ uint64_t desc_kmajor(uint32_t plane_saddr, uint32_t R, uint32_t ks) {
+  return smem_desc(plane_saddr + 2u * ks * R * 16u, R * 16u, 128u);
+}
+// MN-major view of a plane with R rows: K step ks (8 plane rows), MMA rows start at channel c0 (multiple of 4)
+__device__ __forceinline__ uint64_t desc_mnmajor(uint32_t plane_saddr, uint32_t R, uint32_t ks, uint32_t c0 = 0) {
+  return smem_desc(plane_saddr + (c0 >> 2) * R * 16u + ks * 128u, 128u, R * 16u);
+}
+// instruction descriptor: kind::tf32, fp32 accumulate, dense; a_mn / b_mn = operand is MN-major
+__host__ __device__ constexpr uint32_t idesc_tf32(int M, int N, bool a_mn, bool b_mn) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// D[tmem] (+)= A[smem] * B[smem]; issued by ONE thread
+__device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// all MMAs issued so far by this thread -> one arrival on the mbarrier when they have completed
+__device__ __forceinline__ void mma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_addr(bar)) : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------ split
+__device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+__device__ __forceinline__ void split4(const float4& x, float4& hi, float4& lo) {
+  hi.x = tf32_hi(x.x); hi.y = tf32_hi(x.y); hi.z = tf32_hi(x.z); hi.w = tf32_hi(x.w);
+  lo.x = x.x - hi.x; lo.y = x.y - hi.y; lo.z = x.z - hi.z; lo.w = x.w - hi.w;
+}
+// byte offset of (row r, channel c) in a plane with R rows
+__host__ __device__ constexpr uint32_t plane_off(uint32_t R, uint32_t r, uint32_t c) { return ((c >> 2) * R + r) * 16u + (c & 3u) * 4u; }
+
+}  // namespace tc
+}  // namespace csmpn

@@ -265,6 +265,18 @@ int csmpn_lift_count(const csmpn_lift_desc* desc, int32_t* counts, int64_t* node
 int csmpn_lift_fill(const csmpn_lift_desc* desc, const int64_t* node_ptr, const int64_t* pair_ptr, int64_t n_pairs_total,
                     int64_t* edge_index, float* x_ind, int64_t* node_types, int64_t* batch, csmpn_stream_t stream);
 
+/* ---- tensor-core diagnostics ------------------------------------------------------------------------------------
+ * Single-tile tcgen05 probe (csrc/tc_probe.cu): D = A x B on the TF32 tensor pipe from the shared-memory "plane"
+ * operand layout every tensor-core kernel of this library uses; dumps the [128 lanes, N] TMEM accumulator.
+ * mode 0: A [128,K], B [N,K] (both K-major); mode 1: A [128,K], B [K,N] (B MN-major); mode 2: A [K,M], B [K,N] (both
+ * MN-major, M in {64,128}).  flags: 1 / 2 swap LBO and SBO of A / B (must fail), 4 = hi/lo split with three MMAs. */
+int csmpn_tc_probe(int mode, int M, int N, int K, int flags, const float* A, const float* B, float* dump,
+                   csmpn_stream_t stream);
+/* Raw variant: byte-exact shared-memory images of both operands and explicit descriptor fields (prm16: M, N, a_mn, b_mn,
+ * a_lbo, a_sbo, a_layout, b_lbo, b_sbo, b_layout, ksteps, a_kinc, b_kinc, a_off, b_off, 0), for layout exploration. */
+int csmpn_tc_probe_raw(const float* a_img, int a_words, const float* b_img, int b_words, const uint32_t* prm16,
+                       float* dump, csmpn_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
