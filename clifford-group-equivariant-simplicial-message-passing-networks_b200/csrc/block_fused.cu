@@ -1035,9 +1035,23 @@ inline int check_desc(int dim, const csmpn_block_desc* d) {
 
 }  // namespace csmpn
 
+namespace csmpn {
+// tensor-core engine (tc_block_fwd.cu / tc_block_bwd.cu)
+int tc_block_fwd(int dim, const csmpn_block_desc* d, cudaStream_t stream);
+bool tc_block_supported(int dim, int c_in, int c);
+}  // namespace csmpn
+
 using namespace csmpn;
 
 extern "C" {
+
+int csmpn_block_tc_supported(int dim, int c_in, int c) { return tc_block_supported(dim, c_in, c) ? 1 : 0; }
+
+int64_t csmpn_bpt_floats(int dim, int64_t rows, int channels) {
+  if (dim < 1 || dim > 5 || rows < 0 || channels < 1) return -1;
+  const int64_t cp = (channels + 15) / 16 * 16;
+  return ((rows + 127) / 128) * (int64_t)(1 << dim) * cp * 128;
+}
 
 int csmpn_block_fwd(int dim, const csmpn_block_desc* desc, csmpn_stream_t stream) {
   int st = check_desc(dim, desc);
@@ -1045,6 +1059,7 @@ int csmpn_block_fwd(int dim, const csmpn_block_desc* desc, csmpn_stream_t stream
   if (!desc->y) return CSMPN_ERR_BAD_ARG;
   if (desc->rows == 0) return CSMPN_OK;
   cudaStream_t s = (cudaStream_t)stream;
+  if (desc->engine == 1) return tc_block_fwd(dim, desc, s);
   switch (dim) {
     case 2: return launch_block_fwd<2>(*desc, s);
     case 3: return launch_block_fwd<3>(*desc, s);

@@ -1,0 +1,534 @@
+// Tensor-core forward of one CEMLP block (cegnn_utils.py:180-207) for Euclidean Cl(2,0) / Cl(3,0):
+//
+//   tc_f1_kernel:  x0 (gathered / concatenated API-layout rows, or a BPT tensor) --MVLinear W1--> y1 (+bias, saved)
+//                  --MVSiLU--> y2 (BPT)
+//   tc_f2_kernel:  y2 --linear_right / linear_left--> xr, xl --normalisation, weighted geometric product, 1/sqrt2-->
+//                  o --MVLayerNorm (+ residual)--> y        (xr and o saved for the backward)
+//
+// The three per-grade channel GEMMs run on the 5th-generation tensor cores (tcgen05.mma kind::tf32, accumulators in
+// TMEM) with the error-compensated split x = hi + lo (three MMAs per product) that keeps fp32 accuracy.  One CTA per
+// SM, persistent over 128-row tiles.  Per tile the K dimension is streamed in 8-channel chunks through two
+// shared-memory chunk buffers: chunk q+1 is produced (bulk copies + split pass, or the gathering/transposing
+// producer) while the MMAs of chunk q run.  Blade b of a tile accumulates into TMEM columns [b*Cp, (b+1)*Cp) with the
+// weight image of grade(b), so the [Cout, Cin, B] repeat_interleave'd weight of the reference never exists.
+// The epilogues map one thread to one row (TMEM lane) and four channels at a time.
+#include "tc_block.cuh"
+
+namespace csmpn {
+namespace tcb {
+
+struct FwdArgs {
+  int64_t rows;
+  int tiles;
+  int C, Cp;      // block width, padded to a multiple of 16
+  int cin, kin8;  // input channels of the first linear, padded to a multiple of 8
+  int in_bpt, in_cp;
+  int mode, c0, c1, c2;
+  const float *p0, *p1, *p2;
+  const int32_t *src, *dst, *eid;
+  const float *w1, *b1, *sa, *sb, *wr, *na, *wl, *bl, *wp, *la;
+  float *save_y1, *y2, *save_xr, *save_o, *save_x0;
+  float* y;
+  const float* res;
+  int out_bpt, has_b1;
+};
+
+struct Pipe {
+  uint64_t* load_bar;  // [2] bulk copies of a chunk have landed
+  uint64_t* mma_bar;   // [2] the MMAs that read a chunk buffer have completed
+  uint8_t* bufs;       // 2 x (hi | lo)
+  uint32_t half;       // bytes of hi (or lo) of one chunk buffer
+};
+
+// ---- producer 1: bulk copies of one 8-channel chunk of a BPT tensor (thread 0) ---------------------------------
+template <int B>
+__device__ __forceinline__ void issue_chunk_load(const Pipe& p, int buf, const float* bpt, int cp, int64_t tile, int kc) {
+  uint8_t* hi = p.bufs + (size_t)buf * 2 * p.half;
+  mbar_arrive_expect_tx(&p.load_bar[buf], B * 4096u);
+#pragma unroll 1
+  for (int b = 0; b < B; ++b) {
+    const float* src = bpt + bpt_off(B, cp, tile, b, 2 * kc, 0);
+    bulk_g2s(hi + b * kPS, src, 2048u, &p.load_bar[buf]);
+    bulk_g2s(hi + b * kPS + kKH, src + 512, 2048u, &p.load_bar[buf]);
+  }
+}
+// split pass: hi in place, lo beside it
+template <int B>
+__device__ __forceinline__ void split_chunk(const Pipe& p, int buf) {
+  uint8_t* hi = p.bufs + (size_t)buf * 2 * p.half;
+  uint8_t* lo = hi + p.half;
+  for (int it = threadIdx.x; it < B * 2 * kTile; it += kThreads) {
+    const int r = it & (kTile - 1), kh = (it >> 7) & 1, b = it >> 8;
+    const uint32_t off = b * kPS + kh * kKH + r * 16;
+    const float4 x = *reinterpret_cast<const float4*>(hi + off);
+    float4 h, l;
+    split4(x, h, l);
+    *reinterpret_cast<float4*>(hi + off) = h;
+    *reinterpret_cast<float4*>(lo + off) = l;
+  }
+}
+
+// ---- producer 2: gather / concatenate API-layout rows, transpose to planes, split (all threads) ------------------
+template <int DIM>
+__device__ __forceinline__ void stage_chunk_api(const Pipe& p, int buf, const FwdArgs& a, int64_t row0, int kc) {
+  constexpr int B = Alg<DIM>::B, H = B / 4, PPR = 8 * H;
+  uint8_t* hi = p.bufs + (size_t)buf * 2 * p.half;
+  uint8_t* lo = hi + p.half;
+  for (int it = threadIdx.x; it < kTile * PPR; it += kThreads) {
+    const int r = it / PPR, pc = it - r * PPR;
+    const int cl = pc / H, h = pc - cl * H;
+    const int c = kc * 8 + cl;
+    const int64_t R = row0 + r;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (R < a.rows && c < a.cin) {
+      if (a.mode == 1) {
+        if (c < a.c0) {
+          const int64_t d = a.dst[R], s = a.src[R];
+          const float4 x = __ldg(reinterpret_cast<const float4*>(a.p0 + (d * a.c0 + c) * B + 4 * h));
+          const float4 z = __ldg(reinterpret_cast<const float4*>(a.p0 + (s * a.c0 + c) * B + 4 * h));
+          v = make_float4(x.x - z.x, x.y - z.y, x.z - z.z, x.w - z.w);
+        } else {
+          const int64_t e = a.eid[R];
+          v = __ldg(reinterpret_cast<const float4*>(a.p1 + (e * a.c1 + (c - a.c0)) * B + 4 * h));
+        }
+      } else {
+        if (c < a.c0) v = __ldg(reinterpret_cast<const float4*>(a.p0 + (R * a.c0 + c) * B + 4 * h));
+        else if (c < a.c0 + a.c1) v = __ldg(reinterpret_cast<const float4*>(a.p1 + (R * a.c1 + (c - a.c0)) * B + 4 * h));
+        else v = __ldg(reinterpret_cast<const float4*>(a.p2 + (R * a.c2 + (c - a.c0 - a.c1)) * B + 4 * h));
+      }
+    }
+    float4 hv, lv;
+    split4(v, hv, lv);
+    const uint32_t off = (4 * h) * kPS + (cl >> 2) * kKH + r * 16 + (cl & 3) * 4;
+    *reinterpret_cast<float*>(hi + off) = hv.x;
+    *reinterpret_cast<float*>(hi + off + kPS) = hv.y;
+    *reinterpret_cast<float*>(hi + off + 2 * kPS) = hv.z;
+    *reinterpret_cast<float*>(hi + off + 3 * kPS) = hv.w;
+    *reinterpret_cast<float*>(lo + off) = lv.x;
+    *reinterpret_cast<float*>(lo + off + kPS) = lv.y;
+    *reinterpret_cast<float*>(lo + off + 2 * kPS) = lv.z;
+    *reinterpret_cast<float*>(lo + off + 3 * kPS) = lv.w;
+  }
+}
+// copy of the assembled input rows for the weight-gradient GEMM of the backward: chunk buffer -> BPT (coalesced)
+template <int B>
+__device__ __forceinline__ void save_chunk_bpt(const Pipe& p, int buf, float* dst, int cp, int64_t tile, int kc) {
+  const uint8_t* hi = p.bufs + (size_t)buf * 2 * p.half;
+  const uint8_t* lo = hi + p.half;
+  for (int it = threadIdx.x; it < B * 2 * kTile; it += kThreads) {
+    const int r = it & (kTile - 1), kh = (it >> 7) & 1, b = it >> 8;
+    const uint32_t off = b * kPS + kh * kKH + r * 16;
+    const float4 h = *reinterpret_cast<const float4*>(hi + off);
+    const float4 l = *reinterpret_cast<const float4*>(lo + off);
+    *reinterpret_cast<float4*>(dst + bpt_off(B, cp, tile, b, 2 * kc + kh, r)) = make_float4(h.x + l.x, h.y + l.y, h.z + l.z, h.w + l.w);
+  }
+}
+
+// ---- MMA issue for one chunk (thread 0): nsets weight sets, set s accumulates at column offset s*B*Cp -------------
+template <int DIM>
+__device__ __forceinline__ void issue_chunk_mma(const Pipe& p, int buf, uint32_t tbase, int Cp, int kc, const uint8_t* wimg0,
+                                                uint32_t img_bytes, int nsets, uint32_t set_bytes, uint32_t idesc) {
+  using A = Alg<DIM>;
+  constexpr int B = A::B;
+  const uint32_t hi = smem_addr(p.bufs + (size_t)buf * 2 * p.half), lo = hi + p.half;
+#pragma unroll 1
+  for (int s = 0; s < nsets; ++s) {
+#pragma unroll 1
+    for (int b = 0; b < B; ++b) {
+      const int g = A::grade_of(b);
+      const uint32_t w_hi = smem_addr(wimg0 + (size_t)s * set_bytes + (size_t)(2 * g) * img_bytes);
+      const uint64_t a_hi = chunk_desc(hi, b), a_lo = chunk_desc(lo, b);
+      const uint64_t b_hi = desc_kmajor(w_hi, Cp, kc), b_lo = desc_kmajor(w_hi + img_bytes, Cp, kc);
+      const uint32_t d = tbase + (uint32_t)(s * B + b) * Cp;
+      mma_tf32(d, a_hi, b_hi, idesc, kc > 0);
+      mma_tf32(d, a_hi, b_lo, idesc, 1);
+      mma_tf32(d, a_lo, b_hi, idesc, 1);
+    }
+  }
+  mma_commit(&p.mma_bar[buf]);
+}
+
+// =====================================================================================================================
+// F1: MVLinear (W1) + bias + MVSiLU
+template <int DIM, bool BPT_IN>
+__global__ void __launch_bounds__(kThreads, 1) tc_f1_kernel(FwdArgs a) {
+  using A = Alg<DIM>;
+  constexpr int B = A::B, G = A::G;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int C = a.C, Cp = a.Cp, nk = a.kin8 / 8;
+  Pipe p;
+  p.half = B * kPS;
+  p.bufs = smem;
+  const uint32_t img = (uint32_t)a.kin8 * Cp * 4;
+  uint8_t* wimg = smem + 4 * p.half;
+  float* b1_s = reinterpret_cast<float*>(wimg + (size_t)G * 2 * img);
+  float* sa_s = b1_s + Cp;
+  float* sb_s = sa_s + Cp * G;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sb_s + Cp * G);
+  p.load_bar = bars;
+  p.mma_bar = bars + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+
+  stage_weight_images<DIM, false>(wimg, img, a.w1, C, a.cin, Cp, a.kin8);
+  for (int i = tid; i < Cp; i += kThreads) b1_s[i] = (i < C && a.has_b1) ? a.b1[i] : 0.f;
+  for (int i = tid; i < Cp * G; i += kThreads) {
+    sa_s[i] = (i < C * G) ? a.sa[i] : 0.f;
+    sb_s[i] = (i < C * G) ? a.sb[i] : 0.f;
+  }
+  if (tid == 0) {
+    mbar_init(&p.load_bar[0], 1); mbar_init(&p.load_bar[1], 1);
+    mbar_init(&p.mma_bar[0], 1); mbar_init(&p.mma_bar[1], 1);
+    mbar_fence_init();
+  }
+  const uint32_t tcols = (B * Cp <= 32) ? 32 : (B * Cp <= 64) ? 64 : (B * Cp <= 128) ? 128 : (B * Cp <= 256) ? 256 : 512;
+  if (warp == 0) tmem_alloc(tmem_slot, tcols);
+  fence_async_smem();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tbase = *tmem_slot;
+  const uint32_t idesc = idesc_tf32(kTile, Cp, false, false);
+  const int my_tiles = (a.tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int total_chunks = my_tiles * nk;
+  auto tile_of = [&](int q) { return (int64_t)blockIdx.x + (int64_t)(q / nk) * gridDim.x; };
+
+  int q = 0;       // chunk sequence number of this CTA; chunk q lives in buffer q & 1
+  int loaded = 0;  // thread 0: chunks whose bulk copies have been issued
+  if (BPT_IN && tid == 0) {
+    for (; loaded < 2 && loaded < total_chunks; ++loaded)
+      issue_chunk_load<B>(p, loaded, a.p0, a.in_cp, tile_of(loaded), loaded % nk);
+  }
+  for (int t = 0; t < my_tiles; ++t) {
+    const int64_t tile = (int64_t)blockIdx.x + (int64_t)t * gridDim.x;
+    const int64_t row0 = tile * kTile;
+    for (int kc = 0; kc < nk; ++kc, ++q) {
+      const int buf = q & 1;
+      if (BPT_IN) {
+        mbar_wait(&p.load_bar[buf], (q >> 1) & 1);
+        split_chunk<B>(p, buf);
+      } else {
+        if (q >= 2) mbar_wait(&p.mma_bar[buf], ((q - 2) >> 1) & 1);  // MMAs of chunk q-2 have released this buffer
+        stage_chunk_api<DIM>(p, buf, a, row0, kc);
+      }
+      fence_async_smem();
+      fence_before_sync();
+      __syncthreads();
+      if (!BPT_IN && a.save_x0) save_chunk_bpt<B>(p, buf, a.save_x0, round_up(a.kin8, 16), tile, kc);
+      if (tid == 0) {
+        fence_after_sync();
+        issue_chunk_mma<DIM>(p, buf, tbase, Cp, kc, wimg, img, 1, 0, idesc);
+        if (BPT_IN && loaded == q + 1 && loaded < total_chunks) {
+          // buffer (q+1)&1 was read by the MMAs of chunk q-1: reload it for chunk q+1 as soon as they are done
+          if (q >= 1) mbar_wait(&p.mma_bar[buf ^ 1], ((q - 1) >> 1) & 1);
+          issue_chunk_load<B>(p, buf ^ 1, a.p0, a.in_cp, tile_of(loaded), loaded % nk);
+          ++loaded;
+        }
+      }
+    }
+    // ---- epilogue: all MMAs of this tile have completed
+    mbar_wait(&p.mma_bar[(q - 1) & 1], ((q - 1) >> 1) & 1);
+    fence_after_sync();
+    if (BPT_IN && tid == 0) {  // both chunk buffers are free: prefetch the next tile's first chunks under the epilogue
+      for (; loaded < q + 2 && loaded < total_chunks; ++loaded)
+        issue_chunk_load<B>(p, loaded & 1, a.p0, a.in_cp, tile_of(loaded), loaded % nk);
+    }
+    const int r = (warp & 3) * 32 + lane;
+    const bool row_ok = row0 + r < a.rows;
+    for (int c4 = warp >> 2; c4 < (Cp >> 2); c4 += 4) {
+      float v[B][4];
+#pragma unroll
+      for (int b = 0; b < B; ++b) tmem_ld4(tmem_at(tbase, (warp & 3) * 32, b * Cp + c4 * 4), v[b]);
+      tmem_wait_ld();
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int ch = c4 * 4 + j;
+        float y1[B];
+        const bool ok = row_ok && ch < C;
+#pragma unroll
+        for (int b = 0; b < B; ++b) y1[b] = ok ? v[b][j] : 0.f;
+        if (ok) y1[0] += b1_s[ch];
+#pragma unroll
+        for (int b = 0; b < B; ++b) v[b][j] = y1[b];
+      }
+      if (a.save_y1) {
+#pragma unroll
+        for (int b = 0; b < B; ++b)
+          *reinterpret_cast<float4*>(a.save_y1 + bpt_off(B, Cp, tile, b, c4, r)) = make_float4(v[b][0], v[b][1], v[b][2], v[b][3]);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int ch = c4 * 4 + j;
+        float y1[B], sg[G], inv[G];
+#pragma unroll
+        for (int b = 0; b < B; ++b) y1[b] = v[b][j];
+        silu_gates<DIM>(y1, sa_s + ch * G, sb_s + ch * G, sg, inv);
+#pragma unroll
+        for (int b = 0; b < B; ++b) v[b][j] = y1[b] * sg[A::grade_of(b)];
+      }
+#pragma unroll
+      for (int b = 0; b < B; ++b)
+        *reinterpret_cast<float4*>(a.y2 + bpt_off(B, Cp, tile, b, c4, r)) = make_float4(v[b][0], v[b][1], v[b][2], v[b][3]);
+    }
+    fence_before_sync();  // the next tile's first MMA overwrites the accumulators: ordered by the next __syncthreads
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tbase, tcols);
+}
+
+// =====================================================================================================================
+// F2: linear_right / linear_left + normalisation + weighted geometric product + MVLayerNorm (+ residual)
+template <int DIM>
+__global__ void __launch_bounds__(kThreads, 1) tc_f2_kernel(FwdArgs a) {
+  using A = Alg<DIM>;
+  constexpr int B = A::B, G = A::G, P = A::P;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int C = a.C, Cp = a.Cp, nk = Cp / 8;
+  Pipe p;
+  p.half = B * kPS;
+  p.bufs = smem;
+  const uint32_t img = (uint32_t)Cp * Cp * 4;
+  const uint32_t set_bytes = G * 2 * img;
+  uint8_t* wimg = smem + 4 * p.half;  // set 0: linear_right, set 1: linear_left
+  float* sn_s = reinterpret_cast<float*>(wimg + 2 * (size_t)set_bytes);  // sigmoid(normalization.a) [Cp][G]
+  float* wv_s = sn_s + Cp * G;                                           // path weights [Cp][P]
+  float* bl_s = wv_s + Cp * P;
+  float* la_s = bl_s + Cp;
+  float* rowsum_s = la_s + Cp;                                           // [4][128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(rowsum_s + 4 * kTile);
+  p.load_bar = bars;
+  p.mma_bar = bars + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+
+  stage_weight_images<DIM, false>(wimg, img, a.wr, C, C, Cp, Cp);
+  stage_weight_images<DIM, false>(wimg + set_bytes, img, a.wl, C, C, Cp, Cp);
+  for (int i = tid; i < Cp * G; i += kThreads) sn_s[i] = (i < C * G) ? sigmoidf_(a.na[i]) : 0.f;
+  for (int i = tid; i < Cp * P; i += kThreads) wv_s[i] = (i < C * P) ? a.wp[i] : 0.f;
+  for (int i = tid; i < Cp; i += kThreads) {
+    bl_s[i] = (i < C) ? a.bl[i] : 0.f;
+    la_s[i] = (i < C) ? a.la[i] : 0.f;
+  }
+  if (tid == 0) {
+    mbar_init(&p.load_bar[0], 1); mbar_init(&p.load_bar[1], 1);
+    mbar_init(&p.mma_bar[0], 1); mbar_init(&p.mma_bar[1], 1);
+    mbar_fence_init();
+  }
+  const uint32_t need = 2 * B * Cp;
+  const uint32_t tcols = need <= 32 ? 32 : need <= 64 ? 64 : need <= 128 ? 128 : need <= 256 ? 256 : 512;
+  if (warp == 0) tmem_alloc(tmem_slot, tcols);
+  fence_async_smem();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tbase = *tmem_slot;
+  const uint32_t idesc = idesc_tf32(kTile, Cp, false, false);
+  const int my_tiles = (a.tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int total_chunks = my_tiles * nk;
+  auto tile_of = [&](int q) { return (int64_t)blockIdx.x + (int64_t)(q / nk) * gridDim.x; };
+  const uint32_t col_r = 0, col_l = B * Cp;
+  const uint32_t lane_base = (warp & 3) * 32;
+
+  int q = 0, loaded = 0;
+  if (tid == 0) {
+    for (; loaded < 2 && loaded < total_chunks; ++loaded) issue_chunk_load<B>(p, loaded, a.y2, Cp, tile_of(loaded), loaded % nk);
+  }
+  for (int t = 0; t < my_tiles; ++t) {
+    const int64_t tile = (int64_t)blockIdx.x + (int64_t)t * gridDim.x;
+    const int64_t row0 = tile * kTile;
+    for (int kc = 0; kc < nk; ++kc, ++q) {
+      const int buf = q & 1;
+      mbar_wait(&p.load_bar[buf], (q >> 1) & 1);
+      split_chunk<B>(p, buf);
+      fence_async_smem();
+      fence_before_sync();
+      __syncthreads();
+      if (tid == 0) {
+        fence_after_sync();
+        issue_chunk_mma<DIM>(p, buf, tbase, Cp, kc, wimg, img, 2, set_bytes, idesc);
+        if (loaded == q + 1 && loaded < total_chunks) {
+          if (q >= 1) mbar_wait(&p.mma_bar[buf ^ 1], ((q - 1) >> 1) & 1);
+          issue_chunk_load<B>(p, buf ^ 1, a.y2, Cp, tile_of(loaded), loaded % nk);
+          ++loaded;
+        }
+      }
+    }
+    mbar_wait(&p.mma_bar[(q - 1) & 1], ((q - 1) >> 1) & 1);
+    fence_after_sync();
+    if (tid == 0) {
+      for (; loaded < q + 2 && loaded < total_chunks; ++loaded) issue_chunk_load<B>(p, loaded & 1, a.y2, Cp, tile_of(loaded), loaded % nk);
+    }
+    const int r = lane_base + lane;
+    const bool row_ok = row0 + r < a.rows;
+    // ---- pass 1: per channel normalisation + weighted geometric product; o -> TMEM (over xl); row sum of norms
+    float rs = 0.f;
+    for (int c4 = warp >> 2; c4 < (Cp >> 2); c4 += 4) {
+      float4 y2v[B];
+#pragma unroll
+      for (int b = 0; b < B; ++b) y2v[b] = *reinterpret_cast<const float4*>(a.y2 + bpt_off(B, Cp, tile, b, c4, r));
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int ch = c4 * 4 + j;
+        float xr[B], o[B], y2[B], qv[G], nrm[G], rinv[G];
+#pragma unroll
+        for (int b = 0; b < B; ++b) {
+          tmem_ld1(tmem_at(tbase, lane_base, col_r + b * Cp + ch), xr[b]);
+          tmem_ld1(tmem_at(tbase, lane_base, col_l + b * Cp + ch), o[b]);
+        }
+#pragma unroll
+        for (int b = 0; b < B; ++b) y2[b] = j == 0 ? y2v[b].x : j == 1 ? y2v[b].y : j == 2 ? y2v[b].z : y2v[b].w;
+        tmem_wait_ld();
+        norm_factors<DIM>(xr, sn_s + ch * G, qv, nrm, rinv);
+#pragma unroll
+        for (int b = 0; b < B; ++b) xr[b] *= rinv[A::grade_of(b)];
+        o[0] += bl_s[ch];
+        A::template wgp<false>(y2, xr, wv_s + ch * P, nullptr, o);
+        const bool ok = row_ok && ch < C;
+#pragma unroll
+        for (int b = 0; b < B; ++b) o[b] = ok ? o[b] * kInvSqrt2 : 0.f;
+        if (ok) rs += smooth_abs_sqrt(mv_sumsq<DIM>(o));
+#pragma unroll
+        for (int b = 0; b < B; ++b)
+          asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(tmem_at(tbase, lane_base, col_l + b * Cp + ch)),
+                       "r"(__float_as_uint(o[b]))
+                       : "memory");
+      }
+    }
+    tmem_wait_st();
+    rowsum_s[(warp >> 2) * kTile + r] = rs;
+    __syncthreads();
+    const float inv_mu = 1.f / ((rowsum_s[r] + rowsum_s[kTile + r] + rowsum_s[2 * kTile + r] + rowsum_s[3 * kTile + r]) / (float)C + kEps);
+    // ---- pass 2: saves, MVLayerNorm scale, residual, output
+    for (int c4 = warp >> 2; c4 < (Cp >> 2); c4 += 4) {
+      float o[B][4];
+      if (a.save_xr) {
+#pragma unroll
+        for (int b = 0; b < B; ++b) tmem_ld4(tmem_at(tbase, lane_base, col_r + b * Cp + c4 * 4), o[b]);
+        tmem_wait_ld();
+#pragma unroll
+        for (int b = 0; b < B; ++b) {
+          float4 x = make_float4(o[b][0], o[b][1], o[b][2], o[b][3]);
+          if (!row_ok) x = make_float4(0.f, 0.f, 0.f, 0.f);
+          *reinterpret_cast<float4*>(a.save_xr + bpt_off(B, Cp, tile, b, c4, r)) = x;
+        }
+      }
+#pragma unroll
+      for (int b = 0; b < B; ++b) tmem_ld4(tmem_at(tbase, lane_base, col_l + b * Cp + c4 * 4), o[b]);
+      tmem_wait_ld();
+      if (a.save_o) {
+#pragma unroll
+        for (int b = 0; b < B; ++b)
+          *reinterpret_cast<float4*>(a.save_o + bpt_off(B, Cp, tile, b, c4, r)) = make_float4(o[b][0], o[b][1], o[b][2], o[b][3]);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float sc = la_s[c4 * 4 + j] * inv_mu;
+#pragma unroll
+        for (int b = 0; b < B; ++b) o[b][j] *= sc;
+      }
+      if (a.out_bpt) {
+#pragma unroll
+        for (int b = 0; b < B; ++b)
+          *reinterpret_cast<float4*>(a.y + bpt_off(B, Cp, tile, b, c4, r)) = make_float4(o[b][0], o[b][1], o[b][2], o[b][3]);
+      } else if (row_ok) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int ch = c4 * 4 + j;
+          if (ch >= C) continue;
+          const size_t off = ((size_t)(row0 + r) * C + ch) * B;
+#pragma unroll
+          for (int h = 0; h < B / 4; ++h) {
+            float4 x = make_float4(o[4 * h][j], o[4 * h + 1][j], o[4 * h + 2][j], o[4 * h + 3][j]);
+            if (a.res) {
+              const float4 rv = *reinterpret_cast<const float4*>(a.res + off + 4 * h);
+              x.x += rv.x; x.y += rv.y; x.z += rv.z; x.w += rv.w;
+            }
+            *reinterpret_cast<float4*>(a.y + off + 4 * h) = x;
+          }
+        }
+      }
+    }
+    fence_before_sync();
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tbase, tcols);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+template <int DIM>
+size_t f1_smem(int Cp, int kin8) {
+  constexpr int B = Alg<DIM>::B, G = Alg<DIM>::G;
+  return (size_t)4 * B * kPS + (size_t)G * 2 * kin8 * Cp * 4 + (size_t)Cp * (1 + 2 * G) * 4 + 64;
+}
+template <int DIM>
+size_t f2_smem(int Cp) {
+  constexpr int B = Alg<DIM>::B, G = Alg<DIM>::G, P = Alg<DIM>::P;
+  return (size_t)4 * B * kPS + (size_t)2 * G * 2 * Cp * Cp * 4 + (size_t)Cp * (G + P + 2) * 4 + 4 * kTile * 4 + 64;
+}
+constexpr size_t kSmemMax = 227 * 1024;
+
+template <int DIM>
+bool fwd_supported(int cin, int c) {
+  constexpr int B = Alg<DIM>::B;
+  if (c < 1 || cin < 1) return false;
+  const int Cp = round_up(c, 16), kin8 = round_up(cin, 8);
+  if (2 * B * Cp > 512) return false;
+  return f1_smem<DIM>(Cp, kin8) <= kSmemMax && f2_smem<DIM>(Cp) <= kSmemMax;
+}
+
+template <int DIM>
+int launch_fwd(const csmpn_block_desc& d, cudaStream_t stream) {
+  constexpr int B = Alg<DIM>::B;
+  FwdArgs a;
+  memset(&a, 0, sizeof(a));
+  a.rows = d.rows;
+  a.tiles = (int)((d.rows + kTile - 1) / kTile);
+  a.C = d.c;
+  a.Cp = round_up(d.c, 16);
+  a.cin = d.c0 + d.c1 + d.c2;
+  a.kin8 = round_up(a.cin, 8);
+  a.in_bpt = d.in_bpt;
+  a.in_cp = round_up(a.cin, 16);
+  a.mode = d.mode; a.c0 = d.c0; a.c1 = d.c1; a.c2 = d.c2;
+  a.p0 = d.p0; a.p1 = d.p1; a.p2 = d.p2;
+  a.src = d.src; a.dst = d.dst; a.eid = d.eid;
+  a.w1 = d.w1; a.b1 = d.b1; a.sa = d.sa; a.sb = d.sb; a.wr = d.wr; a.na = d.na; a.wl = d.wl; a.bl = d.bl; a.wp = d.wp; a.la = d.la;
+  a.save_y1 = d.save_y1; a.y2 = d.save_y2; a.save_xr = d.save_xr; a.save_o = d.save_o; a.save_x0 = d.save_x0;
+  a.y = d.y; a.res = d.res; a.out_bpt = d.out_bpt; a.has_b1 = d.has_b1;
+  if (!a.y2 || !a.y) return CSMPN_ERR_BAD_ARG;
+  if (a.in_bpt && (d.mode != 0 || d.c1 || d.c2)) return CSMPN_ERR_BAD_ARG;
+  if (a.out_bpt && d.res) return CSMPN_ERR_BAD_ARG;
+  if (!fwd_supported<DIM>(a.cin, a.C)) return CSMPN_ERR_UNSUPPORTED;
+  if (a.tiles == 0) return CSMPN_OK;
+  const int grid = a.tiles < sm_count_cached() ? a.tiles : sm_count_cached();
+  const size_t s1 = f1_smem<DIM>(a.Cp, a.kin8), s2 = f2_smem<DIM>(a.Cp);
+  if (a.in_bpt) {
+    CSMPN_CUDA_TRY(cudaFuncSetAttribute(tc_f1_kernel<DIM, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s1));
+    tc_f1_kernel<DIM, true><<<grid, kThreads, s1, stream>>>(a);
+  } else {
+    CSMPN_CUDA_TRY(cudaFuncSetAttribute(tc_f1_kernel<DIM, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s1));
+    tc_f1_kernel<DIM, false><<<grid, kThreads, s1, stream>>>(a);
+  }
+  CSMPN_LAUNCH_CHECK("tc_f1_kernel");
+  CSMPN_CUDA_TRY(cudaFuncSetAttribute(tc_f2_kernel<DIM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s2));
+  tc_f2_kernel<DIM><<<grid, kThreads, s2, stream>>>(a);
+  CSMPN_LAUNCH_CHECK("tc_f2_kernel");
+  return CSMPN_OK;
+}
+
+}  // namespace tcb
+
+int tc_block_fwd(int dim, const csmpn_block_desc* d, cudaStream_t stream) {
+  if (dim == 2) return tcb::launch_fwd<2>(*d, stream);
+  if (dim == 3) return tcb::launch_fwd<3>(*d, stream);
+  return CSMPN_ERR_UNSUPPORTED;
+}
+bool tc_block_supported(int dim, int c_in, int c) {
+  if (dim == 2) return tcb::fwd_supported<2>(c_in, c);
+  if (dim == 3) return tcb::fwd_supported<3>(c_in, c);
+  return false;
+}
+
+}  // namespace csmpn

@@ -4,13 +4,13 @@
 //   a plane holds a [R rows x Cc channels] fp32 matrix as 16-byte units of 4 consecutive channels,
 //       byte offset of (r, c) = ((c / 4) * R + r) * 16 + (c % 4) * 4
 //   i.e. [Cc/4][R][4].  Eight consecutive rows of one unit column are 128 contiguous bytes = one UMMA core matrix.
-//   The same plane serves
-//     * as a K-major operand (MMA rows = plane rows, K = channels): one K=8 step is two unit columns,
-//       LBO (K direction) = R*16 bytes, SBO (8-row groups) = 128 bytes, start = base + 2*ks*R*16;
-//     * as an MN-major operand (MMA rows = channels, K = plane rows): one K=8 step is eight plane rows,
-//       SBO (groups of 4 channels) = R*16 bytes, LBO (K groups) = 128 bytes, start = base + ks*128.
-//   (canonical SWIZZLE_NONE layouts: K-major ((8,n),2):((1,SBO),LBO), MN-major ((1,n),(8,k)):((X,SBO),(1,LBO)) in
-//   16-byte units.)
+//   Used as a K-major operand (MMA rows = plane rows, K = channels): one K=8 step is two unit columns,
+//   LBO (K direction) = R*16 bytes, SBO (8-row groups) = 128 bytes, start = base + 2*ks*R*16
+//   (canonical SWIZZLE_NONE K-major layout ((8,n),2):((1,SBO),LBO) in 16-byte units).
+// MN-major TF32 operands (K = plane rows, MMA rows = channels; the weight-gradient GEMMs) only exist in the
+// SWIZZLE_128B_BASE32B layout: 32-channel groups of [rows][128 B], the 32-byte unit index of a row xor-ed with
+// (row & 3); LBO = byte stride between 32-channel groups, SBO = 512 (groups of 4 rows), one K=8 step = 1024 bytes.
+// Every encoding here was pinned on a B200 with tools/tc_probe_raw.py (profiles/r01_tc_probe.log).
 // fp32 accuracy on the TF32 pipe comes from the usual error-compensated split  x = hi + lo  with hi = x with the low
 // 13 mantissa bits cleared (exactly representable in TF32) and three MMAs per product: hi*hi + hi*lo + lo*hi.
 #pragma once
@@ -117,9 +117,14 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes
 __device__ __forceinline__ uint64_t desc_kmajor(uint32_t plane_saddr, uint32_t R, uint32_t ks) {
   return smem_desc(plane_saddr + 2u * ks * R * 16u, R * 16u, 128u);
 }
-// MN-major view of a plane with R rows: K step ks (8 plane rows), MMA rows start at channel c0 (multiple of 4)
-__device__ __forceinline__ uint64_t desc_mnmajor(uint32_t plane_saddr, uint32_t R, uint32_t ks, uint32_t c0 = 0) {
-  return smem_desc(plane_saddr + (c0 >> 2) * R * 16u + ks * 128u, 128u, R * 16u);
+// MN-major TF32 operand: [rows][32 channels] groups in the SWIZZLE_128B_BASE32B layout (base 512-byte aligned),
+// K step ks = rows 8*ks .. 8*ks+7; group_stride = bytes between consecutive 32-channel groups
+__device__ __forceinline__ uint64_t desc_mn32b(uint32_t base_saddr, uint32_t group_stride, uint32_t ks) {
+  return smem_desc(base_saddr + ks * 1024u, group_stride, 512u) | ((uint64_t)1 << 61);
+}
+// byte offset of (row r, channel c < 32) inside one 32-channel group of that layout
+__host__ __device__ constexpr uint32_t mn32b_off(uint32_t r, uint32_t c) {
+  return r * 128u + ((((c >> 3) ^ (r & 3u)) << 5) | ((c & 7u) << 2));
 }
 // instruction descriptor: kind::tf32, fp32 accumulate, dense; a_mn / b_mn = operand is MN-major
 __host__ __device__ constexpr uint32_t idesc_tf32(int M, int N, bool a_mn, bool b_mn) {

@@ -57,8 +57,8 @@ __global__ void __launch_bounds__(128, 1) tc_probe_kernel(const float* __restric
       for (int pass = 0; pass < (split ? 3 : 1); ++pass) {
         const uint8_t* ap = (pass == 2) ? a_lo : a_hi;
         const uint8_t* bp = (pass == 1) ? b_lo : b_hi;
-        uint64_t ad = (mode == 2) ? desc_mnmajor(smem_addr(ap), a_rows, ks) : desc_kmajor(smem_addr(ap), a_rows, ks);
-        uint64_t bd = (mode == 0) ? desc_kmajor(smem_addr(bp), b_rows, ks) : desc_mnmajor(smem_addr(bp), b_rows, ks);
+        uint64_t ad = desc_kmajor(smem_addr(ap), a_rows, ks);
+        uint64_t bd = desc_kmajor(smem_addr(bp), b_rows, ks);
         if (flags & 1) ad = (ad & ~0x3FFF3FFF0000ull) | (((ad >> 16) & 0x3FFF) << 32) | (((ad >> 32) & 0x3FFF) << 16);
         if (flags & 2) bd = (bd & ~0x3FFF3FFF0000ull) | (((bd >> 16) & 0x3FFF) << 32) | (((bd >> 32) & 0x3FFF) << 16);
         mma_tf32(tbase, ad, bd, idesc, acc);
@@ -86,7 +86,7 @@ using namespace csmpn;
 
 extern "C" int csmpn_tc_probe(int mode, int M, int N, int K, int flags, const float* A, const float* Bsrc, float* dump,
                               csmpn_stream_t stream) {
-  if (mode < 0 || mode > 2 || (M != 64 && M != 128) || N < 8 || N > 64 || N % 8 || K < 8 || K > 128 || K % 8)
+  if (mode != 0 || (M != 64 && M != 128) || N < 8 || N > 64 || N % 8 || K < 8 || K > 128 || K % 8)
     return CSMPN_ERR_BAD_ARG;
   if (mode != 2 && M != 128) return CSMPN_ERR_BAD_ARG;
   if (!A || !Bsrc || !dump) return CSMPN_ERR_BAD_ARG;

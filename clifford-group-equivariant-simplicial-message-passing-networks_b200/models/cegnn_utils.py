@@ -241,6 +241,8 @@ class CEMLP(nn.Module):
         from . import fused
 
         if fused.enabled(self.algebra):
+            if x.dim() == 3:
+                return fused.mlp_forward(self.algebra, list(self.layers), x, rows=x.shape[0])
             for layer in self.layers:
                 x = fused.block_forward(self.algebra, layer, x)
             return x

@@ -32,6 +32,8 @@ class BlockDesc(ctypes.Structure):
         ("w1", c_void_p), ("b1", c_void_p), ("sa", c_void_p), ("sb", c_void_p), ("wr", c_void_p), ("na", c_void_p),
         ("wl", c_void_p), ("bl", c_void_p), ("wp", c_void_p), ("la", c_void_p),
         ("y", c_void_p), ("res", c_void_p), ("save_y1", c_void_p), ("save_xr", c_void_p), ("save_o", c_void_p),
+        ("engine", c_int32), ("in_bpt", c_int32), ("out_bpt", c_int32), ("reserved_", c_int32),
+        ("save_y2", c_void_p), ("save_x0", c_void_p),
     ]
 
 
@@ -49,6 +51,22 @@ def _declare():
 
 
 FUSED_DIMS = (2, 3, 5)
+
+
+def tc_enabled() -> bool:
+    """Tensor-core (tcgen05) engine switch: CSMPN_TC=0 forces the FP32 SIMT kernels (tests cross-check the two)."""
+    return os.environ.get("CSMPN_TC", "1") != "0"
+
+
+def tc_supported(dim: int, c_in: int, c: int) -> bool:
+    return tc_enabled() and bool(lib().csmpn_block_tc_supported(dim, c_in, c))
+
+
+def bpt_empty(dim: int, rows: int, channels: int, device, zero: bool = False) -> torch.Tensor:
+    """A blade-plane tile tensor [ceil(rows/128), B, cp/4, 128, 4] (include/csmpn_b200.h, engine 1)."""
+    cp = (channels + 15) // 16 * 16
+    shape = ((rows + 127) // 128, 1 << dim, cp // 4, 128, 4)
+    return (torch.zeros if zero else torch.empty)(shape, dtype=torch.float32, device=device)
 
 
 def available() -> bool:
@@ -210,6 +228,57 @@ class FusedBlockFn(torch.autograd.Function):
         return (None, gsrc[0], gsrc[1], gsrc[2], gres, *pgr)
 
 
+class TcBlockFn(torch.autograd.Function):
+    """One CEMLP block on the tensor-core engine (csrc/tc_block_fwd.cu, tc_block_bwd.cu).
+
+    cfg: dim, mode, sgraph, rows, in_bpt (p0 is a BPT tensor with cfg["c_in"] channels), out_bpt, need_grad.
+    Intermediates and saved tensors are BPT (blade-plane tile) tensors; only the block boundary facing the rest of the
+    model (gathered h / edge_attr, the messages, the layer output and the residual) is in the reference layout."""
+
+    @staticmethod
+    def forward(ctx, cfg, p0, p1, p2, res, w1, b1, sa, sb, wr, na, wl, bl, wp, la):
+        _declare()
+        dim, mode, sgraph = cfg["dim"], cfg["mode"], cfg.get("sgraph")
+        in_bpt, out_bpt = bool(cfg.get("in_bpt")), bool(cfg.get("out_bpt"))
+        srcs = [None if t is None else f32c(t) for t in (p0, p1, p2)]
+        require_cuda(*srcs, what="tensor-core block")
+        B = 1 << dim
+        chans = [cfg["c_in"], 0, 0] if in_bpt else [0 if t is None else t.shape[1] for t in srcs]
+        c = w1.shape[0]
+        cin = sum(chans)
+        if cin != w1.shape[1]:
+            raise ValueError(f"tensor-core block: input channels {chans} do not match weight {tuple(w1.shape)}")
+        rows = cfg["rows"] if in_bpt else (sgraph.csr.n_pairs if mode == 1 else srcs[0].shape[0])
+        params = tuple(None if t is None else f32c(t) for t in (w1, b1, sa, sb, wr, na, wl, bl, wp, la))
+        dev = srcs[0].device
+        y = bpt_empty(dim, rows, c, dev) if out_bpt else torch.empty((rows, c, B), dtype=torch.float32, device=dev)
+        need_grad = cfg["need_grad"]
+        y2 = bpt_empty(dim, rows, c, dev)
+        saves = tuple(bpt_empty(dim, rows, c, dev) for _ in range(3)) if need_grad else None
+        x0 = bpt_empty(dim, rows, cin, dev, zero=True) if (need_grad and not in_bpt) else None
+        resc = None if res is None else f32c(res)
+        d = _fill_desc(dim, mode, srcs, chans, rows, c, params, sgraph, y, resc, saves)
+        d.engine, d.in_bpt, d.out_bpt = 1, int(in_bpt), int(out_bpt)
+        d.save_y2 = y2.data_ptr()
+        d.save_x0 = None if x0 is None else x0.data_ptr()
+        check(lib().csmpn_block_fwd(dim, ctypes.byref(d), stream_ptr(dev)), "block_fwd (tensor-core)")
+        if need_grad:
+            ctx.save_for_backward(*[t for t in srcs if t is not None], *[t for t in params if t is not None], *saves, y2,
+                                  *([] if x0 is None else [x0]))
+            ctx.meta = (dim, mode, sgraph, chans, c, rows, [t is not None for t in srcs], [t is not None for t in params],
+                        res is not None, [None if t is None else t.shape for t in (w1, b1, sa, sb, wr, na, wl, bl, wp, la)],
+                        [None if t is None else t.shape for t in (p0, p1, p2)], in_bpt, out_bpt, x0 is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        return _tc_block_backward(ctx, gy)
+
+
+def _tc_block_backward(ctx, gy):
+    raise NotImplementedError("tensor-core block backward")
+
+
 class SegmentReduceSortedFn(torch.autograd.Function):
     """[E_sorted, W] -> [N, W]; rows of a receiver are contiguous (deterministic, fixed order)."""
 
@@ -238,15 +307,48 @@ def _need_grad(*tensors_and_params):
     return torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors_and_params)
 
 
-def block_forward(algebra, layer, x, p1=None, p2=None, res=None, mode=0, sgraph=None):
-    """Run one CEMLP block (nn.Sequential of the four sub-layers) through the fused kernel."""
-    if not _block_supported(layer) or (x is not None and x.dim() != 3):
+TC_BACKWARD_READY = False  # flipped to True once csrc/tc_block_bwd.cu is bound
+
+
+def _block_uses_tc(algebra, layer, need_grad) -> bool:
+    lin = layer[0]
+    if algebra.dim not in (2, 3) or (need_grad and not TC_BACKWARD_READY):
+        return False
+    return tc_supported(algebra.dim, lin.in_features, lin.out_features)
+
+
+def block_forward(algebra, layer, x, p1=None, p2=None, res=None, mode=0, sgraph=None, bpt_rows=None, out_bpt=False):
+    """Run one CEMLP block (nn.Sequential of the four sub-layers) through the fused kernels.
+
+    bpt_rows: x is a BPT tensor (output of a previous tensor-core block) holding that many rows.
+    out_bpt:  return a BPT tensor (only honoured on the tensor-core engine; the caller checks with is_bpt)."""
+    in_bpt = bpt_rows is not None
+    if not in_bpt and (not _block_supported(layer) or (x is not None and x.dim() != 3)):
         y = x if p1 is None else torch.cat([t for t in (x, p1, p2) if t is not None], dim=1)
         y = layer(y)
         return y if res is None else res + y
     params = _block_params(layer)
-    cfg = {"dim": algebra.dim, "mode": mode, "sgraph": sgraph, "need_grad": _need_grad(x, p1, p2, res, *params)}
+    need_grad = _need_grad(x, p1, p2, res, *params)
+    cfg = {"dim": algebra.dim, "mode": mode, "sgraph": sgraph, "need_grad": need_grad}
+    if in_bpt or _block_uses_tc(algebra, layer, need_grad):
+        cfg.update(in_bpt=in_bpt, out_bpt=out_bpt, rows=bpt_rows, c_in=layer[0].in_features)
+        return TcBlockFn.apply(cfg, x, p1, p2, res, *params)
     return FusedBlockFn.apply(cfg, x, p1, p2, res, *params)
+
+
+def _chain_uses_tc(algebra, blocks, need_grad) -> bool:
+    return all(_block_supported(b) for b in blocks) and all(_block_uses_tc(algebra, b, need_grad) for b in blocks)
+
+
+def mlp_forward(algebra, blocks, x, p1=None, p2=None, res=None, mode=0, sgraph=None, rows=None):
+    """A CEMLP (list of blocks): on the tensor-core engine the tensors between blocks stay in the BPT layout."""
+    need_grad = _need_grad(x, p1, p2, res, *[t for b in blocks for t in _block_params(b)])
+    tc = len(blocks) > 1 and _chain_uses_tc(algebra, blocks, need_grad)
+    u = block_forward(algebra, blocks[0], x, p1, p2, res if len(blocks) == 1 else None, mode=mode, sgraph=sgraph, out_bpt=tc)
+    for k, blk in enumerate(blocks[1:]):
+        last = k == len(blocks) - 2
+        u = block_forward(algebra, blk, u, res=res if last else None, bpt_rows=rows if tc else None, out_bpt=tc and not last)
+    return u
 
 
 def egcl_forward(egcl, h, edge_index, edge_attr=None, node_attr=None):
@@ -263,19 +365,11 @@ def egcl_forward(egcl, h, edge_index, edge_attr=None, node_attr=None):
     sg = sorted_graph(csr)
     h = f32c(h)
     if csr.n_pairs > 0:
-        m = block_forward(alg, blocks_e[0], h, edge_attr, None, None, mode=1, sgraph=sg)
-        for blk in blocks_e[1:]:
-            m = block_forward(alg, blk, m)
+        m = mlp_forward(alg, blocks_e, h, edge_attr, None, None, mode=1, sgraph=sg, rows=csr.n_pairs)
         agg = SegmentReduceSortedFn.apply(m.reshape(csr.n_pairs, -1), sg, egcl.aggr == "mean").reshape(N, -1, B)
     else:
         agg = h.new_zeros((N, egcl.out_features, B))
-    u = block_forward(alg, blocks_n[0], h, agg, node_attr)
-    for k, blk in enumerate(blocks_n[1:]):
-        last = k == len(blocks_n) - 2
-        u = block_forward(alg, blk, u, res=h if (last and egcl.residual) else None)
-    if len(blocks_n) == 1 and egcl.residual:
-        u = h + u
-    return u
+    return mlp_forward(alg, blocks_n, h, agg, node_attr, h if egcl.residual else None, rows=N)
 
 
 # ------------------------------------------------------------------------------------------------- bench helper

@@ -182,6 +182,17 @@ typedef struct csmpn_block_desc {
   float* y;         /* [rows, c, B] */
   const float* res; /* [rows, c, B] or NULL */
   float *save_y1, *save_xr, *save_o;    /* [rows, c, B] each, or all NULL (inference) */
+  /* ---- engine 1: tcgen05 tensor-core kernels (csrc/tc_block_*.cu), Cl(2,0) / Cl(3,0), see csmpn_block_tc_supported.
+   * Intermediates use the blade-plane tile layout "BPT": [ceil(rows/128)][B][cp/4][128][4] fp32 with the channel count
+   * padded to cp = a multiple of 16 (csmpn_bpt_floats); padded rows and channels hold zeros.  With engine 1 the three
+   * save_* tensors are BPT [c], save_y2 (BPT [c], MVSiLU output) is REQUIRED (it is also the scratch between the two
+   * forward kernels), save_x0 (BPT [c_in], zero-initialised by the caller) keeps the assembled input row of a block
+   * whose input is not already BPT, for the weight-gradient GEMM of the backward. */
+  int32_t engine;                       /* 0 = FP32 SIMT kernels (csrc/block_fused.cu), 1 = tensor-core kernels */
+  int32_t in_bpt;                       /* engine 1, mode 0, c1 = c2 = 0: p0 is a BPT [c0] tensor */
+  int32_t out_bpt;                      /* engine 1: y is written as a BPT [c] tensor (res must be NULL) */
+  int32_t reserved_;
+  float *save_y2, *save_x0;
 } csmpn_block_desc;
 
 /* gradients produced by csmpn_block_bwd (all overwritten; parameter gradients reduced deterministically) */
@@ -193,6 +204,10 @@ typedef struct csmpn_block_grads {
 } csmpn_block_grads;
 
 int csmpn_block_fwd(int dim, const csmpn_block_desc* desc, csmpn_stream_t stream);
+/* 1 if the tensor-core engine handles a block of this shape (c_in input channels, width c) in algebra dimension dim */
+int csmpn_block_tc_supported(int dim, int c_in, int c);
+/* number of floats of a BPT tensor with `rows` rows and `channels` channels (padded to a multiple of 16) */
+int64_t csmpn_bpt_floats(int dim, int64_t rows, int channels);
 /* workspace for csmpn_block_bwd (device bytes; zero-initialised by the call itself) */
 int64_t csmpn_block_bwd_workspace(int dim, const csmpn_block_desc* desc);
 int csmpn_block_bwd(int dim, const csmpn_block_desc* desc, const csmpn_block_grads* grads, void* workspace,

@@ -1,0 +1,105 @@
+"""GPU parity of the tensor-core (tcgen05, 3xTF32) CEMLP-block engine: against the CPU oracle (fp32 tolerance of the
+north star: forward rel 1e-5, gradients rel 1e-4) and against the FP32 SIMT engine on the same inputs."""
+import pytest
+import torch
+
+from conftest import assert_close, rel_err
+from oracle import layers_ref as R
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+CASES = [
+    # name, metric, C, T, complexes, simplices/complex, pairs/complex, aggr
+    ("motion", (1, 1, 1), 28, 3, 6, 47, 226, "mean"),
+    ("md17", (1, 1, 1), 32, 3, 4, 87, 527, "sum"),
+    ("nba", (1, 1), 40, 3, 6, 41, 345, "sum"),
+    ("odd_c", (1, 1, 1), 30, 2, 3, 19, 77, "mean"),
+    ("tiny", (1, 1, 1), 8, 3, 1, 5, 3, "sum"),
+    ("one_tile_exact", (1, 1, 1), 16, 3, 1, 128, 256, "mean"),
+]
+
+
+def _mods():
+    from csmpn_b200.algebra.cliffordalgebra import CliffordAlgebra
+    from csmpn_b200.models import cegnn_utils as M
+
+    return CliffordAlgebra, M
+
+
+def _load(module, params):
+    missing, unexpected = module.load_state_dict({k: v for k, v in params.items()}, strict=False)
+    assert not unexpected and all("algebra" in m for m in missing), (missing, unexpected)
+
+
+def _graph(n_cplx, n, e, gen):
+    src = torch.randint(0, n, (n_cplx, e), generator=gen)
+    dst = torch.randint(0, n, (n_cplx, e), generator=gen)
+    off = (torch.arange(n_cplx) * n).unsqueeze(1)
+    return torch.stack([(src + off).reshape(-1), (dst + off).reshape(-1)])
+
+
+def _inputs(case):
+    name, metric, C, T, ncx, n, e, aggr = case
+    gen = torch.Generator().manual_seed(sum(map(ord, name)))
+    ralg = R.RefAlgebra(metric)
+    B = ralg.B
+    params = R.init_egcl_params(ralg, C, T, gen)
+    N = ncx * n
+    h = torch.randn(N, C, B, generator=gen)
+    ei = _graph(ncx, n, e, gen)
+    na = torch.zeros(N, T, B)
+    na[..., 0] = torch.randn(T, T, generator=gen)[torch.randint(0, T, (N,), generator=gen)]
+    ea = torch.cat([na[ei[0]], na[ei[1]]], 1)
+    cot = torch.randn(N, C, B, generator=gen)
+    return ralg, params, h, ei, ea, na, cot
+
+
+def test_tc_engine_is_selected():
+    from csmpn_b200.models import fused
+
+    assert fused.tc_supported(3, 38, 32) and fused.tc_supported(3, 67, 32) and fused.tc_supported(2, 46, 40)
+    assert not fused.tc_supported(5, 28, 28)  # Cl(5,0): 32 blades do not fit the TMEM accumulator budget
+    assert not fused.tc_supported(3, 64, 64)
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+def test_tc_forward_vs_oracle(case, monkeypatch):
+    name, metric, C, T, ncx, n, e, aggr = case
+    CliffordAlgebra, M = _mods()
+    ralg, params, h, ei, ea, na, _ = _inputs(case)
+    yr = R.egcl(ralg, h, ei, ea, na, params, aggr=aggr)
+    alg = CliffordAlgebra(metric).to(DEV)
+    m = M.EGCL(alg, C, C, C, edge_attr_features=2 * T, node_attr_features=T, aggr=aggr).to(DEV)
+    _load(m, params)
+    from csmpn_b200 import _lib
+
+    outs = {}
+    for tc in ("1", "0"):
+        monkeypatch.setenv("CSMPN_TC", tc)
+        n0 = _lib.lib().csmpn_launch_count()
+        with torch.no_grad():
+            outs[tc] = m(h.to(DEV), ei.to(DEV), ea.to(DEV), na.to(DEV)).cpu()
+        outs["launches" + tc] = _lib.lib().csmpn_launch_count() - n0
+    # the tensor-core engine launches two kernels per block (8 per layer) where the SIMT engine launches one
+    assert outs["launches1"] == outs["launches0"] + 4, (outs["launches1"], outs["launches0"])
+    assert_close(outs["1"], yr, 1e-5, f"{name} tensor-core fwd vs oracle")
+    assert_close(outs["1"], outs["0"], 1e-5, f"{name} tensor-core fwd vs SIMT engine")
+
+
+def test_tc_cemlp_dense_rows(monkeypatch):
+    """CEMLP on plain rows (the models' embedding / projection MLPs): rows not a multiple of the 128-row tile."""
+    CliffordAlgebra, M = _mods()
+    gen = torch.Generator().manual_seed(5)
+    ralg = R.RefAlgebra((1, 1, 1))
+    alg = CliffordAlgebra((1, 1, 1)).to(DEV)
+    for cin, c, rows in ((7, 32, 1000), (32, 32, 129), (3, 16, 1)):
+        params = R.init_cemlp_params(ralg, cin, c, c, 2, gen)
+        m = M.CEMLP(alg, cin, c, c, n_layers=2).to(DEV)
+        _load(m, params)
+        x = torch.randn(rows, cin, 8, generator=gen)
+        yr = R.cemlp(ralg, x, params)
+        monkeypatch.setenv("CSMPN_TC", "1")
+        with torch.no_grad():
+            y = m(x.to(DEV))
+        assert_close(y, yr, 1e-5, f"cemlp {cin}->{c} rows={rows}")
