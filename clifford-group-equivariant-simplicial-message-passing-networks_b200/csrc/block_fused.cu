@@ -1038,6 +1038,8 @@ inline int check_desc(int dim, const csmpn_block_desc* d) {
 namespace csmpn {
 // tensor-core engine (tc_block_fwd.cu / tc_block_bwd.cu)
 int tc_block_fwd(int dim, const csmpn_block_desc* d, cudaStream_t stream);
+int tc_block_bwd(int dim, const csmpn_block_desc* d, const csmpn_block_grads* g, void* ws, int64_t bytes, cudaStream_t stream);
+int64_t tc_block_bwd_workspace(int dim, const csmpn_block_desc* d);
 bool tc_block_supported(int dim, int c_in, int c);
 }  // namespace csmpn
 
@@ -1070,6 +1072,7 @@ int csmpn_block_fwd(int dim, const csmpn_block_desc* desc, csmpn_stream_t stream
 
 int64_t csmpn_block_bwd_workspace(int dim, const csmpn_block_desc* desc) {
   if (check_desc(dim, desc)) return -1;
+  if (desc->engine == 1) return tc_block_bwd_workspace(dim, desc);
   switch (dim) {
     case 2: return block_bwd_ws_bytes<2>(*desc, nullptr);
     case 3: return block_bwd_ws_bytes<3>(*desc, nullptr);
@@ -1087,6 +1090,7 @@ int csmpn_block_bwd(int dim, const csmpn_block_desc* desc, const csmpn_block_gra
       !grads->g_wp || !grads->g_la)
     return CSMPN_ERR_BAD_ARG;
   cudaStream_t s = (cudaStream_t)stream;
+  if (desc->engine == 1) return tc_block_bwd(dim, desc, grads, workspace, workspace_bytes, s);
   switch (dim) {
     case 2: return launch_block_bwd<2>(*desc, *grads, workspace, workspace_bytes, s);
     case 3: return launch_block_bwd<3>(*desc, *grads, workspace, workspace_bytes, s);

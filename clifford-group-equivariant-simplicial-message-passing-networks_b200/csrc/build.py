@@ -7,7 +7,7 @@ import sys
 from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SOURCES = ["api.cu", "elementwise.cu", "linear.cu", "graph.cu", "block_fused.cu", "lift.cu", "tc_probe.cu", "tc_block_fwd.cu"]
+SOURCES = ["api.cu", "elementwise.cu", "linear.cu", "graph.cu", "block_fused.cu", "lift.cu", "tc_probe.cu", "tc_block_fwd.cu", "tc_block_bwd.cu"]
 LIB = os.path.join(HERE, "libcsmpn_b200.so")
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

@@ -1,0 +1,779 @@
+// Tensor-core backward of one CEMLP block (autograd of cegnn_utils.py:180-207) for Euclidean Cl(2,0) / Cl(3,0).
+//
+// All intermediates are BPT tensors (tc_block.cuh).  Saved by the forward: y1 (pre-SiLU), y2 (post-SiLU), xr
+// (pre-normalisation), o (pre-LayerNorm), and x0 (the assembled input row) when the input was not already BPT.
+//
+//   tc_b1_kernel  (FP32 pipe)   MVLayerNorm + weighted-geometric-product + normalisation adjoints:
+//                               grad_y, o, xr, y2 -> d (grad of the product sum), dxr, dy2p; grads of la, wp, na, bl
+//   tc_bgemm      (tensor pipe) dy2 = dy2p + d * WL + dxr * WR                     (K = 2C, transposed weights)
+//   tc_b3_kernel  (FP32 pipe)   MVSiLU adjoint: dy2, y1 -> dy1; grads of sa, sb, b1
+//   tc_bgemm      (tensor pipe) grad_x = dy1 * W1                                    (BPT or reference layout)
+//   tc_dw_kernel  (tensor pipe) weight gradients [d | dxr]^T y2 and dy1^T x0: MN-major TF32 operands, K = rows,
+//                               accumulated over blades of a grade and over all tiles of a CTA in TMEM
+//   tc_final_kernel             fixed-order sum of the per-CTA partials -> reference parameter layouts
+//
+// The elementwise kernels keep one channel per thread for the whole kernel (warp = 4 channels x 8 rows), so every
+// per-channel parameter gradient is a register accumulator and every BPT access of a warp is one 128-byte line.
+#include "tc_block.cuh"
+
+namespace csmpn {
+namespace tcb {
+
+// =====================================================================================================================
+// B1 / B3: elementwise adjoints
+struct EwArgs {
+  int64_t rows;
+  int tiles, C, Cp;
+  const float* gy;  // grad_y: BPT [Cp] or reference layout [rows, C, B]
+  int gy_bpt;
+  const float *o, *xr, *y2, *y1, *dy2;
+  const float *la, *wp, *na, *sa, *sb;
+  float *d, *dxr, *dy2p, *dy1;
+  float* partial;  // [grid][C][NP]
+};
+
+template <int DIM>
+__device__ __forceinline__ void load_mv_bpt(float* v, const float* t, int Cp, int64_t tile, int c4, int r, int j) {
+  constexpr int B = Alg<DIM>::B;
+#pragma unroll
+  for (int b = 0; b < B; ++b) v[b] = t[bpt_off(B, Cp, tile, b, c4, r) + j];
+}
+template <int DIM>
+__device__ __forceinline__ void store_mv_bpt(float* t, const float* v, int Cp, int64_t tile, int c4, int r, int j) {
+  constexpr int B = Alg<DIM>::B;
+#pragma unroll
+  for (int b = 0; b < B; ++b) t[bpt_off(B, Cp, tile, b, c4, r) + j] = v[b];
+}
+
+template <int DIM>
+__global__ void __launch_bounds__(512) tc_b1_kernel(EwArgs a) {
+  using A = Alg<DIM>;
+  constexpr int B = A::B, G = A::G, P = A::P, NP = P + G + 2;
+  extern __shared__ float sm[];
+  const int nw = a.Cp >> 2;
+  float* part1 = sm;                 // [nw][128]
+  float* part2 = part1 + nw * kTile; // [nw][128]
+  float* inv_mu_s = part2 + nw * kTile;
+  float* dmu_s = inv_mu_s + kTile;
+  const int tid = threadIdx.x, c4 = tid >> 5, lane = tid & 31, j = lane & 3, rr = lane >> 2;
+  const int ch = c4 * 4 + j, C = a.C, Cp = a.Cp;
+  const bool ch_ok = ch < C;
+  float la = ch_ok ? a.la[ch] : 0.f, wv[P], sn[G];
+#pragma unroll
+  for (int q = 0; q < P; ++q) wv[q] = ch_ok ? a.wp[ch * P + q] : 0.f;
+#pragma unroll
+  for (int g = 0; g < G; ++g) sn[g] = ch_ok ? sigmoidf_(a.na[ch * G + g]) : 0.f;
+  float g_w[P], g_na[G], g_la = 0.f, g_bl = 0.f;
+#pragma unroll
+  for (int q = 0; q < P; ++q) g_w[q] = 0.f;
+#pragma unroll
+  for (int g = 0; g < G; ++g) g_na[g] = 0.f;
+
+  auto load_gy = [&](float* v, int64_t tile, int r, bool ok) {
+    if (a.gy_bpt) {
+      load_mv_bpt<DIM>(v, a.gy, Cp, tile, c4, r, j);
+    } else if (ok) {
+      load_vec<B>(v, a.gy + ((size_t)(tile * kTile + r) * C + ch) * B);
+    } else {
+#pragma unroll
+      for (int b = 0; b < B; ++b) v[b] = 0.f;
+    }
+  };
+
+  for (int64_t tile = blockIdx.x; tile < a.tiles; tile += gridDim.x) {
+    const int64_t row0 = tile * kTile;
+    // ---- phase 1: row statistics of the layer norm
+#pragma unroll 1
+    for (int s = 0; s < kTile / 8; ++s) {
+      const int r = s * 8 + rr;
+      const bool ok = ch_ok && row0 + r < a.rows;
+      float o[B], dy[B];
+      load_mv_bpt<DIM>(o, a.o, Cp, tile, c4, r, j);
+      load_gy(dy, tile, r, ok);
+      float dot = 0.f;
+#pragma unroll
+      for (int b = 0; b < B; ++b) dot = fmaf(dy[b], o[b], dot);
+      float nu = ok ? smooth_abs_sqrt(mv_sumsq<DIM>(o)) : 0.f;
+      float dt = ok ? la * dot : 0.f;
+      nu += __shfl_xor_sync(0xffffffffu, nu, 1); dt += __shfl_xor_sync(0xffffffffu, dt, 1);
+      nu += __shfl_xor_sync(0xffffffffu, nu, 2); dt += __shfl_xor_sync(0xffffffffu, dt, 2);
+      if (j == 0) { part1[c4 * kTile + r] = nu; part2[c4 * kTile + r] = dt; }
+    }
+    __syncthreads();
+    if (tid < kTile) {
+      float s1 = 0.f, s2 = 0.f;
+      for (int w = 0; w < nw; ++w) { s1 += part1[w * kTile + tid]; s2 += part2[w * kTile + tid]; }
+      const float inv_mu = 1.f / (s1 / (float)C + kEps);
+      inv_mu_s[tid] = inv_mu;
+      dmu_s[tid] = -s2 * inv_mu * inv_mu / (float)C;
+    }
+    __syncthreads();
+    // ---- phase 2: adjoints
+#pragma unroll 1
+    for (int s = 0; s < kTile / 8; ++s) {
+      const int r = s * 8 + rr;
+      const bool ok = ch_ok && row0 + r < a.rows;
+      float o[B], dd[B];
+      load_mv_bpt<DIM>(o, a.o, Cp, tile, c4, r, j);
+      load_gy(dd, tile, r, ok);
+      {
+        const float inv_mu = inv_mu_s[r];
+        float dot = 0.f;
+#pragma unroll
+        for (int b = 0; b < B; ++b) dot = fmaf(dd[b], o[b], dot);
+        if (ok) g_la = fmaf(dot, inv_mu, g_la);
+        const float Q = mv_sumsq<DIM>(o);
+        const float nu = smooth_abs_sqrt(Q);
+        const float k1 = la * inv_mu * kInvSqrt2;
+        const float k2 = dmu_s[r] * Q / (nu * nu * nu) * kInvSqrt2;
+#pragma unroll
+        for (int b = 0; b < B; ++b) dd[b] = ok ? fmaf(k1, dd[b], k2 * o[b]) : 0.f;  // d = do / sqrt2
+      }
+      store_mv_bpt<DIM>(a.d, dd, Cp, tile, c4, r, j);
+      g_bl += dd[0];
+      float y2[B], xr[B], q[G], nrm[G], rinv[G], xn[B], dxn[B], dy2[B];
+      load_mv_bpt<DIM>(y2, a.y2, Cp, tile, c4, r, j);
+      load_mv_bpt<DIM>(xr, a.xr, Cp, tile, c4, r, j);
+      norm_factors<DIM>(xr, sn, q, nrm, rinv);
+#pragma unroll
+      for (int b = 0; b < B; ++b) { xn[b] = xr[b] * rinv[A::grade_of(b)]; dy2[b] = 0.f; dxn[b] = 0.f; }
+      A::template wgp_bwd<false>(y2, xn, wv, dd, nullptr, dy2, dxn, g_w);
+      store_mv_bpt<DIM>(a.dy2p, dy2, Cp, tile, c4, r, j);
+      float t[G], coef[G];
+#pragma unroll
+      for (int g = 0; g < G; ++g) t[g] = 0.f;
+#pragma unroll
+      for (int b = 0; b < B; ++b) t[A::grade_of(b)] = fmaf(dxn[b], xr[b], t[A::grade_of(b)]);
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        const float ddn = -t[g] * rinv[g] * rinv[g];
+        g_na[g] = fmaf(ddn * (nrm[g] - 1.f), sn[g] * (1.f - sn[g]), g_na[g]);
+        coef[g] = ddn * sn[g] * q[g] / (nrm[g] * nrm[g] * nrm[g]);
+      }
+#pragma unroll
+      for (int b = 0; b < B; ++b) dxn[b] = fmaf(dxn[b], rinv[A::grade_of(b)], coef[A::grade_of(b)] * xr[b]);
+      store_mv_bpt<DIM>(a.dxr, dxn, Cp, tile, c4, r, j);
+    }
+  }
+  // ---- fixed-order reduction over the 8 row lanes of a channel, one partial per CTA
+  auto red = [&](float v) {
+    v += __shfl_xor_sync(0xffffffffu, v, 4);
+    v += __shfl_xor_sync(0xffffffffu, v, 8);
+    v += __shfl_xor_sync(0xffffffffu, v, 16);
+    return v;
+  };
+  float* out = a.partial + ((size_t)blockIdx.x * C + (ch_ok ? ch : 0)) * NP;
+#pragma unroll
+  for (int q = 0; q < P; ++q) { const float v = red(g_w[q]); if (rr == 0 && ch_ok) out[q] = v; }
+#pragma unroll
+  for (int g = 0; g < G; ++g) { const float v = red(g_na[g]); if (rr == 0 && ch_ok) out[P + g] = v; }
+  { const float v = red(g_la); if (rr == 0 && ch_ok) out[P + G] = v; }
+  { const float v = red(g_bl); if (rr == 0 && ch_ok) out[P + G + 1] = v; }
+}
+
+template <int DIM>
+__global__ void __launch_bounds__(512) tc_b3_kernel(EwArgs a) {
+  using A = Alg<DIM>;
+  constexpr int B = A::B, G = A::G, NP = 2 * G + 1;
+  const int tid = threadIdx.x, c4 = tid >> 5, lane = tid & 31, j = lane & 3, rr = lane >> 2;
+  const int ch = c4 * 4 + j, C = a.C, Cp = a.Cp;
+  const bool ch_ok = ch < C;
+  float sa[G], sb[G], g_sa[G], g_sb[G], g_b1 = 0.f;
+#pragma unroll
+  for (int g = 0; g < G; ++g) {
+    sa[g] = ch_ok ? a.sa[ch * G + g] : 0.f;
+    sb[g] = ch_ok ? a.sb[ch * G + g] : 0.f;
+    g_sa[g] = 0.f; g_sb[g] = 0.f;
+  }
+  for (int64_t tile = blockIdx.x; tile < a.tiles; tile += gridDim.x) {
+    const int64_t row0 = tile * kTile;
+#pragma unroll 1
+    for (int s = 0; s < kTile / 8; ++s) {
+      const int r = s * 8 + rr;
+      const bool ok = ch_ok && row0 + r < a.rows;
+      float y1[B], dy[B], sg[G], inv[G], t[G], ds[G];
+      load_mv_bpt<DIM>(y1, a.y1, Cp, tile, c4, r, j);
+      load_mv_bpt<DIM>(dy, a.dy2, Cp, tile, c4, r, j);
+      silu_gates<DIM>(y1, sa, sb, sg, inv);
+#pragma unroll
+      for (int g = 0; g < G; ++g) t[g] = 0.f;
+#pragma unroll
+      for (int b = 0; b < B; ++b) t[A::grade_of(b)] = fmaf(dy[b], y1[b], t[A::grade_of(b)]);
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        ds[g] = ok ? t[g] * sg[g] * (1.f - sg[g]) : 0.f;
+        g_sa[g] = fmaf(ds[g], inv[g], g_sa[g]);
+        g_sb[g] += ds[g];
+      }
+#pragma unroll
+      for (int b = 0; b < B; ++b) {
+        const int g = A::grade_of(b);
+        const float dinv = (g == 0) ? 1.f : 2.f * y1[b];
+        dy[b] = ok ? fmaf(sg[g], dy[b], ds[g] * sa[g] * dinv) : 0.f;
+      }
+      g_b1 += dy[0];
+      store_mv_bpt<DIM>(a.dy1, dy, Cp, tile, c4, r, j);
+    }
+  }
+  auto red = [&](float v) {
+    v += __shfl_xor_sync(0xffffffffu, v, 4);
+    v += __shfl_xor_sync(0xffffffffu, v, 8);
+    v += __shfl_xor_sync(0xffffffffu, v, 16);
+    return v;
+  };
+  float* out = a.partial + ((size_t)blockIdx.x * C + (ch_ok ? ch : 0)) * NP;
+#pragma unroll
+  for (int g = 0; g < G; ++g) { const float v = red(g_sa[g]); if (rr == 0 && ch_ok) out[g] = v; }
+#pragma unroll
+  for (int g = 0; g < G; ++g) { const float v = red(g_sb[g]); if (rr == 0 && ch_ok) out[G + g] = v; }
+  { const float v = red(g_b1); if (rr == 0 && ch_ok) out[2 * G] = v; }
+}
+
+// =====================================================================================================================
+// transposed-weight GEMM:  out[r, n] = addend[r, n] + sum_s sum_k src_s[r, k] * W_s[k, n]     (W_s global [K_s, N_s, G])
+struct GemmArgs {
+  int64_t rows;
+  int tiles;
+  const float* src[2];  // BPT sources, channel padding cp[s], nk[s] K chunks each
+  int cp[2], nk[2];
+  const float* w[2];    // weights [wk[s]][wn][G] (c_out = K side, c_in = N side)
+  int wk[2], wn;
+  int n16;              // N padded to 16 (image rows)
+  int kmax;             // max nk * 8 (image columns)
+  const float* addend;  // BPT [n16] or NULL
+  float* out;
+  int out_bpt;          // 1: BPT [n16]; 0: reference layout [rows, wn, B]
+};
+
+template <int B>
+__device__ __forceinline__ void g_issue_load(uint8_t* hi, uint64_t* bar, const float* bpt, int cp, int64_t tile, int kc) {
+  mbar_arrive_expect_tx(bar, B * 4096u);
+#pragma unroll 1
+  for (int b = 0; b < B; ++b) {
+    const float* src = bpt + bpt_off(B, cp, tile, b, 2 * kc, 0);
+    bulk_g2s(hi + b * kPS, src, 2048u, bar);
+    bulk_g2s(hi + b * kPS + kKH, src + 512, 2048u, bar);
+  }
+}
+
+template <int DIM>
+__global__ void __launch_bounds__(kThreads, 1) tc_bgemm_kernel(GemmArgs a) {
+  using A = Alg<DIM>;
+  constexpr int B = A::B, G = A::G;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t half = B * kPS;
+  uint8_t* bufs = smem;
+  const uint32_t img = (uint32_t)a.n16 * a.kmax * 4;
+  const uint32_t set_bytes = G * 2 * img;
+  uint8_t* wimg = smem + 4 * half;
+  const int nsets = a.src[1] ? 2 : 1;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(wimg + (size_t)nsets * set_bytes);
+  uint64_t* load_bar = bars;
+  uint64_t* mma_bar = bars + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+  for (int s = 0; s < nsets; ++s) stage_weight_images<DIM, true>(wimg + (size_t)s * set_bytes, img, a.w[s], a.wk[s], a.wn, a.n16, a.kmax);
+  if (tid == 0) {
+    mbar_init(&load_bar[0], 1); mbar_init(&load_bar[1], 1);
+    mbar_init(&mma_bar[0], 1); mbar_init(&mma_bar[1], 1);
+    mbar_fence_init();
+  }
+  const int nmax = (512 / B) / 16 * 16;                       // output channels per pass (TMEM columns / blades)
+  const int npass = (a.n16 + nmax - 1) / nmax;
+  const uint32_t need = (uint32_t)B * (a.n16 < nmax ? a.n16 : nmax);
+  const uint32_t tcols = need <= 32 ? 32 : need <= 64 ? 64 : need <= 128 ? 128 : need <= 256 ? 256 : 512;
+  if (warp == 0) tmem_alloc(tmem_slot, tcols);
+  fence_async_smem();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tbase = *tmem_slot;
+  const int nk = a.nk[0] + a.nk[1];
+  const int per_tile = npass * nk;
+  const int my_tiles = (a.tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int total_chunks = my_tiles * per_tile;
+  auto issue = [&](int qq) {  // chunk qq of this CTA -> buffer qq & 1
+    const int64_t tile = (int64_t)blockIdx.x + (int64_t)(qq / per_tile) * gridDim.x;
+    const int kc = (qq % per_tile) % nk;
+    const int s = kc < a.nk[0] ? 0 : 1;
+    g_issue_load<B>(bufs + (size_t)(qq & 1) * 2 * half, &load_bar[qq & 1], a.src[s], a.cp[s], tile, s ? kc - a.nk[0] : kc);
+  };
+  int q = 0, loaded = 0;
+  if (tid == 0) for (; loaded < 2 && loaded < total_chunks; ++loaded) issue(loaded);
+  const uint32_t lane_base = (warp & 3) * 32;
+  for (int t = 0; t < my_tiles; ++t) {
+    const int64_t tile = (int64_t)blockIdx.x + (int64_t)t * gridDim.x;
+    const int64_t row0 = tile * kTile;
+    for (int ps = 0; ps < npass; ++ps) {
+      const int n0 = ps * nmax;
+      const int Np = (a.n16 - n0) < nmax ? (a.n16 - n0) : nmax;
+      const uint32_t idesc = idesc_tf32(kTile, Np, false, false);
+      for (int kc = 0; kc < nk; ++kc, ++q) {
+        const int buf = q & 1;
+        uint8_t* hi = bufs + (size_t)buf * 2 * half;
+        mbar_wait(&load_bar[buf], (q >> 1) & 1);
+        for (int it = tid; it < B * 2 * kTile; it += kThreads) {
+          const int r = it & (kTile - 1), kh = (it >> 7) & 1, b = it >> 8;
+          const uint32_t off = b * kPS + kh * kKH + r * 16;
+          const float4 x = *reinterpret_cast<const float4*>(hi + off);
+          float4 h, l;
+          split4(x, h, l);
+          *reinterpret_cast<float4*>(hi + off) = h;
+          *reinterpret_cast<float4*>(hi + half + off) = l;
+        }
+        fence_async_smem();
+        fence_before_sync();
+        __syncthreads();
+        if (tid == 0) {
+          fence_after_sync();
+          const int s = kc < a.nk[0] ? 0 : 1;
+          const int ks = s ? kc - a.nk[0] : kc;
+          const uint32_t hi_a = smem_addr(hi), lo_a = hi_a + half;
+#pragma unroll 1
+          for (int b = 0; b < B; ++b) {
+            const int g = A::grade_of(b);
+            const uint32_t w_hi = smem_addr(wimg + (size_t)s * set_bytes + (size_t)(2 * g) * img) + (uint32_t)n0 * 16u;
+            const uint64_t a_hi = chunk_desc(hi_a, b), a_lo = chunk_desc(lo_a, b);
+            const uint64_t b_hi = smem_desc(w_hi + 2u * ks * a.n16 * 16u, a.n16 * 16u, 128u);
+            const uint64_t b_lo = smem_desc(w_hi + img + 2u * ks * a.n16 * 16u, a.n16 * 16u, 128u);
+            const uint32_t d = tbase + (uint32_t)b * Np;
+            mma_tf32(d, a_hi, b_hi, idesc, kc > 0);
+            mma_tf32(d, a_hi, b_lo, idesc, 1);
+            mma_tf32(d, a_lo, b_hi, idesc, 1);
+          }
+          mma_commit(&mma_bar[buf]);
+          if (loaded == q + 1 && loaded < total_chunks) {
+            if (q >= 1) mbar_wait(&mma_bar[buf ^ 1], ((q - 1) >> 1) & 1);
+            issue(loaded);
+            ++loaded;
+          }
+        }
+      }
+      mbar_wait(&mma_bar[(q - 1) & 1], ((q - 1) >> 1) & 1);
+      fence_after_sync();
+      if (tid == 0) for (; loaded < q + 2 && loaded < total_chunks; ++loaded) issue(loaded);
+      // ---- epilogue of this pass: output channels [n0, n0 + Np)
+      const int r = lane_base + lane;
+      const bool row_ok = row0 + r < a.rows;
+      for (int c4 = warp >> 2; c4 < (Np >> 2); c4 += 4) {
+        float v[B][4];
+#pragma unroll
+        for (int b = 0; b < B; ++b) tmem_ld4(tmem_at(tbase, lane_base, b * Np + c4 * 4), v[b]);
+        tmem_wait_ld();
+        const int gc4 = (n0 >> 2) + c4;
+        if (a.addend) {
+#pragma unroll
+          for (int b = 0; b < B; ++b) {
+            const float4 x = *reinterpret_cast<const float4*>(a.addend + bpt_off(B, a.n16, tile, b, gc4, r));
+            v[b][0] += x.x; v[b][1] += x.y; v[b][2] += x.z; v[b][3] += x.w;
+          }
+        }
+        if (a.out_bpt) {
+#pragma unroll
+          for (int b = 0; b < B; ++b) {
+            float4 x = make_float4(v[b][0], v[b][1], v[b][2], v[b][3]);
+            if (!row_ok) x = make_float4(0.f, 0.f, 0.f, 0.f);
+            *reinterpret_cast<float4*>(a.out + bpt_off(B, a.n16, tile, b, gc4, r)) = x;
+          }
+        } else if (row_ok) {
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) {
+            const int n = gc4 * 4 + jj;
+            if (n >= a.wn) continue;
+            float* dst = a.out + ((size_t)(row0 + r) * a.wn + n) * B;
+#pragma unroll
+            for (int h = 0; h < B / 4; ++h)
+              *reinterpret_cast<float4*>(dst + 4 * h) = make_float4(v[4 * h][jj], v[4 * h + 1][jj], v[4 * h + 2][jj], v[4 * h + 3][jj]);
+          }
+        }
+      }
+      fence_before_sync();
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tbase, tcols);
+}
+
+// =====================================================================================================================
+// weight-gradient GEMM:  D_g[m, n] += sum_{tiles, blades b of grade g, rows r} Acat[r, m, b] * Bsrc[r, n, b]
+// Acat = channels of a0 followed by the channels of a1 (BPT, cpa each); operands MN-major (K = rows).
+struct DwArgs {
+  int64_t rows;
+  int tiles;
+  const float *a0, *a1, *bsrc;
+  int cpa, cpb;   // channel paddings (multiples of 16); cpb = channels of B used by this launch (N)
+  int cpb_total;  // channel padding of the bsrc tensor
+  int b_c4;       // first 4-channel group of bsrc used by this launch
+  int M;          // 64 or 128, >= channels of Acat
+  float* partial; // [grid][G][M][cpb]
+};
+
+constexpr uint32_t kLand = 2048 + 16;  // landing stride of one (plane, 4-channel group) column: [128][4] fp32 + pad
+
+template <int DIM>
+__global__ void __launch_bounds__(256, 1) tc_dw_kernel(DwArgs a) {
+  using A = Alg<DIM>;
+  constexpr int B = A::B, G = A::G;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int na4 = (a.a1 ? 2 : 1) * (a.cpa >> 2);  // 4-channel groups of Acat
+  const int nb4 = a.cpb >> 2;
+  const int ga = a.M / 32, gb = (a.cpb + 31) / 32;  // 32-channel operand groups
+  const uint32_t grp = kTile * 128;                 // bytes of one operand group [128 rows][32 ch]
+  uint8_t* op_a = smem;                             // hi groups then lo groups
+  uint8_t* op_b = op_a + 2 * (size_t)ga * grp;
+  uint8_t* land = op_b + 2 * (size_t)gb * grp;      // 2 x (na4 + nb4) columns
+  const uint32_t land_bytes = (uint32_t)(na4 + nb4) * kLand;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(land + 2 * (size_t)land_bytes);
+  uint64_t* load_bar = bars;       // [2]
+  uint64_t* mma_bar = bars + 2;    // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
+  for (uint32_t i = tid; i < (2 * (ga + gb) * grp) >> 4; i += 256) reinterpret_cast<float4*>(smem)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (tid == 0) {
+    mbar_init(&load_bar[0], 1); mbar_init(&load_bar[1], 1); mbar_init(&mma_bar[0], 1);
+    mbar_fence_init();
+  }
+  const uint32_t need = (uint32_t)G * a.cpb;
+  const uint32_t tcols = need <= 32 ? 32 : need <= 64 ? 64 : need <= 128 ? 128 : need <= 256 ? 256 : 512;
+  if (warp == 0) tmem_alloc(tmem_slot, tcols);
+  fence_async_smem();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tbase = *tmem_slot;
+  const uint32_t idesc = idesc_tf32(a.M, a.cpb, true, true);
+  const int my_tiles = (a.tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int steps = my_tiles * B;  // step = (tile, blade)
+  auto issue = [&](int st) {
+    const int64_t tile = (int64_t)blockIdx.x + (int64_t)(st / B) * gridDim.x;
+    const int b = st % B;
+    uint8_t* dst = land + (size_t)(st & 1) * land_bytes;
+    uint64_t* bar = &load_bar[st & 1];
+    mbar_arrive_expect_tx(bar, (uint32_t)(na4 + nb4) * 2048u);
+    const int ca4 = a.cpa >> 2;
+#pragma unroll 1
+    for (int u = 0; u < na4; ++u) {
+      const float* src = (u < ca4) ? a.a0 + bpt_off(B, a.cpa, tile, b, u, 0) : a.a1 + bpt_off(B, a.cpa, tile, b, u - ca4, 0);
+      bulk_g2s(dst + (size_t)u * kLand, src, 2048u, bar);
+    }
+#pragma unroll 1
+    for (int u = 0; u < nb4; ++u)
+      bulk_g2s(dst + (size_t)(na4 + u) * kLand, a.bsrc + bpt_off(B, a.cpb_total, tile, b, a.b_c4 + u, 0), 2048u, bar);
+  };
+  if (tid == 0 && steps > 0) issue(0);
+  uint32_t grade_used = 0;
+  for (int st = 0; st < steps; ++st) {
+    const int b = st % B, g = A::grade_of(b);
+    if (tid == 0 && st + 1 < steps) issue(st + 1);  // landing buffer (st+1)&1 was consumed by the conversion of step st-1
+    mbar_wait(&load_bar[st & 1], (st >> 1) & 1);
+    if (st > 0) mbar_wait(&mma_bar[0], (st - 1) & 1);  // the MMAs of the previous step have finished reading the operands
+    const uint8_t* src = land + (size_t)(st & 1) * land_bytes;
+    // conversion: landing [4-group][row][4] -> hi / lo operand groups [row][32] (32-byte units xor (row & 3))
+    const int n4 = na4 + nb4;
+    for (int it = tid; it < kTile * n4; it += 256) {
+      const int r = it / n4, u = it - r * n4;
+      const float4 x = *reinterpret_cast<const float4*>(src + (size_t)u * kLand + r * 16);
+      float4 h, l;
+      split4(x, h, l);
+      const bool isb = u >= na4;
+      const int cc = (isb ? u - na4 : u) * 4;  // channel inside its operand
+      uint8_t* base = isb ? op_b : op_a;
+      const int ng = isb ? gb : ga;
+      const uint32_t off = (uint32_t)(cc >> 5) * grp + mn32b_off(r, cc & 31);
+      *reinterpret_cast<float4*>(base + off) = h;
+      *reinterpret_cast<float4*>(base + (size_t)ng * grp + off) = l;
+    }
+    fence_async_smem();
+    fence_before_sync();
+    __syncthreads();
+    if (tid == 0) {
+      fence_after_sync();
+      const uint32_t a_hi = smem_addr(op_a), a_lo = a_hi + ga * grp, b_hi = smem_addr(op_b), b_lo = b_hi + gb * grp;
+      const uint32_t d = tbase + (uint32_t)g * a.cpb;
+      uint32_t acc = (grade_used >> g) & 1;
+#pragma unroll 1
+      for (int ks = 0; ks < kTile / 8; ++ks) {
+        mma_tf32(d, desc_mn32b(a_hi, grp, ks), desc_mn32b(b_hi, grp, ks), idesc, acc);
+        mma_tf32(d, desc_mn32b(a_hi, grp, ks), desc_mn32b(b_lo, grp, ks), idesc, 1);
+        mma_tf32(d, desc_mn32b(a_lo, grp, ks), desc_mn32b(b_hi, grp, ks), idesc, 1);
+        acc = 1;
+      }
+      mma_commit(&mma_bar[0]);
+    }
+    grade_used |= 1u << g;
+  }
+  if (steps > 0) mbar_wait(&mma_bar[0], (steps - 1) & 1);
+  fence_after_sync();
+  // ---- epilogue: D_g -> per-CTA partial [G][M][cpb]; grades this CTA never touched are written as zeros
+  float* out = a.partial + (size_t)blockIdx.x * G * a.M * a.cpb;
+  if (warp < 4) {
+    const bool m64 = a.M == 64;
+    const int m = m64 ? warp * 16 + (lane & 15) : warp * 32 + lane;
+    const bool lane_ok = !m64 || lane < 16;
+    for (int g = 0; g < G; ++g) {
+      const bool used = steps > 0 && ((grade_used >> g) & 1);
+      for (int n = 0; n < a.cpb; n += 4) {
+        float v[4] = {0.f, 0.f, 0.f, 0.f};
+        if (used) {
+          tmem_ld4(tmem_at(tbase, warp * 32, g * a.cpb + n), v);
+          tmem_wait_ld();
+        }
+        if (lane_ok) *reinterpret_cast<float4*>(out + ((size_t)g * a.M + m) * a.cpb + n) = make_float4(v[0], v[1], v[2], v[3]);
+      }
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tbase, tcols);
+}
+
+// =====================================================================================================================
+// fixed-order reduction of per-CTA partials
+struct FinalJob {
+  const float* in;   // partials
+  float* out;
+  int parts;         // number of partials
+  int64_t stride;    // floats between partials
+  int kind;          // 0: out[i] = sum in[p][i] (n = count);  1: weight gradient from [G][M][N] partials
+  int n;             // kind 0: element count; kind 1: c_out * c_in * G
+  int G, M, N, m0, co, ci;  // kind 1: out[(o*ci_tot + i0 + i)*G + g] = sum_p in[p][(g*M + m0 + o)*N + i], i < ci
+  int ci_tot, i0;
+};
+struct FinalJobs { FinalJob j[14]; int count; };
+
+__global__ void tc_final_kernel(FinalJobs jobs) {
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (int k = 0; k < jobs.count; ++k) {
+    const FinalJob& jb = jobs.j[k];
+    if (idx < jb.n) {
+      if (!jb.out) return;
+      size_t src;
+      if (jb.kind == 0) {
+        src = (size_t)idx;
+      } else {
+        const int g = (int)(idx % jb.G), i = (int)((idx / jb.G) % jb.ci), o = (int)(idx / ((int64_t)jb.G * jb.ci));
+        src = ((size_t)g * jb.M + jb.m0 + o) * jb.N + i;
+      }
+      float s = 0.f;
+      for (int p = 0; p < jb.parts; ++p) s += jb.in[(size_t)p * jb.stride + src];
+      if (jb.kind == 0) {
+        jb.out[idx] = s;
+      } else {
+        const int g = (int)(idx % jb.G), i = (int)((idx / jb.G) % jb.ci), o = (int)(idx / ((int64_t)jb.G * jb.ci));
+        jb.out[((size_t)o * jb.ci_tot + jb.i0 + i) * jb.G + g] = s;
+      }
+      return;
+    }
+    idx -= jb.n;
+  }
+}
+
+// =====================================================================================================================
+// host side
+template <int DIM>
+size_t gemm_smem(int nsets, int n16, int kmax) {
+  constexpr int B = Alg<DIM>::B, G = Alg<DIM>::G;
+  return (size_t)4 * B * kPS + (size_t)nsets * G * 2 * n16 * kmax * 4 + 64;
+}
+template <int DIM>
+size_t dw_smem(int M, int na4, int cpb) {
+  const int ga = M / 32, gb = (cpb + 31) / 32;
+  return (size_t)2 * (ga + gb) * kTile * 128 + (size_t)2 * (na4 + cpb / 4) * kLand + 64;
+}
+constexpr size_t kSmemMax = 227 * 1024;
+
+struct BwdPlan {
+  int Cp, cin, n16, tiles;
+  int grid_ew, grid_dw;
+  int M1, M2;  // dW GEMM heights: [d|dxr] and dy1
+  int nbw;       // input channels per column pass of the W1 gradient (64 or 32)
+  int dw_split;  // the [d|dxr] weight-gradient GEMM does not fit shared memory as one job: run d and dxr separately
+  // workspace layout (float offsets)
+  size_t o_d, o_dxr, o_dy2p, o_dy2, o_dy1, o_p1, o_p3, o_dwa, o_dwb, total;
+};
+
+template <int DIM>
+int make_bwd_plan(const csmpn_block_desc& d, BwdPlan* p) {
+  constexpr int B = Alg<DIM>::B, G = Alg<DIM>::G, P = Alg<DIM>::P;
+  p->Cp = round_up(d.c, 16);
+  p->cin = d.c0 + d.c1 + d.c2;
+  p->n16 = round_up(p->cin, 16);
+  p->tiles = (int)((d.rows + kTile - 1) / kTile);
+  if (2 * B * p->Cp > 512 || p->Cp > 64) return CSMPN_ERR_UNSUPPORTED;
+  p->M1 = 2 * p->Cp <= 64 ? 64 : 128;
+  p->M2 = 64;
+  p->dw_split = 0;
+  if (dw_smem<DIM>(p->M1, 2 * p->Cp / 4, p->Cp) > kSmemMax) { p->dw_split = 1; p->M1 = 64; }
+  if (gemm_smem<DIM>(2, p->Cp, p->Cp) > kSmemMax || gemm_smem<DIM>(1, p->n16, p->Cp) > kSmemMax) return CSMPN_ERR_UNSUPPORTED;
+  // the W1 gradient runs in column passes of <= nbw input channels
+  p->nbw = dw_smem<DIM>(p->M2, p->Cp / 4, p->n16 < 64 ? p->n16 : 64) <= kSmemMax ? 64 : 32;
+  const int nb = p->n16 < p->nbw ? p->n16 : p->nbw;
+  if (dw_smem<DIM>(p->M1, (p->dw_split ? 1 : 2) * p->Cp / 4, p->Cp) > kSmemMax || dw_smem<DIM>(p->M2, p->Cp / 4, nb) > kSmemMax)
+    return CSMPN_ERR_UNSUPPORTED;
+  if (p->n16 > 4 * p->nbw) return CSMPN_ERR_UNSUPPORTED;
+  const int sms = sm_count_cached();
+  p->grid_ew = p->tiles < 2 * sms ? (p->tiles > 0 ? p->tiles : 1) : 2 * sms;
+  p->grid_dw = p->tiles < sms ? (p->tiles > 0 ? p->tiles : 1) : sms;
+  const size_t t = (size_t)bpt_floats(B, d.rows, p->Cp);
+  size_t o = 0;
+  p->o_d = o; o += t;
+  p->o_dxr = o; o += t;
+  p->o_dy2p = o; o += t;
+  p->o_dy2 = o; o += t;
+  p->o_dy1 = o; o += t;
+  auto al = [](size_t x) { return (x + 31) / 32 * 32; };  // keep every segment 128-byte aligned
+  p->o_p1 = o; o = al(o + (size_t)p->grid_ew * d.c * (P + G + 2));
+  p->o_p3 = o; o = al(o + (size_t)p->grid_ew * d.c * (2 * G + 1));
+  p->o_dwa = o; o += (size_t)p->grid_dw * G * p->M1 * p->Cp * (p->dw_split ? 2 : 1);
+  p->o_dwb = o; o += (size_t)p->grid_dw * G * p->M2 * p->n16;
+  p->total = o;
+  return CSMPN_OK;
+}
+
+template <int DIM>
+int launch_bwd(const csmpn_block_desc& d, const csmpn_block_grads& g, void* workspace, int64_t bytes, cudaStream_t stream) {
+  constexpr int B = Alg<DIM>::B, G = Alg<DIM>::G, P = Alg<DIM>::P;
+  BwdPlan p;
+  int st = make_bwd_plan<DIM>(d, &p);
+  if (st) return st;
+  if (!workspace || bytes < (int64_t)(p.total * 4)) return CSMPN_ERR_WORKSPACE;
+  if (!d.save_y1 || !d.save_y2 || !d.save_xr || !d.save_o) return CSMPN_ERR_BAD_ARG;
+  const float* x0 = d.in_bpt ? d.p0 : d.save_x0;
+  if (!x0) return CSMPN_ERR_BAD_ARG;
+  if (p.tiles == 0) return CSMPN_OK;
+  float* ws = (float*)workspace;
+  const int C = d.c, Cp = p.Cp;
+  // ---- B1
+  EwArgs e;
+  memset(&e, 0, sizeof(e));
+  e.rows = d.rows; e.tiles = p.tiles; e.C = C; e.Cp = Cp;
+  e.gy = g.grad_y; e.gy_bpt = g.gy_bpt;
+  e.o = d.save_o; e.xr = d.save_xr; e.y2 = d.save_y2; e.y1 = d.save_y1;
+  e.la = d.la; e.wp = d.wp; e.na = d.na; e.sa = d.sa; e.sb = d.sb;
+  e.d = ws + p.o_d; e.dxr = ws + p.o_dxr; e.dy2p = ws + p.o_dy2p; e.dy2 = ws + p.o_dy2; e.dy1 = ws + p.o_dy1;
+  e.partial = ws + p.o_p1;
+  const int ew_threads = (Cp / 4) * 32;
+  tc_b1_kernel<DIM><<<p.grid_ew, ew_threads, (size_t)(2 * (Cp / 4) * kTile + 2 * kTile) * 4, stream>>>(e);
+  CSMPN_LAUNCH_CHECK("tc_b1_kernel");
+  // ---- dy2 = dy2p + d WL + dxr WR
+  const int grid = p.tiles < sm_count_cached() ? p.tiles : sm_count_cached();
+  GemmArgs ga;
+  memset(&ga, 0, sizeof(ga));
+  ga.rows = d.rows; ga.tiles = p.tiles;
+  ga.src[0] = ws + p.o_d; ga.src[1] = ws + p.o_dxr; ga.cp[0] = ga.cp[1] = Cp; ga.nk[0] = ga.nk[1] = Cp / 8;
+  ga.w[0] = d.wl; ga.w[1] = d.wr; ga.wk[0] = ga.wk[1] = C; ga.wn = C;
+  ga.n16 = Cp; ga.kmax = Cp;
+  ga.addend = ws + p.o_dy2p; ga.out = ws + p.o_dy2; ga.out_bpt = 1;
+  size_t sm = gemm_smem<DIM>(2, ga.n16, ga.kmax);
+  CSMPN_CUDA_TRY(cudaFuncSetAttribute(tc_bgemm_kernel<DIM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
+  tc_bgemm_kernel<DIM><<<grid, kThreads, sm, stream>>>(ga);
+  CSMPN_LAUNCH_CHECK("tc_bgemm_kernel(dy2)");
+  // ---- B3
+  e.partial = ws + p.o_p3;
+  tc_b3_kernel<DIM><<<p.grid_ew, ew_threads, 0, stream>>>(e);
+  CSMPN_LAUNCH_CHECK("tc_b3_kernel");
+  // ---- grad_x = dy1 W1
+  if (g.grad_x) {
+    memset(&ga, 0, sizeof(ga));
+    ga.rows = d.rows; ga.tiles = p.tiles;
+    ga.src[0] = ws + p.o_dy1; ga.cp[0] = Cp; ga.nk[0] = Cp / 8;
+    ga.w[0] = d.w1; ga.wk[0] = C; ga.wn = p.cin;
+    ga.n16 = p.n16; ga.kmax = Cp;
+    ga.out = g.grad_x; ga.out_bpt = g.gx_bpt;
+    sm = gemm_smem<DIM>(1, ga.n16, ga.kmax);
+    tc_bgemm_kernel<DIM><<<grid, kThreads, sm, stream>>>(ga);
+    CSMPN_LAUNCH_CHECK("tc_bgemm_kernel(grad_x)");
+  }
+  // ---- weight gradients
+  CSMPN_CUDA_TRY(cudaFuncSetAttribute(tc_dw_kernel<DIM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
+  DwArgs da;
+  memset(&da, 0, sizeof(da));
+  da.rows = d.rows; da.tiles = p.tiles;
+  da.a0 = ws + p.o_d; da.a1 = ws + p.o_dxr; da.cpa = Cp; da.bsrc = d.save_y2; da.cpb = Cp; da.cpb_total = Cp; da.b_c4 = 0;
+  da.M = p.M1;
+  da.partial = ws + p.o_dwa;
+  const size_t dwa_part = (size_t)p.grid_dw * G * p.M1 * Cp;
+  if (!p.dw_split) {
+    tc_dw_kernel<DIM><<<p.grid_dw, 256, dw_smem<DIM>(da.M, 2 * Cp / 4, Cp), stream>>>(da);
+    CSMPN_LAUNCH_CHECK("tc_dw_kernel(wl,wr)");
+  } else {
+    da.a1 = nullptr;
+    tc_dw_kernel<DIM><<<p.grid_dw, 256, dw_smem<DIM>(da.M, Cp / 4, Cp), stream>>>(da);
+    CSMPN_LAUNCH_CHECK("tc_dw_kernel(wl)");
+    da.a0 = ws + p.o_dxr;
+    da.partial = ws + p.o_dwa + dwa_part;
+    tc_dw_kernel<DIM><<<p.grid_dw, 256, dw_smem<DIM>(da.M, Cp / 4, Cp), stream>>>(da);
+    CSMPN_LAUNCH_CHECK("tc_dw_kernel(wr)");
+  }
+  for (int i0 = 0; i0 < p.n16; i0 += p.nbw) {
+    const int nb = (p.n16 - i0) < p.nbw ? (p.n16 - i0) : p.nbw;
+    da.a0 = ws + p.o_dy1; da.a1 = nullptr; da.cpa = Cp; da.bsrc = x0; da.cpb = nb; da.cpb_total = p.n16; da.b_c4 = i0 / 4;
+    da.M = p.M2;
+    da.partial = ws + p.o_dwb + (size_t)p.grid_dw * G * p.M2 * i0;
+    tc_dw_kernel<DIM><<<p.grid_dw, 256, dw_smem<DIM>(da.M, Cp / 4, nb), stream>>>(da);
+    CSMPN_LAUNCH_CHECK("tc_dw_kernel(w1)");
+  }
+  // ---- final reduction
+  FinalJobs fj;
+  memset(&fj, 0, sizeof(fj));
+  int k = 0;
+  auto wjob = [&](const float* in, float* out, int parts, int M, int N, int m0, int co, int ci) {
+    FinalJob& jb = fj.j[k++];
+    jb.in = in; jb.out = out; jb.parts = parts; jb.stride = (int64_t)G * M * N; jb.kind = 1; jb.n = co * ci * G;
+    jb.G = G; jb.M = M; jb.N = N; jb.m0 = m0; jb.co = co; jb.ci = ci; jb.ci_tot = ci; jb.i0 = 0;
+  };
+  wjob(ws + p.o_dwa, g.g_wl, p.grid_dw, p.M1, Cp, 0, C, C);
+  if (!p.dw_split) wjob(ws + p.o_dwa, g.g_wr, p.grid_dw, p.M1, Cp, Cp, C, C);
+  else wjob(ws + p.o_dwa + dwa_part, g.g_wr, p.grid_dw, p.M1, Cp, 0, C, C);
+  for (int i0 = 0; i0 < p.cin; i0 += p.nbw) {
+    const int nb = (p.n16 - i0) < p.nbw ? (p.n16 - i0) : p.nbw;
+    const int ci = (p.cin - i0) < p.nbw ? (p.cin - i0) : p.nbw;
+    wjob(ws + p.o_dwb + (size_t)p.grid_dw * G * p.M2 * i0, g.g_w1, p.grid_dw, p.M2, nb, 0, C, ci);
+    fj.j[k - 1].ci_tot = p.cin;
+    fj.j[k - 1].i0 = i0;
+  }
+  // small per-channel gradients: partial rows [C][NP]; viewed as kind-1 jobs with G := 1, "N" := NP, one column each
+  auto cjob = [&](const float* in, float* out, int parts, int NPk, int col0, int width) {
+    // out[ch*width + q] = sum_p in[p][ch*NPk + col0 + q]  ==  kind 1 with G = 1, M = C, N = NPk, co = C, ci = width, offset col0
+    FinalJob& jb = fj.j[k++];
+    jb.in = in + col0; jb.out = out; jb.parts = parts; jb.stride = (int64_t)C * NPk; jb.kind = 1; jb.n = C * width;
+    jb.G = 1; jb.M = C; jb.N = NPk; jb.m0 = 0; jb.co = C; jb.ci = width; jb.ci_tot = width; jb.i0 = 0;
+  };
+  const int NP1 = P + G + 2, NP3 = 2 * G + 1;
+  cjob(ws + p.o_p1, g.g_wp, p.grid_ew, NP1, 0, P);
+  cjob(ws + p.o_p1, g.g_na, p.grid_ew, NP1, P, G);
+  cjob(ws + p.o_p1, g.g_la, p.grid_ew, NP1, P + G, 1);
+  cjob(ws + p.o_p1, g.g_bl, p.grid_ew, NP1, P + G + 1, 1);
+  cjob(ws + p.o_p3, g.g_sa, p.grid_ew, NP3, 0, G);
+  cjob(ws + p.o_p3, g.g_sb, p.grid_ew, NP3, G, G);
+  cjob(ws + p.o_p3, d.has_b1 ? g.g_b1 : nullptr, p.grid_ew, NP3, 2 * G, 1);
+  fj.count = k;
+  int64_t total = 0;
+  for (int i = 0; i < k; ++i) total += fj.j[i].n;
+  tc_final_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(fj);
+  CSMPN_LAUNCH_CHECK("tc_final_kernel");
+  return CSMPN_OK;
+}
+
+template <int DIM>
+int64_t bwd_ws_bytes(const csmpn_block_desc& d) {
+  BwdPlan p;
+  if (make_bwd_plan<DIM>(d, &p)) return -1;
+  return (int64_t)(p.total * 4);
+}
+
+}  // namespace tcb
+
+int tc_block_bwd(int dim, const csmpn_block_desc* d, const csmpn_block_grads* g, void* ws, int64_t bytes, cudaStream_t stream) {
+  if (dim == 2) return tcb::launch_bwd<2>(*d, *g, ws, bytes, stream);
+  if (dim == 3) return tcb::launch_bwd<3>(*d, *g, ws, bytes, stream);
+  return CSMPN_ERR_UNSUPPORTED;
+}
+int64_t tc_block_bwd_workspace(int dim, const csmpn_block_desc* d) {
+  if (dim == 2) return tcb::bwd_ws_bytes<2>(*d);
+  if (dim == 3) return tcb::bwd_ws_bytes<3>(*d);
+  return -1;
+}
+
+}  // namespace csmpn

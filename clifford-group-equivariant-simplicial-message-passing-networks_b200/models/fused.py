@@ -42,6 +42,7 @@ class BlockGrads(ctypes.Structure):
         ("grad_y", c_void_p), ("grad_x", c_void_p),
         ("g_w1", c_void_p), ("g_b1", c_void_p), ("g_sa", c_void_p), ("g_sb", c_void_p), ("g_wr", c_void_p),
         ("g_na", c_void_p), ("g_wl", c_void_p), ("g_bl", c_void_p), ("g_wp", c_void_p), ("g_la", c_void_p),
+        ("gy_bpt", c_int32), ("gx_bpt", c_int32),
     ]
 
 
@@ -276,7 +277,61 @@ class TcBlockFn(torch.autograd.Function):
 
 
 def _tc_block_backward(ctx, gy):
-    raise NotImplementedError("tensor-core block backward")
+    (dim, mode, sgraph, chans, c, rows, src_mask, par_mask, has_res, pshapes, sshapes, in_bpt, out_bpt, has_x0) = ctx.meta
+    saved = list(ctx.saved_tensors)
+    srcs = [saved.pop(0) if m else None for m in src_mask]
+    params = [saved.pop(0) if m else None for m in par_mask]
+    y1, xr, o, y2 = saved[:4]
+    x0 = saved[4] if has_x0 else None
+    gy = f32c(gy)
+    dev = gy.device
+    B = 1 << dim
+    cin = sum(chans)
+    d = _fill_desc(dim, mode, srcs, chans, rows, c, params, sgraph, gy, None, (y1, xr, o))
+    d.engine, d.in_bpt, d.out_bpt = 1, int(in_bpt), int(out_bpt)
+    d.save_y2 = y2.data_ptr()
+    d.save_x0 = None if x0 is None else x0.data_ptr()
+    gx = bpt_empty(dim, rows, cin, dev) if in_bpt else torch.empty((rows, cin, B), dtype=torch.float32, device=dev)
+    pg = [None if t is None else torch.empty_like(t) for t in params]
+    g = BlockGrads()
+    g.grad_y, g.grad_x = gy.data_ptr(), gx.data_ptr()
+    g.gy_bpt, g.gx_bpt = int(out_bpt), int(in_bpt)
+    names = ("g_w1", "g_b1", "g_sa", "g_sb", "g_wr", "g_na", "g_wl", "g_bl", "g_wp", "g_la")
+    for n, t in zip(names, pg):
+        setattr(g, n, None if t is None else t.data_ptr())
+    nbytes = lib().csmpn_block_bwd_workspace(dim, ctypes.byref(d))
+    if nbytes < 0:
+        raise _lib.CsmpnError("tensor-core block backward: unsupported configuration")
+    ws = workspace(nbytes, dev)
+    check(lib().csmpn_block_bwd(dim, ctypes.byref(d), ctypes.byref(g), ptr(ws), ws.numel(), stream_ptr(dev)),
+          "block_bwd (tensor-core)")
+    gsrc = [None, None, None]
+    if in_bpt:
+        gsrc[0] = gx
+    elif mode == 0:
+        off = 0
+        for k in range(3):
+            if srcs[k] is not None:
+                gsrc[k] = gx[:, off:off + chans[k]] if (chans[k] != cin) else gx
+                off += chans[k]
+    else:
+        csr = sgraph.csr
+        n_nodes, width = srcs[0].shape[0], chans[0] * B
+        gh = torch.empty((n_nodes, chans[0], B), dtype=torch.float32, device=dev)
+        check(lib().csmpn_scatter_diff_sorted(ptr(gx), cin * B, ptr(csr.rowptr_dst), ptr(csr.rowptr_src), ptr(csr.perm_src),
+                                              ptr(sgraph.rank), ptr(gh), n_nodes, width, 0, stream_ptr(dev)),
+              "scatter_diff_sorted")
+        gsrc[0] = gh
+        if srcs[1] is not None:
+            ge = torch.empty((rows, chans[1], B), dtype=torch.float32, device=dev)
+            check(lib().csmpn_scatter_rows(ptr(gx), cin * B, chans[0] * B, ptr(csr.perm_dst), ptr(ge), rows, chans[1] * B,
+                                           stream_ptr(dev)), "scatter_rows")
+            gsrc[1] = ge
+    if not in_bpt:
+        gsrc = [None if t is None else t.reshape(s) for t, s in zip(gsrc, sshapes)]
+    gres = gy if has_res else None
+    pgr = [None if t is None else t.reshape(s) for t, s in zip(pg, pshapes)]
+    return (None, gsrc[0], gsrc[1], gsrc[2], gres, *pgr)
 
 
 class SegmentReduceSortedFn(torch.autograd.Function):
@@ -307,7 +362,7 @@ def _need_grad(*tensors_and_params):
     return torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors_and_params)
 
 
-TC_BACKWARD_READY = False  # flipped to True once csrc/tc_block_bwd.cu is bound
+TC_BACKWARD_READY = True
 
 
 def _block_uses_tc(algebra, layer, need_grad) -> bool:

@@ -201,6 +201,8 @@ typedef struct csmpn_block_grads {
   float* grad_x;         /* [rows, c_in, B] gradient of the assembled input row (mode 1: w.r.t. the difference and the
                             gathered extra channels, in sorted-row order; scatter with csmpn_scatter_rows) */
   float *g_w1, *g_b1, *g_sa, *g_sb, *g_wr, *g_na, *g_wl, *g_bl, *g_wp, *g_la;
+  /* engine 1 only: grad_y is a BPT [c] tensor / grad_x is written as a BPT [c_in] tensor (grad_x may be NULL) */
+  int32_t gy_bpt, gx_bpt;
 } csmpn_block_grads;
 
 int csmpn_block_fwd(int dim, const csmpn_block_desc* desc, csmpn_stream_t stream);
