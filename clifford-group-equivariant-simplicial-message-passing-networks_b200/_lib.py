@@ -59,6 +59,7 @@ def _declare(lib):
         "csmpn_block_fwd": (c_int, [i32, P, P]),
         "csmpn_block_tc_supported": (c_int, [i32, i32, i32]),
         "csmpn_bpt_floats": (i64, [i32, i64, i32]),
+        "csmpn_tc_debug_buffer": (c_int, [P]),
         "csmpn_block_bwd_workspace": (i64, [i32, P]),
         "csmpn_block_bwd": (c_int, [i32, P, P, P, i64, P]),
         "csmpn_csr_sorted_indices": (c_int, [P, P, P, P, P, i64, P]),

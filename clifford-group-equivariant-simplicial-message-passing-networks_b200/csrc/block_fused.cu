@@ -1041,6 +1041,7 @@ int tc_block_fwd(int dim, const csmpn_block_desc* d, cudaStream_t stream);
 int tc_block_bwd(int dim, const csmpn_block_desc* d, const csmpn_block_grads* g, void* ws, int64_t bytes, cudaStream_t stream);
 int64_t tc_block_bwd_workspace(int dim, const csmpn_block_desc* d);
 bool tc_block_supported(int dim, int c_in, int c);
+void tc_set_debug_buffer(long long* p);
 }  // namespace csmpn
 
 using namespace csmpn;
@@ -1048,6 +1049,11 @@ using namespace csmpn;
 extern "C" {
 
 int csmpn_block_tc_supported(int dim, int c_in, int c) { return tc_block_supported(dim, c_in, c) ? 1 : 0; }
+
+int csmpn_tc_debug_buffer(int64_t* device_buffer_1024) {
+  tc_set_debug_buffer((long long*)device_buffer_1024);
+  return CSMPN_OK;
+}
 
 int64_t csmpn_bpt_floats(int dim, int64_t rows, int channels) {
   if (dim < 1 || dim > 5 || rows < 0 || channels < 1) return -1;

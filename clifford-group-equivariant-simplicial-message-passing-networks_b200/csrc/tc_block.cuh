@@ -33,6 +33,16 @@ __device__ __forceinline__ size_t bpt_off(int B, int cp, int64_t tile, int b, in
   return ((((size_t)tile * B + b) * (cp >> 2) + c4) * kTile + r) * 4;
 }
 
+// Approximate SFU forms (rcp / sqrt / ex2 .approx: <= 2 ulp) instead of the IEEE-rounded sequences of sqrtf, expf and
+// '/': each of those costs 8-20 instructions and the elementwise stages evaluate ~15 of them per multivector.  Their
+// error (2^-22) is an order of magnitude below the fp32 parity budget (1e-5 forward, 1e-4 gradients).
+__device__ __forceinline__ float fast_rcp(float x) { float y; asm("rcp.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float fast_sqrt(float x) { float y; asm("sqrt.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float fast_ex2(float x) { float y; asm("ex2.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float fast_sigmoid(float v) { return fast_rcp(1.f + fast_ex2(-1.4426950408889634f * v)); }
+// (q^2 + 1e-16)^(1/4)
+__device__ __forceinline__ float fast_sas(float q) { return fast_sqrt(fast_sqrt(fmaf(q, q, kSmoothEps))); }
+
 template <int DIM>
 __device__ __forceinline__ void silu_gates(const float* y1, const float* a, const float* b, float* sg, float* inv) {
   using A = Alg<DIM>;
@@ -42,7 +52,7 @@ __device__ __forceinline__ void silu_gates(const float* y1, const float* a, cons
   for (int i = 0; i < A::B; ++i) inv[A::grade_of(i)] = fmaf(y1[i], y1[i], inv[A::grade_of(i)]);
   inv[0] = y1[0];
 #pragma unroll
-  for (int g = 0; g < A::G; ++g) sg[g] = sigmoidf_(fmaf(a[g], inv[g], b[g]));
+  for (int g = 0; g < A::G; ++g) sg[g] = fast_sigmoid(fmaf(a[g], inv[g], b[g]));
 }
 
 // normalisation: xn_i = xr_i * rinv[g];  den_g = s_g (nrm_g - 1) + 1 + eps
@@ -55,8 +65,8 @@ __device__ __forceinline__ void norm_factors(const float* xr, const float* s, fl
   for (int i = 0; i < A::B; ++i) q[A::grade_of(i)] = fmaf(xr[i], xr[i], q[A::grade_of(i)]);
 #pragma unroll
   for (int g = 0; g < A::G; ++g) {
-    nrm[g] = smooth_abs_sqrt(q[g]);
-    rinv[g] = 1.f / (fmaf(s[g], nrm[g] - 1.f, 1.f) + kEps);
+    nrm[g] = fast_sas(q[g]);
+    rinv[g] = fast_rcp(fmaf(s[g], nrm[g] - 1.f, 1.f) + kEps);
   }
 }
 
@@ -96,6 +106,97 @@ __device__ __forceinline__ void stage_weight_images(uint8_t* img0, uint32_t img_
 // A-operand descriptors of blade b in a chunk buffer half
 __device__ __forceinline__ uint64_t chunk_desc(uint32_t half_saddr, int b) {
   return smem_desc(half_saddr + (uint32_t)b * kPS, kKH, 128u);
+}
+
+// ---- K-chunk pipeline shared by the GEMM kernels ------------------------------------------------------------------
+// A chunk = 8 channels of all blades of a 128-row tile.  Chunk q lands (bulk copies) in raw slot q % kRing; the split
+// pass turns the slot into the TF32-exact high parts in place and writes the remainders to the single `lo` buffer;
+// the MMAs of the chunk read both.  Loads run kRing-1 chunks ahead of the MMAs (two chunks = 64 KB per SM in flight).
+constexpr int kRing = 3;
+constexpr int kPipeBars = 2 * kRing + 1;
+struct Pipe {
+  uint8_t* raw;        // kRing slots of `half` bytes
+  uint8_t* lo;         // one slot
+  uint64_t* load_bar;  // [kRing] the bulk copies of the chunk have landed
+  uint64_t* slot_bar;  // [kRing] every MMA reading the slot has completed
+  uint64_t* lo_bar;    // [1]     the MMAs reading `lo` have completed
+  uint32_t half;
+  __device__ __forceinline__ uint8_t* slot(int q) const { return raw + (size_t)(q % kRing) * half; }
+  __device__ __forceinline__ void init(uint8_t* base, uint64_t* bars, uint32_t half_bytes) {
+    raw = base; lo = base + (size_t)kRing * half_bytes; half = half_bytes;
+    load_bar = bars; slot_bar = bars + kRing; lo_bar = bars + 2 * kRing;
+    if (threadIdx.x == 0) {
+      for (int i = 0; i < kPipeBars; ++i) mbar_init(&bars[i], 1);
+      mbar_fence_init();
+    }
+  }
+  __device__ __forceinline__ uint32_t bytes() const { return (kRing + 1) * half; }
+};
+
+// bulk copies of chunk q (8 channels kc of a BPT tensor) into its raw slot: called by ALL lanes of one warp
+template <int B>
+__device__ __forceinline__ void issue_chunk_load(const Pipe& p, int q, const float* bpt, int cp, int64_t tile, int kc) {
+  const int lane = threadIdx.x & 31;
+  uint64_t* bar = &p.load_bar[q % kRing];
+  if (lane == 0) mbar_arrive_expect_tx(bar, B * 4096u);
+  __syncwarp();
+  for (int u = lane; u < 2 * B; u += 32) {
+    const int b = u >> 1, kh = u & 1;
+    bulk_g2s(p.slot(q) + b * kPS + kh * kKH, bpt + bpt_off(B, cp, tile, b, 2 * kc + kh, 0), 2048u, bar);
+  }
+}
+// split pass over the landed chunk q: high parts in place, remainders to `lo`
+template <int B>
+__device__ __forceinline__ void split_chunk(const Pipe& p, int q) {
+  uint8_t* hi = p.slot(q);
+  for (int it = threadIdx.x; it < B * 2 * kTile; it += kThreads) {
+    const int r = it & (kTile - 1), kh = (it >> 7) & 1, b = it >> 8;
+    const uint32_t off = b * kPS + kh * kKH + r * 16;
+    const float4 x = *reinterpret_cast<const float4*>(hi + off);
+    float4 h, l;
+    split4(x, h, l);
+    *reinterpret_cast<float4*>(hi + off) = h;
+    *reinterpret_cast<float4*>(p.lo + off) = l;
+  }
+}
+// the MMAs of chunk q (called by every lane of one converged warp; an elected lane issues).  Weight set s: images at wimg0 + s*set_bytes, image (g, hi/lo) = 2g / 2g+1, plane
+// rows = w_rows, K step ks, first output row n0; accumulator of (set s, blade b) at column (s*B + b)*ncols.
+// The issuing thread's instruction stream is serial, so descriptors are formed by adding small 16-byte-unit offsets to
+// bases computed once per chunk, and the loops are fully unrolled.
+template <int DIM>
+__device__ __forceinline__ void issue_chunk_mma(const Pipe& p, int q, uint32_t tbase, uint32_t ncols, bool accumulate,
+                                                const uint8_t* wimg0, uint32_t img_bytes, int s0, int nsets, uint32_t set_bytes,
+                                                uint32_t w_rows, int ks, int n0, uint32_t idesc) {
+  using A = Alg<DIM>;
+  constexpr int B = A::B;
+  const uint64_t a_hi = chunk_desc(smem_addr(p.slot(q)), 0), a_lo = chunk_desc(smem_addr(p.lo), 0);
+  const uint64_t w0 = smem_desc(smem_addr(wimg0) + (uint32_t)s0 * set_bytes + 2u * ks * w_rows * 16u + (uint32_t)n0 * 16u,
+                                w_rows * 16u, 128u);
+  const uint64_t img16 = img_bytes >> 4, set16 = set_bytes >> 4;
+  constexpr uint64_t ps16 = kPS >> 4;
+#pragma unroll
+  for (int s = 0; s < 2; ++s) {
+    if (s < nsets) {
+#pragma unroll
+      for (int b = 0; b < B; ++b)
+        mma_tf32_w(tbase + (uint32_t)(s * B + b) * ncols, a_lo + b * ps16, w0 + s * set16 + (2 * A::grade_of(b)) * img16, idesc,
+                 accumulate);
+    }
+  }
+  mma_commit_w(p.lo_bar);
+#pragma unroll
+  for (int s = 0; s < 2; ++s) {
+    if (s < nsets) {
+#pragma unroll
+      for (int b = 0; b < B; ++b) {
+        const uint64_t wd = w0 + s * set16 + (2 * A::grade_of(b)) * img16;
+        const uint32_t d = tbase + (uint32_t)(s * B + b) * ncols;
+        mma_tf32_w(d, a_hi + b * ps16, wd, idesc, 1);
+        mma_tf32_w(d, a_hi + b * ps16, wd + img16, idesc, 1);
+      }
+    }
+  }
+  mma_commit_w(&p.slot_bar[q % kRing]);
 }
 
 }  // namespace tcb

@@ -80,12 +80,15 @@ __global__ void __launch_bounds__(512) tc_b1_kernel(EwArgs a) {
     }
   };
 
-  for (int64_t tile = blockIdx.x; tile < a.tiles; tile += gridDim.x) {
+  // work unit = half a tile (64 rows): finer units balance the persistent CTAs when there are only a few tiles per SM
+  for (int64_t unit = blockIdx.x; unit < 2 * (int64_t)a.tiles; unit += gridDim.x) {
+    const int64_t tile = unit >> 1;
+    const int rbase = (int)(unit & 1) * (kTile / 2);
     const int64_t row0 = tile * kTile;
     // ---- phase 1: row statistics of the layer norm
 #pragma unroll 1
-    for (int s = 0; s < kTile / 8; ++s) {
-      const int r = s * 8 + rr;
+    for (int s = 0; s < kTile / 16; ++s) {
+      const int r = rbase + s * 8 + rr;
       const bool ok = ch_ok && row0 + r < a.rows;
       float o[B], dy[B];
       load_mv_bpt<DIM>(o, a.o, Cp, tile, c4, r, j);
@@ -93,29 +96,32 @@ __global__ void __launch_bounds__(512) tc_b1_kernel(EwArgs a) {
       float dot = 0.f;
 #pragma unroll
       for (int b = 0; b < B; ++b) dot = fmaf(dy[b], o[b], dot);
-      float nu = ok ? smooth_abs_sqrt(mv_sumsq<DIM>(o)) : 0.f;
+      float nu = ok ? fast_sas(mv_sumsq<DIM>(o)) : 0.f;
       float dt = ok ? la * dot : 0.f;
       nu += __shfl_xor_sync(0xffffffffu, nu, 1); dt += __shfl_xor_sync(0xffffffffu, dt, 1);
       nu += __shfl_xor_sync(0xffffffffu, nu, 2); dt += __shfl_xor_sync(0xffffffffu, dt, 2);
       if (j == 0) { part1[c4 * kTile + r] = nu; part2[c4 * kTile + r] = dt; }
     }
     __syncthreads();
-    if (tid < kTile) {
+    if (tid < kTile / 2) {
+      const int r = rbase + tid;
       float s1 = 0.f, s2 = 0.f;
-      for (int w = 0; w < nw; ++w) { s1 += part1[w * kTile + tid]; s2 += part2[w * kTile + tid]; }
+      for (int w = 0; w < nw; ++w) { s1 += part1[w * kTile + r]; s2 += part2[w * kTile + r]; }
       const float inv_mu = 1.f / (s1 / (float)C + kEps);
-      inv_mu_s[tid] = inv_mu;
-      dmu_s[tid] = -s2 * inv_mu * inv_mu / (float)C;
+      inv_mu_s[r] = inv_mu;
+      dmu_s[r] = -s2 * inv_mu * inv_mu / (float)C;
     }
     __syncthreads();
     // ---- phase 2: adjoints
 #pragma unroll 1
-    for (int s = 0; s < kTile / 8; ++s) {
-      const int r = s * 8 + rr;
+    for (int s = 0; s < kTile / 16; ++s) {
+      const int r = rbase + s * 8 + rr;
       const bool ok = ch_ok && row0 + r < a.rows;
-      float o[B], dd[B];
+      float o[B], dd[B], y2[B], xr[B];
       load_mv_bpt<DIM>(o, a.o, Cp, tile, c4, r, j);
       load_gy(dd, tile, r, ok);
+      load_mv_bpt<DIM>(y2, a.y2, Cp, tile, c4, r, j);
+      load_mv_bpt<DIM>(xr, a.xr, Cp, tile, c4, r, j);
       {
         const float inv_mu = inv_mu_s[r];
         float dot = 0.f;
@@ -123,17 +129,15 @@ __global__ void __launch_bounds__(512) tc_b1_kernel(EwArgs a) {
         for (int b = 0; b < B; ++b) dot = fmaf(dd[b], o[b], dot);
         if (ok) g_la = fmaf(dot, inv_mu, g_la);
         const float Q = mv_sumsq<DIM>(o);
-        const float nu = smooth_abs_sqrt(Q);
+        const float nu = fast_sas(Q);
         const float k1 = la * inv_mu * kInvSqrt2;
-        const float k2 = dmu_s[r] * Q / (nu * nu * nu) * kInvSqrt2;
+        const float k2 = dmu_s[r] * Q * fast_rcp(nu * nu * nu) * kInvSqrt2;
 #pragma unroll
         for (int b = 0; b < B; ++b) dd[b] = ok ? fmaf(k1, dd[b], k2 * o[b]) : 0.f;  // d = do / sqrt2
       }
       store_mv_bpt<DIM>(a.d, dd, Cp, tile, c4, r, j);
       g_bl += dd[0];
-      float y2[B], xr[B], q[G], nrm[G], rinv[G], xn[B], dxn[B], dy2[B];
-      load_mv_bpt<DIM>(y2, a.y2, Cp, tile, c4, r, j);
-      load_mv_bpt<DIM>(xr, a.xr, Cp, tile, c4, r, j);
+      float q[G], nrm[G], rinv[G], xn[B], dxn[B], dy2[B];
       norm_factors<DIM>(xr, sn, q, nrm, rinv);
 #pragma unroll
       for (int b = 0; b < B; ++b) { xn[b] = xr[b] * rinv[A::grade_of(b)]; dy2[b] = 0.f; dxn[b] = 0.f; }
@@ -148,7 +152,7 @@ __global__ void __launch_bounds__(512) tc_b1_kernel(EwArgs a) {
       for (int g = 0; g < G; ++g) {
         const float ddn = -t[g] * rinv[g] * rinv[g];
         g_na[g] = fmaf(ddn * (nrm[g] - 1.f), sn[g] * (1.f - sn[g]), g_na[g]);
-        coef[g] = ddn * sn[g] * q[g] / (nrm[g] * nrm[g] * nrm[g]);
+        coef[g] = ddn * sn[g] * q[g] * fast_rcp(nrm[g] * nrm[g] * nrm[g]);
       }
 #pragma unroll
       for (int b = 0; b < B; ++b) dxn[b] = fmaf(dxn[b], rinv[A::grade_of(b)], coef[A::grade_of(b)] * xr[b]);
@@ -185,11 +189,13 @@ __global__ void __launch_bounds__(512) tc_b3_kernel(EwArgs a) {
     sb[g] = ch_ok ? a.sb[ch * G + g] : 0.f;
     g_sa[g] = 0.f; g_sb[g] = 0.f;
   }
-  for (int64_t tile = blockIdx.x; tile < a.tiles; tile += gridDim.x) {
+  for (int64_t unit = blockIdx.x; unit < 2 * (int64_t)a.tiles; unit += gridDim.x) {
+    const int64_t tile = unit >> 1;
+    const int rbase = (int)(unit & 1) * (kTile / 2);
     const int64_t row0 = tile * kTile;
-#pragma unroll 1
-    for (int s = 0; s < kTile / 8; ++s) {
-      const int r = s * 8 + rr;
+#pragma unroll 2
+    for (int s = 0; s < kTile / 16; ++s) {
+      const int r = rbase + s * 8 + rr;
       const bool ok = ch_ok && row0 + r < a.rows;
       float y1[B], dy[B], sg[G], inv[G], t[G], ds[G];
       load_mv_bpt<DIM>(y1, a.y1, Cp, tile, c4, r, j);
@@ -245,39 +251,21 @@ struct GemmArgs {
   int out_bpt;          // 1: BPT [n16]; 0: reference layout [rows, wn, B]
 };
 
-template <int B>
-__device__ __forceinline__ void g_issue_load(uint8_t* hi, uint64_t* bar, const float* bpt, int cp, int64_t tile, int kc) {
-  mbar_arrive_expect_tx(bar, B * 4096u);
-#pragma unroll 1
-  for (int b = 0; b < B; ++b) {
-    const float* src = bpt + bpt_off(B, cp, tile, b, 2 * kc, 0);
-    bulk_g2s(hi + b * kPS, src, 2048u, bar);
-    bulk_g2s(hi + b * kPS + kKH, src + 512, 2048u, bar);
-  }
-}
-
 template <int DIM>
 __global__ void __launch_bounds__(kThreads, 1) tc_bgemm_kernel(GemmArgs a) {
   using A = Alg<DIM>;
   constexpr int B = A::B, G = A::G;
   extern __shared__ __align__(1024) uint8_t smem[];
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const uint32_t half = B * kPS;
-  uint8_t* bufs = smem;
+  const int tid = threadIdx.x, warp = uniform_warp_idx(), lane = tid & 31;
   const uint32_t img = (uint32_t)a.n16 * a.kmax * 4;
   const uint32_t set_bytes = G * 2 * img;
-  uint8_t* wimg = smem + 4 * half;
+  uint8_t* wimg = smem + (kRing + 1) * B * kPS;
   const int nsets = a.src[1] ? 2 : 1;
   uint64_t* bars = reinterpret_cast<uint64_t*>(wimg + (size_t)nsets * set_bytes);
-  uint64_t* load_bar = bars;
-  uint64_t* mma_bar = bars + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kPipeBars);
+  Pipe p;
+  p.init(smem, bars, B * kPS);
   for (int s = 0; s < nsets; ++s) stage_weight_images<DIM, true>(wimg + (size_t)s * set_bytes, img, a.w[s], a.wk[s], a.wn, a.n16, a.kmax);
-  if (tid == 0) {
-    mbar_init(&load_bar[0], 1); mbar_init(&load_bar[1], 1);
-    mbar_init(&mma_bar[0], 1); mbar_init(&mma_bar[1], 1);
-    mbar_fence_init();
-  }
   const int nmax = (512 / B) / 16 * 16;                       // output channels per pass (TMEM columns / blades)
   const int npass = (a.n16 + nmax - 1) / nmax;
   const uint32_t need = (uint32_t)B * (a.n16 < nmax ? a.n16 : nmax);
@@ -292,14 +280,14 @@ __global__ void __launch_bounds__(kThreads, 1) tc_bgemm_kernel(GemmArgs a) {
   const int per_tile = npass * nk;
   const int my_tiles = (a.tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   const int total_chunks = my_tiles * per_tile;
-  auto issue = [&](int qq) {  // chunk qq of this CTA -> buffer qq & 1
+  auto issue = [&](int qq) {  // chunk qq of this CTA (all lanes of warp 0)
     const int64_t tile = (int64_t)blockIdx.x + (int64_t)(qq / per_tile) * gridDim.x;
     const int kc = (qq % per_tile) % nk;
     const int s = kc < a.nk[0] ? 0 : 1;
-    g_issue_load<B>(bufs + (size_t)(qq & 1) * 2 * half, &load_bar[qq & 1], a.src[s], a.cp[s], tile, s ? kc - a.nk[0] : kc);
+    issue_chunk_load<B>(p, qq, a.src[s], a.cp[s], tile, s ? kc - a.nk[0] : kc);
   };
   int q = 0, loaded = 0;
-  if (tid == 0) for (; loaded < 2 && loaded < total_chunks; ++loaded) issue(loaded);
+  if (warp == 0) for (; loaded < kRing - 1 && loaded < total_chunks; ++loaded) issue(loaded);
   const uint32_t lane_base = (warp & 3) * 32;
   for (int t = 0; t < my_tiles; ++t) {
     const int64_t tile = (int64_t)blockIdx.x + (int64_t)t * gridDim.x;
@@ -309,49 +297,28 @@ __global__ void __launch_bounds__(kThreads, 1) tc_bgemm_kernel(GemmArgs a) {
       const int Np = (a.n16 - n0) < nmax ? (a.n16 - n0) : nmax;
       const uint32_t idesc = idesc_tf32(kTile, Np, false, false);
       for (int kc = 0; kc < nk; ++kc, ++q) {
-        const int buf = q & 1;
-        uint8_t* hi = bufs + (size_t)buf * 2 * half;
-        mbar_wait(&load_bar[buf], (q >> 1) & 1);
-        for (int it = tid; it < B * 2 * kTile; it += kThreads) {
-          const int r = it & (kTile - 1), kh = (it >> 7) & 1, b = it >> 8;
-          const uint32_t off = b * kPS + kh * kKH + r * 16;
-          const float4 x = *reinterpret_cast<const float4*>(hi + off);
-          float4 h, l;
-          split4(x, h, l);
-          *reinterpret_cast<float4*>(hi + off) = h;
-          *reinterpret_cast<float4*>(hi + half + off) = l;
-        }
+        mbar_wait(&p.load_bar[q % kRing], (q / kRing) & 1);
+        if (q >= 1) mbar_wait(p.lo_bar, (q - 1) & 1);
+        split_chunk<B>(p, q);
         fence_async_smem();
         fence_before_sync();
         __syncthreads();
-        if (tid == 0) {
+        if (warp == 0) {
           fence_after_sync();
-          const int s = kc < a.nk[0] ? 0 : 1;
-          const int ks = s ? kc - a.nk[0] : kc;
-          const uint32_t hi_a = smem_addr(hi), lo_a = hi_a + half;
-#pragma unroll 1
-          for (int b = 0; b < B; ++b) {
-            const int g = A::grade_of(b);
-            const uint32_t w_hi = smem_addr(wimg + (size_t)s * set_bytes + (size_t)(2 * g) * img) + (uint32_t)n0 * 16u;
-            const uint64_t a_hi = chunk_desc(hi_a, b), a_lo = chunk_desc(lo_a, b);
-            const uint64_t b_hi = smem_desc(w_hi + 2u * ks * a.n16 * 16u, a.n16 * 16u, 128u);
-            const uint64_t b_lo = smem_desc(w_hi + img + 2u * ks * a.n16 * 16u, a.n16 * 16u, 128u);
-            const uint32_t d = tbase + (uint32_t)b * Np;
-            mma_tf32(d, a_hi, b_hi, idesc, kc > 0);
-            mma_tf32(d, a_hi, b_lo, idesc, 1);
-            mma_tf32(d, a_lo, b_hi, idesc, 1);
+          {
+            const int s = kc < a.nk[0] ? 0 : 1;
+            issue_chunk_mma<DIM>(p, q, tbase, Np, kc > 0, wimg, img, s, 1, set_bytes, a.n16, s ? kc - a.nk[0] : kc, n0, idesc);
           }
-          mma_commit(&mma_bar[buf]);
-          if (loaded == q + 1 && loaded < total_chunks) {
-            if (q >= 1) mbar_wait(&mma_bar[buf ^ 1], ((q - 1) >> 1) & 1);
+          if (loaded == q + kRing - 1 && loaded < total_chunks) {
+            if (q >= 1) mbar_wait(&p.slot_bar[(q - 1) % kRing], ((q - 1) / kRing) & 1);
             issue(loaded);
             ++loaded;
           }
         }
       }
-      mbar_wait(&mma_bar[(q - 1) & 1], ((q - 1) >> 1) & 1);
+      mbar_wait(&p.slot_bar[(q - 1) % kRing], ((q - 1) / kRing) & 1);
       fence_after_sync();
-      if (tid == 0) for (; loaded < q + 2 && loaded < total_chunks; ++loaded) issue(loaded);
+      if (warp == 0) for (; loaded < q + kRing && loaded < total_chunks; ++loaded) issue(loaded);
       // ---- epilogue of this pass: output channels [n0, n0 + Np)
       const int r = lane_base + lane;
       const bool row_ok = row0 + r < a.rows;
@@ -409,29 +376,37 @@ struct DwArgs {
   float* partial; // [grid][G][M][cpb]
 };
 
-constexpr uint32_t kLand = 2048 + 16;  // landing stride of one (plane, 4-channel group) column: [128][4] fp32 + pad
+// Step = (tile, blade, half of the tile's rows): 64 rows = 8 K steps.  The BPT columns of a step ([64 rows][4 ch] = 1 KB
+// each) land through a ring of kDwLand landing slots (loads run kDwLand-1 steps ahead), a conversion pass splits them
+// into hi / lo and re-lays them out as [row][32 channels] operand groups (SWIZZLE_128B_BASE32B), double-buffered so
+// that the conversion of step s+1 overlaps the MMAs of step s.
+constexpr int kDwRows = 64;
+constexpr int kDwLand = 4;
+constexpr uint32_t kLand = kDwRows * 16 + 16;  // landing stride of one 4-channel column (+16: conflict-free conversion reads)
 
 template <int DIM>
 __global__ void __launch_bounds__(256, 1) tc_dw_kernel(DwArgs a) {
   using A = Alg<DIM>;
   constexpr int B = A::B, G = A::G;
   extern __shared__ __align__(1024) uint8_t smem[];
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int na4 = (a.a1 ? 2 : 1) * (a.cpa >> 2);  // 4-channel groups of Acat
+  const int tid = threadIdx.x, warp = uniform_warp_idx(), lane = tid & 31;
+  const int ca4 = a.cpa >> 2;
+  const int na4 = (a.a1 ? 2 : 1) * ca4;  // 4-channel groups of Acat
   const int nb4 = a.cpb >> 2;
+  const int n4 = na4 + nb4;
   const int ga = a.M / 32, gb = (a.cpb + 31) / 32;  // 32-channel operand groups
-  const uint32_t grp = kTile * 128;                 // bytes of one operand group [128 rows][32 ch]
-  uint8_t* op_a = smem;                             // hi groups then lo groups
-  uint8_t* op_b = op_a + 2 * (size_t)ga * grp;
-  uint8_t* land = op_b + 2 * (size_t)gb * grp;      // 2 x (na4 + nb4) columns
-  const uint32_t land_bytes = (uint32_t)(na4 + nb4) * kLand;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(land + 2 * (size_t)land_bytes);
-  uint64_t* load_bar = bars;       // [2]
-  uint64_t* mma_bar = bars + 2;    // [1]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
-  for (uint32_t i = tid; i < (2 * (ga + gb) * grp) >> 4; i += 256) reinterpret_cast<float4*>(smem)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  const uint32_t grp = kDwRows * 128;               // bytes of one operand group [64 rows][32 ch]
+  const uint32_t op_bytes = 2u * (ga + gb) * grp;   // one operand buffer: A hi, A lo, B hi, B lo
+  uint8_t* ops = smem;                              // 2 operand buffers
+  uint8_t* land = ops + 2 * (size_t)op_bytes;       // kDwLand landing slots
+  const uint32_t land_bytes = (uint32_t)n4 * kLand;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(land + (size_t)kDwLand * land_bytes);
+  uint64_t* load_bar = bars;            // [kDwLand]
+  uint64_t* op_bar = bars + kDwLand;    // [2] the MMAs reading an operand buffer have completed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kDwLand + 2);
+  for (uint32_t i = tid; i < (2 * op_bytes) >> 4; i += 256) reinterpret_cast<float4*>(smem)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   if (tid == 0) {
-    mbar_init(&load_bar[0], 1); mbar_init(&load_bar[1], 1); mbar_init(&mma_bar[0], 1);
+    for (int i = 0; i < kDwLand + 2; ++i) mbar_init(&bars[i], 1);
     mbar_fence_init();
   }
   const uint32_t need = (uint32_t)G * a.cpb;
@@ -444,34 +419,33 @@ __global__ void __launch_bounds__(256, 1) tc_dw_kernel(DwArgs a) {
   const uint32_t tbase = *tmem_slot;
   const uint32_t idesc = idesc_tf32(a.M, a.cpb, true, true);
   const int my_tiles = (a.tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-  const int steps = my_tiles * B;  // step = (tile, blade)
-  auto issue = [&](int st) {
-    const int64_t tile = (int64_t)blockIdx.x + (int64_t)(st / B) * gridDim.x;
-    const int b = st % B;
-    uint8_t* dst = land + (size_t)(st & 1) * land_bytes;
-    uint64_t* bar = &load_bar[st & 1];
-    mbar_arrive_expect_tx(bar, (uint32_t)(na4 + nb4) * 2048u);
-    const int ca4 = a.cpa >> 2;
-#pragma unroll 1
-    for (int u = 0; u < na4; ++u) {
-      const float* src = (u < ca4) ? a.a0 + bpt_off(B, a.cpa, tile, b, u, 0) : a.a1 + bpt_off(B, a.cpa, tile, b, u - ca4, 0);
-      bulk_g2s(dst + (size_t)u * kLand, src, 2048u, bar);
+  const int steps = my_tiles * B * 2;  // step = (tile, blade, row half)
+  auto issue = [&](int st) {           // all lanes of warp 0
+    const int64_t tile = (int64_t)blockIdx.x + (int64_t)(st / (2 * B)) * gridDim.x;
+    const int b = (st >> 1) % B, rh = st & 1;
+    uint8_t* dst = land + (size_t)(st % kDwLand) * land_bytes;
+    uint64_t* bar = &load_bar[st % kDwLand];
+    if (lane == 0) mbar_arrive_expect_tx(bar, (uint32_t)n4 * (kDwRows * 16u));
+    __syncwarp();
+    for (int u = lane; u < n4; u += 32) {
+      const float* src;
+      if (u < ca4) src = a.a0 + bpt_off(B, a.cpa, tile, b, u, rh * kDwRows);
+      else if (u < na4) src = a.a1 + bpt_off(B, a.cpa, tile, b, u - ca4, rh * kDwRows);
+      else src = a.bsrc + bpt_off(B, a.cpb_total, tile, b, a.b_c4 + (u - na4), rh * kDwRows);
+      bulk_g2s(dst + (size_t)u * kLand, src, kDwRows * 16u, bar);
     }
-#pragma unroll 1
-    for (int u = 0; u < nb4; ++u)
-      bulk_g2s(dst + (size_t)(na4 + u) * kLand, a.bsrc + bpt_off(B, a.cpb_total, tile, b, a.b_c4 + u, 0), 2048u, bar);
   };
-  if (tid == 0 && steps > 0) issue(0);
+  int loaded = 0;
+  if (warp == 0) for (; loaded < kDwLand - 1 && loaded < steps; ++loaded) issue(loaded);
   uint32_t grade_used = 0;
   for (int st = 0; st < steps; ++st) {
-    const int b = st % B, g = A::grade_of(b);
-    if (tid == 0 && st + 1 < steps) issue(st + 1);  // landing buffer (st+1)&1 was consumed by the conversion of step st-1
-    mbar_wait(&load_bar[st & 1], (st >> 1) & 1);
-    if (st > 0) mbar_wait(&mma_bar[0], (st - 1) & 1);  // the MMAs of the previous step have finished reading the operands
-    const uint8_t* src = land + (size_t)(st & 1) * land_bytes;
-    // conversion: landing [4-group][row][4] -> hi / lo operand groups [row][32] (32-byte units xor (row & 3))
-    const int n4 = na4 + nb4;
-    for (int it = tid; it < kTile * n4; it += 256) {
+    const int b = (st >> 1) % B, g = A::grade_of(b);
+    mbar_wait(&load_bar[st % kDwLand], (st / kDwLand) & 1);
+    if (st >= 2) mbar_wait(&op_bar[st & 1], ((st - 2) >> 1) & 1);  // the MMAs of step st-2 released this operand buffer
+    const uint8_t* src = land + (size_t)(st % kDwLand) * land_bytes;
+    uint8_t* op_a = ops + (size_t)(st & 1) * op_bytes;  // A hi groups, A lo groups
+    uint8_t* op_b = op_a + 2 * (size_t)ga * grp;        // B hi groups, B lo groups
+    for (int it = tid; it < kDwRows * n4; it += 256) {
       const int r = it / n4, u = it - r * n4;
       const float4 x = *reinterpret_cast<const float4*>(src + (size_t)u * kLand + r * 16);
       float4 h, l;
@@ -487,23 +461,28 @@ __global__ void __launch_bounds__(256, 1) tc_dw_kernel(DwArgs a) {
     fence_async_smem();
     fence_before_sync();
     __syncthreads();
-    if (tid == 0) {
-      fence_after_sync();
-      const uint32_t a_hi = smem_addr(op_a), a_lo = a_hi + ga * grp, b_hi = smem_addr(op_b), b_lo = b_hi + gb * grp;
-      const uint32_t d = tbase + (uint32_t)g * a.cpb;
-      uint32_t acc = (grade_used >> g) & 1;
-#pragma unroll 1
-      for (int ks = 0; ks < kTile / 8; ++ks) {
-        mma_tf32(d, desc_mn32b(a_hi, grp, ks), desc_mn32b(b_hi, grp, ks), idesc, acc);
-        mma_tf32(d, desc_mn32b(a_hi, grp, ks), desc_mn32b(b_lo, grp, ks), idesc, 1);
-        mma_tf32(d, desc_mn32b(a_lo, grp, ks), desc_mn32b(b_hi, grp, ks), idesc, 1);
-        acc = 1;
+    if (warp == 0) {
+      {
+        fence_after_sync();
+        const uint64_t a_hi = desc_mn32b(smem_addr(op_a), grp, 0), a_lo = a_hi + ((uint64_t)ga * grp >> 4);
+        const uint64_t b_hi = desc_mn32b(smem_addr(op_b), grp, 0), b_lo = b_hi + ((uint64_t)gb * grp >> 4);
+        const uint32_t d = tbase + (uint32_t)g * a.cpb;
+        const uint32_t acc = (grade_used >> g) & 1;
+#pragma unroll
+        for (int ks = 0; ks < kDwRows / 8; ++ks) {  // one K step = 8 rows = 1024 bytes = 64 descriptor units
+          mma_tf32_w(d, a_hi + ks * 64, b_hi + ks * 64, idesc, ks == 0 ? acc : 1u);
+          mma_tf32_w(d, a_hi + ks * 64, b_lo + ks * 64, idesc, 1);
+          mma_tf32_w(d, a_lo + ks * 64, b_hi + ks * 64, idesc, 1);
+        }
+        mma_commit_w(&op_bar[st & 1]);
       }
-      mma_commit(&mma_bar[0]);
+      __syncwarp();
+      // landing slot (st-1) % kDwLand was consumed by the conversion of step st-1 (before the barrier above)
+      if (loaded < steps) { issue(loaded); ++loaded; }
     }
     grade_used |= 1u << g;
   }
-  if (steps > 0) mbar_wait(&mma_bar[0], (steps - 1) & 1);
+  if (steps > 0) mbar_wait(&op_bar[(steps - 1) & 1], ((steps - 1) >> 1) & 1);
   fence_after_sync();
   // ---- epilogue: D_g -> per-CTA partial [G][M][cpb]; grades this CTA never touched are written as zeros
   float* out = a.partial + (size_t)blockIdx.x * G * a.M * a.cpb;
@@ -542,27 +521,27 @@ struct FinalJob {
 };
 struct FinalJobs { FinalJob j[14]; int count; };
 
+// one warp per output element: lanes stride over the partials, then a fixed xor tree (bit-reproducible)
 __global__ void tc_final_kernel(FinalJobs jobs) {
-  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t idx = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
   for (int k = 0; k < jobs.count; ++k) {
     const FinalJob& jb = jobs.j[k];
     if (idx < jb.n) {
       if (!jb.out) return;
-      size_t src;
+      size_t src, dst;
       if (jb.kind == 0) {
-        src = (size_t)idx;
+        src = dst = (size_t)idx;
       } else {
         const int g = (int)(idx % jb.G), i = (int)((idx / jb.G) % jb.ci), o = (int)(idx / ((int64_t)jb.G * jb.ci));
         src = ((size_t)g * jb.M + jb.m0 + o) * jb.N + i;
+        dst = ((size_t)o * jb.ci_tot + jb.i0 + i) * jb.G + g;
       }
       float s = 0.f;
-      for (int p = 0; p < jb.parts; ++p) s += jb.in[(size_t)p * jb.stride + src];
-      if (jb.kind == 0) {
-        jb.out[idx] = s;
-      } else {
-        const int g = (int)(idx % jb.G), i = (int)((idx / jb.G) % jb.ci), o = (int)(idx / ((int64_t)jb.G * jb.ci));
-        jb.out[((size_t)o * jb.ci_tot + jb.i0 + i) * jb.G + g] = s;
-      }
+      for (int p = lane; p < jb.parts; p += 32) s += jb.in[(size_t)p * jb.stride + src];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      if (lane == 0) jb.out[dst] = s;
       return;
     }
     idx -= jb.n;
@@ -574,12 +553,12 @@ __global__ void tc_final_kernel(FinalJobs jobs) {
 template <int DIM>
 size_t gemm_smem(int nsets, int n16, int kmax) {
   constexpr int B = Alg<DIM>::B, G = Alg<DIM>::G;
-  return (size_t)4 * B * kPS + (size_t)nsets * G * 2 * n16 * kmax * 4 + 64;
+  return (size_t)(kRing + 1) * B * kPS + (size_t)nsets * G * 2 * n16 * kmax * 4 + 96;
 }
 template <int DIM>
 size_t dw_smem(int M, int na4, int cpb) {
   const int ga = M / 32, gb = (cpb + 31) / 32;
-  return (size_t)2 * (ga + gb) * kTile * 128 + (size_t)2 * (na4 + cpb / 4) * kLand + 64;
+  return (size_t)2 * 2 * (ga + gb) * kDwRows * 128 + (size_t)kDwLand * (na4 + cpb / 4) * kLand + 96;
 }
 constexpr size_t kSmemMax = 227 * 1024;
 
@@ -613,7 +592,7 @@ int make_bwd_plan(const csmpn_block_desc& d, BwdPlan* p) {
     return CSMPN_ERR_UNSUPPORTED;
   if (p->n16 > 4 * p->nbw) return CSMPN_ERR_UNSUPPORTED;
   const int sms = sm_count_cached();
-  p->grid_ew = p->tiles < 2 * sms ? (p->tiles > 0 ? p->tiles : 1) : 2 * sms;
+  p->grid_ew = 2 * p->tiles < 2 * sms ? (p->tiles > 0 ? 2 * p->tiles : 1) : 2 * sms;
   p->grid_dw = p->tiles < sms ? (p->tiles > 0 ? p->tiles : 1) : sms;
   const size_t t = (size_t)bpt_floats(B, d.rows, p->Cp);
   size_t o = 0;
@@ -751,7 +730,7 @@ int launch_bwd(const csmpn_block_desc& d, const csmpn_block_grads& g, void* work
   fj.count = k;
   int64_t total = 0;
   for (int i = 0; i < k; ++i) total += fj.j[i].n;
-  tc_final_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(fj);
+  tc_final_kernel<<<(unsigned)((total * 32 + 255) / 256), 256, 0, stream>>>(fj);
   CSMPN_LAUNCH_CHECK("tc_final_kernel");
   return CSMPN_OK;
 }

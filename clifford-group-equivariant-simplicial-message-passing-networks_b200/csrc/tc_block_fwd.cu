@@ -31,49 +31,23 @@ struct FwdArgs {
   float* y;
   const float* res;
   int out_bpt, has_b1;
+  long long* dbg;  // optional timeline buffer (csmpn_tc_debug_buffer): CTA 0 records clock64() stamps of threads 0 and 64
 };
-
-struct Pipe {
-  uint64_t* load_bar;  // [2] bulk copies of a chunk have landed
-  uint64_t* mma_bar;   // [2] the MMAs that read a chunk buffer have completed
-  uint8_t* bufs;       // 2 x (hi | lo)
-  uint32_t half;       // bytes of hi (or lo) of one chunk buffer
-};
-
-// ---- producer 1: bulk copies of one 8-channel chunk of a BPT tensor (thread 0) ---------------------------------
-template <int B>
-__device__ __forceinline__ void issue_chunk_load(const Pipe& p, int buf, const float* bpt, int cp, int64_t tile, int kc) {
-  uint8_t* hi = p.bufs + (size_t)buf * 2 * p.half;
-  mbar_arrive_expect_tx(&p.load_bar[buf], B * 4096u);
-#pragma unroll 1
-  for (int b = 0; b < B; ++b) {
-    const float* src = bpt + bpt_off(B, cp, tile, b, 2 * kc, 0);
-    bulk_g2s(hi + b * kPS, src, 2048u, &p.load_bar[buf]);
-    bulk_g2s(hi + b * kPS + kKH, src + 512, 2048u, &p.load_bar[buf]);
-  }
-}
-// split pass: hi in place, lo beside it
-template <int B>
-__device__ __forceinline__ void split_chunk(const Pipe& p, int buf) {
-  uint8_t* hi = p.bufs + (size_t)buf * 2 * p.half;
-  uint8_t* lo = hi + p.half;
-  for (int it = threadIdx.x; it < B * 2 * kTile; it += kThreads) {
-    const int r = it & (kTile - 1), kh = (it >> 7) & 1, b = it >> 8;
-    const uint32_t off = b * kPS + kh * kKH + r * 16;
-    const float4 x = *reinterpret_cast<const float4*>(hi + off);
-    float4 h, l;
-    split4(x, h, l);
-    *reinterpret_cast<float4*>(hi + off) = h;
-    *reinterpret_cast<float4*>(lo + off) = l;
-  }
-}
+#define TSTAMP(code)                                                                         \
+  do {                                                                                       \
+    if (a.dbg && blockIdx.x == 0 && (tid == 0 || tid == 64) && dbg_n < 250) {                \
+      a.dbg[(tid ? 512 : 0) + 2 * dbg_n] = (code);                                           \
+      a.dbg[(tid ? 512 : 0) + 2 * dbg_n + 1] = clock64();                                    \
+      ++dbg_n;                                                                               \
+    }                                                                                        \
+  } while (0)
 
 // ---- producer 2: gather / concatenate API-layout rows, transpose to planes, split (all threads) ------------------
 template <int DIM>
-__device__ __forceinline__ void stage_chunk_api(const Pipe& p, int buf, const FwdArgs& a, int64_t row0, int kc) {
+__device__ __forceinline__ void stage_chunk_api(const Pipe& p, int q, const FwdArgs& a, int64_t row0, int kc) {
   constexpr int B = Alg<DIM>::B, H = B / 4, PPR = 8 * H;
-  uint8_t* hi = p.bufs + (size_t)buf * 2 * p.half;
-  uint8_t* lo = hi + p.half;
+  uint8_t* hi = p.slot(q);
+  uint8_t* lo = p.lo;
   for (int it = threadIdx.x; it < kTile * PPR; it += kThreads) {
     const int r = it / PPR, pc = it - r * PPR;
     const int cl = pc / H, h = pc - cl * H;
@@ -112,9 +86,9 @@ __device__ __forceinline__ void stage_chunk_api(const Pipe& p, int buf, const Fw
 }
 // copy of the assembled input rows for the weight-gradient GEMM of the backward: chunk buffer -> BPT (coalesced)
 template <int B>
-__device__ __forceinline__ void save_chunk_bpt(const Pipe& p, int buf, float* dst, int cp, int64_t tile, int kc) {
-  const uint8_t* hi = p.bufs + (size_t)buf * 2 * p.half;
-  const uint8_t* lo = hi + p.half;
+__device__ __forceinline__ void save_chunk_bpt(const Pipe& p, int q, float* dst, int cp, int64_t tile, int kc) {
+  const uint8_t* hi = p.slot(q);
+  const uint8_t* lo = p.lo;
   for (int it = threadIdx.x; it < B * 2 * kTile; it += kThreads) {
     const int r = it & (kTile - 1), kh = (it >> 7) & 1, b = it >> 8;
     const uint32_t off = b * kPS + kh * kKH + r * 16;
@@ -124,30 +98,6 @@ __device__ __forceinline__ void save_chunk_bpt(const Pipe& p, int buf, float* ds
   }
 }
 
-// ---- MMA issue for one chunk (thread 0): nsets weight sets, set s accumulates at column offset s*B*Cp -------------
-template <int DIM>
-__device__ __forceinline__ void issue_chunk_mma(const Pipe& p, int buf, uint32_t tbase, int Cp, int kc, const uint8_t* wimg0,
-                                                uint32_t img_bytes, int nsets, uint32_t set_bytes, uint32_t idesc) {
-  using A = Alg<DIM>;
-  constexpr int B = A::B;
-  const uint32_t hi = smem_addr(p.bufs + (size_t)buf * 2 * p.half), lo = hi + p.half;
-#pragma unroll 1
-  for (int s = 0; s < nsets; ++s) {
-#pragma unroll 1
-    for (int b = 0; b < B; ++b) {
-      const int g = A::grade_of(b);
-      const uint32_t w_hi = smem_addr(wimg0 + (size_t)s * set_bytes + (size_t)(2 * g) * img_bytes);
-      const uint64_t a_hi = chunk_desc(hi, b), a_lo = chunk_desc(lo, b);
-      const uint64_t b_hi = desc_kmajor(w_hi, Cp, kc), b_lo = desc_kmajor(w_hi + img_bytes, Cp, kc);
-      const uint32_t d = tbase + (uint32_t)(s * B + b) * Cp;
-      mma_tf32(d, a_hi, b_hi, idesc, kc > 0);
-      mma_tf32(d, a_hi, b_lo, idesc, 1);
-      mma_tf32(d, a_lo, b_hi, idesc, 1);
-    }
-  }
-  mma_commit(&p.mma_bar[buf]);
-}
-
 // =====================================================================================================================
 // F1: MVLinear (W1) + bias + MVSiLU
 template <int DIM, bool BPT_IN>
@@ -155,31 +105,23 @@ __global__ void __launch_bounds__(kThreads, 1) tc_f1_kernel(FwdArgs a) {
   using A = Alg<DIM>;
   constexpr int B = A::B, G = A::G;
   extern __shared__ __align__(1024) uint8_t smem[];
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = uniform_warp_idx(), lane = tid & 31;
   const int C = a.C, Cp = a.Cp, nk = a.kin8 / 8;
-  Pipe p;
-  p.half = B * kPS;
-  p.bufs = smem;
   const uint32_t img = (uint32_t)a.kin8 * Cp * 4;
-  uint8_t* wimg = smem + 4 * p.half;
+  uint8_t* wimg = smem + (kRing + 1) * B * kPS;
   float* b1_s = reinterpret_cast<float*>(wimg + (size_t)G * 2 * img);
   float* sa_s = b1_s + Cp;
   float* sb_s = sa_s + Cp * G;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sb_s + Cp * G);
-  p.load_bar = bars;
-  p.mma_bar = bars + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kPipeBars);
+  Pipe p;
+  p.init(smem, bars, B * kPS);
 
   stage_weight_images<DIM, false>(wimg, img, a.w1, C, a.cin, Cp, a.kin8);
   for (int i = tid; i < Cp; i += kThreads) b1_s[i] = (i < C && a.has_b1) ? a.b1[i] : 0.f;
   for (int i = tid; i < Cp * G; i += kThreads) {
     sa_s[i] = (i < C * G) ? a.sa[i] : 0.f;
     sb_s[i] = (i < C * G) ? a.sb[i] : 0.f;
-  }
-  if (tid == 0) {
-    mbar_init(&p.load_bar[0], 1); mbar_init(&p.load_bar[1], 1);
-    mbar_init(&p.mma_bar[0], 1); mbar_init(&p.mma_bar[1], 1);
-    mbar_fence_init();
   }
   const uint32_t tcols = (B * Cp <= 32) ? 32 : (B * Cp <= 64) ? 64 : (B * Cp <= 128) ? 128 : (B * Cp <= 256) ? 256 : 512;
   if (warp == 0) tmem_alloc(tmem_slot, tcols);
@@ -193,45 +135,46 @@ __global__ void __launch_bounds__(kThreads, 1) tc_f1_kernel(FwdArgs a) {
   const int total_chunks = my_tiles * nk;
   auto tile_of = [&](int q) { return (int64_t)blockIdx.x + (int64_t)(q / nk) * gridDim.x; };
 
-  int q = 0;       // chunk sequence number of this CTA; chunk q lives in buffer q & 1
-  int loaded = 0;  // thread 0: chunks whose bulk copies have been issued
-  if (BPT_IN && tid == 0) {
-    for (; loaded < 2 && loaded < total_chunks; ++loaded)
+  int q = 0;       // chunk sequence number of this CTA; chunk q lives in raw slot q % kRing
+  int loaded = 0;  // warp 0: chunks whose bulk copies have been issued
+  if (BPT_IN && warp == 0) {
+    for (; loaded < kRing - 1 && loaded < total_chunks; ++loaded)
       issue_chunk_load<B>(p, loaded, a.p0, a.in_cp, tile_of(loaded), loaded % nk);
   }
   for (int t = 0; t < my_tiles; ++t) {
     const int64_t tile = (int64_t)blockIdx.x + (int64_t)t * gridDim.x;
     const int64_t row0 = tile * kTile;
     for (int kc = 0; kc < nk; ++kc, ++q) {
-      const int buf = q & 1;
       if (BPT_IN) {
-        mbar_wait(&p.load_bar[buf], (q >> 1) & 1);
-        split_chunk<B>(p, buf);
+        mbar_wait(&p.load_bar[q % kRing], (q / kRing) & 1);
+        if (q >= 1) mbar_wait(p.lo_bar, (q - 1) & 1);
+        split_chunk<B>(p, q);
       } else {
-        if (q >= 2) mbar_wait(&p.mma_bar[buf], ((q - 2) >> 1) & 1);  // MMAs of chunk q-2 have released this buffer
-        stage_chunk_api<DIM>(p, buf, a, row0, kc);
+        if (q >= kRing) mbar_wait(&p.slot_bar[q % kRing], ((q - kRing) / kRing) & 1);  // MMAs of chunk q-kRing released the slot
+        if (q >= 1) mbar_wait(p.lo_bar, (q - 1) & 1);
+        stage_chunk_api<DIM>(p, q, a, row0, kc);
       }
       fence_async_smem();
       fence_before_sync();
       __syncthreads();
-      if (!BPT_IN && a.save_x0) save_chunk_bpt<B>(p, buf, a.save_x0, round_up(a.kin8, 16), tile, kc);
-      if (tid == 0) {
+      if (!BPT_IN && a.save_x0) save_chunk_bpt<B>(p, q, a.save_x0, round_up(a.kin8, 16), tile, kc);
+      if (warp == 0) {
         fence_after_sync();
-        issue_chunk_mma<DIM>(p, buf, tbase, Cp, kc, wimg, img, 1, 0, idesc);
-        if (BPT_IN && loaded == q + 1 && loaded < total_chunks) {
-          // buffer (q+1)&1 was read by the MMAs of chunk q-1: reload it for chunk q+1 as soon as they are done
-          if (q >= 1) mbar_wait(&p.mma_bar[buf ^ 1], ((q - 1) >> 1) & 1);
-          issue_chunk_load<B>(p, buf ^ 1, a.p0, a.in_cp, tile_of(loaded), loaded % nk);
+        issue_chunk_mma<DIM>(p, q, tbase, Cp, kc > 0, wimg, img, 0, 1, 0, Cp, kc, 0, idesc);
+        if (BPT_IN && loaded == q + kRing - 1 && loaded < total_chunks) {
+          // slot (q-1) % kRing was read by the MMAs of chunk q-1: reload it as soon as they are done
+          if (q >= 1) mbar_wait(&p.slot_bar[(q - 1) % kRing], ((q - 1) / kRing) & 1);
+          issue_chunk_load<B>(p, loaded, a.p0, a.in_cp, tile_of(loaded), loaded % nk);
           ++loaded;
         }
       }
     }
     // ---- epilogue: all MMAs of this tile have completed
-    mbar_wait(&p.mma_bar[(q - 1) & 1], ((q - 1) >> 1) & 1);
+    mbar_wait(&p.slot_bar[(q - 1) % kRing], ((q - 1) / kRing) & 1);
     fence_after_sync();
-    if (BPT_IN && tid == 0) {  // both chunk buffers are free: prefetch the next tile's first chunks under the epilogue
-      for (; loaded < q + 2 && loaded < total_chunks; ++loaded)
-        issue_chunk_load<B>(p, loaded & 1, a.p0, a.in_cp, tile_of(loaded), loaded % nk);
+    if (BPT_IN && warp == 0) {  // every slot is free: prefetch the next tile's first chunks under the epilogue
+      for (; loaded < q + kRing && loaded < total_chunks; ++loaded)
+        issue_chunk_load<B>(p, loaded, a.p0, a.in_cp, tile_of(loaded), loaded % nk);
     }
     const int r = (warp & 3) * 32 + lane;
     const bool row_ok = row0 + r < a.rows;
@@ -284,23 +227,20 @@ __global__ void __launch_bounds__(kThreads, 1) tc_f2_kernel(FwdArgs a) {
   using A = Alg<DIM>;
   constexpr int B = A::B, G = A::G, P = A::P;
   extern __shared__ __align__(1024) uint8_t smem[];
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = uniform_warp_idx(), lane = tid & 31;
   const int C = a.C, Cp = a.Cp, nk = Cp / 8;
-  Pipe p;
-  p.half = B * kPS;
-  p.bufs = smem;
   const uint32_t img = (uint32_t)Cp * Cp * 4;
   const uint32_t set_bytes = G * 2 * img;
-  uint8_t* wimg = smem + 4 * p.half;  // set 0: linear_right, set 1: linear_left
+  uint8_t* wimg = smem + (kRing + 1) * B * kPS;  // set 0: linear_right, set 1: linear_left
   float* sn_s = reinterpret_cast<float*>(wimg + 2 * (size_t)set_bytes);  // sigmoid(normalization.a) [Cp][G]
   float* wv_s = sn_s + Cp * G;                                           // path weights [Cp][P]
   float* bl_s = wv_s + Cp * P;
   float* la_s = bl_s + Cp;
   float* rowsum_s = la_s + Cp;                                           // [4][128]
   uint64_t* bars = reinterpret_cast<uint64_t*>(rowsum_s + 4 * kTile);
-  p.load_bar = bars;
-  p.mma_bar = bars + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kPipeBars);
+  Pipe p;
+  p.init(smem, bars, B * kPS);
 
   stage_weight_images<DIM, false>(wimg, img, a.wr, C, C, Cp, Cp);
   stage_weight_images<DIM, false>(wimg + set_bytes, img, a.wl, C, C, Cp, Cp);
@@ -309,11 +249,6 @@ __global__ void __launch_bounds__(kThreads, 1) tc_f2_kernel(FwdArgs a) {
   for (int i = tid; i < Cp; i += kThreads) {
     bl_s[i] = (i < C) ? a.bl[i] : 0.f;
     la_s[i] = (i < C) ? a.la[i] : 0.f;
-  }
-  if (tid == 0) {
-    mbar_init(&p.load_bar[0], 1); mbar_init(&p.load_bar[1], 1);
-    mbar_init(&p.mma_bar[0], 1); mbar_init(&p.mma_bar[1], 1);
-    mbar_fence_init();
   }
   const uint32_t need = 2 * B * Cp;
   const uint32_t tcols = need <= 32 ? 32 : need <= 64 ? 64 : need <= 128 ? 128 : need <= 256 ? 256 : 512;
@@ -330,34 +265,44 @@ __global__ void __launch_bounds__(kThreads, 1) tc_f2_kernel(FwdArgs a) {
   const uint32_t col_r = 0, col_l = B * Cp;
   const uint32_t lane_base = (warp & 3) * 32;
 
-  int q = 0, loaded = 0;
-  if (tid == 0) {
-    for (; loaded < 2 && loaded < total_chunks; ++loaded) issue_chunk_load<B>(p, loaded, a.y2, Cp, tile_of(loaded), loaded % nk);
+  int q = 0, loaded = 0, dbg_n = 0;
+  TSTAMP(1);
+  if (warp == 0) {
+    for (; loaded < kRing - 1 && loaded < total_chunks; ++loaded) issue_chunk_load<B>(p, loaded, a.y2, Cp, tile_of(loaded), loaded % nk);
   }
   for (int t = 0; t < my_tiles; ++t) {
     const int64_t tile = (int64_t)blockIdx.x + (int64_t)t * gridDim.x;
     const int64_t row0 = tile * kTile;
     for (int kc = 0; kc < nk; ++kc, ++q) {
-      const int buf = q & 1;
-      mbar_wait(&p.load_bar[buf], (q >> 1) & 1);
-      split_chunk<B>(p, buf);
+      TSTAMP(10);
+      mbar_wait(&p.load_bar[q % kRing], (q / kRing) & 1);
+      TSTAMP(11);
+      if (q >= 1) mbar_wait(p.lo_bar, (q - 1) & 1);
+      TSTAMP(12);
+      split_chunk<B>(p, q);
       fence_async_smem();
       fence_before_sync();
+      TSTAMP(13);
       __syncthreads();
-      if (tid == 0) {
+      TSTAMP(14);
+      if (warp == 0) {
         fence_after_sync();
-        issue_chunk_mma<DIM>(p, buf, tbase, Cp, kc, wimg, img, 2, set_bytes, idesc);
-        if (loaded == q + 1 && loaded < total_chunks) {
-          if (q >= 1) mbar_wait(&p.mma_bar[buf ^ 1], ((q - 1) >> 1) & 1);
-          issue_chunk_load<B>(p, buf ^ 1, a.y2, Cp, tile_of(loaded), loaded % nk);
+        issue_chunk_mma<DIM>(p, q, tbase, Cp, kc > 0, wimg, img, 0, 2, set_bytes, Cp, kc, 0, idesc);
+        TSTAMP(15);
+        if (loaded == q + kRing - 1 && loaded < total_chunks) {
+          if (q >= 1) mbar_wait(&p.slot_bar[(q - 1) % kRing], ((q - 1) / kRing) & 1);
+          issue_chunk_load<B>(p, loaded, a.y2, Cp, tile_of(loaded), loaded % nk);
           ++loaded;
         }
+        TSTAMP(16);
       }
     }
-    mbar_wait(&p.mma_bar[(q - 1) & 1], ((q - 1) >> 1) & 1);
+    TSTAMP(20);
+    mbar_wait(&p.slot_bar[(q - 1) % kRing], ((q - 1) / kRing) & 1);
     fence_after_sync();
-    if (tid == 0) {
-      for (; loaded < q + 2 && loaded < total_chunks; ++loaded) issue_chunk_load<B>(p, loaded & 1, a.y2, Cp, tile_of(loaded), loaded % nk);
+    TSTAMP(21);
+    if (warp == 0) {
+      for (; loaded < q + kRing && loaded < total_chunks; ++loaded) issue_chunk_load<B>(p, loaded, a.y2, Cp, tile_of(loaded), loaded % nk);
     }
     const int r = lane_base + lane;
     const bool row_ok = row0 + r < a.rows;
@@ -365,40 +310,43 @@ __global__ void __launch_bounds__(kThreads, 1) tc_f2_kernel(FwdArgs a) {
     float rs = 0.f;
     for (int c4 = warp >> 2; c4 < (Cp >> 2); c4 += 4) {
       float4 y2v[B];
+      float xr[B][4], o[B][4];
 #pragma unroll
       for (int b = 0; b < B; ++b) y2v[b] = *reinterpret_cast<const float4*>(a.y2 + bpt_off(B, Cp, tile, b, c4, r));
 #pragma unroll
+      for (int b = 0; b < B; ++b) tmem_ld4(tmem_at(tbase, lane_base, col_r + b * Cp + c4 * 4), xr[b]);
+#pragma unroll
+      for (int b = 0; b < B; ++b) tmem_ld4(tmem_at(tbase, lane_base, col_l + b * Cp + c4 * 4), o[b]);
+      tmem_wait_ld();
+#pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int ch = c4 * 4 + j;
-        float xr[B], o[B], y2[B], qv[G], nrm[G], rinv[G];
+        float xn[B], oj[B], y2[B], qv[G], nrm[G], rinv[G];
 #pragma unroll
-        for (int b = 0; b < B; ++b) {
-          tmem_ld1(tmem_at(tbase, lane_base, col_r + b * Cp + ch), xr[b]);
-          tmem_ld1(tmem_at(tbase, lane_base, col_l + b * Cp + ch), o[b]);
-        }
+        for (int b = 0; b < B; ++b) { xn[b] = xr[b][j]; oj[b] = o[b][j]; }
 #pragma unroll
         for (int b = 0; b < B; ++b) y2[b] = j == 0 ? y2v[b].x : j == 1 ? y2v[b].y : j == 2 ? y2v[b].z : y2v[b].w;
-        tmem_wait_ld();
-        norm_factors<DIM>(xr, sn_s + ch * G, qv, nrm, rinv);
+        norm_factors<DIM>(xn, sn_s + ch * G, qv, nrm, rinv);
 #pragma unroll
-        for (int b = 0; b < B; ++b) xr[b] *= rinv[A::grade_of(b)];
-        o[0] += bl_s[ch];
-        A::template wgp<false>(y2, xr, wv_s + ch * P, nullptr, o);
+        for (int b = 0; b < B; ++b) xn[b] *= rinv[A::grade_of(b)];
+        oj[0] += bl_s[ch];
+        A::template wgp<false>(y2, xn, wv_s + ch * P, nullptr, oj);
         const bool ok = row_ok && ch < C;
 #pragma unroll
-        for (int b = 0; b < B; ++b) o[b] = ok ? o[b] * kInvSqrt2 : 0.f;
-        if (ok) rs += smooth_abs_sqrt(mv_sumsq<DIM>(o));
+        for (int b = 0; b < B; ++b) oj[b] = ok ? oj[b] * kInvSqrt2 : 0.f;
+        if (ok) rs += fast_sas(mv_sumsq<DIM>(oj));
 #pragma unroll
-        for (int b = 0; b < B; ++b)
-          asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(tmem_at(tbase, lane_base, col_l + b * Cp + ch)),
-                       "r"(__float_as_uint(o[b]))
-                       : "memory");
+        for (int b = 0; b < B; ++b) o[b][j] = oj[b];
       }
+#pragma unroll
+      for (int b = 0; b < B; ++b) tmem_st4(tmem_at(tbase, lane_base, col_l + b * Cp + c4 * 4), o[b]);
     }
     tmem_wait_st();
+    TSTAMP(22);
     rowsum_s[(warp >> 2) * kTile + r] = rs;
     __syncthreads();
-    const float inv_mu = 1.f / ((rowsum_s[r] + rowsum_s[kTile + r] + rowsum_s[2 * kTile + r] + rowsum_s[3 * kTile + r]) / (float)C + kEps);
+    TSTAMP(23);
+    const float inv_mu = fast_rcp((rowsum_s[r] + rowsum_s[kTile + r] + rowsum_s[2 * kTile + r] + rowsum_s[3 * kTile + r]) / (float)C + kEps);
     // ---- pass 2: saves, MVLayerNorm scale, residual, output
     for (int c4 = warp >> 2; c4 < (Cp >> 2); c4 += 4) {
       float o[B][4];
@@ -450,6 +398,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_f2_kernel(FwdArgs a) {
       }
     }
     fence_before_sync();
+    TSTAMP(24);
   }
   fence_before_sync();
   __syncthreads();
@@ -457,15 +406,20 @@ __global__ void __launch_bounds__(kThreads, 1) tc_f2_kernel(FwdArgs a) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+long long*& debug_buffer() {
+  static long long* p = nullptr;
+  return p;
+}
+
 template <int DIM>
 size_t f1_smem(int Cp, int kin8) {
   constexpr int B = Alg<DIM>::B, G = Alg<DIM>::G;
-  return (size_t)4 * B * kPS + (size_t)G * 2 * kin8 * Cp * 4 + (size_t)Cp * (1 + 2 * G) * 4 + 64;
+  return (size_t)(kRing + 1) * B * kPS + (size_t)G * 2 * kin8 * Cp * 4 + (size_t)Cp * (1 + 2 * G) * 4 + 96;
 }
 template <int DIM>
 size_t f2_smem(int Cp) {
   constexpr int B = Alg<DIM>::B, G = Alg<DIM>::G, P = Alg<DIM>::P;
-  return (size_t)4 * B * kPS + (size_t)2 * G * 2 * Cp * Cp * 4 + (size_t)Cp * (G + P + 2) * 4 + 4 * kTile * 4 + 64;
+  return (size_t)(kRing + 1) * B * kPS + (size_t)2 * G * 2 * Cp * Cp * 4 + (size_t)Cp * (G + P + 2) * 4 + 4 * kTile * 4 + 96;
 }
 constexpr size_t kSmemMax = 227 * 1024;
 
@@ -497,6 +451,7 @@ int launch_fwd(const csmpn_block_desc& d, cudaStream_t stream) {
   a.w1 = d.w1; a.b1 = d.b1; a.sa = d.sa; a.sb = d.sb; a.wr = d.wr; a.na = d.na; a.wl = d.wl; a.bl = d.bl; a.wp = d.wp; a.la = d.la;
   a.save_y1 = d.save_y1; a.y2 = d.save_y2; a.save_xr = d.save_xr; a.save_o = d.save_o; a.save_x0 = d.save_x0;
   a.y = d.y; a.res = d.res; a.out_bpt = d.out_bpt; a.has_b1 = d.has_b1;
+  a.dbg = debug_buffer();
   if (!a.y2 || !a.y) return CSMPN_ERR_BAD_ARG;
   if (a.in_bpt && (d.mode != 0 || d.c1 || d.c2)) return CSMPN_ERR_BAD_ARG;
   if (a.out_bpt && d.res) return CSMPN_ERR_BAD_ARG;
@@ -525,6 +480,7 @@ int tc_block_fwd(int dim, const csmpn_block_desc* d, cudaStream_t stream) {
   if (dim == 3) return tcb::launch_fwd<3>(*d, stream);
   return CSMPN_ERR_UNSUPPORTED;
 }
+void tc_set_debug_buffer(long long* p) { tcb::debug_buffer() = p; }
 bool tc_block_supported(int dim, int c_in, int c) {
   if (dim == 2) return tcb::fwd_supported<2>(c_in, c);
   if (dim == 3) return tcb::fwd_supported<3>(c_in, c);

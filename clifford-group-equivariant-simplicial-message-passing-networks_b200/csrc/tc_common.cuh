@@ -131,6 +131,23 @@ __host__ __device__ constexpr uint32_t idesc_tf32(int M, int N, bool a_mn, bool 
   return (1u << 4) | (2u << 7) | (2u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
          ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
+// One elected lane of a fully converged warp.  The MMA-issuing code is executed by the WHOLE warp with only the
+// tcgen05 instructions predicated on the elected lane: descriptors then live in uniform registers.  (Issuing from
+// inside an `if (lane == 0)` region costs ~65 cycles per MMA: every operand goes through an R2UR waterfall loop.)
+__device__ __forceinline__ uint32_t elect_one_sync() {
+  uint32_t pred = 0, laneid = 0;
+  asm volatile(
+      "{\n\t.reg .b32 %%rx;\n\t.reg .pred %%px;\n\t"
+      "elect.sync %%rx|%%px, %2;\n\t"
+      "@%%px mov.s32 %1, 1;\n\t"
+      "mov.s32 %0, %%rx;\n\t}"
+      : "+r"(laneid), "+r"(pred)
+      : "r"(0xFFFFFFFFu));
+  return pred;
+}
+// warp index as a provably warp-uniform value
+__device__ __forceinline__ int uniform_warp_idx() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
+
 // D[tmem] (+)= A[smem] * B[smem]; issued by ONE thread
 __device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -138,6 +155,14 @@ __device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
+}
+// warp-collective forms: call from a converged warp, one elected lane issues
+__device__ __forceinline__ void mma_tf32_w(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  if (elect_one_sync()) mma_tf32(d_tmem, adesc, bdesc, idesc, accumulate);
+}
+__device__ __forceinline__ void mma_commit(uint64_t* bar);
+__device__ __forceinline__ void mma_commit_w(uint64_t* bar) {
+  if (elect_one_sync()) mma_commit(bar);
 }
 // all MMAs issued so far by this thread -> one arrival on the mbarrier when they have completed
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {

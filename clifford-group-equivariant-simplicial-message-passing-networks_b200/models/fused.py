@@ -365,9 +365,17 @@ def _need_grad(*tensors_and_params):
 TC_BACKWARD_READY = True
 
 
-def _block_uses_tc(algebra, layer, need_grad) -> bool:
+def tc_min_rows() -> int:
+    """Rows below which a block stays on the FP32 SIMT engine: the tensor-core engine runs a block as several
+    persistent kernels over 128-row tiles and needs a few tiles per SM to amortise their pipelines."""
+    return int(os.environ.get("CSMPN_TC_MIN_ROWS", "32768"))
+
+
+def _block_uses_tc(algebra, layer, need_grad, rows=None) -> bool:
     lin = layer[0]
     if algebra.dim not in (2, 3) or (need_grad and not TC_BACKWARD_READY):
+        return False
+    if rows is not None and rows < tc_min_rows():
         return False
     return tc_supported(algebra.dim, lin.in_features, lin.out_features)
 
@@ -385,20 +393,21 @@ def block_forward(algebra, layer, x, p1=None, p2=None, res=None, mode=0, sgraph=
     params = _block_params(layer)
     need_grad = _need_grad(x, p1, p2, res, *params)
     cfg = {"dim": algebra.dim, "mode": mode, "sgraph": sgraph, "need_grad": need_grad}
-    if in_bpt or _block_uses_tc(algebra, layer, need_grad):
+    rows_now = bpt_rows if in_bpt else (sgraph.csr.n_pairs if mode == 1 else x.shape[0])
+    if in_bpt or _block_uses_tc(algebra, layer, need_grad, rows_now):
         cfg.update(in_bpt=in_bpt, out_bpt=out_bpt, rows=bpt_rows, c_in=layer[0].in_features)
         return TcBlockFn.apply(cfg, x, p1, p2, res, *params)
     return FusedBlockFn.apply(cfg, x, p1, p2, res, *params)
 
 
-def _chain_uses_tc(algebra, blocks, need_grad) -> bool:
-    return all(_block_supported(b) for b in blocks) and all(_block_uses_tc(algebra, b, need_grad) for b in blocks)
+def _chain_uses_tc(algebra, blocks, need_grad, rows) -> bool:
+    return all(_block_supported(b) for b in blocks) and all(_block_uses_tc(algebra, b, need_grad, rows) for b in blocks)
 
 
 def mlp_forward(algebra, blocks, x, p1=None, p2=None, res=None, mode=0, sgraph=None, rows=None):
     """A CEMLP (list of blocks): on the tensor-core engine the tensors between blocks stay in the BPT layout."""
     need_grad = _need_grad(x, p1, p2, res, *[t for b in blocks for t in _block_params(b)])
-    tc = len(blocks) > 1 and _chain_uses_tc(algebra, blocks, need_grad)
+    tc = len(blocks) > 1 and _chain_uses_tc(algebra, blocks, need_grad, rows)
     u = block_forward(algebra, blocks[0], x, p1, p2, res if len(blocks) == 1 else None, mode=mode, sgraph=sgraph, out_bpt=tc)
     for k, blk in enumerate(blocks[1:]):
         last = k == len(blocks) - 2

@@ -208,6 +208,9 @@ typedef struct csmpn_block_grads {
 int csmpn_block_fwd(int dim, const csmpn_block_desc* desc, csmpn_stream_t stream);
 /* 1 if the tensor-core engine handles a block of this shape (c_in input channels, width c) in algebra dimension dim */
 int csmpn_block_tc_supported(int dim, int c_in, int c);
+/* Diagnostics: when set to a device buffer of 1024 int64 (NULL to disable), the second forward kernel of engine 1 records
+ * (phase code, clock64) pairs of two threads of CTA 0: the per-tile timeline used to tune the pipeline (tools/tc_timeline.py). */
+int csmpn_tc_debug_buffer(int64_t* device_buffer_1024);
 /* number of floats of a BPT tensor with `rows` rows and `channels` channels (padded to a multiple of 16) */
 int64_t csmpn_bpt_floats(int dim, int64_t rows, int channels);
 /* workspace for csmpn_block_bwd (device bytes; zero-initialised by the call itself) */

@@ -9,6 +9,12 @@ from oracle import layers_ref as R
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
 
+
+@pytest.fixture(autouse=True)
+def _force_tc_for_small_batches(monkeypatch):
+    """the default policy keeps blocks with few rows on the SIMT engine; the parity cases here are small on purpose"""
+    monkeypatch.setenv("CSMPN_TC_MIN_ROWS", "0")
+
 CASES = [
     # name, metric, C, T, complexes, simplices/complex, pairs/complex, aggr
     ("motion", (1, 1, 1), 28, 3, 6, 47, 226, "mean"),
