@@ -927,23 +927,37 @@ __global__ void __launch_bounds__(256, 1) block_bwd_kernel(csmpn_block_desc d, c
 }
 
 // ---------------------------------------------------------------------------------------------------
-// final fixed-order reduction of the per-CTA partials into the parameter gradients: one warp per element,
-// lane l sums parts l, l+32, ...; fixed xor tree across lanes.
+// final fixed-order reduction of the per-CTA partials into the parameter gradients: 16 consecutive elements per CTA x
+// 16 partial groups.  Thread (e, pg) sums partials pg, pg+16, ... in order (all loads independent, 64 contiguous bytes
+// per partial row), then the 16 group sums are combined in a fixed order: bit-reproducible run to run.
 struct FinalSeg { const float* in; float* out; int n; int parts; int64_t stride; };
 struct FinalSegs { FinalSeg s[10]; int count; int total; };
 
 __global__ void __launch_bounds__(256) block_bwd_final_kernel(FinalSegs segs) {
-  int q = (int)((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5);
-  const int lane = threadIdx.x & 31;
-  if (q >= segs.total) return;
-  int k = 0;
-  while (k < segs.count - 1 && q >= segs.s[k].n) { q -= segs.s[k].n; ++k; }
-  const FinalSeg& sg = segs.s[k];
+  __shared__ float red[16][17];
+  const int e = threadIdx.x & 15, pg = threadIdx.x >> 4;
+  int q = (int)blockIdx.x * 16 + e;
   float s = 0.f;
-  for (int pidx = lane; pidx < sg.parts; pidx += 32) s += sg.in[(size_t)pidx * sg.stride + q];
+  float* outp = nullptr;
+  if (q < segs.total) {
+    int k = 0;
+    while (k < segs.count - 1 && q >= segs.s[k].n) { q -= segs.s[k].n; ++k; }
+    const FinalSeg& sg = segs.s[k];
+    if (sg.out != nullptr && q < sg.n) {
+      const float* in = sg.in + q;
+#pragma unroll 4
+      for (int pidx = pg; pidx < sg.parts; pidx += 16) s += in[(size_t)pidx * sg.stride];
+      outp = sg.out + q;
+    }
+  }
+  red[pg][e] = s;
+  __syncthreads();
+  if (pg == 0 && outp) {
+    float t = 0.f;
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  if (lane == 0 && sg.out != nullptr && q < sg.n) sg.out[q] = s;
+    for (int i = 0; i < 16; ++i) t += red[i][e];
+    *outp = t;
+  }
 }
 
 template <int DIM>
@@ -1015,8 +1029,7 @@ int launch_block_bwd(const csmpn_block_desc& d, const csmpn_block_grads& g, void
   fs.count = k;
   fs.total = 0;
   for (int i = 0; i < k; ++i) fs.total += fs.s[i].n;
-  const int64_t threads = (int64_t)fs.total * 32;
-  block_bwd_final_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(fs);
+  block_bwd_final_kernel<<<(unsigned)((fs.total + 15) / 16), 256, 0, s>>>(fs);
   CSMPN_LAUNCH_CHECK("block_bwd_final");
   return CSMPN_OK;
 }

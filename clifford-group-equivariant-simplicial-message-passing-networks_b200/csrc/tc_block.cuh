@@ -82,19 +82,23 @@ __device__ __forceinline__ float mv_sumsq(const float* x) {
 //   image (g, hl) = plane with R = rows_p rows;  TRANS == false: row = output channel, column = input channel
 //                                                TRANS == true : row = input channel,  column = output channel
 // hl = 0: TF32-exact high part, hl = 1: remainder.  Rows/columns beyond the real sizes are zero.
+// row0: first plane row of this weight (two weights can share one image set: rows [0, n) and [n, 2n)); zero: clear the
+// image set first (only the first weight staged into a set does).
 template <int DIM, bool TRANS>
 __device__ __forceinline__ void stage_weight_images(uint8_t* img0, uint32_t img_bytes, const float* __restrict__ w, int c_out,
-                                                    int c_in, int rows_p, int cols_p) {
+                                                    int c_in, int rows_p, int cols_p, int row0 = 0, bool zero = true) {
   constexpr int G = Alg<DIM>::G;
-  for (uint32_t i = threadIdx.x; i < G * 2 * (img_bytes >> 4); i += blockDim.x)
-    reinterpret_cast<float4*>(img0)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (zero) {
+    for (uint32_t i = threadIdx.x; i < G * 2 * (img_bytes >> 4); i += blockDim.x)
+      reinterpret_cast<float4*>(img0)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
   __syncthreads();
   const int total = c_out * c_in * G;
   for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
     const int g = idx % G, i = (idx / G) % c_in, o = idx / (G * c_in);
     const float x = w[idx];
     const float hi = tf32_hi(x);
-    const int r = TRANS ? i : o, c = TRANS ? o : i;
+    const int r = row0 + (TRANS ? i : o), c = TRANS ? o : i;
     if (r < rows_p && c < cols_p) {
       const uint32_t off = plane_off(rows_p, r, c);
       *reinterpret_cast<float*>(img0 + (size_t)(g * 2 + 0) * img_bytes + off) = hi;
@@ -145,18 +149,30 @@ __device__ __forceinline__ void issue_chunk_load(const Pipe& p, int q, const flo
     bulk_g2s(p.slot(q) + b * kPS + kh * kKH, bpt + bpt_off(B, cp, tile, b, 2 * kc + kh, 0), 2048u, bar);
   }
 }
-// split pass over the landed chunk q: high parts in place, remainders to `lo`
+// split pass over the landed chunk q: high parts in place, remainders to `lo`.  The remainders wait in registers until
+// the MMAs of chunk q-1 (the previous readers of `lo`) have completed, so reading the chunk, splitting it and storing
+// the high parts overlap those MMAs.
 template <int B>
 __device__ __forceinline__ void split_chunk(const Pipe& p, int q) {
   uint8_t* hi = p.slot(q);
-  for (int it = threadIdx.x; it < B * 2 * kTile; it += kThreads) {
+  constexpr int N = B * 2 * kTile / kThreads;
+  float4 l[N];
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    const int it = threadIdx.x + i * kThreads;
     const int r = it & (kTile - 1), kh = (it >> 7) & 1, b = it >> 8;
     const uint32_t off = b * kPS + kh * kKH + r * 16;
     const float4 x = *reinterpret_cast<const float4*>(hi + off);
-    float4 h, l;
-    split4(x, h, l);
+    float4 h;
+    split4(x, h, l[i]);
     *reinterpret_cast<float4*>(hi + off) = h;
-    *reinterpret_cast<float4*>(p.lo + off) = l;
+  }
+  if (q >= 1) mbar_wait(p.lo_bar, (q - 1) & 1);
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    const int it = threadIdx.x + i * kThreads;
+    const int r = it & (kTile - 1), kh = (it >> 7) & 1, b = it >> 8;
+    *reinterpret_cast<float4*>(p.lo + b * kPS + kh * kKH + r * 16) = l[i];
   }
 }
 // the MMAs of chunk q (called by every lane of one converged warp; an elected lane issues).  Weight set s: images at wimg0 + s*set_bytes, image (g, hi/lo) = 2g / 2g+1, plane

@@ -298,7 +298,6 @@ __global__ void __launch_bounds__(kThreads, 1) tc_bgemm_kernel(GemmArgs a) {
       const uint32_t idesc = idesc_tf32(kTile, Np, false, false);
       for (int kc = 0; kc < nk; ++kc, ++q) {
         mbar_wait(&p.load_bar[q % kRing], (q / kRing) & 1);
-        if (q >= 1) mbar_wait(p.lo_bar, (q - 1) & 1);
         split_chunk<B>(p, q);
         fence_async_smem();
         fence_before_sync();
@@ -521,30 +520,43 @@ struct FinalJob {
 };
 struct FinalJobs { FinalJob j[14]; int count; };
 
-// one warp per output element: lanes stride over the partials, then a fixed xor tree (bit-reproducible)
-__global__ void tc_final_kernel(FinalJobs jobs) {
-  int64_t idx = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
+// 16 consecutive elements per CTA x 16 partial groups: thread (e, pg) sums partials pg, pg+16, ... in order (independent
+// loads, 64 contiguous bytes per partial row), then the 16 group sums are combined in a fixed order (bit-reproducible).
+// Elements are enumerated in SOURCE order (i fastest).
+__global__ void __launch_bounds__(256) tc_final_kernel(FinalJobs jobs) {
+  __shared__ float red[16][17];
+  const int e = threadIdx.x & 15, pg = threadIdx.x >> 4;
+  int64_t idx = (int64_t)blockIdx.x * 16 + e;
+  float s = 0.f;
+  float* outp = nullptr;
   for (int k = 0; k < jobs.count; ++k) {
     const FinalJob& jb = jobs.j[k];
     if (idx < jb.n) {
-      if (!jb.out) return;
-      size_t src, dst;
-      if (jb.kind == 0) {
-        src = dst = (size_t)idx;
-      } else {
-        const int g = (int)(idx % jb.G), i = (int)((idx / jb.G) % jb.ci), o = (int)(idx / ((int64_t)jb.G * jb.ci));
-        src = ((size_t)g * jb.M + jb.m0 + o) * jb.N + i;
-        dst = ((size_t)o * jb.ci_tot + jb.i0 + i) * jb.G + g;
+      if (jb.out) {
+        size_t src, dst;
+        if (jb.kind == 0) {
+          src = dst = (size_t)idx;
+        } else {
+          const int i = (int)(idx % jb.ci), o = (int)((idx / jb.ci) % jb.co), g = (int)(idx / ((int64_t)jb.ci * jb.co));
+          src = ((size_t)g * jb.M + jb.m0 + o) * jb.N + i;
+          dst = ((size_t)o * jb.ci_tot + jb.i0 + i) * jb.G + g;
+        }
+        const float* in = jb.in + src;
+#pragma unroll 4
+        for (int p = pg; p < jb.parts; p += 16) s += in[(size_t)p * jb.stride];
+        outp = jb.out + dst;
       }
-      float s = 0.f;
-      for (int p = lane; p < jb.parts; p += 32) s += jb.in[(size_t)p * jb.stride + src];
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-      if (lane == 0) jb.out[dst] = s;
-      return;
+      break;
     }
     idx -= jb.n;
+  }
+  red[pg][e] = s;
+  __syncthreads();
+  if (pg == 0 && outp) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) t += red[i][e];
+    *outp = t;
   }
 }
 
@@ -633,8 +645,11 @@ int launch_bwd(const csmpn_block_desc& d, const csmpn_block_grads& g, void* work
   e.d = ws + p.o_d; e.dxr = ws + p.o_dxr; e.dy2p = ws + p.o_dy2p; e.dy2 = ws + p.o_dy2; e.dy1 = ws + p.o_dy1;
   e.partial = ws + p.o_p1;
   const int ew_threads = (Cp / 4) * 32;
-  tc_b1_kernel<DIM><<<p.grid_ew, ew_threads, (size_t)(2 * (Cp / 4) * kTile + 2 * kTile) * 4, stream>>>(e);
-  CSMPN_LAUNCH_CHECK("tc_b1_kernel");
+  const int mask = d.stage_mask ? d.stage_mask : ~0;
+  if (mask & 1) {
+    tc_b1_kernel<DIM><<<p.grid_ew, ew_threads, (size_t)(2 * (Cp / 4) * kTile + 2 * kTile) * 4, stream>>>(e);
+    CSMPN_LAUNCH_CHECK("tc_b1_kernel");
+  }
   // ---- dy2 = dy2p + d WL + dxr WR
   const int grid = p.tiles < sm_count_cached() ? p.tiles : sm_count_cached();
   GemmArgs ga;
@@ -646,14 +661,18 @@ int launch_bwd(const csmpn_block_desc& d, const csmpn_block_grads& g, void* work
   ga.addend = ws + p.o_dy2p; ga.out = ws + p.o_dy2; ga.out_bpt = 1;
   size_t sm = gemm_smem<DIM>(2, ga.n16, ga.kmax);
   CSMPN_CUDA_TRY(cudaFuncSetAttribute(tc_bgemm_kernel<DIM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
-  tc_bgemm_kernel<DIM><<<grid, kThreads, sm, stream>>>(ga);
-  CSMPN_LAUNCH_CHECK("tc_bgemm_kernel(dy2)");
+  if (mask & 2) {
+    tc_bgemm_kernel<DIM><<<grid, kThreads, sm, stream>>>(ga);
+    CSMPN_LAUNCH_CHECK("tc_bgemm_kernel(dy2)");
+  }
   // ---- B3
   e.partial = ws + p.o_p3;
-  tc_b3_kernel<DIM><<<p.grid_ew, ew_threads, 0, stream>>>(e);
-  CSMPN_LAUNCH_CHECK("tc_b3_kernel");
+  if (mask & 4) {
+    tc_b3_kernel<DIM><<<p.grid_ew, ew_threads, 0, stream>>>(e);
+    CSMPN_LAUNCH_CHECK("tc_b3_kernel");
+  }
   // ---- grad_x = dy1 W1
-  if (g.grad_x) {
+  if (g.grad_x && (mask & 8)) {
     memset(&ga, 0, sizeof(ga));
     ga.rows = d.rows; ga.tiles = p.tiles;
     ga.src[0] = ws + p.o_dy1; ga.cp[0] = Cp; ga.nk[0] = Cp / 8;
@@ -673,7 +692,8 @@ int launch_bwd(const csmpn_block_desc& d, const csmpn_block_grads& g, void* work
   da.M = p.M1;
   da.partial = ws + p.o_dwa;
   const size_t dwa_part = (size_t)p.grid_dw * G * p.M1 * Cp;
-  if (!p.dw_split) {
+  if (!(mask & 16)) {
+  } else if (!p.dw_split) {
     tc_dw_kernel<DIM><<<p.grid_dw, 256, dw_smem<DIM>(da.M, 2 * Cp / 4, Cp), stream>>>(da);
     CSMPN_LAUNCH_CHECK("tc_dw_kernel(wl,wr)");
   } else {
@@ -685,7 +705,7 @@ int launch_bwd(const csmpn_block_desc& d, const csmpn_block_grads& g, void* work
     tc_dw_kernel<DIM><<<p.grid_dw, 256, dw_smem<DIM>(da.M, Cp / 4, Cp), stream>>>(da);
     CSMPN_LAUNCH_CHECK("tc_dw_kernel(wr)");
   }
-  for (int i0 = 0; i0 < p.n16; i0 += p.nbw) {
+  for (int i0 = 0; i0 < p.n16 && (mask & 32); i0 += p.nbw) {
     const int nb = (p.n16 - i0) < p.nbw ? (p.n16 - i0) : p.nbw;
     da.a0 = ws + p.o_dy1; da.a1 = nullptr; da.cpa = Cp; da.bsrc = x0; da.cpb = nb; da.cpb_total = p.n16; da.b_c4 = i0 / 4;
     da.M = p.M2;
@@ -730,8 +750,10 @@ int launch_bwd(const csmpn_block_desc& d, const csmpn_block_grads& g, void* work
   fj.count = k;
   int64_t total = 0;
   for (int i = 0; i < k; ++i) total += fj.j[i].n;
-  tc_final_kernel<<<(unsigned)((total * 32 + 255) / 256), 256, 0, stream>>>(fj);
-  CSMPN_LAUNCH_CHECK("tc_final_kernel");
+  if (mask & 64) {
+    tc_final_kernel<<<(unsigned)((total + 15) / 16), 256, 0, stream>>>(fj);
+    CSMPN_LAUNCH_CHECK("tc_final_kernel");
+  }
   return CSMPN_OK;
 }
 

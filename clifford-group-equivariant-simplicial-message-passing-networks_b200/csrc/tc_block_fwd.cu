@@ -35,53 +35,81 @@ struct FwdArgs {
 };
 #define TSTAMP(code)                                                                         \
   do {                                                                                       \
-    if (a.dbg && blockIdx.x == 0 && (tid == 0 || tid == 64) && dbg_n < 250) {                \
+    if (TL && a.dbg && blockIdx.x == 0 && (tid == 0 || tid == 64) && dbg_n < 250) {          \
       a.dbg[(tid ? 512 : 0) + 2 * dbg_n] = (code);                                           \
       a.dbg[(tid ? 512 : 0) + 2 * dbg_n + 1] = clock64();                                    \
       ++dbg_n;                                                                               \
     }                                                                                        \
   } while (0)
 
-// ---- producer 2: gather / concatenate API-layout rows, transpose to planes, split (all threads) ------------------
+// ---- producer 2: gather / concatenate API-layout rows (all threads) ------------------------------------------------
+// Item = (row r, channel cl of the chunk, blade quad h): one float4.  gather_chunk_api only LOADS (the values stay in
+// registers, so the loads of chunk q+1 are in flight while chunk q is split, stored and multiplied);
+// store_chunk_api transposes to planes, splits and stores.
 template <int DIM>
-__device__ __forceinline__ void stage_chunk_api(const Pipe& p, int q, const FwdArgs& a, int64_t row0, int kc) {
-  constexpr int B = Alg<DIM>::B, H = B / 4, PPR = 8 * H;
-  uint8_t* hi = p.slot(q);
-  uint8_t* lo = p.lo;
-  for (int it = threadIdx.x; it < kTile * PPR; it += kThreads) {
+struct ApiItems { static constexpr int H = Alg<DIM>::B / 4, PPR = 8 * H, N = kTile * PPR / kThreads; };
+
+template <int DIM>
+__device__ __forceinline__ void gather_chunk_api(const FwdArgs& a, int64_t row0, int kc, float4* v) {
+  constexpr int B = Alg<DIM>::B, H = ApiItems<DIM>::H, PPR = ApiItems<DIM>::PPR, N = ApiItems<DIM>::N;
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    const int it = threadIdx.x + i * kThreads;
     const int r = it / PPR, pc = it - r * PPR;
     const int cl = pc / H, h = pc - cl * H;
     const int c = kc * 8 + cl;
     const int64_t R = row0 + r;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (R < a.rows && c < a.cin) {
       if (a.mode == 1) {
         if (c < a.c0) {
           const int64_t d = a.dst[R], s = a.src[R];
           const float4 x = __ldg(reinterpret_cast<const float4*>(a.p0 + (d * a.c0 + c) * B + 4 * h));
           const float4 z = __ldg(reinterpret_cast<const float4*>(a.p0 + (s * a.c0 + c) * B + 4 * h));
-          v = make_float4(x.x - z.x, x.y - z.y, x.z - z.z, x.w - z.w);
+          v[i] = make_float4(x.x - z.x, x.y - z.y, x.z - z.z, x.w - z.w);
         } else {
           const int64_t e = a.eid[R];
-          v = __ldg(reinterpret_cast<const float4*>(a.p1 + (e * a.c1 + (c - a.c0)) * B + 4 * h));
+          v[i] = __ldg(reinterpret_cast<const float4*>(a.p1 + (e * a.c1 + (c - a.c0)) * B + 4 * h));
         }
       } else {
-        if (c < a.c0) v = __ldg(reinterpret_cast<const float4*>(a.p0 + (R * a.c0 + c) * B + 4 * h));
-        else if (c < a.c0 + a.c1) v = __ldg(reinterpret_cast<const float4*>(a.p1 + (R * a.c1 + (c - a.c0)) * B + 4 * h));
-        else v = __ldg(reinterpret_cast<const float4*>(a.p2 + (R * a.c2 + (c - a.c0 - a.c1)) * B + 4 * h));
+        if (c < a.c0) v[i] = __ldg(reinterpret_cast<const float4*>(a.p0 + (R * a.c0 + c) * B + 4 * h));
+        else if (c < a.c0 + a.c1) v[i] = __ldg(reinterpret_cast<const float4*>(a.p1 + (R * a.c1 + (c - a.c0)) * B + 4 * h));
+        else v[i] = __ldg(reinterpret_cast<const float4*>(a.p2 + (R * a.c2 + (c - a.c0 - a.c1)) * B + 4 * h));
       }
     }
-    float4 hv, lv;
-    split4(v, hv, lv);
+  }
+}
+// high parts first (the raw slot of chunk q is free), then -- once the MMAs of chunk q-1 have released `lo` -- the remainders
+template <int DIM>
+__device__ __forceinline__ void store_chunk_api(const Pipe& p, int q, const float4* v) {
+  constexpr int H = ApiItems<DIM>::H, PPR = ApiItems<DIM>::PPR, N = ApiItems<DIM>::N;
+  uint8_t* hi = p.slot(q);
+  uint8_t* lo = p.lo;
+  float4 lv[N];
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    const int it = threadIdx.x + i * kThreads;
+    const int r = it / PPR, pc = it - r * PPR;
+    const int cl = pc / H, h = pc - cl * H;
+    float4 hv;
+    split4(v[i], hv, lv[i]);
     const uint32_t off = (4 * h) * kPS + (cl >> 2) * kKH + r * 16 + (cl & 3) * 4;
     *reinterpret_cast<float*>(hi + off) = hv.x;
     *reinterpret_cast<float*>(hi + off + kPS) = hv.y;
     *reinterpret_cast<float*>(hi + off + 2 * kPS) = hv.z;
     *reinterpret_cast<float*>(hi + off + 3 * kPS) = hv.w;
-    *reinterpret_cast<float*>(lo + off) = lv.x;
-    *reinterpret_cast<float*>(lo + off + kPS) = lv.y;
-    *reinterpret_cast<float*>(lo + off + 2 * kPS) = lv.z;
-    *reinterpret_cast<float*>(lo + off + 3 * kPS) = lv.w;
+  }
+  if (q >= 1) mbar_wait(p.lo_bar, (q - 1) & 1);
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    const int it = threadIdx.x + i * kThreads;
+    const int r = it / PPR, pc = it - r * PPR;
+    const int cl = pc / H, h = pc - cl * H;
+    const uint32_t off = (4 * h) * kPS + (cl >> 2) * kKH + r * 16 + (cl & 3) * 4;
+    *reinterpret_cast<float*>(lo + off) = lv[i].x;
+    *reinterpret_cast<float*>(lo + off + kPS) = lv[i].y;
+    *reinterpret_cast<float*>(lo + off + 2 * kPS) = lv[i].z;
+    *reinterpret_cast<float*>(lo + off + 3 * kPS) = lv[i].w;
   }
 }
 // copy of the assembled input rows for the weight-gradient GEMM of the backward: chunk buffer -> BPT (coalesced)
@@ -95,6 +123,15 @@ __device__ __forceinline__ void save_chunk_bpt(const Pipe& p, int q, float* dst,
     const float4 h = *reinterpret_cast<const float4*>(hi + off);
     const float4 l = *reinterpret_cast<const float4*>(lo + off);
     *reinterpret_cast<float4*>(dst + bpt_off(B, cp, tile, b, 2 * kc + kh, r)) = make_float4(h.x + l.x, h.y + l.y, h.z + l.z, h.w + l.w);
+  }
+}
+
+// zero the 8 padding channels of chunk kc of a BPT tensor (c_in padded to 16 but staged in chunks of 8)
+template <int B>
+__device__ __forceinline__ void zero_chunk_bpt(float* dst, int cp, int64_t tile, int kc) {
+  for (int it = threadIdx.x; it < B * 2 * kTile; it += kThreads) {
+    const int r = it & (kTile - 1), kh = (it >> 7) & 1, b = it >> 8;
+    *reinterpret_cast<float4*>(dst + bpt_off(B, cp, tile, b, 2 * kc + kh, r)) = make_float4(0.f, 0.f, 0.f, 0.f);
   }
 }
 
@@ -137,6 +174,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_f1_kernel(FwdArgs a) {
 
   int q = 0;       // chunk sequence number of this CTA; chunk q lives in raw slot q % kRing
   int loaded = 0;  // warp 0: chunks whose bulk copies have been issued
+  float4 gv[BPT_IN ? 1 : ApiItems<DIM>::N];  // gathered items of the NEXT chunk to stage (API-layout input)
+  if (!BPT_IN && total_chunks > 0) gather_chunk_api<DIM>(a, tile_of(0) * kTile, 0, gv);
   if (BPT_IN && warp == 0) {
     for (; loaded < kRing - 1 && loaded < total_chunks; ++loaded)
       issue_chunk_load<B>(p, loaded, a.p0, a.in_cp, tile_of(loaded), loaded % nk);
@@ -147,17 +186,19 @@ __global__ void __launch_bounds__(kThreads, 1) tc_f1_kernel(FwdArgs a) {
     for (int kc = 0; kc < nk; ++kc, ++q) {
       if (BPT_IN) {
         mbar_wait(&p.load_bar[q % kRing], (q / kRing) & 1);
-        if (q >= 1) mbar_wait(p.lo_bar, (q - 1) & 1);
         split_chunk<B>(p, q);
       } else {
         if (q >= kRing) mbar_wait(&p.slot_bar[q % kRing], ((q - kRing) / kRing) & 1);  // MMAs of chunk q-kRing released the slot
-        if (q >= 1) mbar_wait(p.lo_bar, (q - 1) & 1);
-        stage_chunk_api<DIM>(p, q, a, row0, kc);
+        store_chunk_api<DIM>(p, q, gv);
+        if (q + 1 < total_chunks) gather_chunk_api<DIM>(a, tile_of(q + 1) * kTile, (q + 1) % nk, gv);
       }
       fence_async_smem();
       fence_before_sync();
       __syncthreads();
-      if (!BPT_IN && a.save_x0) save_chunk_bpt<B>(p, q, a.save_x0, round_up(a.kin8, 16), tile, kc);
+      if (!BPT_IN && a.save_x0) {
+        save_chunk_bpt<B>(p, q, a.save_x0, round_up(a.kin8, 16), tile, kc);
+        if (kc == nk - 1 && (a.kin8 & 8)) zero_chunk_bpt<B>(a.save_x0, round_up(a.kin8, 16), tile, nk);
+      }
       if (warp == 0) {
         fence_after_sync();
         issue_chunk_mma<DIM>(p, q, tbase, Cp, kc > 0, wimg, img, 0, 1, 0, Cp, kc, 0, idesc);
@@ -222,17 +263,21 @@ __global__ void __launch_bounds__(kThreads, 1) tc_f1_kernel(FwdArgs a) {
 
 // =====================================================================================================================
 // F2: linear_right / linear_left + normalisation + weighted geometric product + MVLayerNorm (+ residual)
-template <int DIM>
+// The two linears share ONE MMA per (blade, split term): the weight images hold linear_right in plane rows [0, Cp) and
+// linear_left in rows [Cp, 2Cp), so the instruction shape is 128 x 2Cp x 8 and the A operand (the activations, the
+// expensive shared-memory read) is fetched once for both.  Blade b accumulates into columns [2 b Cp, 2 (b+1) Cp):
+// xr first, xl second.  TL: record the per-phase timeline (csmpn_tc_debug_buffer).
+template <int DIM, bool TL>
 __global__ void __launch_bounds__(kThreads, 1) tc_f2_kernel(FwdArgs a) {
   using A = Alg<DIM>;
   constexpr int B = A::B, G = A::G, P = A::P;
   extern __shared__ __align__(1024) uint8_t smem[];
   const int tid = threadIdx.x, warp = uniform_warp_idx(), lane = tid & 31;
   const int C = a.C, Cp = a.Cp, nk = Cp / 8;
-  const uint32_t img = (uint32_t)Cp * Cp * 4;
+  const uint32_t img = (uint32_t)2 * Cp * Cp * 4;  // one image: [2Cp rows (right | left output channels)] x [Cp]
   const uint32_t set_bytes = G * 2 * img;
-  uint8_t* wimg = smem + (kRing + 1) * B * kPS;  // set 0: linear_right, set 1: linear_left
-  float* sn_s = reinterpret_cast<float*>(wimg + 2 * (size_t)set_bytes);  // sigmoid(normalization.a) [Cp][G]
+  uint8_t* wimg = smem + (kRing + 1) * B * kPS;
+  float* sn_s = reinterpret_cast<float*>(wimg + (size_t)set_bytes);  // sigmoid(normalization.a) [Cp][G]
   float* wv_s = sn_s + Cp * G;                                           // path weights [Cp][P]
   float* bl_s = wv_s + Cp * P;
   float* la_s = bl_s + Cp;
@@ -242,8 +287,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_f2_kernel(FwdArgs a) {
   Pipe p;
   p.init(smem, bars, B * kPS);
 
-  stage_weight_images<DIM, false>(wimg, img, a.wr, C, C, Cp, Cp);
-  stage_weight_images<DIM, false>(wimg + set_bytes, img, a.wl, C, C, Cp, Cp);
+  stage_weight_images<DIM, false>(wimg, img, a.wr, C, C, 2 * Cp, Cp, 0, true);
+  stage_weight_images<DIM, false>(wimg, img, a.wl, C, C, 2 * Cp, Cp, Cp, false);
   for (int i = tid; i < Cp * G; i += kThreads) sn_s[i] = (i < C * G) ? sigmoidf_(a.na[i]) : 0.f;
   for (int i = tid; i < Cp * P; i += kThreads) wv_s[i] = (i < C * P) ? a.wp[i] : 0.f;
   for (int i = tid; i < Cp; i += kThreads) {
@@ -258,11 +303,11 @@ __global__ void __launch_bounds__(kThreads, 1) tc_f2_kernel(FwdArgs a) {
   __syncthreads();
   fence_after_sync();
   const uint32_t tbase = *tmem_slot;
-  const uint32_t idesc = idesc_tf32(kTile, Cp, false, false);
+  const uint32_t idesc = idesc_tf32(kTile, 2 * Cp, false, false);
   const int my_tiles = (a.tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   const int total_chunks = my_tiles * nk;
   auto tile_of = [&](int q) { return (int64_t)blockIdx.x + (int64_t)(q / nk) * gridDim.x; };
-  const uint32_t col_r = 0, col_l = B * Cp;
+  const uint32_t col_r = 0, col_l = Cp, bcols = 2 * Cp;  // column of (blade b, channel c): b * bcols + col_{r,l} + c
   const uint32_t lane_base = (warp & 3) * 32;
 
   int q = 0, loaded = 0, dbg_n = 0;
@@ -277,8 +322,6 @@ __global__ void __launch_bounds__(kThreads, 1) tc_f2_kernel(FwdArgs a) {
       TSTAMP(10);
       mbar_wait(&p.load_bar[q % kRing], (q / kRing) & 1);
       TSTAMP(11);
-      if (q >= 1) mbar_wait(p.lo_bar, (q - 1) & 1);
-      TSTAMP(12);
       split_chunk<B>(p, q);
       fence_async_smem();
       fence_before_sync();
@@ -287,7 +330,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_f2_kernel(FwdArgs a) {
       TSTAMP(14);
       if (warp == 0) {
         fence_after_sync();
-        issue_chunk_mma<DIM>(p, q, tbase, Cp, kc > 0, wimg, img, 0, 2, set_bytes, Cp, kc, 0, idesc);
+        issue_chunk_mma<DIM>(p, q, tbase, bcols, kc > 0, wimg, img, 0, 1, 0, bcols, kc, 0, idesc);
         TSTAMP(15);
         if (loaded == q + kRing - 1 && loaded < total_chunks) {
           if (q >= 1) mbar_wait(&p.slot_bar[(q - 1) % kRing], ((q - 1) / kRing) & 1);
@@ -314,9 +357,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc_f2_kernel(FwdArgs a) {
 #pragma unroll
       for (int b = 0; b < B; ++b) y2v[b] = *reinterpret_cast<const float4*>(a.y2 + bpt_off(B, Cp, tile, b, c4, r));
 #pragma unroll
-      for (int b = 0; b < B; ++b) tmem_ld4(tmem_at(tbase, lane_base, col_r + b * Cp + c4 * 4), xr[b]);
+      for (int b = 0; b < B; ++b) tmem_ld4(tmem_at(tbase, lane_base, b * bcols + col_r + c4 * 4), xr[b]);
 #pragma unroll
-      for (int b = 0; b < B; ++b) tmem_ld4(tmem_at(tbase, lane_base, col_l + b * Cp + c4 * 4), o[b]);
+      for (int b = 0; b < B; ++b) tmem_ld4(tmem_at(tbase, lane_base, b * bcols + col_l + c4 * 4), o[b]);
       tmem_wait_ld();
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -339,7 +382,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_f2_kernel(FwdArgs a) {
         for (int b = 0; b < B; ++b) o[b][j] = oj[b];
       }
 #pragma unroll
-      for (int b = 0; b < B; ++b) tmem_st4(tmem_at(tbase, lane_base, col_l + b * Cp + c4 * 4), o[b]);
+      for (int b = 0; b < B; ++b) tmem_st4(tmem_at(tbase, lane_base, b * bcols + col_l + c4 * 4), o[b]);
     }
     tmem_wait_st();
     TSTAMP(22);
@@ -352,7 +395,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_f2_kernel(FwdArgs a) {
       float o[B][4];
       if (a.save_xr) {
 #pragma unroll
-        for (int b = 0; b < B; ++b) tmem_ld4(tmem_at(tbase, lane_base, col_r + b * Cp + c4 * 4), o[b]);
+        for (int b = 0; b < B; ++b) tmem_ld4(tmem_at(tbase, lane_base, b * bcols + col_r + c4 * 4), o[b]);
         tmem_wait_ld();
 #pragma unroll
         for (int b = 0; b < B; ++b) {
@@ -362,7 +405,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_f2_kernel(FwdArgs a) {
         }
       }
 #pragma unroll
-      for (int b = 0; b < B; ++b) tmem_ld4(tmem_at(tbase, lane_base, col_l + b * Cp + c4 * 4), o[b]);
+      for (int b = 0; b < B; ++b) tmem_ld4(tmem_at(tbase, lane_base, b * bcols + col_l + c4 * 4), o[b]);
       tmem_wait_ld();
       if (a.save_o) {
 #pragma unroll
@@ -459,17 +502,26 @@ int launch_fwd(const csmpn_block_desc& d, cudaStream_t stream) {
   if (a.tiles == 0) return CSMPN_OK;
   const int grid = a.tiles < sm_count_cached() ? a.tiles : sm_count_cached();
   const size_t s1 = f1_smem<DIM>(a.Cp, a.kin8), s2 = f2_smem<DIM>(a.Cp);
-  if (a.in_bpt) {
+  const int mask = d.stage_mask ? d.stage_mask : ~0;
+  if (!(mask & 1)) {
+  } else if (a.in_bpt) {
     CSMPN_CUDA_TRY(cudaFuncSetAttribute(tc_f1_kernel<DIM, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s1));
     tc_f1_kernel<DIM, true><<<grid, kThreads, s1, stream>>>(a);
   } else {
     CSMPN_CUDA_TRY(cudaFuncSetAttribute(tc_f1_kernel<DIM, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s1));
     tc_f1_kernel<DIM, false><<<grid, kThreads, s1, stream>>>(a);
   }
-  CSMPN_LAUNCH_CHECK("tc_f1_kernel");
-  CSMPN_CUDA_TRY(cudaFuncSetAttribute(tc_f2_kernel<DIM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s2));
-  tc_f2_kernel<DIM><<<grid, kThreads, s2, stream>>>(a);
-  CSMPN_LAUNCH_CHECK("tc_f2_kernel");
+  if (mask & 1) CSMPN_LAUNCH_CHECK("tc_f1_kernel");
+  if (mask & 2) {
+    if (a.dbg) {
+      CSMPN_CUDA_TRY(cudaFuncSetAttribute(tc_f2_kernel<DIM, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s2));
+      tc_f2_kernel<DIM, true><<<grid, kThreads, s2, stream>>>(a);
+    } else {
+      CSMPN_CUDA_TRY(cudaFuncSetAttribute(tc_f2_kernel<DIM, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s2));
+      tc_f2_kernel<DIM, false><<<grid, kThreads, s2, stream>>>(a);
+    }
+    CSMPN_LAUNCH_CHECK("tc_f2_kernel");
+  }
   return CSMPN_OK;
 }
 

@@ -1,0 +1,51 @@
+"""CUDA-graph replay of the layer step for a fixed complex structure.
+
+One EGCL layer forward + backward is ~35 kernels of 10-200 us each; launched eagerly through autograd the host side
+(Python autograd nodes, ctypes calls, allocator) leaves gaps between them that add up to 15-20 % of the step.  A batch
+of complexes has a static structure (same CSR, same shapes) for every layer of a model and -- for fixed-topology data
+such as the motion skeleton -- for every step, so the launch sequence is captured once and replayed.
+
+``GraphedEGCL`` wraps ``torch.cuda.make_graphed_callables``: forward and backward are captured as two graphs behind
+one autograd node, parameters stay live (their gradients are produced by the captured backward), inputs are copied
+into the graph's static buffers on every call.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from .models.ops import CSRGraph, get_csr
+
+
+class _BoundLayer(nn.Module):
+    """EGCL with its (non-tensor) CSR structure bound, so that the call takes tensors only."""
+
+    def __init__(self, layer: nn.Module, graph: CSRGraph):
+        super().__init__()
+        self.layer = layer
+        self._graph = graph
+
+    def forward(self, h, edge_attr, node_attr):
+        return self.layer(h, self._graph, edge_attr, node_attr)
+
+
+class GraphedEGCL:
+    """layer(h, graph, edge_attr, node_attr) for a FIXED ``graph`` (CSRGraph or edge_index) and fixed shapes, replayed
+    from CUDA graphs.  ``h`` may require grad; ``edge_attr`` / ``node_attr`` follow the sample tensors' requires_grad."""
+
+    def __init__(self, layer: nn.Module, graph, h: torch.Tensor, edge_attr: torch.Tensor, node_attr: torch.Tensor):
+        if not h.is_cuda:
+            raise ValueError("GraphedEGCL needs CUDA tensors")
+        csr = get_csr(graph, h.shape[0])
+        # build every lazily-created helper structure (sorted views of the CSR) BEFORE capture
+        with torch.no_grad():
+            layer(h, csr, edge_attr, node_attr)
+        torch.cuda.synchronize(h.device)
+        self.bound = _BoundLayer(layer, csr)
+        sample = (h.detach().clone().requires_grad_(True),
+                  edge_attr.detach().clone().requires_grad_(edge_attr.requires_grad),
+                  node_attr.detach().clone().requires_grad_(node_attr.requires_grad))
+        self.fn = torch.cuda.make_graphed_callables(self.bound, sample)
+
+    def __call__(self, h, edge_attr, node_attr):
+        return self.fn(h, edge_attr, node_attr)

@@ -32,7 +32,7 @@ class BlockDesc(ctypes.Structure):
         ("w1", c_void_p), ("b1", c_void_p), ("sa", c_void_p), ("sb", c_void_p), ("wr", c_void_p), ("na", c_void_p),
         ("wl", c_void_p), ("bl", c_void_p), ("wp", c_void_p), ("la", c_void_p),
         ("y", c_void_p), ("res", c_void_p), ("save_y1", c_void_p), ("save_xr", c_void_p), ("save_o", c_void_p),
-        ("engine", c_int32), ("in_bpt", c_int32), ("out_bpt", c_int32), ("reserved_", c_int32),
+        ("engine", c_int32), ("in_bpt", c_int32), ("out_bpt", c_int32), ("stage_mask", c_int32),
         ("save_y2", c_void_p), ("save_x0", c_void_p),
     ]
 
@@ -218,7 +218,7 @@ class FusedBlockFn(torch.autograd.Function):
                                                   ptr(sgraph.rank), ptr(gh), n_nodes, width, 0, stream_ptr(dev)),
                   "scatter_diff_sorted")
             gsrc[0] = gh
-            if srcs[1] is not None:
+            if srcs[1] is not None and ctx.needs_input_grad[2]:
                 ge = torch.empty((rows, chans[1], B), dtype=torch.float32, device=dev)
                 check(lib().csmpn_scatter_rows(ptr(gx), cin * B, chans[0] * B, ptr(csr.perm_dst), ptr(ge), rows, chans[1] * B,
                                                stream_ptr(dev)), "scatter_rows")
@@ -256,7 +256,7 @@ class TcBlockFn(torch.autograd.Function):
         need_grad = cfg["need_grad"]
         y2 = bpt_empty(dim, rows, c, dev)
         saves = tuple(bpt_empty(dim, rows, c, dev) for _ in range(3)) if need_grad else None
-        x0 = bpt_empty(dim, rows, cin, dev, zero=True) if (need_grad and not in_bpt) else None
+        x0 = bpt_empty(dim, rows, cin, dev) if (need_grad and not in_bpt) else None
         resc = None if res is None else f32c(res)
         d = _fill_desc(dim, mode, srcs, chans, rows, c, params, sgraph, y, resc, saves)
         d.engine, d.in_bpt, d.out_bpt = 1, int(in_bpt), int(out_bpt)
@@ -322,7 +322,7 @@ def _tc_block_backward(ctx, gy):
                                               ptr(sgraph.rank), ptr(gh), n_nodes, width, 0, stream_ptr(dev)),
               "scatter_diff_sorted")
         gsrc[0] = gh
-        if srcs[1] is not None:
+        if srcs[1] is not None and ctx.needs_input_grad[2]:
             ge = torch.empty((rows, chans[1], B), dtype=torch.float32, device=dev)
             check(lib().csmpn_scatter_rows(ptr(gx), cin * B, chans[0] * B, ptr(csr.perm_dst), ptr(ge), rows, chans[1] * B,
                                            stream_ptr(dev)), "scatter_rows")
@@ -437,9 +437,26 @@ def egcl_forward(egcl, h, edge_index, edge_attr=None, node_attr=None):
 
 
 # ------------------------------------------------------------------------------------------------- bench helper
+def _time_call(fn, flush, iters, warm=3):
+    ts = []
+    for it in range(iters + warm):
+        flush.fill_(0.0)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        if it >= warm:
+            ts.append(e0.elapsed_time(e1))
+    return sum(ts) / len(ts) * 1e-3
+
+
 def bench_dominant_kernel(layer, d, graph, hbm_peak, peak_src, iters=10):
-    """Time the dominant kernel (backward of the first edge block: gather prologue, 3 transposed GEMMs, 3 weight-gradient
-    GEMMs) alone with CUDA events on the launching stream, L2 flushed between launches."""
+    """Time every kernel of the first edge block (the widest launch of the layer: one row per adjacency pair) ALONE with
+    CUDA events on the launching stream, L2 flushed between launches, and report the one with the largest duration
+    against the HBM roof.  Algorithmic bytes of a kernel = the tensors it must read and write once.
+    On the tensor-core engine a block is several kernels (csmpn_block_desc.stage_mask selects one); on the FP32 SIMT
+    engine it is one forward and one backward kernel."""
     alg = layer.algebra
     B = alg.n_blades
     csr = ops.get_csr(graph, d["h"].shape[0])
@@ -449,52 +466,94 @@ def bench_dominant_kernel(layer, d, graph, hbm_peak, peak_src, iters=10):
     h, ea = f32c(d["h"]), f32c(d["edge_attr"])
     E, C = csr.n_pairs, params[0].shape[0]
     c0, c1 = h.shape[1], ea.shape[1]
+    cin = c0 + c1
     dev = h.device
+    tc = _block_uses_tc(alg, blk, True, E)
+    s = stream_ptr(dev)
+    flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)
+    names = ("g_w1", "g_b1", "g_sa", "g_sb", "g_wr", "g_na", "g_wl", "g_bl", "g_wp", "g_la")
+    pg = [None if t is None else torch.empty_like(t) for t in params]
+    g = BlockGrads()
+    for n, t in zip(names, pg):
+        setattr(g, n, None if t is None else t.data_ptr())
+    fl_lin = 2 * B * C * (cin + 2 * C)
+    if tc:
+        y = bpt_empty(alg.dim, E, C, dev)
+        saves = tuple(bpt_empty(alg.dim, E, C, dev) for _ in range(3))
+        y2 = bpt_empty(alg.dim, E, C, dev)
+        x0 = bpt_empty(alg.dim, E, cin, dev)
+        desc = _fill_desc(alg.dim, 1, [h, ea, None], [c0, c1, 0], E, C, params, sg, y, None, saves)
+        desc.engine, desc.in_bpt, desc.out_bpt = 1, 0, 1
+        desc.save_y2, desc.save_x0 = y2.data_ptr(), x0.data_ptr()
+        check(lib().csmpn_block_fwd(alg.dim, ctypes.byref(desc), s), "block_fwd")
+        gy = torch.randn_like(y)
+        gx = torch.empty((E, cin, B), device=dev)
+        g.grad_y, g.grad_x, g.gy_bpt, g.gx_bpt = gy.data_ptr(), gx.data_ptr(), 1, 0
+        ws = workspace(lib().csmpn_block_bwd_workspace(alg.dim, ctypes.byref(desc)), dev)
+        check(lib().csmpn_block_bwd(alg.dim, ctypes.byref(desc), ctypes.byref(g), ptr(ws), ws.numel(), s), "block_bwd")
+        T = y.numel() * 4          # one BPT [C] tensor
+        Tin = x0.numel() * 4       # one BPT [c_in] tensor
+        Tg = E * (2 * c0 + c1) * B * 4 + 12 * E  # gathered rows + indices
+        Tx = E * cin * B * 4
+        # (name, is_bwd, mask, algorithmic bytes, tensor-pipe FLOPs (3 TF32 MMAs per product))
+        stages = [
+            ("tc_f1_kernel<3,0> (gather + MVLinear W1 + MVSiLU)", 0, 1, Tg + Tin + 2 * T, 3 * E * 2 * B * C * cin),
+            ("tc_f2_kernel (linear_left/right + norm + weighted GP + MVLayerNorm)", 0, 2, 5 * T, 3 * E * 4 * B * C * C),
+            ("tc_b1_kernel (LayerNorm / weighted GP / normalisation adjoints)", 1, 1, 7 * T, 0),
+            ("tc_bgemm_kernel (dy2 = dy2p + d WL + dxr WR)", 1, 2, 4 * T, 3 * E * 4 * B * C * C),
+            ("tc_b3_kernel (MVSiLU adjoint)", 1, 4, 3 * T, 0),
+            ("tc_bgemm_kernel (grad_x = dy1 W1)", 1, 8, T + Tx, 3 * E * 2 * B * C * cin),
+            ("tc_dw_kernel (dWL, dWR = [d|dxr]^T y2)", 1, 16, 3 * T, 3 * E * 4 * B * C * C),
+            ("tc_dw_kernel (dW1 = dy1^T x0)", 1, 32, T + Tin, 3 * E * 2 * B * C * cin),
+            ("tc_final_kernel (fixed-order reduction of per-CTA partials)", 1, 64, 0, 0),
+        ]
+        table = []
+        for name, is_bwd, mask, nbytes, tflops in stages:
+            desc.stage_mask = mask
+            if is_bwd:
+                fn = lambda: check(lib().csmpn_block_bwd(alg.dim, ctypes.byref(desc), ctypes.byref(g), ptr(ws), ws.numel(), s), "bwd")
+            else:
+                fn = lambda: check(lib().csmpn_block_fwd(alg.dim, ctypes.byref(desc), s), "fwd")
+            t = _time_call(fn, flush, iters)
+            table.append({"kernel": name, "launch_ms": t * 1e3, "algorithmic_bytes": nbytes, "hbm_gbs": nbytes / t / 1e9,
+                          "hbm_frac": nbytes / t / 1e9 / hbm_peak, "tensor_tflops_tf32x3": tflops / t / 1e12})
+        desc.stage_mask = 0
+        t_fwd = _time_call(lambda: check(lib().csmpn_block_fwd(alg.dim, ctypes.byref(desc), s), "fwd"), flush, iters)
+        t_bwd = _time_call(lambda: check(lib().csmpn_block_bwd(alg.dim, ctypes.byref(desc), ctypes.byref(g), ptr(ws), ws.numel(), s), "bwd"), flush, iters)
+        dom = max(table, key=lambda r: r["launch_ms"])
+        return {
+            "bound": "hbm", "achieved": dom["hbm_gbs"], "peak": hbm_peak, "unit": "GB/s", "frac": dom["hbm_frac"], "traffic": None,
+            "peak_source": peak_src, "kernel": dom["kernel"], "launch_ms": dom["launch_ms"],
+            "algorithmic_bytes_per_launch": dom["algorithmic_bytes"], "rows_per_launch": E, "engine": "tcgen05 (3xTF32, TMEM accumulators)",
+            "block": {"what": "first edge block (c_in=%d, C=%d, %d pairs), all kernels of the call" % (cin, C, E),
+                      "fwd_ms": t_fwd * 1e3, "bwd_ms": t_bwd * 1e3,
+                      "fused_algorithmic_bytes_fwd_bwd": 4 * B * E * (2 * c0 + c1 + 4 * C) + 4 * B * E * (4 * C + 2 * c0 + c1 + cin) + 24 * E,
+                      "fp32_equiv_tflops_fwd": E * (fl_lin + 3 * B * B * C + 18 * B * C) / t_fwd / 1e12,
+                      "fp32_equiv_tflops_bwd": E * (2 * fl_lin + 6 * B * B * C + 40 * B * C) / t_bwd / 1e12},
+            "kernels": table,
+        }
+    # ---- FP32 SIMT engine
     y = torch.empty((E, C, B), device=dev)
     saves = tuple(torch.empty((E, C, B), device=dev) for _ in range(3))
     desc = _fill_desc(alg.dim, 1, [h, ea, None], [c0, c1, 0], E, C, params, sg, y, None, saves)
-    s = stream_ptr(dev)
     check(lib().csmpn_block_fwd(alg.dim, ctypes.byref(desc), s), "block_fwd")
     gy = torch.randn_like(y)
-    gx = torch.empty((E, c0 + c1, B), device=dev)
-    pg = [None if t is None else torch.empty_like(t) for t in params]
-    g = BlockGrads()
+    gx = torch.empty((E, cin, B), device=dev)
     g.grad_y, g.grad_x = gy.data_ptr(), gx.data_ptr()
-    for n, t in zip(("g_w1", "g_b1", "g_sa", "g_sb", "g_wr", "g_na", "g_wl", "g_bl", "g_wp", "g_la"), pg):
-        setattr(g, n, None if t is None else t.data_ptr())
     ws = workspace(lib().csmpn_block_bwd_workspace(alg.dim, ctypes.byref(desc)), dev)
-    flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)
-    times = {"fwd": [], "bwd": []}
-    for it in range(iters + 3):
-        for which in ("fwd", "bwd"):
-            flush.fill_(0.0)
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            if which == "fwd":
-                check(lib().csmpn_block_fwd(alg.dim, ctypes.byref(desc), s), "block_fwd")
-            else:
-                check(lib().csmpn_block_bwd(alg.dim, ctypes.byref(desc), ctypes.byref(g), ptr(ws), ws.numel(), s), "block_bwd")
-            e1.record()
-            torch.cuda.synchronize()
-            if it >= 3:
-                times[which].append(e0.elapsed_time(e1))
-    t_bwd = sum(times["bwd"]) / len(times["bwd"]) * 1e-3
-    t_fwd = sum(times["fwd"]) / len(times["fwd"]) * 1e-3
-    cin = c0 + c1
-    G = alg.dim + 1
+    t_fwd = _time_call(lambda: check(lib().csmpn_block_fwd(alg.dim, ctypes.byref(desc), s), "fwd"), flush, iters)
+    t_bwd = _time_call(lambda: check(lib().csmpn_block_bwd(alg.dim, ctypes.byref(desc), ctypes.byref(g), ptr(ws), ws.numel(), s), "bwd"), flush, iters)
     # algorithmic bytes of the backward launch: read grad_y, o, y1, xr ([E,C,B] each), gather h twice per pair for the
     # weight gradient (2 x [E,c0,B]) + edge_attr, write grad_x [E,cin,B]; indices 12 B per pair
     bytes_bwd = 4 * B * E * (4 * C + 2 * c0 + c1 + cin) + 12 * E
     bytes_fwd = 4 * B * E * (2 * c0 + c1 + 4 * C) + 12 * E
-    # FLOPs: transposed GEMMs + weight-gradient GEMMs (2 per linear) + products
-    fl_lin = 2 * B * C * (cin + 2 * C)
     flops_bwd = E * (2 * fl_lin + 6 * B * B * C + 40 * B * C)
     flops_fwd = E * (fl_lin + 3 * B * B * C + 18 * B * C)
     return {
         "bound": "hbm", "achieved": bytes_bwd / t_bwd / 1e9, "peak": hbm_peak, "unit": "GB/s",
         "frac": bytes_bwd / t_bwd / 1e9 / hbm_peak, "traffic": None, "peak_source": peak_src,
-        "kernel": "block_bwd_kernel<3> (first edge block: gather prologue + 3 transposed GEMMs + 3 weight-gradient GEMMs)",
-        "launch_ms": t_bwd * 1e3, "algorithmic_bytes_per_launch": bytes_bwd, "rows_per_launch": E,
+        "kernel": "block_bwd_kernel (FP32 SIMT engine, first edge block: gather prologue + 3 transposed GEMMs + 3 weight-gradient GEMMs)",
+        "launch_ms": t_bwd * 1e3, "algorithmic_bytes_per_launch": bytes_bwd, "rows_per_launch": E, "engine": "fp32 simt",
         "fp32": {"achieved_tflops": flops_bwd / t_bwd / 1e12, "peak_tflops": 74.4, "frac": flops_bwd / t_bwd / 1e12 / 74.4,
                  "note": "binding roof: FP32 FMA pipe (148 SM x 128 lanes x 2 x 1.965 GHz); ~110 FLOP/B vs ridge 11"},
         "fwd_kernel": {"launch_ms": t_fwd * 1e3, "hbm_gbs": bytes_fwd / t_fwd / 1e9, "fp32_tflops": flops_fwd / t_fwd / 1e12},

@@ -186,12 +186,14 @@ typedef struct csmpn_block_desc {
    * Intermediates use the blade-plane tile layout "BPT": [ceil(rows/128)][B][cp/4][128][4] fp32 with the channel count
    * padded to cp = a multiple of 16 (csmpn_bpt_floats); padded rows and channels hold zeros.  With engine 1 the three
    * save_* tensors are BPT [c], save_y2 (BPT [c], MVSiLU output) is REQUIRED (it is also the scratch between the two
-   * forward kernels), save_x0 (BPT [c_in], zero-initialised by the caller) keeps the assembled input row of a block
+   * forward kernels), save_x0 (BPT [c_in], fully written by the forward) keeps the assembled input row of a block
    * whose input is not already BPT, for the weight-gradient GEMM of the backward. */
   int32_t engine;                       /* 0 = FP32 SIMT kernels (csrc/block_fused.cu), 1 = tensor-core kernels */
   int32_t in_bpt;                       /* engine 1, mode 0, c1 = c2 = 0: p0 is a BPT [c0] tensor */
   int32_t out_bpt;                      /* engine 1: y is written as a BPT [c] tensor (res must be NULL) */
-  int32_t reserved_;
+  int32_t stage_mask;                   /* engine 1 diagnostics: 0 = every kernel of the call; otherwise bit k selects kernel k
+                                           (fwd: 0 f1, 1 f2; bwd: 0 b1, 1 gemm dy2, 2 b3, 3 gemm grad_x, 4 dW wl/wr, 5 dW w1,
+                                           6 final reduce) -- bench.py times one kernel at a time with it */
   float *save_y2, *save_x0;
 } csmpn_block_desc;
 
