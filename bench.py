@@ -263,14 +263,14 @@ def make_md17_graphs(n_complexes, seed, dev, frames=10, atoms=21):
     return graphs
 
 
-def train_leg(dev, world, rank, steps, warmup, lib):
+def train_leg(dev, world, rank, steps, warmup, lib, graphed=True):
     """train complexes/s: the md17 model (C=32, 5 layers, 10 frames) on 100 complexes per GPU -- GPU lifting once, then
     per step forward + backward + flat-bucket gradient all-reduce + Adam."""
     import torch.distributed as dist
 
     from csmpn_b200.data.modules.simplicial_data import SimplicialTransform
     from csmpn_b200.models.md17_cssmpnn import CliffordSharedSimplicialMPNN_md17
-    from csmpn_b200.train_step import DataParallelStep
+    from csmpn_b200.train_step import DataParallelStep, GraphedDataParallelStep
 
     ncx = 100
     graphs = make_md17_graphs(ncx, 2000 + rank, dev)
@@ -278,8 +278,16 @@ def train_leg(dev, world, rank, steps, warmup, lib):
     torch.manual_seed(0)
     model = CliffordSharedSimplicialMPNN_md17().to(dev)
     opt = torch.optim.Adam(model.parameters(), lr=1e-3, fused=True)
-    step = DataParallelStep(model, opt)
     loc0 = batch.loc.clone()
+    batch.loc = loc0
+    lc0 = lib.csmpn_launch_count()
+    model(batch, 0, "train")[0].backward()  # one eager pass: counts this library's launches per step
+    launches_eager = lib.csmpn_launch_count() - lc0
+    model.zero_grad(set_to_none=True)
+    if graphed:
+        step = GraphedDataParallelStep(model, opt, batch)
+    else:
+        step = DataParallelStep(model, opt)
 
     def one():
         batch.loc = loc0
@@ -307,7 +315,9 @@ def train_leg(dev, world, rank, steps, warmup, lib):
     return {"metric": "train complexes/sec (md17 model: Cl(3,0), C=32, 5 layers, 10 frames, Adam)", "value": ncx * world / (ms * 1e-3),
             "unit": "complexes/s", "ms_per_step": ms, "complexes_per_step_per_gpu": ncx, "simplices_per_gpu": int(batch.x_ind.shape[0]),
             "pairs_per_gpu": int(batch.edge_index.shape[1]), "params": sum(p.numel() for p in model.parameters()),
-            "gpu_launches_per_step": launches / steps, "final_loss": float(loss.detach())}
+            "gpu_launches_per_step": launches_eager, "final_loss": float(loss.detach()),
+            "launch": "forward + backward replayed from one CUDA graph (GraphedDataParallelStep); all-reduce and Adam eager"
+            if graphed else "eager"}
 
 # ----------------------------------------------------------------------------------------------- GPU arm
 def run_ours(args):
@@ -445,7 +455,7 @@ def run_ours(args):
     if rank == 0:
         sampler.start()
     total_ms, launches = timed(step_resident, args.steps, args.warmup)
-    train = None if args.no_train else train_leg(dev, world, rank, max(3, args.steps // 2), 3, lib)
+    train = None if args.no_train else train_leg(dev, world, rank, max(3, args.steps // 2), 3, lib, graphed=not args.no_graph)
     clocks = sampler.stop() if rank == 0 else None  # sampled over the layer-step and train-step timed regions
 
     ms_per_step = total_ms / args.steps

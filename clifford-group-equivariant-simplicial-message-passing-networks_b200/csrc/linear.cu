@@ -235,26 +235,41 @@ __global__ void __launch_bounds__(256) mvlinear_dw_kernel(const float* __restric
   }
 }
 
-// grad_w = sum over splits (fixed order); gw == 1 additionally sums the grades (subspaces=False)
-__global__ void dw_final_kernel(const float* __restrict__ ws_out, const float* __restrict__ ws_bias,
-                                float* __restrict__ grad_w, float* __restrict__ grad_bias, int c_out, int c_in, int G,
-                                int gw, int splits) {
+// grad_w = sum over splits (fixed order); gw == 1 additionally sums the grades (subspaces=False).
+// 16 consecutive outputs per CTA x 16 split groups: thread (e, pg) sums splits pg, pg+16, ... (independent loads), then
+// the 16 group sums are combined in a fixed order.
+__global__ void __launch_bounds__(256) dw_final_kernel(const float* __restrict__ ws_out, const float* __restrict__ ws_bias,
+                                                       float* __restrict__ grad_w, float* __restrict__ grad_bias, int c_out,
+                                                       int c_in, int G, int gw, int splits) {
+  __shared__ float red[16][17];
+  const int e = threadIdx.x & 15, pg = threadIdx.x >> 4;
   const int total_w = c_out * c_in * gw;
-  int q = blockIdx.x * blockDim.x + threadIdx.x;
+  const int q = blockIdx.x * 16 + e;
+  float s = 0.f;
+  float* outp = nullptr;
   if (q < total_w) {
-    float s = 0.f;
     if (gw == 1) {
-      for (int sp = 0; sp < splits; ++sp)
-        for (int g = 0; g < G; ++g) s += ws_out[((size_t)sp * c_out * c_in + q) * G + g];
+      for (int sp = pg; sp < splits; sp += 16) {
+        const float* p = ws_out + ((size_t)sp * c_out * c_in + q) * G;
+        for (int g = 0; g < G; ++g) s += p[g];
+      }
     } else {
-      for (int sp = 0; sp < splits; ++sp) s += ws_out[(size_t)sp * c_out * c_in * G + q];
+#pragma unroll 4
+      for (int sp = pg; sp < splits; sp += 16) s += ws_out[(size_t)sp * c_out * c_in * G + q];
     }
-    grad_w[q] = s;
+    outp = grad_w + q;
   } else if (grad_bias && q < total_w + c_out) {
-    int n = q - total_w;
-    float s = 0.f;
-    for (int sp = 0; sp < splits; ++sp) s += ws_bias[(size_t)sp * c_out + n];
-    grad_bias[n] = s;
+    const int n = q - total_w;
+    for (int sp = pg; sp < splits; sp += 16) s += ws_bias[(size_t)sp * c_out + n];
+    outp = grad_bias + n;
+  }
+  red[pg][e] = s;
+  __syncthreads();
+  if (pg == 0 && outp) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) t += red[i][e];
+    *outp = t;
   }
 }
 
@@ -335,7 +350,7 @@ int csmpn_mvlinear_bwd_weight(int dim, const float* x, const float* grad_y, floa
     mvlinear_dw_kernel<D><<<grid, p.threads, p.smem, s>>>(x, grad_y, ws_out, ws_bias, rows, c_in, c_out, p);
     CSMPN_LAUNCH_CHECK("mvlinear_dw");
     const int total = c_out * c_in * gw + c_out;
-    dw_final_kernel<<<(total + 127) / 128, 128, 0, s>>>(ws_out, ws_bias, grad_w, grad_bias, c_out, c_in, G, gw, p.splits);
+    dw_final_kernel<<<(total + 15) / 16, 256, 0, s>>>(ws_out, ws_bias, grad_w, grad_bias, c_out, c_in, G, gw, p.splits);
     CSMPN_LAUNCH_CHECK("mvlinear_dw_final");
   });
   return CSMPN_OK;

@@ -62,7 +62,8 @@ def global_mean_pool(x, batch, size=None):
     size = int(batch.max()) + 1 if size is None else size
     out = x.new_zeros((size,) + tuple(x.shape[1:]))
     out.index_add_(0, batch, x)
-    cnt = torch.bincount(batch, minlength=size).clamp(min=1).to(x.dtype)
+    # counts by index_add (torch.bincount synchronises with the host, which also forbids CUDA-graph capture)
+    cnt = x.new_zeros(size).index_add_(0, batch, x.new_ones(batch.shape[0])).clamp(min=1)
     return out / cnt.reshape((-1,) + (1,) * (x.dim() - 1))
 
 
@@ -101,7 +102,10 @@ class SharedSimplicialBase(nn.Module):
         else:
             table = torch.eye(self.num_node_type, device=graph.node_types.device)
         node_attr = torch.zeros((graph.node_types.shape[0], table.shape[1], B), device=table.device, dtype=table.dtype)
-        node_attr[..., 0] = table[graph.node_types]
+        # table[node_types] written as a one-hot product: same values, but the gradient of the [T, T] table is a small
+        # matmul instead of an index_put with ~N/T duplicates per row (0.9 ms of serialised atomics per step at N = 8.6 k)
+        onehot = (graph.node_types.unsqueeze(1) == torch.arange(table.shape[0], device=table.device)).to(table.dtype)
+        node_attr[..., 0] = onehot @ table
         ei = graph.edge_index
         edge_attr = torch.cat((node_attr[ei[0]], node_attr[ei[1]]), dim=1)
         return node_attr, edge_attr

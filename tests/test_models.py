@@ -80,3 +80,34 @@ def test_model_on_gpu_lifted_batch_matches_fixture_batch(gold):
     m.load_state_dict(fx["state_dict"], strict=False)
     loss, _ = m(g, 0, "train")
     assert_close(loss, fx["loss"], FWD_TOL, "nba loss on the GPU-lifted batch")
+
+
+@pytest.mark.gpu
+def test_graphed_train_step_equals_eager(gold):
+    """GraphedDataParallelStep (forward + backward replayed from one CUDA graph) follows the eager DataParallelStep:
+    same losses and the same parameters after three Adam steps on the md17 fixture batch."""
+    from csmpn_b200.train_step import DataParallelStep, GraphedDataParallelStep
+
+    dev = torch.device("cuda:0")
+    fx = gold["md17"]
+    results = []
+    for graphed in (False, True):
+        m = model_class("md17")(**fx["kwargs"]).to(dev)
+        m.load_state_dict(fx["state_dict"], strict=False)
+        g = types.SimpleNamespace(**{k: v.clone().to(dev) for k, v in fx["batch"].items()})
+        loc0 = g.loc.clone()
+        opt = torch.optim.Adam(m.parameters(), lr=1e-3)
+        step = GraphedDataParallelStep(m, opt, g) if graphed else DataParallelStep(m, opt)
+        if graphed:  # the capture warm-up ran backward passes but no optimizer step: parameters are still the fixture's
+            assert all(torch.equal(p.detach().cpu(), fx["state_dict"][n]) for n, p in m.named_parameters())
+        losses = []
+        for _ in range(3):
+            g.loc = loc0
+            loss, _ = step(g)
+            losses.append(float(loss))
+        results.append((losses, [p.detach().clone() for p in m.parameters()]))
+    (l0, p0), (l1, p1) = results
+    for a, b in zip(l0, l1):
+        assert abs(a - b) <= 1e-6 * max(1.0, abs(a)), (l0, l1)
+    for a, b in zip(p0, p1):
+        assert_close(b, a, 1e-5, "parameters after 3 steps")
