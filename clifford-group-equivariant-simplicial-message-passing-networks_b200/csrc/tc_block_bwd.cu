@@ -400,12 +400,16 @@ __global__ void __launch_bounds__(256, 1) tc_dw_kernel(DwArgs a) {
   uint8_t* land = ops + 2 * (size_t)op_bytes;       // kDwLand landing slots
   const uint32_t land_bytes = (uint32_t)n4 * kLand;
   uint64_t* bars = reinterpret_cast<uint64_t*>(land + (size_t)kDwLand * land_bytes);
-  uint64_t* load_bar = bars;            // [kDwLand]
-  uint64_t* op_bar = bars + kDwLand;    // [2] the MMAs reading an operand buffer have completed
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kDwLand + 2);
+  uint64_t* load_bar = bars;                 // [kDwLand] the bulk copies of a step have landed
+  uint64_t* op_bar = bars + kDwLand;         // [2] the MMAs reading an operand buffer have completed
+  uint64_t* full_bar = bars + kDwLand + 2;   // [2] every converter warp has written its part of an operand buffer
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kDwLand + 4);
+  constexpr int kConvWarps = 7;              // warps 1..7 convert, warp 0 only issues copies and MMAs
   for (uint32_t i = tid; i < (2 * op_bytes) >> 4; i += 256) reinterpret_cast<float4*>(smem)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   if (tid == 0) {
     for (int i = 0; i < kDwLand + 2; ++i) mbar_init(&bars[i], 1);
+    mbar_init(&full_bar[0], kConvWarps);
+    mbar_init(&full_bar[1], kConvWarps);
     mbar_fence_init();
   }
   const uint32_t need = (uint32_t)G * a.cpb;
@@ -419,68 +423,77 @@ __global__ void __launch_bounds__(256, 1) tc_dw_kernel(DwArgs a) {
   const uint32_t idesc = idesc_tf32(a.M, a.cpb, true, true);
   const int my_tiles = (a.tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   const int steps = my_tiles * B * 2;  // step = (tile, blade, row half)
-  auto issue = [&](int st) {           // all lanes of warp 0
-    const int64_t tile = (int64_t)blockIdx.x + (int64_t)(st / (2 * B)) * gridDim.x;
-    const int b = (st >> 1) % B, rh = st & 1;
-    uint8_t* dst = land + (size_t)(st % kDwLand) * land_bytes;
-    uint64_t* bar = &load_bar[st % kDwLand];
-    if (lane == 0) mbar_arrive_expect_tx(bar, (uint32_t)n4 * (kDwRows * 16u));
-    __syncwarp();
-    for (int u = lane; u < n4; u += 32) {
-      const float* src;
-      if (u < ca4) src = a.a0 + bpt_off(B, a.cpa, tile, b, u, rh * kDwRows);
-      else if (u < na4) src = a.a1 + bpt_off(B, a.cpa, tile, b, u - ca4, rh * kDwRows);
-      else src = a.bsrc + bpt_off(B, a.cpb_total, tile, b, a.b_c4 + (u - na4), rh * kDwRows);
-      bulk_g2s(dst + (size_t)u * kLand, src, kDwRows * 16u, bar);
-    }
-  };
-  int loaded = 0;
-  if (warp == 0) for (; loaded < kDwLand - 1 && loaded < steps; ++loaded) issue(loaded);
-  uint32_t grade_used = 0;
-  for (int st = 0; st < steps; ++st) {
-    const int b = (st >> 1) % B, g = A::grade_of(b);
-    mbar_wait(&load_bar[st % kDwLand], (st / kDwLand) & 1);
-    if (st >= 2) mbar_wait(&op_bar[st & 1], ((st - 2) >> 1) & 1);  // the MMAs of step st-2 released this operand buffer
-    const uint8_t* src = land + (size_t)(st % kDwLand) * land_bytes;
-    uint8_t* op_a = ops + (size_t)(st & 1) * op_bytes;  // A hi groups, A lo groups
-    uint8_t* op_b = op_a + 2 * (size_t)ga * grp;        // B hi groups, B lo groups
-    for (int it = tid; it < kDwRows * n4; it += 256) {
-      const int r = it / n4, u = it - r * n4;
-      const float4 x = *reinterpret_cast<const float4*>(src + (size_t)u * kLand + r * 16);
-      float4 h, l;
-      split4(x, h, l);
-      const bool isb = u >= na4;
-      const int cc = (isb ? u - na4 : u) * 4;  // channel inside its operand
-      uint8_t* base = isb ? op_b : op_a;
-      const int ng = isb ? gb : ga;
-      const uint32_t off = (uint32_t)(cc >> 5) * grp + mn32b_off(r, cc & 31);
-      *reinterpret_cast<float4*>(base + off) = h;
-      *reinterpret_cast<float4*>(base + (size_t)ng * grp + off) = l;
-    }
-    fence_async_smem();
-    fence_before_sync();
-    __syncthreads();
-    if (warp == 0) {
-      {
-        fence_after_sync();
-        const uint64_t a_hi = desc_mn32b(smem_addr(op_a), grp, 0), a_lo = a_hi + ((uint64_t)ga * grp >> 4);
-        const uint64_t b_hi = desc_mn32b(smem_addr(op_b), grp, 0), b_lo = b_hi + ((uint64_t)gb * grp >> 4);
-        const uint32_t d = tbase + (uint32_t)g * a.cpb;
-        const uint32_t acc = (grade_used >> g) & 1;
-#pragma unroll
-        for (int ks = 0; ks < kDwRows / 8; ++ks) {  // one K step = 8 rows = 1024 bytes = 64 descriptor units
-          mma_tf32_w(d, a_hi + ks * 64, b_hi + ks * 64, idesc, ks == 0 ? acc : 1u);
-          mma_tf32_w(d, a_hi + ks * 64, b_lo + ks * 64, idesc, 1);
-          mma_tf32_w(d, a_lo + ks * 64, b_hi + ks * 64, idesc, 1);
-        }
-        mma_commit_w(&op_bar[st & 1]);
-      }
+  // The producer/issuer warp and the converter warps are decoupled by mbarriers (no CTA-wide barrier in the loop): the
+  // conversion of step st+1 runs while warp 0 issues the MMAs of step st and the copies of step st+kDwLand.
+  if (warp == 0) {
+    auto issue = [&](int st) {           // all lanes of warp 0
+      const int64_t tile = (int64_t)blockIdx.x + (int64_t)(st / (2 * B)) * gridDim.x;
+      const int b = (st >> 1) % B, rh = st & 1;
+      uint8_t* dst = land + (size_t)(st % kDwLand) * land_bytes;
+      uint64_t* bar = &load_bar[st % kDwLand];
+      if (lane == 0) mbar_arrive_expect_tx(bar, (uint32_t)n4 * (kDwRows * 16u));
       __syncwarp();
-      // landing slot (st-1) % kDwLand was consumed by the conversion of step st-1 (before the barrier above)
+      for (int u = lane; u < n4; u += 32) {
+        const float* src;
+        if (u < ca4) src = a.a0 + bpt_off(B, a.cpa, tile, b, u, rh * kDwRows);
+        else if (u < na4) src = a.a1 + bpt_off(B, a.cpa, tile, b, u - ca4, rh * kDwRows);
+        else src = a.bsrc + bpt_off(B, a.cpb_total, tile, b, a.b_c4 + (u - na4), rh * kDwRows);
+        bulk_g2s(dst + (size_t)u * kLand, src, kDwRows * 16u, bar);
+      }
+    };
+    int loaded = 0;
+    for (; loaded < kDwLand && loaded < steps; ++loaded) issue(loaded);
+    uint32_t grade_used = 0;
+    for (int st = 0; st < steps; ++st) {
+      const int b = (st >> 1) % B, g = A::grade_of(b);
+      mbar_wait(&full_bar[st & 1], (st >> 1) & 1);
+      fence_after_sync();
+      const uint8_t* op_a = ops + (size_t)(st & 1) * op_bytes;
+      const uint8_t* op_b = op_a + 2 * (size_t)ga * grp;
+      const uint64_t a_hi = desc_mn32b(smem_addr(op_a), grp, 0), a_lo = a_hi + ((uint64_t)ga * grp >> 4);
+      const uint64_t b_hi = desc_mn32b(smem_addr(op_b), grp, 0), b_lo = b_hi + ((uint64_t)gb * grp >> 4);
+      const uint32_t dcol = tbase + (uint32_t)g * a.cpb;
+      const uint32_t acc = (grade_used >> g) & 1;
+#pragma unroll
+      for (int ks = 0; ks < kDwRows / 8; ++ks) {  // one K step = 8 rows = 1024 bytes = 64 descriptor units
+        mma_tf32_w(dcol, a_hi + ks * 64, b_hi + ks * 64, idesc, ks == 0 ? acc : 1u);
+        mma_tf32_w(dcol, a_hi + ks * 64, b_lo + ks * 64, idesc, 1);
+        mma_tf32_w(dcol, a_lo + ks * 64, b_hi + ks * 64, idesc, 1);
+      }
+      mma_commit_w(&op_bar[st & 1]);
+      __syncwarp();
+      // the landing slot of step st was consumed by its conversion (full_bar observed above): refill it
       if (loaded < steps) { issue(loaded); ++loaded; }
+      grade_used |= 1u << g;
     }
-    grade_used |= 1u << g;
+  } else {
+    const int ct = tid - 32, nconv = kConvWarps * 32;
+    for (int st = 0; st < steps; ++st) {
+      mbar_wait(&load_bar[st % kDwLand], (st / kDwLand) & 1);
+      if (st >= 2) mbar_wait(&op_bar[st & 1], ((st - 2) >> 1) & 1);  // the MMAs of step st-2 released this operand buffer
+      const uint8_t* src = land + (size_t)(st % kDwLand) * land_bytes;
+      uint8_t* op_a = ops + (size_t)(st & 1) * op_bytes;  // A hi groups, A lo groups
+      uint8_t* op_b = op_a + 2 * (size_t)ga * grp;        // B hi groups, B lo groups
+      for (int it = ct; it < kDwRows * n4; it += nconv) {
+        const int r = it / n4, u = it - r * n4;
+        const float4 x = *reinterpret_cast<const float4*>(src + (size_t)u * kLand + r * 16);
+        float4 h, l;
+        split4(x, h, l);
+        const bool isb = u >= na4;
+        const int cc = (isb ? u - na4 : u) * 4;  // channel inside its operand
+        uint8_t* base = isb ? op_b : op_a;
+        const int ng = isb ? gb : ga;
+        const uint32_t off = (uint32_t)(cc >> 5) * grp + mn32b_off(r, cc & 31);
+        *reinterpret_cast<float4*>(base + off) = h;
+        *reinterpret_cast<float4*>(base + (size_t)ng * grp + off) = l;
+      }
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full_bar[st & 1]);
+    }
   }
+  uint32_t grade_used = 0;
+  for (int st = 0; st < steps; ++st) grade_used |= 1u << A::grade_of((st >> 1) % B);
   if (steps > 0) mbar_wait(&op_bar[(steps - 1) & 1], ((steps - 1) >> 1) & 1);
   fence_after_sync();
   // ---- epilogue: D_g -> per-CTA partial [G][M][cpb]; grades this CTA never touched are written as zeros
@@ -570,7 +583,7 @@ size_t gemm_smem(int nsets, int n16, int kmax) {
 template <int DIM>
 size_t dw_smem(int M, int na4, int cpb) {
   const int ga = M / 32, gb = (cpb + 31) / 32;
-  return (size_t)2 * 2 * (ga + gb) * kDwRows * 128 + (size_t)kDwLand * (na4 + cpb / 4) * kLand + 96;
+  return (size_t)2 * 2 * (ga + gb) * kDwRows * 128 + (size_t)kDwLand * (na4 + cpb / 4) * kLand + 128;
 }
 constexpr size_t kSmemMax = 227 * 1024;
 

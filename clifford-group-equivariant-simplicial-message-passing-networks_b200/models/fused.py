@@ -507,6 +507,11 @@ def bench_dominant_kernel(layer, d, graph, hbm_peak, peak_src, iters=10):
             ("tc_dw_kernel (dW1 = dy1^T x0)", 1, 32, T + Tin, 3 * E * 2 * B * C * cin),
             ("tc_final_kernel (fixed-order reduction of per-CTA partials)", 1, 64, 0, 0),
         ]
+        # DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) from the committed `ncu --set full` capture of
+        # this workload (profiles/r01_ncu_full_tc_kernels.txt: md17, 53 976 pairs, C = 32); other shapes report null
+        ncu_traffic = {}
+        if (alg.dim, E, C, cin) == (3, 53976, 32, 38):
+            ncu_traffic = {1: 139.0e6, 2: 178.2e6, 101: 403.2e6, 102: 199.0e6, 104: 140.0e6, 108: 69.0e6, 116: 169.9e6, 132: 114.4e6}
         table = []
         for name, is_bwd, mask, nbytes, tflops in stages:
             desc.stage_mask = mask
@@ -516,13 +521,14 @@ def bench_dominant_kernel(layer, d, graph, hbm_peak, peak_src, iters=10):
                 fn = lambda: check(lib().csmpn_block_fwd(alg.dim, ctypes.byref(desc), s), "fwd")
             t = _time_call(fn, flush, iters)
             table.append({"kernel": name, "launch_ms": t * 1e3, "algorithmic_bytes": nbytes, "hbm_gbs": nbytes / t / 1e9,
+                          "traffic": ncu_traffic.get(100 * is_bwd + mask),
                           "hbm_frac": nbytes / t / 1e9 / hbm_peak, "tensor_tflops_tf32x3": tflops / t / 1e12})
         desc.stage_mask = 0
         t_fwd = _time_call(lambda: check(lib().csmpn_block_fwd(alg.dim, ctypes.byref(desc), s), "fwd"), flush, iters)
         t_bwd = _time_call(lambda: check(lib().csmpn_block_bwd(alg.dim, ctypes.byref(desc), ctypes.byref(g), ptr(ws), ws.numel(), s), "bwd"), flush, iters)
         dom = max(table, key=lambda r: r["launch_ms"])
         return {
-            "bound": "hbm", "achieved": dom["hbm_gbs"], "peak": hbm_peak, "unit": "GB/s", "frac": dom["hbm_frac"], "traffic": None,
+            "bound": "hbm", "achieved": dom["hbm_gbs"], "peak": hbm_peak, "unit": "GB/s", "frac": dom["hbm_frac"], "traffic": dom["traffic"],
             "peak_source": peak_src, "kernel": dom["kernel"], "launch_ms": dom["launch_ms"],
             "algorithmic_bytes_per_launch": dom["algorithmic_bytes"], "rows_per_launch": E, "engine": "tcgen05 (3xTF32, TMEM accumulators)",
             "block": {"what": "first edge block (c_in=%d, C=%d, %d pairs), all kernels of the call" % (cin, C, E),
