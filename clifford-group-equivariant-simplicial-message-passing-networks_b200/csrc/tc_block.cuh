@@ -116,23 +116,43 @@ __device__ __forceinline__ uint64_t chunk_desc(uint32_t half_saddr, int b) {
 // A chunk = 8 channels of all blades of a 128-row tile.  Chunk q lands (bulk copies) in raw slot q % kRing; the split
 // pass turns the slot into the TF32-exact high parts in place and writes the remainders to the single `lo` buffer;
 // the MMAs of the chunk read both.  Loads run kRing-1 chunks ahead of the MMAs (two chunks = 64 KB per SM in flight).
+//
+// Roles during the K loop: warp 0 is the ISSUER (bulk copies + MMAs, nothing else); warps 1..15 are CONVERTERS (split
+// pass / gathering producer).  They are decoupled by mbarriers only -- no CTA-wide barrier inside the K loop -- so the
+// conversion of chunk q+1 overlaps the issue and execution of the MMAs of chunk q.  Every warp takes part in the tile
+// epilogue.
 constexpr int kRing = 3;
-constexpr int kPipeBars = 2 * kRing + 1;
+constexpr int kPipeBars = 3 * kRing + 1;
+constexpr int kConvWarps = kThreads / 32 - 1;
+constexpr int kConv = kConvWarps * 32;
 struct Pipe {
   uint8_t* raw;        // kRing slots of `half` bytes
   uint8_t* lo;         // one slot
   uint64_t* load_bar;  // [kRing] the bulk copies of the chunk have landed
   uint64_t* slot_bar;  // [kRing] every MMA reading the slot has completed
+  uint64_t* full_bar;  // [kRing] every converter warp has finished the chunk in this slot (count kConvWarps)
   uint64_t* lo_bar;    // [1]     the MMAs reading `lo` have completed
   uint32_t half;
   __device__ __forceinline__ uint8_t* slot(int q) const { return raw + (size_t)(q % kRing) * half; }
   __device__ __forceinline__ void init(uint8_t* base, uint64_t* bars, uint32_t half_bytes) {
     raw = base; lo = base + (size_t)kRing * half_bytes; half = half_bytes;
-    load_bar = bars; slot_bar = bars + kRing; lo_bar = bars + 2 * kRing;
+    load_bar = bars; slot_bar = bars + kRing; full_bar = bars + 2 * kRing; lo_bar = bars + 3 * kRing;
     if (threadIdx.x == 0) {
-      for (int i = 0; i < kPipeBars; ++i) mbar_init(&bars[i], 1);
+      for (int i = 0; i < kPipeBars; ++i) mbar_init(&bars[i], (i >= 2 * kRing && i < 3 * kRing) ? kConvWarps : 1);
       mbar_fence_init();
     }
+  }
+  // converter warps: this warp's part of chunk q is in shared memory (generic-proxy writes made visible to the MMAs)
+  __device__ __forceinline__ void conv_done(int q) const {
+    fence_async_smem();
+    fence_before_sync();
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) mbar_arrive(&full_bar[q % kRing]);
+  }
+  // issuer warp: wait until chunk q is complete in shared memory
+  __device__ __forceinline__ void wait_full(int q) const {
+    mbar_wait(&full_bar[q % kRing], (q / kRing) & 1);
+    fence_after_sync();
   }
   __device__ __forceinline__ uint32_t bytes() const { return (kRing + 1) * half; }
 };
@@ -149,31 +169,38 @@ __device__ __forceinline__ void issue_chunk_load(const Pipe& p, int q, const flo
     bulk_g2s(p.slot(q) + b * kPS + kh * kKH, bpt + bpt_off(B, cp, tile, b, 2 * kc + kh, 0), 2048u, bar);
   }
 }
-// split pass over the landed chunk q: high parts in place, remainders to `lo`.  The remainders wait in registers until
-// the MMAs of chunk q-1 (the previous readers of `lo`) have completed, so reading the chunk, splitting it and storing
-// the high parts overlap those MMAs.
+// split pass over the landed chunk q (CONVERTER warps only): high parts in place, remainders to `lo`.  The remainders
+// wait in registers until the MMAs of chunk q-1 (the previous readers of `lo`) have completed, so reading the chunk,
+// splitting it and storing the high parts overlap those MMAs.  Ends with conv_done(q).
 template <int B>
 __device__ __forceinline__ void split_chunk(const Pipe& p, int q) {
   uint8_t* hi = p.slot(q);
-  constexpr int N = B * 2 * kTile / kThreads;
+  constexpr int TOT = B * 2 * kTile;
+  constexpr int N = (TOT + kConv - 1) / kConv;
+  const int ct = (int)threadIdx.x - 32;
   float4 l[N];
 #pragma unroll
   for (int i = 0; i < N; ++i) {
-    const int it = threadIdx.x + i * kThreads;
-    const int r = it & (kTile - 1), kh = (it >> 7) & 1, b = it >> 8;
-    const uint32_t off = b * kPS + kh * kKH + r * 16;
-    const float4 x = *reinterpret_cast<const float4*>(hi + off);
-    float4 h;
-    split4(x, h, l[i]);
-    *reinterpret_cast<float4*>(hi + off) = h;
+    const int it = ct + i * kConv;
+    if (it < TOT) {
+      const int r = it & (kTile - 1), kh = (it >> 7) & 1, b = it >> 8;
+      const uint32_t off = b * kPS + kh * kKH + r * 16;
+      const float4 x = *reinterpret_cast<const float4*>(hi + off);
+      float4 h;
+      split4(x, h, l[i]);
+      *reinterpret_cast<float4*>(hi + off) = h;
+    }
   }
   if (q >= 1) mbar_wait(p.lo_bar, (q - 1) & 1);
 #pragma unroll
   for (int i = 0; i < N; ++i) {
-    const int it = threadIdx.x + i * kThreads;
-    const int r = it & (kTile - 1), kh = (it >> 7) & 1, b = it >> 8;
-    *reinterpret_cast<float4*>(p.lo + b * kPS + kh * kKH + r * 16) = l[i];
+    const int it = ct + i * kConv;
+    if (it < TOT) {
+      const int r = it & (kTile - 1), kh = (it >> 7) & 1, b = it >> 8;
+      *reinterpret_cast<float4*>(p.lo + b * kPS + kh * kKH + r * 16) = l[i];
+    }
   }
+  p.conv_done(q);
 }
 // the MMAs of chunk q (called by every lane of one converged warp; an elected lane issues).  Weight set s: images at wimg0 + s*set_bytes, image (g, hi/lo) = 2g / 2g+1, plane
 // rows = w_rows, K step ks, first output row n0; accumulator of (set s, blade b) at column (s*B + b)*ncols.

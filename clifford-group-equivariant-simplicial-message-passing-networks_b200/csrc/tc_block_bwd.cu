@@ -297,13 +297,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_bgemm_kernel(GemmArgs a) {
       const int Np = (a.n16 - n0) < nmax ? (a.n16 - n0) : nmax;
       const uint32_t idesc = idesc_tf32(kTile, Np, false, false);
       for (int kc = 0; kc < nk; ++kc, ++q) {
-        mbar_wait(&p.load_bar[q % kRing], (q / kRing) & 1);
-        split_chunk<B>(p, q);
-        fence_async_smem();
-        fence_before_sync();
-        __syncthreads();
-        if (warp == 0) {
-          fence_after_sync();
+        if (warp == 0) {  // issuer
+          p.wait_full(q);
           {
             const int s = kc < a.nk[0] ? 0 : 1;
             issue_chunk_mma<DIM>(p, q, tbase, Np, kc > 0, wimg, img, s, 1, set_bytes, a.n16, s ? kc - a.nk[0] : kc, n0, idesc);
@@ -313,6 +308,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc_bgemm_kernel(GemmArgs a) {
             issue(loaded);
             ++loaded;
           }
+        } else {          // converters
+          mbar_wait(&p.load_bar[q % kRing], (q / kRing) & 1);
+          split_chunk<B>(p, q);
         }
       }
       mbar_wait(&p.slot_bar[(q - 1) % kRing], ((q - 1) / kRing) & 1);

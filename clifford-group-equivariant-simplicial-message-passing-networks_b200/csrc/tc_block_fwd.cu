@@ -47,20 +47,23 @@ struct FwdArgs {
 // registers, so the loads of chunk q+1 are in flight while chunk q is split, stored and multiplied);
 // store_chunk_api transposes to planes, splits and stores.
 template <int DIM>
-struct ApiItems { static constexpr int H = Alg<DIM>::B / 4, PPR = 8 * H, N = kTile * PPR / kThreads; };
+struct ApiItems {
+  static constexpr int H = Alg<DIM>::B / 4, PPR = 8 * H, TOT = kTile * PPR, N = (TOT + kConv - 1) / kConv;
+};
 
 template <int DIM>
 __device__ __forceinline__ void gather_chunk_api(const FwdArgs& a, int64_t row0, int kc, float4* v) {
-  constexpr int B = Alg<DIM>::B, H = ApiItems<DIM>::H, PPR = ApiItems<DIM>::PPR, N = ApiItems<DIM>::N;
+  constexpr int B = Alg<DIM>::B, H = ApiItems<DIM>::H, PPR = ApiItems<DIM>::PPR, N = ApiItems<DIM>::N, TOT = ApiItems<DIM>::TOT;
+  const int ct = (int)threadIdx.x - 32;
 #pragma unroll
   for (int i = 0; i < N; ++i) {
-    const int it = threadIdx.x + i * kThreads;
+    const int it = ct + i * kConv;
     const int r = it / PPR, pc = it - r * PPR;
     const int cl = pc / H, h = pc - cl * H;
     const int c = kc * 8 + cl;
     const int64_t R = row0 + r;
     v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (R < a.rows && c < a.cin) {
+    if (it < TOT && R < a.rows && c < a.cin) {
       if (a.mode == 1) {
         if (c < a.c0) {
           const int64_t d = a.dst[R], s = a.src[R];
@@ -82,42 +85,49 @@ __device__ __forceinline__ void gather_chunk_api(const FwdArgs& a, int64_t row0,
 // high parts first (the raw slot of chunk q is free), then -- once the MMAs of chunk q-1 have released `lo` -- the remainders
 template <int DIM>
 __device__ __forceinline__ void store_chunk_api(const Pipe& p, int q, const float4* v) {
-  constexpr int H = ApiItems<DIM>::H, PPR = ApiItems<DIM>::PPR, N = ApiItems<DIM>::N;
+  constexpr int H = ApiItems<DIM>::H, PPR = ApiItems<DIM>::PPR, N = ApiItems<DIM>::N, TOT = ApiItems<DIM>::TOT;
+  const int ct = (int)threadIdx.x - 32;
   uint8_t* hi = p.slot(q);
   uint8_t* lo = p.lo;
   float4 lv[N];
 #pragma unroll
   for (int i = 0; i < N; ++i) {
-    const int it = threadIdx.x + i * kThreads;
-    const int r = it / PPR, pc = it - r * PPR;
-    const int cl = pc / H, h = pc - cl * H;
-    float4 hv;
-    split4(v[i], hv, lv[i]);
-    const uint32_t off = (4 * h) * kPS + (cl >> 2) * kKH + r * 16 + (cl & 3) * 4;
-    *reinterpret_cast<float*>(hi + off) = hv.x;
-    *reinterpret_cast<float*>(hi + off + kPS) = hv.y;
-    *reinterpret_cast<float*>(hi + off + 2 * kPS) = hv.z;
-    *reinterpret_cast<float*>(hi + off + 3 * kPS) = hv.w;
+    const int it = ct + i * kConv;
+    if (it < TOT) {
+      const int r = it / PPR, pc = it - r * PPR;
+      const int cl = pc / H, h = pc - cl * H;
+      float4 hv;
+      split4(v[i], hv, lv[i]);
+      const uint32_t off = (4 * h) * kPS + (cl >> 2) * kKH + r * 16 + (cl & 3) * 4;
+      *reinterpret_cast<float*>(hi + off) = hv.x;
+      *reinterpret_cast<float*>(hi + off + kPS) = hv.y;
+      *reinterpret_cast<float*>(hi + off + 2 * kPS) = hv.z;
+      *reinterpret_cast<float*>(hi + off + 3 * kPS) = hv.w;
+    }
   }
   if (q >= 1) mbar_wait(p.lo_bar, (q - 1) & 1);
 #pragma unroll
   for (int i = 0; i < N; ++i) {
-    const int it = threadIdx.x + i * kThreads;
-    const int r = it / PPR, pc = it - r * PPR;
-    const int cl = pc / H, h = pc - cl * H;
-    const uint32_t off = (4 * h) * kPS + (cl >> 2) * kKH + r * 16 + (cl & 3) * 4;
-    *reinterpret_cast<float*>(lo + off) = lv[i].x;
-    *reinterpret_cast<float*>(lo + off + kPS) = lv[i].y;
-    *reinterpret_cast<float*>(lo + off + 2 * kPS) = lv[i].z;
-    *reinterpret_cast<float*>(lo + off + 3 * kPS) = lv[i].w;
+    const int it = ct + i * kConv;
+    if (it < TOT) {
+      const int r = it / PPR, pc = it - r * PPR;
+      const int cl = pc / H, h = pc - cl * H;
+      const uint32_t off = (4 * h) * kPS + (cl >> 2) * kKH + r * 16 + (cl & 3) * 4;
+      *reinterpret_cast<float*>(lo + off) = lv[i].x;
+      *reinterpret_cast<float*>(lo + off + kPS) = lv[i].y;
+      *reinterpret_cast<float*>(lo + off + 2 * kPS) = lv[i].z;
+      *reinterpret_cast<float*>(lo + off + 3 * kPS) = lv[i].w;
+    }
   }
 }
+// barrier among the converter warps only (named barrier 1; warp 0 never joins)
+__device__ __forceinline__ void conv_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(kConv) : "memory"); }
 // copy of the assembled input rows for the weight-gradient GEMM of the backward: chunk buffer -> BPT (coalesced)
 template <int B>
 __device__ __forceinline__ void save_chunk_bpt(const Pipe& p, int q, float* dst, int cp, int64_t tile, int kc) {
   const uint8_t* hi = p.slot(q);
   const uint8_t* lo = p.lo;
-  for (int it = threadIdx.x; it < B * 2 * kTile; it += kThreads) {
+  for (int it = (int)threadIdx.x - 32; it < B * 2 * kTile; it += kConv) {
     const int r = it & (kTile - 1), kh = (it >> 7) & 1, b = it >> 8;
     const uint32_t off = b * kPS + kh * kKH + r * 16;
     const float4 h = *reinterpret_cast<const float4*>(hi + off);
@@ -129,7 +139,7 @@ __device__ __forceinline__ void save_chunk_bpt(const Pipe& p, int q, float* dst,
 // zero the 8 padding channels of chunk kc of a BPT tensor (c_in padded to 16 but staged in chunks of 8)
 template <int B>
 __device__ __forceinline__ void zero_chunk_bpt(float* dst, int cp, int64_t tile, int kc) {
-  for (int it = threadIdx.x; it < B * 2 * kTile; it += kThreads) {
+  for (int it = (int)threadIdx.x - 32; it < B * 2 * kTile; it += kConv) {
     const int r = it & (kTile - 1), kh = (it >> 7) & 1, b = it >> 8;
     *reinterpret_cast<float4*>(dst + bpt_off(B, cp, tile, b, 2 * kc + kh, r)) = make_float4(0.f, 0.f, 0.f, 0.f);
   }
@@ -175,7 +185,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_f1_kernel(FwdArgs a) {
   int q = 0;       // chunk sequence number of this CTA; chunk q lives in raw slot q % kRing
   int loaded = 0;  // warp 0: chunks whose bulk copies have been issued
   float4 gv[BPT_IN ? 1 : ApiItems<DIM>::N];  // gathered items of the NEXT chunk to stage (API-layout input)
-  if (!BPT_IN && total_chunks > 0) gather_chunk_api<DIM>(a, tile_of(0) * kTile, 0, gv);
+  if (!BPT_IN && warp != 0 && total_chunks > 0) gather_chunk_api<DIM>(a, tile_of(0) * kTile, 0, gv);
   if (BPT_IN && warp == 0) {
     for (; loaded < kRing - 1 && loaded < total_chunks; ++loaded)
       issue_chunk_load<B>(p, loaded, a.p0, a.in_cp, tile_of(loaded), loaded % nk);
@@ -184,29 +194,31 @@ __global__ void __launch_bounds__(kThreads, 1) tc_f1_kernel(FwdArgs a) {
     const int64_t tile = (int64_t)blockIdx.x + (int64_t)t * gridDim.x;
     const int64_t row0 = tile * kTile;
     for (int kc = 0; kc < nk; ++kc, ++q) {
-      if (BPT_IN) {
-        mbar_wait(&p.load_bar[q % kRing], (q / kRing) & 1);
-        split_chunk<B>(p, q);
-      } else {
-        if (q >= kRing) mbar_wait(&p.slot_bar[q % kRing], ((q - kRing) / kRing) & 1);  // MMAs of chunk q-kRing released the slot
-        store_chunk_api<DIM>(p, q, gv);
-        if (q + 1 < total_chunks) gather_chunk_api<DIM>(a, tile_of(q + 1) * kTile, (q + 1) % nk, gv);
-      }
-      fence_async_smem();
-      fence_before_sync();
-      __syncthreads();
-      if (!BPT_IN && a.save_x0) {
-        save_chunk_bpt<B>(p, q, a.save_x0, round_up(a.kin8, 16), tile, kc);
-        if (kc == nk - 1 && (a.kin8 & 8)) zero_chunk_bpt<B>(a.save_x0, round_up(a.kin8, 16), tile, nk);
-      }
-      if (warp == 0) {
-        fence_after_sync();
+      if (warp == 0) {  // issuer
+        p.wait_full(q);
         issue_chunk_mma<DIM>(p, q, tbase, Cp, kc > 0, wimg, img, 0, 1, 0, Cp, kc, 0, idesc);
         if (BPT_IN && loaded == q + kRing - 1 && loaded < total_chunks) {
           // slot (q-1) % kRing was read by the MMAs of chunk q-1: reload it as soon as they are done
           if (q >= 1) mbar_wait(&p.slot_bar[(q - 1) % kRing], ((q - 1) / kRing) & 1);
           issue_chunk_load<B>(p, loaded, a.p0, a.in_cp, tile_of(loaded), loaded % nk);
           ++loaded;
+        }
+      } else if (BPT_IN) {  // converters: split the landed chunk
+        mbar_wait(&p.load_bar[q % kRing], (q / kRing) & 1);
+        split_chunk<B>(p, q);
+      } else {              // converters: gathering producer
+        if (q >= kRing) mbar_wait(&p.slot_bar[q % kRing], ((q - kRing) / kRing) & 1);  // MMAs of chunk q-kRing released the slot
+        store_chunk_api<DIM>(p, q, gv);
+        if (q + 1 < total_chunks) gather_chunk_api<DIM>(a, tile_of(q + 1) * kTile, (q + 1) % nk, gv);
+        if (a.save_x0) {
+          fence_async_smem();
+          conv_barrier();  // the whole chunk is in shared memory
+          p.conv_done(q);
+          save_chunk_bpt<B>(p, q, a.save_x0, round_up(a.kin8, 16), tile, kc);
+          if (kc == nk - 1 && (a.kin8 & 8)) zero_chunk_bpt<B>(a.save_x0, round_up(a.kin8, 16), tile, nk);
+          conv_barrier();  // every reader of `lo` is done before the next chunk's remainders are stored
+        } else {
+          p.conv_done(q);
         }
       }
     }
@@ -320,16 +332,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc_f2_kernel(FwdArgs a) {
     const int64_t row0 = tile * kTile;
     for (int kc = 0; kc < nk; ++kc, ++q) {
       TSTAMP(10);
-      mbar_wait(&p.load_bar[q % kRing], (q / kRing) & 1);
-      TSTAMP(11);
-      split_chunk<B>(p, q);
-      fence_async_smem();
-      fence_before_sync();
-      TSTAMP(13);
-      __syncthreads();
-      TSTAMP(14);
-      if (warp == 0) {
-        fence_after_sync();
+      if (warp == 0) {  // issuer
+        p.wait_full(q);
+        TSTAMP(14);
         issue_chunk_mma<DIM>(p, q, tbase, bcols, kc > 0, wimg, img, 0, 1, 0, bcols, kc, 0, idesc);
         TSTAMP(15);
         if (loaded == q + kRing - 1 && loaded < total_chunks) {
@@ -338,6 +343,11 @@ __global__ void __launch_bounds__(kThreads, 1) tc_f2_kernel(FwdArgs a) {
           ++loaded;
         }
         TSTAMP(16);
+      } else {          // converters
+        mbar_wait(&p.load_bar[q % kRing], (q / kRing) & 1);
+        TSTAMP(11);
+        split_chunk<B>(p, q);
+        TSTAMP(13);
       }
     }
     TSTAMP(20);
