@@ -45,16 +45,40 @@ __device__ __forceinline__ void store_mv_bpt(float* t, const float* v, int Cp, i
   for (int b = 0; b < B; ++b) t[bpt_off(B, Cp, tile, b, c4, r) + j] = v[b];
 }
 
+// ---- register-free prefetch: every thread streams ITS OWN elements of the next iteration into a private column of a
+// shared-memory stage with 4-byte cp.async (LDGSTS), two stages deep, and reads them back with LDS.  No cross-thread
+// traffic, so no barrier: cp.async.wait_group orders a thread's own copies.  The loads of iteration i+1 are in flight
+// during the ~900 instructions of iteration i, which the 128-register budget (2 CTAs per SM) cannot do with registers.
+__device__ __forceinline__ void cp_async4(float* dst_smem, const float* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_addr(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int DIM>
+__device__ __forceinline__ void prefetch_mv_bpt(float* st, int nt, const float* t, int Cp, int64_t tile, int c4, int r, int j) {
+  constexpr int B = Alg<DIM>::B;
+#pragma unroll
+  for (int b = 0; b < B; ++b) cp_async4(st + b * nt, t + bpt_off(B, Cp, tile, b, c4, r) + j);
+}
+template <int DIM>
+__device__ __forceinline__ void read_stage(float* v, const float* st, int nt) {
+#pragma unroll
+  for (int b = 0; b < Alg<DIM>::B; ++b) v[b] = st[b * nt];
+}
+
 template <int DIM>
 __global__ void __launch_bounds__(512) tc_b1_kernel(EwArgs a) {
   using A = Alg<DIM>;
   constexpr int B = A::B, G = A::G, P = A::P, NP = P + G + 2;
   extern __shared__ float sm[];
-  const int nw = a.Cp >> 2;
+  const int nw = a.Cp >> 2, nt = blockDim.x;
   float* part1 = sm;                 // [nw][128]
   float* part2 = part1 + nw * kTile; // [nw][128]
   float* inv_mu_s = part2 + nw * kTile;
   float* dmu_s = inv_mu_s + kTile;
+  float* stage = dmu_s + kTile;      // [2 stages][4 tensors][B][nt]
   const int tid = threadIdx.x, c4 = tid >> 5, lane = tid & 31, j = lane & 3, rr = lane >> 2;
   const int ch = c4 * 4 + j, C = a.C, Cp = a.Cp;
   const bool ch_ok = ch < C;
@@ -69,60 +93,85 @@ __global__ void __launch_bounds__(512) tc_b1_kernel(EwArgs a) {
 #pragma unroll
   for (int g = 0; g < G; ++g) g_na[g] = 0.f;
 
-  auto load_gy = [&](float* v, int64_t tile, int r, bool ok) {
+  // iteration it of a unit: it < 8 -> phase 1 (row statistics: o, grad_y), it >= 8 -> phase 2 (adjoints: + y2, xr);
+  // 8 rows of the unit per iteration
+  constexpr int kIt = kTile / 16;
+  auto stage_of = [&](int s, int tensor) { return stage + ((size_t)(s * 4 + tensor) * B) * nt + tid; };
+  auto prefetch = [&](int64_t unit, int it, int s) {
+    const int64_t tile = unit >> 1;
+    const int r = (int)(unit & 1) * (kTile / 2) + (it & (kIt - 1)) * 8 + rr;
+    prefetch_mv_bpt<DIM>(stage_of(s, 0), nt, a.o, Cp, tile, c4, r, j);
     if (a.gy_bpt) {
-      load_mv_bpt<DIM>(v, a.gy, Cp, tile, c4, r, j);
-    } else if (ok) {
-      load_vec<B>(v, a.gy + ((size_t)(tile * kTile + r) * C + ch) * B);
+      prefetch_mv_bpt<DIM>(stage_of(s, 1), nt, a.gy, Cp, tile, c4, r, j);
     } else {
+      float* dst = stage_of(s, 1);
+      if (ch_ok && tile * kTile + r < a.rows) {
+        const float* src = a.gy + ((size_t)(tile * kTile + r) * C + ch) * B;
 #pragma unroll
-      for (int b = 0; b < B; ++b) v[b] = 0.f;
+        for (int b = 0; b < B; ++b) cp_async4(dst + b * nt, src + b);
+      } else {
+#pragma unroll
+        for (int b = 0; b < B; ++b) dst[b * nt] = 0.f;
+      }
     }
+    if (it >= kIt) {
+      prefetch_mv_bpt<DIM>(stage_of(s, 2), nt, a.y2, Cp, tile, c4, r, j);
+      prefetch_mv_bpt<DIM>(stage_of(s, 3), nt, a.xr, Cp, tile, c4, r, j);
+    }
+    cp_async_commit();
   };
 
   // work unit = half a tile (64 rows): finer units balance the persistent CTAs when there are only a few tiles per SM
-  for (int64_t unit = blockIdx.x; unit < 2 * (int64_t)a.tiles; unit += gridDim.x) {
+  const int64_t n_units = 2 * (int64_t)a.tiles;
+  int seq = 0;  // global iteration counter of this thread: stage = seq & 1
+  if ((int64_t)blockIdx.x < n_units) prefetch(blockIdx.x, 0, 0);
+  for (int64_t unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
     const int64_t tile = unit >> 1;
     const int rbase = (int)(unit & 1) * (kTile / 2);
     const int64_t row0 = tile * kTile;
-    // ---- phase 1: row statistics of the layer norm
 #pragma unroll 1
-    for (int s = 0; s < kTile / 16; ++s) {
-      const int r = rbase + s * 8 + rr;
+    for (int it = 0; it < 2 * kIt; ++it, ++seq) {
+      // stream the next iteration (possibly the first one of this CTA's next unit), then wait for the current one
+      if (it + 1 < 2 * kIt) prefetch(unit, it + 1, (seq + 1) & 1);
+      else if (unit + gridDim.x < n_units) prefetch(unit + gridDim.x, 0, (seq + 1) & 1);
+      else cp_async_commit();
+      cp_async_wait<1>();
+      const int s = seq & 1;
+      const int r = rbase + (it & (kIt - 1)) * 8 + rr;
       const bool ok = ch_ok && row0 + r < a.rows;
-      float o[B], dy[B];
-      load_mv_bpt<DIM>(o, a.o, Cp, tile, c4, r, j);
-      load_gy(dy, tile, r, ok);
-      float dot = 0.f;
+      if (it < kIt) {
+        // ---- phase 1: row statistics of the layer norm
+        float o[B], dy[B];
+        read_stage<DIM>(o, stage_of(s, 0), nt);
+        read_stage<DIM>(dy, stage_of(s, 1), nt);
+        float dot = 0.f;
 #pragma unroll
-      for (int b = 0; b < B; ++b) dot = fmaf(dy[b], o[b], dot);
-      float nu = ok ? fast_sas(mv_sumsq<DIM>(o)) : 0.f;
-      float dt = ok ? la * dot : 0.f;
-      nu += __shfl_xor_sync(0xffffffffu, nu, 1); dt += __shfl_xor_sync(0xffffffffu, dt, 1);
-      nu += __shfl_xor_sync(0xffffffffu, nu, 2); dt += __shfl_xor_sync(0xffffffffu, dt, 2);
-      if (j == 0) { part1[c4 * kTile + r] = nu; part2[c4 * kTile + r] = dt; }
-    }
-    __syncthreads();
-    if (tid < kTile / 2) {
-      const int r = rbase + tid;
-      float s1 = 0.f, s2 = 0.f;
-      for (int w = 0; w < nw; ++w) { s1 += part1[w * kTile + r]; s2 += part2[w * kTile + r]; }
-      const float inv_mu = 1.f / (s1 / (float)C + kEps);
-      inv_mu_s[r] = inv_mu;
-      dmu_s[r] = -s2 * inv_mu * inv_mu / (float)C;
-    }
-    __syncthreads();
-    // ---- phase 2: adjoints
-#pragma unroll 1
-    for (int s = 0; s < kTile / 16; ++s) {
-      const int r = rbase + s * 8 + rr;
-      const bool ok = ch_ok && row0 + r < a.rows;
-      float o[B], dd[B], y2[B], xr[B];
-      load_mv_bpt<DIM>(o, a.o, Cp, tile, c4, r, j);
-      load_gy(dd, tile, r, ok);
-      load_mv_bpt<DIM>(y2, a.y2, Cp, tile, c4, r, j);
-      load_mv_bpt<DIM>(xr, a.xr, Cp, tile, c4, r, j);
+        for (int b = 0; b < B; ++b) dot = fmaf(dy[b], o[b], dot);
+        float nu = ok ? fast_sas(mv_sumsq<DIM>(o)) : 0.f;
+        float dt = ok ? la * dot : 0.f;
+        nu += __shfl_xor_sync(0xffffffffu, nu, 1); dt += __shfl_xor_sync(0xffffffffu, dt, 1);
+        nu += __shfl_xor_sync(0xffffffffu, nu, 2); dt += __shfl_xor_sync(0xffffffffu, dt, 2);
+        if (j == 0) { part1[c4 * kTile + r] = nu; part2[c4 * kTile + r] = dt; }
+        if (it == kIt - 1) {
+          __syncthreads();
+          if (tid < kTile / 2) {
+            const int r2 = rbase + tid;
+            float s1 = 0.f, s2 = 0.f;
+            for (int w = 0; w < nw; ++w) { s1 += part1[w * kTile + r2]; s2 += part2[w * kTile + r2]; }
+            const float inv_mu = 1.f / (s1 / (float)C + kEps);
+            inv_mu_s[r2] = inv_mu;
+            dmu_s[r2] = -s2 * inv_mu * inv_mu / (float)C;
+          }
+          __syncthreads();
+        }
+        continue;
+      }
+      // ---- phase 2: adjoints
+      float dd[B];
       {
+        float o[B];
+        read_stage<DIM>(o, stage_of(s, 0), nt);
+        read_stage<DIM>(dd, stage_of(s, 1), nt);
         const float inv_mu = inv_mu_s[r];
         float dot = 0.f;
 #pragma unroll
@@ -137,6 +186,9 @@ __global__ void __launch_bounds__(512) tc_b1_kernel(EwArgs a) {
       }
       store_mv_bpt<DIM>(a.d, dd, Cp, tile, c4, r, j);
       g_bl += dd[0];
+      float y2[B], xr[B];
+      read_stage<DIM>(y2, stage_of(s, 2), nt);
+      read_stage<DIM>(xr, stage_of(s, 3), nt);
       float q[G], nrm[G], rinv[G], xn[B], dxn[B], dy2[B];
       norm_factors<DIM>(xr, sn, q, nrm, rinv);
 #pragma unroll
@@ -159,6 +211,7 @@ __global__ void __launch_bounds__(512) tc_b1_kernel(EwArgs a) {
       store_mv_bpt<DIM>(a.dxr, dxn, Cp, tile, c4, r, j);
     }
   }
+  cp_async_wait<0>();
   // ---- fixed-order reduction over the 8 row lanes of a channel, one partial per CTA
   auto red = [&](float v) {
     v += __shfl_xor_sync(0xffffffffu, v, 4);
@@ -179,6 +232,9 @@ template <int DIM>
 __global__ void __launch_bounds__(512) tc_b3_kernel(EwArgs a) {
   using A = Alg<DIM>;
   constexpr int B = A::B, G = A::G, NP = 2 * G + 1;
+  extern __shared__ float sm[];
+  const int nt = blockDim.x;
+  float* stage = sm;  // [2 stages][2 tensors][B][nt]
   const int tid = threadIdx.x, c4 = tid >> 5, lane = tid & 31, j = lane & 3, rr = lane >> 2;
   const int ch = c4 * 4 + j, C = a.C, Cp = a.Cp;
   const bool ch_ok = ch < C;
@@ -189,17 +245,34 @@ __global__ void __launch_bounds__(512) tc_b3_kernel(EwArgs a) {
     sb[g] = ch_ok ? a.sb[ch * G + g] : 0.f;
     g_sa[g] = 0.f; g_sb[g] = 0.f;
   }
-  for (int64_t unit = blockIdx.x; unit < 2 * (int64_t)a.tiles; unit += gridDim.x) {
+  constexpr int kIt = kTile / 16;
+  auto stage_of = [&](int s, int tensor) { return stage + ((size_t)(s * 2 + tensor) * B) * nt + tid; };
+  auto prefetch = [&](int64_t unit, int it, int s) {
+    const int64_t tile = unit >> 1;
+    const int r = (int)(unit & 1) * (kTile / 2) + it * 8 + rr;
+    prefetch_mv_bpt<DIM>(stage_of(s, 0), nt, a.y1, Cp, tile, c4, r, j);
+    prefetch_mv_bpt<DIM>(stage_of(s, 1), nt, a.dy2, Cp, tile, c4, r, j);
+    cp_async_commit();
+  };
+  const int64_t n_units = 2 * (int64_t)a.tiles;
+  int seq = 0;
+  if ((int64_t)blockIdx.x < n_units) prefetch(blockIdx.x, 0, 0);
+  for (int64_t unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
     const int64_t tile = unit >> 1;
     const int rbase = (int)(unit & 1) * (kTile / 2);
     const int64_t row0 = tile * kTile;
-#pragma unroll 2
-    for (int s = 0; s < kTile / 16; ++s) {
-      const int r = rbase + s * 8 + rr;
+#pragma unroll 1
+    for (int it = 0; it < kIt; ++it, ++seq) {
+      if (it + 1 < kIt) prefetch(unit, it + 1, (seq + 1) & 1);
+      else if (unit + gridDim.x < n_units) prefetch(unit + gridDim.x, 0, (seq + 1) & 1);
+      else cp_async_commit();
+      cp_async_wait<1>();
+      const int s = seq & 1;
+      const int r = rbase + it * 8 + rr;
       const bool ok = ch_ok && row0 + r < a.rows;
       float y1[B], dy[B], sg[G], inv[G], t[G], ds[G];
-      load_mv_bpt<DIM>(y1, a.y1, Cp, tile, c4, r, j);
-      load_mv_bpt<DIM>(dy, a.dy2, Cp, tile, c4, r, j);
+      read_stage<DIM>(y1, stage_of(s, 0), nt);
+      read_stage<DIM>(dy, stage_of(s, 1), nt);
       silu_gates<DIM>(y1, sa, sb, sg, inv);
 #pragma unroll
       for (int g = 0; g < G; ++g) t[g] = 0.f;
@@ -221,6 +294,7 @@ __global__ void __launch_bounds__(512) tc_b3_kernel(EwArgs a) {
       store_mv_bpt<DIM>(a.dy1, dy, Cp, tile, c4, r, j);
     }
   }
+  cp_async_wait<0>();
   auto red = [&](float v) {
     v += __shfl_xor_sync(0xffffffffu, v, 4);
     v += __shfl_xor_sync(0xffffffffu, v, 8);
@@ -658,7 +732,9 @@ int launch_bwd(const csmpn_block_desc& d, const csmpn_block_grads& g, void* work
   const int ew_threads = (Cp / 4) * 32;
   const int mask = d.stage_mask ? d.stage_mask : ~0;
   if (mask & 1) {
-    tc_b1_kernel<DIM><<<p.grid_ew, ew_threads, (size_t)(2 * (Cp / 4) * kTile + 2 * kTile) * 4, stream>>>(e);
+    const size_t sm1 = (size_t)(2 * (Cp / 4) * kTile + 2 * kTile) * 4 + (size_t)2 * 4 * B * ew_threads * 4;
+    CSMPN_CUDA_TRY(cudaFuncSetAttribute(tc_b1_kernel<DIM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1));
+    tc_b1_kernel<DIM><<<p.grid_ew, ew_threads, sm1, stream>>>(e);
     CSMPN_LAUNCH_CHECK("tc_b1_kernel");
   }
   // ---- dy2 = dy2p + d WL + dxr WR
@@ -679,7 +755,9 @@ int launch_bwd(const csmpn_block_desc& d, const csmpn_block_grads& g, void* work
   // ---- B3
   e.partial = ws + p.o_p3;
   if (mask & 4) {
-    tc_b3_kernel<DIM><<<p.grid_ew, ew_threads, 0, stream>>>(e);
+    const size_t sm3 = (size_t)2 * 2 * B * ew_threads * 4;
+    CSMPN_CUDA_TRY(cudaFuncSetAttribute(tc_b3_kernel<DIM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm3));
+    tc_b3_kernel<DIM><<<p.grid_ew, ew_threads, sm3, stream>>>(e);
     CSMPN_LAUNCH_CHECK("tc_b3_kernel");
   }
   // ---- grad_x = dy1 W1
