@@ -85,9 +85,10 @@ def _pairs_from_complex(n, edges, tris, extra_zero_zero):
     return src, dst
 
 
-def make_batch(workload, n_complexes, seed):
+def make_batch(workload, n_complexes, seed, hidden=None):
     """One batch: h [N,C,B], edge_index [2,E] int64, node_attr [N,T,B], edge_attr [E,2T,B], cotangent [N,C,B]."""
     metric, C, aggr, _, _ = WORKLOADS[workload]
+    C = hidden or C
     rng = np.random.default_rng(seed)
     B = 1 << len(metric)
     srcs, dsts, types = [], [], []
@@ -202,11 +203,11 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------------- CPU oracle arm
-def cpu_layer_time(workload, n_complexes, steps, warmup, seed=1000):
+def cpu_layer_time(workload, n_complexes, steps, warmup, seed=1000, hidden=None):
     from oracle import layers_ref as R
 
     torch.set_num_threads(os.cpu_count() or 1)
-    b = make_batch(workload, n_complexes, seed)
+    b = make_batch(workload, n_complexes, seed, hidden=hidden)
     ralg = R.RefAlgebra(b["metric"])
     params = {k: v.requires_grad_() for k, v in R.init_egcl_params(ralg, b["C"], T_TYPES, torch.Generator().manual_seed(0)).items()}
     times = []
@@ -227,7 +228,7 @@ def run_reference(args):
         return
     metric, C, aggr, ncx, desc = WORKLOADS[args.workload]
     sample_cx = 25
-    N, E, times = cpu_layer_time(args.workload, sample_cx, args.steps, args.warmup)
+    N, E, times = cpu_layer_time(args.workload, sample_cx, args.steps, args.warmup, hidden=args.hidden or None)
     ms = 1e3 * sum(times) / len(times)
     value = N / (ms * 1e-3)
     cores = os.cpu_count() or 1
@@ -338,7 +339,12 @@ def run_ours(args):
 
     lib = _lib.lib()
     metric, C, aggr, ncx, desc = WORKLOADS[args.workload]
-    b = make_batch(args.workload, ncx, 1000 + rank)
+    if args.complexes:
+        ncx = args.complexes  # scaling sweep (BASELINE.json configs[4]): same complexes, larger batch
+    if args.hidden:
+        C = args.hidden
+        desc = desc.rsplit("C=", 1)[0] + f"C={C}"
+    b = make_batch(args.workload, ncx, 1000 + rank, hidden=C)
     N, E, B = b["N"], b["E"], b["B"]
     torch.manual_seed(0)
     alg = CliffordAlgebra(metric).to(dev)
@@ -486,7 +492,7 @@ def run_ours(args):
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             sample_cx = 25
-            cN, cE, times = cpu_layer_time(args.workload, sample_cx, 3, 1)
+            cN, cE, times = cpu_layer_time(args.workload, sample_cx, 3, 1, hidden=args.hidden or None)
             cms = statistics.median(times)
             cores = os.cpu_count() or 1
             cpu = {"value": cN / cms, "unit": "simplices/s", "cores": cores, "kind": "port",
@@ -544,6 +550,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="md17", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--complexes", type=int, default=0, help="complexes per GPU per step (default: the workload's batch of 100)")
+    ap.add_argument("--hidden", type=int, default=0, help="hidden width C (default: the workload's)")
     ap.add_argument("--no-train", action="store_true", help="skip the full-model train-step leg")
     ap.add_argument("--no-graph", action="store_true", help="launch the layer step eagerly instead of replaying CUDA graphs")
     args = ap.parse_args()

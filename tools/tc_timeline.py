@@ -13,7 +13,7 @@ os.environ["CSMPN_TC"] = "1"
 os.environ["CSMPN_TC_MIN_ROWS"] = "0"
 import bench  # noqa: E402
 
-NAMES = {1: "start", 10: "chunk top", 11: "load landed", 12: "lo free", 13: "split done", 14: "after barrier", 15: "mma issued",
+NAMES = {1: "start", 10: "chunk top", 11: "load landed", 12: "lo free", 13: "split done", 14: "chunk full", 15: "mma issued",
          16: "load issued", 20: "K loop end", 21: "all MMAs done", 22: "pass1 done", 23: "rowsum barrier", 24: "tile end"}
 
 
@@ -34,7 +34,11 @@ def main():
     from csmpn_b200.models import fused
 
     sg = fused.sorted_graph(graph)
-    with torch.no_grad():
+    import contextlib
+    grad = len(sys.argv) > 1 and sys.argv[1] == "grad"
+    if grad:
+        d["h"].requires_grad_()
+    with (contextlib.nullcontext() if grad else torch.no_grad()):
         for _ in range(2):
             m = fused.block_forward(alg, blk[0], d["h"], d["edge_attr"], mode=1, sgraph=sg, out_bpt=True)
         buf = torch.zeros(1024, dtype=torch.int64, device=dev)
