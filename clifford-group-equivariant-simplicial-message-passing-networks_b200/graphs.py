@@ -37,6 +37,8 @@ class GraphedEGCL:
         if not h.is_cuda:
             raise ValueError("GraphedEGCL needs CUDA tensors")
         csr = get_csr(graph, h.shape[0])
+        if not isinstance(graph, CSRGraph):  # own the structure: set_graph() rewrites it in place
+            csr = CSRGraph(graph.clone(), h.shape[0])
         # build every lazily-created helper structure (sorted views of the CSR) BEFORE capture
         with torch.no_grad():
             layer(h, csr, edge_attr, node_attr)
@@ -46,6 +48,11 @@ class GraphedEGCL:
                   edge_attr.detach().clone().requires_grad_(edge_attr.requires_grad),
                   node_attr.detach().clone().requires_grad_(node_attr.requires_grad))
         self.fn = torch.cuda.make_graphed_callables(self.bound, sample)
+
+    def set_graph(self, edge_index: torch.Tensor):
+        """New complexes with the SAME counts (N simplices, E pairs): the CSR and its sorted views are rebuilt in place
+        (a handful of eager launches), the captured graphs read them at replay."""
+        self.bound._graph.rebuild_(edge_index)
 
     def __call__(self, h, edge_attr, node_attr):
         return self.fn(h, edge_attr, node_attr)

@@ -113,7 +113,13 @@ class SortedGraph:
         self.src_sorted = torch.empty(max(E, 1), dtype=torch.int32, device=dev)
         self.dst_sorted = torch.empty(max(E, 1), dtype=torch.int32, device=dev)
         self.rank = torch.empty(max(E, 1), dtype=torch.int32, device=dev)
-        s = stream_ptr(dev)
+        self.refresh_()
+
+    def refresh_(self):
+        """(re)compute the sorted views in place from the CSR (CSRGraph.rebuild_ calls this)"""
+        g = self.csr
+        E = g.n_pairs
+        s = stream_ptr(g.edge_index.device)
         check(lib().csmpn_csr_sorted_indices(ptr(g.src), ptr(g.dst), ptr(g.perm_dst), ptr(self.src_sorted),
                                              ptr(self.dst_sorted), E, s), "csr_sorted_indices")
         check(lib().csmpn_csr_rank(ptr(g.perm_dst), ptr(self.rank), E, s), "csr_rank")

@@ -210,6 +210,26 @@ class CSRGraph:
               "csr_build(src)")
         self._key = (edge_index.data_ptr(), tuple(edge_index.shape), edge_index._version, N)
 
+    def rebuild_(self, edge_index: torch.Tensor):
+        """Rebuild IN PLACE for a new ``edge_index`` of the same shape: every tensor of this object keeps its address, so
+        CUDA graphs captured on it (csmpn_b200.graphs) stay valid.  Same node count; values are copied."""
+        require_cuda(edge_index, what="CSRGraph.rebuild_")
+        if tuple(edge_index.shape) != tuple(self.edge_index.shape) or edge_index.dtype != torch.int64:
+            raise ValueError("CSRGraph.rebuild_: edge_index must keep its shape [2, E] and dtype int64")
+        self.edge_index.copy_(edge_index)
+        dev = self.edge_index.device
+        E, N = self.n_pairs, self.n_nodes
+        ws = workspace(lib().csmpn_csr_workspace(E, N), dev)
+        s = stream_ptr(dev)
+        check(lib().csmpn_csr_build(ptr(self.dst), E, N, ptr(self.rowptr_dst), ptr(self.perm_dst), ptr(ws), ws.numel(), s),
+              "csr_build(dst)")
+        check(lib().csmpn_csr_build(ptr(self.src), E, N, ptr(self.rowptr_src), ptr(self.perm_src), ptr(ws), ws.numel(), s),
+              "csr_build(src)")
+        sg = getattr(self, "_sorted", None)
+        if sg is not None:
+            sg.refresh_()
+        return self
+
 
 _CSR_CACHE: dict = {}
 

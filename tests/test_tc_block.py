@@ -167,3 +167,33 @@ def test_graphed_layer_matches_eager():
         assert torch.equal(y, yg)
         for a, b in zip(ge, gg):
             assert torch.equal(a, b)
+
+
+def test_graphed_layer_new_structure_same_shape():
+    """GraphedEGCL.set_graph: a different complex structure with the same counts is rebuilt in place (CSR + sorted views)
+    and the replayed graphs follow it."""
+    from csmpn_b200.graphs import GraphedEGCL
+    from csmpn_b200.models.ops import CSRGraph
+
+    case = CASES[0]
+    name, metric, C, T, ncx, n, e, aggr = case
+    CliffordAlgebra, M = _mods()
+    ralg, params, h, ei, ea, na, cot = _inputs(case)
+    alg = CliffordAlgebra(metric).to(DEV)
+    m = M.EGCL(alg, C, C, C, edge_attr_features=2 * T, node_attr_features=T, aggr=aggr).to(DEV)
+    _load(m, params)
+    plist = list(m.parameters())
+    hd, nad, cotd = h.to(DEV), na.to(DEV), cot.to(DEV)
+    g = GraphedEGCL(m, ei.to(DEV), hd, ea.to(DEV), nad)
+    ei2 = _graph(ncx, n, e, torch.Generator().manual_seed(4242))
+    ea2 = torch.cat([na[ei2[0]], na[ei2[1]]], 1).to(DEV)
+    h1 = hd.clone().requires_grad_()
+    y = m(h1, CSRGraph(ei2.to(DEV), h.shape[0]), ea2, nad)
+    ge = torch.autograd.grad(y, [h1] + plist, cotd)
+    g.set_graph(ei2.to(DEV))
+    h2 = hd.clone().requires_grad_()
+    yg = g(h2, ea2, nad)
+    gg = torch.autograd.grad(yg, [h2] + plist, cotd)
+    assert torch.equal(y, yg)
+    for a, b in zip(ge, gg):
+        assert torch.equal(a, b)
