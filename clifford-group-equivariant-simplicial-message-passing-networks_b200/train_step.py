@@ -5,7 +5,8 @@ samples with ``DistributedSampler`` (csmpn/data/md17.py:143-150); the step order
 (engineer/trainer/trainer.py:204-216): forward -> zero_grad -> backward -> optimizer step.  Complexes are independent,
 so the only exchange is ONE gradient all-reduce (mean) per step.  All parameters of these models together are
 0.8-1.5 MB, i.e. a latency-bound collective: the gradients live in ONE flat fp32 bucket (every ``p.grad`` is a view
-into it), the backward kernels accumulate straight into it, and a single NCCL all-reduce over NVLink covers the model.
+into it after one multi-tensor pack), and a single NCCL all-reduce over NVLink covers the model.  On one GPU the optimizer
+reads the gradient tensors of the backward pass directly.
 """
 from __future__ import annotations
 
@@ -43,10 +44,34 @@ class FlatGradBucket:
             raise ValueError("FlatGradBucket needs all parameters on one device with one dtype")
         self.numel = sum(p.numel() for p in self.params)
         self.flat = torch.zeros(self.numel, dtype=dt, device=dev)
+        self.views = []
         off = 0
         for p in self.params:
-            p.grad = self.flat[off: off + p.numel()].view_as(p)
+            self.views.append(self.flat[off: off + p.numel()].view_as(p))
             off += p.numel()
+        self.attach()
+
+    def attach(self):
+        """p.grad = its view into the flat buffer (a backward pass then ACCUMULATES into the bucket)"""
+        for p, v in zip(self.params, self.views):
+            p.grad = v
+
+    def release(self):
+        """p.grad = None: the next backward pass hands its gradient tensors over without the per-parameter
+        `grad += new` kernel (one tiny launch per parameter tensor, ~200 per step for these models)"""
+        for p in self.params:
+            p.grad = None
+
+    def gather(self, grads=None):
+        """pack the gradients produced by a backward pass after release() into the flat buffer (multi-tensor copy),
+        then attach the views; parameters that received no gradient get zeros"""
+        grads = [p.grad for p in self.params] if grads is None else grads
+        have = [(v, g) for v, g in zip(self.views, grads) if g is not None]
+        if len(have) != len(self.views):
+            self.flat.zero_()
+        if have:
+            torch._foreach_copy_([v for v, _ in have], [g for _, g in have])
+        self.attach()
 
     def zero(self):
         self.flat.zero_()
@@ -65,11 +90,16 @@ class DataParallelStep:
         self.model, self.optimizer, self.group = model, optimizer, group
         self.bucket = FlatGradBucket(model.parameters())
 
+    def _distributed(self):
+        return dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1
+
     def __call__(self, batch, step: int = 0):
         loss, out = self.model(batch, step, "train")
-        self.bucket.zero()
+        self.bucket.release()
         loss.backward()
-        self.bucket.all_reduce_mean(self.group)
+        if self._distributed():
+            self.bucket.gather()
+            self.bucket.all_reduce_mean(self.group)
         self.optimizer.step()
         return loss, out
 
@@ -91,16 +121,18 @@ class GraphedDataParallelStep(DataParallelStep):
         with torch.cuda.stream(side):
             for _ in range(warmup):  # builds every per-batch cache (CSR, simplex rows) and the autograd buffers
                 loss, _ = self.model(batch, 0, "train")
-                self.bucket.zero()
+                self.bucket.release()
                 loss.backward()
         cur.wait_stream(side)
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
+        self.bucket.release()
         with torch.cuda.graph(self.graph):
             loss, out = self.model(batch, 0, "train")
-            self.bucket.zero()
             loss.backward()
         self.loss, self.out = loss.detach(), {k: v.detach() for k, v in out.items()}
+        # the gradient tensors the captured backward writes on every replay (static addresses inside the graph's pool)
+        self.static_grads = [p.grad for p in self.bucket.params]
         # the graph holds raw pointers: keep every tensor of the captured batch alive even if the caller rebinds attributes
         self._keepalive = [v for v in vars(batch).values() if torch.is_tensor(v)] if hasattr(batch, "__dict__") else []
 
@@ -112,6 +144,8 @@ class GraphedDataParallelStep(DataParallelStep):
         if batch is not None and batch is not self.batch:
             raise ValueError("GraphedDataParallelStep replays the batch it was captured on; use update() for new values")
         self.graph.replay()
-        self.bucket.all_reduce_mean(self.group)
+        if self._distributed():
+            self.bucket.gather(self.static_grads)
+            self.bucket.all_reduce_mean(self.group)
         self.optimizer.step()
         return self.loss, self.out

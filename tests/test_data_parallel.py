@@ -65,6 +65,7 @@ def _worker(rank, world, port, ret):
         step = DataParallelStep(model, opt)
         before = [p.detach().clone() for p in model.parameters()]
         step({"x": x[ids], "y": y[ids]})
+        assert all(p.grad.data_ptr() >= step.bucket.flat.data_ptr() for p in model.parameters())  # packed + attached
         ret[rank] = dict(grad=step.bucket.flat.clone(), params=[p.detach().clone() for p in model.parameters()], before=before)
     finally:
         dist.destroy_process_group()
@@ -88,3 +89,25 @@ def test_two_rank_step_equals_global_batch_step():
     assert torch.allclose(ret[0]["grad"], ref, rtol=1e-5, atol=1e-7)
     for p, q, b in zip(ret[0]["params"], ret[1]["params"], ret[0]["before"]):
         assert torch.equal(p, q) and not torch.equal(p, b)
+
+
+def test_bucket_release_gather_roundtrip():
+    """release() lets backward hand over its gradient tensors; gather() packs them (zeros for unused parameters)"""
+    from csmpn_b200.train_step import FlatGradBucket
+
+    m = torch.nn.Sequential(torch.nn.Linear(3, 4), torch.nn.Linear(4, 2))
+    unused = torch.nn.Parameter(torch.ones(5))
+    params = list(m.parameters()) + [unused]
+    b = FlatGradBucket(params)
+    b.flat.fill_(7.0)
+    b.release()
+    assert all(p.grad is None for p in params)
+    m(torch.randn(5, 3)).sum().backward()
+    ref = [None if p.grad is None else p.grad.clone() for p in params]
+    b.gather()
+    off = 0
+    for p, r in zip(params, ref):
+        seg = b.flat[off: off + p.numel()].view_as(p)
+        assert torch.equal(seg, torch.zeros_like(p) if r is None else r)
+        assert p.grad.data_ptr() == seg.data_ptr()
+        off += p.numel()
