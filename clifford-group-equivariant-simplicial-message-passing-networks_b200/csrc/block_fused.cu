@@ -1063,6 +1063,25 @@ extern "C" {
 
 int csmpn_block_tc_supported(int dim, int c_in, int c) { return tc_block_supported(dim, c_in, c) ? 1 : 0; }
 
+// > 0 (= rows per shared-memory tile) if the FP32 SIMT engine keeps the three weight matrices of such a block resident in shared memory for both the forward
+// and the backward kernel; 0 if it would fall back to staging them per GEMM (slower than the unit kernels: callers
+// then compose the block from csmpn_mvlinear_* / csmpn_mvsilu_* / ... instead)
+int csmpn_block_simt_resident(int dim, int c_in, int c) {
+  csmpn_block_desc d;
+  memset(&d, 0, sizeof(d));
+  d.c0 = c_in; d.c = c; d.rows = 1;
+  FusedPlan pf, pb;
+  int sf, sb;
+  switch (dim) {
+    case 2: sf = make_fused_plan<2>(d, false, &pf); sb = make_fused_plan<2>(d, true, &pb); break;
+    case 3: sf = make_fused_plan<3>(d, false, &pf); sb = make_fused_plan<3>(d, true, &pb); break;
+    case 5: sf = make_fused_plan<5>(d, false, &pf); sb = make_fused_plan<5>(d, true, &pb); break;
+    default: return 0;
+  }
+  if (!(sf == CSMPN_OK && sb == CSMPN_OK && pf.resident && pb.resident)) return 0;
+  return pf.tr < pb.tr ? pf.tr : pb.tr;  // rows per tile that still fit next to the resident weights
+}
+
 int csmpn_tc_debug_buffer(int64_t* device_buffer_1024) {
   tc_set_debug_buffer((long long*)device_buffer_1024);
   return CSMPN_OK;

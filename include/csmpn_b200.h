@@ -210,6 +210,10 @@ typedef struct csmpn_block_grads {
 int csmpn_block_fwd(int dim, const csmpn_block_desc* desc, csmpn_stream_t stream);
 /* 1 if the tensor-core engine handles a block of this shape (c_in input channels, width c) in algebra dimension dim */
 int csmpn_block_tc_supported(int dim, int c_in, int c);
+/* > 0 (the rows per shared-memory tile) if engine 0 keeps the block's weights resident in shared memory (forward and
+ * backward), 0 if it would stage them per GEMM; with fewer than 8 rows per tile or staged weights the unit kernels
+ * (csmpn_mvlinear_*, csmpn_mvsilu_*, csmpn_wgp_*, ...) composed by the host are the faster path for that shape */
+int csmpn_block_simt_resident(int dim, int c_in, int c);
 /* Diagnostics: when set to a device buffer of 1024 int64 (NULL to disable), the second forward kernel of engine 1 records
  * (phase code, clock64) pairs of two threads of CTA 0: the per-tile timeline used to tune the pipeline (tools/tc_timeline.py). */
 int csmpn_tc_debug_buffer(int64_t* device_buffer_1024);
