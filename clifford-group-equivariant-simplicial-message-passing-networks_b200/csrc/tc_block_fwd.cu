@@ -83,8 +83,12 @@ __device__ __forceinline__ void gather_chunk_api(const FwdArgs& a, int64_t row0,
   }
 }
 // high parts first (the raw slot of chunk q is free), then -- once the MMAs of chunk q-1 have released `lo` -- the remainders
+// x0 != nullptr: the assembled input rows are also written to the BPT tensor x0 (kept for the weight-gradient GEMM of
+// the backward) straight from the registers, between the two shared-memory phases: a warp covers two rows x 8 channels
+// x all blades, i.e. full 32-byte sectors of every blade plane.
 template <int DIM>
-__device__ __forceinline__ void store_chunk_api(const Pipe& p, int q, const float4* v) {
+__device__ __forceinline__ void store_chunk_api(const Pipe& p, int q, const float4* v, float* x0, int x0_cp, int64_t tile, int kc) {
+  constexpr int B = Alg<DIM>::B;
   constexpr int H = ApiItems<DIM>::H, PPR = ApiItems<DIM>::PPR, N = ApiItems<DIM>::N, TOT = ApiItems<DIM>::TOT;
   const int ct = (int)threadIdx.x - 32;
   uint8_t* hi = p.slot(q);
@@ -103,6 +107,22 @@ __device__ __forceinline__ void store_chunk_api(const Pipe& p, int q, const floa
       *reinterpret_cast<float*>(hi + off + kPS) = hv.y;
       *reinterpret_cast<float*>(hi + off + 2 * kPS) = hv.z;
       *reinterpret_cast<float*>(hi + off + 3 * kPS) = hv.w;
+    }
+  }
+  if (x0) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      const int it = ct + i * kConv;
+      if (it < TOT) {
+        const int r = it / PPR, pc = it - r * PPR;
+        const int cl = pc / H, h = pc - cl * H;
+        float* dst = x0 + bpt_off(B, x0_cp, tile, 4 * h, 2 * kc + (cl >> 2), r) + (cl & 3);
+        const size_t bs = (size_t)(x0_cp >> 2) * kTile * 4;  // floats between blade planes
+        dst[0] = v[i].x;
+        dst[bs] = v[i].y;
+        dst[2 * bs] = v[i].z;
+        dst[3 * bs] = v[i].w;
+      }
     }
   }
   if (q >= 1) mbar_wait(p.lo_bar, (q - 1) & 1);
@@ -208,18 +228,10 @@ __global__ void __launch_bounds__(kThreads, 1) tc_f1_kernel(FwdArgs a) {
         split_chunk<B>(p, q);
       } else {              // converters: gathering producer
         if (q >= kRing) mbar_wait(&p.slot_bar[q % kRing], ((q - kRing) / kRing) & 1);  // MMAs of chunk q-kRing released the slot
-        store_chunk_api<DIM>(p, q, gv);
+        store_chunk_api<DIM>(p, q, gv, a.save_x0, round_up(a.kin8, 16), tile, kc);
+        p.conv_done(q);
         if (q + 1 < total_chunks) gather_chunk_api<DIM>(a, tile_of(q + 1) * kTile, (q + 1) % nk, gv);
-        if (a.save_x0) {
-          fence_async_smem();
-          conv_barrier();  // the whole chunk is in shared memory
-          p.conv_done(q);
-          save_chunk_bpt<B>(p, q, a.save_x0, round_up(a.kin8, 16), tile, kc);
-          if (kc == nk - 1 && (a.kin8 & 8)) zero_chunk_bpt<B>(a.save_x0, round_up(a.kin8, 16), tile, nk);
-          conv_barrier();  // every reader of `lo` is done before the next chunk's remainders are stored
-        } else {
-          p.conv_done(q);
-        }
+        if (a.save_x0 && kc == nk - 1 && (a.kin8 & 8)) zero_chunk_bpt<B>(a.save_x0, round_up(a.kin8, 16), tile, nk);
       }
     }
     // ---- epilogue: all MMAs of this tile have completed
