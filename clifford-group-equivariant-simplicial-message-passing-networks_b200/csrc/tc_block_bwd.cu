@@ -391,12 +391,18 @@ __global__ void __launch_bounds__(kThreads, 1) tc_bgemm_kernel(GemmArgs a) {
           split_chunk<B>(p, q);
         }
       }
+      // ---- epilogue of this pass: output channels [n0, n0 + Np).  The addend rows of the first channel group are
+      // requested before waiting for the MMAs, those of the next group while the current one is processed.
+      const int r = lane_base + lane;
+      const bool row_ok = row0 + r < a.rows;
+      float4 ad[B];
+      if (a.addend && (warp >> 2) < (Np >> 2)) {
+#pragma unroll
+        for (int b = 0; b < B; ++b) ad[b] = *reinterpret_cast<const float4*>(a.addend + bpt_off(B, a.n16, tile, b, (n0 >> 2) + (warp >> 2), r));
+      }
       mbar_wait(&p.slot_bar[(q - 1) % kRing], ((q - 1) / kRing) & 1);
       fence_after_sync();
       if (warp == 0) for (; loaded < q + kRing && loaded < total_chunks; ++loaded) issue(loaded);
-      // ---- epilogue of this pass: output channels [n0, n0 + Np)
-      const int r = lane_base + lane;
-      const bool row_ok = row0 + r < a.rows;
       for (int c4 = warp >> 2; c4 < (Np >> 2); c4 += 4) {
         float v[B][4];
 #pragma unroll
@@ -406,8 +412,11 @@ __global__ void __launch_bounds__(kThreads, 1) tc_bgemm_kernel(GemmArgs a) {
         if (a.addend) {
 #pragma unroll
           for (int b = 0; b < B; ++b) {
-            const float4 x = *reinterpret_cast<const float4*>(a.addend + bpt_off(B, a.n16, tile, b, gc4, r));
-            v[b][0] += x.x; v[b][1] += x.y; v[b][2] += x.z; v[b][3] += x.w;
+            v[b][0] += ad[b].x; v[b][1] += ad[b].y; v[b][2] += ad[b].z; v[b][3] += ad[b].w;
+          }
+          if (c4 + 4 < (Np >> 2)) {
+#pragma unroll
+            for (int b = 0; b < B; ++b) ad[b] = *reinterpret_cast<const float4*>(a.addend + bpt_off(B, a.n16, tile, b, gc4 + 4, r));
           }
         }
         if (a.out_bpt) {

@@ -363,21 +363,28 @@ __global__ void __launch_bounds__(kThreads, 1) tc_f2_kernel(FwdArgs a) {
       }
     }
     TSTAMP(20);
+    const int r = lane_base + lane;
+    const bool row_ok = row0 + r < a.rows;
+    // y2 of this thread's first channel group is requested before waiting for the MMAs (left operand of the product)
+    float4 y2v[B];
+    if ((warp >> 2) < (Cp >> 2)) {
+#pragma unroll
+      for (int b = 0; b < B; ++b) y2v[b] = *reinterpret_cast<const float4*>(a.y2 + bpt_off(B, Cp, tile, b, warp >> 2, r));
+    }
     mbar_wait(&p.slot_bar[(q - 1) % kRing], ((q - 1) / kRing) & 1);
     fence_after_sync();
     TSTAMP(21);
     if (warp == 0) {
       for (; loaded < q + kRing && loaded < total_chunks; ++loaded) issue_chunk_load<B>(p, loaded, a.y2, Cp, tile_of(loaded), loaded % nk);
     }
-    const int r = lane_base + lane;
-    const bool row_ok = row0 + r < a.rows;
     // ---- pass 1: per channel normalisation + weighted geometric product; o -> TMEM (over xl); row sum of norms
     float rs = 0.f;
     for (int c4 = warp >> 2; c4 < (Cp >> 2); c4 += 4) {
-      float4 y2v[B];
       float xr[B][4], o[B][4];
+      if (c4 != (warp >> 2)) {
 #pragma unroll
-      for (int b = 0; b < B; ++b) y2v[b] = *reinterpret_cast<const float4*>(a.y2 + bpt_off(B, Cp, tile, b, c4, r));
+        for (int b = 0; b < B; ++b) y2v[b] = *reinterpret_cast<const float4*>(a.y2 + bpt_off(B, Cp, tile, b, c4, r));
+      }
 #pragma unroll
       for (int b = 0; b < B; ++b) tmem_ld4(tmem_at(tbase, lane_base, b * bcols + col_r + c4 * 4), xr[b]);
 #pragma unroll
