@@ -323,8 +323,11 @@ def _tc_block_backward(ctx, gy):
     if nbytes < 0:
         raise _lib.CsmpnError("tensor-core block backward: unsupported configuration")
     ws = workspace(nbytes, dev)
-    check(lib().csmpn_block_bwd(dim, ctypes.byref(d), ctypes.byref(g), ptr(ws), ws.numel(), stream_ptr(dev)),
-          "block_bwd (tensor-core)")
+    if _fork_enabled() and rows <= fork_max_rows():
+        _tc_backward_forked(dim, d, g, ws, dev)
+    else:
+        check(lib().csmpn_block_bwd(dim, ctypes.byref(d), ctypes.byref(g), ptr(ws), ws.numel(), stream_ptr(dev)),
+              "block_bwd (tensor-core)")
     gsrc = [None, None, None]
     if in_bpt:
         gsrc[0] = gx
@@ -352,6 +355,51 @@ def _tc_block_backward(ctx, gy):
     gres = gy if has_res else None
     pgr = [None if t is None else t.reshape(s) for t, s in zip(pg, pshapes)]
     return (None, gsrc[0], gsrc[1], gsrc[2], gres, *pgr)
+
+
+_SIDE_STREAMS: dict = {}
+
+
+def _fork_enabled() -> bool:
+    return os.environ.get("CSMPN_TC_FORK", "1") != "0"
+
+
+def fork_max_rows() -> int:
+    """Blocks with at most this many rows run their weight-gradient kernels on a side stream next to the dy2 / dy1 / grad_x
+    chain.  Default: always.  Measured on B200 (layer step, CUDA-graph replay): md17 1.63 -> 1.50 ms with the node blocks
+    (69 tiles, each kernel fills half the GPU) on the tensor-core engine, and still 1.51 -> 1.48 ms from forking the
+    per-pair blocks alone, whose persistent kernels leave SMs idle in their last wave (2.85 tiles per SM)."""
+    return int(os.environ.get("CSMPN_TC_FORK_MAX_ROWS", str(1 << 40)))
+
+
+def _tc_backward_forked(dim, d, g, ws, dev):
+    """csmpn_block_bwd (engine 1) as two concurrent chains, joined before returning:
+         main:  b1 -> gemm(dy2) -> b3 -> gemm(grad_x)
+         side:        dW(wl, wr) [after b1] -> dW(w1) [after b3] -> final reduce"""
+    main = torch.cuda.current_stream(dev)
+    side = _SIDE_STREAMS.get(dev)
+    if side is None:
+        side = _SIDE_STREAMS[dev] = torch.cuda.Stream(dev)
+
+    def run(mask, stream):
+        d.stage_mask = mask
+        check(lib().csmpn_block_bwd(dim, ctypes.byref(d), ctypes.byref(g), ptr(ws), ws.numel(), c_void_p(stream.cuda_stream)),
+              "block_bwd (tensor-core, forked)")
+
+    side.wait_stream(main)          # workspace and saved tensors were produced on the main stream
+    run(1, main)
+    e1 = torch.cuda.Event()
+    e1.record(main)
+    side.wait_event(e1)
+    run(16, side)
+    run(2 | 4, main)
+    e2 = torch.cuda.Event()
+    e2.record(main)
+    side.wait_event(e2)
+    run(32 | 64, side)
+    run(8, main)
+    main.wait_stream(side)
+    d.stage_mask = 0
 
 
 class SegmentReduceSortedFn(torch.autograd.Function):
@@ -387,8 +435,9 @@ TC_BACKWARD_READY = True
 
 def tc_min_rows() -> int:
     """Rows below which a block stays on the FP32 SIMT engine: the tensor-core engine runs a block as several
-    persistent kernels over 128-row tiles and needs a few tiles per SM to amortise their pipelines."""
-    return int(os.environ.get("CSMPN_TC_MIN_ROWS", "32768"))
+    persistent kernels over 128-row tiles; below ~64 tiles the SIMT engine's 16-row tiles use the GPU better
+    (motion-shaped batch, 4 700 simplices: 0.935 ms on SIMT node blocks vs 0.966 ms on tensor-core ones)."""
+    return int(os.environ.get("CSMPN_TC_MIN_ROWS", "8192"))  # 64 tiles; see DESIGN.md 4.4 for the measurements behind it
 
 
 def _block_uses_tc(algebra, layer, need_grad, rows=None) -> bool:
