@@ -497,7 +497,13 @@ __global__ void __launch_bounds__(256, 1) tc_dw_kernel(DwArgs a) {
     mbar_init(&full_bar[1], kConvWarps);
     mbar_fence_init();
   }
-  const uint32_t need = (uint32_t)G * a.cpb;
+  // M == 64 ("merged"): the hi and lo operand groups are contiguous in shared memory, so ONE instruction per K step of
+  // shape 128 x (2 * 32 gb) x 8 multiplies [A_hi; A_lo] by [B_hi | B_lo] and yields all four split products at once
+  // (lanes 0-63: A_hi rows, lanes 64-127: A_lo rows; first column half: B_hi, second: B_lo) instead of three M = 64
+  // instructions.  The epilogue adds the two column halves and writes the two lane halves as two partials.
+  const bool merged = a.M == 64;
+  const uint32_t ncol = merged ? 2u * gb * 32u : (uint32_t)a.cpb;  // accumulator columns per grade
+  const uint32_t need = (uint32_t)G * ncol;
   const uint32_t tcols = need <= 32 ? 32 : need <= 64 ? 64 : need <= 128 ? 128 : need <= 256 ? 256 : 512;
   if (warp == 0) tmem_alloc(tmem_slot, tcols);
   fence_async_smem();
@@ -505,7 +511,7 @@ __global__ void __launch_bounds__(256, 1) tc_dw_kernel(DwArgs a) {
   __syncthreads();
   fence_after_sync();
   const uint32_t tbase = *tmem_slot;
-  const uint32_t idesc = idesc_tf32(a.M, a.cpb, true, true);
+  const uint32_t idesc = merged ? idesc_tf32(128, (int)ncol, true, true) : idesc_tf32(a.M, a.cpb, true, true);
   const int my_tiles = (a.tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   const int steps = my_tiles * B * 2;  // step = (tile, blade, row half)
   // The producer/issuer warp and the converter warps are decoupled by mbarriers (no CTA-wide barrier in the loop): the
@@ -537,13 +543,18 @@ __global__ void __launch_bounds__(256, 1) tc_dw_kernel(DwArgs a) {
       const uint8_t* op_b = op_a + 2 * (size_t)ga * grp;
       const uint64_t a_hi = desc_mn32b(smem_addr(op_a), grp, 0), a_lo = a_hi + ((uint64_t)ga * grp >> 4);
       const uint64_t b_hi = desc_mn32b(smem_addr(op_b), grp, 0), b_lo = b_hi + ((uint64_t)gb * grp >> 4);
-      const uint32_t dcol = tbase + (uint32_t)g * a.cpb;
+      const uint32_t dcol = tbase + (uint32_t)g * ncol;
       const uint32_t acc = (grade_used >> g) & 1;
+      if (merged) {
 #pragma unroll
-      for (int ks = 0; ks < kDwRows / 8; ++ks) {  // one K step = 8 rows = 1024 bytes = 64 descriptor units
-        mma_tf32_w(dcol, a_hi + ks * 64, b_hi + ks * 64, idesc, ks == 0 ? acc : 1u);
-        mma_tf32_w(dcol, a_hi + ks * 64, b_lo + ks * 64, idesc, 1);
-        mma_tf32_w(dcol, a_lo + ks * 64, b_hi + ks * 64, idesc, 1);
+        for (int ks = 0; ks < kDwRows / 8; ++ks) mma_tf32_w(dcol, a_hi + ks * 64, b_hi + ks * 64, idesc, ks == 0 ? acc : 1u);
+      } else {
+#pragma unroll
+        for (int ks = 0; ks < kDwRows / 8; ++ks) {  // one K step = 8 rows = 1024 bytes = 64 descriptor units
+          mma_tf32_w(dcol, a_hi + ks * 64, b_hi + ks * 64, idesc, ks == 0 ? acc : 1u);
+          mma_tf32_w(dcol, a_hi + ks * 64, b_lo + ks * 64, idesc, 1);
+          mma_tf32_w(dcol, a_lo + ks * 64, b_hi + ks * 64, idesc, 1);
+        }
       }
       mma_commit_w(&op_bar[st & 1]);
       __syncwarp();
@@ -553,15 +564,18 @@ __global__ void __launch_bounds__(256, 1) tc_dw_kernel(DwArgs a) {
     }
   } else {
     const int ct = tid - 32, nconv = kConvWarps * 32;
+    const int r_first = ct / n4, u_first = ct - r_first * n4, r_step = nconv / n4, u_step = nconv - r_step * n4;
     for (int st = 0; st < steps; ++st) {
       mbar_wait(&load_bar[st % kDwLand], (st / kDwLand) & 1);
       if (st >= 2) mbar_wait(&op_bar[st & 1], ((st - 2) >> 1) & 1);  // the MMAs of step st-2 released this operand buffer
       const uint8_t* src = land + (size_t)(st % kDwLand) * land_bytes;
       uint8_t* op_a = ops + (size_t)(st & 1) * op_bytes;  // A hi groups, A lo groups
       uint8_t* op_b = op_a + 2 * (size_t)ga * grp;        // B hi groups, B lo groups
-      for (int it = ct; it < kDwRows * n4; it += nconv) {
-        const int r = it / n4, u = it - r * n4;
-        const float4 x = *reinterpret_cast<const float4*>(src + (size_t)u * kLand + r * 16);
+      // (r, u) = (it / n4, it % n4) advanced incrementally: an integer division per item was a quarter of this loop
+      int r = r_first, u = u_first;
+      for (int it = ct; it < kDwRows * n4; it += nconv, r += r_step, u += u_step) {
+        if (u >= n4) { u -= n4; ++r; }
+        const float4 x = *reinterpret_cast<const float4*>(src + (uint32_t)u * kLand + r * 16);
         float4 h, l;
         split4(x, h, l);
         const bool isb = u >= na4;
@@ -582,11 +596,25 @@ __global__ void __launch_bounds__(256, 1) tc_dw_kernel(DwArgs a) {
   if (steps > 0) mbar_wait(&op_bar[(steps - 1) & 1], ((steps - 1) >> 1) & 1);
   fence_after_sync();
   // ---- epilogue: D_g -> per-CTA partial [G][M][cpb]; grades this CTA never touched are written as zeros
-  float* out = a.partial + (size_t)blockIdx.x * G * a.M * a.cpb;
-  if (warp < 4) {
-    const bool m64 = a.M == 64;
-    const int m = m64 ? warp * 16 + (lane & 15) : warp * 32 + lane;
-    const bool lane_ok = !m64 || lane < 16;
+  if (warp < 4 && merged) {
+    // lane R = 32 warp + lane: rows R < 64 are A_hi products, R >= 64 A_lo products -> partial 2 * blockIdx + (R >> 6)
+    const int R = warp * 32 + lane, m = R & 63;
+    float* out = a.partial + ((size_t)blockIdx.x * 2 + (R >> 6)) * G * 64 * a.cpb;
+    for (int g = 0; g < G; ++g) {
+      const bool used = steps > 0 && ((grade_used >> g) & 1);
+      for (int n = 0; n < a.cpb; n += 4) {
+        float v[4] = {0.f, 0.f, 0.f, 0.f}, w[4] = {0.f, 0.f, 0.f, 0.f};
+        if (used) {
+          tmem_ld4(tmem_at(tbase, warp * 32, g * ncol + n), v);
+          tmem_ld4(tmem_at(tbase, warp * 32, g * ncol + gb * 32 + n), w);
+          tmem_wait_ld();
+        }
+        *reinterpret_cast<float4*>(out + ((size_t)g * 64 + m) * a.cpb + n) = make_float4(v[0] + w[0], v[1] + w[1], v[2] + w[2], v[3] + w[3]);
+      }
+    }
+  } else if (warp < 4) {
+    float* out = a.partial + (size_t)blockIdx.x * G * a.M * a.cpb;
+    const int m = warp * 32 + lane;
     for (int g = 0; g < G; ++g) {
       const bool used = steps > 0 && ((grade_used >> g) & 1);
       for (int n = 0; n < a.cpb; n += 4) {
@@ -595,7 +623,7 @@ __global__ void __launch_bounds__(256, 1) tc_dw_kernel(DwArgs a) {
           tmem_ld4(tmem_at(tbase, warp * 32, g * a.cpb + n), v);
           tmem_wait_ld();
         }
-        if (lane_ok) *reinterpret_cast<float4*>(out + ((size_t)g * a.M + m) * a.cpb + n) = make_float4(v[0], v[1], v[2], v[3]);
+        *reinterpret_cast<float4*>(out + ((size_t)g * a.M + m) * a.cpb + n) = make_float4(v[0], v[1], v[2], v[3]);
       }
     }
   }
@@ -714,8 +742,9 @@ int make_bwd_plan(const csmpn_block_desc& d, BwdPlan* p) {
   auto al = [](size_t x) { return (x + 31) / 32 * 32; };  // keep every segment 128-byte aligned
   p->o_p1 = o; o = al(o + (size_t)p->grid_ew * d.c * (P + G + 2));
   p->o_p3 = o; o = al(o + (size_t)p->grid_ew * d.c * (2 * G + 1));
-  p->o_dwa = o; o += (size_t)p->grid_dw * G * p->M1 * p->Cp * (p->dw_split ? 2 : 1);
-  p->o_dwb = o; o += (size_t)p->grid_dw * G * p->M2 * p->n16;
+  // M == 64 launches write two partials per CTA (hi and lo operand halves, see tc_dw_kernel)
+  p->o_dwa = o; o += (size_t)p->grid_dw * (p->M1 == 64 ? 2 : 1) * G * p->M1 * p->Cp * (p->dw_split ? 2 : 1);
+  p->o_dwb = o; o += (size_t)p->grid_dw * 2 * G * p->M2 * p->n16;
   p->total = o;
   return CSMPN_OK;
 }
@@ -805,7 +834,8 @@ int launch_bwd(const csmpn_block_desc& d, const csmpn_block_grads& g, void* work
   da.a0 = ws + p.o_d; da.a1 = ws + p.o_dxr; da.cpa = Cp; da.bsrc = d.save_y2; da.cpb = Cp; da.cpb_total = Cp; da.b_c4 = 0;
   da.M = p.M1;
   da.partial = ws + p.o_dwa;
-  const size_t dwa_part = (size_t)p.grid_dw * G * p.M1 * Cp;
+  const int pa = p.M1 == 64 ? 2 : 1;  // partials per CTA
+  const size_t dwa_part = (size_t)p.grid_dw * pa * G * p.M1 * Cp;
   if (!(mask & 16)) {
   } else if (!p.dw_split) {
     tc_dw_kernel<DIM><<<p.grid_dw, 256, dw_smem<DIM>(da.M, 2 * Cp / 4, Cp), stream>>>(da);
@@ -823,7 +853,7 @@ int launch_bwd(const csmpn_block_desc& d, const csmpn_block_grads& g, void* work
     const int nb = (p.n16 - i0) < p.nbw ? (p.n16 - i0) : p.nbw;
     da.a0 = ws + p.o_dy1; da.a1 = nullptr; da.cpa = Cp; da.bsrc = x0; da.cpb = nb; da.cpb_total = p.n16; da.b_c4 = i0 / 4;
     da.M = p.M2;
-    da.partial = ws + p.o_dwb + (size_t)p.grid_dw * G * p.M2 * i0;
+    da.partial = ws + p.o_dwb + (size_t)p.grid_dw * 2 * G * p.M2 * i0;
     tc_dw_kernel<DIM><<<p.grid_dw, 256, dw_smem<DIM>(da.M, Cp / 4, nb), stream>>>(da);
     CSMPN_LAUNCH_CHECK("tc_dw_kernel(w1)");
   }
@@ -836,13 +866,13 @@ int launch_bwd(const csmpn_block_desc& d, const csmpn_block_grads& g, void* work
     jb.in = in; jb.out = out; jb.parts = parts; jb.stride = (int64_t)G * M * N; jb.kind = 1; jb.n = co * ci * G;
     jb.G = G; jb.M = M; jb.N = N; jb.m0 = m0; jb.co = co; jb.ci = ci; jb.ci_tot = ci; jb.i0 = 0;
   };
-  wjob(ws + p.o_dwa, g.g_wl, p.grid_dw, p.M1, Cp, 0, C, C);
-  if (!p.dw_split) wjob(ws + p.o_dwa, g.g_wr, p.grid_dw, p.M1, Cp, Cp, C, C);
-  else wjob(ws + p.o_dwa + dwa_part, g.g_wr, p.grid_dw, p.M1, Cp, 0, C, C);
+  wjob(ws + p.o_dwa, g.g_wl, p.grid_dw * pa, p.M1, Cp, 0, C, C);
+  if (!p.dw_split) wjob(ws + p.o_dwa, g.g_wr, p.grid_dw * pa, p.M1, Cp, Cp, C, C);
+  else wjob(ws + p.o_dwa + dwa_part, g.g_wr, p.grid_dw * pa, p.M1, Cp, 0, C, C);
   for (int i0 = 0; i0 < p.cin; i0 += p.nbw) {
     const int nb = (p.n16 - i0) < p.nbw ? (p.n16 - i0) : p.nbw;
     const int ci = (p.cin - i0) < p.nbw ? (p.cin - i0) : p.nbw;
-    wjob(ws + p.o_dwb + (size_t)p.grid_dw * G * p.M2 * i0, g.g_w1, p.grid_dw, p.M2, nb, 0, C, ci);
+    wjob(ws + p.o_dwb + (size_t)p.grid_dw * 2 * G * p.M2 * i0, g.g_w1, p.grid_dw * 2, p.M2, nb, 0, C, ci);
     fj.j[k - 1].ci_tot = p.cin;
     fj.j[k - 1].i0 = i0;
   }

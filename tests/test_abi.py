@@ -74,3 +74,16 @@ def test_product_refuses_cpu_tensors(built_lib):
         alg.geometric_product(torch.randn(2, 8), torch.randn(2, 8))
     with pytest.raises(RuntimeError, match="no CPU path"):
         MVLinear(alg, 4, 4)(torch.randn(3, 4, 8))
+
+
+def test_simt_tile_rows_query(built_lib):
+    """csmpn_block_simt_resident: rows per shared-memory tile of the SIMT engine (0 = weights would be staged); the host
+    side composes blocks from unit kernels below 4 rows (models/fused.py)"""
+    from csmpn_b200 import _lib
+
+    l = _lib.lib()
+    assert l.csmpn_block_simt_resident(3, 38, 32) >= 8       # md17 edge block
+    assert l.csmpn_block_simt_resident(5, 34, 28) >= 4       # hulls, Cl(5,0)
+    assert 0 <= l.csmpn_block_simt_resident(3, 70, 64) < 4   # wide block: composed from unit kernels
+    assert l.csmpn_block_simt_resident(3, 131, 64) == 0
+    assert l.csmpn_block_simt_resident(4, 8, 8) == 0         # unsupported dimension
