@@ -458,22 +458,33 @@ struct DwArgs {
   int b_c4;       // first 4-channel group of bsrc used by this launch
   int M;          // 64 or 128, >= channels of Acat
   float* partial; // [grid][G][M][cpb]
+  long long* dbg; // optional timeline buffer (csmpn_tc_debug_buffer): CTA 0, threads 0 (issuer) and 32 (converter)
 };
+long long*& debug_buffer();  // tc_block_fwd.cu
+#define DW_STAMP(code)                                                                       \
+  do {                                                                                       \
+    if (TL && a.dbg && blockIdx.x == 0 && (tid == 0 || tid == 32) && dbg_n < 250) {          \
+      a.dbg[(tid ? 512 : 0) + 2 * dbg_n] = (code);                                           \
+      a.dbg[(tid ? 512 : 0) + 2 * dbg_n + 1] = clock64();                                    \
+      ++dbg_n;                                                                               \
+    }                                                                                        \
+  } while (0)
 
 // Step = (tile, blade, half of the tile's rows): 64 rows = 8 K steps.  The BPT columns of a step ([64 rows][4 ch] = 1 KB
 // each) land through a ring of kDwLand landing slots (loads run kDwLand-1 steps ahead), a conversion pass splits them
 // into hi / lo and re-lays them out as [row][32 channels] operand groups (SWIZZLE_128B_BASE32B), double-buffered so
 // that the conversion of step s+1 overlaps the MMAs of step s.
 constexpr int kDwRows = 64;
-constexpr int kDwLand = 4;
-constexpr uint32_t kLand = kDwRows * 16 + 16;  // landing stride of one 4-channel column (+16: conflict-free conversion reads)
+constexpr int kDwLand = 2;                 // landing slots; a slot holds one (tile, blade) = both row halves = two steps
+constexpr uint32_t kLand = kTile * 16;     // landing stride of one 4-channel column: [128 rows][4 channels], as in global memory
 
-template <int DIM>
+template <int DIM, bool TL>
 __global__ void __launch_bounds__(256, 1) tc_dw_kernel(DwArgs a) {
   using A = Alg<DIM>;
   constexpr int B = A::B, G = A::G;
   extern __shared__ __align__(1024) uint8_t smem[];
   const int tid = threadIdx.x, warp = uniform_warp_idx(), lane = tid & 31;
+  int dbg_n = 0;
   const int ca4 = a.cpa >> 2;
   const int na4 = (a.a1 ? 2 : 1) * ca4;  // 4-channel groups of Acat
   const int nb4 = a.cpb >> 2;
@@ -485,6 +496,9 @@ __global__ void __launch_bounds__(256, 1) tc_dw_kernel(DwArgs a) {
   uint8_t* land = ops + 2 * (size_t)op_bytes;       // kDwLand landing slots
   const uint32_t land_bytes = (uint32_t)n4 * kLand;
   uint64_t* bars = reinterpret_cast<uint64_t*>(land + (size_t)kDwLand * land_bytes);
+  // A (tile, blade) of a BPT tensor is contiguous ([channel/4][128 rows][4]), so a landing unit is 2-3 bulk copies of
+  // 8-32 KB.  (cp.async.bulk is a uniform-datapath instruction: per-lane addresses are serialised at ~70 cycles per copy,
+  // and the 24 one-KB copies per step of the first version took 72 % of the issuer's time.)
   uint64_t* load_bar = bars;                 // [kDwLand] the bulk copies of a step have landed
   uint64_t* op_bar = bars + kDwLand;         // [2] the MMAs reading an operand buffer have completed
   uint64_t* full_bar = bars + kDwLand + 2;   // [2] every converter warp has written its part of an operand buffer
@@ -517,28 +531,29 @@ __global__ void __launch_bounds__(256, 1) tc_dw_kernel(DwArgs a) {
   // The producer/issuer warp and the converter warps are decoupled by mbarriers (no CTA-wide barrier in the loop): the
   // conversion of step st+1 runs while warp 0 issues the MMAs of step st and the copies of step st+kDwLand.
   if (warp == 0) {
-    auto issue = [&](int st) {           // all lanes of warp 0
-      const int64_t tile = (int64_t)blockIdx.x + (int64_t)(st / (2 * B)) * gridDim.x;
-      const int b = (st >> 1) % B, rh = st & 1;
-      uint8_t* dst = land + (size_t)(st % kDwLand) * land_bytes;
-      uint64_t* bar = &load_bar[st % kDwLand];
-      if (lane == 0) mbar_arrive_expect_tx(bar, (uint32_t)n4 * (kDwRows * 16u));
-      __syncwarp();
-      for (int u = lane; u < n4; u += 32) {
-        const float* src;
-        if (u < ca4) src = a.a0 + bpt_off(B, a.cpa, tile, b, u, rh * kDwRows);
-        else if (u < na4) src = a.a1 + bpt_off(B, a.cpa, tile, b, u - ca4, rh * kDwRows);
-        else src = a.bsrc + bpt_off(B, a.cpb_total, tile, b, a.b_c4 + (u - na4), rh * kDwRows);
-        bulk_g2s(dst + (size_t)u * kLand, src, kDwRows * 16u, bar);
+    const int units = steps >> 1;        // landing units = (tile, blade)
+    auto issue = [&](int lu) {           // all lanes of warp 0
+      const int64_t tile = (int64_t)blockIdx.x + (int64_t)(lu / B) * gridDim.x;
+      const int b = lu % B;
+      uint8_t* dst = land + (size_t)(lu % kDwLand) * land_bytes;
+      uint64_t* bar = &load_bar[lu % kDwLand];
+      if (lane == 0) {
+        mbar_arrive_expect_tx(bar, (uint32_t)n4 * kLand);
+        bulk_g2s(dst, a.a0 + bpt_off(B, a.cpa, tile, b, 0, 0), (uint32_t)ca4 * kLand, bar);
+        if (a.a1) bulk_g2s(dst + (size_t)ca4 * kLand, a.a1 + bpt_off(B, a.cpa, tile, b, 0, 0), (uint32_t)ca4 * kLand, bar);
+        bulk_g2s(dst + (size_t)na4 * kLand, a.bsrc + bpt_off(B, a.cpb_total, tile, b, a.b_c4, 0), (uint32_t)nb4 * kLand, bar);
       }
+      __syncwarp();
     };
     int loaded = 0;
-    for (; loaded < kDwLand && loaded < steps; ++loaded) issue(loaded);
+    for (; loaded < kDwLand && loaded < units; ++loaded) issue(loaded);
     uint32_t grade_used = 0;
     for (int st = 0; st < steps; ++st) {
       const int b = (st >> 1) % B, g = A::grade_of(b);
+      DW_STAMP(30);
       mbar_wait(&full_bar[st & 1], (st >> 1) & 1);
       fence_after_sync();
+      DW_STAMP(31);
       const uint8_t* op_a = ops + (size_t)(st & 1) * op_bytes;
       const uint8_t* op_b = op_a + 2 * (size_t)ga * grp;
       const uint64_t a_hi = desc_mn32b(smem_addr(op_a), grp, 0), a_lo = a_hi + ((uint64_t)ga * grp >> 4);
@@ -558,23 +573,31 @@ __global__ void __launch_bounds__(256, 1) tc_dw_kernel(DwArgs a) {
       }
       mma_commit_w(&op_bar[st & 1]);
       __syncwarp();
-      // the landing slot of step st was consumed by its conversion (full_bar observed above): refill it
-      if (loaded < steps) { issue(loaded); ++loaded; }
+      DW_STAMP(32);
+      // both row halves of the landing unit st >> 1 have been converted (full_bar observed above): refill its slot
+      if ((st & 1) && loaded < units) { issue(loaded); ++loaded; }
+      DW_STAMP(33);
       grade_used |= 1u << g;
     }
   } else {
     const int ct = tid - 32, nconv = kConvWarps * 32;
-    const int r_first = ct / n4, u_first = ct - r_first * n4, r_step = nconv / n4, u_step = nconv - r_step * n4;
     for (int st = 0; st < steps; ++st) {
-      mbar_wait(&load_bar[st % kDwLand], (st / kDwLand) & 1);
+      const int lu = st >> 1, rh = st & 1;
+      DW_STAMP(40);
+      mbar_wait(&load_bar[lu % kDwLand], (lu / kDwLand) & 1);
+      DW_STAMP(41);
       if (st >= 2) mbar_wait(&op_bar[st & 1], ((st - 2) >> 1) & 1);  // the MMAs of step st-2 released this operand buffer
-      const uint8_t* src = land + (size_t)(st % kDwLand) * land_bytes;
+      DW_STAMP(42);
+      const uint8_t* src = land + (size_t)(lu % kDwLand) * land_bytes + (uint32_t)rh * (kDwRows * 16);
       uint8_t* op_a = ops + (size_t)(st & 1) * op_bytes;  // A hi groups, A lo groups
       uint8_t* op_b = op_a + 2 * (size_t)ga * grp;        // B hi groups, B lo groups
-      // (r, u) = (it / n4, it % n4) advanced incrementally: an integer division per item was a quarter of this loop
-      int r = r_first, u = u_first;
-      for (int it = ct; it < kDwRows * n4; it += nconv, r += r_step, u += u_step) {
-        if (u >= n4) { u -= n4; ++r; }
+      // Item -> (column u, row r): every aligned group of 8 threads (one 128-bit shared-memory phase) takes rows
+      // rb .. rb+7 of a column PAIR, four rows from each column.  The reads then cover eight distinct 16-byte bank
+      // groups (r mod 8; columns are 2 KB apart) and so do the swizzled writes ((c/8 ^ r%4, c%8/4) differs in all 8).
+      for (int it = ct; it < kDwRows * n4; it += nconv) {
+        const int pr = it >> 7, w = it & 127, q = w & 7, g8 = w >> 3;
+        const int swap = g8 >> 3, r = ((g8 & 7) << 3) + q;
+        const int u = 2 * pr + ((q >> 2) ^ swap);
         const float4 x = *reinterpret_cast<const float4*>(src + (uint32_t)u * kLand + r * 16);
         float4 h, l;
         split4(x, h, l);
@@ -589,6 +612,7 @@ __global__ void __launch_bounds__(256, 1) tc_dw_kernel(DwArgs a) {
       fence_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(&full_bar[st & 1]);
+      DW_STAMP(43);
     }
   }
   uint32_t grade_used = 0;
@@ -696,7 +720,7 @@ size_t gemm_smem(int nsets, int n16, int kmax) {
 template <int DIM>
 size_t dw_smem(int M, int na4, int cpb) {
   const int ga = M / 32, gb = (cpb + 31) / 32;
-  return (size_t)2 * 2 * (ga + gb) * kDwRows * 128 + (size_t)kDwLand * (na4 + cpb / 4) * kLand + 128;
+  return (size_t)2 * 2 * (ga + gb) * kDwRows * 128 + (size_t)kDwLand * (na4 + cpb / 4) * kLand + 128;  // kLand = 2 KB
 }
 constexpr size_t kSmemMax = 227 * 1024;
 
@@ -827,9 +851,11 @@ int launch_bwd(const csmpn_block_desc& d, const csmpn_block_grads& g, void* work
     CSMPN_LAUNCH_CHECK("tc_bgemm_kernel(grad_x)");
   }
   // ---- weight gradients
-  CSMPN_CUDA_TRY(cudaFuncSetAttribute(tc_dw_kernel<DIM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
   DwArgs da;
   memset(&da, 0, sizeof(da));
+  da.dbg = debug_buffer();
+  auto dw_kernel = da.dbg ? tc_dw_kernel<DIM, true> : tc_dw_kernel<DIM, false>;
+  CSMPN_CUDA_TRY(cudaFuncSetAttribute(dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
   da.rows = d.rows; da.tiles = p.tiles;
   da.a0 = ws + p.o_d; da.a1 = ws + p.o_dxr; da.cpa = Cp; da.bsrc = d.save_y2; da.cpb = Cp; da.cpb_total = Cp; da.b_c4 = 0;
   da.M = p.M1;
@@ -838,15 +864,15 @@ int launch_bwd(const csmpn_block_desc& d, const csmpn_block_grads& g, void* work
   const size_t dwa_part = (size_t)p.grid_dw * pa * G * p.M1 * Cp;
   if (!(mask & 16)) {
   } else if (!p.dw_split) {
-    tc_dw_kernel<DIM><<<p.grid_dw, 256, dw_smem<DIM>(da.M, 2 * Cp / 4, Cp), stream>>>(da);
+    dw_kernel<<<p.grid_dw, 256, dw_smem<DIM>(da.M, 2 * Cp / 4, Cp), stream>>>(da);
     CSMPN_LAUNCH_CHECK("tc_dw_kernel(wl,wr)");
   } else {
     da.a1 = nullptr;
-    tc_dw_kernel<DIM><<<p.grid_dw, 256, dw_smem<DIM>(da.M, Cp / 4, Cp), stream>>>(da);
+    dw_kernel<<<p.grid_dw, 256, dw_smem<DIM>(da.M, Cp / 4, Cp), stream>>>(da);
     CSMPN_LAUNCH_CHECK("tc_dw_kernel(wl)");
     da.a0 = ws + p.o_dxr;
     da.partial = ws + p.o_dwa + dwa_part;
-    tc_dw_kernel<DIM><<<p.grid_dw, 256, dw_smem<DIM>(da.M, Cp / 4, Cp), stream>>>(da);
+    dw_kernel<<<p.grid_dw, 256, dw_smem<DIM>(da.M, Cp / 4, Cp), stream>>>(da);
     CSMPN_LAUNCH_CHECK("tc_dw_kernel(wr)");
   }
   for (int i0 = 0; i0 < p.n16 && (mask & 32); i0 += p.nbw) {
@@ -854,7 +880,7 @@ int launch_bwd(const csmpn_block_desc& d, const csmpn_block_grads& g, void* work
     da.a0 = ws + p.o_dy1; da.a1 = nullptr; da.cpa = Cp; da.bsrc = x0; da.cpb = nb; da.cpb_total = p.n16; da.b_c4 = i0 / 4;
     da.M = p.M2;
     da.partial = ws + p.o_dwb + (size_t)p.grid_dw * 2 * G * p.M2 * i0;
-    tc_dw_kernel<DIM><<<p.grid_dw, 256, dw_smem<DIM>(da.M, Cp / 4, nb), stream>>>(da);
+    dw_kernel<<<p.grid_dw, 256, dw_smem<DIM>(da.M, Cp / 4, nb), stream>>>(da);
     CSMPN_LAUNCH_CHECK("tc_dw_kernel(w1)");
   }
   // ---- final reduction
