@@ -18,10 +18,12 @@ constexpr int kTile = 128;     // rows per tile = UMMA M
 constexpr int kThreads = 512;  // 16 warps: warp w owns TMEM lanes 32*(w%4).., channel groups (w/4), (w/4)+4, ...
 constexpr float kInvSqrt2 = 0.70710678118654752440f;
 
-// chunk buffer (one K step of 8 channels, all blades): hi planes then lo planes.  A plane is [2][128][4] fp32; the two
-// halves are KH apart and planes PS apart, padded so that the scalar stores of the transposing producer (lanes differ
-// in channel and blade half) spread over all 32 banks.
-constexpr uint32_t kKH = 2048 + 32;
+// chunk buffer (one K step of 8 channels, all blades): hi planes then lo planes.  A plane is [2][128][4] fp32, 4 KB
+// contiguous exactly as in a BPT tensor, so ONE bulk copy brings a blade of a chunk in (cp.async.bulk is issued from
+// the uniform datapath: per-lane addresses serialise at ~70 cycles per copy, so fewer and larger copies matter).
+// Planes are PS apart; the 16-byte pad makes the scalar stores of the transposing producer (lanes = 4 channels x 4
+// rows x 2 blade quads) hit all 32 banks.
+constexpr uint32_t kKH = 2048;
 constexpr uint32_t kPS = 2 * kKH + 16;
 
 __host__ __device__ constexpr int round_up(int x, int m) { return (x + m - 1) / m * m; }
@@ -164,10 +166,7 @@ __device__ __forceinline__ void issue_chunk_load(const Pipe& p, int q, const flo
   uint64_t* bar = &p.load_bar[q % kRing];
   if (lane == 0) mbar_arrive_expect_tx(bar, B * 4096u);
   __syncwarp();
-  for (int u = lane; u < 2 * B; u += 32) {
-    const int b = u >> 1, kh = u & 1;
-    bulk_g2s(p.slot(q) + b * kPS + kh * kKH, bpt + bpt_off(B, cp, tile, b, 2 * kc + kh, 0), 2048u, bar);
-  }
+  if (lane < B) bulk_g2s(p.slot(q) + lane * kPS, bpt + bpt_off(B, cp, tile, lane, 2 * kc, 0), 4096u, bar);
 }
 // split pass over the landed chunk q (CONVERTER warps only): high parts in place, remainders to `lo`.  The remainders
 // wait in registers until the MMAs of chunk q-1 (the previous readers of `lo`) have completed, so reading the chunk,

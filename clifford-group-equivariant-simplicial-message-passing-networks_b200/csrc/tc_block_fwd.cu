@@ -49,6 +49,16 @@ struct FwdArgs {
 template <int DIM>
 struct ApiItems {
   static constexpr int H = Alg<DIM>::B / 4, PPR = 8 * H, TOT = kTile * PPR, N = (TOT + kConv - 1) / kConv;
+  // item -> (row r, chunk channel cl, blade quad h).  A warp covers 4 channels x (8 / H) rows x H blade quads, so that
+  // its transposing scalar stores (bank = 16 h + 4 (r % 4) + cl % 4 for Cl(3,0)) are conflict-free and its global
+  // reads / x0 writes are 128 / 64 contiguous bytes per row.
+  __device__ static __forceinline__ void decode(int it, int& r, int& cl, int& h) {
+    const int l = it & 31, g = it >> 5;
+    h = l % H;
+    const int clo = (l / H) & 3, rlo = l / (4 * H);  // rlo < 8 / H
+    cl = (g & 1) * 4 + clo;
+    r = (g >> 1) * (8 / H) + rlo;
+  }
 };
 
 template <int DIM>
@@ -58,8 +68,8 @@ __device__ __forceinline__ void gather_chunk_api(const FwdArgs& a, int64_t row0,
 #pragma unroll
   for (int i = 0; i < N; ++i) {
     const int it = ct + i * kConv;
-    const int r = it / PPR, pc = it - r * PPR;
-    const int cl = pc / H, h = pc - cl * H;
+    int r, cl, h;
+    ApiItems<DIM>::decode(it, r, cl, h);
     const int c = kc * 8 + cl;
     const int64_t R = row0 + r;
     v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -98,8 +108,8 @@ __device__ __forceinline__ void store_chunk_api(const Pipe& p, int q, const floa
   for (int i = 0; i < N; ++i) {
     const int it = ct + i * kConv;
     if (it < TOT) {
-      const int r = it / PPR, pc = it - r * PPR;
-      const int cl = pc / H, h = pc - cl * H;
+      int r, cl, h;
+      ApiItems<DIM>::decode(it, r, cl, h);
       float4 hv;
       split4(v[i], hv, lv[i]);
       const uint32_t off = (4 * h) * kPS + (cl >> 2) * kKH + r * 16 + (cl & 3) * 4;
@@ -114,8 +124,8 @@ __device__ __forceinline__ void store_chunk_api(const Pipe& p, int q, const floa
     for (int i = 0; i < N; ++i) {
       const int it = ct + i * kConv;
       if (it < TOT) {
-        const int r = it / PPR, pc = it - r * PPR;
-        const int cl = pc / H, h = pc - cl * H;
+        int r, cl, h;
+        ApiItems<DIM>::decode(it, r, cl, h);
         float* dst = x0 + bpt_off(B, x0_cp, tile, 4 * h, 2 * kc + (cl >> 2), r) + (cl & 3);
         const size_t bs = (size_t)(x0_cp >> 2) * kTile * 4;  // floats between blade planes
         dst[0] = v[i].x;
@@ -130,8 +140,8 @@ __device__ __forceinline__ void store_chunk_api(const Pipe& p, int q, const floa
   for (int i = 0; i < N; ++i) {
     const int it = ct + i * kConv;
     if (it < TOT) {
-      const int r = it / PPR, pc = it - r * PPR;
-      const int cl = pc / H, h = pc - cl * H;
+      int r, cl, h;
+      ApiItems<DIM>::decode(it, r, cl, h);
       const uint32_t off = (4 * h) * kPS + (cl >> 2) * kKH + r * 16 + (cl & 3) * 4;
       *reinterpret_cast<float*>(lo + off) = lv[i].x;
       *reinterpret_cast<float*>(lo + off + kPS) = lv[i].y;
