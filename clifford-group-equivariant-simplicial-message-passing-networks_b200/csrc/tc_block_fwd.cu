@@ -400,6 +400,16 @@ __global__ void __launch_bounds__(kThreads, 1) tc_f2_kernel(FwdArgs a) {
 #pragma unroll
       for (int b = 0; b < B; ++b) tmem_ld4(tmem_at(tbase, lane_base, b * bcols + col_l + c4 * 4), o[b]);
       tmem_wait_ld();
+      // the saved tensors are stored from this (compute-bound) pass, so that their drain overlaps the arithmetic; the
+      // second pass then only writes the block output
+      if (a.save_xr) {
+#pragma unroll
+        for (int b = 0; b < B; ++b) {
+          float4 x = make_float4(xr[b][0], xr[b][1], xr[b][2], xr[b][3]);
+          if (!row_ok) x = make_float4(0.f, 0.f, 0.f, 0.f);
+          *reinterpret_cast<float4*>(a.save_xr + bpt_off(B, Cp, tile, b, c4, r)) = x;
+        }
+      }
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int ch = c4 * 4 + j;
@@ -422,6 +432,11 @@ __global__ void __launch_bounds__(kThreads, 1) tc_f2_kernel(FwdArgs a) {
       }
 #pragma unroll
       for (int b = 0; b < B; ++b) tmem_st4(tmem_at(tbase, lane_base, b * bcols + col_l + c4 * 4), o[b]);
+      if (a.save_o) {
+#pragma unroll
+        for (int b = 0; b < B; ++b)
+          *reinterpret_cast<float4*>(a.save_o + bpt_off(B, Cp, tile, b, c4, r)) = make_float4(o[b][0], o[b][1], o[b][2], o[b][3]);
+      }
     }
     tmem_wait_st();
     TSTAMP(22);
@@ -432,25 +447,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc_f2_kernel(FwdArgs a) {
     // ---- pass 2: saves, MVLayerNorm scale, residual, output
     for (int c4 = warp >> 2; c4 < (Cp >> 2); c4 += 4) {
       float o[B][4];
-      if (a.save_xr) {
-#pragma unroll
-        for (int b = 0; b < B; ++b) tmem_ld4(tmem_at(tbase, lane_base, b * bcols + col_r + c4 * 4), o[b]);
-        tmem_wait_ld();
-#pragma unroll
-        for (int b = 0; b < B; ++b) {
-          float4 x = make_float4(o[b][0], o[b][1], o[b][2], o[b][3]);
-          if (!row_ok) x = make_float4(0.f, 0.f, 0.f, 0.f);
-          *reinterpret_cast<float4*>(a.save_xr + bpt_off(B, Cp, tile, b, c4, r)) = x;
-        }
-      }
 #pragma unroll
       for (int b = 0; b < B; ++b) tmem_ld4(tmem_at(tbase, lane_base, b * bcols + col_l + c4 * 4), o[b]);
       tmem_wait_ld();
-      if (a.save_o) {
-#pragma unroll
-        for (int b = 0; b < B; ++b)
-          *reinterpret_cast<float4*>(a.save_o + bpt_off(B, Cp, tile, b, c4, r)) = make_float4(o[b][0], o[b][1], o[b][2], o[b][3]);
-      }
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const float sc = la_s[c4 * 4 + j] * inv_mu;
