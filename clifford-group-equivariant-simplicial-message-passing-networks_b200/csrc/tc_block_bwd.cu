@@ -377,14 +377,14 @@ __global__ void __launch_bounds__(kThreads, 1) tc_bgemm_kernel(GemmArgs a) {
       for (int kc = 0; kc < nk; ++kc, ++q) {
         if (warp == 0) {  // issuer
           p.wait_full(q);
-          {
-            const int s = kc < a.nk[0] ? 0 : 1;
-            issue_chunk_mma<DIM>(p, q, tbase, Np, kc > 0, wimg, img, s, 1, set_bytes, a.n16, s ? kc - a.nk[0] : kc, n0, idesc);
-          }
-          if (loaded == q + kRing - 1 && loaded < total_chunks) {
+          if (loaded == q + kRing - 1 && loaded < total_chunks) {  // reload the slot of chunk q-1 before issuing the MMAs
             if (q >= 1) mbar_wait(&p.slot_bar[(q - 1) % kRing], ((q - 1) / kRing) & 1);
             issue(loaded);
             ++loaded;
+          }
+          {
+            const int s = kc < a.nk[0] ? 0 : 1;
+            issue_chunk_mma<DIM>(p, q, tbase, Np, kc > 0, wimg, img, s, 1, set_bytes, a.n16, s ? kc - a.nk[0] : kc, n0, idesc);
           }
         } else {          // converters
           mbar_wait(&p.load_bar[q % kRing], (q / kRing) & 1);

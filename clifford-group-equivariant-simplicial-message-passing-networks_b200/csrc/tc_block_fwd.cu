@@ -226,13 +226,14 @@ __global__ void __launch_bounds__(kThreads, 1) tc_f1_kernel(FwdArgs a) {
     for (int kc = 0; kc < nk; ++kc, ++q) {
       if (warp == 0) {  // issuer
         p.wait_full(q);
-        issue_chunk_mma<DIM>(p, q, tbase, Cp, kc > 0, wimg, img, 0, 1, 0, Cp, kc, 0, idesc);
         if (BPT_IN && loaded == q + kRing - 1 && loaded < total_chunks) {
-          // slot (q-1) % kRing was read by the MMAs of chunk q-1: reload it as soon as they are done
+          // slot (q-1) % kRing was read by the MMAs of chunk q-1, issued a whole chunk period ago: reload it first, so
+          // that the copy has the issue time of this chunk's MMAs as extra lead
           if (q >= 1) mbar_wait(&p.slot_bar[(q - 1) % kRing], ((q - 1) / kRing) & 1);
           issue_chunk_load<B>(p, loaded, a.p0, a.in_cp, tile_of(loaded), loaded % nk);
           ++loaded;
         }
+        issue_chunk_mma<DIM>(p, q, tbase, Cp, kc > 0, wimg, img, 0, 1, 0, Cp, kc, 0, idesc);
       } else if (BPT_IN) {  // converters: split the landed chunk
         mbar_wait(&p.load_bar[q % kRing], (q / kRing) & 1);
         split_chunk<B>(p, q);
@@ -357,14 +358,14 @@ __global__ void __launch_bounds__(kThreads, 1) tc_f2_kernel(FwdArgs a) {
       if (warp == 0) {  // issuer
         p.wait_full(q);
         TSTAMP(14);
-        issue_chunk_mma<DIM>(p, q, tbase, bcols, kc > 0, wimg, img, 0, 1, 0, bcols, kc, 0, idesc);
-        TSTAMP(15);
         if (loaded == q + kRing - 1 && loaded < total_chunks) {
           if (q >= 1) mbar_wait(&p.slot_bar[(q - 1) % kRing], ((q - 1) / kRing) & 1);
           issue_chunk_load<B>(p, loaded, a.y2, Cp, tile_of(loaded), loaded % nk);
           ++loaded;
         }
         TSTAMP(16);
+        issue_chunk_mma<DIM>(p, q, tbase, bcols, kc > 0, wimg, img, 0, 1, 0, bcols, kc, 0, idesc);
+        TSTAMP(15);
       } else {          // converters
         mbar_wait(&p.load_bar[q % kRing], (q / kRing) & 1);
         TSTAMP(11);
