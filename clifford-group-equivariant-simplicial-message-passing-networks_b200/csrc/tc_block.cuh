@@ -123,6 +123,10 @@ __device__ __forceinline__ uint64_t chunk_desc(uint32_t half_saddr, int b) {
 // pass / gathering producer).  They are decoupled by mbarriers only -- no CTA-wide barrier inside the K loop -- so the
 // conversion of chunk q+1 overlaps the issue and execution of the MMAs of chunk q.  Every warp takes part in the tile
 // epilogue.
+// tcgen05.mma kind::tf32 reads fp32 operands and ignores the low 13 mantissa bits (truncation, verified on B200 by the
+// 1e-5 parity tests, which a round-to-nearest read would fail by 2^-11): the raw chunk already IS the high operand, so the
+// split pass only has to produce the remainders.
+constexpr bool kTf32Truncates = true;
 constexpr int kRing = 3;
 constexpr int kPipeBars = 3 * kRing + 1;
 constexpr int kConvWarps = kThreads / 32 - 1;
@@ -187,7 +191,7 @@ __device__ __forceinline__ void split_chunk(const Pipe& p, int q) {
       const float4 x = *reinterpret_cast<const float4*>(hi + off);
       float4 h;
       split4(x, h, l[i]);
-      *reinterpret_cast<float4*>(hi + off) = h;
+      if (!kTf32Truncates) *reinterpret_cast<float4*>(hi + off) = h;
     }
   }
   if (q >= 1) mbar_wait(p.lo_bar, (q - 1) & 1);
