@@ -470,10 +470,11 @@ long long*& debug_buffer();  // tc_block_fwd.cu
     }                                                                                        \
   } while (0)
 
-// Step = (tile, blade, half of the tile's rows): 64 rows = 8 K steps.  The BPT columns of a step ([64 rows][4 ch] = 1 KB
-// each) land through a ring of kDwLand landing slots (loads run kDwLand-1 steps ahead), a conversion pass splits them
-// into hi / lo and re-lays them out as [row][32 channels] operand groups (SWIZZLE_128B_BASE32B), double-buffered so
-// that the conversion of step s+1 overlaps the MMAs of step s.
+// Step = (tile, blade, half of the tile's rows): 64 rows = 8 K steps.  A landing unit = (tile, blade) = two steps: the
+// blade slabs of the operand tensors ([channels/4][128 rows][4], contiguous in a BPT tensor) arrive with 2-3 large bulk
+// copies into one of kDwLand landing slots (the next unit loads while the current one is converted); a conversion pass
+// splits a step into hi / lo and re-lays it out as [row][32 channels] operand groups (SWIZZLE_128B_BASE32B),
+// double-buffered so that the conversion of step s+1 overlaps the MMAs of step s.
 constexpr int kDwRows = 64;
 constexpr int kDwLand = 2;                 // landing slots; a slot holds one (tile, blade) = both row halves = two steps
 constexpr uint32_t kLand = kTile * 16;     // landing stride of one 4-channel column: [128 rows][4 channels], as in global memory

@@ -152,20 +152,6 @@ __device__ __forceinline__ void store_chunk_api(const Pipe& p, int q, const floa
 }
 // barrier among the converter warps only (named barrier 1; warp 0 never joins)
 __device__ __forceinline__ void conv_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(kConv) : "memory"); }
-// copy of the assembled input rows for the weight-gradient GEMM of the backward: chunk buffer -> BPT (coalesced)
-template <int B>
-__device__ __forceinline__ void save_chunk_bpt(const Pipe& p, int q, float* dst, int cp, int64_t tile, int kc) {
-  const uint8_t* hi = p.slot(q);
-  const uint8_t* lo = p.lo;
-  for (int it = (int)threadIdx.x - 32; it < B * 2 * kTile; it += kConv) {
-    const int r = it & (kTile - 1), kh = (it >> 7) & 1, b = it >> 8;
-    const uint32_t off = b * kPS + kh * kKH + r * 16;
-    const float4 h = *reinterpret_cast<const float4*>(hi + off);
-    const float4 l = *reinterpret_cast<const float4*>(lo + off);
-    *reinterpret_cast<float4*>(dst + bpt_off(B, cp, tile, b, 2 * kc + kh, r)) = make_float4(h.x + l.x, h.y + l.y, h.z + l.z, h.w + l.w);
-  }
-}
-
 // zero the 8 padding channels of chunk kc of a BPT tensor (c_in padded to 16 but staged in chunks of 8)
 template <int B>
 __device__ __forceinline__ void zero_chunk_bpt(float* dst, int cp, int64_t tile, int kc) {
