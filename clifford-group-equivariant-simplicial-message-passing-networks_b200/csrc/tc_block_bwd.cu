@@ -367,6 +367,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_bgemm_kernel(GemmArgs a) {
   int q = 0, loaded = 0;
   if (warp == 0) for (; loaded < kRing - 1 && loaded < total_chunks; ++loaded) issue(loaded);
   const uint32_t lane_base = (warp & 3) * 32;
+  const bool wide_ok = aligned32(a.out);
   for (int t = 0; t < my_tiles; ++t) {
     const int64_t tile = (int64_t)blockIdx.x + (int64_t)t * gridDim.x;
     const int64_t row0 = tile * kTile;
@@ -432,6 +433,15 @@ __global__ void __launch_bounds__(kThreads, 1) tc_bgemm_kernel(GemmArgs a) {
             const int n = gc4 * 4 + jj;
             if (n >= a.wn) continue;
             float* dst = a.out + ((size_t)(row0 + r) * a.wn + n) * B;
+            if constexpr (B == 8) {
+              if (wide_ok) {
+                float w8[8];
+#pragma unroll
+                for (int b = 0; b < 8; ++b) w8[b] = v[b][jj];
+                st_global_v8(dst, w8);
+                continue;
+              }
+            }
 #pragma unroll
             for (int h = 0; h < B / 4; ++h)
               *reinterpret_cast<float4*>(dst + 4 * h) = make_float4(v[4 * h][jj], v[4 * h + 1][jj], v[4 * h + 2][jj], v[4 * h + 3][jj]);

@@ -329,6 +329,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_f2_kernel(FwdArgs a) {
   const int total_chunks = my_tiles * nk;
   auto tile_of = [&](int q) { return (int64_t)blockIdx.x + (int64_t)(q / nk) * gridDim.x; };
   const uint32_t col_r = 0, col_l = Cp, bcols = 2 * Cp;  // column of (blade b, channel c): b * bcols + col_{r,l} + c
+  const bool wide_ok = aligned32(a.y) && (!a.res || aligned32(a.res));
   const uint32_t lane_base = (warp & 3) * 32;
 
   int q = 0, loaded = 0, dbg_n = 0;
@@ -453,6 +454,21 @@ __global__ void __launch_bounds__(kThreads, 1) tc_f2_kernel(FwdArgs a) {
           const int ch = c4 * 4 + j;
           if (ch >= C) continue;
           const size_t off = ((size_t)(row0 + r) * C + ch) * B;
+          if constexpr (B == 8) {
+            if (wide_ok) {  // one 32-byte sector per (row, channel)
+              float v[8];
+#pragma unroll
+              for (int b = 0; b < 8; ++b) v[b] = o[b][j];
+              if (a.res) {
+                float rv[8];
+                ld_global_v8(rv, a.res + off);
+#pragma unroll
+                for (int b = 0; b < 8; ++b) v[b] += rv[b];
+              }
+              st_global_v8(a.y + off, v);
+              continue;
+            }
+          }
 #pragma unroll
           for (int h = 0; h < B / 4; ++h) {
             float4 x = make_float4(o[4 * h][j], o[4 * h + 1][j], o[4 * h + 2][j], o[4 * h + 3][j]);

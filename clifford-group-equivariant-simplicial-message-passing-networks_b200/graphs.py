@@ -47,6 +47,11 @@ class GraphedEGCL:
         sample = (h.detach().clone().requires_grad_(True),
                   edge_attr.detach().clone().requires_grad_(edge_attr.requires_grad),
                   node_attr.detach().clone().requires_grad_(node_attr.requires_grad))
+        # capture runs on a side stream while the parameters' AccumulateGrad nodes may date from the default stream; the
+        # mismatch is intended here and torch's warning would repeat on every backward
+        quiet = getattr(torch.autograd.graph, "set_warn_on_accumulate_grad_stream_mismatch", None)
+        if quiet is not None:
+            quiet(False)
         self.fn = torch.cuda.make_graphed_callables(self.bound, sample)
 
     def set_graph(self, edge_index: torch.Tensor):
