@@ -56,16 +56,26 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+__device__ __forceinline__ void cp_async16(float* dst_smem, const float* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr(dst_smem)), "l"(src) : "memory");
+}
+// Stage of one warp and one tensor: [blade][8 rows][4 channels] floats = the warp's 8 rows x 4 channels of an iteration.
+// The warp fills it COOPERATIVELY with 16-byte copies (8 B copies per tensor, B / 4 per lane, a quarter of the 4-byte
+// copies a thread-private stage needs: the kernel was throttled by its memory-instruction queue); thread (row rr,
+// channel j) = lane 4 rr + j then reads word lane of every blade row.  Cross-lane: __syncwarp after cp.async.wait_group.
 template <int DIM>
-__device__ __forceinline__ void prefetch_mv_bpt(float* st, int nt, const float* t, int Cp, int64_t tile, int c4, int r, int j) {
+__device__ __forceinline__ void prefetch_mv_bpt(float* st, const float* t, int Cp, int64_t tile, int c4, int r0, int lane) {
   constexpr int B = Alg<DIM>::B;
 #pragma unroll
-  for (int b = 0; b < B; ++b) cp_async4(st + b * nt, t + bpt_off(B, Cp, tile, b, c4, r) + j);
+  for (int k = lane; k < B * 8; k += 32) {
+    const int b = k >> 3, row = k & 7;
+    cp_async16(st + (b * 8 + row) * 4, t + bpt_off(B, Cp, tile, b, c4, r0 + row));
+  }
 }
 template <int DIM>
-__device__ __forceinline__ void read_stage(float* v, const float* st, int nt) {
+__device__ __forceinline__ void read_stage(float* v, const float* st, int lane) {
 #pragma unroll
-  for (int b = 0; b < Alg<DIM>::B; ++b) v[b] = st[b * nt];
+  for (int b = 0; b < Alg<DIM>::B; ++b) v[b] = st[b * 32 + lane];
 }
 
 // CP (channel padding) is a template constant: thread count, BPT blade stride and stage strides become immediates, which
@@ -99,27 +109,30 @@ __global__ void __launch_bounds__(CP * 8, CP <= 32 ? 2 : 1) tc_b1_kernel(EwArgs 
   // iteration it of a unit: it < 8 -> phase 1 (row statistics: o, grad_y), it >= 8 -> phase 2 (adjoints: + y2, xr);
   // 8 rows of the unit per iteration
   constexpr int kIt = kTile / 16;
-  auto stage_of = [&](int s, int tensor) { return stage + ((size_t)(s * 4 + tensor) * B) * nt + tid; };
+  // warp-private stages: [stage s][tensor][blade][8 rows][4 channels]
+  float* stage_w = stage + (size_t)c4 * (2 * 4 * B * 32);
+  auto stage_of = [&](int s, int tensor) { return stage_w + (size_t)(s * 4 + tensor) * B * 32; };
   auto prefetch = [&](int64_t unit, int it, int s) {
     const int64_t tile = unit >> 1;
-    const int r = (int)(unit & 1) * (kTile / 2) + (it & (kIt - 1)) * 8 + rr;
-    prefetch_mv_bpt<DIM>(stage_of(s, 0), nt, a.o, Cp, tile, c4, r, j);
+    const int r0 = (int)(unit & 1) * (kTile / 2) + (it & (kIt - 1)) * 8, r = r0 + rr;
+    __syncwarp();  // every lane has finished reading this stage (iteration before last)
+    prefetch_mv_bpt<DIM>(stage_of(s, 0), a.o, Cp, tile, c4, r0, lane);
     if (a.gy_bpt) {
-      prefetch_mv_bpt<DIM>(stage_of(s, 1), nt, a.gy, Cp, tile, c4, r, j);
+      prefetch_mv_bpt<DIM>(stage_of(s, 1), a.gy, Cp, tile, c4, r0, lane);
     } else {
-      float* dst = stage_of(s, 1);
+      float* dst = stage_of(s, 1) + lane;  // reference layout: every thread fetches its own multivector
       if (ch_ok && tile * kTile + r < a.rows) {
         const float* src = a.gy + ((size_t)(tile * kTile + r) * C + ch) * B;
 #pragma unroll
-        for (int b = 0; b < B; ++b) cp_async4(dst + b * nt, src + b);
+        for (int b = 0; b < B; ++b) cp_async4(dst + b * 32, src + b);
       } else {
 #pragma unroll
-        for (int b = 0; b < B; ++b) dst[b * nt] = 0.f;
+        for (int b = 0; b < B; ++b) dst[b * 32] = 0.f;
       }
     }
     if (it >= kIt) {
-      prefetch_mv_bpt<DIM>(stage_of(s, 2), nt, a.y2, Cp, tile, c4, r, j);
-      prefetch_mv_bpt<DIM>(stage_of(s, 3), nt, a.xr, Cp, tile, c4, r, j);
+      prefetch_mv_bpt<DIM>(stage_of(s, 2), a.y2, Cp, tile, c4, r0, lane);
+      prefetch_mv_bpt<DIM>(stage_of(s, 3), a.xr, Cp, tile, c4, r0, lane);
     }
     cp_async_commit();
   };
@@ -139,14 +152,15 @@ __global__ void __launch_bounds__(CP * 8, CP <= 32 ? 2 : 1) tc_b1_kernel(EwArgs 
       else if (unit + gridDim.x < n_units) prefetch(unit + gridDim.x, 0, (seq + 1) & 1);
       else cp_async_commit();
       cp_async_wait<1>();
+      __syncwarp();  // the copies of all lanes of this warp have landed
       const int s = seq & 1;
       const int r = rbase + (it & (kIt - 1)) * 8 + rr;
       const bool ok = ch_ok && row0 + r < a.rows;
       if (it < kIt) {
         // ---- phase 1: row statistics of the layer norm
         float o[B], dy[B];
-        read_stage<DIM>(o, stage_of(s, 0), nt);
-        read_stage<DIM>(dy, stage_of(s, 1), nt);
+        read_stage<DIM>(o, stage_of(s, 0), lane);
+        read_stage<DIM>(dy, stage_of(s, 1), lane);
         float dot = 0.f;
 #pragma unroll
         for (int b = 0; b < B; ++b) dot = fmaf(dy[b], o[b], dot);
@@ -173,8 +187,8 @@ __global__ void __launch_bounds__(CP * 8, CP <= 32 ? 2 : 1) tc_b1_kernel(EwArgs 
       float dd[B];
       {
         float o[B];
-        read_stage<DIM>(o, stage_of(s, 0), nt);
-        read_stage<DIM>(dd, stage_of(s, 1), nt);
+        read_stage<DIM>(o, stage_of(s, 0), lane);
+        read_stage<DIM>(dd, stage_of(s, 1), lane);
         const float inv_mu = inv_mu_s[r];
         float dot = 0.f;
 #pragma unroll
@@ -190,8 +204,8 @@ __global__ void __launch_bounds__(CP * 8, CP <= 32 ? 2 : 1) tc_b1_kernel(EwArgs 
       store_mv_bpt<DIM>(a.d, dd, Cp, tile, c4, r, j);
       g_bl += dd[0];
       float y2[B], xr[B];
-      read_stage<DIM>(y2, stage_of(s, 2), nt);
-      read_stage<DIM>(xr, stage_of(s, 3), nt);
+      read_stage<DIM>(y2, stage_of(s, 2), lane);
+      read_stage<DIM>(xr, stage_of(s, 3), lane);
       float q[G], nrm[G], rinv[G], xn[B], dxn[B], dy2[B];
       norm_factors<DIM>(xr, sn, q, nrm, rinv);
 #pragma unroll
@@ -250,12 +264,14 @@ __global__ void __launch_bounds__(CP * 8, CP <= 32 ? 2 : 1) tc_b3_kernel(EwArgs 
     g_sa[g] = 0.f; g_sb[g] = 0.f;
   }
   constexpr int kIt = kTile / 16;
-  auto stage_of = [&](int s, int tensor) { return stage + ((size_t)(s * 2 + tensor) * B) * nt + tid; };
+  float* stage_w = stage + (size_t)c4 * (2 * 2 * B * 32);
+  auto stage_of = [&](int s, int tensor) { return stage_w + (size_t)(s * 2 + tensor) * B * 32; };
   auto prefetch = [&](int64_t unit, int it, int s) {
     const int64_t tile = unit >> 1;
-    const int r = (int)(unit & 1) * (kTile / 2) + it * 8 + rr;
-    prefetch_mv_bpt<DIM>(stage_of(s, 0), nt, a.y1, Cp, tile, c4, r, j);
-    prefetch_mv_bpt<DIM>(stage_of(s, 1), nt, a.dy2, Cp, tile, c4, r, j);
+    const int r0 = (int)(unit & 1) * (kTile / 2) + it * 8;
+    __syncwarp();
+    prefetch_mv_bpt<DIM>(stage_of(s, 0), a.y1, Cp, tile, c4, r0, lane);
+    prefetch_mv_bpt<DIM>(stage_of(s, 1), a.dy2, Cp, tile, c4, r0, lane);
     cp_async_commit();
   };
   const int64_t n_units = 2 * (int64_t)a.tiles;
@@ -271,12 +287,13 @@ __global__ void __launch_bounds__(CP * 8, CP <= 32 ? 2 : 1) tc_b3_kernel(EwArgs 
       else if (unit + gridDim.x < n_units) prefetch(unit + gridDim.x, 0, (seq + 1) & 1);
       else cp_async_commit();
       cp_async_wait<1>();
+      __syncwarp();
       const int s = seq & 1;
       const int r = rbase + it * 8 + rr;
       const bool ok = ch_ok && row0 + r < a.rows;
       float y1[B], dy[B], sg[G], inv[G], t[G], ds[G];
-      read_stage<DIM>(y1, stage_of(s, 0), nt);
-      read_stage<DIM>(dy, stage_of(s, 1), nt);
+      read_stage<DIM>(y1, stage_of(s, 0), lane);
+      read_stage<DIM>(dy, stage_of(s, 1), lane);
       silu_gates<DIM>(y1, sa, sb, sg, inv);
 #pragma unroll
       for (int g = 0; g < G; ++g) t[g] = 0.f;
