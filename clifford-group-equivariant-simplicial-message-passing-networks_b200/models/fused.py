@@ -584,7 +584,7 @@ def bench_dominant_kernel(layer, d, graph, hbm_peak, peak_src, iters=10):
         # this workload (profiles/r01_ncu_full_tc_kernels.txt: md17, 53 976 pairs, C = 32); other shapes report null
         ncu_traffic = {}
         if (alg.dim, E, C, cin) == (3, 53976, 32, 38):
-            ncu_traffic = {1: 153.4e6, 2: 180.6e6, 101: 373.1e6, 102: 198.0e6, 104: 135.9e6, 108: 76.3e6, 116: 171.1e6, 132: 144.1e6, 164: 18.3e6}
+            ncu_traffic = {1: 153.9e6, 2: 177.6e6, 101: 392.3e6, 102: 198.5e6, 104: 134.9e6, 108: 79.2e6, 116: 170.1e6, 132: 143.7e6, 164: 18.3e6}
         table = []
         for name, is_bwd, mask, nbytes, tflops in stages:
             desc.stage_mask = mask
