@@ -87,3 +87,23 @@ def test_simt_tile_rows_query(built_lib):
     assert 0 <= l.csmpn_block_simt_resident(3, 70, 64) < 4   # wide block: composed from unit kernels
     assert l.csmpn_block_simt_resident(3, 131, 64) == 0
     assert l.csmpn_block_simt_resident(4, 8, 8) == 0         # unsupported dimension
+
+
+def test_host_side_modules_import_without_gpu():
+    """graphs / pipeline / train_step are importable on a CPU-only box (they touch CUDA only when used)"""
+    import importlib
+
+    for name in ("csmpn_b200.graphs", "csmpn_b200.pipeline", "csmpn_b200.train_step", "csmpn_b200.models.fused"):
+        importlib.import_module(name)
+    from csmpn_b200.models import fused
+
+    assert fused.tc_min_rows() == 8192 and fused.fork_max_rows() > 1 << 30
+
+
+def test_bench_accounting_matches_survey_formulas():
+    """bench.layer_flops_bytes restates SURVEY.md 8d: 23.6 kB and 2.63 MFLOP per simplex at C=32, B=8, E/N=6"""
+    import bench
+
+    flops, nbytes = bench.layer_flops_bytes(1000, 6000, 32, 8)
+    assert abs(nbytes / 1000 - 23.6e3) / 23.6e3 < 0.02
+    assert abs(flops / 1000 - 2.63e6) / 2.63e6 < 0.02
