@@ -60,7 +60,6 @@ def _declare(lib):
         "csmpn_block_tc_supported": (c_int, [i32, i32, i32]),
         "csmpn_block_simt_resident": (c_int, [i32, i32, i32]),
         "csmpn_bpt_floats": (i64, [i32, i64, i32]),
-        "csmpn_tc_debug_buffer": (c_int, [P]),
         "csmpn_block_bwd_workspace": (i64, [i32, P]),
         "csmpn_block_bwd": (c_int, [i32, P, P, P, i64, P]),
         "csmpn_csr_sorted_indices": (c_int, [P, P, P, P, P, i64, P]),
@@ -72,10 +71,14 @@ def _declare(lib):
         # simplicial lifting
         "csmpn_lift_count": (c_int, [P, P, P, P, P, P]),
         "csmpn_lift_fill": (c_int, [P, P, P, i64, P, P, P, P, P]),
-        # tensor-core diagnostics
+    }
+    # bring-up diagnostics: only in a CSMPN_DEBUG_BUILD=1 library (csrc/csmpn_debug.h)
+    debug = {
+        "csmpn_tc_debug_buffer": (c_int, [P]),
         "csmpn_tc_probe": (c_int, [i32, i32, i32, i32, i32, P, P, P, P]),
         "csmpn_tc_probe_raw": (c_int, [P, i32, P, i32, P, P, P]),
     }
+    sigs.update({k: v for k, v in debug.items() if hasattr(lib, k)})
     for name, (res, args) in sigs.items():
         fn = getattr(lib, name)
         fn.restype = res

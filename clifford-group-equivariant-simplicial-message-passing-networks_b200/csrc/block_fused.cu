@@ -1082,10 +1082,15 @@ int csmpn_block_simt_resident(int dim, int c_in, int c) {
   return pf.tr < pb.tr ? pf.tr : pb.tr;  // rows per tile that still fit next to the resident weights
 }
 
+#ifdef CSMPN_DEBUG_TOOLS
+}  // extern "C"
+#include "csmpn_debug.h"
+extern "C" {
 int csmpn_tc_debug_buffer(int64_t* device_buffer_1024) {
   tc_set_debug_buffer((long long*)device_buffer_1024);
   return CSMPN_OK;
 }
+#endif
 
 int64_t csmpn_bpt_floats(int dim, int64_t rows, int channels) {
   if (dim < 1 || dim > 5 || rows < 0 || channels < 1) return -1;

@@ -7,12 +7,16 @@ import sys
 from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SOURCES = ["api.cu", "elementwise.cu", "linear.cu", "graph.cu", "block_fused.cu", "lift.cu", "tc_probe.cu", "tc_block_fwd.cu", "tc_block_bwd.cu"]
+SOURCES = ["api.cu", "elementwise.cu", "linear.cu", "graph.cu", "block_fused.cu", "lift.cu", "tc_block_fwd.cu", "tc_block_bwd.cu"]
+# CSMPN_DEBUG_BUILD=1: also build the bring-up diagnostics (csmpn_debug.h: single-tile tcgen05 probe, in-kernel timelines)
+DEBUG_BUILD = os.environ.get("CSMPN_DEBUG_BUILD", "0") == "1"
+if DEBUG_BUILD:
+    SOURCES.append("tc_probe.cu")
 LIB = os.path.join(HERE, "libcsmpn_b200.so")
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v",
-]
+] + (["-DCSMPN_DEBUG_TOOLS"] if DEBUG_BUILD else [])
 
 
 def _nvcc():
@@ -31,9 +35,23 @@ def _digest(paths):
     return h.hexdigest()
 
 
+def generate_tables():
+    """algebra_gen.cuh (unrolled sign/index tables of Cl(2,0), Cl(3,0), Cl(5,0)) is GENERATED from algebra/metric.py by
+    gen_algebra.py whenever it is missing or older than its generator; it is not tracked in git."""
+    out = os.path.join(HERE, "algebra_gen.cuh")
+    srcs = [os.path.join(HERE, "gen_algebra.py"), os.path.join(HERE, "..", "algebra", "metric.py")]
+    if os.path.exists(out) and all(os.path.getmtime(out) >= os.path.getmtime(s) for s in srcs):
+        return out
+    r = subprocess.run([sys.executable, os.path.join(HERE, "gen_algebra.py")], capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"gen_algebra.py failed:\n{r.stdout}\n{r.stderr}")
+    return out
+
+
 def build(force=False, verbose=False):
+    generate_tables()
     srcs = [s for s in SOURCES if os.path.exists(os.path.join(HERE, s))]
-    deps = [os.path.join(HERE, f) for f in os.listdir(HERE) if f.endswith((".cu", ".cuh"))]
+    deps = [os.path.join(HERE, f) for f in os.listdir(HERE) if f.endswith((".cu", ".cuh", ".h"))]
     deps.append(os.path.join(HERE, "..", "..", "include", "csmpn_b200.h"))
     stamp = os.path.join(HERE, "build", "stamp.txt")
     dig = _digest(deps)

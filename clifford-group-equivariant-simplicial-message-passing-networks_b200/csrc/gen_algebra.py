@@ -15,7 +15,7 @@ emits ``template<> struct Alg<DIM>`` with
 Everything is straight-line code over register arrays: the Cayley tensor's B^2 non-zeros out of B^3
 become B^2 FFMAs with the sign folded into the instruction's negate modifier.
 
-Run:  python gen_algebra.py   (writes algebra_gen.cuh next to this file; the output is committed)
+Run:  python gen_algebra.py   (writes algebra_gen.cuh next to this file; csrc/build.py runs it at build time, the output is not tracked)
 """
 import os
 import sys

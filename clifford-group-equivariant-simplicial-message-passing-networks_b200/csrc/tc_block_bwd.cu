@@ -488,6 +488,7 @@ struct DwArgs {
   long long* dbg; // optional timeline buffer (csmpn_tc_debug_buffer): CTA 0, threads 0 (issuer) and 32 (converter)
 };
 long long*& debug_buffer();  // tc_block_fwd.cu
+#ifdef CSMPN_DEBUG_TOOLS
 #define DW_STAMP(code)                                                                       \
   do {                                                                                       \
     if (TL && a.dbg && blockIdx.x == 0 && (tid == 0 || tid == 32) && dbg_n < 250) {          \
@@ -496,6 +497,9 @@ long long*& debug_buffer();  // tc_block_fwd.cu
       ++dbg_n;                                                                               \
     }                                                                                        \
   } while (0)
+#else
+#define DW_STAMP(code) do { } while (0)
+#endif
 
 // Step = (tile, blade, half of the tile's rows): 64 rows = 8 K steps.  A landing unit = (tile, blade) = two steps: the
 // blade slabs of the operand tensors ([channels/4][128 rows][4], contiguous in a BPT tensor) arrive with 2-3 large bulk
@@ -512,7 +516,7 @@ __global__ void __launch_bounds__(256, 1) tc_dw_kernel(DwArgs a) {
   constexpr int B = A::B, G = A::G;
   extern __shared__ __align__(1024) uint8_t smem[];
   const int tid = threadIdx.x, warp = uniform_warp_idx(), lane = tid & 31;
-  int dbg_n = 0;
+  [[maybe_unused]] int dbg_n = 0;
   const int ca4 = a.cpa >> 2;
   const int na4 = (a.a1 ? 2 : 1) * ca4;  // 4-channel groups of Acat
   const int nb4 = a.cpb >> 2;
@@ -882,7 +886,11 @@ int launch_bwd(const csmpn_block_desc& d, const csmpn_block_grads& g, void* work
   DwArgs da;
   memset(&da, 0, sizeof(da));
   da.dbg = debug_buffer();
+#ifdef CSMPN_DEBUG_TOOLS
   auto dw_kernel = da.dbg ? tc_dw_kernel<DIM, true> : tc_dw_kernel<DIM, false>;
+#else
+  auto dw_kernel = tc_dw_kernel<DIM, false>;
+#endif
   CSMPN_CUDA_TRY(cudaFuncSetAttribute(dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
   da.rows = d.rows; da.tiles = p.tiles;
   da.a0 = ws + p.o_d; da.a1 = ws + p.o_dxr; da.cpa = Cp; da.bsrc = d.save_y2; da.cpb = Cp; da.cpb_total = Cp; da.b_c4 = 0;

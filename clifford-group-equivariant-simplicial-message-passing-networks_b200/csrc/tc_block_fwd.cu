@@ -33,6 +33,7 @@ struct FwdArgs {
   int out_bpt, has_b1;
   long long* dbg;  // optional timeline buffer (csmpn_tc_debug_buffer): CTA 0 records clock64() stamps of threads 0 and 64
 };
+#ifdef CSMPN_DEBUG_TOOLS
 #define TSTAMP(code)                                                                         \
   do {                                                                                       \
     if (TL && a.dbg && blockIdx.x == 0 && (tid == 0 || tid == 64) && dbg_n < 250) {          \
@@ -41,6 +42,9 @@ struct FwdArgs {
       ++dbg_n;                                                                               \
     }                                                                                        \
   } while (0)
+#else
+#define TSTAMP(code) do { } while (0)
+#endif
 
 // ---- producer 2: gather / concatenate API-layout rows (all threads) ------------------------------------------------
 // Item = (row r, channel cl of the chunk, blade quad h): one float4.  gather_chunk_api only LOADS (the values stay in
@@ -275,7 +279,10 @@ __global__ void __launch_bounds__(kThreads, 1) tc_f1_kernel(FwdArgs a) {
       for (int b = 0; b < B; ++b)
         *reinterpret_cast<float4*>(a.y2 + bpt_off(B, Cp, tile, b, c4, r)) = make_float4(v[b][0], v[b][1], v[b][2], v[b][3]);
     }
-    fence_before_sync();  // the next tile's first MMA overwrites the accumulators: ordered by the next __syncthreads
+    // The next tile's first MMA overwrites these accumulators.  It is issued only after full_bar of the next chunk has
+    // collected an arrival from EVERY converter warp (conv_done), and each warp arrives after its own epilogue loads
+    // (tcgen05.wait::ld above) -- the issuer warp runs its epilogue part itself -- so the mbarrier orders the reuse.
+    fence_before_sync();
   }
   fence_before_sync();
   __syncthreads();
@@ -332,7 +339,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_f2_kernel(FwdArgs a) {
   const bool wide_ok = aligned32(a.y) && (!a.res || aligned32(a.res));
   const uint32_t lane_base = (warp & 3) * 32;
 
-  int q = 0, loaded = 0, dbg_n = 0;
+  int q = 0, loaded = 0;
+  [[maybe_unused]] int dbg_n = 0;
   TSTAMP(1);
   if (warp == 0) {
     for (; loaded < kRing - 1 && loaded < total_chunks; ++loaded) issue_chunk_load<B>(p, loaded, a.y2, Cp, tile_of(loaded), loaded % nk);
@@ -554,10 +562,13 @@ int launch_fwd(const csmpn_block_desc& d, cudaStream_t stream) {
   }
   if (mask & 1) CSMPN_LAUNCH_CHECK("tc_f1_kernel");
   if (mask & 2) {
+#ifdef CSMPN_DEBUG_TOOLS
     if (a.dbg) {
       CSMPN_CUDA_TRY(cudaFuncSetAttribute(tc_f2_kernel<DIM, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s2));
       tc_f2_kernel<DIM, true><<<grid, kThreads, s2, stream>>>(a);
-    } else {
+    } else
+#endif
+    {
       CSMPN_CUDA_TRY(cudaFuncSetAttribute(tc_f2_kernel<DIM, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s2));
       tc_f2_kernel<DIM, false><<<grid, kThreads, s2, stream>>>(a);
     }

@@ -3,6 +3,7 @@
 // accumulator lane by lane, so a test can check operand majors, LBO/SBO roles, the M=64 lane mapping and the accuracy
 // of the error-compensated split.
 #include "tc_common.cuh"
+#include "csmpn_debug.h"
 
 namespace csmpn {
 using namespace tc;

@@ -214,9 +214,6 @@ int csmpn_block_tc_supported(int dim, int c_in, int c);
  * backward), 0 if it would stage them per GEMM; with fewer than 8 rows per tile or staged weights the unit kernels
  * (csmpn_mvlinear_*, csmpn_mvsilu_*, csmpn_wgp_*, ...) composed by the host are the faster path for that shape */
 int csmpn_block_simt_resident(int dim, int c_in, int c);
-/* Diagnostics: when set to a device buffer of 1024 int64 (NULL to disable), the second forward kernel of engine 1 records
- * (phase code, clock64) pairs of two threads of CTA 0: the per-tile timeline used to tune the pipeline (tools/tc_timeline.py). */
-int csmpn_tc_debug_buffer(int64_t* device_buffer_1024);
 /* number of floats of a BPT tensor with `rows` rows and `channels` channels (padded to a multiple of 16) */
 int64_t csmpn_bpt_floats(int dim, int64_t rows, int channels);
 /* workspace for csmpn_block_bwd (device bytes; zero-initialised by the call itself) */
@@ -290,18 +287,6 @@ int csmpn_lift_count(const csmpn_lift_desc* desc, int32_t* counts, int64_t* node
  * order, zero padded), node_types [N] int64 (simplex dimension), batch [N] int64 (complex id).                     */
 int csmpn_lift_fill(const csmpn_lift_desc* desc, const int64_t* node_ptr, const int64_t* pair_ptr, int64_t n_pairs_total,
                     int64_t* edge_index, float* x_ind, int64_t* node_types, int64_t* batch, csmpn_stream_t stream);
-
-/* ---- tensor-core diagnostics ------------------------------------------------------------------------------------
- * Single-tile tcgen05 probe (csrc/tc_probe.cu): D = A x B on the TF32 tensor pipe from the shared-memory "plane"
- * operand layout every tensor-core kernel of this library uses; dumps the [128 lanes, N] TMEM accumulator.
- * mode 0: A [128,K], B [N,K] (both K-major); mode 1: A [128,K], B [K,N] (B MN-major); mode 2: A [K,M], B [K,N] (both
- * MN-major, M in {64,128}).  flags: 1 / 2 swap LBO and SBO of A / B (must fail), 4 = hi/lo split with three MMAs. */
-int csmpn_tc_probe(int mode, int M, int N, int K, int flags, const float* A, const float* B, float* dump,
-                   csmpn_stream_t stream);
-/* Raw variant: byte-exact shared-memory images of both operands and explicit descriptor fields (prm16: M, N, a_mn, b_mn,
- * a_lbo, a_sbo, a_layout, b_lbo, b_sbo, b_layout, ksteps, a_kinc, b_kinc, a_off, b_off, 0), for layout exploration. */
-int csmpn_tc_probe_raw(const float* a_img, int a_words, const float* b_img, int b_words, const uint32_t* prm16,
-                       float* dump, csmpn_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -15,7 +15,7 @@ Contents
 
 Pinning status: the reference ships no tests and no golden vectors.  layers_ref.py is
 pinned against outputs of the reference's own code run in the build container (tests/golden/*.pt, generated
-by tests/golden/make_golden.py; re-checked live by tests/test_oracle_vs_reference.py when /root/reference is
+by tests/golden/make_golden.py; re-checked live by tests/test_oracle_golden.py when /root/reference is
 mounted).  lift_ref.py is pinned the same way for everything except gudhi's traversal orders (gudhi is not
 installable here): for those parts parity is UNPINNED against real gudhi and pinned only against the
 documented SimplexTree semantics; motion's ManualTransform is literal and fully pinned.

@@ -14,7 +14,14 @@ import types
 
 import torch
 
-REFERENCE_ROOT = os.environ.get("CSMPN_REFERENCE_ROOT", "/root/reference")
+def _default_root() -> str:
+    """/root/reference in the build container; on the GPU box the verbatim copy oracle/make_ref.py left in oracle/_ref"""
+    if os.path.isdir("/root/reference/csmpn"):
+        return "/root/reference"
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+
+
+REFERENCE_ROOT = os.environ.get("CSMPN_REFERENCE_ROOT") or _default_root()
 
 
 def reference_available() -> bool:

@@ -113,3 +113,47 @@ def test_graphed_train_step_equals_eager(gold):
         # Adam divides by sqrt(v): fp32 run-to-run noise (1e-7, torch's atomic index_add in the pooling) of near-zero
         # gradients is amplified to ~1e-5 of a parameter after three steps, in eager mode as well
         assert_close(b, a, 2e-4, "parameters after 3 steps")
+
+
+@pytest.mark.gpu
+def test_md17_model_at_benched_size_matches_reference():
+    """The md17 model at the size `bench.py`'s train leg runs (100 complexes: ~8.6 k simplices, ~52 k pairs, so the layers'
+    per-pair blocks run on the tensor-core engine with 3 tiles per persistent CTA) against the UNMODIFIED reference
+    model's loss and parameter gradients (tests/golden/md17_bench.pt, made by tests/golden/make_golden_md17_bench.py).
+    The batch is regenerated from the seed and lifted on the GPU; checksums tie it to the one the reference saw."""
+    import hashlib
+    import os
+    import sys
+
+    from conftest import ROOT
+    from csmpn_b200 import _lib
+    from csmpn_b200.data.modules.simplicial_data import SimplicialTransform
+
+    if ROOT not in sys.path:
+        sys.path.insert(0, ROOT)
+    import bench
+
+    dev = torch.device("cuda:0")
+    fx = load_golden("md17_bench.pt")
+    graphs = bench.make_md17_graphs(fx["n_complexes"], fx["seed"], dev)
+    batch = SimplicialTransform(dim=2, dis=2.5, label="md17", molecule_type="aspirin").lift(graphs, device=dev)
+    sha = lambda t: hashlib.sha256(t.contiguous().cpu().numpy().tobytes()).hexdigest()
+    assert sha(batch.edge_index) == fx["edge_index_sha256"] and sha(batch.x_ind) == fx["x_ind_sha256"]
+    assert int(batch.edge_index.shape[1]) == fx["n_pairs"] >= 8192
+    m = model_class("md17")().to(dev)
+    missing, unexpected = m.load_state_dict(fx["state_dict"], strict=False)
+    assert not unexpected and all("algebra" in k for k in missing), (missing, unexpected)
+    n0 = _lib.lib().csmpn_launch_count()
+    loss, out = m(batch, 0, "train")
+    named = list(m.named_parameters())
+    grads = torch.autograd.grad(loss, [p for _, p in named], allow_unused=True)
+    assert _lib.lib().csmpn_launch_count() - n0 > 150
+    assert_close(loss, fx["loss"], FWD_TOL, "md17@100 loss")
+    for k, v in fx["out"].items():
+        assert_close(out[k], v, FWD_TOL, f"md17@100 out[{k}]")
+    for (n, _), gr in zip(named, grads):
+        ref = fx["grads"][n]
+        if ref is None:
+            assert gr is None or float(gr.abs().max()) == 0.0, n
+            continue
+        assert_close(gr, ref, GRAD_TOL, f"md17@100 grad {n}")

@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""Per-step timeline of the weight-gradient kernel (tc_dw_kernel, dWL/dWR launch) of the first edge block of the md17
+"""[needs a diagnostics build: CSMPN_DEBUG_BUILD=1 python -c "import __graft_entry__ as g; g.build()"]
+Per-step timeline of the weight-gradient kernel (tc_dw_kernel, dWL/dWR launch) of the first edge block of the md17
 workload: clock64 stamps of the issuer thread and of one converter thread of CTA 0 (csmpn_tc_debug_buffer)."""
 import collections, ctypes, os, sys
 import torch

@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""Layout exploration with csmpn_tc_probe_raw: build shared-memory images for a hypothesis (layout function + descriptor
+"""[needs a diagnostics build: CSMPN_DEBUG_BUILD=1 python -c "import __graft_entry__ as g; g.build()"]
+Layout exploration with csmpn_tc_probe_raw: build shared-memory images for a hypothesis (layout function + descriptor
 fields), run one tile on the tensor pipe, compare with torch.  One subprocess per experiment.  GPU box only."""
 import ctypes
 import json

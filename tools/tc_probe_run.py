@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""Run the tcgen05 probe (csmpn_tc_probe) over its modes and print the error of every variant against torch fp64.
+"""[needs a diagnostics build: CSMPN_DEBUG_BUILD=1 python -c "import __graft_entry__ as g; g.build()"]
+Run the tcgen05 probe (csmpn_tc_probe) over its modes and print the error of every variant against torch fp64.
 Each variant runs in its own process so a faulting descriptor cannot poison the others.  GPU box only."""
 import os
 import subprocess

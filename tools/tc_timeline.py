@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""Per-phase timeline of the second forward kernel (tc_f2) of the tensor-core engine: clock64 stamps of two threads of
+"""[needs a diagnostics build: CSMPN_DEBUG_BUILD=1 python -c "import __graft_entry__ as g; g.build()"]
+Per-phase timeline of the second forward kernel (tc_f2) of the tensor-core engine: clock64 stamps of two threads of
 CTA 0 (csmpn_tc_debug_buffer).  Prints cycles spent between consecutive stamps, aggregated by (from, to) phase code."""
 import collections
 import os
