@@ -261,7 +261,12 @@ __device__ __forceinline__ int input_pieces(RowPiece* pc, float* tile, int s3, f
   } else {
     pc[n++] = RowPiece{tile, s3, 0, d.p0, d.c0, d.dst};
     pc[n++] = RowPiece{tmp, s1, 0, d.p0, d.c0, d.src};
-    if (d.c1) pc[n++] = RowPiece{tile, s3, d.c0 * B, d.p1, d.c1, d.eid};
+    if (d.c1 && d.pair_attr) {  // extra channels = (table[src] | table[dst]), table = p1 [n_nodes, c1/2, B]
+      pc[n++] = RowPiece{tile, s3, d.c0 * B, d.p1, d.c1 / 2, d.src};
+      pc[n++] = RowPiece{tile, s3, (d.c0 + d.c1 / 2) * B, d.p1, d.c1 / 2, d.dst};
+    } else if (d.c1) {
+      pc[n++] = RowPiece{tile, s3, d.c0 * B, d.p1, d.c1, d.eid};
+    }
   }
   return n;
 }
@@ -457,9 +462,9 @@ __global__ void __launch_bounds__(256, 1) block_fwd_kernel(csmpn_block_desc d, F
     fence_proxy_async();
     g.sync();  // previous tile's generic accesses are done
     {
-      RowPiece pc[4];
+      RowPiece pc[5];
       const int np = input_pieces<DIM>(pc, tA, p.s3, tB, p.s1, d);
-      tma_issue_pieces<DIM, 4>(g, pc, np, row0, valid, bar);
+      tma_issue_pieces<DIM, 5>(g, pc, np, row0, valid, bar);
     }
     mbar_wait(bar, phase);
     phase ^= 1;
@@ -838,10 +843,10 @@ __global__ void __launch_bounds__(256, 1) block_bwd_kernel(csmpn_block_desc d, c
     fence_proxy_async();
     g.sync();  // generic accesses to t1, t2, t3 are done
     {
-      RowPiece pc[4];
+      RowPiece pc[5];
       pc[0] = RowPiece{t2, p.s2, 0, d.save_y1, C, nullptr};
       const int np = 1 + input_pieces<DIM>(pc + 1, t3, p.s3, t1, p.s1, d);
-      tma_issue_pieces<DIM, 4>(g, pc, np, row0, valid, bar + 1);
+      tma_issue_pieces<DIM, 5>(g, pc, np, row0, valid, bar + 1);
     }
     mbar_wait(bar + 1, phase);
     phase ^= 1;
@@ -1040,7 +1045,8 @@ inline int check_desc(int dim, const csmpn_block_desc* d) {
   if (d->rows < 0 || d->c <= 0 || d->c0 <= 0 || d->c1 < 0 || d->c2 < 0) return CSMPN_ERR_BAD_ARG;
   if (d->mode != 0 && d->mode != 1) return CSMPN_ERR_BAD_ARG;
   if (!d->p0 || (d->c1 > 0 && !d->p1) || (d->c2 > 0 && !d->p2)) return CSMPN_ERR_BAD_ARG;
-  if (d->mode == 1 && (!d->src || !d->dst || (d->c1 > 0 && !d->eid) || d->c2 != 0)) return CSMPN_ERR_BAD_ARG;
+  if (d->mode == 1 && (!d->src || !d->dst || (d->c1 > 0 && !d->eid && !d->pair_attr) || d->c2 != 0)) return CSMPN_ERR_BAD_ARG;
+  if (d->pair_attr && (d->mode != 1 || (d->c1 & 1))) return CSMPN_ERR_BAD_ARG;
   if (!d->w1 || !d->sa || !d->sb || !d->wr || !d->na || !d->wl || !d->bl || !d->wp || !d->la) return CSMPN_ERR_BAD_ARG;
   if (d->has_b1 && !d->b1) return CSMPN_ERR_BAD_ARG;
   return CSMPN_OK;

@@ -309,6 +309,29 @@ __global__ void scatter_diff_sorted_kernel(const float* __restrict__ g, int64_t 
   }
 }
 
+// out[n, :] = sum_{pairs p with dst = n} g[p, col_dst : col_dst + width] + sum_{pairs with src = n} g[p, col_src : ...]
+// (gradient of a per-simplex table that entered every pair as  table[src] | table[dst]); fixed order, no atomics
+__global__ void scatter_pair_sorted_kernel(const float* __restrict__ g, int64_t ld, int64_t col_src, int64_t col_dst,
+                                           const int32_t* __restrict__ rp_dst, const int32_t* __restrict__ rp_src,
+                                           const int32_t* __restrict__ pm_src, const int32_t* __restrict__ rank,
+                                           float* __restrict__ out, int64_t n_nodes, int64_t width) {
+  const int64_t vpr = width / 4, total = n_nodes * vpr;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t n = idx / vpr, v = idx - n * vpr;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int32_t p = rp_dst[n]; p < rp_dst[n + 1]; ++p) {
+      const float4 t = *(reinterpret_cast<const float4*>(g + (int64_t)p * ld + col_dst) + v);
+      acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+    }
+    for (int32_t q = rp_src[n]; q < rp_src[n + 1]; ++q) {
+      const int64_t p = rank[pm_src[q]];
+      const float4 t = *(reinterpret_cast<const float4*>(g + p * ld + col_src) + v);
+      acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+    }
+    *(reinterpret_cast<float4*>(out + n * width) + v) = acc;
+  }
+}
+
 __global__ void scatter_rows_kernel(const float* __restrict__ g, int64_t ld, int64_t col0, const int32_t* __restrict__ eid,
                                     float* __restrict__ out, int64_t n_rows, int64_t width) {
   const int64_t vpr = width / 4, total = n_rows * vpr;
@@ -480,6 +503,20 @@ int csmpn_scatter_rows(const float* g, int64_t ld, int64_t col0, const int32_t* 
   cudaStream_t s = (cudaStream_t)stream;
   scatter_rows_kernel<<<grid_for(n_rows * width / 4, 256), 256, 0, s>>>(g, ld, col0, eid, out, n_rows, width);
   CSMPN_LAUNCH_CHECK("scatter_rows");
+  return CSMPN_OK;
+}
+
+int csmpn_scatter_pair_sorted(const float* g, int64_t ld, int64_t col_src, int64_t col_dst, const int32_t* rowptr_dst,
+                              const int32_t* rowptr_src, const int32_t* perm_src, const int32_t* rank, float* out,
+                              int64_t n_nodes, int64_t width, csmpn_stream_t stream) {
+  if (n_nodes < 0 || width <= 0 || width % 4 || ld % 4 || col_src % 4 || col_dst % 4 || col_src < 0 || col_dst < 0)
+    return CSMPN_ERR_BAD_ARG;
+  if (n_nodes == 0) return CSMPN_OK;
+  if (!g || !rowptr_dst || !rowptr_src || !out) return CSMPN_ERR_BAD_ARG;
+  cudaStream_t s = (cudaStream_t)stream;
+  scatter_pair_sorted_kernel<<<grid_for(n_nodes * width / 4, 256), 256, 0, s>>>(g, ld, col_src, col_dst, rowptr_dst, rowptr_src,
+                                                                                  perm_src, rank, out, n_nodes, width);
+  CSMPN_LAUNCH_CHECK("scatter_pair_sorted");
   return CSMPN_OK;
 }
 

@@ -23,7 +23,7 @@ struct FwdArgs {
   int C, Cp;      // block width, padded to a multiple of 16
   int cin, kin8;  // input channels of the first linear, padded to a multiple of 8
   int in_bpt, in_cp;
-  int mode, c0, c1, c2;
+  int mode, c0, c1, c2, pair_attr;
   const float *p0, *p1, *p2;
   const int32_t *src, *dst, *eid;
   const float *w1, *b1, *sa, *sb, *wr, *na, *wl, *bl, *wp, *la;
@@ -84,6 +84,10 @@ __device__ __forceinline__ void gather_chunk_api(const FwdArgs& a, int64_t row0,
           const float4 x = __ldg(reinterpret_cast<const float4*>(a.p0 + (d * a.c0 + c) * B + 4 * h));
           const float4 z = __ldg(reinterpret_cast<const float4*>(a.p0 + (s * a.c0 + c) * B + 4 * h));
           v[i] = make_float4(x.x - z.x, x.y - z.y, x.z - z.z, x.w - z.w);
+        } else if (a.pair_attr) {  // (table[src] | table[dst]), table = p1 [n_nodes, c1/2, B]
+          const int k = c - a.c0, half = a.c1 >> 1;
+          const int64_t n = k < half ? a.src[R] : a.dst[R];
+          v[i] = __ldg(reinterpret_cast<const float4*>(a.p1 + (n * half + (k < half ? k : k - half)) * B + 4 * h));
         } else {
           const int64_t e = a.eid[R];
           v[i] = __ldg(reinterpret_cast<const float4*>(a.p1 + (e * a.c1 + (c - a.c0)) * B + 4 * h));
@@ -537,7 +541,7 @@ int launch_fwd(const csmpn_block_desc& d, cudaStream_t stream) {
   a.kin8 = round_up(a.cin, 8);
   a.in_bpt = d.in_bpt;
   a.in_cp = round_up(a.cin, 16);
-  a.mode = d.mode; a.c0 = d.c0; a.c1 = d.c1; a.c2 = d.c2;
+  a.mode = d.mode; a.c0 = d.c0; a.c1 = d.c1; a.c2 = d.c2; a.pair_attr = d.pair_attr;
   a.p0 = d.p0; a.p1 = d.p1; a.p2 = d.p2;
   a.src = d.src; a.dst = d.dst; a.eid = d.eid;
   a.w1 = d.w1; a.b1 = d.b1; a.sa = d.sa; a.sb = d.sb; a.wr = d.wr; a.na = d.na; a.wl = d.wl; a.bl = d.bl; a.wp = d.wp; a.la = d.la;

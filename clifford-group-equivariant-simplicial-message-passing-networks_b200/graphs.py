@@ -29,13 +29,25 @@ class _BoundLayer(nn.Module):
         return self.layer(h, self._graph, edge_attr, node_attr)
 
 
+class _BoundPairedLayer(_BoundLayer):
+    """the same with edge_attr = PairedNodeAttr(node_attr): (node_attr[src] | node_attr[dst]) gathered by the kernel"""
+
+    def forward(self, h, node_attr):
+        from .models.cegnn_utils import PairedNodeAttr
+
+        return self.layer(h, self._graph, PairedNodeAttr(node_attr), node_attr)
+
+
 class GraphedEGCL:
     """layer(h, graph, edge_attr, node_attr) for a FIXED ``graph`` (CSRGraph or edge_index) and fixed shapes, replayed
     from CUDA graphs.  ``h`` may require grad; ``edge_attr`` / ``node_attr`` follow the sample tensors' requires_grad."""
 
-    def __init__(self, layer: nn.Module, graph, h: torch.Tensor, edge_attr: torch.Tensor, node_attr: torch.Tensor):
+    def __init__(self, layer: nn.Module, graph, h: torch.Tensor, edge_attr, node_attr: torch.Tensor):
+        from .models.cegnn_utils import PairedNodeAttr
+
         if not h.is_cuda:
             raise ValueError("GraphedEGCL needs CUDA tensors")
+        self.paired = isinstance(edge_attr, PairedNodeAttr)
         csr = get_csr(graph, h.shape[0])
         if not isinstance(graph, CSRGraph):  # own the structure: set_graph() rewrites it in place
             csr = CSRGraph(graph.clone(), h.shape[0])
@@ -43,10 +55,15 @@ class GraphedEGCL:
         with torch.no_grad():
             layer(h, csr, edge_attr, node_attr)
         torch.cuda.synchronize(h.device)
-        self.bound = _BoundLayer(layer, csr)
-        sample = (h.detach().clone().requires_grad_(True),
-                  edge_attr.detach().clone().requires_grad_(edge_attr.requires_grad),
-                  node_attr.detach().clone().requires_grad_(node_attr.requires_grad))
+        if self.paired:
+            self.bound = _BoundPairedLayer(layer, csr)
+            sample = (h.detach().clone().requires_grad_(True),
+                      node_attr.detach().clone().requires_grad_(node_attr.requires_grad))
+        else:
+            self.bound = _BoundLayer(layer, csr)
+            sample = (h.detach().clone().requires_grad_(True),
+                      edge_attr.detach().clone().requires_grad_(edge_attr.requires_grad),
+                      node_attr.detach().clone().requires_grad_(node_attr.requires_grad))
         # capture runs on a side stream while the parameters' AccumulateGrad nodes may date from the default stream; the
         # mismatch is intended here and torch's warning would repeat on every backward
         quiet = getattr(torch.autograd.graph, "set_warn_on_accumulate_grad_stream_mismatch", None)
@@ -60,4 +77,6 @@ class GraphedEGCL:
         self.bound._graph.rebuild_(edge_index)
 
     def __call__(self, h, edge_attr, node_attr):
+        if self.paired:  # edge_attr (a PairedNodeAttr or None) is implied by node_attr
+            return self.fn(h, node_attr)
         return self.fn(h, edge_attr, node_attr)

@@ -106,9 +106,11 @@ class SharedSimplicialBase(nn.Module):
         # matmul instead of an index_put with ~N/T duplicates per row (0.9 ms of serialised atomics per step at N = 8.6 k)
         onehot = (graph.node_types.unsqueeze(1) == torch.arange(table.shape[0], device=table.device)).to(table.dtype)
         node_attr[..., 0] = onehot @ table
-        ei = graph.edge_index
-        edge_attr = torch.cat((node_attr[ei[0]], node_attr[ei[1]]), dim=1)
-        return node_attr, edge_attr
+        # edge_attr = cat(node_attr[ei[0]], node_attr[ei[1]]) (md17_cssmpnn.py:131) stays symbolic: the message kernels
+        # gather the two rows of the [N, T, B] table themselves, the [E, 2T, B] tensor is never built
+        from .cegnn_utils import PairedNodeAttr
+
+        return node_attr, PairedNodeAttr(node_attr)
 
     def vertex_features(self, graph, verts):
         """[rows, k] global vertex ids -> [rows, k * F, B] multivector features (vertex-major channels)."""

@@ -251,6 +251,31 @@ class CEMLP(nn.Module):
         return x
 
 
+class PairedNodeAttr:
+    """``edge_attr = torch.cat((node_attr[edge_index[0]], node_attr[edge_index[1]]), dim=1)`` kept SYMBOLIC.
+
+    That is how all four reference models build ``edge_attr`` (md17_cssmpnn.py:131, motion :134, nba :122,
+    hulls :138): the [E, 2T, B] tensor only repeats rows of the [N, T, B] per-simplex attributes.  Passing
+    ``PairedNodeAttr(node_attr)`` as ``edge_attr`` to ``EGCL.forward`` gives the same values and the same gradient
+    w.r.t. ``node_attr``, but the message kernel gathers ``node_attr[src] | node_attr[dst]`` itself
+    (csmpn_block_desc.pair_attr) and the gradient is one fixed-order segment sum (csmpn_scatter_pair_sorted):
+    nothing of size E x 2T x B is built, copied or stored.  A plain tensor ``edge_attr`` keeps working as in the
+    reference."""
+
+    def __init__(self, node_attr: torch.Tensor):
+        if node_attr.dim() != 3:
+            raise ValueError("PairedNodeAttr: node_attr must be [N, T, 2**dim]")
+        self.node_attr = node_attr
+
+    @property
+    def requires_grad(self):
+        return self.node_attr.requires_grad
+
+    def materialize(self, edge_index):
+        ei = getattr(edge_index, "edge_index", edge_index)
+        return torch.cat((self.node_attr[ei[0]], self.node_attr[ei[1]]), dim=1)
+
+
 class EGCL(nn.Module):
     """Shared simplicial message layer (cegnn_utils.py:216-284).  The reference subclasses PyG's
     ``MessagePassing``; here ``propagate`` is the CSR path of csrc/graph.cu (flow source_to_target:
@@ -310,6 +335,8 @@ class EGCL(nn.Module):
 
         if fused.enabled(self.algebra):
             return fused.egcl_forward(self, h, edge_index, edge_attr, node_attr)
+        if isinstance(edge_attr, PairedNodeAttr):
+            edge_attr = edge_attr.materialize(edge_index)
         h = self.algebra.flatten(h)
         x = self.propagate(edge_index, h=h, edge_attr=edge_attr, node_attr=node_attr)
         return self.algebra.split(x)

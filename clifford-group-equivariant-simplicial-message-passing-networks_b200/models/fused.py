@@ -34,6 +34,7 @@ class BlockDesc(ctypes.Structure):
         ("y", c_void_p), ("res", c_void_p), ("save_y1", c_void_p), ("save_xr", c_void_p), ("save_o", c_void_p),
         ("engine", c_int32), ("in_bpt", c_int32), ("out_bpt", c_int32), ("stage_mask", c_int32),
         ("save_y2", c_void_p), ("save_x0", c_void_p),
+        ("pair_attr", c_int32),
     ]
 
 
@@ -147,9 +148,10 @@ def sorted_graph(g: ops.CSRGraph) -> SortedGraph:
     return sg
 
 
-def _fill_desc(dim, mode, srcs, chans, rows, c, params, sgraph, y, res, saves):
+def _fill_desc(dim, mode, srcs, chans, rows, c, params, sgraph, y, res, saves, pair_attr=False):
     w1, b1, sa, sb, wr, na, wl, bl, wp, la = params
     d = BlockDesc()
+    d.pair_attr = int(bool(pair_attr))
     d.mode, d.c0, d.c1, d.c2, d.c = mode, chans[0], chans[1], chans[2], c
     d.has_b1 = int(b1 is not None)
     d.rows = rows
@@ -178,6 +180,9 @@ class FusedBlockFn(torch.autograd.Function):
         require_cuda(*srcs, what="fused block")
         B = 1 << dim
         chans = [0 if t is None else t.shape[1] for t in srcs]
+        pair = bool(cfg.get("pair_attr"))
+        if pair:
+            chans[1] *= 2  # p1 is the per-simplex table: every pair sees table[src] | table[dst]
         c = w1.shape[0]
         if sum(chans) != w1.shape[1]:
             raise ValueError(f"fused block: input channels {chans} do not match weight {tuple(w1.shape)}")
@@ -188,18 +193,18 @@ class FusedBlockFn(torch.autograd.Function):
         need_grad = cfg["need_grad"]
         saves = tuple(torch.empty((rows, c, B), dtype=torch.float32, device=dev) for _ in range(3)) if need_grad else None
         resc = None if res is None else f32c(res)
-        d = _fill_desc(dim, mode, srcs, chans, rows, c, params, sgraph, y, resc, saves)
+        d = _fill_desc(dim, mode, srcs, chans, rows, c, params, sgraph, y, resc, saves, pair)
         check(lib().csmpn_block_fwd(dim, ctypes.byref(d), stream_ptr(dev)), "block_fwd")
         if need_grad:
             ctx.save_for_backward(*[t for t in srcs if t is not None], *[t for t in params if t is not None], *saves)
             ctx.meta = (dim, mode, sgraph, chans, c, rows, [t is not None for t in srcs], [t is not None for t in params],
                         res is not None, [None if t is None else t.shape for t in (w1, b1, sa, sb, wr, na, wl, bl, wp, la)],
-                        [None if t is None else t.shape for t in (p0, p1, p2)])
+                        [None if t is None else t.shape for t in (p0, p1, p2)], pair)
         return y
 
     @staticmethod
     def backward(ctx, gy):
-        dim, mode, sgraph, chans, c, rows, src_mask, par_mask, has_res, pshapes, sshapes = ctx.meta
+        dim, mode, sgraph, chans, c, rows, src_mask, par_mask, has_res, pshapes, sshapes, pair = ctx.meta
         saved = list(ctx.saved_tensors)
         srcs = [saved.pop(0) if m else None for m in src_mask]
         params = [saved.pop(0) if m else None for m in par_mask]
@@ -209,7 +214,7 @@ class FusedBlockFn(torch.autograd.Function):
         B = 1 << dim
         cin = sum(chans)
         y_dummy = gy  # desc.y is not written by the backward
-        d = _fill_desc(dim, mode, srcs, chans, rows, c, params, sgraph, y_dummy, None, saves)
+        d = _fill_desc(dim, mode, srcs, chans, rows, c, params, sgraph, y_dummy, None, saves, pair)
         gx = torch.empty((rows, cin, B), dtype=torch.float32, device=dev)
         pg = [None if t is None else torch.empty_like(t) for t in params]
         g = BlockGrads()
@@ -239,14 +244,28 @@ class FusedBlockFn(torch.autograd.Function):
                   "scatter_diff_sorted")
             gsrc[0] = gh
             if srcs[1] is not None and ctx.needs_input_grad[2]:
-                ge = torch.empty((rows, chans[1], B), dtype=torch.float32, device=dev)
-                check(lib().csmpn_scatter_rows(ptr(gx), cin * B, chans[0] * B, ptr(csr.perm_dst), ptr(ge), rows, chans[1] * B,
-                                               stream_ptr(dev)), "scatter_rows")
-                gsrc[1] = ge
+                gsrc[1] = _extra_channel_grad(gx, cin, chans, B, sgraph, srcs[1], rows, pair, dev)
         gsrc = [None if t is None else t.reshape(s) for t, s in zip(gsrc, sshapes)]
         gres = gy if has_res else None
         pgr = [None if t is None else t.reshape(s) for t, s in zip(pg, pshapes)]
         return (None, gsrc[0], gsrc[1], gsrc[2], gres, *pgr)
+
+
+def _extra_channel_grad(gx, cin, chans, B, sgraph, p1, rows, pair, dev):
+    """gradient of the gathered extra channels of a mode-1 block: per pair in the original pair order (edge_attr), or --
+    pair_attr -- summed onto the per-simplex table that entered every pair as table[src] | table[dst]"""
+    csr = sgraph.csr
+    if pair:
+        half = chans[1] // 2
+        gt = torch.empty((p1.shape[0], half, B), dtype=torch.float32, device=dev)
+        check(lib().csmpn_scatter_pair_sorted(ptr(gx), cin * B, chans[0] * B, (chans[0] + half) * B, ptr(csr.rowptr_dst),
+                                              ptr(csr.rowptr_src), ptr(csr.perm_src), ptr(sgraph.rank), ptr(gt), p1.shape[0],
+                                              half * B, stream_ptr(dev)), "scatter_pair_sorted")
+        return gt
+    ge = torch.empty((rows, chans[1], B), dtype=torch.float32, device=dev)
+    check(lib().csmpn_scatter_rows(ptr(gx), cin * B, chans[0] * B, ptr(csr.perm_dst), ptr(ge), rows, chans[1] * B,
+                                   stream_ptr(dev)), "scatter_rows")
+    return ge
 
 
 class TcBlockFn(torch.autograd.Function):
@@ -265,6 +284,9 @@ class TcBlockFn(torch.autograd.Function):
         require_cuda(*srcs, what="tensor-core block")
         B = 1 << dim
         chans = [cfg["c_in"], 0, 0] if in_bpt else [0 if t is None else t.shape[1] for t in srcs]
+        pair = bool(cfg.get("pair_attr")) and not in_bpt
+        if pair:
+            chans[1] *= 2  # p1 is the per-simplex table: every pair sees table[src] | table[dst]
         c = w1.shape[0]
         cin = sum(chans)
         if cin != w1.shape[1]:
@@ -278,7 +300,7 @@ class TcBlockFn(torch.autograd.Function):
         saves = tuple(bpt_empty(dim, rows, c, dev) for _ in range(3)) if need_grad else None
         x0 = bpt_empty(dim, rows, cin, dev) if (need_grad and not in_bpt) else None
         resc = None if res is None else f32c(res)
-        d = _fill_desc(dim, mode, srcs, chans, rows, c, params, sgraph, y, resc, saves)
+        d = _fill_desc(dim, mode, srcs, chans, rows, c, params, sgraph, y, resc, saves, pair)
         d.engine, d.in_bpt, d.out_bpt = 1, int(in_bpt), int(out_bpt)
         d.save_y2 = y2.data_ptr()
         d.save_x0 = None if x0 is None else x0.data_ptr()
@@ -288,7 +310,7 @@ class TcBlockFn(torch.autograd.Function):
                                   *([] if x0 is None else [x0]))
             ctx.meta = (dim, mode, sgraph, chans, c, rows, [t is not None for t in srcs], [t is not None for t in params],
                         res is not None, [None if t is None else t.shape for t in (w1, b1, sa, sb, wr, na, wl, bl, wp, la)],
-                        [None if t is None else t.shape for t in (p0, p1, p2)], in_bpt, out_bpt, x0 is not None)
+                        [None if t is None else t.shape for t in (p0, p1, p2)], in_bpt, out_bpt, x0 is not None, pair)
         return y
 
     @staticmethod
@@ -297,7 +319,7 @@ class TcBlockFn(torch.autograd.Function):
 
 
 def _tc_block_backward(ctx, gy):
-    (dim, mode, sgraph, chans, c, rows, src_mask, par_mask, has_res, pshapes, sshapes, in_bpt, out_bpt, has_x0) = ctx.meta
+    (dim, mode, sgraph, chans, c, rows, src_mask, par_mask, has_res, pshapes, sshapes, in_bpt, out_bpt, has_x0, pair) = ctx.meta
     saved = list(ctx.saved_tensors)
     srcs = [saved.pop(0) if m else None for m in src_mask]
     params = [saved.pop(0) if m else None for m in par_mask]
@@ -307,7 +329,7 @@ def _tc_block_backward(ctx, gy):
     dev = gy.device
     B = 1 << dim
     cin = sum(chans)
-    d = _fill_desc(dim, mode, srcs, chans, rows, c, params, sgraph, gy, None, (y1, xr, o))
+    d = _fill_desc(dim, mode, srcs, chans, rows, c, params, sgraph, gy, None, (y1, xr, o), pair)
     d.engine, d.in_bpt, d.out_bpt = 1, int(in_bpt), int(out_bpt)
     d.save_y2 = y2.data_ptr()
     d.save_x0 = None if x0 is None else x0.data_ptr()
@@ -346,10 +368,7 @@ def _tc_block_backward(ctx, gy):
               "scatter_diff_sorted")
         gsrc[0] = gh
         if srcs[1] is not None and ctx.needs_input_grad[2]:
-            ge = torch.empty((rows, chans[1], B), dtype=torch.float32, device=dev)
-            check(lib().csmpn_scatter_rows(ptr(gx), cin * B, chans[0] * B, ptr(csr.perm_dst), ptr(ge), rows, chans[1] * B,
-                                           stream_ptr(dev)), "scatter_rows")
-            gsrc[1] = ge
+            gsrc[1] = _extra_channel_grad(gx, cin, chans, B, sgraph, srcs[1], rows, pair, dev)
     if not in_bpt:
         gsrc = [None if t is None else t.reshape(s) for t, s in zip(gsrc, sshapes)]
     gres = gy if has_res else None
@@ -449,7 +468,8 @@ def _block_uses_tc(algebra, layer, need_grad, rows=None) -> bool:
     return tc_supported(algebra.dim, lin.in_features, lin.out_features)
 
 
-def block_forward(algebra, layer, x, p1=None, p2=None, res=None, mode=0, sgraph=None, bpt_rows=None, out_bpt=False):
+def block_forward(algebra, layer, x, p1=None, p2=None, res=None, mode=0, sgraph=None, bpt_rows=None, out_bpt=False,
+                  pair_attr=False):
     """Run one CEMLP block (nn.Sequential of the four sub-layers) through the fused kernels.
 
     bpt_rows: x is a BPT tensor (output of a previous tensor-core block) holding that many rows.
@@ -461,7 +481,7 @@ def block_forward(algebra, layer, x, p1=None, p2=None, res=None, mode=0, sgraph=
         return y if res is None else res + y
     params = _block_params(layer)
     need_grad = _need_grad(x, p1, p2, res, *params)
-    cfg = {"dim": algebra.dim, "mode": mode, "sgraph": sgraph, "need_grad": need_grad}
+    cfg = {"dim": algebra.dim, "mode": mode, "sgraph": sgraph, "need_grad": need_grad, "pair_attr": pair_attr}
     rows_now = bpt_rows if in_bpt else (sgraph.csr.n_pairs if mode == 1 else x.shape[0])
     if in_bpt or _block_uses_tc(algebra, layer, need_grad, rows_now):
         cfg.update(in_bpt=in_bpt, out_bpt=out_bpt, rows=bpt_rows, c_in=layer[0].in_features)
@@ -473,11 +493,12 @@ def _chain_uses_tc(algebra, blocks, need_grad, rows) -> bool:
     return all(_block_supported(b) for b in blocks) and all(_block_uses_tc(algebra, b, need_grad, rows) for b in blocks)
 
 
-def mlp_forward(algebra, blocks, x, p1=None, p2=None, res=None, mode=0, sgraph=None, rows=None):
+def mlp_forward(algebra, blocks, x, p1=None, p2=None, res=None, mode=0, sgraph=None, rows=None, pair_attr=False):
     """A CEMLP (list of blocks): on the tensor-core engine the tensors between blocks stay in the BPT layout."""
     need_grad = _need_grad(x, p1, p2, res, *[t for b in blocks for t in _block_params(b)])
     tc = len(blocks) > 1 and _chain_uses_tc(algebra, blocks, need_grad, rows)
-    u = block_forward(algebra, blocks[0], x, p1, p2, res if len(blocks) == 1 else None, mode=mode, sgraph=sgraph, out_bpt=tc)
+    u = block_forward(algebra, blocks[0], x, p1, p2, res if len(blocks) == 1 else None, mode=mode, sgraph=sgraph, out_bpt=tc,
+                      pair_attr=pair_attr)
     for k, blk in enumerate(blocks[1:]):
         last = k == len(blocks) - 2
         u = block_forward(algebra, blk, u, res=res if last else None, bpt_rows=rows if tc else None, out_bpt=tc and not last)
@@ -486,9 +507,14 @@ def mlp_forward(algebra, blocks, x, p1=None, p2=None, res=None, mode=0, sgraph=N
 
 def egcl_forward(egcl, h, edge_index, edge_attr=None, node_attr=None):
     """EGCL.forward (cegnn_utils.py:277-284) on the fused path."""
+    from .cegnn_utils import PairedNodeAttr
+
     alg = egcl.algebra
     blocks_e, blocks_n = list(egcl.edge_model.layers), list(egcl.node_model.layers)
+    pair = isinstance(edge_attr, PairedNodeAttr)
     if not all(_block_supported(b) for b in blocks_e + blocks_n) or h.dim() != 3:
+        if pair:
+            edge_attr = edge_attr.materialize(edge_index)
         hf = alg.flatten(h)
         return alg.split(egcl.propagate(edge_index, h=hf, edge_attr=edge_attr, node_attr=node_attr))
     require_cuda(h, what="EGCL")
@@ -498,7 +524,8 @@ def egcl_forward(egcl, h, edge_index, edge_attr=None, node_attr=None):
     sg = sorted_graph(csr)
     h = f32c(h)
     if csr.n_pairs > 0:
-        m = mlp_forward(alg, blocks_e, h, edge_attr, None, None, mode=1, sgraph=sg, rows=csr.n_pairs)
+        m = mlp_forward(alg, blocks_e, h, edge_attr.node_attr if pair else edge_attr, None, None, mode=1, sgraph=sg,
+                        rows=csr.n_pairs, pair_attr=pair)
         agg = SegmentReduceSortedFn.apply(m.reshape(csr.n_pairs, -1), sg, egcl.aggr == "mean").reshape(N, -1, B)
     else:
         agg = h.new_zeros((N, egcl.out_features, B))

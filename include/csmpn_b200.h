@@ -195,6 +195,10 @@ typedef struct csmpn_block_desc {
                                            (fwd: 0 f1, 1 f2; bwd: 0 b1, 1 gemm dy2, 2 b3, 3 gemm grad_x, 4 dW wl/wr, 5 dW w1,
                                            6 final reduce) -- bench.py times one kernel at a time with it */
   float *save_y2, *save_x0;
+  int32_t pair_attr;                    /* mode 1: the c1 extra channels of a pair are  table[src] | table[dst]  with
+                                           table = p1 [n_nodes, c1/2, B] (per-simplex attributes, e.g. the simplex-type
+                                           embedding of md17_cssmpnn.py:122-133) instead of a materialised [E, c1, B]
+                                           edge_attr read through eid; its gradient: csmpn_scatter_pair_sorted */
 } csmpn_block_desc;
 
 /* gradients produced by csmpn_block_bwd (all overwritten; parameter gradients reduced deterministically) */
@@ -241,6 +245,13 @@ int csmpn_segment_expand_sorted(const float* grad_out, const int32_t* dst_sorted
 int csmpn_scatter_diff_sorted(const float* g, int64_t ld, const int32_t* rowptr_dst, const int32_t* rowptr_src,
                               const int32_t* perm_src, const int32_t* rank, float* grad_h, int64_t n_nodes,
                               int64_t width, int accumulate, csmpn_stream_t stream);
+/* Gradient of a per-simplex table that entered every pair as  table[src] | table[dst]  (csmpn_block_desc.pair_attr):
+ * out[n, :] = sum_{dst(p) = n} g[p, col_dst : col_dst + width] + sum_{src(p) = n} g[p, col_src : col_src + width]
+ * over receiver-sorted pair rows of g (leading dimension ld floats); fixed summation order.  Replaces the autograd of
+ * `torch.cat((node_attr[ei[0]], node_attr[ei[1]]), 1)` (md17_cssmpnn.py:131). */
+int csmpn_scatter_pair_sorted(const float* g, int64_t ld, int64_t col_src, int64_t col_dst, const int32_t* rowptr_dst,
+                              const int32_t* rowptr_src, const int32_t* perm_src, const int32_t* rank, float* out,
+                              int64_t n_nodes, int64_t width, csmpn_stream_t stream);
 /* out[eid[p], 0:width] = g[p, col0 : col0 + width]   (un-permute the gathered extra channels' gradient)        */
 int csmpn_scatter_rows(const float* g, int64_t ld, int64_t col0, const int32_t* eid, float* out, int64_t n_rows,
                        int64_t width, csmpn_stream_t stream);

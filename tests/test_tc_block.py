@@ -242,3 +242,64 @@ def test_host_feeder_round_trip():
     torch.cuda.synchronize()
     for i in range(steps):
         assert torch.equal(outs[i], torch.full((1 << 16,), 2.0 * i + i))
+
+
+@pytest.mark.parametrize("engine", ["tc", "simt"])
+@pytest.mark.parametrize("case", [CASES[0], CASES[2], CASES[3]], ids=["motion", "nba", "odd_c"])
+def test_paired_node_attr_equals_materialised_edge_attr(case, engine, monkeypatch):
+    """edge_attr = PairedNodeAttr(node_attr) (the kernel gathers node_attr[src] | node_attr[dst] itself) gives the layer
+    output of the materialised torch.cat((node_attr[ei[0]], node_attr[ei[1]]), 1) of the reference models
+    (md17_cssmpnn.py:131) bit for bit, and the same gradients -- node_attr's includes the part that flowed through
+    edge_attr -- on both engines and against the CPU oracle."""
+    name, metric, C, T, ncx, n, e, aggr = case
+    CliffordAlgebra, M = _mods()
+    monkeypatch.setenv("CSMPN_TC", "1" if engine == "tc" else "0")
+    ralg, params, h, ei, _, na, cot = _inputs(case)
+    hr, nar = h.clone().requires_grad_(), na.clone().requires_grad_()
+    pr = {k: v.clone().requires_grad_() for k, v in params.items()}
+    yr = R.egcl(ralg, hr, ei, torch.cat([nar[ei[0]], nar[ei[1]]], 1), nar, pr, aggr=aggr)
+    names = list(pr)
+    gr = torch.autograd.grad(yr, [hr, nar] + [pr[k] for k in names], cot)
+
+    alg = CliffordAlgebra(metric).to(DEV)
+    m = M.EGCL(alg, C, C, C, edge_attr_features=2 * T, node_attr_features=T, aggr=aggr).to(DEV)
+    _load(m, params)
+    pd = dict(m.named_parameters())
+    eid = ei.to(DEV)
+    out = {}
+    for mode in ("paired", "materialised"):
+        hd, nad = h.to(DEV).requires_grad_(), na.to(DEV).requires_grad_()
+        ea = M.PairedNodeAttr(nad) if mode == "paired" else torch.cat([nad[eid[0]], nad[eid[1]]], 1)
+        y = m(hd, eid, ea, nad)
+        out[mode] = (y, torch.autograd.grad(y, [hd, nad] + [pd[k] for k in names], cot.to(DEV)))
+    assert torch.equal(out["paired"][0], out["materialised"][0])
+    assert_close(out["paired"][0], yr, 1e-5, f"{name} fwd")
+    for what, a, b, c in zip(["gh", "gnode_attr"] + names, out["paired"][1], out["materialised"][1], gr):
+        assert_close(a, b, 1e-5, f"{name} {what} paired vs materialised")
+        assert_close(a, c, 1e-4, f"{name} {what} paired vs oracle")
+
+
+def test_graphed_layer_with_paired_node_attr():
+    from csmpn_b200.graphs import GraphedEGCL
+    from csmpn_b200.models.ops import CSRGraph
+
+    case = CASES[1]
+    name, metric, C, T, ncx, n, e, aggr = case
+    CliffordAlgebra, M = _mods()
+    ralg, params, h, ei, ea, na, cot = _inputs(case)
+    alg = CliffordAlgebra(metric).to(DEV)
+    m = M.EGCL(alg, C, C, C, edge_attr_features=2 * T, node_attr_features=T, aggr=aggr).to(DEV)
+    _load(m, params)
+    plist = list(m.parameters())
+    hd, nad, cotd = h.to(DEV), na.to(DEV).requires_grad_(), cot.to(DEV)
+    graph = CSRGraph(ei.to(DEV), h.shape[0])
+    g = GraphedEGCL(m, graph, hd, M.PairedNodeAttr(nad), nad)
+    h1 = hd.clone().requires_grad_()
+    y = m(h1, graph, M.PairedNodeAttr(nad), nad)
+    ge = torch.autograd.grad(y, [h1, nad] + plist, cotd)
+    h2 = hd.clone().requires_grad_()
+    yg = g(h2, None, nad)
+    gg = torch.autograd.grad(yg, [h2, nad] + plist, cotd)
+    assert torch.equal(y, yg)
+    for a, b in zip(ge, gg):
+        assert torch.equal(a, b)
