@@ -1,18 +1,22 @@
 #!/usr/bin/env python
 """bench.py -- the CSMPN hot path on B200: one EGCL layer forward+backward over a batch of synthetic complexes.
 
-    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload md17|motion|nba]
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload md17|motion|nba|hulls]
 
 Metric (BASELINE.json): simplices/sec fwd+bwd per CSMPN layer.  A step = one pass (forward + backward, all
 parameter and input gradients) of one shared simplicial message layer (EGCL) over one batch of 100 complexes.
 Default workload = BASELINE.json configs[1]: MD17-aspirin-shaped, 21 atoms, kNN(k=3) clique complex lifted to
-edges + triangles, Cl(3,0), hidden width 32, aggr "sum".
+edges + triangles, Cl(3,0), hidden width 32, aggr "sum".  ONE JSON line is printed; the other named configs
+(motion, NBA) ride along under "workloads" (layer step, resident inputs), the lifting and train-step figures
+under "lifting" and "train".
 
   value     whole-job simplices/s with inputs resident in HBM (CUDA events, L2 flushed between steps, max over ranks)
   e2e       the same step through the public layer API starting from HOST buffers: pinned H2D of
-            (h, edge_index, edge_attr, node_attr), CSR build, forward, backward, D2H of the layer output
-  roofline  the dominant kernel (fused edge-block backward) against the measured HBM peak; fp32-FMA fraction beside it
-  cpu_baseline / --impl reference   the CPU oracle port of the reference layer (oracle/layers_ref.py) on the host cores
+            (h, edge_index, node_attr), CSR build, forward, backward, D2H of the layer output AND of every gradient
+  roofline  the dominant kernel CLASS of the layer step by time share (every kernel timed alone, CUDA events) against
+            the measured HBM peak; roofline.layer = the whole layer against SURVEY 8d's fused-minimum bytes / FLOPs
+  cpu_baseline / --impl reference   the reference's own EGCL (oracle/_ref, the unmodified Python reference behind
+            oracle/refshim.py's PyG stand-in) on the host cores, same batch; the oracle port if oracle/_ref is absent
 """
 import argparse
 import json
@@ -34,6 +38,9 @@ WORKLOADS = {
     "md17": ((1.0, 1.0, 1.0), 32, "sum", 100, "MD17-aspirin-shaped: 21 atoms, kNN(k=3) clique complex (edges+triangles), Cl(3,0), C=32"),
     "motion": ((1.0, 1.0, 1.0), 28, "mean", 100, "CMU-motion-shaped: fixed 31v+12e+4t complex, 226 pairs, Cl(3,0), C=28"),
     "nba": ((1.0, 1.0), 40, "sum", 100, "NBA-shaped: 10 players + ball, full Rips complex, Cl(2,0), C=40"),
+    # BASELINE.json configs[0] (the reference's CPU-runnable case; csmpn/configs/hulls.yaml:20-23, hulls_cssmpnn.py:13-28):
+    # 8 points ~ N(0,1)^5, all <=2-faces of the Qhull facets, batch 16, Cl(5,0), C=28, aggr mean
+    "hulls": ((1.0, 1.0, 1.0, 1.0, 1.0), 28, "mean", 16, "convex-hulls-shaped: 8 points in R^5, faces of the Qhull facets, Cl(5,0), C=28, batch 16"),
 }
 T_TYPES = 3
 
@@ -107,6 +114,16 @@ def make_batch(workload, n_complexes, seed, hidden=None):
             n = 11
             und = [(i, j) for i in range(n) for j in range(i + 1, n)]
             edges, tris = _clique_complex(n, und)
+            s, t = _pairs_from_complex(n, edges, tris, extra_zero_zero=True)
+        elif workload == "hulls":
+            from scipy.spatial import ConvexHull
+
+            n = 8
+            facets = ConvexHull(rng.normal(0, 1, (n, 5))).simplices
+            edges = sorted({(min(a, b), max(a, b)) for f in facets for a in f for b in f if a != b})
+            tris = sorted({tuple(sorted((a, b, c))) for f in facets for a in f for b in f for c in f if a < b < c})
+            edges = [(int(a), int(b)) for a, b in edges]
+            tris = [(int(a), int(b), int(c)) for a, b, c in tris]
             s, t = _pairs_from_complex(n, edges, tris, extra_zero_zero=True)
         else:  # motion: 31 v, 12 e, 4 t; 130 skeleton pairs + 96 fixed pairs
             n = 31
@@ -202,24 +219,60 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-# ----------------------------------------------------------------------------------------------- CPU oracle arm
+# ----------------------------------------------------------------------------------------------- CPU reference arm
+def _reference_layer(b):
+    """The reference's own EGCL (csmpn/models/cegnn_utils.py:216-284, UNMODIFIED, from oracle/_ref -- a verbatim copy made
+    by oracle/make_ref.py) behind oracle/refshim.py's stand-in for PyG's MessagePassing; None if oracle/_ref is absent."""
+    ref_root = os.path.join(ROOT, "oracle", "_ref")
+    if not os.path.isdir(os.path.join(ref_root, "csmpn")):
+        return None
+    os.environ["CSMPN_REFERENCE_ROOT"] = ref_root  # never /root/reference at run time
+    from oracle import refshim
+
+    refshim.REFERENCE_ROOT = ref_root
+    refshim.install()
+    from csmpn.algebra.cliffordalgebra import CliffordAlgebra
+    from csmpn.models.cegnn_utils import EGCL
+
+    alg = CliffordAlgebra(b["metric"])
+    return EGCL(alg, b["C"], b["C"], b["C"], edge_attr_features=2 * T_TYPES, node_attr_features=T_TYPES, aggr=b["aggr"])
+
+
 def cpu_layer_time(workload, n_complexes, steps, warmup, seed=1000, hidden=None):
+    """fwd + bwd (input and all parameter gradients) of one layer on the host cores: (N, E, times, kind)"""
     from oracle import layers_ref as R
 
     torch.set_num_threads(os.cpu_count() or 1)
     b = make_batch(workload, n_complexes, seed, hidden=hidden)
     ralg = R.RefAlgebra(b["metric"])
-    params = {k: v.requires_grad_() for k, v in R.init_egcl_params(ralg, b["C"], T_TYPES, torch.Generator().manual_seed(0)).items()}
+    init = R.init_egcl_params(ralg, b["C"], T_TYPES, torch.Generator().manual_seed(0))
+    layer = _reference_layer(b)
+    if layer is not None:
+        missing, unexpected = layer.load_state_dict(init, strict=False)
+        assert not unexpected and all("algebra" in k for k in missing), (missing, unexpected)
+        plist = list(layer.parameters())
+        run = lambda h: layer(h, b["edge_index"], b["edge_attr"], b["node_attr"])
+        kind = "reference"
+    else:
+        params = {k: v.requires_grad_() for k, v in init.items()}
+        plist = list(params.values())
+        run = lambda h: R.egcl(ralg, h, b["edge_index"], b["edge_attr"], b["node_attr"], params, aggr=b["aggr"])
+        kind = "port"
     times = []
     for it in range(warmup + steps):
         h = b["h"].clone().requires_grad_()
         t0 = time.perf_counter()
-        y = R.egcl(ralg, h, b["edge_index"], b["edge_attr"], b["node_attr"], params, aggr=b["aggr"])
-        torch.autograd.grad(y, [h] + list(params.values()), b["cot"])
+        y = run(h)
+        torch.autograd.grad(y, [h] + plist, b["cot"])
         dt = time.perf_counter() - t0
         if it >= warmup:
             times.append(dt)
-    return b["N"], b["E"], times
+    return b["N"], b["E"], times, kind
+
+
+def _cpu_what(kind, cores):
+    return ("the reference's own EGCL (oracle/_ref: unmodified csmpn/models/cegnn_utils.py behind the PyG stand-in of oracle/refshim.py)"
+            if kind == "reference" else "oracle/layers_ref.py (port; oracle/_ref absent)") + f", torch CPU, {cores} threads"
 
 
 def run_reference(args):
@@ -227,22 +280,22 @@ def run_reference(args):
     if rank != 0:
         return
     metric, C, aggr, ncx, desc = WORKLOADS[args.workload]
-    sample_cx = 25
-    N, E, times = cpu_layer_time(args.workload, sample_cx, args.steps, args.warmup, hidden=args.hidden or None)
+    ncx = args.complexes or ncx  # the SAME batch as the GPU arm
+    N, E, times, kind = cpu_layer_time(args.workload, ncx, args.steps, args.warmup, hidden=args.hidden or None)
     ms = 1e3 * sum(times) / len(times)
     value = N / (ms * 1e-3)
     cores = os.cpu_count() or 1
+    C = args.hidden or C
     line = {
         "impl": "reference", "metric": "simplices/sec fwd+bwd per CSMPN layer", "value": value, "unit": "simplices/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": desc, "aggr": aggr, "hidden": C, "complexes_per_step": sample_cx, "simplices": N, "pairs": E},
-        "cpu_baseline": {"value": value, "unit": "simplices/s", "cores": cores, "kind": "port",
-                         "sample": f"{sample_cx} complexes ({N} simplices, {E} pairs) per step, oracle/layers_ref.py (torch CPU, {cores} threads)"},
+        "config": {"workload": desc, "aggr": aggr, "hidden": C, "complexes_per_step_per_gpu": ncx, "simplices_per_gpu": N, "pairs_per_gpu": E},
+        "cpu_baseline": {"value": value, "unit": "simplices/s", "cores": cores, "kind": kind,
+                         "sample": f"{ncx} complexes ({N} simplices, {E} pairs) per step, {_cpu_what(kind, cores)}"},
         "e2e": {"value": value, "unit": "simplices/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
-
 
 
 # ----------------------------------------------------------------------------------------------- full-model train step
@@ -264,63 +317,304 @@ def make_md17_graphs(n_complexes, seed, dev, frames=10, atoms=21):
     return graphs
 
 
-def train_leg(dev, world, rank, steps, warmup, lib, graphed=True):
-    """train complexes/s: the md17 model (C=32, 5 layers, 10 frames) on 100 complexes per GPU -- GPU lifting once, then
-    per step forward + backward + flat-bucket gradient all-reduce + Adam."""
+def _timed_region(fn, steps, dev, world):
+    """K calls of fn between two CUDA events, barrier + synchronize on both sides, max over ranks -> ms per call"""
     import torch.distributed as dist
 
-    from csmpn_b200.data.modules.simplicial_data import SimplicialTransform
-    from csmpn_b200.models.md17_cssmpnn import CliffordSharedSimplicialMPNN_md17
-    from csmpn_b200.train_step import DataParallelStep, GraphedDataParallelStep
-
-    ncx = 100
-    graphs = make_md17_graphs(ncx, 2000 + rank, dev)
-    batch = SimplicialTransform(dim=2, dis=2.5, label="md17", molecule_type="aspirin").lift(graphs, device=dev)
-    torch.manual_seed(0)
-    model = CliffordSharedSimplicialMPNN_md17().to(dev)
-    opt = torch.optim.Adam(model.parameters(), lr=1e-3, fused=True)
-    loc0 = batch.loc.clone()
-    batch.loc = loc0
-    lc0 = lib.csmpn_launch_count()
-    model(batch, 0, "train")[0].backward()  # one eager pass: counts this library's launches per step
-    launches_eager = lib.csmpn_launch_count() - lc0
-    model.zero_grad(set_to_none=True)
-    if graphed:
-        step = GraphedDataParallelStep(model, opt, batch)
-    else:
-        step = DataParallelStep(model, opt)
-
-    def one():
-        batch.loc = loc0
-        loss, _ = step(batch)
-        return loss
-
-    for _ in range(warmup):
-        one()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    l0 = lib.csmpn_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(steps):
-        loss = one()
+    for i in range(steps):
+        fn(i)
     e1.record()
     torch.cuda.synchronize()
-    launches = lib.csmpn_launch_count() - l0
     t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item()) / steps
-    return {"metric": "train complexes/sec (md17 model: Cl(3,0), C=32, 5 layers, 10 frames, Adam)", "value": ncx * world / (ms * 1e-3),
-            "unit": "complexes/s", "ms_per_step": ms, "complexes_per_step_per_gpu": ncx, "simplices_per_gpu": int(batch.x_ind.shape[0]),
-            "pairs_per_gpu": int(batch.edge_index.shape[1]), "params": sum(p.numel() for p in model.parameters()),
-            "gpu_launches_per_step": launches_eager, "final_loss": float(loss.detach()),
-            "launch": "forward + backward replayed from one CUDA graph (GraphedDataParallelStep); all-reduce and Adam eager"
-            if graphed else "eager"}
+    return float(t.item()) / steps
+
+
+def train_leg(dev, world, rank, steps, warmup, lib, graphed=True):
+    """train complexes/s: the md17 model (C=32, 5 layers, 10 frames) on 100 complexes per GPU, two ways:
+
+    fixed   one batch trained on repeatedly: forward + backward (+ all-reduce + Adam, see `launch`) replayed from ONE CUDA
+            graph -- what fixed-topology data (the motion skeleton) allows;
+    stream  a DIFFERENT batch every step (MD17 / NBA complexes change from sample to sample): per step the raw samples'
+            kNN pairs and features are copied from pinned host memory, lifted on the GPU (csmpn_lift_*), collated, CSR
+            built, then forward -> zero_grad -> backward -> all-reduce -> Adam -> cosine schedule, eagerly, in the
+            reference trainer's order (engineer/trainer/trainer.py:204-227)."""
+    from csmpn_b200.data.modules.simplicial_data import SimplicialTransform
+    from csmpn_b200.models.md17_cssmpnn import CliffordSharedSimplicialMPNN_md17
+    from csmpn_b200.train_step import CosineAnnealingLR, DataParallelStep, GraphedDataParallelStep
+
+    ncx = 100
+    lift = SimplicialTransform(dim=2, dis=2.5, label="md17", molecule_type="aspirin")
+    graphs = make_md17_graphs(ncx, 2000 + rank, dev)
+    batch = lift.lift(graphs, device=dev)
+    torch.manual_seed(0)
+    model = CliffordSharedSimplicialMPNN_md17().to(dev)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3, fused=True, capturable=True)
+    lc0 = lib.csmpn_launch_count()
+    model(batch, 0, "train")[0].backward()  # one eager pass: counts this library's launches per step
+    launches_eager = lib.csmpn_launch_count() - lc0
+    model.zero_grad(set_to_none=True)
+    out = {"metric": "train complexes/sec (md17 model: Cl(3,0), C=32, 5 layers, 10 frames, Adam)", "unit": "complexes/s",
+           "complexes_per_step_per_gpu": ncx, "params": sum(p.numel() for p in model.parameters()),
+           "gpu_launches_per_step": launches_eager}
+    # ---- (b) a stream of different batches, eager
+    n_pool = 8
+    pool = [make_md17_graphs(ncx, 3000 + 17 * k + rank, "cpu") for k in range(n_pool)]
+    for gs in pool:
+        for g in gs:
+            for k in ("loc", "vel", "edge_index", "charges", "y"):
+                setattr(g, k, getattr(g, k).pin_memory())
+    sched = CosineAnnealingLR(opt, steps * 64, warmup_steps=steps, decay_steps=steps * 16)
+    eager = DataParallelStep(model, opt)
+    sizes = []
+
+    def stream_step(i):
+        b = lift.lift(pool[i % n_pool], device=dev)  # pinned H2D of the raw samples + GPU lifting + collation
+        loss, _ = eager(b, i)
+        sched.step()
+        sizes.append(int(b.x_ind.shape[0]))
+        return loss
+
+    for i in range(warmup):
+        stream_step(i)
+    sizes.clear()
+    ms_stream = _timed_region(stream_step, steps, dev, world)
+    out["stream"] = {"value": ncx * world / (ms_stream * 1e-3), "ms_per_step": ms_stream,
+                     "simplices_per_step_per_gpu": [min(sizes), max(sizes)],
+                     "what": "different batch every step: pinned H2D of raw samples, GPU lifting, CSR build, forward, zero_grad, backward, "
+                             "flat-bucket all-reduce, fused Adam, cosine schedule; eager launches"}
+    # ---- (a) fixed structure, graph replay
+    loc0 = batch.loc.clone()
+    batch.loc = loc0
+    step = GraphedDataParallelStep(model, opt, batch) if graphed else DataParallelStep(model, opt)
+
+    def fixed_step(i):
+        batch.loc = loc0
+        return step(batch)[0]
+
+    for i in range(warmup):
+        fixed_step(i)
+    ms = _timed_region(fixed_step, steps, dev, world)
+    loss = fixed_step(0)
+    out.update({"value": ncx * world / (ms * 1e-3), "ms_per_step": ms, "simplices_per_gpu": int(batch.x_ind.shape[0]),
+                "pairs_per_gpu": int(batch.edge_index.shape[1]), "final_loss": float(loss.detach()),
+                "launch": getattr(step, "describe", lambda: "eager")()})
+    return out
+
+
+# ----------------------------------------------------------------------------------------------- lifting leg
+def lifting_leg(dev, hbm_peak, iters=10):
+    """GPU lifting throughput (SURVEY 8d lists lifting among the HBM-bound kernels): csmpn_lift_count + csmpn_lift_fill on
+    100 md17-shaped complexes per call and on a 4 000-complex batch; bytes = every output the lifter writes once
+    (edge_index int64, x_ind fp32, node_types / batch int64) + the pair lists it reads."""
+    from csmpn_b200.data.modules.lifting import LIFT_CLIQUE, lift_batch
+
+    res = {}
+    for ncx in (100, 4000):
+        base = make_md17_graphs(min(ncx, 200), 4000, "cpu")
+        graphs = [base[i % len(base)] for i in range(ncx)]
+        pairs = torch.cat([g.edge_index for g in graphs], 1).to(dev)
+        ppc = [g.edge_index.shape[1] for g in graphs]
+        nv = [g.loc.shape[0] for g in graphs]
+        lb = lift_batch(LIFT_CLIQUE, nv, pairs=pairs, pairs_per_complex=ppc, dim=2, device=dev)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            lb = lift_batch(LIFT_CLIQUE, nv, pairs=pairs, pairs_per_complex=ppc, dim=2, device=dev)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / iters
+        N, E = int(lb.x_ind.shape[0]), int(lb.edge_index.shape[1])
+        nbytes = 16 * E + 12 * N + 16 * N + 16 * pairs.shape[1]
+        res[f"{ncx}_complexes"] = {"complexes_per_s": ncx / (ms * 1e-3), "ms_per_call": ms, "simplices": N, "pairs": E,
+                                   "algorithmic_bytes": nbytes, "hbm_gbs": nbytes / (ms * 1e-3) / 1e9,
+                                   "hbm_frac": nbytes / (ms * 1e-3) / 1e9 / hbm_peak}
+    res["note"] = ("one call = csmpn_lift_count + one host sync for the output sizes + csmpn_lift_fill (one warp per complex); at 100 "
+                   "complexes the call is launch/sync-latency bound, at 4 000 it approaches the write bandwidth")
+    return res
+
 
 # ----------------------------------------------------------------------------------------------- GPU arm
+def _traffic_for_build():
+    """DRAM bytes per kernel class per layer step from an `ncu --set full` capture (tools/ncu_traffic.py writes
+    profiles/ncu_traffic.json) -- used ONLY when the capture was made from this very build of csrc/ (digest match)"""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        stamp = open(os.path.join(ROOT, "clifford-group-equivariant-simplicial-message-passing-networks_b200", "csrc", "build", "stamp.txt")).read().strip()
+        return t if t.get("csrc_digest") == stamp else None
+    except Exception:
+        return None
+
+
+def layer_leg(workload, ncx, C, dev, world, rank, steps, warmup, lib, use_graph=True, with_e2e=True, with_roofline=True,
+              hbm_peak=6553.0, peak_src=""):
+    """One workload: the layer step with resident inputs (`value`), from host buffers (`e2e`), its kernel roofline."""
+    import torch.distributed as dist
+
+    from csmpn_b200.algebra.cliffordalgebra import CliffordAlgebra
+    from csmpn_b200.models.cegnn_utils import EGCL, PairedNodeAttr
+    from csmpn_b200.models.ops import CSRGraph
+
+    metric, _, aggr, _, desc = WORKLOADS[workload]
+    b = make_batch(workload, ncx, 1000 + rank, hidden=C)
+    N, E, B = b["N"], b["E"], b["B"]
+    torch.manual_seed(0)
+    alg = CliffordAlgebra(metric).to(dev)
+    layer = EGCL(alg, C, C, C, edge_attr_features=2 * T_TYPES, node_attr_features=T_TYPES, aggr=aggr).to(dev)
+    params = [p for p in layer.parameters()]
+    n_par = sum(p.numel() for p in params)
+    # device-resident inputs.  edge_attr = node_attr[src] | node_attr[dst] (md17_cssmpnn.py:131) is passed symbolically
+    # (PairedNodeAttr): the message kernel gathers the two table rows itself, no [E, 2T, B] tensor exists
+    d = {k: b[k].to(dev) for k in ("h", "edge_index", "node_attr", "cot")}
+    graph = CSRGraph(d["edge_index"], N)
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
+
+    l0 = lib.csmpn_launch_count()
+    h_ = d["h"].detach().requires_grad_()
+    torch.autograd.grad(layer(h_, graph, PairedNodeAttr(d["node_attr"]), d["node_attr"]), [h_] + params, d["cot"])
+    launches_per_step = lib.csmpn_launch_count() - l0
+    glayer = None
+    flat = torch.empty(n_par, device=dev)
+
+    def step(h, graph_, node_attr):
+        hh = h.detach().requires_grad_()
+        if glayer is not None:
+            y = glayer(hh, None, node_attr)
+        else:
+            y = layer(hh, graph_, PairedNodeAttr(node_attr), node_attr)
+        grads = torch.autograd.grad(y, [hh] + params, d["cot"])
+        torch._foreach_copy_(list(flat.split([p.numel() for p in params])), [g.reshape(-1) for g in grads[1:]])
+        if world > 1:
+            dist.all_reduce(flat)
+            flat.div_(world)
+        return y, grads[0]
+
+    # host-resident inputs (pinned) for the end-to-end leg
+    host_in = {k: b[k].pin_memory() for k in ("h", "edge_index", "node_attr")}
+    y_host = torch.empty((N, C, B), dtype=torch.float32).pin_memory()
+    gh_host = torch.empty((N, C, B), dtype=torch.float32).pin_memory()
+    gp_host = torch.empty(n_par, dtype=torch.float32).pin_memory()
+    h2d_bytes = sum(v.numel() * v.element_size() for v in host_in.values())
+    d2h_bytes = (y_host.numel() + gh_host.numel() + gp_host.numel()) * 4
+
+    from csmpn_b200.pipeline import HostFeeder
+
+    feeder = HostFeeder(dev)
+
+    def run_e2e(n_steps):
+        """n_steps layer steps from HOST buffers through the public API: every step copies its inputs from pinned host
+        memory (HostFeeder: the copy of step i+1 overlaps the kernels of step i), builds the CSR of its edge_index, runs
+        forward + backward and copies the layer output, grad_h and all parameter gradients back to pinned host memory."""
+        feeder.submit(host_in)
+        for i in range(n_steps):
+            dv = feeder.next()
+            if i + 1 < n_steps:
+                feeder.submit(host_in)
+            flush.fill_(1.0)  # L2 flush, inside the timed region
+            if glayer is not None:  # batches of a fixed shape: CSR rebuilt in place, layer replayed from CUDA graphs
+                glayer.set_graph(dv["edge_index"])
+                y, gh = step(dv["h"], None, dv["node_attr"])
+            else:
+                y, gh = step(dv["h"], CSRGraph(dv["edge_index"], N), dv["node_attr"])
+            feeder.drain(y.detach(), y_host)
+            feeder.drain(gh, gh_host)
+            feeder.drain(flat, gp_host)
+            feeder.release(dv)
+        feeder.join()
+
+    def timed_e2e(steps, warmup, regions=3):
+        run_e2e(warmup)
+        out = []
+        for _ in range(regions):
+            out.append(_timed_block(lambda: run_e2e(steps), dev, world))
+        return statistics.median(out), out
+
+    def timed(steps, warmup):
+        for _ in range(warmup):
+            step(d["h"], graph, d["node_attr"])
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        evs = []
+        for _ in range(steps):
+            flush.fill_(1.0)  # L2 flush (256 MiB > 126 MB L2), outside the timed events
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            step(d["h"], graph, d["node_attr"])
+            e1.record()
+            evs.append((e0, e1))
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t = torch.tensor([sum(a.elapsed_time(bb) for a, bb in evs)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    if use_graph:
+        from csmpn_b200.graphs import GraphedEGCL
+
+        glayer = GraphedEGCL(layer, graph, d["h"], PairedNodeAttr(d["node_attr"]), d["node_attr"])
+    res = {"workload": desc, "aggr": aggr, "hidden": C, "complexes_per_step_per_gpu": ncx, "simplices_per_gpu": N, "pairs_per_gpu": E,
+           "gpu_launches_per_step": int(launches_per_step)}
+    if with_e2e:
+        e2e_ms, regions = timed_e2e(steps, max(3, warmup // 2))
+        res["e2e_ms_per_step"] = e2e_ms / steps
+        res["e2e_regions_ms_per_step"] = [r / steps for r in regions]
+        res["h2d_bytes_per_step"], res["d2h_bytes_per_step"] = h2d_bytes, d2h_bytes
+    total_ms = timed(steps, warmup)
+    res["ms_per_step"] = total_ms / steps
+    nt = torch.tensor([N], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(nt)
+    res["simplices_all_gpus"] = int(nt.item())
+    res["value"] = res["simplices_all_gpus"] / (res["ms_per_step"] * 1e-3)
+    if with_e2e:
+        res["e2e_value"] = res["simplices_all_gpus"] / (res["e2e_ms_per_step"] * 1e-3)
+    flops, nbytes = layer_flops_bytes(N, E, C, B)
+    t_s = res["ms_per_step"] * 1e-3
+    res["layer_roofline"] = {"algorithmic_bytes": nbytes, "algorithmic_flops": flops, "hbm_gbs": nbytes / t_s / 1e9,
+                             "hbm_frac": nbytes / t_s / 1e9 / hbm_peak, "fp32_tflops": flops / t_s / 1e12,
+                             "fp32_frac_of_74.4": flops / t_s / 1e12 / 74.4}
+    if with_roofline and rank == 0:
+        from csmpn_b200.models import fused
+
+        try:
+            res["roofline"] = fused.bench_layer_kernels(layer, d, graph, hbm_peak, peak_src, traffic=_traffic_for_build())
+        except Exception as e:  # pragma: no cover
+            res["roofline"] = {"bound": "hbm", "achieved": None, "peak": hbm_peak, "unit": "GB/s", "frac": None, "traffic": None,
+                               "kernel": f"unavailable: {e}", "peak_source": peak_src}
+    del glayer
+    return res
+
+
+def _timed_block(fn, dev, world):
+    import torch.distributed as dist
+
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    fn()
+    e1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
 def run_ours(args):
     import torch.distributed as dist
 
@@ -333,190 +627,67 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
 
     from csmpn_b200 import _lib
-    from csmpn_b200.algebra.cliffordalgebra import CliffordAlgebra
-    from csmpn_b200.models.cegnn_utils import EGCL
-    from csmpn_b200.models.ops import CSRGraph
 
     lib = _lib.lib()
     metric, C, aggr, ncx, desc = WORKLOADS[args.workload]
-    if args.complexes:
-        ncx = args.complexes  # scaling sweep (BASELINE.json configs[4]): same complexes, larger batch
-    if args.hidden:
-        C = args.hidden
-        desc = desc.rsplit("C=", 1)[0] + f"C={C}"
-    b = make_batch(args.workload, ncx, 1000 + rank, hidden=C)
-    N, E, B = b["N"], b["E"], b["B"]
-    torch.manual_seed(0)
-    alg = CliffordAlgebra(metric).to(dev)
-    layer = EGCL(alg, C, C, C, edge_attr_features=2 * T_TYPES, node_attr_features=T_TYPES, aggr=aggr).to(dev)
-    params = [p for p in layer.parameters()]
-    flat_grads = None
+    ncx = args.complexes or ncx  # scaling sweep (BASELINE.json configs[4]): same complexes, larger batch
+    C = args.hidden or C
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
 
-    # device-resident inputs
-    d = {k: b[k].to(dev) for k in ("h", "edge_index", "node_attr", "edge_attr", "cot")}
-    graph = CSRGraph(d["edge_index"], N)
-    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
-
-    # launches of one eager step (the CUDA-graph replay launches the same kernels without passing through the C ABI)
-    l0 = lib.csmpn_launch_count()
-    h_ = d["h"].detach().requires_grad_()
-    torch.autograd.grad(layer(h_, graph, d["edge_attr"], d["node_attr"]), [h_] + params, d["cot"])
-    launches_per_step = lib.csmpn_launch_count() - l0
-    glayer = None  # created after the end-to-end leg (which runs eagerly)
-
-    def step_resident():
-        h = d["h"].detach().requires_grad_()
-        y = glayer(h, d["edge_attr"], d["node_attr"]) if glayer is not None else layer(h, graph, d["edge_attr"], d["node_attr"])
-        grads = torch.autograd.grad(y, [h] + params, d["cot"])
-        if world > 1:
-            flat = torch.cat([g.reshape(-1) for g in grads[1:]])
-            dist.all_reduce(flat)
-            flat.div_(world)
-        return y
-
-    # host-resident inputs (pinned) for the end-to-end leg
-    pin = {k: b[k].pin_memory() for k in ("h", "edge_index", "node_attr", "edge_attr", "cot")}
-    y_host = torch.empty((N, C, B), dtype=torch.float32).pin_memory()
-    h2d_bytes = sum(pin[k].numel() * pin[k].element_size() for k in ("h", "edge_index", "node_attr", "edge_attr"))
-    d2h_bytes = y_host.numel() * 4
-
-    from csmpn_b200.pipeline import HostFeeder
-
-    host_in = {k: pin[k] for k in ("h", "edge_index", "node_attr", "edge_attr")}
-    feeder = HostFeeder(dev)
-
-    def run_e2e(n_steps):
-        """n_steps layer steps from HOST buffers through the public API: every step copies its inputs from pinned host
-        memory (HostFeeder: the copy of step i+1 overlaps the kernels of step i), builds the CSR of its edge_index,
-        runs forward + backward and copies the layer output back to pinned host memory."""
-        feeder.submit(host_in)
-        for i in range(n_steps):
-            dv = feeder.next()
-            if i + 1 < n_steps:
-                feeder.submit(host_in)
-            flush.fill_(1.0)  # L2 flush, inside the timed region
-            hh = dv["h"].detach().requires_grad_()
-            if glayer is not None:  # batches of a fixed shape: CSR rebuilt in place, layer replayed from CUDA graphs
-                glayer.set_graph(dv["edge_index"])
-                y = glayer(hh, dv["edge_attr"], dv["node_attr"])
-            else:
-                y = layer(hh, CSRGraph(dv["edge_index"], N), dv["edge_attr"], dv["node_attr"])
-            grads = torch.autograd.grad(y, [hh] + params, d["cot"])
-            if world > 1:
-                flat = torch.cat([g.reshape(-1) for g in grads[1:]])
-                dist.all_reduce(flat)
-            feeder.drain(y.detach(), y_host)
-            feeder.release(dv)
-        feeder.join()
-
-    def timed_e2e(steps, warmup, regions=3):
-        """`regions` timed regions of `steps` steps each (max over ranks per region); the median region is reported: the
-        eager host-fed loop is sensitive to single host-side stalls of the shared box, which one region cannot tell apart"""
-        run_e2e(warmup)
-        out = []
-        for _ in range(regions):
-            torch.cuda.synchronize()
-            if world > 1:
-                dist.barrier()
-            torch.cuda.synchronize()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            run_e2e(steps)
-            e1.record()
-            torch.cuda.synchronize()
-            t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
-            if world > 1:
-                dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            out.append(float(t.item()))
-        return statistics.median(out), out
-
-    def timed(fn, steps, warmup):
-        for _ in range(warmup):
-            fn()
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        evs = []
-        l0 = lib.csmpn_launch_count()
-        for _ in range(steps):
-            flush.fill_(1.0)  # L2 flush (256 MiB > 126 MB L2), outside the timed events
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            fn()
-            e1.record()
-            evs.append((e0, e1))
-        torch.cuda.synchronize()
-        launches = lib.csmpn_launch_count() - l0
-        if world > 1:
-            dist.barrier()
-        total_ms = sum(a.elapsed_time(bb) for a, bb in evs)
-        t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item()), launches
-
-    if not args.no_graph:
-        from csmpn_b200.graphs import GraphedEGCL
-
-        glayer = GraphedEGCL(layer, graph, d["h"], d["edge_attr"], d["node_attr"])
-    e2e_ms, e2e_regions = timed_e2e(args.steps, max(3, args.warmup // 2))
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    total_ms, launches = timed(step_resident, args.steps, args.warmup)
+    main = layer_leg(args.workload, ncx, C, dev, world, rank, args.steps, args.warmup, lib, use_graph=not args.no_graph,
+                     hbm_peak=hbm_peak, peak_src=peak_src)
+    clocks = sampler.stop() if rank == 0 else None  # sampled over the e2e and layer-step timed regions of the headline workload
+    others = {}
+    if args.workload == "md17" and not args.complexes and not args.hidden and not args.only:
+        for w in ("motion", "nba"):  # the other named GPU configs (BASELINE.json configs[2], [3]): resident layer step
+            r = layer_leg(w, WORKLOADS[w][3], WORKLOADS[w][1], dev, world, rank, max(5, args.steps // 2), 3, lib,
+                          use_graph=not args.no_graph, with_e2e=False, with_roofline=True, hbm_peak=hbm_peak, peak_src=peak_src)
+            if "roofline" in r:  # keep the line readable: class summary only
+                r["roofline"] = {k: r["roofline"].get(k) for k in ("kernel", "achieved", "frac", "unit", "classes", "summed_kernel_ms")}
+            others[w] = r
     train = None if args.no_train else train_leg(dev, world, rank, max(3, args.steps // 2), 3, lib, graphed=not args.no_graph)
-    clocks = sampler.stop() if rank == 0 else None  # sampled over the layer-step and train-step timed regions
-
-    ms_per_step = total_ms / args.steps
-    n_total = N * world  # every rank holds a batch of the same shape (weak scaling); N differs by a few per rank
-    nt = torch.tensor([N], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(nt)
-        n_total = int(nt.item())
-    value = n_total / (ms_per_step * 1e-3)
-    e2e_value = n_total / (e2e_ms / args.steps * 1e-3)
+    lifting = lifting_leg(dev, hbm_peak) if (rank == 0 and not args.only) else None
 
     if rank == 0:
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
-        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
-        flops, nbytes = layer_flops_bytes(N, E, C, B)
-        t_s = ms_per_step * 1e-3
-        roof = roofline_dominant_kernel(args, layer, d, graph, N, E, C, B, hbm_peak, peak_src, lib)
-        roof["layer"] = {"algorithmic_bytes": nbytes, "algorithmic_flops": flops, "hbm_gbs": nbytes / t_s / 1e9,
-                         "hbm_frac": nbytes / t_s / 1e9 / hbm_peak, "fp32_tflops": flops / t_s / 1e12,
-                         "fp32_frac_of_74.4": flops / t_s / 1e12 / 74.4,
-                         "note": "fused-minimum bytes / FLOPs of SURVEY 8d; the tensor-core engine runs a block as several kernels "
-                                 "whose intermediates cross L2/HBM (per-kernel figures under roofline.kernels)"}
+        roof = main.pop("roofline")
+        lr = main.pop("layer_roofline")
+        lr["note"] = ("the whole layer step (`value`) against SURVEY 8d's fused-minimum bytes / FLOPs; the tensor-core engine runs a block "
+                      "as several kernels whose intermediates cross L2/HBM (per-kernel figures under roofline.kernels)")
+        roof["layer"] = lr
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            sample_cx = 25
-            cN, cE, times = cpu_layer_time(args.workload, sample_cx, 3, 1, hidden=args.hidden or None)
+            cN, cE, times, kind = cpu_layer_time(args.workload, ncx, 3, 1, hidden=args.hidden or None)
             cms = statistics.median(times)
             cores = os.cpu_count() or 1
-            cpu = {"value": cN / cms, "unit": "simplices/s", "cores": cores, "kind": "port",
-                   "sample": f"{sample_cx} complexes ({cN} simplices, {cE} pairs), median of 3 after 1 warm-up, oracle/layers_ref.py torch CPU {cores} threads"}
+            cpu = {"value": cN / cms, "unit": "simplices/s", "cores": cores, "kind": kind,
+                   "sample": f"the same {ncx} complexes ({cN} simplices, {cE} pairs), median of 3 steps after 1 warm-up, {_cpu_what(kind, cores)}"}
+        glaunch = "CUDA-graph replay of the layer forward and backward (csmpn_b200.graphs.GraphedEGCL)" if not args.no_graph else "eager"
         line = {
-            "metric": "simplices/sec fwd+bwd per CSMPN layer", "value": value, "unit": "simplices/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "metric": "simplices/sec fwd+bwd per CSMPN layer", "value": main["value"], "unit": "simplices/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": main["ms_per_step"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": desc, "aggr": aggr, "hidden": C, "complexes_per_step_per_gpu": ncx, "simplices_per_gpu": N,
-                       "pairs_per_gpu": E, "l2": "flushed between timed steps (256 MiB write)",
-                       "parallelism": f"dp{world}" if world > 1 else "single", "path": fused_path_name(),
-                       "launch": "CUDA-graph replay of the layer forward and backward (csmpn_b200.graphs.GraphedEGCL)"
-                       if glayer is not None else "eager"},
-            "e2e": {"value": e2e_value, "unit": "simplices/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
-                    "ms_per_step": e2e_ms / args.steps, "regions_ms_per_step": [r / args.steps for r in e2e_regions],
-                    "how": "median of 3 regions of K steps, each timed as one region; per step: pinned H2D of h, edge_index, edge_attr, node_attr (csmpn_b200.pipeline."
-                           "HostFeeder, copy of step i+1 overlaps the kernels of step i), CSR build (in place), layer forward + backward "
-                           "(CUDA-graph replay unless --no-graph), "
-                           "D2H of the layer output; 256 MiB L2 flush inside the region every step"},
-            "gpu_launches": int(launches_per_step * args.steps), "gpu_launches_per_step": int(launches_per_step), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "train": train,
+            "config": {"workload": desc, "aggr": aggr, "hidden": C, "complexes_per_step_per_gpu": ncx, "simplices_per_gpu": main["simplices_per_gpu"],
+                       "pairs_per_gpu": main["pairs_per_gpu"], "l2": "flushed between timed steps (256 MiB write)",
+                       "parallelism": f"dp{world}" if world > 1 else "single", "path": fused_path_name(), "launch": glaunch,
+                       "edge_attr": "PairedNodeAttr(node_attr): node_attr[src] | node_attr[dst] gathered inside the message kernel"},
+            "e2e": {"value": main["e2e_value"], "unit": "simplices/s", "h2d_bytes_per_step": main["h2d_bytes_per_step"],
+                    "d2h_bytes_per_step": main["d2h_bytes_per_step"], "ms_per_step": main["e2e_ms_per_step"],
+                    "regions_ms_per_step": main["e2e_regions_ms_per_step"],
+                    "how": "median of 3 regions of K steps, each timed as one region; per step: pinned H2D of h, edge_index, node_attr "
+                           "(csmpn_b200.pipeline.HostFeeder, copy of step i+1 overlaps the kernels of step i), CSR build (in place), layer "
+                           "forward + backward (CUDA-graph replay unless --no-graph), D2H of the layer output, grad_h and every parameter "
+                           "gradient; 256 MiB L2 flush inside the region every step"},
+            "gpu_launches": int(main["gpu_launches_per_step"] * args.steps), "gpu_launches_per_step": main["gpu_launches_per_step"],
+            "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "workloads": others or None, "train": train, "lifting": lifting,
         }
         print(json.dumps(line))
     if world > 1:
@@ -524,27 +695,9 @@ def run_ours(args):
 
 
 def fused_path_name():
-    try:
-        from csmpn_b200.models import fused
+    from csmpn_b200.models import fused
 
-        return "fused block kernels: tcgen05 engine for blocks with >= %d rows, FP32 SIMT engine below" % fused.tc_min_rows() if fused.available() else "unit kernels (composed)"
-    except Exception:
-        return "unit kernels (composed)"
-
-
-def roofline_dominant_kernel(args, layer, d, graph, N, E, C, B, hbm_peak, peak_src, lib):
-    """Time the dominant kernel alone with CUDA events on the launching stream (fused edge-block backward when the
-    fused path is present; until then the layer-level figures stand in and `kernel` says so)."""
-    try:
-        from csmpn_b200.models import fused
-
-        if fused.available():
-            return fused.bench_dominant_kernel(layer, d, graph, hbm_peak, peak_src)
-    except Exception as e:  # pragma: no cover
-        return {"bound": "hbm", "achieved": None, "peak": hbm_peak, "unit": "GB/s", "frac": None, "traffic": None,
-                "kernel": f"unavailable: {e}", "peak_source": peak_src}
-    return {"bound": "hbm", "achieved": None, "peak": hbm_peak, "unit": "GB/s", "frac": None, "traffic": None,
-            "kernel": "composed unit kernels (no single dominant kernel yet)", "peak_source": peak_src}
+    return "fused block kernels: tcgen05 engine for blocks with >= %d rows, FP32 SIMT engine below" % fused.tc_min_rows()
 
 
 def main():
@@ -559,6 +712,7 @@ def main():
     ap.add_argument("--hidden", type=int, default=0, help="hidden width C (default: the workload's)")
     ap.add_argument("--no-train", action="store_true", help="skip the full-model train-step leg")
     ap.add_argument("--no-graph", action="store_true", help="launch the layer step eagerly instead of replaying CUDA graphs")
+    ap.add_argument("--only", action="store_true", help="only the named workload's layer legs (no motion/NBA side runs, no lifting leg)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -313,8 +313,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_f2_kernel(FwdArgs a) {
   float* wv_s = sn_s + Cp * G;                                           // path weights [Cp][P]
   float* bl_s = wv_s + Cp * P;
   float* la_s = bl_s + Cp;
-  float* rowsum_s = la_s + Cp;                                           // [4][128]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(rowsum_s + 4 * kTile);
+  float* rowsum_s = la_s + Cp;                                           // [2 tile parities][4][128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(rowsum_s + 8 * kTile);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kPipeBars);
   Pipe p;
   p.init(smem, bars, B * kPS);
@@ -440,10 +440,13 @@ __global__ void __launch_bounds__(kThreads, 1) tc_f2_kernel(FwdArgs a) {
     }
     tmem_wait_st();
     TSTAMP(22);
-    rowsum_s[(warp >> 2) * kTile + r] = rs;
+    // two copies, alternating by tile: a warp's reads of tile t and another warp's writes of tile t+1 are ordered by the
+    // mbarrier chain of the next K loop anyway, but never touch the same words this way
+    float* rowsum_t = rowsum_s + (t & 1) * 4 * kTile;
+    rowsum_t[(warp >> 2) * kTile + r] = rs;
     __syncthreads();
     TSTAMP(23);
-    const float inv_mu = fast_rcp((rowsum_s[r] + rowsum_s[kTile + r] + rowsum_s[2 * kTile + r] + rowsum_s[3 * kTile + r]) / (float)C + kEps);
+    const float inv_mu = fast_rcp((rowsum_t[r] + rowsum_t[kTile + r] + rowsum_t[2 * kTile + r] + rowsum_t[3 * kTile + r]) / (float)C + kEps);
     // ---- pass 2: saves, MVLayerNorm scale, residual, output
     for (int c4 = warp >> 2; c4 < (Cp >> 2); c4 += 4) {
       float o[B][4];
@@ -515,7 +518,7 @@ size_t f1_smem(int Cp, int kin8) {
 template <int DIM>
 size_t f2_smem(int Cp) {
   constexpr int B = Alg<DIM>::B, G = Alg<DIM>::G, P = Alg<DIM>::P;
-  return (size_t)(kRing + 1) * B * kPS + (size_t)2 * G * 2 * Cp * Cp * 4 + (size_t)Cp * (G + P + 2) * 4 + 4 * kTile * 4 + 96;
+  return (size_t)(kRing + 1) * B * kPS + (size_t)2 * G * 2 * Cp * Cp * 4 + (size_t)Cp * (G + P + 2) * 4 + 8 * kTile * 4 + 96;
 }
 constexpr size_t kSmemMax = 227 * 1024;
 

@@ -54,6 +54,16 @@ def _declare():
 
 FUSED_DIMS = (2, 3, 5)
 
+# bench.py's per-kernel timing: when a list is bound here, every block call appends (kind, dim, descriptor copies and the
+# tensors they point to); bench_layer_kernels() then replays each recorded call one kernel at a time (stage_mask)
+_RECORDER = None
+
+
+def _record(kind, dim, d, g=None, ws=None, keep=()):
+    if _RECORDER is not None:
+        _RECORDER.append({"kind": kind, "dim": dim, "desc": BlockDesc.from_buffer_copy(d),
+                          "grads": None if g is None else BlockGrads.from_buffer_copy(g), "ws": ws, "keep": list(keep)})
+
 
 def tc_enabled() -> bool:
     """Tensor-core (tcgen05) engine switch: CSMPN_TC=0 forces the FP32 SIMT kernels (tests cross-check the two)."""
@@ -195,6 +205,7 @@ class FusedBlockFn(torch.autograd.Function):
         resc = None if res is None else f32c(res)
         d = _fill_desc(dim, mode, srcs, chans, rows, c, params, sgraph, y, resc, saves, pair)
         check(lib().csmpn_block_fwd(dim, ctypes.byref(d), stream_ptr(dev)), "block_fwd")
+        _record("fwd", dim, d, keep=[srcs, params, y, resc, saves])
         if need_grad:
             ctx.save_for_backward(*[t for t in srcs if t is not None], *[t for t in params if t is not None], *saves)
             ctx.meta = (dim, mode, sgraph, chans, c, rows, [t is not None for t in srcs], [t is not None for t in params],
@@ -227,6 +238,7 @@ class FusedBlockFn(torch.autograd.Function):
             raise _lib.CsmpnError("fused block backward: unsupported configuration")
         ws = workspace(nbytes, dev)
         check(lib().csmpn_block_bwd(dim, ctypes.byref(d), ctypes.byref(g), ptr(ws), ws.numel(), stream_ptr(dev)), "block_bwd")
+        _record("bwd", dim, d, g, ws, keep=[srcs, params, saves, gy, gx, pg])
         # split the gradient of the assembled input row back onto the sources
         gsrc = [None, None, None]
         if mode == 0:
@@ -305,6 +317,7 @@ class TcBlockFn(torch.autograd.Function):
         d.save_y2 = y2.data_ptr()
         d.save_x0 = None if x0 is None else x0.data_ptr()
         check(lib().csmpn_block_fwd(dim, ctypes.byref(d), stream_ptr(dev)), "block_fwd (tensor-core)")
+        _record("fwd", dim, d, keep=[srcs, params, y, resc, saves, y2, x0])
         if need_grad:
             ctx.save_for_backward(*[t for t in srcs if t is not None], *[t for t in params if t is not None], *saves, y2,
                                   *([] if x0 is None else [x0]))
@@ -345,6 +358,7 @@ def _tc_block_backward(ctx, gy):
     if nbytes < 0:
         raise _lib.CsmpnError("tensor-core block backward: unsupported configuration")
     ws = workspace(nbytes, dev)
+    _record("bwd", dim, d, g, ws, keep=[srcs, params, y1, xr, o, y2, x0, gy, gx, pg])
     if _fork_enabled() and rows <= fork_max_rows():
         _tc_backward_forked(dim, d, g, ws, dev)
     else:
@@ -547,120 +561,108 @@ def _time_call(fn, flush, iters, warm=3):
     return sum(ts) / len(ts) * 1e-3
 
 
-def bench_dominant_kernel(layer, d, graph, hbm_peak, peak_src, iters=10):
-    """Time every kernel of the first edge block (the widest launch of the layer: one row per adjacency pair) ALONE with
-    CUDA events on the launching stream, L2 flushed between launches, and report the one with the largest duration
-    against the HBM roof.  Algorithmic bytes of a kernel = the tensors it must read and write once.
-    On the tensor-core engine a block is several kernels (csmpn_block_desc.stage_mask selects one); on the FP32 SIMT
-    engine it is one forward and one backward kernel."""
+def _kernel_stages(d: BlockDesc, g, B: int):
+    """(class, description, mask, algorithmic bytes, tensor-pipe FLOPs) of every kernel behind one recorded block call.
+    Algorithmic bytes = every tensor the kernel must read or write, once; T = one BPT [rows, Cp]
+    tensor, Tin = one BPT [rows, c_in] tensor; tensor-pipe FLOPs count the three TF32 MMAs of a split product."""
+    rows, C = int(d.rows), int(d.c)
+    cin = d.c0 + d.c1 + d.c2
+    cp, cinp = (C + 15) // 16 * 16, (cin + 15) // 16 * 16
+    tiles = (rows + 127) // 128
+    T, Tin = tiles * 128 * B * cp * 4, tiles * 128 * B * cinp * 4
+    ref = lambda ch: rows * ch * B * 4
+    if d.engine == 0:  # FP32 SIMT engine: one kernel per direction
+        src = ref(2 * d.c0 + d.c1) + 12 * rows if d.mode == 1 else ref(cin)
+        if g is None:
+            return [("block_fwd (fp32 simt)", "fused CEMLP block forward", 0, src + ref(4 * C), 0)]
+        return [("block_bwd (fp32 simt)", "fused CEMLP block backward + parameter-gradient reduce", 0, src + ref(4 * C) + ref(cin), 0)]
+    if g is None:
+        f1_in = Tin if d.in_bpt else (ref(2 * d.c0) + ref(d.c1) + 12 * rows if d.mode == 1 else ref(cin))
+        f1_out = (0 if d.in_bpt else Tin) + 2 * T
+        y_out = T if d.out_bpt else ref(C) * (2 if d.res else 1)
+        return [("tc_f1", "input rows (gather | BPT) -> MVLinear W1 + bias -> y1, MVSiLU -> y2", 1, f1_in + f1_out, 3 * rows * 2 * B * C * cin),
+                ("tc_f2", "linear_right/left + normalisation + weighted GP + MVLayerNorm (+residual)", 2, 4 * T + y_out, 3 * rows * 4 * B * C * C)]
+    gy = T if g.gy_bpt else ref(C)
+    gx = 0 if not g.grad_x else (Tin if g.gx_bpt else ref(cin))
+    return [("tc_b1", "MVLayerNorm / weighted GP / normalisation adjoints", 1, 6 * T + gy, 0),
+            ("tc_bgemm", "dy2 = dy2p + d WL + dxr WR", 2, 4 * T, 3 * rows * 4 * B * C * C),
+            ("tc_b3", "MVSiLU adjoint", 4, 3 * T, 0),
+            ("tc_bgemm", "grad_x = dy1 W1", 8, T + gx, 3 * rows * 2 * B * C * cin),
+            ("tc_dw", "dWL, dWR = [d|dxr]^T y2", 16, 3 * T, 3 * rows * 4 * B * C * C),
+            ("tc_dw", "dW1 = dy1^T x0", 32, T + Tin, 3 * rows * 2 * B * C * cin),
+            ("tc_final", "fixed-order reduction of per-CTA partials", 64, 0, 0)]
+
+
+def bench_layer_kernels(layer, d, graph, hbm_peak, peak_src, traffic=None, iters=8):
+    """Per-kernel roofline of ONE layer step, measured live: one eager forward + backward is recorded (every block call of
+    the layer with its descriptors), then every kernel behind every recorded call is launched ALONE (stage_mask) and
+    timed with CUDA events on the launching stream, L2 flushed between launches.  Kernels are grouped by class; the
+    DOMINANT class is the one with the largest share of the summed kernel time of the layer, and the reported figure is
+    its algorithmic bytes over its time (all its launches in the layer).  ``traffic``: optional {class: DRAM bytes per
+    layer step} from an ncu capture of this very build (bench.py passes it only when the build digest matches)."""
+    global _RECORDER
+    from .cegnn_utils import PairedNodeAttr
+
     alg = layer.algebra
     B = alg.n_blades
-    csr = ops.get_csr(graph, d["h"].shape[0])
-    sg = sorted_graph(csr)
-    blk = layer.edge_model.layers[0]
-    if not _block_supported(blk):
-        return {"bound": "hbm", "achieved": None, "peak": hbm_peak, "unit": "GB/s", "frac": None, "traffic": None,
-                "peak_source": peak_src, "engine": "unit kernels",
-                "kernel": "composed unit kernels (this block shape is outside both fused engines; no single dominant kernel timed)"}
-    params = tuple(None if t is None else f32c(t.detach()) for t in _block_params(blk))
-    h, ea = f32c(d["h"]), f32c(d["edge_attr"])
-    E, C = csr.n_pairs, params[0].shape[0]
-    c0, c1 = h.shape[1], ea.shape[1]
-    cin = c0 + c1
-    dev = h.device
-    tc = _block_uses_tc(alg, blk, True, E)
+    dev = d["h"].device
     s = stream_ptr(dev)
     flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)
-    names = ("g_w1", "g_b1", "g_sa", "g_sb", "g_wr", "g_na", "g_wl", "g_bl", "g_wp", "g_la")
-    pg = [None if t is None else torch.empty_like(t) for t in params]
-    g = BlockGrads()
-    for n, t in zip(names, pg):
-        setattr(g, n, None if t is None else t.data_ptr())
-    fl_lin = 2 * B * C * (cin + 2 * C)
-    if tc:
-        y = bpt_empty(alg.dim, E, C, dev)
-        saves = tuple(bpt_empty(alg.dim, E, C, dev) for _ in range(3))
-        y2 = bpt_empty(alg.dim, E, C, dev)
-        x0 = bpt_empty(alg.dim, E, cin, dev)
-        desc = _fill_desc(alg.dim, 1, [h, ea, None], [c0, c1, 0], E, C, params, sg, y, None, saves)
-        desc.engine, desc.in_bpt, desc.out_bpt = 1, 0, 1
-        desc.save_y2, desc.save_x0 = y2.data_ptr(), x0.data_ptr()
-        check(lib().csmpn_block_fwd(alg.dim, ctypes.byref(desc), s), "block_fwd")
-        gy = torch.randn_like(y)
-        gx = torch.empty((E, cin, B), device=dev)
-        g.grad_y, g.grad_x, g.gy_bpt, g.gx_bpt = gy.data_ptr(), gx.data_ptr(), 1, 0
-        ws = workspace(lib().csmpn_block_bwd_workspace(alg.dim, ctypes.byref(desc)), dev)
-        check(lib().csmpn_block_bwd(alg.dim, ctypes.byref(desc), ctypes.byref(g), ptr(ws), ws.numel(), s), "block_bwd")
-        T = y.numel() * 4          # one BPT [C] tensor
-        Tin = x0.numel() * 4       # one BPT [c_in] tensor
-        Tg = E * (2 * c0 + c1) * B * 4 + 12 * E  # gathered rows + indices
-        Tx = E * cin * B * 4
-        # (name, is_bwd, mask, algorithmic bytes, tensor-pipe FLOPs (3 TF32 MMAs per product))
-        stages = [
-            ("tc_f1_kernel<3,0> (gather + MVLinear W1 + MVSiLU)", 0, 1, Tg + Tin + 2 * T, 3 * E * 2 * B * C * cin),
-            ("tc_f2_kernel (linear_left/right + norm + weighted GP + MVLayerNorm)", 0, 2, 5 * T, 3 * E * 4 * B * C * C),
-            ("tc_b1_kernel (LayerNorm / weighted GP / normalisation adjoints)", 1, 1, 7 * T, 0),
-            ("tc_bgemm_kernel (dy2 = dy2p + d WL + dxr WR)", 1, 2, 4 * T, 3 * E * 4 * B * C * C),
-            ("tc_b3_kernel (MVSiLU adjoint)", 1, 4, 3 * T, 0),
-            ("tc_bgemm_kernel (grad_x = dy1 W1)", 1, 8, T + Tx, 3 * E * 2 * B * C * cin),
-            ("tc_dw_kernel (dWL, dWR = [d|dxr]^T y2)", 1, 16, 3 * T, 3 * E * 4 * B * C * C),
-            ("tc_dw_kernel (dW1 = dy1^T x0)", 1, 32, T + Tin, 3 * E * 2 * B * C * cin),
-            ("tc_final_kernel (fixed-order reduction of per-CTA partials)", 1, 64, 0, 0),
-        ]
-        # DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) from the committed `ncu --set full` capture of
-        # this workload (profiles/r01_ncu_full_tc_kernels.txt: md17, 53 976 pairs, C = 32); other shapes report null
-        ncu_traffic = {}
-        if (alg.dim, E, C, cin) == (3, 53976, 32, 38):
-            ncu_traffic = {1: 153.9e6, 2: 177.6e6, 101: 392.3e6, 102: 198.5e6, 104: 134.9e6, 108: 79.2e6, 116: 170.1e6, 132: 143.7e6, 164: 18.3e6}
-        table = []
-        for name, is_bwd, mask, nbytes, tflops in stages:
+    h = d["h"].detach().requires_grad_()
+    na = d["node_attr"]
+    ea = d.get("edge_attr")
+    ea = PairedNodeAttr(na) if ea is None else ea
+    fork = os.environ.get("CSMPN_TC_FORK")
+    os.environ["CSMPN_TC_FORK"] = "0"  # single-stream eager pass: the recorded descriptors carry stage_mask 0
+    _RECORDER = rec = []
+    try:
+        y = layer(h, graph, ea, na)
+        torch.autograd.grad(y, [h] + list(layer.parameters()), d["cot"])
+        torch.cuda.synchronize()
+    finally:
+        _RECORDER = None
+        if fork is None:
+            os.environ.pop("CSMPN_TC_FORK", None)
+        else:
+            os.environ["CSMPN_TC_FORK"] = fork
+    table = []
+    for call in rec:
+        desc, g, ws, dim = call["desc"], call["grads"], call["ws"], call["dim"]
+        cin = desc.c0 + desc.c1 + desc.c2
+        where = "%s block, c_in=%d, C=%d, %d rows" % ("per-pair" if desc.rows == graph.n_pairs else "per-simplex", cin, desc.c, desc.rows)
+        for cls, what, mask, nbytes, tflops in _kernel_stages(desc, g, B):
             desc.stage_mask = mask
-            if is_bwd:
-                fn = lambda: check(lib().csmpn_block_bwd(alg.dim, ctypes.byref(desc), ctypes.byref(g), ptr(ws), ws.numel(), s), "bwd")
+            if g is None:
+                fn = lambda: check(lib().csmpn_block_fwd(dim, ctypes.byref(desc), s), "fwd")
             else:
-                fn = lambda: check(lib().csmpn_block_fwd(alg.dim, ctypes.byref(desc), s), "fwd")
+                fn = lambda: check(lib().csmpn_block_bwd(dim, ctypes.byref(desc), ctypes.byref(g), ptr(ws), ws.numel(), s), "bwd")
             t = _time_call(fn, flush, iters)
-            table.append({"kernel": name, "launch_ms": t * 1e3, "algorithmic_bytes": nbytes, "hbm_gbs": nbytes / t / 1e9,
-                          "traffic": ncu_traffic.get(100 * is_bwd + mask),
-                          "hbm_frac": nbytes / t / 1e9 / hbm_peak, "tensor_tflops_tf32x3": tflops / t / 1e12})
+            table.append({"class": cls, "kernel": what, "block": where, "launch_ms": t * 1e3, "algorithmic_bytes": nbytes,
+                          "hbm_gbs": nbytes / t / 1e9, "hbm_frac": nbytes / t / 1e9 / hbm_peak,
+                          "tensor_tflops_tf32x3": tflops / t / 1e12})
         desc.stage_mask = 0
-        t_fwd = _time_call(lambda: check(lib().csmpn_block_fwd(alg.dim, ctypes.byref(desc), s), "fwd"), flush, iters)
-        t_bwd = _time_call(lambda: check(lib().csmpn_block_bwd(alg.dim, ctypes.byref(desc), ctypes.byref(g), ptr(ws), ws.numel(), s), "bwd"), flush, iters)
-        dom = max(table, key=lambda r: r["launch_ms"])
-        return {
-            "bound": "hbm", "achieved": dom["hbm_gbs"], "peak": hbm_peak, "unit": "GB/s", "frac": dom["hbm_frac"], "traffic": dom["traffic"],
-            "peak_source": peak_src, "kernel": dom["kernel"], "launch_ms": dom["launch_ms"],
-            "algorithmic_bytes_per_launch": dom["algorithmic_bytes"], "rows_per_launch": E, "engine": "tcgen05 (3xTF32, TMEM accumulators)",
-            "block": {"what": "first edge block (c_in=%d, C=%d, %d pairs), all kernels of the call" % (cin, C, E),
-                      "fwd_ms": t_fwd * 1e3, "bwd_ms": t_bwd * 1e3,
-                      "fused_algorithmic_bytes_fwd_bwd": 4 * B * E * (2 * c0 + c1 + 4 * C) + 4 * B * E * (4 * C + 2 * c0 + c1 + cin) + 24 * E,
-                      "fp32_equiv_tflops_fwd": E * (fl_lin + 3 * B * B * C + 18 * B * C) / t_fwd / 1e12,
-                      "fp32_equiv_tflops_bwd": E * (2 * fl_lin + 6 * B * B * C + 40 * B * C) / t_bwd / 1e12},
-            "kernels": table,
-        }
-    # ---- FP32 SIMT engine
-    y = torch.empty((E, C, B), device=dev)
-    saves = tuple(torch.empty((E, C, B), device=dev) for _ in range(3))
-    desc = _fill_desc(alg.dim, 1, [h, ea, None], [c0, c1, 0], E, C, params, sg, y, None, saves)
-    check(lib().csmpn_block_fwd(alg.dim, ctypes.byref(desc), s), "block_fwd")
-    gy = torch.randn_like(y)
-    gx = torch.empty((E, cin, B), device=dev)
-    g.grad_y, g.grad_x = gy.data_ptr(), gx.data_ptr()
-    ws = workspace(lib().csmpn_block_bwd_workspace(alg.dim, ctypes.byref(desc)), dev)
-    t_fwd = _time_call(lambda: check(lib().csmpn_block_fwd(alg.dim, ctypes.byref(desc), s), "fwd"), flush, iters)
-    t_bwd = _time_call(lambda: check(lib().csmpn_block_bwd(alg.dim, ctypes.byref(desc), ctypes.byref(g), ptr(ws), ws.numel(), s), "bwd"), flush, iters)
-    # algorithmic bytes of the backward launch: read grad_y, o, y1, xr ([E,C,B] each), gather h twice per pair for the
-    # weight gradient (2 x [E,c0,B]) + edge_attr, write grad_x [E,cin,B]; indices 12 B per pair
-    bytes_bwd = 4 * B * E * (4 * C + 2 * c0 + c1 + cin) + 12 * E
-    bytes_fwd = 4 * B * E * (2 * c0 + c1 + 4 * C) + 12 * E
-    flops_bwd = E * (2 * fl_lin + 6 * B * B * C + 40 * B * C)
-    flops_fwd = E * (fl_lin + 3 * B * B * C + 18 * B * C)
+    total = sum(r["launch_ms"] for r in table)
+    classes = {}
+    for r in table:
+        c = classes.setdefault(r["class"], {"launches": 0, "ms": 0.0, "bytes": 0})
+        c["launches"] += 1
+        c["ms"] += r["launch_ms"]
+        c["bytes"] += r["algorithmic_bytes"]
+    for name, c in classes.items():
+        c["share_of_layer_kernel_time"] = c["ms"] / total
+        c["hbm_gbs"] = c["bytes"] / (c["ms"] * 1e-3) / 1e9
+        c["hbm_frac"] = c["hbm_gbs"] / hbm_peak
+        c["traffic"] = None if not traffic else traffic.get(name)
+    dom_name = max(classes, key=lambda k: classes[k]["ms"])
+    dom = classes[dom_name]
     return {
-        "bound": "hbm", "achieved": bytes_bwd / t_bwd / 1e9, "peak": hbm_peak, "unit": "GB/s",
-        "frac": bytes_bwd / t_bwd / 1e9 / hbm_peak, "traffic": None, "peak_source": peak_src,
-        "kernel": "block_bwd_kernel (FP32 SIMT engine, first edge block: gather prologue + 3 transposed GEMMs + 3 weight-gradient GEMMs)",
-        "launch_ms": t_bwd * 1e3, "algorithmic_bytes_per_launch": bytes_bwd, "rows_per_launch": E, "engine": "fp32 simt",
-        "fp32": {"achieved_tflops": flops_bwd / t_bwd / 1e12, "peak_tflops": 74.4, "frac": flops_bwd / t_bwd / 1e12 / 74.4,
-                 "note": "binding roof: FP32 FMA pipe (148 SM x 128 lanes x 2 x 1.965 GHz); ~110 FLOP/B vs ridge 11"},
-        "fwd_kernel": {"launch_ms": t_fwd * 1e3, "hbm_gbs": bytes_fwd / t_fwd / 1e9, "fp32_tflops": flops_fwd / t_fwd / 1e12},
+        "bound": "hbm", "achieved": dom["hbm_gbs"], "peak": hbm_peak, "unit": "GB/s", "frac": dom["hbm_frac"],
+        "traffic": dom["traffic"], "peak_source": peak_src,
+        "kernel": "%s (%d launches per layer step, %.0f %% of the layer's summed kernel time)" % (dom_name, dom["launches"], 100 * dom["share_of_layer_kernel_time"]),
+        "launch_ms": dom["ms"] / dom["launches"], "algorithmic_bytes_per_launch": dom["bytes"] / dom["launches"],
+        "how": "every kernel of one layer step launched alone (csmpn_block_desc.stage_mask) between CUDA events on the launching "
+               "stream, L2 flushed before each launch, mean of %d; dominant = kernel class with the largest time share; achieved = its "
+               "algorithmic bytes / its time over all its launches in the step; traffic = ncu dram bytes of the class per step "
+               "(only when profiles/ holds a capture of this build, else null)" % iters,
+        "classes": classes, "kernels": table, "summed_kernel_ms": total,
     }

@@ -232,6 +232,7 @@ class CSRGraph:
 
 
 _CSR_CACHE: dict = {}
+_CSR_CACHE_SIZE = 8
 
 
 def get_csr(edge_index, n_nodes) -> CSRGraph:
@@ -241,10 +242,12 @@ def get_csr(edge_index, n_nodes) -> CSRGraph:
     key = (edge_index.data_ptr(), tuple(edge_index.shape), edge_index._version, int(n_nodes))
     g = _CSR_CACHE.get(key)
     if g is None:
-        if len(_CSR_CACHE) > 8:
-            _CSR_CACHE.clear()
+        while len(_CSR_CACHE) >= _CSR_CACHE_SIZE:  # least recently used first; holders of a CSRGraph keep theirs alive
+            _CSR_CACHE.pop(next(iter(_CSR_CACHE)))
         g = CSRGraph(edge_index, n_nodes)
-        _CSR_CACHE[key] = g
+    else:
+        _CSR_CACHE.pop(key)
+    _CSR_CACHE[key] = g  # most recently used last
     return g
 
 

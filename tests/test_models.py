@@ -96,8 +96,12 @@ def test_graphed_train_step_equals_eager(gold):
         m.load_state_dict(fx["state_dict"], strict=False)
         g = types.SimpleNamespace(**{k: v.clone().to(dev) for k, v in fx["batch"].items()})
         loc0 = g.loc.clone()
-        opt = torch.optim.Adam(m.parameters(), lr=1e-3)
+        # graphed: capturable fused Adam with a device-tensor learning rate, optimizer step INSIDE the graph
+        opt = (torch.optim.Adam(m.parameters(), lr=torch.tensor(1e-3, device=dev), fused=True, capturable=True) if graphed
+               else torch.optim.Adam(m.parameters(), lr=1e-3))
         step = GraphedDataParallelStep(m, opt, g) if graphed else DataParallelStep(m, opt)
+        if graphed:
+            assert step.captured_optimizer and "Adam" in step.describe()
         if graphed:  # the capture warm-up ran backward passes but no optimizer step: parameters are still the fixture's
             assert all(torch.equal(p.detach().cpu(), fx["state_dict"][n]) for n, p in m.named_parameters())
         losses = []
@@ -157,3 +161,70 @@ def test_md17_model_at_benched_size_matches_reference():
             assert gr is None or float(gr.abs().max()) == 0.0, n
             continue
         assert_close(gr, ref, GRAD_TOL, f"md17@100 grad {n}")
+
+
+@pytest.mark.gpu
+def test_graphed_motion_step_follows_updates(gold):
+    """The motion model REBINDS graph.pos in forward (centring, motion_cssmpnn.py:146): the graphed step must keep reading
+    the tensors it captured and take new input values through update().  Two steps with different positions, graphed vs
+    eager: same losses, same parameters."""
+    from csmpn_b200.train_step import CosineAnnealingLR, DataParallelStep, GraphedDataParallelStep
+
+    dev = torch.device("cuda:0")
+    fx = gold["motion"]
+    pos1 = fx["batch"]["pos"].clone().to(dev)
+    pos2 = (pos1 * 0.5 + 0.25).contiguous()
+    results = []
+    for graphed in (False, True):
+        m = model_class("motion")(**fx["kwargs"]).to(dev)
+        m.load_state_dict(fx["state_dict"], strict=False)
+        g = types.SimpleNamespace(**{k: v.clone().to(dev) for k, v in fx["batch"].items()})
+        if graphed:
+            opt = torch.optim.Adam(m.parameters(), lr=torch.tensor(1e-3, device=dev), fused=True, capturable=True)
+            step = GraphedDataParallelStep(m, opt, g)
+        else:
+            opt = torch.optim.Adam(m.parameters(), lr=1e-3)
+            step = DataParallelStep(m, opt)
+        sched = CosineAnnealingLR(opt, 8, warmup_steps=2, decay_steps=2)
+        losses = []
+        for pos in (pos1, pos2, pos1):
+            if graphed:
+                step.update(pos=pos)
+                loss, _ = step()
+            else:
+                g.pos = pos.clone()
+                loss, _ = step(g)
+            sched.step()
+            losses.append(float(loss.detach()))
+        results.append((losses, [p.detach().clone() for p in m.parameters()]))
+    (l0, p0), (l1, p1) = results
+    assert abs(l0[0] - l0[1]) > 1e-4 * abs(l0[0])  # the update really changed the input
+    for a, b in zip(l0, l1):
+        assert abs(a - b) <= 1e-5 * max(1.0, abs(a)), (l0, l1)
+    for a, b in zip(p0, p1):
+        assert_close(b, a, 2e-4, "motion parameters after 3 scheduled steps")
+
+
+@pytest.mark.gpu
+def test_csr_cache_eviction_does_not_invalidate_a_captured_step(gold):
+    """the captured step holds its own references to the CSR of its batch; running many other batches eagerly
+    between replays (which cycles the identity-keyed CSR cache) must not change what the replay computes."""
+    from csmpn_b200.models.ops import get_csr
+    from csmpn_b200.train_step import GraphedDataParallelStep
+
+    dev = torch.device("cuda:0")
+    fx = gold["md17"]
+    m = model_class("md17")(**fx["kwargs"]).to(dev)
+    m.load_state_dict(fx["state_dict"], strict=False)
+    g = types.SimpleNamespace(**{k: v.clone().to(dev) for k, v in fx["batch"].items()})
+    opt = torch.optim.SGD(m.parameters(), lr=0.0)
+    step = GraphedDataParallelStep(m, opt, g)
+    l0 = float(step()[0])
+    keep = []
+    for k in range(12):  # more distinct edge_index tensors than the cache holds
+        ei = g.edge_index.clone()
+        keep.append(ei)
+        get_csr(ei, g.x_ind.shape[0])
+    torch.cuda.synchronize()
+    l1 = float(step()[0])
+    assert l0 == l1
