@@ -344,12 +344,39 @@ struct GemmArgs {
   const float* addend;  // BPT [n16] or NULL
   float* out;
   int out_bpt;          // 1: BPT [n16]; 0: reference layout [rows, wn, B]
+  // SILU epilogue (the MVSiLU adjoint folded into the dy2 GEMM, so dy2 never leaves the SM): out = dy1
+  const float *y1, *sa, *sb;  // pre-activation (BPT [n16]), gate parameters [C, G]
+  float* partial;             // [grid][C][2G + 1] per-CTA partials of the gradients of sa, sb, b1
+  int C;
 };
 
-template <int DIM>
+// Sum n <= 16 register values over the 32 lanes of a warp with n shuffles (instead of 5 n): in round `step` a lane keeps
+// the half of the values selected by its lane bit and receives the partner's copy of the same half.  Afterwards lane l
+// holds the warp total of value (l & 15), in v[0].
+__device__ __forceinline__ float warp_transpose_reduce16(float (&v)[16], int lane) {
+#pragma unroll
+  for (int step = 8; step >= 1; step >>= 1) {
+    const bool up = (lane & step) != 0;
+#pragma unroll
+    for (int i = 0; i < step; ++i) {
+      const float send = up ? v[i] : v[i + step];
+      const float keep = up ? v[i + step] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, step);
+    }
+  }
+  return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 16);
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+template <int DIM, bool SILU>
 __global__ void __launch_bounds__(kThreads, 1) tc_bgemm_kernel(GemmArgs a) {
   using A = Alg<DIM>;
-  constexpr int B = A::B, G = A::G;
+  constexpr int B = A::B, G = A::G, NPS = 2 * G + 1;  // NPS: per-channel SiLU parameter gradients (sa[G], sb[G], b1)
+  static_assert(2 * NPS <= 18, "two channels' SiLU gradients are reduced as 16 + 2 values");
   extern __shared__ __align__(1024) uint8_t smem[];
   const int tid = threadIdx.x, warp = uniform_warp_idx(), lane = tid & 31;
   const uint32_t img = (uint32_t)a.n16 * a.kmax * 4;
@@ -358,8 +385,25 @@ __global__ void __launch_bounds__(kThreads, 1) tc_bgemm_kernel(GemmArgs a) {
   const int nsets = a.src[1] ? 2 : 1;
   uint64_t* bars = reinterpret_cast<uint64_t*>(wimg + (size_t)nsets * set_bytes);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kPipeBars);
+  float* sa_s = reinterpret_cast<float*>(tmem_slot + 4);  // SILU: [n16][G] gate parameters
+  float* sb_s = sa_s + a.n16 * G;
   Pipe p;
   p.init(smem, bars, B * kPS);
+  if (SILU) {
+    for (int i = tid; i < a.n16 * G; i += kThreads) {
+      sa_s[i] = (i < a.C * G) ? a.sa[i] : 0.f;
+      sb_s[i] = (i < a.C * G) ? a.sb[i] : 0.f;
+    }
+  }
+  // SILU: per-lane accumulators of the parameter gradients of this warp's channel groups (iteration it of the epilogue
+  // loop = channel group (warp >> 2) + 4 it; two channel pairs per group): lane l holds value (l & 15) of the pair's 18
+  // values (index = 9 * (channel & 1) + k) for l < 16, lanes 16 and 17 hold values 16 and 17
+  float acc[4][2];
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+#pragma unroll
+    for (int pr = 0; pr < 2; ++pr) acc[it][pr] = 0.f;
+  }
   for (int s = 0; s < nsets; ++s) stage_weight_images<DIM, true>(wimg + (size_t)s * set_bytes, img, a.w[s], a.wk[s], a.wn, a.n16, a.kmax);
   const int nmax = (512 / B) / 16 * 16;                       // output channels per pass (TMEM columns / blades)
   const int npass = (a.n16 + nmax - 1) / nmax;
@@ -437,6 +481,67 @@ __global__ void __launch_bounds__(kThreads, 1) tc_bgemm_kernel(GemmArgs a) {
             for (int b = 0; b < B; ++b) ad[b] = *reinterpret_cast<const float4*>(a.addend + bpt_off(B, a.n16, tile, b, gc4 + 4, r));
           }
         }
+        if constexpr (SILU) {
+          // MVSiLU adjoint on the dy2 values in registers (cegnn_utils.py:73-83): dy1 replaces dy2 in v; the gate
+          // parameter gradients are summed over the warp's 32 rows here and over tiles / lane quadrants at the end
+          const int it = c4 >> 2;  // (c4 - (warp >> 2)) / 4
+#pragma unroll
+          for (int pr = 0; pr < 2; ++pr) {
+            float2 y1v[B];  // the two channels of this pair (8-byte loads: half the live registers of a float4 per blade)
+#pragma unroll
+            for (int b = 0; b < B; ++b)
+              y1v[b] = *reinterpret_cast<const float2*>(a.y1 + bpt_off(B, a.n16, tile, b, gc4, r) + 2 * pr);
+            float vals[16], t0 = 0.f, t1 = 0.f;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) vals[i] = 0.f;
+#pragma unroll
+            for (int jj = 0; jj < 2; ++jj) {
+              const int j = 2 * pr + jj, ch = gc4 * 4 + j;
+              float y1[B], dy[B], sg[G], inv[G], tg[G], ds[G];
+#pragma unroll
+              for (int b = 0; b < B; ++b) {
+                y1[b] = jj == 0 ? y1v[b].x : y1v[b].y;
+                dy[b] = v[b][j];
+              }
+              const float* sa = sa_s + ch * G;
+              silu_gates<DIM>(y1, sa, sb_s + ch * G, sg, inv);
+#pragma unroll
+              for (int g = 0; g < G; ++g) tg[g] = 0.f;
+#pragma unroll
+              for (int b = 0; b < B; ++b) tg[A::grade_of(b)] = fmaf(dy[b], y1[b], tg[A::grade_of(b)]);
+              const bool ok = row_ok && ch < a.C;
+              float gv[NPS];
+#pragma unroll
+              for (int g = 0; g < G; ++g) {
+                ds[g] = ok ? tg[g] * sg[g] * (1.f - sg[g]) : 0.f;
+                gv[g] = ds[g] * inv[g];
+                gv[G + g] = ds[g];
+              }
+#pragma unroll
+              for (int b = 0; b < B; ++b) {
+                const int g = A::grade_of(b);
+                const float dinv = (g == 0) ? 1.f : 2.f * y1[b];
+                v[b][j] = ok ? fmaf(sg[g], dy[b], ds[g] * sa[g] * dinv) : 0.f;
+              }
+              gv[2 * G] = v[0][j];
+#pragma unroll
+              for (int k = 0; k < NPS; ++k) {
+                const int idx = jj * NPS + k;  // compile-time after unrolling
+                if (idx < 16) vals[idx] = gv[k];
+                else if (idx == 16) t0 = gv[k];
+                else t1 = gv[k];
+              }
+            }
+            const float s16 = warp_transpose_reduce16(vals, lane);
+            t0 = warp_sum(t0);
+            t1 = warp_sum(t1);
+            const float mine = lane < 16 ? s16 : lane == 16 ? t0 : lane == 17 ? t1 : 0.f;
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4) {
+              if (q4 == it) acc[q4][pr] += mine;
+            }
+          }
+        }
         if (a.out_bpt) {
 #pragma unroll
           for (int b = 0; b < B; ++b) {
@@ -471,6 +576,28 @@ __global__ void __launch_bounds__(kThreads, 1) tc_bgemm_kernel(GemmArgs a) {
   fence_before_sync();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tbase, tcols);
+  if constexpr (SILU) {
+    // combine the four lane-quadrant warps of every channel group in a fixed order -> one partial per CTA, in the layout
+    // the MVSiLU-adjoint kernel writes ([C][2G + 1]); the chunk ring is free now (every MMA of this CTA has completed)
+    float* red = reinterpret_cast<float*>(p.lo);  // [16 warps][4 it][2 pairs][18]
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+#pragma unroll
+      for (int pr = 0; pr < 2; ++pr) {
+        float* dst = red + ((warp * 4 + it) * 2 + pr) * 18;
+        if (lane < 18) dst[lane] = acc[it][pr];
+      }
+    }
+    __syncthreads();
+    for (int e = tid; e < a.C * NPS; e += kThreads) {
+      const int ch = e / NPS, k = e - ch * NPS;
+      const int c4 = ch >> 2, j = ch & 3, cg = c4 & 3, it = c4 >> 2, pr = j >> 1, idx = (j & 1) * NPS + k;
+      float sum = 0.f;
+#pragma unroll
+      for (int q4 = 0; q4 < 4; ++q4) sum += red[(((cg * 4 + q4) * 4 + it) * 2 + pr) * 18 + idx];
+      a.partial[((size_t)blockIdx.x * a.C + ch) * NPS + k] = sum;
+    }
+  }
 }
 
 // =====================================================================================================================
@@ -747,7 +874,12 @@ __global__ void __launch_bounds__(256) tc_final_kernel(FinalJobs jobs) {
 template <int DIM>
 size_t gemm_smem(int nsets, int n16, int kmax) {
   constexpr int B = Alg<DIM>::B, G = Alg<DIM>::G;
-  return (size_t)(kRing + 1) * B * kPS + (size_t)nsets * G * 2 * n16 * kmax * 4 + 96;
+  return (size_t)(kRing + 1) * B * kPS + (size_t)nsets * G * 2 * n16 * kmax * 4 + 128 + (size_t)2 * n16 * G * 4;
+}
+// CSMPN_TC_FUSE_SILU=0 keeps the MVSiLU adjoint as its own kernel (tests compare the two paths)
+inline bool fuse_silu_adjoint() {
+  const char* e = getenv("CSMPN_TC_FUSE_SILU");  // read per call: a test toggles it within one process
+  return !(e && e[0] == '0');
 }
 template <int DIM>
 size_t dw_smem(int M, int na4, int cpb) {
@@ -850,15 +982,23 @@ int launch_bwd(const csmpn_block_desc& d, const csmpn_block_grads& g, void* work
   ga.w[0] = d.wl; ga.w[1] = d.wr; ga.wk[0] = ga.wk[1] = C; ga.wn = C;
   ga.n16 = Cp; ga.kmax = Cp;
   ga.addend = ws + p.o_dy2p; ga.out = ws + p.o_dy2; ga.out_bpt = 1;
+  // the MVSiLU adjoint runs in the epilogue of this GEMM (dy2 stays in registers, the kernel writes dy1) unless disabled
+  const bool fuse_silu = fuse_silu_adjoint() && Cp <= 64;
+  if (fuse_silu) {
+    ga.out = ws + p.o_dy1;
+    ga.y1 = d.save_y1; ga.sa = d.sa; ga.sb = d.sb; ga.partial = ws + p.o_p3; ga.C = C;
+  }
   size_t sm = gemm_smem<DIM>(2, ga.n16, ga.kmax);
-  CSMPN_CUDA_TRY(cudaFuncSetAttribute(tc_bgemm_kernel<DIM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
+  CSMPN_CUDA_TRY(cudaFuncSetAttribute(tc_bgemm_kernel<DIM, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
+  CSMPN_CUDA_TRY(cudaFuncSetAttribute(tc_bgemm_kernel<DIM, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
   if (mask & 2) {
-    tc_bgemm_kernel<DIM><<<grid, kThreads, sm, stream>>>(ga);
+    if (fuse_silu) tc_bgemm_kernel<DIM, true><<<grid, kThreads, sm, stream>>>(ga);
+    else tc_bgemm_kernel<DIM, false><<<grid, kThreads, sm, stream>>>(ga);
     CSMPN_LAUNCH_CHECK("tc_bgemm_kernel(dy2)");
   }
   // ---- B3
   e.partial = ws + p.o_p3;
-  if (mask & 4) {
+  if ((mask & 4) && !fuse_silu) {
     const size_t sm3 = (size_t)2 * 2 * B * ew_threads * 4;
     auto run = [&](auto kern) -> int {
       CSMPN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm3));
@@ -879,7 +1019,7 @@ int launch_bwd(const csmpn_block_desc& d, const csmpn_block_grads& g, void* work
     ga.n16 = p.n16; ga.kmax = Cp;
     ga.out = g.grad_x; ga.out_bpt = g.gx_bpt;
     sm = gemm_smem<DIM>(1, ga.n16, ga.kmax);
-    tc_bgemm_kernel<DIM><<<grid, kThreads, sm, stream>>>(ga);
+    tc_bgemm_kernel<DIM, false><<<grid, kThreads, sm, stream>>>(ga);
     CSMPN_LAUNCH_CHECK("tc_bgemm_kernel(grad_x)");
   }
   // ---- weight gradients
@@ -950,9 +1090,10 @@ int launch_bwd(const csmpn_block_desc& d, const csmpn_block_grads& g, void* work
   cjob(ws + p.o_p1, g.g_na, p.grid_ew, NP1, P, G);
   cjob(ws + p.o_p1, g.g_la, p.grid_ew, NP1, P + G, 1);
   cjob(ws + p.o_p1, g.g_bl, p.grid_ew, NP1, P + G + 1, 1);
-  cjob(ws + p.o_p3, g.g_sa, p.grid_ew, NP3, 0, G);
-  cjob(ws + p.o_p3, g.g_sb, p.grid_ew, NP3, G, G);
-  cjob(ws + p.o_p3, d.has_b1 ? g.g_b1 : nullptr, p.grid_ew, NP3, 2 * G, 1);
+  const int parts3 = fuse_silu ? grid : p.grid_ew;  // per-CTA partials of the kernel that ran the MVSiLU adjoint
+  cjob(ws + p.o_p3, g.g_sa, parts3, NP3, 0, G);
+  cjob(ws + p.o_p3, g.g_sb, parts3, NP3, G, G);
+  cjob(ws + p.o_p3, d.has_b1 ? g.g_b1 : nullptr, parts3, NP3, 2 * G, 1);
   fj.count = k;
   int64_t total = 0;
   for (int i = 0; i < k; ++i) total += fj.j[i].n;

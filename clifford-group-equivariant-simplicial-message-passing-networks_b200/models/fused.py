@@ -584,9 +584,11 @@ def _kernel_stages(d: BlockDesc, g, B: int):
                 ("tc_f2", "linear_right/left + normalisation + weighted GP + MVLayerNorm (+residual)", 2, 4 * T + y_out, 3 * rows * 4 * B * C * C)]
     gy = T if g.gy_bpt else ref(C)
     gx = 0 if not g.grad_x else (Tin if g.gx_bpt else ref(cin))
-    return [("tc_b1", "MVLayerNorm / weighted GP / normalisation adjoints", 1, 6 * T + gy, 0),
-            ("tc_bgemm", "dy2 = dy2p + d WL + dxr WR", 2, 4 * T, 3 * rows * 4 * B * C * C),
-            ("tc_b3", "MVSiLU adjoint", 4, 3 * T, 0),
+    fused_silu = os.environ.get("CSMPN_TC_FUSE_SILU", "1") != "0" and cp <= 64
+    mid = ([("tc_bgemm", "dy2 = dy2p + d WL + dxr WR, MVSiLU adjoint in the epilogue -> dy1", 2, 5 * T, 3 * rows * 4 * B * C * C)]
+           if fused_silu else
+           [("tc_bgemm", "dy2 = dy2p + d WL + dxr WR", 2, 4 * T, 3 * rows * 4 * B * C * C), ("tc_b3", "MVSiLU adjoint", 4, 3 * T, 0)])
+    return [("tc_b1", "MVLayerNorm / weighted GP / normalisation adjoints", 1, 6 * T + gy, 0)] + mid + [
             ("tc_bgemm", "grad_x = dy1 W1", 8, T + gx, 3 * rows * 2 * B * C * cin),
             ("tc_dw", "dWL, dWR = [d|dxr]^T y2", 16, 3 * T, 3 * rows * 4 * B * C * C),
             ("tc_dw", "dW1 = dy1^T x0", 32, T + Tin, 3 * rows * 2 * B * C * cin),

@@ -303,3 +303,31 @@ def test_graphed_layer_with_paired_node_attr():
     assert torch.equal(y, yg)
     for a, b in zip(ge, gg):
         assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("case", [CASES[1], CASES[2], CASES[3]], ids=["md17", "nba", "odd_c"])
+def test_silu_adjoint_folded_into_gemm_matches_separate_kernel(case, monkeypatch):
+    """The MVSiLU adjoint runs in the epilogue of the dy2 GEMM (dy2 never leaves the SM; warp-transposed reduction of the
+    gate-parameter gradients); CSMPN_TC_FUSE_SILU=0 keeps it as its own kernel.  Same gradients either way."""
+    name, metric, C, T, ncx, n, e, aggr = case
+    CliffordAlgebra, M = _mods()
+    ralg, params, h, ei, ea, na, cot = _inputs(case)
+    alg = CliffordAlgebra(metric).to(DEV)
+    m = M.EGCL(alg, C, C, C, edge_attr_features=2 * T, node_attr_features=T, aggr=aggr).to(DEV)
+    _load(m, params)
+    names = [k for k, _ in m.named_parameters()]
+    plist = [p for _, p in m.named_parameters()]
+    out = {}
+    from csmpn_b200 import _lib
+
+    for fuse in ("1", "0"):
+        monkeypatch.setenv("CSMPN_TC_FUSE_SILU", fuse)
+        hd = h.to(DEV).requires_grad_()
+        n0 = _lib.lib().csmpn_launch_count()
+        y = m(hd, ei.to(DEV), ea.to(DEV), na.to(DEV))
+        out[fuse] = torch.autograd.grad(y, [hd] + plist, cot.to(DEV))
+        torch.cuda.synchronize()
+        out["launches" + fuse] = _lib.lib().csmpn_launch_count() - n0
+    assert out["launches0"] == out["launches1"] + 4  # one kernel less per block
+    for what, a, b in zip(["gh"] + names, out["1"], out["0"]):
+        assert_close(a, b, 2e-6, f"{name} {what} fused vs separate MVSiLU adjoint")
