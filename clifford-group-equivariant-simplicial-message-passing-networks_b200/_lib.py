@@ -68,6 +68,7 @@ def _declare(lib):
         "csmpn_segment_expand_sorted": (c_int, [P, P, P, P, i64, i64, i32, P]),
         "csmpn_scatter_diff_sorted": (c_int, [P, i64, P, P, P, P, P, i64, i64, i32, P]),
         "csmpn_scatter_rows": (c_int, [P, i64, i64, P, P, i64, i64, P]),
+        "csmpn_add3_rows": (c_int, [P, i64, P, i64, P, i64, P, i64, i64, P]),
         "csmpn_scatter_pair_sorted": (c_int, [P, i64, i64, i64, P, P, P, P, P, i64, i64, P]),
         # simplicial lifting
         "csmpn_lift_count": (c_int, [P, P, P, P, P, P]),

@@ -332,6 +332,19 @@ __global__ void scatter_pair_sorted_kernel(const float* __restrict__ g, int64_t 
   }
 }
 
+// out[r, :] = a[r, :] + b[r, :] + c[r, :] with per-operand leading dimensions (b / c may be column slices of wider rows)
+__global__ void add3_rows_kernel(const float* __restrict__ a, int64_t lda, const float* __restrict__ b, int64_t ldb,
+                                 const float* __restrict__ c, int64_t ldc, float* __restrict__ out, int64_t n_rows, int64_t width) {
+  const int64_t vpr = width / 4, total = n_rows * vpr;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = idx / vpr, v = idx - r * vpr;
+    const float4 x = *(reinterpret_cast<const float4*>(a + r * lda) + v);
+    const float4 y = *(reinterpret_cast<const float4*>(b + r * ldb) + v);
+    const float4 z = *(reinterpret_cast<const float4*>(c + r * ldc) + v);
+    *(reinterpret_cast<float4*>(out + r * width) + v) = make_float4(x.x + y.x + z.x, x.y + y.y + z.y, x.z + y.z + z.z, x.w + y.w + z.w);
+  }
+}
+
 __global__ void scatter_rows_kernel(const float* __restrict__ g, int64_t ld, int64_t col0, const int32_t* __restrict__ eid,
                                     float* __restrict__ out, int64_t n_rows, int64_t width) {
   const int64_t vpr = width / 4, total = n_rows * vpr;
@@ -517,6 +530,20 @@ int csmpn_scatter_pair_sorted(const float* g, int64_t ld, int64_t col_src, int64
   scatter_pair_sorted_kernel<<<grid_for(n_nodes * width / 4, 256), 256, 0, s>>>(g, ld, col_src, col_dst, rowptr_dst, rowptr_src,
                                                                                   perm_src, rank, out, n_nodes, width);
   CSMPN_LAUNCH_CHECK("scatter_pair_sorted");
+  return CSMPN_OK;
+}
+
+int csmpn_add3_rows(const float* a, int64_t lda, const float* b, int64_t ldb, const float* c, int64_t ldc, float* out,
+                    int64_t n_rows, int64_t width, csmpn_stream_t stream) {
+  if (n_rows < 0 || width <= 0 || width % 4 || lda % 4 || ldb % 4 || ldc % 4) return CSMPN_ERR_BAD_ARG;
+  if (n_rows == 0) return CSMPN_OK;
+  if (!a || !b || !c || !out) return CSMPN_ERR_BAD_ARG;
+  if ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(c) |
+       reinterpret_cast<uintptr_t>(out)) & 15)
+    return CSMPN_ERR_BAD_ARG;
+  cudaStream_t s = (cudaStream_t)stream;
+  add3_rows_kernel<<<grid_for(n_rows * width / 4, 256), 256, 0, s>>>(a, lda, b, ldb, c, ldc, out, n_rows, width);
+  CSMPN_LAUNCH_CHECK("add3_rows");
   return CSMPN_OK;
 }
 

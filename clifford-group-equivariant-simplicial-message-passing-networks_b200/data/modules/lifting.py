@@ -43,6 +43,20 @@ class LiftedBatch:
     def num_nodes(self):
         return int(self.x_ind.shape[0])
 
+    @property
+    def vertex_rows(self):
+        """[sum n_vertices] int64: row of every vertex in the collated simplex axis (the vertices of complex c are the
+        first n_c rows of its block).  Device-side arithmetic only, no host sync."""
+        rows = self.__dict__.get("_vertex_rows")
+        if rows is None:
+            nv = self.n_vertices.long()
+            total = int(self.n_vertices_host.sum())
+            first = torch.repeat_interleave(self.node_ptr[:-1], nv, output_size=total)
+            v0 = torch.cumsum(nv, 0) - nv
+            rows = first + torch.arange(total, device=nv.device) - torch.repeat_interleave(v0, nv, output_size=total)
+            self._vertex_rows = rows
+        return rows
+
     def block_sizes(self, c: int, single: bool):
         """pair counts of the six adjacency blocks of complex c (host ints)."""
         n = int(self.n_vertices_host[c])

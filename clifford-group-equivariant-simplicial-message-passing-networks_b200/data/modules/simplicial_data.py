@@ -54,10 +54,12 @@ _VERTEX_FEATURES = {"md17": ("loc", "vel", "charges"), "nba": ("pos", "vel"), "h
 def _pad_vertex_features(feat_list, lb):
     """zero-padded per-simplex features: rows of vertices hold the vertex feature, edge / triangle rows are zero
     (simplicial_data.py:203-215, 224-247)."""
-    x = torch.cat(feat_list, dim=0)
+    x = torch.cat(feat_list, dim=0)          # concatenated where the samples live: ONE host-to-device copy per feature
+    dev = lb.node_types.device
+    x = x.to(dev, non_blocking=True)
     out = x.new_zeros((lb.num_nodes,) + tuple(x.shape[1:]))
-    vmask = lb.node_types == 0
-    out[vmask] = x.to(out.device)
+    # vertex rows of complex c are the first n_c rows of its block: row = node_ptr[c] + local vertex id (no nonzero / sync)
+    out.index_copy_(0, lb.vertex_rows, x)
     return out
 
 
@@ -150,9 +152,9 @@ def _collate(lb, graphs, label):
             if label == "md17" and name == "charges":
                 frames = graphs[0].y.shape[1]
                 feats = [f.unsqueeze(-1).repeat(1, frames).unsqueeze(-1) if f.dim() == 1 else f for f in feats]
-            out[name] = _pad_vertex_features([f.to(dev) for f in feats], lb)
+            out[name] = _pad_vertex_features(feats, lb)
     if all(hasattr(g, "y") and g.y is not None for g in graphs):
-        out.y = torch.cat([g.y.to(dev) for g in graphs], 0)
+        out.y = torch.cat([g.y for g in graphs], 0).to(dev, non_blocking=True)
     if all(hasattr(g, "target") for g in graphs):
         out.target = torch.stack([torch.as_tensor(g.target) for g in graphs]).to(dev)
     return out

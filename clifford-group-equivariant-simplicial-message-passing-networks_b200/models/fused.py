@@ -459,6 +459,33 @@ class SegmentReduceSortedFn(torch.autograd.Function):
         return gm, None, None
 
 
+class FanoutFn(torch.autograd.Function):
+    """h -> (h, h, h) for the three uses of the layer input in EGCL.forward (gather source of the messages, first source of
+    the update, residual); the backward sums the three gradient contributions in ONE kernel (csmpn_add3_rows) instead of
+    two autograd adds plus a copy of the strided slice."""
+
+    @staticmethod
+    def forward(ctx, h):
+        return h.view_as(h), h.view_as(h), h.view_as(h)
+
+    @staticmethod
+    def backward(ctx, g1, g2, g3):
+        gs = [g for g in (g1, g2, g3) if g is not None]
+        if len(gs) == 3 and all(g.dim() == 3 and g.dtype == torch.float32 and g.stride(2) == 1 and g.stride(1) == g.shape[2]
+                                and g.stride(0) % 4 == 0 and g.data_ptr() % 16 == 0 for g in gs):
+            n, width = g1.shape[0], g1.shape[1] * g1.shape[2]
+            out = torch.empty(g1.shape, dtype=torch.float32, device=g1.device)
+            check(lib().csmpn_add3_rows(ptr(g1), g1.stride(0), ptr(g2), g2.stride(0), ptr(g3), g3.stride(0), ptr(out), n, width,
+                                        stream_ptr(g1.device)), "add3_rows")
+            return out
+        if not gs:
+            return None
+        tot = gs[0]
+        for g in gs[1:]:
+            tot = tot + g
+        return tot
+
+
 def _need_grad(*tensors_and_params):
     return torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors_and_params)
 
@@ -537,13 +564,17 @@ def egcl_forward(egcl, h, edge_index, edge_attr=None, node_attr=None):
     csr = ops.get_csr(edge_index, N)
     sg = sorted_graph(csr)
     h = f32c(h)
+    if h.requires_grad and torch.is_grad_enabled() and csr.n_pairs > 0 and egcl.residual:
+        h_msg, h_upd, h_res = FanoutFn.apply(h)
+    else:
+        h_msg = h_upd = h_res = h
     if csr.n_pairs > 0:
-        m = mlp_forward(alg, blocks_e, h, edge_attr.node_attr if pair else edge_attr, None, None, mode=1, sgraph=sg,
+        m = mlp_forward(alg, blocks_e, h_msg, edge_attr.node_attr if pair else edge_attr, None, None, mode=1, sgraph=sg,
                         rows=csr.n_pairs, pair_attr=pair)
         agg = SegmentReduceSortedFn.apply(m.reshape(csr.n_pairs, -1), sg, egcl.aggr == "mean").reshape(N, -1, B)
     else:
         agg = h.new_zeros((N, egcl.out_features, B))
-    return mlp_forward(alg, blocks_n, h, agg, node_attr, h if egcl.residual else None, rows=N)
+    return mlp_forward(alg, blocks_n, h_upd, agg, node_attr, h_res if egcl.residual else None, rows=N)
 
 
 # ------------------------------------------------------------------------------------------------- bench helper

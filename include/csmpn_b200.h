@@ -252,6 +252,12 @@ int csmpn_scatter_diff_sorted(const float* g, int64_t ld, const int32_t* rowptr_
 int csmpn_scatter_pair_sorted(const float* g, int64_t ld, int64_t col_src, int64_t col_dst, const int32_t* rowptr_dst,
                               const int32_t* rowptr_src, const int32_t* perm_src, const int32_t* rank, float* out,
                               int64_t n_nodes, int64_t width, csmpn_stream_t stream);
+/* out[r, 0:width] = a[r, 0:width] + b[r, 0:width] + c[r, 0:width], each operand with its own leading dimension (floats):
+ * the three gradient contributions of the layer input h of EGCL.forward (cegnn_utils.py:254-284: gather source of the
+ * messages, first source of the update, residual) summed in ONE pass instead of two autograd adds and a slice copy.
+ * All pointers 16-byte aligned, width and leading dimensions multiples of 4. */
+int csmpn_add3_rows(const float* a, int64_t lda, const float* b, int64_t ldb, const float* c, int64_t ldc, float* out,
+                    int64_t n_rows, int64_t width, csmpn_stream_t stream);
 /* out[eid[p], 0:width] = g[p, col0 : col0 + width]   (un-permute the gathered extra channels' gradient)        */
 int csmpn_scatter_rows(const float* g, int64_t ld, int64_t col0, const int32_t* eid, float* out, int64_t n_rows,
                        int64_t width, csmpn_stream_t stream);
