@@ -35,6 +35,7 @@ __constant__ uint8_t c_motion_tris[kMotionT][3] = {{6, 7, 8}, {1, 2, 3}, {24, 25
 
 struct LiftWarp {
   uint32_t adj[kMaxV];        // neighbour mask of every vertex
+  uint32_t adj0[kMaxV];       // clique modes with filters: the unfiltered graph (triangle candidates are ITS 3-cliques)
   uint32_t cof[kMaxE];        // per edge (a,b): every x such that {a,b,x} is a triangle of the complex
   uint16_t ebase[kMaxV + 1];  // number of edges whose smaller vertex is < a
   uint16_t tbase[kMaxE + 1];  // number of triangles whose smallest edge (p,q) precedes edge e
@@ -45,6 +46,36 @@ struct LiftWarp {
 
 __device__ __forceinline__ uint32_t bits_above(int v) { return v >= 31 ? 0u : ~((2u << v) - 1u); }  // {v+1 .. 31}
 __device__ __forceinline__ uint32_t bits_below(int v) { return (1u << v) - 1u; }                    // {0 .. v-1}
+
+__device__ __forceinline__ bool clique_like(int mode) { return mode == CSMPN_LIFT_CLIQUE || mode == CSMPN_LIFT_KNN; }
+
+// utils.py:139-148 triangle_area: 0.5 |(v2 - v1) x (v3 - v1)| in fp32 (2-D points are embedded with z = 0).  The reference
+// calls torch.cross without `dim`, which for exactly three triangles picks the wrong axis; this is the per-triangle formula.
+__device__ __forceinline__ float lift_tri_area(const float* P, int D, int a, int b, int c) {
+  float u[3] = {0.f, 0.f, 0.f}, w[3] = {0.f, 0.f, 0.f};
+  for (int k = 0; k < D && k < 3; ++k) {
+    u[k] = __fsub_rn(P[(int64_t)b * D + k], P[(int64_t)a * D + k]);
+    w[k] = __fsub_rn(P[(int64_t)c * D + k], P[(int64_t)a * D + k]);
+  }
+  const float cx = __fsub_rn(__fmul_rn(u[1], w[2]), __fmul_rn(u[2], w[1]));
+  const float cy = __fsub_rn(__fmul_rn(u[2], w[0]), __fmul_rn(u[0], w[2]));
+  const float cz = __fsub_rn(__fmul_rn(u[0], w[1]), __fmul_rn(u[1], w[0]));
+  return 0.5f * sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(cx, cx), __fmul_rn(cy, cy)), __fmul_rn(cz, cz)));
+}
+__device__ __forceinline__ float lift_tri_area_sorted(const float* P, int D, int a, int b, int c) {
+  if (a > b) { const int t = a; a = b; b = t; }
+  if (b > c) { const int t = b; b = c; c = t; }
+  if (a > b) { const int t = a; a = b; b = t; }
+  return lift_tri_area(P, D, a, b, c);
+}
+__device__ __forceinline__ float lift_edge_len(const float* P, int D, int a, int b) {
+  float acc = 0.f;
+  for (int k = 0; k < D; ++k) {
+    const float df = __fsub_rn(P[(int64_t)a * D + k], P[(int64_t)b * D + k]);
+    acc = __fadd_rn(acc, __fmul_rn(df, df));
+  }
+  return sqrtf(acc);
+}
 
 __device__ __forceinline__ int warp_excl_scan(int v, int lane, int* total) {
   int inc = v;
@@ -101,16 +132,69 @@ __device__ void lift_build(LiftWarp& s, const csmpn_lift_desc& d, int c, int lan
       }
     }
     s.adj[lane] = mine;
-  } else if (d.mode == CSMPN_LIFT_CLIQUE) {
+  } else if (clique_like(d.mode)) {
     s.adj[lane] = 0;
     __syncwarp();
-    const int64_t p0 = d.pptr[c], p1 = d.pptr[c + 1];
-    for (int64_t p = p0 + lane; p < p1; p += 32) {
-      const int a = (int)d.pairs[p], b = (int)d.pairs[d.n_pairs + p];
-      if (a != b && a >= 0 && b >= 0 && a < n && b < n) {
-        atomicOr(&s.adj[a], 1u << b);
-        atomicOr(&s.adj[b], 1u << a);
+    if (d.mode == CSMPN_LIFT_CLIQUE) {
+      const int64_t p0 = d.pptr[c], p1 = d.pptr[c + 1];
+      for (int64_t p = p0 + lane; p < p1; p += 32) {
+        const int a = (int)d.pairs[p], b = (int)d.pairs[d.n_pairs + p];
+        if (a != b && a >= 0 && b >= 0 && a < n && b < n) {
+          atomicOr(&s.adj[a], 1u << b);
+          atomicOr(&s.adj[b], 1u << a);
+        }
       }
+    } else if (lane < n) {
+      // knn_graph(points, k) (csmpn/data/md17.py:64, nba.py:48; torch_cluster): every vertex is joined to its k nearest
+      // other vertices, nearest first, ties to the smaller index; the lift only uses the UNDIRECTED edge set
+      // (nx.Graph, utils.py:171-172).  Distances in double over the fp32 coordinates.
+      uint32_t taken = 1u << lane;
+      const int kk = d.knn_k < n - 1 ? d.knn_k : n - 1;
+      for (int t = 0; t < kk; ++t) {
+        double best = 0.0;
+        int bj = -1;
+        for (int j = 0; j < n; ++j) {
+          if (taken >> j & 1u) continue;
+          double acc = 0.0;
+          for (int k = 0; k < d.point_dim; ++k) {
+            const double diff = __dsub_rn((double)d.points[(int64_t)(v0 + lane) * d.point_dim + k],
+                                          (double)d.points[(int64_t)(v0 + j) * d.point_dim + k]);
+            acc = __dadd_rn(acc, __dmul_rn(diff, diff));
+          }
+          const double dist = sqrt(acc);
+          if (bj < 0 || dist < best) { best = dist; bj = j; }
+        }
+        taken |= 1u << bj;
+        atomicOr(&s.adj[lane], 1u << bj);
+        atomicOr(&s.adj[bj], 1u << lane);
+      }
+    }
+    __syncwarp();
+    if (d.use_filters) {
+      // utils.py:181-200: an edge of the graph enters the complex iff its length is <= edge_th OR it is a face of a kept
+      // triangle (SimplexTree.insert adds all faces); a 3-clique of the graph is kept iff its area is <= tri_th
+      const float* P = d.points + (int64_t)v0 * d.point_dim;
+      const uint32_t a0 = lane < n ? s.adj[lane] : 0u;
+      s.adj0[lane] = a0;
+      __syncwarp();
+      uint32_t keep = 0;
+      uint32_t m = a0;
+      while (m) {
+        const int b = __ffs(m) - 1;
+        m &= m - 1;
+        bool k = lift_edge_len(P, d.point_dim, lane, b) <= d.edge_th;
+        if (!k && d.max_dim >= 2) {
+          uint32_t t = a0 & s.adj0[b];
+          while (t && !k) {
+            const int x = __ffs(t) - 1;
+            t &= t - 1;
+            k = lift_tri_area_sorted(P, d.point_dim, lane, b, x) <= d.tri_th;
+          }
+        }
+        if (k) keep |= 1u << b;
+      }
+      __syncwarp();
+      s.adj[lane] = keep;
     }
   } else {  // CSMPN_LIFT_FACETS: two vertices are joined iff some facet holds both
     if (lane < n) {
@@ -152,6 +236,16 @@ __device__ void lift_build(LiftWarp& s, const csmpn_lift_desc& d, int c, int lan
       a = s.ea[e];
       b = s.eb[e];
       cand = s.adj[a] & s.adj[b];
+      if (clique_like(d.mode) && d.use_filters) {  // 3-cliques of the UNFILTERED graph whose area passes tri_th
+        const float* P = d.points + (int64_t)d.vptr[c] * d.point_dim;
+        uint32_t t = s.adj0[a] & s.adj0[b], keep = 0;
+        while (t) {
+          const int x = __ffs(t) - 1;
+          t &= t - 1;
+          if (lift_tri_area_sorted(P, d.point_dim, a, b, x) <= d.tri_th) keep |= 1u << x;
+        }
+        cand = keep;
+      }
       if (d.mode == CSMPN_LIFT_FACETS) {
         uint32_t keep = 0;
         for (int f = d.fptr[c]; f < d.fptr[c + 1]; ++f) {
@@ -184,7 +278,7 @@ __device__ void lift_build(LiftWarp& s, const csmpn_lift_desc& d, int c, int lan
 
 __device__ __forceinline__ int64_t pairs_of(int mode, int n, int n_e, int n_t) {
   int64_t p = 6ll * n_e + 12ll * n_t;
-  if (mode != CSMPN_LIFT_CLIQUE) p += (int64_t)n * (n - 1) - n_e;  // the extra 0_0 pairs of utils.py:90-96
+  if (!clique_like(mode)) p += (int64_t)n * (n - 1) - n_e;  // the extra 0_0 pairs of utils.py:90-96
   return p;
 }
 
@@ -340,7 +434,7 @@ __global__ void __launch_bounds__(32 * kLiftWarps) lift_fill_kernel(csmpn_lift_d
       put_pair(o, pp + pos++, nb + u, nb + lane);
     }
     pp += tot;  // = 2 n_e
-    if (d.mode != CSMPN_LIFT_CLIQUE) {  // ... plus the extra pairs of generate_adjacencies_single (utils.py:90-96)
+    if (!clique_like(d.mode)) {  // ... plus the extra pairs of generate_adjacencies_single (utils.py:90-96)
       const uint32_t up = m0 & bits_above(lane);
       int tot2;
       int q = warp_excl_scan(lane < n ? (n - 1) - __popc(up) : 0, lane, &tot2);
@@ -416,6 +510,10 @@ inline int check_lift_desc(const csmpn_lift_desc* d) {
     case CSMPN_LIFT_CLIQUE:
     case CSMPN_LIFT_MOTION:
       if (!d->pptr || d->n_pairs < 0 || (d->n_pairs > 0 && !d->pairs)) return CSMPN_ERR_BAD_ARG;
+      if (d->use_filters && (d->mode != CSMPN_LIFT_CLIQUE || !d->points || d->point_dim <= 0)) return CSMPN_ERR_BAD_ARG;
+      break;
+    case CSMPN_LIFT_KNN:
+      if (!d->points || d->point_dim <= 0 || d->knn_k < 1) return CSMPN_ERR_BAD_ARG;
       break;
     case CSMPN_LIFT_FACETS:
       if (!d->fptr || !d->facets || d->facet_size < 2 || d->facet_size > kMaxV) return CSMPN_ERR_BAD_ARG;

@@ -872,9 +872,9 @@ __global__ void __launch_bounds__(256) tc_final_kernel(FinalJobs jobs) {
 // =====================================================================================================================
 // host side
 template <int DIM>
-size_t gemm_smem(int nsets, int n16, int kmax) {
+size_t gemm_smem(int nsets, int n16, int kmax, bool silu = false) {
   constexpr int B = Alg<DIM>::B, G = Alg<DIM>::G;
-  return (size_t)(kRing + 1) * B * kPS + (size_t)nsets * G * 2 * n16 * kmax * 4 + 128 + (size_t)2 * n16 * G * 4;
+  return (size_t)(kRing + 1) * B * kPS + (size_t)nsets * G * 2 * n16 * kmax * 4 + 128 + (silu ? (size_t)2 * n16 * G * 4 : 0);
 }
 // CSMPN_TC_FUSE_SILU=0 keeps the MVSiLU adjoint as its own kernel (tests compare the two paths)
 inline bool fuse_silu_adjoint() {
@@ -983,12 +983,12 @@ int launch_bwd(const csmpn_block_desc& d, const csmpn_block_grads& g, void* work
   ga.n16 = Cp; ga.kmax = Cp;
   ga.addend = ws + p.o_dy2p; ga.out = ws + p.o_dy2; ga.out_bpt = 1;
   // the MVSiLU adjoint runs in the epilogue of this GEMM (dy2 stays in registers, the kernel writes dy1) unless disabled
-  const bool fuse_silu = fuse_silu_adjoint() && Cp <= 64;
+  const bool fuse_silu = fuse_silu_adjoint() && Cp <= 64 && gemm_smem<DIM>(2, Cp, Cp, true) <= kSmemMax;
   if (fuse_silu) {
     ga.out = ws + p.o_dy1;
     ga.y1 = d.save_y1; ga.sa = d.sa; ga.sb = d.sb; ga.partial = ws + p.o_p3; ga.C = C;
   }
-  size_t sm = gemm_smem<DIM>(2, ga.n16, ga.kmax);
+  size_t sm = gemm_smem<DIM>(2, ga.n16, ga.kmax, fuse_silu);
   CSMPN_CUDA_TRY(cudaFuncSetAttribute(tc_bgemm_kernel<DIM, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
   CSMPN_CUDA_TRY(cudaFuncSetAttribute(tc_bgemm_kernel<DIM, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
   if (mask & 2) {
@@ -1117,6 +1117,16 @@ int tc_block_bwd(int dim, const csmpn_block_desc* d, const csmpn_block_grads* g,
   if (dim == 2) return tcb::launch_bwd<2>(*d, *g, ws, bytes, stream);
   if (dim == 3) return tcb::launch_bwd<3>(*d, *g, ws, bytes, stream);
   return CSMPN_ERR_UNSUPPORTED;
+}
+// the backward of a block of this shape fits (shared memory / TMEM plans of every backward kernel)
+bool tc_block_bwd_supported(int dim, int c_in, int c) {
+  csmpn_block_desc d;
+  memset(&d, 0, sizeof(d));
+  d.c0 = c_in; d.c = c; d.rows = 128;
+  tcb::BwdPlan p;
+  if (dim == 2) return tcb::make_bwd_plan<2>(d, &p) == CSMPN_OK;
+  if (dim == 3) return tcb::make_bwd_plan<3>(d, &p) == CSMPN_OK;
+  return false;
 }
 int64_t tc_block_bwd_workspace(int dim, const csmpn_block_desc* d) {
   if (dim == 2) return tcb::bwd_ws_bytes<2>(*d);

@@ -592,9 +592,10 @@ int tc_block_fwd(int dim, const csmpn_block_desc* d, cudaStream_t stream) {
   return CSMPN_ERR_UNSUPPORTED;
 }
 void tc_set_debug_buffer(long long* p) { tcb::debug_buffer() = p; }
+bool tc_block_bwd_supported(int dim, int c_in, int c);  // tc_block_bwd.cu
 bool tc_block_supported(int dim, int c_in, int c) {
-  if (dim == 2) return tcb::fwd_supported<2>(c_in, c);
-  if (dim == 3) return tcb::fwd_supported<3>(c_in, c);
+  if (dim == 2) return tcb::fwd_supported<2>(c_in, c) && tc_block_bwd_supported(2, c_in, c);
+  if (dim == 3) return tcb::fwd_supported<3>(c_in, c) && tc_block_bwd_supported(3, c_in, c);
   return false;
 }
 

@@ -13,7 +13,7 @@ import torch
 
 from ..._lib import CsmpnError, check, lib, ptr, require_cuda, stream_ptr
 
-LIFT_RIPS, LIFT_CLIQUE, LIFT_FACETS, LIFT_MOTION = 0, 1, 2, 3
+LIFT_RIPS, LIFT_CLIQUE, LIFT_FACETS, LIFT_MOTION, LIFT_KNN = 0, 1, 2, 3, 4
 MAX_VERTICES = 32
 
 
@@ -24,6 +24,7 @@ class LiftDesc(ctypes.Structure):
         ("max_edge_length", c_double), ("n_pairs", c_int64),
         ("vptr", c_void_p), ("points", c_void_p), ("pairs", c_void_p), ("pptr", c_void_p), ("facets", c_void_p),
         ("fptr", c_void_p),
+        ("knn_k", c_int32), ("use_filters", c_int32), ("edge_th", ctypes.c_float), ("tri_th", ctypes.c_float),
     ]
 
 
@@ -70,9 +71,11 @@ def _i32(t, device):
 
 
 def lift_batch(mode: int, n_vertices, *, points=None, max_edge_length=0.0, pairs=None, pairs_per_complex=None, facets=None,
-               facets_per_complex=None, dim: int = 2, device=None) -> LiftedBatch:
+               facets_per_complex=None, dim: int = 2, device=None, knn_k=None, edge_th=None, tri_th=None) -> LiftedBatch:
     """Lift a batch.  ``n_vertices``: int tensor / list [n_complexes].  mode RIPS: ``points`` [sum n, D] fp32.
     mode CLIQUE / MOTION: ``pairs`` [2, P] int64 local ids concatenated over complexes + ``pairs_per_complex``.
+    mode KNN: CLIQUE whose graph is ``knn_graph(points, knn_k)`` (csmpn/data/md17.py:64), built inside the kernel.
+    CLIQUE / KNN with ``edge_th`` / ``tri_th`` (and ``points``): the length / area filters of utils.py:181-200.
     mode FACETS: ``facets`` [F, k] int64 local ids + ``facets_per_complex``."""
     anchor = points if points is not None else (pairs if pairs is not None else facets)
     if device is None:
@@ -100,6 +103,14 @@ def lift_batch(mode: int, n_vertices, *, points=None, max_edge_length=0.0, pairs
             raise ValueError(f"points must be [sum(n_vertices), D]; got {tuple(pts.shape)} for {int(nv.sum())} vertices")
         d.points, d.point_dim, d.max_edge_length = pts.data_ptr(), pts.shape[1], float(max_edge_length)
         keep.append(pts)
+    elif mode == LIFT_KNN:
+        if points is None or knn_k is None or int(knn_k) < 1:
+            raise ValueError("LIFT_KNN needs points [sum n, D] and knn_k >= 1")
+        pts = points.to(device=device, dtype=torch.float32).contiguous()
+        if pts.dim() != 2 or pts.shape[0] != int(nv.sum()):
+            raise ValueError(f"points must be [sum(n_vertices), D]; got {tuple(pts.shape)} for {int(nv.sum())} vertices")
+        d.points, d.point_dim, d.knn_k = pts.data_ptr(), pts.shape[1], int(knn_k)
+        keep.append(pts)
     elif mode in (LIFT_CLIQUE, LIFT_MOTION):
         pr = pairs.to(device=device, dtype=torch.int64).contiguous()
         if pr.dim() != 2 or pr.shape[0] != 2:
@@ -117,6 +128,18 @@ def lift_batch(mode: int, n_vertices, *, points=None, max_edge_length=0.0, pairs
     else:
         raise ValueError(f"unknown lifting mode {mode}")
 
+    if edge_th is not None or tri_th is not None:
+        if mode not in (LIFT_CLIQUE, LIFT_KNN) or points is None:
+            raise ValueError("edge_th / tri_th filters apply to the clique lifts and need the vertex positions (points)")
+        if mode == LIFT_CLIQUE:
+            pts = points.to(device=device, dtype=torch.float32).contiguous()
+            if pts.dim() != 2 or pts.shape[0] != int(nv.sum()):
+                raise ValueError(f"points must be [sum(n_vertices), D]; got {tuple(pts.shape)}")
+            d.points, d.point_dim = pts.data_ptr(), pts.shape[1]
+            keep.append(pts)
+        d.use_filters = 1
+        d.edge_th = float("inf") if edge_th is None else float(edge_th)
+        d.tri_th = float("inf") if tri_th is None else float(tri_th)
     counts = torch.empty((ncx, 2), dtype=torch.int32, device=device)
     node_ptr = torch.empty(ncx + 1, dtype=torch.int64, device=device)
     pair_ptr = torch.empty(ncx + 1, dtype=torch.int64, device=device)

@@ -7,7 +7,7 @@ from __future__ import annotations
 
 import torch
 
-from .lifting import LIFT_CLIQUE, LIFT_FACETS, LIFT_MOTION, LIFT_RIPS, lift_batch
+from .lifting import LIFT_CLIQUE, LIFT_FACETS, LIFT_KNN, LIFT_MOTION, LIFT_RIPS, lift_batch
 
 
 class Data:
@@ -64,7 +64,10 @@ def _pad_vertex_features(feat_list, lb):
 
 
 class SimplicialTransform:
-    def __init__(self, dim=2, dis: float = 2.0, label=None, edge_th=10000., tri_th=10000., molecule_type=None):
+    def __init__(self, dim=2, dis: float = 2.0, label=None, edge_th=10000., tri_th=10000., molecule_type=None, knn_k=None):
+        # knn_k (extension): build the kNN graph of the samples' first-frame positions on the GPU instead of reading
+        # graph.edge_index (which the reference's dataset computes with torch_cluster on the CPU, data/md17.py:64)
+        self.knn_k = knn_k
         self.dim = dim
         self.dis = dis
         self.label = label
@@ -87,12 +90,18 @@ class SimplicialTransform:
             lb = lift_batch(LIFT_FACETS, nv, facets=torch.cat(fac, 0), facets_per_complex=[f.shape[0] for f in fac],
                             dim=self.dim, device=device)
         elif self.molecule_type == "aspirin":
-            if self.edge_th < 1e4 or self.tri_th < 1e4:
-                raise NotImplementedError("edge_th / tri_th filters below the reference default of 1e4")
             locs = [_loc(g) for g in graphs]
             nv = [l.shape[0] for l in locs]
-            lb = lift_batch(LIFT_CLIQUE, nv, pairs=torch.cat([g.edge_index for g in graphs], 1),
-                            pairs_per_complex=[g.edge_index.shape[1] for g in graphs], device=device)
+            # the length / area filters of simplicial_lift (utils.py:181-200) are no-ops at the shipped 1e4
+            filt = {}
+            if self.edge_th < 1e4 or self.tri_th < 1e4:
+                filt = dict(edge_th=self.edge_th, tri_th=self.tri_th)
+            pts = torch.cat([_first_frame(l) for l in locs], 0) if (filt or self.knn_k) else None
+            if self.knn_k:   # the kNN graph itself is built on the GPU (csmpn/data/md17.py:64): no edge_index needed
+                lb = lift_batch(LIFT_KNN, nv, points=pts, knn_k=self.knn_k, device=device, **filt)
+            else:
+                lb = lift_batch(LIFT_CLIQUE, nv, pairs=torch.cat([g.edge_index for g in graphs], 1),
+                                pairs_per_complex=[g.edge_index.shape[1] for g in graphs], points=pts, device=device, **filt)
         else:
             locs = [_loc(g) for g in graphs]
             nv = [l.shape[0] for l in locs]
@@ -132,6 +141,11 @@ def _loc(g):
         if hasattr(g, name):
             return getattr(g, name)
     raise Exception("Graphs in datasets have to be specified with locations for constructing simplicial complexes.")
+
+
+def _first_frame(loc):
+    """vertex positions used for the filters / the kNN graph: [n, D], the first frame of [n, frames, D]"""
+    return (loc[:, 0] if loc.dim() == 3 else loc).reshape(loc.shape[0], -1).float()
 
 
 def _device_of(g):

@@ -54,13 +54,21 @@ def rips_lift(graph, dim: int, dis: float):
     return x_dict, {k: v for k, v in adj.items() if k in ("0_0", "0_1", "1_1", "1_2")}
 
 
+def triangle_area(vertex1, vertex2, vertex3):
+    """0.5 |(v2 - v1) x (v3 - v1)| per row (utils.py:139-148).  The reference calls ``torch.cross`` without ``dim``, which
+    picks the FIRST axis of size 3 -- the wrong one when exactly three triangles are passed; this is the per-row formula
+    (and what the GPU lifter evaluates)."""
+    return 0.5 * torch.linalg.norm(torch.linalg.cross(vertex2 - vertex1, vertex3 - vertex1, dim=-1), dim=-1)
+
+
 def simplicial_lift(graph, edge_th=10000, tri_th=10000):
     loc = _locations(graph)
-    if edge_th < 1e4 or tri_th < 1e4:
-        # TODO(next row): the edge-length / triangle-area filters of utils.py:183-200 (inactive at the shipped 1e4)
-        raise NotImplementedError("edge_th / tri_th filters below the reference default of 1e4 are not implemented")
     ei = graph.edge_index
-    lb = lift_batch(LIFT_CLIQUE, [loc.shape[0]], pairs=ei, pairs_per_complex=[ei.shape[1]], device=ei.device)
+    filt = {}
+    if edge_th < 1e4 or tri_th < 1e4:  # utils.py:181-200; no-ops at the shipped thresholds
+        pts = (loc[:, 0] if loc.dim() == 3 else loc).reshape(loc.shape[0], -1).float()
+        filt = dict(points=pts, edge_th=edge_th, tri_th=tri_th)
+    lb = lift_batch(LIFT_CLIQUE, [loc.shape[0]], pairs=ei, pairs_per_complex=[ei.shape[1]], device=ei.device, **filt)
     x_dict, adj = split_single(lb, single=False)
     return x_dict, {k: v for k, v in adj.items() if k in ("0_0", "0_1", "1_1", "1_2")}
 

@@ -281,7 +281,10 @@ int csmpn_scatter_rows(const float* g, int64_t ld, int64_t col0, const int32_t* 
  *   mode MOTION  pairs = the skeleton 0-0 pairs of every complex (31 vertices each); 12 edges, 4 triangles and the
  *                96 literal pairs of ManualTransform are appended
  * vptr [n_complexes+1]: first vertex of each complex (vertex counts).  All pointers are device pointers.           */
-enum csmpn_lift_mode { CSMPN_LIFT_RIPS = 0, CSMPN_LIFT_CLIQUE = 1, CSMPN_LIFT_FACETS = 2, CSMPN_LIFT_MOTION = 3 };
+enum csmpn_lift_mode {
+  CSMPN_LIFT_RIPS = 0, CSMPN_LIFT_CLIQUE = 1, CSMPN_LIFT_FACETS = 2, CSMPN_LIFT_MOTION = 3,
+  CSMPN_LIFT_KNN = 4 /* CLIQUE whose graph is knn_graph(points, knn_k) (csmpn/data/md17.py:64, nba.py:48), built in-kernel */
+};
 
 typedef struct csmpn_lift_desc {
   int32_t mode, n_complexes, max_dim, point_dim, facet_size, reserved;
@@ -293,6 +296,11 @@ typedef struct csmpn_lift_desc {
   const int32_t* pptr;
   const int64_t* facets;
   const int32_t* fptr;
+  /* CLIQUE / KNN: the filters of simplicial_lift (utils.py:181-200) over `points` [sum n, point_dim]: a graph edge enters
+   * the complex iff its length <= edge_th or it is a face of a kept triangle; a 3-clique is kept iff its area
+   * (triangle_area, utils.py:139-148) <= tri_th.  use_filters = 0: every edge and every 3-clique (the shipped 1e4). */
+  int32_t knn_k, use_filters;
+  float edge_th, tri_th;
 } csmpn_lift_desc;
 
 /* Pass 1: counts [n_complexes, 2] = (edges, triangles) of every complex; node_ptr / pair_ptr [n_complexes+1] =

@@ -190,26 +190,37 @@ def rips_lift_ref(points, dim, dis):
     return lift_from_tree(st, single=True)
 
 
-def clique_lift_ref(n_vertices, edge_index):
-    """utils.py:151-207 with edge_th = tri_th = 1e4 (no-ops): clique complex (<= triangles) of the kNN graph."""
+def clique_lift_ref(n_vertices, edge_index, loc=None, edge_th=None, tri_th=None):
+    """utils.py:151-207: clique complex (<= triangles) of the kNN graph.  With ``loc`` [n, 3] the filters of
+    utils.py:181-200 apply: a graph edge is inserted iff its length <= edge_th, a 3-clique iff its area
+    (utils.py:139-148, per-triangle formula) <= tri_th -- and SimplexTree.insert adds every face of an inserted
+    triangle, so an edge longer than edge_th still enters through a kept triangle.  Without ``loc``: the shipped
+    thresholds of 1e4, i.e. no filtering."""
     nbr = [set() for _ in range(n_vertices)]
     for a, b in edge_index.t().tolist():
         if a != b:
             nbr[a].add(b)
             nbr[b].add(a)
+
+    def length(a, b):
+        return float(torch.norm(loc[a] - loc[b]))
+
+    def area(a, b, c):
+        return float(0.5 * torch.linalg.norm(torch.linalg.cross(loc[b] - loc[a], loc[c] - loc[a])))
+
     st = SimplexTree()
     for v in range(n_vertices):
         st.insert([v])
     for a in range(n_vertices):
         for b in sorted(nbr[a]):
-            if b > a:
+            if b > a and (loc is None or edge_th is None or length(a, b) <= edge_th):
                 st.insert([a, b])
     for a in range(n_vertices):
         for b in sorted(nbr[a]):
             if b <= a:
                 continue
             for c in sorted(nbr[a] & nbr[b]):
-                if c > b:
+                if c > b and (loc is None or tri_th is None or area(a, b, c) <= tri_th):
                     st.insert([a, b, c])
     return lift_from_tree(st, single=False)
 

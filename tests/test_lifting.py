@@ -191,3 +191,89 @@ def test_gpu_transform_api_matches_reference_fixture(gold):
                                y=torch.zeros(31, 3)))
     assert torch.equal(d.edge_index.cpu(), m["edge_index"]) and torch.equal(d.x_ind.cpu(), m["x_ind"])
     assert torch.equal(d.node_types.cpu(), m["node_types"])
+
+
+# ------------------------------------------------------------------------------------------------ filters + kNN
+@pytest.fixture(scope="module")
+def gold_filtered():
+    return load_golden("lifting_filtered.pt")
+
+
+FILTERED = ["md17_21_k4_mid", "md17_21_k5_edges_only", "md17_13_k4_tris_only", "md17_21_k6_tight"]
+
+
+@pytest.mark.parametrize("name", FILTERED)
+def test_oracle_filters_match_reference_fixture(gold_filtered, name):
+    """edge_th / tri_th of the reference's simplicial_lift (utils.py:181-200): the restatement against fixtures made by
+    the reference's own code (tests/golden/make_golden_lift_filtered.py)"""
+    g = gold_filtered[name]
+    x, adj = L.clique_lift_ref(g["points"].shape[0], g["knn_edge_index"], g["points"], g["edge_th"], g["tri_th"])
+    ei, x_ind, nt = L.merge_ref(x, adj)
+    assert torch.equal(ei, g["edge_index"]) and torch.equal(x_ind, g["x_ind"]) and torch.equal(nt, g["node_types"])
+    assert int((nt == 2).sum()) < g["n_cliques"] or g["tri_th"] >= 1e4          # the area filter removed triangles
+    assert int((nt == 1).sum()) <= g["n_graph_edges"]
+
+
+def test_oracle_knn_graph_matches_fixture(gold_filtered):
+    for name in FILTERED:
+        g = gold_filtered[name]
+        assert torch.equal(L.knn_graph(g["points"], g["knn_k"]), g["knn_edge_index"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", FILTERED)
+def test_gpu_lift_filters_and_knn_match_reference_fixture(gold_filtered, name):
+    """GPU lifter with the length / area filters, from the kNN pairs (LIFT_CLIQUE) and with the kNN graph built in the
+    kernel (LIFT_KNN): bit-exact to the reference fixture"""
+    from csmpn_b200.data.modules import lifting as G
+
+    dev = torch.device("cuda:0")
+    g = gold_filtered[name]
+    n = g["points"].shape[0]
+    ei = g["knn_edge_index"].to(dev)
+    a = G.lift_batch(G.LIFT_CLIQUE, [n], pairs=ei, pairs_per_complex=[ei.shape[1]], points=g["points"].to(dev),
+                     edge_th=g["edge_th"], tri_th=g["tri_th"])
+    b = G.lift_batch(G.LIFT_KNN, [n], points=g["points"].to(dev), knn_k=g["knn_k"], edge_th=g["edge_th"], tri_th=g["tri_th"])
+    for lb in (a, b):
+        assert torch.equal(lb.edge_index.cpu(), g["edge_index"])
+        assert torch.equal(lb.x_ind.cpu(), g["x_ind"]) and torch.equal(lb.node_types.cpu(), g["node_types"])
+
+
+@pytest.mark.gpu
+def test_gpu_knn_lift_batched_equals_pairs_lift(gold):
+    """a ragged batch: LIFT_KNN (graph built on the GPU) == LIFT_CLIQUE fed with the oracle's knn_graph pairs, and the
+    SimplicialTransform API (knn_k=...) gives the same collated batch as the edge_index path"""
+    from csmpn_b200.data.modules import lifting as G
+    from csmpn_b200.data.modules.simplicial_data import Data, SimplicialTransform
+
+    dev = torch.device("cuda:0")
+    gen = torch.Generator().manual_seed(5)
+    sizes = [21, 13, 5, 32, 2, 21, 9]
+    pts = [torch.randn(n, 3, generator=gen) * 1.5 for n in sizes]
+    pairs = [L.knn_graph(p, 3) for p in pts]
+    a = G.lift_batch(G.LIFT_CLIQUE, sizes, pairs=torch.cat(pairs, 1).to(dev), pairs_per_complex=[p.shape[1] for p in pairs])
+    b = G.lift_batch(G.LIFT_KNN, sizes, points=torch.cat(pts).to(dev), knn_k=3)
+    assert torch.equal(a.edge_index, b.edge_index) and torch.equal(a.x_ind, b.x_ind) and torch.equal(a.node_types, b.node_types)
+    graphs = [Data(loc=p.unsqueeze(1).repeat(1, 2, 1), vel=torch.zeros(p.shape[0], 2, 3), edge_index=e, charges=torch.ones(p.shape[0]),
+                   y=torch.zeros(p.shape[0], 2, 3)) for p, e in zip(pts, pairs)]
+    t1 = SimplicialTransform(dim=2, dis=2.5, label="md17", molecule_type="aspirin").lift(graphs, device=dev)
+    t2 = SimplicialTransform(dim=2, dis=2.5, label="md17", molecule_type="aspirin", knn_k=3).lift(graphs, device=dev)
+    assert torch.equal(t1.edge_index, t2.edge_index) and torch.equal(t1.x_ind, t2.x_ind) and torch.equal(t1.loc, t2.loc)
+
+
+@pytest.mark.gpu
+def test_gpu_transform_api_with_filters(gold_filtered):
+    from csmpn_b200.data.modules import utils as U
+    from csmpn_b200.data.modules.simplicial_data import Data, SimplicialTransform
+
+    dev = torch.device("cuda:0")
+    g = gold_filtered["md17_21_k4_mid"]
+    p = g["points"]
+    graph = Data(loc=p.unsqueeze(1).repeat(1, 3, 1).to(dev), vel=torch.zeros(21, 3, 3, device=dev), init_pos=p.to(dev),
+                 edge_index=g["knn_edge_index"].to(dev), charges=torch.ones(21, device=dev), y=torch.zeros(21, 3, 3, device=dev))
+    d = SimplicialTransform(dim=2, dis=2.5, label="md17", molecule_type="aspirin", edge_th=g["edge_th"], tri_th=g["tri_th"])(graph)
+    assert torch.equal(d.edge_index.cpu(), g["edge_index"]) and torch.equal(d.x_ind.cpu(), g["x_ind"])
+    x_dict, adj = U.simplicial_lift(graph, edge_th=g["edge_th"], tri_th=g["tri_th"])
+    assert x_dict[1].shape[0] == int((g["node_types"] == 1).sum()) and x_dict[2].shape[0] == int((g["node_types"] == 2).sum())
+    a = torch.tensor([[0.0, 0.0, 0.0]]); b = torch.tensor([[1.0, 0.0, 0.0]]); c = torch.tensor([[0.0, 2.0, 0.0]])
+    assert float(U.triangle_area(a, b, c)) == 1.0
