@@ -1059,6 +1059,8 @@ namespace csmpn {
 int tc_block_fwd(int dim, const csmpn_block_desc* d, cudaStream_t stream);
 int tc_block_bwd(int dim, const csmpn_block_desc* d, const csmpn_block_grads* g, void* ws, int64_t bytes, cudaStream_t stream);
 int64_t tc_block_bwd_workspace(int dim, const csmpn_block_desc* d);
+int64_t tc_block_fwd_workspace(int dim, const csmpn_block_desc* d);
+int tc_block_plan(int dim, int c_in, int c);
 bool tc_block_supported(int dim, int c_in, int c);
 void tc_set_debug_buffer(long long* p);
 }  // namespace csmpn
@@ -1068,6 +1070,7 @@ using namespace csmpn;
 extern "C" {
 
 int csmpn_block_tc_supported(int dim, int c_in, int c) { return tc_block_supported(dim, c_in, c) ? 1 : 0; }
+int csmpn_block_tc_plan(int dim, int c_in, int c) { return tc_block_plan(dim, c_in, c); }
 
 // > 0 (= rows per shared-memory tile) if the FP32 SIMT engine keeps the three weight matrices of such a block resident in shared memory for both the forward
 // and the backward kernel; 0 if it would fall back to staging them per GEMM (slower than the unit kernels: callers
@@ -1117,6 +1120,11 @@ int csmpn_block_fwd(int dim, const csmpn_block_desc* desc, csmpn_stream_t stream
     case 5: return launch_block_fwd<5>(*desc, s);
   }
   return CSMPN_ERR_UNSUPPORTED;
+}
+
+int64_t csmpn_block_fwd_workspace(int dim, const csmpn_block_desc* desc) {
+  if (check_desc(dim, desc)) return -1;
+  return desc->engine == 1 ? tc_block_fwd_workspace(dim, desc) : 0;
 }
 
 int64_t csmpn_block_bwd_workspace(int dim, const csmpn_block_desc* desc) {

@@ -160,8 +160,64 @@ struct Pipe {
     mbar_wait(&full_bar[q % kRing], (q / kRing) & 1);
     fence_after_sync();
   }
-  __device__ __forceinline__ uint32_t bytes() const { return (kRing + 1) * half; }
 };
+
+// ---- streamed weights (wide blocks) --------------------------------------------------------------------------------
+// When the weight images of a GEMM do not fit shared memory next to the chunk ring (Cl(3,0) with C >= 64), the weights
+// are streamed WITH the activations: a raw slot holds the activation chunk followed by the "weight unit" of the same K
+// chunk -- for every grade the hi and lo images of [R output rows x 8 input channels] (plane layout with R rows) --
+// brought in by ONE more bulk copy from a pre-split image buffer in global memory (tc_weight_images_kernel), laid out
+// unit after unit in the order the kernel walks them: [pass][K chunk][grade][hi | lo][2][R][4] floats.
+template <int DIM>
+__host__ __device__ constexpr uint32_t wunit_bytes(int rows) { return (uint32_t)Alg<DIM>::G * 2u * (uint32_t)rows * 32u; }
+
+// bulk copies of chunk q: the activation planes (bpt != nullptr) and the weight unit; called by ALL lanes of one warp
+template <int B>
+__device__ __forceinline__ void issue_chunk_load_w(const Pipe& p, int q, const float* bpt, int cp, int64_t tile, int kc,
+                                                   const uint8_t* wsrc, uint32_t wbytes) {
+  const int lane = threadIdx.x & 31;
+  uint64_t* bar = &p.load_bar[q % kRing];
+  if (lane == 0) mbar_arrive_expect_tx(bar, (bpt ? B * 4096u : 0u) + wbytes);
+  __syncwarp();
+  if (bpt && lane < B) bulk_g2s(p.slot(q) + lane * kPS, bpt + bpt_off(B, cp, tile, lane, 2 * kc, 0), 4096u, bar);
+  if (lane == B) bulk_g2s(p.slot(q) + B * kPS, wsrc, wbytes, bar);
+}
+
+// Pre-split weight images in global memory for the streamed mode.  One element per thread.
+//   stack = 1: two weights share every unit along the rows ([0, np): w0 rows of the pass, [np, 2 np): w1 rows), one K range
+//   stack = 0: w1 (if any) is a second K range after w0's chunks (the two-source GEMM of the backward)
+//   trans = 0: w is [n_real][k_real][G] (image row = output channel n, column = input channel k)
+//   trans = 1: w is [k_real][n_real][G]
+struct WPrepArgs {
+  const float *w0, *w1;
+  int stack, trans, n_real, k_real0, k_real1, np, npass, nk0, nk1;
+  float* out;
+};
+template <int DIM>
+__global__ void tc_weight_images_kernel(WPrepArgs a) {
+  constexpr int G = Alg<DIM>::G;
+  const int R = a.stack ? 2 * a.np : a.np;
+  const int nk = a.nk0 + (a.stack ? 0 : a.nk1);
+  const int64_t total = (int64_t)a.npass * nk * G * 2 * R * 8;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(e & 3), r = (int)((e >> 2) % R), cu = (int)((e / (4 * R)) & 1), hl = (int)((e / (8 * R)) & 1);
+    const int g = (int)((e / (16 * R)) % G);
+    const int u = (int)(e / ((int64_t)16 * R * G)), ps = u / nk, kc = u % nk;
+    const int second_k = (!a.stack && kc >= a.nk0) ? 1 : 0;
+    const int k = (second_k ? kc - a.nk0 : kc) * 8 + cu * 4 + c;
+    const int k_real = second_k ? a.k_real1 : a.k_real0;
+    const float* w = a.stack ? (r < a.np ? a.w0 : a.w1) : (second_k ? a.w1 : a.w0);
+    const int n = ps * a.np + (a.stack ? r % a.np : r);
+    float x = 0.f;
+    if (w && n < a.n_real && k < k_real) x = a.trans ? w[((size_t)k * a.n_real + n) * G + g] : w[((size_t)n * k_real + k) * G + g];
+    const float hi = tf32_hi(x);
+    a.out[e] = hl ? x - hi : hi;
+  }
+}
+template <int DIM>
+__host__ inline int64_t weight_image_floats(int stack, int np, int npass, int nk_total) {
+  return (int64_t)npass * nk_total * Alg<DIM>::G * 2 * (stack ? 2 * np : np) * 8;
+}
 
 // bulk copies of chunk q (8 channels kc of a BPT tensor) into its raw slot: called by ALL lanes of one warp
 template <int B>

@@ -14,6 +14,8 @@
 //
 // The elementwise kernels keep one channel per thread for the whole kernel (warp = 4 channels x 8 rows), so every
 // per-channel parameter gradient is a register accumulator and every BPT access of a warp is one 128-byte line.
+#include <vector>
+
 #include "tc_block.cuh"
 
 namespace csmpn {
@@ -80,10 +82,15 @@ __device__ __forceinline__ void read_stage(float* v, const float* st, int lane) 
 
 // CP (channel padding) is a template constant: thread count, BPT blade stride and stage strides become immediates, which
 // removes the 64-bit address arithmetic (17 % of the executed instructions when they were runtime values).
-template <int DIM, int CP>
+// CP channels per CTA (CP * 8 threads); CPT = padded channel count of the tensors.  Wide blocks (CPT > CP = 64) run one
+// CTA per (work unit, 64-channel slab = blockIdx.y); the row statistics of the layer norm need every channel, so each
+// CTA walks phase 1 over all slabs and phase 2 over its own.
+template <int DIM, int CP, int CPT>
 __global__ void __launch_bounds__(CP * 8, CP <= 32 ? 2 : 1) tc_b1_kernel(EwArgs a) {
   using A = Alg<DIM>;
   constexpr int B = A::B, G = A::G, P = A::P, NP = P + G + 2;
+  constexpr int NSLAB = CPT / CP;
+  static_assert(CPT % CP == 0, "wide blocks are whole slabs");
   extern __shared__ float sm[];
   constexpr int nw = CP >> 2, nt = CP * 8;
   float* part1 = sm;                 // [nw][128]
@@ -91,9 +98,10 @@ __global__ void __launch_bounds__(CP * 8, CP <= 32 ? 2 : 1) tc_b1_kernel(EwArgs 
   float* inv_mu_s = part2 + nw * kTile;
   float* dmu_s = inv_mu_s + kTile;
   float* stage = dmu_s + kTile;      // [2 stages][4 tensors][B][nt]
-  const int tid = threadIdx.x, c4 = tid >> 5, lane = tid & 31, j = lane & 3, rr = lane >> 2;
+  const int tid = threadIdx.x, c4l = tid >> 5, lane = tid & 31, j = lane & 3, rr = lane >> 2;
+  const int c4 = (NSLAB > 1 ? (int)blockIdx.y * nw : 0) + c4l;  // channel group of phase 2 (own slab)
   const int ch = c4 * 4 + j, C = a.C;
-  constexpr int Cp = CP;
+  constexpr int Cp = CPT;
   const bool ch_ok = ch < C;
   float la = ch_ok ? a.la[ch] : 0.f, wv[P], sn[G];
 #pragma unroll
@@ -109,20 +117,23 @@ __global__ void __launch_bounds__(CP * 8, CP <= 32 ? 2 : 1) tc_b1_kernel(EwArgs 
   // iteration it of a unit: it < 8 -> phase 1 (row statistics: o, grad_y), it >= 8 -> phase 2 (adjoints: + y2, xr);
   // 8 rows of the unit per iteration
   constexpr int kIt = kTile / 16;
+  constexpr int kIt1 = NSLAB * kIt;  // phase-1 iterations of a unit: 8 rows each, slab after slab
   // warp-private stages: [stage s][tensor][blade][8 rows][4 channels]
-  float* stage_w = stage + (size_t)c4 * (2 * 4 * B * 32);
+  float* stage_w = stage + (size_t)c4l * (2 * 4 * B * 32);
   auto stage_of = [&](int s, int tensor) { return stage_w + (size_t)(s * 4 + tensor) * B * 32; };
   auto prefetch = [&](int64_t unit, int it, int s) {
     const int64_t tile = unit >> 1;
     const int r0 = (int)(unit & 1) * (kTile / 2) + (it & (kIt - 1)) * 8, r = r0 + rr;
+    const int c4x = it < kIt1 ? (it / kIt) * nw + c4l : c4;  // phase 1 walks every slab, phase 2 the own one
+    const int chx = c4x * 4 + j;
     __syncwarp();  // every lane has finished reading this stage (iteration before last)
-    prefetch_mv_bpt<DIM>(stage_of(s, 0), a.o, Cp, tile, c4, r0, lane);
+    prefetch_mv_bpt<DIM>(stage_of(s, 0), a.o, Cp, tile, c4x, r0, lane);
     if (a.gy_bpt) {
-      prefetch_mv_bpt<DIM>(stage_of(s, 1), a.gy, Cp, tile, c4, r0, lane);
+      prefetch_mv_bpt<DIM>(stage_of(s, 1), a.gy, Cp, tile, c4x, r0, lane);
     } else {
       float* dst = stage_of(s, 1) + lane;  // reference layout: every thread fetches its own multivector
-      if (ch_ok && tile * kTile + r < a.rows) {
-        const float* src = a.gy + ((size_t)(tile * kTile + r) * C + ch) * B;
+      if (chx < C && tile * kTile + r < a.rows) {
+        const float* src = a.gy + ((size_t)(tile * kTile + r) * C + chx) * B;
 #pragma unroll
         for (int b = 0; b < B; ++b) cp_async4(dst + b * 32, src + b);
       } else {
@@ -130,7 +141,7 @@ __global__ void __launch_bounds__(CP * 8, CP <= 32 ? 2 : 1) tc_b1_kernel(EwArgs 
         for (int b = 0; b < B; ++b) dst[b * 32] = 0.f;
       }
     }
-    if (it >= kIt) {
+    if (it >= kIt1) {
       prefetch_mv_bpt<DIM>(stage_of(s, 2), a.y2, Cp, tile, c4, r0, lane);
       prefetch_mv_bpt<DIM>(stage_of(s, 3), a.xr, Cp, tile, c4, r0, lane);
     }
@@ -146,9 +157,9 @@ __global__ void __launch_bounds__(CP * 8, CP <= 32 ? 2 : 1) tc_b1_kernel(EwArgs 
     const int rbase = (int)(unit & 1) * (kTile / 2);
     const int64_t row0 = tile * kTile;
 #pragma unroll 1
-    for (int it = 0; it < 2 * kIt; ++it, ++seq) {
+    for (int it = 0; it < kIt1 + kIt; ++it, ++seq) {
       // stream the next iteration (possibly the first one of this CTA's next unit), then wait for the current one
-      if (it + 1 < 2 * kIt) prefetch(unit, it + 1, (seq + 1) & 1);
+      if (it + 1 < kIt1 + kIt) prefetch(unit, it + 1, (seq + 1) & 1);
       else if (unit + gridDim.x < n_units) prefetch(unit + gridDim.x, 0, (seq + 1) & 1);
       else cp_async_commit();
       cp_async_wait<1>();
@@ -156,20 +167,26 @@ __global__ void __launch_bounds__(CP * 8, CP <= 32 ? 2 : 1) tc_b1_kernel(EwArgs 
       const int s = seq & 1;
       const int r = rbase + (it & (kIt - 1)) * 8 + rr;
       const bool ok = ch_ok && row0 + r < a.rows;
-      if (it < kIt) {
-        // ---- phase 1: row statistics of the layer norm
+      if (it < kIt1) {
+        // ---- phase 1: row statistics of the layer norm (channel group of slab it / kIt)
+        const int chx = ((it / kIt) * nw + c4l) * 4 + j;
+        const bool okx = chx < C && row0 + r < a.rows;
+        const float lax = NSLAB > 1 ? (chx < C ? a.la[chx] : 0.f) : la;
         float o[B], dy[B];
         read_stage<DIM>(o, stage_of(s, 0), lane);
         read_stage<DIM>(dy, stage_of(s, 1), lane);
         float dot = 0.f;
 #pragma unroll
         for (int b = 0; b < B; ++b) dot = fmaf(dy[b], o[b], dot);
-        float nu = ok ? fast_sas(mv_sumsq<DIM>(o)) : 0.f;
-        float dt = ok ? la * dot : 0.f;
+        float nu = okx ? fast_sas(mv_sumsq<DIM>(o)) : 0.f;
+        float dt = okx ? lax * dot : 0.f;
         nu += __shfl_xor_sync(0xffffffffu, nu, 1); dt += __shfl_xor_sync(0xffffffffu, dt, 1);
         nu += __shfl_xor_sync(0xffffffffu, nu, 2); dt += __shfl_xor_sync(0xffffffffu, dt, 2);
-        if (j == 0) { part1[c4 * kTile + r] = nu; part2[c4 * kTile + r] = dt; }
-        if (it == kIt - 1) {
+        if (j == 0) {
+          if (NSLAB > 1 && it >= kIt) { part1[c4l * kTile + r] += nu; part2[c4l * kTile + r] += dt; }
+          else { part1[c4l * kTile + r] = nu; part2[c4l * kTile + r] = dt; }
+        }
+        if (it == kIt1 - 1) {
           __syncthreads();
           if (tid < kTile / 2) {
             const int r2 = rbase + tid;
@@ -245,16 +262,17 @@ __global__ void __launch_bounds__(CP * 8, CP <= 32 ? 2 : 1) tc_b1_kernel(EwArgs 
   { const float v = red(g_bl); if (rr == 0 && ch_ok) out[P + G + 1] = v; }
 }
 
-template <int DIM, int CP>
+template <int DIM, int CP, int CPT>
 __global__ void __launch_bounds__(CP * 8, CP <= 32 ? 2 : 1) tc_b3_kernel(EwArgs a) {
   using A = Alg<DIM>;
   constexpr int B = A::B, G = A::G, NP = 2 * G + 1;
   extern __shared__ float sm[];
   constexpr int nt = CP * 8;
   float* stage = sm;  // [2 stages][2 tensors][B][nt]
-  const int tid = threadIdx.x, c4 = tid >> 5, lane = tid & 31, j = lane & 3, rr = lane >> 2;
+  const int tid = threadIdx.x, c4l = tid >> 5, lane = tid & 31, j = lane & 3, rr = lane >> 2;
+  const int c4 = (CPT > CP ? (int)blockIdx.y * (CP >> 2) : 0) + c4l;  // wide blocks: 64-channel slab blockIdx.y
   const int ch = c4 * 4 + j, C = a.C;
-  constexpr int Cp = CP;
+  constexpr int Cp = CPT;
   const bool ch_ok = ch < C;
   float sa[G], sb[G], g_sa[G], g_sb[G], g_b1 = 0.f;
 #pragma unroll
@@ -264,7 +282,7 @@ __global__ void __launch_bounds__(CP * 8, CP <= 32 ? 2 : 1) tc_b3_kernel(EwArgs 
     g_sa[g] = 0.f; g_sb[g] = 0.f;
   }
   constexpr int kIt = kTile / 16;
-  float* stage_w = stage + (size_t)c4 * (2 * 2 * B * 32);
+  float* stage_w = stage + (size_t)c4l * (2 * 2 * B * 32);
   auto stage_of = [&](int s, int tensor) { return stage_w + (size_t)(s * 2 + tensor) * B * 32; };
   auto prefetch = [&](int64_t unit, int it, int s) {
     const int64_t tile = unit >> 1;
@@ -348,6 +366,9 @@ struct GemmArgs {
   const float *y1, *sa, *sb;  // pre-activation (BPT [n16]), gate parameters [C, G]
   float* partial;             // [grid][C][2G + 1] per-CTA partials of the gradients of sa, sb, b1
   int C;
+  // streamed-weights mode (wide blocks): pre-split images in global memory, np = output channels per pass
+  const float* wimg;
+  int np;
 };
 
 // Sum n <= 16 register values over the 32 lanes of a warp with n shuffles (instead of 5 n): in round `step` a lane keeps
@@ -372,23 +393,26 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
-template <int DIM, bool SILU>
+template <int DIM, bool SILU, bool ST>
 __global__ void __launch_bounds__(kThreads, 1) tc_bgemm_kernel(GemmArgs a) {
   using A = Alg<DIM>;
   constexpr int B = A::B, G = A::G, NPS = 2 * G + 1;  // NPS: per-channel SiLU parameter gradients (sa[G], sb[G], b1)
   static_assert(2 * NPS <= 18, "two channels' SiLU gradients are reduced as 16 + 2 values");
   extern __shared__ __align__(1024) uint8_t smem[];
   const int tid = threadIdx.x, warp = uniform_warp_idx(), lane = tid & 31;
-  const uint32_t img = (uint32_t)a.n16 * a.kmax * 4;
-  const uint32_t set_bytes = G * 2 * img;
-  uint8_t* wimg = smem + (kRing + 1) * B * kPS;
+  const int nmax = ST ? a.np : (512 / B) / 16 * 16;            // output channels per pass (TMEM columns / blades)
+  const uint32_t wunit = ST ? wunit_bytes<DIM>(nmax) : 0u;
+  const uint32_t half = B * kPS + wunit;
+  const uint32_t img = ST ? (uint32_t)nmax * 32u : (uint32_t)a.n16 * a.kmax * 4;
+  const uint32_t set_bytes = ST ? 0u : G * 2 * img;
+  uint8_t* wimg = smem + (size_t)kRing * half + B * kPS;
   const int nsets = a.src[1] ? 2 : 1;
   uint64_t* bars = reinterpret_cast<uint64_t*>(wimg + (size_t)nsets * set_bytes);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kPipeBars);
   float* sa_s = reinterpret_cast<float*>(tmem_slot + 4);  // SILU: [n16][G] gate parameters
   float* sb_s = sa_s + a.n16 * G;
   Pipe p;
-  p.init(smem, bars, B * kPS);
+  p.init(smem, bars, half);
   if (SILU) {
     for (int i = tid; i < a.n16 * G; i += kThreads) {
       sa_s[i] = (i < a.C * G) ? a.sa[i] : 0.f;
@@ -404,8 +428,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc_bgemm_kernel(GemmArgs a) {
 #pragma unroll
     for (int pr = 0; pr < 2; ++pr) acc[it][pr] = 0.f;
   }
-  for (int s = 0; s < nsets; ++s) stage_weight_images<DIM, true>(wimg + (size_t)s * set_bytes, img, a.w[s], a.wk[s], a.wn, a.n16, a.kmax);
-  const int nmax = (512 / B) / 16 * 16;                       // output channels per pass (TMEM columns / blades)
+  if (!ST) {
+    for (int s = 0; s < nsets; ++s) stage_weight_images<DIM, true>(wimg + (size_t)s * set_bytes, img, a.w[s], a.wk[s], a.wn, a.n16, a.kmax);
+  }
   const int npass = (a.n16 + nmax - 1) / nmax;
   const uint32_t need = (uint32_t)B * (a.n16 < nmax ? a.n16 : nmax);
   const uint32_t tcols = need <= 32 ? 32 : need <= 64 ? 64 : need <= 128 ? 128 : need <= 256 ? 256 : 512;
@@ -423,7 +448,12 @@ __global__ void __launch_bounds__(kThreads, 1) tc_bgemm_kernel(GemmArgs a) {
     const int64_t tile = (int64_t)blockIdx.x + (int64_t)(qq / per_tile) * gridDim.x;
     const int kc = (qq % per_tile) % nk;
     const int s = kc < a.nk[0] ? 0 : 1;
-    issue_chunk_load<B>(p, qq, a.src[s], a.cp[s], tile, s ? kc - a.nk[0] : kc);
+    if constexpr (ST) {
+      const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(a.wimg) + (size_t)(qq % per_tile) * wunit;
+      issue_chunk_load_w<B>(p, qq, a.src[s], a.cp[s], tile, s ? kc - a.nk[0] : kc, wsrc, wunit);
+    } else {
+      issue_chunk_load<B>(p, qq, a.src[s], a.cp[s], tile, s ? kc - a.nk[0] : kc);
+    }
   };
   int q = 0, loaded = 0;
   if (warp == 0) for (; loaded < kRing - 1 && loaded < total_chunks; ++loaded) issue(loaded);
@@ -444,7 +474,10 @@ __global__ void __launch_bounds__(kThreads, 1) tc_bgemm_kernel(GemmArgs a) {
             issue(loaded);
             ++loaded;
           }
-          {
+          if constexpr (ST) {
+            mbar_wait(&p.load_bar[q % kRing], (q / kRing) & 1);  // the weight unit of this chunk has landed
+            issue_chunk_mma<DIM>(p, q, tbase, Np, kc > 0, p.slot(q) + B * kPS, img, 0, 1, 0, nmax, 0, 0, idesc);
+          } else {
             const int s = kc < a.nk[0] ? 0 : 1;
             issue_chunk_mma<DIM>(p, q, tbase, Np, kc > 0, wimg, img, s, 1, set_bytes, a.n16, s ? kc - a.nk[0] : kc, n0, idesc);
           }
@@ -607,7 +640,9 @@ struct DwArgs {
   int64_t rows;
   int tiles;
   const float *a0, *a1, *bsrc;
-  int cpa, cpb;   // channel paddings (multiples of 16); cpb = channels of B used by this launch (N)
+  int cpa, cpb;   // channels of a0 / a1 and of bsrc used by this launch (multiples of 16)
+  int cpa_total;  // channel padding of the a0 / a1 tensors
+  int a_c4;       // first 4-channel group of a0 / a1 used by this launch
   int cpb_total;  // channel padding of the bsrc tensor
   int b_c4;       // first 4-channel group of bsrc used by this launch
   int M;          // 64 or 128, >= channels of Acat
@@ -698,8 +733,8 @@ __global__ void __launch_bounds__(256, 1) tc_dw_kernel(DwArgs a) {
       uint64_t* bar = &load_bar[lu % kDwLand];
       if (lane == 0) {
         mbar_arrive_expect_tx(bar, (uint32_t)n4 * kLand);
-        bulk_g2s(dst, a.a0 + bpt_off(B, a.cpa, tile, b, 0, 0), (uint32_t)ca4 * kLand, bar);
-        if (a.a1) bulk_g2s(dst + (size_t)ca4 * kLand, a.a1 + bpt_off(B, a.cpa, tile, b, 0, 0), (uint32_t)ca4 * kLand, bar);
+        bulk_g2s(dst, a.a0 + bpt_off(B, a.cpa_total, tile, b, a.a_c4, 0), (uint32_t)ca4 * kLand, bar);
+        if (a.a1) bulk_g2s(dst + (size_t)ca4 * kLand, a.a1 + bpt_off(B, a.cpa_total, tile, b, a.a_c4, 0), (uint32_t)ca4 * kLand, bar);
         bulk_g2s(dst + (size_t)na4 * kLand, a.bsrc + bpt_off(B, a.cpb_total, tile, b, a.b_c4, 0), (uint32_t)nb4 * kLand, bar);
       }
       __syncwarp();
@@ -824,10 +859,11 @@ struct FinalJob {
   int64_t stride;    // floats between partials
   int kind;          // 0: out[i] = sum in[p][i] (n = count);  1: weight gradient from [G][M][N] partials
   int n;             // kind 0: element count; kind 1: c_out * c_in * G
-  int G, M, N, m0, co, ci;  // kind 1: out[(o*ci_tot + i0 + i)*G + g] = sum_p in[p][(g*M + m0 + o)*N + i], i < ci
-  int ci_tot, i0;
+  int G, M, N, m0, co, ci;  // kind 1: out[((o0 + o)*ci_tot + i0 + i)*G + g] = sum_p in[p][(g*M + m0 + o)*N + i], i < ci
+  int ci_tot, i0, o0;
 };
-struct FinalJobs { FinalJob j[14]; int count; };
+constexpr int kFinalJobs = 14;
+struct FinalJobs { FinalJob j[kFinalJobs]; int count; };
 
 // 16 consecutive elements per CTA x 16 partial groups: thread (e, pg) sums partials pg, pg+16, ... in order (independent
 // loads, 64 contiguous bytes per partial row), then the 16 group sums are combined in a fixed order (bit-reproducible).
@@ -848,7 +884,7 @@ __global__ void __launch_bounds__(256) tc_final_kernel(FinalJobs jobs) {
         } else {
           const int i = (int)(idx % jb.ci), o = (int)((idx / jb.ci) % jb.co), g = (int)(idx / ((int64_t)jb.ci * jb.co));
           src = ((size_t)g * jb.M + jb.m0 + o) * jb.N + i;
-          dst = ((size_t)o * jb.ci_tot + jb.i0 + i) * jb.G + g;
+          dst = ((size_t)(jb.o0 + o) * jb.ci_tot + jb.i0 + i) * jb.G + g;
         }
         const float* in = jb.in + src;
 #pragma unroll 4
@@ -894,9 +930,20 @@ struct BwdPlan {
   int M1, M2;  // dW GEMM heights: [d|dxr] and dy1
   int nbw;       // input channels per column pass of the W1 gradient (64 or 32)
   int dw_split;  // the [d|dxr] weight-gradient GEMM does not fit shared memory as one job: run d and dxr separately
+  // wide blocks (the resident plan does not fit): GEMM weights streamed with the K chunks in passes of np output channels;
+  // weight gradients as one launch per (64-channel slab of d / dxr / dy1, 32-channel slab of y2 / x0)
+  int wide, np, n_dwa, n_dwb;
+  int64_t img_dy2, img_gx;  // floats of the pre-split weight images of the two GEMMs
+  size_t dw_part;           // floats of the partials of one slab launch
   // workspace layout (float offsets)
-  size_t o_d, o_dxr, o_dy2p, o_dy2, o_dy1, o_p1, o_p3, o_dwa, o_dwb, total;
+  size_t o_d, o_dxr, o_dy2p, o_dy2, o_dy1, o_p1, o_p3, o_dwa, o_dwb, o_img, total;
 };
+constexpr int kSlabA = 64, kSlabB = 32;  // wide weight-gradient launches: A rows (merged M = 64) x B columns
+template <int DIM>
+size_t gemm_smem_streamed(int np) {
+  constexpr int B = Alg<DIM>::B;
+  return (size_t)kRing * (B * kPS + wunit_bytes<DIM>(np)) + (size_t)B * kPS + 128;
+}
 
 template <int DIM>
 int make_bwd_plan(const csmpn_block_desc& d, BwdPlan* p) {
@@ -905,21 +952,39 @@ int make_bwd_plan(const csmpn_block_desc& d, BwdPlan* p) {
   p->cin = d.c0 + d.c1 + d.c2;
   p->n16 = round_up(p->cin, 16);
   p->tiles = (int)((d.rows + kTile - 1) / kTile);
-  if (2 * B * p->Cp > 512 || p->Cp > 64) return CSMPN_ERR_UNSUPPORTED;
-  p->M1 = 2 * p->Cp <= 64 ? 64 : 128;
-  p->M2 = 64;
-  p->dw_split = 0;
-  if (dw_smem<DIM>(p->M1, 2 * p->Cp / 4, p->Cp) > kSmemMax) { p->dw_split = 1; p->M1 = 64; }
-  if (gemm_smem<DIM>(2, p->Cp, p->Cp) > kSmemMax || gemm_smem<DIM>(1, p->n16, p->Cp) > kSmemMax) return CSMPN_ERR_UNSUPPORTED;
-  // the W1 gradient runs in column passes of <= nbw input channels
-  p->nbw = dw_smem<DIM>(p->M2, p->Cp / 4, p->n16 < 64 ? p->n16 : 64) <= kSmemMax ? 64 : 32;
-  const int nb = p->n16 < p->nbw ? p->n16 : p->nbw;
-  if (dw_smem<DIM>(p->M1, (p->dw_split ? 1 : 2) * p->Cp / 4, p->Cp) > kSmemMax || dw_smem<DIM>(p->M2, p->Cp / 4, nb) > kSmemMax)
-    return CSMPN_ERR_UNSUPPORTED;
-  if (p->n16 > 4 * p->nbw) return CSMPN_ERR_UNSUPPORTED;
+  p->wide = 0; p->np = 0; p->n_dwa = p->n_dwb = 0; p->img_dy2 = p->img_gx = 0; p->dw_part = 0;
   const int sms = sm_count_cached();
   p->grid_ew = 2 * p->tiles < 2 * sms ? (p->tiles > 0 ? 2 * p->tiles : 1) : 2 * sms;
   p->grid_dw = p->tiles < sms ? (p->tiles > 0 ? p->tiles : 1) : sms;
+  bool resident = 2 * B * p->Cp <= 512 && p->Cp <= 64;
+  if (resident) {
+    p->M1 = 2 * p->Cp <= 64 ? 64 : 128;
+    p->M2 = 64;
+    p->dw_split = 0;
+    if (dw_smem<DIM>(p->M1, 2 * p->Cp / 4, p->Cp) > kSmemMax) { p->dw_split = 1; p->M1 = 64; }
+    if (gemm_smem<DIM>(2, p->Cp, p->Cp) > kSmemMax || gemm_smem<DIM>(1, p->n16, p->Cp) > kSmemMax) resident = false;
+  }
+  if (resident) {
+    // the W1 gradient runs in column passes of <= nbw input channels
+    p->nbw = dw_smem<DIM>(p->M2, p->Cp / 4, p->n16 < 64 ? p->n16 : 64) <= kSmemMax ? 64 : 32;
+    const int nb = p->n16 < p->nbw ? p->n16 : p->nbw;
+    if (dw_smem<DIM>(p->M1, (p->dw_split ? 1 : 2) * p->Cp / 4, p->Cp) > kSmemMax || dw_smem<DIM>(p->M2, p->Cp / 4, nb) > kSmemMax ||
+        p->n16 > 4 * p->nbw)
+      resident = false;
+  }
+  if (!resident) {
+    // wide plan: elementwise kernels exist for Cp <= 64 and for whole 64-channel slabs up to 256
+    if (!(p->Cp <= 64 || p->Cp == 128 || p->Cp == 256)) return CSMPN_ERR_UNSUPPORTED;
+    p->wide = 1;
+    p->np = (512 / B) / 16 * 16;
+    if (gemm_smem_streamed<DIM>(p->np) > kSmemMax || dw_smem<DIM>(kSlabA, kSlabA / 4, kSlabB) > kSmemMax) return CSMPN_ERR_UNSUPPORTED;
+    const int sa = (p->Cp + kSlabA - 1) / kSlabA;
+    p->n_dwa = 2 * sa * ((p->Cp + kSlabB - 1) / kSlabB);
+    p->n_dwb = sa * ((p->n16 + kSlabB - 1) / kSlabB);
+    p->dw_part = (size_t)p->grid_dw * 2 * G * kSlabA * kSlabB;
+    p->img_dy2 = weight_image_floats<DIM>(0, p->np, (p->Cp + p->np - 1) / p->np, 2 * (p->Cp / 8));
+    p->img_gx = weight_image_floats<DIM>(0, p->np, (p->n16 + p->np - 1) / p->np, p->Cp / 8);
+  }
   const size_t t = (size_t)bpt_floats(B, d.rows, p->Cp);
   size_t o = 0;
   p->o_d = o; o += t;
@@ -931,8 +996,15 @@ int make_bwd_plan(const csmpn_block_desc& d, BwdPlan* p) {
   p->o_p1 = o; o = al(o + (size_t)p->grid_ew * d.c * (P + G + 2));
   p->o_p3 = o; o = al(o + (size_t)p->grid_ew * d.c * (2 * G + 1));
   // M == 64 launches write two partials per CTA (hi and lo operand halves, see tc_dw_kernel)
-  p->o_dwa = o; o += (size_t)p->grid_dw * (p->M1 == 64 ? 2 : 1) * G * p->M1 * p->Cp * (p->dw_split ? 2 : 1);
-  p->o_dwb = o; o += (size_t)p->grid_dw * 2 * G * p->M2 * p->n16;
+  if (p->wide) {
+    p->o_dwa = o; o += (size_t)p->n_dwa * p->dw_part;
+    p->o_dwb = o; o += (size_t)p->n_dwb * p->dw_part;
+    p->o_img = o; o += (size_t)((p->img_dy2 + 31) / 32 * 32 + (p->img_gx + 31) / 32 * 32);
+  } else {
+    p->o_dwa = o; o += (size_t)p->grid_dw * (p->M1 == 64 ? 2 : 1) * G * p->M1 * p->Cp * (p->dw_split ? 2 : 1);
+    p->o_dwb = o; o += (size_t)p->grid_dw * 2 * G * p->M2 * p->n16;
+    p->o_img = o;
+  }
   p->total = o;
   return CSMPN_OK;
 }
@@ -959,22 +1031,28 @@ int launch_bwd(const csmpn_block_desc& d, const csmpn_block_grads& g, void* work
   e.la = d.la; e.wp = d.wp; e.na = d.na; e.sa = d.sa; e.sb = d.sb;
   e.d = ws + p.o_d; e.dxr = ws + p.o_dxr; e.dy2p = ws + p.o_dy2p; e.dy2 = ws + p.o_dy2; e.dy1 = ws + p.o_dy1;
   e.partial = ws + p.o_p1;
-  const int ew_threads = (Cp / 4) * 32;
+  const int cps = Cp <= 64 ? Cp : 64;           // channels per elementwise CTA (wide blocks: 64-channel slabs)
+  const int nslab = Cp / cps;
+  const int ew_threads = (cps / 4) * 32;
+  const dim3 ew_grid(p.grid_ew, nslab);
   const int mask = d.stage_mask ? d.stage_mask : ~0;
   if (mask & 1) {
-    const size_t sm1 = (size_t)(2 * (Cp / 4) * kTile + 2 * kTile) * 4 + (size_t)2 * 4 * B * ew_threads * 4;
+    const size_t sm1 = (size_t)(2 * (cps / 4) * kTile + 2 * kTile) * 4 + (size_t)2 * 4 * B * ew_threads * 4;
     auto run = [&](auto kern) -> int {
       CSMPN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1));
-      kern<<<p.grid_ew, ew_threads, sm1, stream>>>(e);
+      kern<<<ew_grid, ew_threads, sm1, stream>>>(e);
       return CSMPN_OK;
     };
-    int rc = Cp == 16 ? run(tc_b1_kernel<DIM, 16>) : Cp == 32 ? run(tc_b1_kernel<DIM, 32>) : Cp == 48 ? run(tc_b1_kernel<DIM, 48>)
-                                                                                                      : run(tc_b1_kernel<DIM, 64>);
+    int rc = Cp == 16 ? run(tc_b1_kernel<DIM, 16, 16>) : Cp == 32 ? run(tc_b1_kernel<DIM, 32, 32>)
+             : Cp == 48 ? run(tc_b1_kernel<DIM, 48, 48>) : Cp == 64 ? run(tc_b1_kernel<DIM, 64, 64>)
+             : Cp == 128 ? run(tc_b1_kernel<DIM, 64, 128>) : run(tc_b1_kernel<DIM, 64, 256>);
     if (rc) return rc;
     CSMPN_LAUNCH_CHECK("tc_b1_kernel");
   }
   // ---- dy2 = dy2p + d WL + dxr WR
   const int grid = p.tiles < sm_count_cached() ? p.tiles : sm_count_cached();
+  float* img_dy2 = ws + p.o_img;
+  float* img_gx = img_dy2 + (p.img_dy2 + 31) / 32 * 32;
   GemmArgs ga;
   memset(&ga, 0, sizeof(ga));
   ga.rows = d.rows; ga.tiles = p.tiles;
@@ -983,17 +1061,33 @@ int launch_bwd(const csmpn_block_desc& d, const csmpn_block_grads& g, void* work
   ga.n16 = Cp; ga.kmax = Cp;
   ga.addend = ws + p.o_dy2p; ga.out = ws + p.o_dy2; ga.out_bpt = 1;
   // the MVSiLU adjoint runs in the epilogue of this GEMM (dy2 stays in registers, the kernel writes dy1) unless disabled
-  const bool fuse_silu = fuse_silu_adjoint() && Cp <= 64 && gemm_smem<DIM>(2, Cp, Cp, true) <= kSmemMax;
+  const bool fuse_silu = !p.wide && fuse_silu_adjoint() && Cp <= 64 && gemm_smem<DIM>(2, Cp, Cp, true) <= kSmemMax;
   if (fuse_silu) {
     ga.out = ws + p.o_dy1;
     ga.y1 = d.save_y1; ga.sa = d.sa; ga.sb = d.sb; ga.partial = ws + p.o_p3; ga.C = C;
   }
-  size_t sm = gemm_smem<DIM>(2, ga.n16, ga.kmax, fuse_silu);
-  CSMPN_CUDA_TRY(cudaFuncSetAttribute(tc_bgemm_kernel<DIM, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
-  CSMPN_CUDA_TRY(cudaFuncSetAttribute(tc_bgemm_kernel<DIM, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
+  CSMPN_CUDA_TRY(cudaFuncSetAttribute(tc_bgemm_kernel<DIM, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
+  CSMPN_CUDA_TRY(cudaFuncSetAttribute(tc_bgemm_kernel<DIM, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
+  CSMPN_CUDA_TRY(cudaFuncSetAttribute(tc_bgemm_kernel<DIM, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
+  auto prep = [&](const WPrepArgs& w, int64_t floats) -> int {
+    int64_t blocks = (floats + 255) / 256;
+    if (blocks > 4096) blocks = 4096;
+    tc_weight_images_kernel<DIM><<<(unsigned)blocks, 256, 0, stream>>>(w);
+    CSMPN_LAUNCH_CHECK("tc_weight_images_kernel");
+    return CSMPN_OK;
+  };
   if (mask & 2) {
-    if (fuse_silu) tc_bgemm_kernel<DIM, true><<<grid, kThreads, sm, stream>>>(ga);
-    else tc_bgemm_kernel<DIM, false><<<grid, kThreads, sm, stream>>>(ga);
+    if (p.wide) {
+      WPrepArgs w{d.wl, d.wr, 0, 1, C, C, C, p.np, (Cp + p.np - 1) / p.np, Cp / 8, Cp / 8, img_dy2};
+      int rc = prep(w, p.img_dy2);
+      if (rc) return rc;
+      ga.wimg = img_dy2; ga.np = p.np;
+      tc_bgemm_kernel<DIM, false, true><<<grid, kThreads, gemm_smem_streamed<DIM>(p.np), stream>>>(ga);
+    } else {
+      const size_t sm = gemm_smem<DIM>(2, ga.n16, ga.kmax, fuse_silu);
+      if (fuse_silu) tc_bgemm_kernel<DIM, true, false><<<grid, kThreads, sm, stream>>>(ga);
+      else tc_bgemm_kernel<DIM, false, false><<<grid, kThreads, sm, stream>>>(ga);
+    }
     CSMPN_LAUNCH_CHECK("tc_bgemm_kernel(dy2)");
   }
   // ---- B3
@@ -1002,11 +1096,12 @@ int launch_bwd(const csmpn_block_desc& d, const csmpn_block_grads& g, void* work
     const size_t sm3 = (size_t)2 * 2 * B * ew_threads * 4;
     auto run = [&](auto kern) -> int {
       CSMPN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm3));
-      kern<<<p.grid_ew, ew_threads, sm3, stream>>>(e);
+      kern<<<ew_grid, ew_threads, sm3, stream>>>(e);
       return CSMPN_OK;
     };
-    int rc = Cp == 16 ? run(tc_b3_kernel<DIM, 16>) : Cp == 32 ? run(tc_b3_kernel<DIM, 32>) : Cp == 48 ? run(tc_b3_kernel<DIM, 48>)
-                                                                                                      : run(tc_b3_kernel<DIM, 64>);
+    int rc = Cp == 16 ? run(tc_b3_kernel<DIM, 16, 16>) : Cp == 32 ? run(tc_b3_kernel<DIM, 32, 32>)
+             : Cp == 48 ? run(tc_b3_kernel<DIM, 48, 48>) : Cp == 64 ? run(tc_b3_kernel<DIM, 64, 64>)
+             : Cp == 128 ? run(tc_b3_kernel<DIM, 64, 128>) : run(tc_b3_kernel<DIM, 64, 256>);
     if (rc) return rc;
     CSMPN_LAUNCH_CHECK("tc_b3_kernel");
   }
@@ -1018,8 +1113,15 @@ int launch_bwd(const csmpn_block_desc& d, const csmpn_block_grads& g, void* work
     ga.w[0] = d.w1; ga.wk[0] = C; ga.wn = p.cin;
     ga.n16 = p.n16; ga.kmax = Cp;
     ga.out = g.grad_x; ga.out_bpt = g.gx_bpt;
-    sm = gemm_smem<DIM>(1, ga.n16, ga.kmax);
-    tc_bgemm_kernel<DIM, false><<<grid, kThreads, sm, stream>>>(ga);
+    if (p.wide) {
+      WPrepArgs w{d.w1, nullptr, 0, 1, p.cin, C, 0, p.np, (p.n16 + p.np - 1) / p.np, Cp / 8, 0, img_gx};
+      int rc = prep(w, p.img_gx);
+      if (rc) return rc;
+      ga.wimg = img_gx; ga.np = p.np;
+      tc_bgemm_kernel<DIM, false, true><<<grid, kThreads, gemm_smem_streamed<DIM>(p.np), stream>>>(ga);
+    } else {
+      tc_bgemm_kernel<DIM, false, false><<<grid, kThreads, gemm_smem<DIM>(1, ga.n16, ga.kmax), stream>>>(ga);
+    }
     CSMPN_LAUNCH_CHECK("tc_bgemm_kernel(grad_x)");
   }
   // ---- weight gradients
@@ -1033,57 +1135,100 @@ int launch_bwd(const csmpn_block_desc& d, const csmpn_block_grads& g, void* work
 #endif
   CSMPN_CUDA_TRY(cudaFuncSetAttribute(dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
   da.rows = d.rows; da.tiles = p.tiles;
-  da.a0 = ws + p.o_d; da.a1 = ws + p.o_dxr; da.cpa = Cp; da.bsrc = d.save_y2; da.cpb = Cp; da.cpb_total = Cp; da.b_c4 = 0;
-  da.M = p.M1;
-  da.partial = ws + p.o_dwa;
-  const int pa = p.M1 == 64 ? 2 : 1;  // partials per CTA
-  const size_t dwa_part = (size_t)p.grid_dw * pa * G * p.M1 * Cp;
-  if (!(mask & 16)) {
-  } else if (!p.dw_split) {
-    dw_kernel<<<p.grid_dw, 256, dw_smem<DIM>(da.M, 2 * Cp / 4, Cp), stream>>>(da);
-    CSMPN_LAUNCH_CHECK("tc_dw_kernel(wl,wr)");
+  std::vector<FinalJob> jobs;
+  auto wjob = [&](const float* in, float* out, int parts, int M, int N, int m0, int co, int ci, int ci_tot, int i0, int o0) {
+    if (co <= 0 || ci <= 0 || !out) return;
+    FinalJob jb;
+    memset(&jb, 0, sizeof(jb));
+    jb.in = in; jb.out = out; jb.parts = parts; jb.stride = (int64_t)G * M * N; jb.kind = 1; jb.n = co * ci * G;
+    jb.G = G; jb.M = M; jb.N = N; jb.m0 = m0; jb.co = co; jb.ci = ci; jb.ci_tot = ci_tot; jb.i0 = i0; jb.o0 = o0;
+    jobs.push_back(jb);
+  };
+  auto clampi = [](int v, int hi) { return v < 0 ? 0 : (v > hi ? hi : v); };
+  if (p.wide) {
+    // one launch per (64-channel slab of an A tensor, 32-channel slab of the B tensor); merged M = 64: two partials per CTA
+    const size_t smw = dw_smem<DIM>(kSlabA, kSlabA / 4, kSlabB);
+    da.M = kSlabA; da.a1 = nullptr;
+    int li = 0;
+    for (int which = 0; which < 2; ++which) {  // d -> g_wl, dxr -> g_wr
+      for (int ma = 0; ma < Cp; ma += kSlabA) {
+        const int ca = (Cp - ma) < kSlabA ? (Cp - ma) : kSlabA;
+        for (int nb = 0; nb < Cp; nb += kSlabB, ++li) {
+          float* part = ws + p.o_dwa + (size_t)li * p.dw_part;
+          if (mask & 16) {
+            da.a0 = ws + (which ? p.o_dxr : p.o_d); da.cpa = ca; da.cpa_total = Cp; da.a_c4 = ma / 4;
+            da.bsrc = d.save_y2; da.cpb = kSlabB; da.cpb_total = Cp; da.b_c4 = nb / 4;
+            da.partial = part;
+            dw_kernel<<<p.grid_dw, 256, smw, stream>>>(da);
+            CSMPN_LAUNCH_CHECK("tc_dw_kernel(wl,wr slab)");
+          }
+          wjob(part, which ? g.g_wr : g.g_wl, p.grid_dw * 2, kSlabA, kSlabB, 0, clampi(C - ma, ca), clampi(C - nb, kSlabB), C, nb, ma);
+        }
+      }
+    }
+    li = 0;
+    for (int ma = 0; ma < Cp; ma += kSlabA) {
+      const int ca = (Cp - ma) < kSlabA ? (Cp - ma) : kSlabA;
+      for (int nb = 0; nb < p.n16; nb += kSlabB, ++li) {
+        const int cb = (p.n16 - nb) < kSlabB ? (p.n16 - nb) : kSlabB;
+        float* part = ws + p.o_dwb + (size_t)li * p.dw_part;
+        if (mask & 32) {
+          da.a0 = ws + p.o_dy1; da.cpa = ca; da.cpa_total = Cp; da.a_c4 = ma / 4;
+          da.bsrc = x0; da.cpb = cb; da.cpb_total = p.n16; da.b_c4 = nb / 4;
+          da.partial = part;
+          dw_kernel<<<p.grid_dw, 256, dw_smem<DIM>(kSlabA, kSlabA / 4, cb), stream>>>(da);
+          CSMPN_LAUNCH_CHECK("tc_dw_kernel(w1 slab)");
+        }
+        wjob(part, g.g_w1, p.grid_dw * 2, kSlabA, cb, 0, clampi(C - ma, ca), clampi(p.cin - nb, cb), p.cin, nb, ma);
+      }
+    }
   } else {
-    da.a1 = nullptr;
-    dw_kernel<<<p.grid_dw, 256, dw_smem<DIM>(da.M, Cp / 4, Cp), stream>>>(da);
-    CSMPN_LAUNCH_CHECK("tc_dw_kernel(wl)");
-    da.a0 = ws + p.o_dxr;
-    da.partial = ws + p.o_dwa + dwa_part;
-    dw_kernel<<<p.grid_dw, 256, dw_smem<DIM>(da.M, Cp / 4, Cp), stream>>>(da);
-    CSMPN_LAUNCH_CHECK("tc_dw_kernel(wr)");
-  }
-  for (int i0 = 0; i0 < p.n16 && (mask & 32); i0 += p.nbw) {
-    const int nb = (p.n16 - i0) < p.nbw ? (p.n16 - i0) : p.nbw;
-    da.a0 = ws + p.o_dy1; da.a1 = nullptr; da.cpa = Cp; da.bsrc = x0; da.cpb = nb; da.cpb_total = p.n16; da.b_c4 = i0 / 4;
-    da.M = p.M2;
-    da.partial = ws + p.o_dwb + (size_t)p.grid_dw * 2 * G * p.M2 * i0;
-    dw_kernel<<<p.grid_dw, 256, dw_smem<DIM>(da.M, Cp / 4, nb), stream>>>(da);
-    CSMPN_LAUNCH_CHECK("tc_dw_kernel(w1)");
+    da.a0 = ws + p.o_d; da.a1 = ws + p.o_dxr; da.cpa = Cp; da.cpa_total = Cp; da.a_c4 = 0;
+    da.bsrc = d.save_y2; da.cpb = Cp; da.cpb_total = Cp; da.b_c4 = 0;
+    da.M = p.M1;
+    da.partial = ws + p.o_dwa;
+    const int pa = p.M1 == 64 ? 2 : 1;  // partials per CTA
+    const size_t dwa_part = (size_t)p.grid_dw * pa * G * p.M1 * Cp;
+    if (!(mask & 16)) {
+    } else if (!p.dw_split) {
+      dw_kernel<<<p.grid_dw, 256, dw_smem<DIM>(da.M, 2 * Cp / 4, Cp), stream>>>(da);
+      CSMPN_LAUNCH_CHECK("tc_dw_kernel(wl,wr)");
+    } else {
+      da.a1 = nullptr;
+      dw_kernel<<<p.grid_dw, 256, dw_smem<DIM>(da.M, Cp / 4, Cp), stream>>>(da);
+      CSMPN_LAUNCH_CHECK("tc_dw_kernel(wl)");
+      da.a0 = ws + p.o_dxr;
+      da.partial = ws + p.o_dwa + dwa_part;
+      dw_kernel<<<p.grid_dw, 256, dw_smem<DIM>(da.M, Cp / 4, Cp), stream>>>(da);
+      CSMPN_LAUNCH_CHECK("tc_dw_kernel(wr)");
+    }
+    for (int i0 = 0; i0 < p.n16 && (mask & 32); i0 += p.nbw) {
+      const int nb = (p.n16 - i0) < p.nbw ? (p.n16 - i0) : p.nbw;
+      da.a0 = ws + p.o_dy1; da.a1 = nullptr; da.cpa = Cp; da.cpa_total = Cp; da.a_c4 = 0;
+      da.bsrc = x0; da.cpb = nb; da.cpb_total = p.n16; da.b_c4 = i0 / 4;
+      da.M = p.M2;
+      da.partial = ws + p.o_dwb + (size_t)p.grid_dw * 2 * G * p.M2 * i0;
+      dw_kernel<<<p.grid_dw, 256, dw_smem<DIM>(da.M, Cp / 4, nb), stream>>>(da);
+      CSMPN_LAUNCH_CHECK("tc_dw_kernel(w1)");
+    }
+    wjob(ws + p.o_dwa, g.g_wl, p.grid_dw * pa, p.M1, Cp, 0, C, C, C, 0, 0);
+    if (!p.dw_split) wjob(ws + p.o_dwa, g.g_wr, p.grid_dw * pa, p.M1, Cp, Cp, C, C, C, 0, 0);
+    else wjob(ws + p.o_dwa + dwa_part, g.g_wr, p.grid_dw * pa, p.M1, Cp, 0, C, C, C, 0, 0);
+    for (int i0 = 0; i0 < p.cin; i0 += p.nbw) {
+      const int nb = (p.n16 - i0) < p.nbw ? (p.n16 - i0) : p.nbw;
+      const int ci = (p.cin - i0) < p.nbw ? (p.cin - i0) : p.nbw;
+      wjob(ws + p.o_dwb + (size_t)p.grid_dw * 2 * G * p.M2 * i0, g.g_w1, p.grid_dw * 2, p.M2, nb, 0, C, ci, p.cin, i0, 0);
+    }
   }
   // ---- final reduction
-  FinalJobs fj;
-  memset(&fj, 0, sizeof(fj));
-  int k = 0;
-  auto wjob = [&](const float* in, float* out, int parts, int M, int N, int m0, int co, int ci) {
-    FinalJob& jb = fj.j[k++];
-    jb.in = in; jb.out = out; jb.parts = parts; jb.stride = (int64_t)G * M * N; jb.kind = 1; jb.n = co * ci * G;
-    jb.G = G; jb.M = M; jb.N = N; jb.m0 = m0; jb.co = co; jb.ci = ci; jb.ci_tot = ci; jb.i0 = 0;
-  };
-  wjob(ws + p.o_dwa, g.g_wl, p.grid_dw * pa, p.M1, Cp, 0, C, C);
-  if (!p.dw_split) wjob(ws + p.o_dwa, g.g_wr, p.grid_dw * pa, p.M1, Cp, Cp, C, C);
-  else wjob(ws + p.o_dwa + dwa_part, g.g_wr, p.grid_dw * pa, p.M1, Cp, 0, C, C);
-  for (int i0 = 0; i0 < p.cin; i0 += p.nbw) {
-    const int nb = (p.n16 - i0) < p.nbw ? (p.n16 - i0) : p.nbw;
-    const int ci = (p.cin - i0) < p.nbw ? (p.cin - i0) : p.nbw;
-    wjob(ws + p.o_dwb + (size_t)p.grid_dw * 2 * G * p.M2 * i0, g.g_w1, p.grid_dw * 2, p.M2, nb, 0, C, ci);
-    fj.j[k - 1].ci_tot = p.cin;
-    fj.j[k - 1].i0 = i0;
-  }
-  // small per-channel gradients: partial rows [C][NP]; viewed as kind-1 jobs with G := 1, "N" := NP, one column each
+  // small per-channel gradients: partial rows [C][NP]; viewed as kind-1 jobs with G := 1, "N" := NP, one column range each
   auto cjob = [&](const float* in, float* out, int parts, int NPk, int col0, int width) {
     // out[ch*width + q] = sum_p in[p][ch*NPk + col0 + q]  ==  kind 1 with G = 1, M = C, N = NPk, co = C, ci = width, offset col0
-    FinalJob& jb = fj.j[k++];
+    FinalJob jb;
+    memset(&jb, 0, sizeof(jb));
     jb.in = in + col0; jb.out = out; jb.parts = parts; jb.stride = (int64_t)C * NPk; jb.kind = 1; jb.n = C * width;
-    jb.G = 1; jb.M = C; jb.N = NPk; jb.m0 = 0; jb.co = C; jb.ci = width; jb.ci_tot = width; jb.i0 = 0;
+    jb.G = 1; jb.M = C; jb.N = NPk; jb.m0 = 0; jb.co = C; jb.ci = width; jb.ci_tot = width; jb.i0 = 0; jb.o0 = 0;
+    jobs.push_back(jb);
   };
   const int NP1 = P + G + 2, NP3 = 2 * G + 1;
   cjob(ws + p.o_p1, g.g_wp, p.grid_ew, NP1, 0, P);
@@ -1094,12 +1239,18 @@ int launch_bwd(const csmpn_block_desc& d, const csmpn_block_grads& g, void* work
   cjob(ws + p.o_p3, g.g_sa, parts3, NP3, 0, G);
   cjob(ws + p.o_p3, g.g_sb, parts3, NP3, G, G);
   cjob(ws + p.o_p3, d.has_b1 ? g.g_b1 : nullptr, parts3, NP3, 2 * G, 1);
-  fj.count = k;
-  int64_t total = 0;
-  for (int i = 0; i < k; ++i) total += fj.j[i].n;
   if (mask & 64) {
-    tc_final_kernel<<<(unsigned)((total + 15) / 16), 256, 0, stream>>>(fj);
-    CSMPN_LAUNCH_CHECK("tc_final_kernel");
+    for (size_t j0 = 0; j0 < jobs.size(); j0 += kFinalJobs) {  // wide blocks have more jobs than one launch takes
+      FinalJobs fj;
+      memset(&fj, 0, sizeof(fj));
+      int64_t total = 0;
+      for (size_t k = j0; k < jobs.size() && k < j0 + kFinalJobs; ++k) {
+        fj.j[fj.count++] = jobs[k];
+        total += jobs[k].n;
+      }
+      tc_final_kernel<<<(unsigned)((total + 15) / 16), 256, 0, stream>>>(fj);
+      CSMPN_LAUNCH_CHECK("tc_final_kernel");
+    }
   }
   return CSMPN_OK;
 }
@@ -1127,6 +1278,14 @@ bool tc_block_bwd_supported(int dim, int c_in, int c) {
   if (dim == 2) return tcb::make_bwd_plan<2>(d, &p) == CSMPN_OK;
   if (dim == 3) return tcb::make_bwd_plan<3>(d, &p) == CSMPN_OK;
   return false;
+}
+int tc_block_bwd_wide(int dim, int c_in, int c) {
+  csmpn_block_desc d;
+  memset(&d, 0, sizeof(d));
+  d.c0 = c_in; d.c = c; d.rows = 128;
+  tcb::BwdPlan p;
+  const int st = dim == 2 ? tcb::make_bwd_plan<2>(d, &p) : dim == 3 ? tcb::make_bwd_plan<3>(d, &p) : -1;
+  return st == CSMPN_OK && p.wide;
 }
 int64_t tc_block_bwd_workspace(int dim, const csmpn_block_desc* d) {
   if (dim == 2) return tcb::bwd_ws_bytes<2>(*d);

@@ -31,6 +31,9 @@ struct FwdArgs {
   float* y;
   const float* res;
   int out_bpt, has_b1;
+  // streamed-weights mode (wide blocks): pre-split weight images in global memory and the channels per pass
+  const float *wimg1, *wimg2;
+  int ns1, ns2;
   long long* dbg;  // optional timeline buffer (csmpn_tc_debug_buffer): CTA 0 records clock64() stamps of threads 0 and 64
 };
 #ifdef CSMPN_DEBUG_TOOLS
@@ -170,123 +173,148 @@ __device__ __forceinline__ void zero_chunk_bpt(float* dst, int cp, int64_t tile,
 }
 
 // =====================================================================================================================
-// F1: MVLinear (W1) + bias + MVSiLU
-template <int DIM, bool BPT_IN>
+// F1: MVLinear (W1) + bias + MVSiLU.  ST (streamed weights, wide blocks): the output channels are produced in passes of
+// a.ns1 channels (accumulators = B * ns1 TMEM columns), the K chunks of the input are walked once per pass and every chunk
+// arrives with its weight unit (tc_block.cuh); the resident weight images do not exist.
+template <int DIM, bool BPT_IN, bool ST>
 __global__ void __launch_bounds__(kThreads, 1) tc_f1_kernel(FwdArgs a) {
   using A = Alg<DIM>;
   constexpr int B = A::B, G = A::G;
+  constexpr bool LOADS = BPT_IN || ST;  // the issuer warp runs the copy-ahead logic (activation planes and / or weight units)
   extern __shared__ __align__(1024) uint8_t smem[];
   const int tid = threadIdx.x, warp = uniform_warp_idx(), lane = tid & 31;
   const int C = a.C, Cp = a.Cp, nk = a.kin8 / 8;
-  const uint32_t img = (uint32_t)a.kin8 * Cp * 4;
-  uint8_t* wimg = smem + (kRing + 1) * B * kPS;
-  float* b1_s = reinterpret_cast<float*>(wimg + (size_t)G * 2 * img);
+  const int NS = ST ? a.ns1 : Cp;                     // output channels per pass
+  const int npass = ST ? Cp / NS : 1;
+  const uint32_t wunit = ST ? wunit_bytes<DIM>(NS) : 0u;
+  const uint32_t half = B * kPS + wunit;
+  const uint32_t img = ST ? (uint32_t)NS * 32u : (uint32_t)a.kin8 * Cp * 4;
+  uint8_t* wimg = smem + (size_t)kRing * half + B * kPS;
+  float* b1_s = reinterpret_cast<float*>(wimg + (ST ? 0 : (size_t)G * 2 * img));
   float* sa_s = b1_s + Cp;
   float* sb_s = sa_s + Cp * G;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sb_s + Cp * G);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kPipeBars);
   Pipe p;
-  p.init(smem, bars, B * kPS);
+  p.init(smem, bars, half);
 
-  stage_weight_images<DIM, false>(wimg, img, a.w1, C, a.cin, Cp, a.kin8);
+  if (!ST) stage_weight_images<DIM, false>(wimg, img, a.w1, C, a.cin, Cp, a.kin8);
   for (int i = tid; i < Cp; i += kThreads) b1_s[i] = (i < C && a.has_b1) ? a.b1[i] : 0.f;
   for (int i = tid; i < Cp * G; i += kThreads) {
     sa_s[i] = (i < C * G) ? a.sa[i] : 0.f;
     sb_s[i] = (i < C * G) ? a.sb[i] : 0.f;
   }
-  const uint32_t tcols = (B * Cp <= 32) ? 32 : (B * Cp <= 64) ? 64 : (B * Cp <= 128) ? 128 : (B * Cp <= 256) ? 256 : 512;
+  const uint32_t need = (uint32_t)B * NS;
+  const uint32_t tcols = need <= 32 ? 32 : need <= 64 ? 64 : need <= 128 ? 128 : need <= 256 ? 256 : 512;
   if (warp == 0) tmem_alloc(tmem_slot, tcols);
   fence_async_smem();
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
   const uint32_t tbase = *tmem_slot;
-  const uint32_t idesc = idesc_tf32(kTile, Cp, false, false);
+  const uint32_t idesc = idesc_tf32(kTile, NS, false, false);
   const int my_tiles = (a.tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-  const int total_chunks = my_tiles * nk;
-  auto tile_of = [&](int q) { return (int64_t)blockIdx.x + (int64_t)(q / nk) * gridDim.x; };
+  const int per_tile = npass * nk;
+  const int total_chunks = my_tiles * per_tile;
+  auto tile_of = [&](int q) { return (int64_t)blockIdx.x + (int64_t)(q / per_tile) * gridDim.x; };
+  auto load = [&](int qq) {  // copies of chunk qq of this CTA (all lanes of warp 0)
+    if constexpr (ST) {
+      const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(a.wimg1) + (size_t)(qq % per_tile) * wunit;
+      issue_chunk_load_w<B>(p, qq, BPT_IN ? a.p0 : nullptr, a.in_cp, tile_of(qq), qq % nk, wsrc, wunit);
+    } else {
+      issue_chunk_load<B>(p, qq, a.p0, a.in_cp, tile_of(qq), qq % nk);
+    }
+  };
 
   int q = 0;       // chunk sequence number of this CTA; chunk q lives in raw slot q % kRing
   int loaded = 0;  // warp 0: chunks whose bulk copies have been issued
   float4 gv[BPT_IN ? 1 : ApiItems<DIM>::N];  // gathered items of the NEXT chunk to stage (API-layout input)
   if (!BPT_IN && warp != 0 && total_chunks > 0) gather_chunk_api<DIM>(a, tile_of(0) * kTile, 0, gv);
-  if (BPT_IN && warp == 0) {
-    for (; loaded < kRing - 1 && loaded < total_chunks; ++loaded)
-      issue_chunk_load<B>(p, loaded, a.p0, a.in_cp, tile_of(loaded), loaded % nk);
+  if (LOADS && warp == 0) {
+    for (; loaded < kRing - 1 && loaded < total_chunks; ++loaded) load(loaded);
   }
   for (int t = 0; t < my_tiles; ++t) {
     const int64_t tile = (int64_t)blockIdx.x + (int64_t)t * gridDim.x;
     const int64_t row0 = tile * kTile;
-    for (int kc = 0; kc < nk; ++kc, ++q) {
-      if (warp == 0) {  // issuer
-        p.wait_full(q);
-        if (BPT_IN && loaded == q + kRing - 1 && loaded < total_chunks) {
-          // slot (q-1) % kRing was read by the MMAs of chunk q-1, issued a whole chunk period ago: reload it first, so
-          // that the copy has the issue time of this chunk's MMAs as extra lead
-          if (q >= 1) mbar_wait(&p.slot_bar[(q - 1) % kRing], ((q - 1) / kRing) & 1);
-          issue_chunk_load<B>(p, loaded, a.p0, a.in_cp, tile_of(loaded), loaded % nk);
-          ++loaded;
+    for (int ps = 0; ps < npass; ++ps) {
+      const int n0 = ps * NS;
+      for (int kc = 0; kc < nk; ++kc, ++q) {
+        if (warp == 0) {  // issuer
+          p.wait_full(q);
+          if (LOADS && loaded == q + kRing - 1 && loaded < total_chunks) {
+            // slot (q-1) % kRing was read by the MMAs of chunk q-1, issued a whole chunk period ago: reload it first, so
+            // that the copy has the issue time of this chunk's MMAs as extra lead
+            if (q >= 1) mbar_wait(&p.slot_bar[(q - 1) % kRing], ((q - 1) / kRing) & 1);
+            load(loaded);
+            ++loaded;
+          }
+          if constexpr (ST) {
+            mbar_wait(&p.load_bar[q % kRing], (q / kRing) & 1);  // the weight unit of this chunk has landed
+            issue_chunk_mma<DIM>(p, q, tbase, NS, kc > 0, p.slot(q) + B * kPS, img, 0, 1, 0, NS, 0, 0, idesc);
+          } else {
+            issue_chunk_mma<DIM>(p, q, tbase, Cp, kc > 0, wimg, img, 0, 1, 0, Cp, kc, 0, idesc);
+          }
+        } else if (BPT_IN) {  // converters: split the landed chunk
+          mbar_wait(&p.load_bar[q % kRing], (q / kRing) & 1);
+          split_chunk<B>(p, q);
+        } else {              // converters: gathering producer (wide blocks gather the input rows once per pass)
+          if (q >= kRing) mbar_wait(&p.slot_bar[q % kRing], ((q - kRing) / kRing) & 1);  // MMAs of chunk q-kRing released the slot
+          float* x0 = ps == 0 ? a.save_x0 : nullptr;
+          store_chunk_api<DIM>(p, q, gv, x0, round_up(a.kin8, 16), tile, kc);
+          p.conv_done(q);
+          if (q + 1 < total_chunks) gather_chunk_api<DIM>(a, tile_of(q + 1) * kTile, (q + 1) % nk, gv);
+          if (x0 && kc == nk - 1 && (a.kin8 & 8)) zero_chunk_bpt<B>(x0, round_up(a.kin8, 16), tile, nk);
         }
-        issue_chunk_mma<DIM>(p, q, tbase, Cp, kc > 0, wimg, img, 0, 1, 0, Cp, kc, 0, idesc);
-      } else if (BPT_IN) {  // converters: split the landed chunk
-        mbar_wait(&p.load_bar[q % kRing], (q / kRing) & 1);
-        split_chunk<B>(p, q);
-      } else {              // converters: gathering producer
-        if (q >= kRing) mbar_wait(&p.slot_bar[q % kRing], ((q - kRing) / kRing) & 1);  // MMAs of chunk q-kRing released the slot
-        store_chunk_api<DIM>(p, q, gv, a.save_x0, round_up(a.kin8, 16), tile, kc);
-        p.conv_done(q);
-        if (q + 1 < total_chunks) gather_chunk_api<DIM>(a, tile_of(q + 1) * kTile, (q + 1) % nk, gv);
-        if (a.save_x0 && kc == nk - 1 && (a.kin8 & 8)) zero_chunk_bpt<B>(a.save_x0, round_up(a.kin8, 16), tile, nk);
       }
-    }
-    // ---- epilogue: all MMAs of this tile have completed
-    mbar_wait(&p.slot_bar[(q - 1) % kRing], ((q - 1) / kRing) & 1);
-    fence_after_sync();
-    if (BPT_IN && warp == 0) {  // every slot is free: prefetch the next tile's first chunks under the epilogue
-      for (; loaded < q + kRing && loaded < total_chunks; ++loaded)
-        issue_chunk_load<B>(p, loaded, a.p0, a.in_cp, tile_of(loaded), loaded % nk);
-    }
-    const int r = (warp & 3) * 32 + lane;
-    const bool row_ok = row0 + r < a.rows;
-    for (int c4 = warp >> 2; c4 < (Cp >> 2); c4 += 4) {
-      float v[B][4];
-#pragma unroll
-      for (int b = 0; b < B; ++b) tmem_ld4(tmem_at(tbase, (warp & 3) * 32, b * Cp + c4 * 4), v[b]);
-      tmem_wait_ld();
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int ch = c4 * 4 + j;
-        float y1[B];
-        const bool ok = row_ok && ch < C;
-#pragma unroll
-        for (int b = 0; b < B; ++b) y1[b] = ok ? v[b][j] : 0.f;
-        if (ok) y1[0] += b1_s[ch];
-#pragma unroll
-        for (int b = 0; b < B; ++b) v[b][j] = y1[b];
+      // ---- epilogue of this pass: all its MMAs have completed
+      mbar_wait(&p.slot_bar[(q - 1) % kRing], ((q - 1) / kRing) & 1);
+      fence_after_sync();
+      if (LOADS && warp == 0) {  // every slot is free: prefetch the next chunks under the epilogue
+        for (; loaded < q + kRing && loaded < total_chunks; ++loaded) load(loaded);
       }
-      if (a.save_y1) {
+      const int r = (warp & 3) * 32 + lane;
+      const bool row_ok = row0 + r < a.rows;
+      for (int c4 = warp >> 2; c4 < (NS >> 2); c4 += 4) {
+        const int gc4 = (n0 >> 2) + c4;
+        float v[B][4];
+#pragma unroll
+        for (int b = 0; b < B; ++b) tmem_ld4(tmem_at(tbase, (warp & 3) * 32, b * NS + c4 * 4), v[b]);
+        tmem_wait_ld();
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int ch = gc4 * 4 + j;
+          float y1[B];
+          const bool ok = row_ok && ch < C;
+#pragma unroll
+          for (int b = 0; b < B; ++b) y1[b] = ok ? v[b][j] : 0.f;
+          if (ok) y1[0] += b1_s[ch];
+#pragma unroll
+          for (int b = 0; b < B; ++b) v[b][j] = y1[b];
+        }
+        if (a.save_y1) {
+#pragma unroll
+          for (int b = 0; b < B; ++b)
+            *reinterpret_cast<float4*>(a.save_y1 + bpt_off(B, Cp, tile, b, gc4, r)) = make_float4(v[b][0], v[b][1], v[b][2], v[b][3]);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int ch = gc4 * 4 + j;
+          float y1[B], sg[G], inv[G];
+#pragma unroll
+          for (int b = 0; b < B; ++b) y1[b] = v[b][j];
+          silu_gates<DIM>(y1, sa_s + ch * G, sb_s + ch * G, sg, inv);
+#pragma unroll
+          for (int b = 0; b < B; ++b) v[b][j] = y1[b] * sg[A::grade_of(b)];
+        }
 #pragma unroll
         for (int b = 0; b < B; ++b)
-          *reinterpret_cast<float4*>(a.save_y1 + bpt_off(B, Cp, tile, b, c4, r)) = make_float4(v[b][0], v[b][1], v[b][2], v[b][3]);
+          *reinterpret_cast<float4*>(a.y2 + bpt_off(B, Cp, tile, b, gc4, r)) = make_float4(v[b][0], v[b][1], v[b][2], v[b][3]);
       }
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int ch = c4 * 4 + j;
-        float y1[B], sg[G], inv[G];
-#pragma unroll
-        for (int b = 0; b < B; ++b) y1[b] = v[b][j];
-        silu_gates<DIM>(y1, sa_s + ch * G, sb_s + ch * G, sg, inv);
-#pragma unroll
-        for (int b = 0; b < B; ++b) v[b][j] = y1[b] * sg[A::grade_of(b)];
-      }
-#pragma unroll
-      for (int b = 0; b < B; ++b)
-        *reinterpret_cast<float4*>(a.y2 + bpt_off(B, Cp, tile, b, c4, r)) = make_float4(v[b][0], v[b][1], v[b][2], v[b][3]);
+      // The next pass's first MMA overwrites these accumulators.  It is issued only after full_bar of the next chunk has
+      // collected an arrival from EVERY converter warp (conv_done), and each warp arrives after its own epilogue loads
+      // (tcgen05.wait::ld above) -- the issuer warp runs its epilogue part itself -- so the mbarrier orders the reuse.
+      fence_before_sync();
     }
-    // The next tile's first MMA overwrites these accumulators.  It is issued only after full_bar of the next chunk has
-    // collected an arrival from EVERY converter warp (conv_done), and each warp arrives after its own epilogue loads
-    // (tcgen05.wait::ld above) -- the issuer warp runs its epilogue part itself -- so the mbarrier orders the reuse.
-    fence_before_sync();
   }
   fence_before_sync();
   __syncthreads();
@@ -295,20 +323,27 @@ __global__ void __launch_bounds__(kThreads, 1) tc_f1_kernel(FwdArgs a) {
 
 // =====================================================================================================================
 // F2: linear_right / linear_left + normalisation + weighted geometric product + MVLayerNorm (+ residual)
-// The two linears share ONE MMA per (blade, split term): the weight images hold linear_right in plane rows [0, Cp) and
-// linear_left in rows [Cp, 2Cp), so the instruction shape is 128 x 2Cp x 8 and the A operand (the activations, the
-// expensive shared-memory read) is fetched once for both.  Blade b accumulates into columns [2 b Cp, 2 (b+1) Cp):
-// xr first, xl second.  TL: record the per-phase timeline (csmpn_tc_debug_buffer).
-template <int DIM, bool TL>
+// The two linears share ONE MMA per (blade, split term): the weight images hold linear_right in plane rows [0, NS) and
+// linear_left in rows [NS, 2 NS), so the instruction shape is 128 x 2 NS x 8 and the A operand (the activations, the
+// expensive shared-memory read) is fetched once for both.  Blade b accumulates into columns [2 b NS, 2 (b+1) NS):
+// xr first, xl second.  TL: record the per-phase timeline (diagnostics build).
+// ST (streamed weights, wide blocks): NS = a.ns2 < Cp output channels per pass, weight units streamed with the chunks; the
+// row statistics of the MVLayerNorm accumulate over the passes and the final scaling pass re-reads the product sum `o`
+// from the saved tensor (written by the same thread one pass earlier) instead of keeping it in TMEM.
+template <int DIM, bool TL, bool ST>
 __global__ void __launch_bounds__(kThreads, 1) tc_f2_kernel(FwdArgs a) {
   using A = Alg<DIM>;
   constexpr int B = A::B, G = A::G, P = A::P;
   extern __shared__ __align__(1024) uint8_t smem[];
   const int tid = threadIdx.x, warp = uniform_warp_idx(), lane = tid & 31;
   const int C = a.C, Cp = a.Cp, nk = Cp / 8;
-  const uint32_t img = (uint32_t)2 * Cp * Cp * 4;  // one image: [2Cp rows (right | left output channels)] x [Cp]
-  const uint32_t set_bytes = G * 2 * img;
-  uint8_t* wimg = smem + (kRing + 1) * B * kPS;
+  const int NS = ST ? a.ns2 : Cp;                      // output channels per pass
+  const int npass = ST ? Cp / NS : 1;
+  const uint32_t wunit = ST ? wunit_bytes<DIM>(2 * NS) : 0u;
+  const uint32_t half = B * kPS + wunit;
+  const uint32_t img = ST ? (uint32_t)2 * NS * 32u : (uint32_t)2 * Cp * Cp * 4;  // one image: [2 NS rows (right | left)] x [K]
+  const uint32_t set_bytes = ST ? 0u : G * 2 * img;
+  uint8_t* wimg = smem + (size_t)kRing * half + B * kPS;
   float* sn_s = reinterpret_cast<float*>(wimg + (size_t)set_bytes);  // sigmoid(normalization.a) [Cp][G]
   float* wv_s = sn_s + Cp * G;                                           // path weights [Cp][P]
   float* bl_s = wv_s + Cp * P;
@@ -317,17 +352,19 @@ __global__ void __launch_bounds__(kThreads, 1) tc_f2_kernel(FwdArgs a) {
   uint64_t* bars = reinterpret_cast<uint64_t*>(rowsum_s + 8 * kTile);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kPipeBars);
   Pipe p;
-  p.init(smem, bars, B * kPS);
+  p.init(smem, bars, half);
 
-  stage_weight_images<DIM, false>(wimg, img, a.wr, C, C, 2 * Cp, Cp, 0, true);
-  stage_weight_images<DIM, false>(wimg, img, a.wl, C, C, 2 * Cp, Cp, Cp, false);
+  if (!ST) {
+    stage_weight_images<DIM, false>(wimg, img, a.wr, C, C, 2 * Cp, Cp, 0, true);
+    stage_weight_images<DIM, false>(wimg, img, a.wl, C, C, 2 * Cp, Cp, Cp, false);
+  }
   for (int i = tid; i < Cp * G; i += kThreads) sn_s[i] = (i < C * G) ? sigmoidf_(a.na[i]) : 0.f;
   for (int i = tid; i < Cp * P; i += kThreads) wv_s[i] = (i < C * P) ? a.wp[i] : 0.f;
   for (int i = tid; i < Cp; i += kThreads) {
     bl_s[i] = (i < C) ? a.bl[i] : 0.f;
     la_s[i] = (i < C) ? a.la[i] : 0.f;
   }
-  const uint32_t need = 2 * B * Cp;
+  const uint32_t need = 2 * B * NS;
   const uint32_t tcols = need <= 32 ? 32 : need <= 64 ? 64 : need <= 128 ? 128 : need <= 256 ? 256 : 512;
   if (warp == 0) tmem_alloc(tmem_slot, tcols);
   fence_async_smem();
@@ -335,11 +372,20 @@ __global__ void __launch_bounds__(kThreads, 1) tc_f2_kernel(FwdArgs a) {
   __syncthreads();
   fence_after_sync();
   const uint32_t tbase = *tmem_slot;
-  const uint32_t idesc = idesc_tf32(kTile, 2 * Cp, false, false);
+  const uint32_t idesc = idesc_tf32(kTile, 2 * NS, false, false);
   const int my_tiles = (a.tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-  const int total_chunks = my_tiles * nk;
-  auto tile_of = [&](int q) { return (int64_t)blockIdx.x + (int64_t)(q / nk) * gridDim.x; };
-  const uint32_t col_r = 0, col_l = Cp, bcols = 2 * Cp;  // column of (blade b, channel c): b * bcols + col_{r,l} + c
+  const int per_tile = npass * nk;
+  const int total_chunks = my_tiles * per_tile;
+  auto tile_of = [&](int q) { return (int64_t)blockIdx.x + (int64_t)(q / per_tile) * gridDim.x; };
+  auto load = [&](int qq) {
+    if constexpr (ST) {
+      const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(a.wimg2) + (size_t)(qq % per_tile) * wunit;
+      issue_chunk_load_w<B>(p, qq, a.y2, Cp, tile_of(qq), qq % nk, wsrc, wunit);
+    } else {
+      issue_chunk_load<B>(p, qq, a.y2, Cp, tile_of(qq), qq % nk);
+    }
+  };
+  const uint32_t col_r = 0, col_l = NS, bcols = 2 * NS;  // column of (blade b, channel c of the pass): b * bcols + col_{r,l} + c
   const bool wide_ok = aligned32(a.y) && (!a.res || aligned32(a.res));
   const uint32_t lane_base = (warp & 3) * 32;
 
@@ -347,98 +393,106 @@ __global__ void __launch_bounds__(kThreads, 1) tc_f2_kernel(FwdArgs a) {
   [[maybe_unused]] int dbg_n = 0;
   TSTAMP(1);
   if (warp == 0) {
-    for (; loaded < kRing - 1 && loaded < total_chunks; ++loaded) issue_chunk_load<B>(p, loaded, a.y2, Cp, tile_of(loaded), loaded % nk);
+    for (; loaded < kRing - 1 && loaded < total_chunks; ++loaded) load(loaded);
   }
   for (int t = 0; t < my_tiles; ++t) {
     const int64_t tile = (int64_t)blockIdx.x + (int64_t)t * gridDim.x;
     const int64_t row0 = tile * kTile;
-    for (int kc = 0; kc < nk; ++kc, ++q) {
-      TSTAMP(10);
-      if (warp == 0) {  // issuer
-        p.wait_full(q);
-        TSTAMP(14);
-        if (loaded == q + kRing - 1 && loaded < total_chunks) {
-          if (q >= 1) mbar_wait(&p.slot_bar[(q - 1) % kRing], ((q - 1) / kRing) & 1);
-          issue_chunk_load<B>(p, loaded, a.y2, Cp, tile_of(loaded), loaded % nk);
-          ++loaded;
-        }
-        TSTAMP(16);
-        issue_chunk_mma<DIM>(p, q, tbase, bcols, kc > 0, wimg, img, 0, 1, 0, bcols, kc, 0, idesc);
-        TSTAMP(15);
-      } else {          // converters
-        mbar_wait(&p.load_bar[q % kRing], (q / kRing) & 1);
-        TSTAMP(11);
-        split_chunk<B>(p, q);
-        TSTAMP(13);
-      }
-    }
-    TSTAMP(20);
     const int r = lane_base + lane;
     const bool row_ok = row0 + r < a.rows;
-    // y2 of this thread's first channel group is requested before waiting for the MMAs (left operand of the product)
-    float4 y2v[B];
-    if ((warp >> 2) < (Cp >> 2)) {
-#pragma unroll
-      for (int b = 0; b < B; ++b) y2v[b] = *reinterpret_cast<const float4*>(a.y2 + bpt_off(B, Cp, tile, b, warp >> 2, r));
-    }
-    mbar_wait(&p.slot_bar[(q - 1) % kRing], ((q - 1) / kRing) & 1);
-    fence_after_sync();
-    TSTAMP(21);
-    if (warp == 0) {
-      for (; loaded < q + kRing && loaded < total_chunks; ++loaded) issue_chunk_load<B>(p, loaded, a.y2, Cp, tile_of(loaded), loaded % nk);
-    }
-    // ---- pass 1: per channel normalisation + weighted geometric product; o -> TMEM (over xl); row sum of norms
-    float rs = 0.f;
-    for (int c4 = warp >> 2; c4 < (Cp >> 2); c4 += 4) {
-      float xr[B][4], o[B][4];
-      if (c4 != (warp >> 2)) {
-#pragma unroll
-        for (int b = 0; b < B; ++b) y2v[b] = *reinterpret_cast<const float4*>(a.y2 + bpt_off(B, Cp, tile, b, c4, r));
-      }
-#pragma unroll
-      for (int b = 0; b < B; ++b) tmem_ld4(tmem_at(tbase, lane_base, b * bcols + col_r + c4 * 4), xr[b]);
-#pragma unroll
-      for (int b = 0; b < B; ++b) tmem_ld4(tmem_at(tbase, lane_base, b * bcols + col_l + c4 * 4), o[b]);
-      tmem_wait_ld();
-      // the saved tensors are stored from this (compute-bound) pass, so that their drain overlaps the arithmetic; the
-      // second pass then only writes the block output
-      if (a.save_xr) {
-#pragma unroll
-        for (int b = 0; b < B; ++b) {
-          float4 x = make_float4(xr[b][0], xr[b][1], xr[b][2], xr[b][3]);
-          if (!row_ok) x = make_float4(0.f, 0.f, 0.f, 0.f);
-          *reinterpret_cast<float4*>(a.save_xr + bpt_off(B, Cp, tile, b, c4, r)) = x;
+    float rs = 0.f;  // this thread's part of the row sum of norms (MVLayerNorm), over all passes
+    for (int ps = 0; ps < npass; ++ps) {
+      const int n0 = ps * NS;
+      for (int kc = 0; kc < nk; ++kc, ++q) {
+        TSTAMP(10);
+        if (warp == 0) {  // issuer
+          p.wait_full(q);
+          TSTAMP(14);
+          if (loaded == q + kRing - 1 && loaded < total_chunks) {
+            if (q >= 1) mbar_wait(&p.slot_bar[(q - 1) % kRing], ((q - 1) / kRing) & 1);
+            load(loaded);
+            ++loaded;
+          }
+          TSTAMP(16);
+          if constexpr (ST) issue_chunk_mma<DIM>(p, q, tbase, bcols, kc > 0, p.slot(q) + B * kPS, img, 0, 1, 0, bcols, 0, 0, idesc);
+          else issue_chunk_mma<DIM>(p, q, tbase, bcols, kc > 0, wimg, img, 0, 1, 0, bcols, kc, 0, idesc);
+          TSTAMP(15);
+        } else {          // converters
+          mbar_wait(&p.load_bar[q % kRing], (q / kRing) & 1);
+          TSTAMP(11);
+          split_chunk<B>(p, q);
+          TSTAMP(13);
         }
       }
+      TSTAMP(20);
+      // y2 of this thread's first channel group is requested before waiting for the MMAs (left operand of the product)
+      float4 y2v[B];
+      if ((warp >> 2) < (NS >> 2)) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int ch = c4 * 4 + j;
-        float xn[B], oj[B], y2[B], qv[G], nrm[G], rinv[G];
-#pragma unroll
-        for (int b = 0; b < B; ++b) { xn[b] = xr[b][j]; oj[b] = o[b][j]; }
-#pragma unroll
-        for (int b = 0; b < B; ++b) y2[b] = j == 0 ? y2v[b].x : j == 1 ? y2v[b].y : j == 2 ? y2v[b].z : y2v[b].w;
-        norm_factors<DIM>(xn, sn_s + ch * G, qv, nrm, rinv);
-#pragma unroll
-        for (int b = 0; b < B; ++b) xn[b] *= rinv[A::grade_of(b)];
-        oj[0] += bl_s[ch];
-        A::template wgp<false>(y2, xn, wv_s + ch * P, nullptr, oj);
-        const bool ok = row_ok && ch < C;
-#pragma unroll
-        for (int b = 0; b < B; ++b) oj[b] = ok ? oj[b] * kInvSqrt2 : 0.f;
-        if (ok) rs += fast_sas(mv_sumsq<DIM>(oj));
-#pragma unroll
-        for (int b = 0; b < B; ++b) o[b][j] = oj[b];
+        for (int b = 0; b < B; ++b) y2v[b] = *reinterpret_cast<const float4*>(a.y2 + bpt_off(B, Cp, tile, b, (n0 >> 2) + (warp >> 2), r));
       }
-#pragma unroll
-      for (int b = 0; b < B; ++b) tmem_st4(tmem_at(tbase, lane_base, b * bcols + col_l + c4 * 4), o[b]);
-      if (a.save_o) {
-#pragma unroll
-        for (int b = 0; b < B; ++b)
-          *reinterpret_cast<float4*>(a.save_o + bpt_off(B, Cp, tile, b, c4, r)) = make_float4(o[b][0], o[b][1], o[b][2], o[b][3]);
+      mbar_wait(&p.slot_bar[(q - 1) % kRing], ((q - 1) / kRing) & 1);
+      fence_after_sync();
+      TSTAMP(21);
+      if (warp == 0) {
+        for (; loaded < q + kRing && loaded < total_chunks; ++loaded) load(loaded);
       }
+      // ---- pass 1: per channel normalisation + weighted geometric product; o -> TMEM over xl (ST: -> save_o only)
+      for (int c4 = warp >> 2; c4 < (NS >> 2); c4 += 4) {
+        const int gc4 = (n0 >> 2) + c4;
+        float xr[B][4], o[B][4];
+        if (c4 != (warp >> 2)) {
+#pragma unroll
+          for (int b = 0; b < B; ++b) y2v[b] = *reinterpret_cast<const float4*>(a.y2 + bpt_off(B, Cp, tile, b, gc4, r));
+        }
+#pragma unroll
+        for (int b = 0; b < B; ++b) tmem_ld4(tmem_at(tbase, lane_base, b * bcols + col_r + c4 * 4), xr[b]);
+#pragma unroll
+        for (int b = 0; b < B; ++b) tmem_ld4(tmem_at(tbase, lane_base, b * bcols + col_l + c4 * 4), o[b]);
+        tmem_wait_ld();
+        // the saved tensors are stored from this (compute-bound) pass, so that their drain overlaps the arithmetic; the
+        // second pass then only writes the block output
+        if (a.save_xr) {
+#pragma unroll
+          for (int b = 0; b < B; ++b) {
+            float4 x = make_float4(xr[b][0], xr[b][1], xr[b][2], xr[b][3]);
+            if (!row_ok) x = make_float4(0.f, 0.f, 0.f, 0.f);
+            *reinterpret_cast<float4*>(a.save_xr + bpt_off(B, Cp, tile, b, gc4, r)) = x;
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int ch = gc4 * 4 + j;
+          float xn[B], oj[B], y2[B], qv[G], nrm[G], rinv[G];
+#pragma unroll
+          for (int b = 0; b < B; ++b) { xn[b] = xr[b][j]; oj[b] = o[b][j]; }
+#pragma unroll
+          for (int b = 0; b < B; ++b) y2[b] = j == 0 ? y2v[b].x : j == 1 ? y2v[b].y : j == 2 ? y2v[b].z : y2v[b].w;
+          norm_factors<DIM>(xn, sn_s + ch * G, qv, nrm, rinv);
+#pragma unroll
+          for (int b = 0; b < B; ++b) xn[b] *= rinv[A::grade_of(b)];
+          oj[0] += bl_s[ch];
+          A::template wgp<false>(y2, xn, wv_s + ch * P, nullptr, oj);
+          const bool ok = row_ok && ch < C;
+#pragma unroll
+          for (int b = 0; b < B; ++b) oj[b] = ok ? oj[b] * kInvSqrt2 : 0.f;
+          if (ok) rs += fast_sas(mv_sumsq<DIM>(oj));
+#pragma unroll
+          for (int b = 0; b < B; ++b) o[b][j] = oj[b];
+        }
+        if constexpr (!ST) {
+#pragma unroll
+          for (int b = 0; b < B; ++b) tmem_st4(tmem_at(tbase, lane_base, b * bcols + col_l + c4 * 4), o[b]);
+        }
+        if (ST || a.save_o) {
+#pragma unroll
+          for (int b = 0; b < B; ++b)
+            *reinterpret_cast<float4*>(a.save_o + bpt_off(B, Cp, tile, b, gc4, r)) = make_float4(o[b][0], o[b][1], o[b][2], o[b][3]);
+        }
+      }
+      if constexpr (!ST) tmem_wait_st();
+      fence_before_sync();  // ST: the next pass's first MMA overwrites the accumulators (ordered by the full_bar chain)
     }
-    tmem_wait_st();
     TSTAMP(22);
     // two copies, alternating by tile: a warp's reads of tile t and another warp's writes of tile t+1 are ordered by the
     // mbarrier chain of the next K loop anyway, but never touch the same words this way
@@ -447,26 +501,34 @@ __global__ void __launch_bounds__(kThreads, 1) tc_f2_kernel(FwdArgs a) {
     __syncthreads();
     TSTAMP(23);
     const float inv_mu = fast_rcp((rowsum_t[r] + rowsum_t[kTile + r] + rowsum_t[2 * kTile + r] + rowsum_t[3 * kTile + r]) / (float)C + kEps);
-    // ---- pass 2: saves, MVLayerNorm scale, residual, output
-    for (int c4 = warp >> 2; c4 < (Cp >> 2); c4 += 4) {
+    // ---- pass 2: MVLayerNorm scale, residual, output (every channel group this thread handled in pass 1)
+    for (int gc4 = warp >> 2; gc4 < (Cp >> 2); gc4 += 4) {
       float o[B][4];
+      if constexpr (ST) {
 #pragma unroll
-      for (int b = 0; b < B; ++b) tmem_ld4(tmem_at(tbase, lane_base, b * bcols + col_l + c4 * 4), o[b]);
-      tmem_wait_ld();
+        for (int b = 0; b < B; ++b) {
+          const float4 x = *reinterpret_cast<const float4*>(a.save_o + bpt_off(B, Cp, tile, b, gc4, r));
+          o[b][0] = x.x; o[b][1] = x.y; o[b][2] = x.z; o[b][3] = x.w;
+        }
+      } else {
+#pragma unroll
+        for (int b = 0; b < B; ++b) tmem_ld4(tmem_at(tbase, lane_base, b * bcols + col_l + gc4 * 4), o[b]);
+        tmem_wait_ld();
+      }
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const float sc = la_s[c4 * 4 + j] * inv_mu;
+        const float sc = la_s[gc4 * 4 + j] * inv_mu;
 #pragma unroll
         for (int b = 0; b < B; ++b) o[b][j] *= sc;
       }
       if (a.out_bpt) {
 #pragma unroll
         for (int b = 0; b < B; ++b)
-          *reinterpret_cast<float4*>(a.y + bpt_off(B, Cp, tile, b, c4, r)) = make_float4(o[b][0], o[b][1], o[b][2], o[b][3]);
+          *reinterpret_cast<float4*>(a.y + bpt_off(B, Cp, tile, b, gc4, r)) = make_float4(o[b][0], o[b][1], o[b][2], o[b][3]);
       } else if (row_ok) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const int ch = c4 * 4 + j;
+          const int ch = gc4 * 4 + j;
           if (ch >= C) continue;
           const size_t off = ((size_t)(row0 + r) * C + ch) * B;
           if constexpr (B == 8) {
@@ -510,25 +572,76 @@ long long*& debug_buffer() {
   return p;
 }
 
-template <int DIM>
-size_t f1_smem(int Cp, int kin8) {
-  constexpr int B = Alg<DIM>::B, G = Alg<DIM>::G;
-  return (size_t)(kRing + 1) * B * kPS + (size_t)G * 2 * kin8 * Cp * 4 + (size_t)Cp * (1 + 2 * G) * 4 + 96;
-}
-template <int DIM>
-size_t f2_smem(int Cp) {
-  constexpr int B = Alg<DIM>::B, G = Alg<DIM>::G, P = Alg<DIM>::P;
-  return (size_t)(kRing + 1) * B * kPS + (size_t)2 * G * 2 * Cp * Cp * 4 + (size_t)Cp * (G + P + 2) * 4 + 8 * kTile * 4 + 96;
-}
 constexpr size_t kSmemMax = 227 * 1024;
 
+// How the two forward kernels of a block of this shape run: weights resident in shared memory, or -- wide blocks --
+// streamed with the K chunks in passes of ns1 / ns2 output channels (tc_block.cuh).
+struct FwdPlan {
+  bool ok;
+  bool st1, st2;
+  int Cp, kin8, ns1, ns2;
+  size_t s1, s2;            // dynamic shared memory of f1 / f2
+  int64_t w1_floats, w2_floats;  // pre-split weight image buffers (streamed mode), floats
+};
+
 template <int DIM>
-bool fwd_supported(int cin, int c) {
-  constexpr int B = Alg<DIM>::B;
-  if (c < 1 || cin < 1) return false;
+FwdPlan fwd_plan(int cin, int c) {
+  constexpr int B = Alg<DIM>::B, G = Alg<DIM>::G, P = Alg<DIM>::P;
+  FwdPlan p;
+  memset(&p, 0, sizeof(p));
+  if (c < 1 || cin < 1) return p;
   const int Cp = round_up(c, 16), kin8 = round_up(cin, 8);
-  if (2 * B * Cp > 512) return false;
-  return f1_smem<DIM>(Cp, kin8) <= kSmemMax && f2_smem<DIM>(Cp) <= kSmemMax;
+  p.Cp = Cp; p.kin8 = kin8;
+  const size_t ring = (size_t)(kRing + 1) * B * kPS;
+  const size_t par1 = (size_t)Cp * (1 + 2 * G) * 4 + 96, par2 = (size_t)Cp * (G + P + 2) * 4 + 8 * kTile * 4 + 96;
+  // ---- f1
+  p.s1 = ring + (size_t)G * 2 * kin8 * Cp * 4 + par1;
+  p.ns1 = Cp;
+  if (B * Cp > 512 || p.s1 > kSmemMax) {
+    p.st1 = true;
+    int ns = (512 / B) / 16 * 16;
+    while (ns >= 16 && (Cp % ns || (size_t)kRing * wunit_bytes<DIM>(ns) + ring + par1 > kSmemMax)) ns -= 16;
+    if (ns < 16) return p;
+    p.ns1 = ns;
+    p.s1 = (size_t)kRing * wunit_bytes<DIM>(ns) + ring + par1;
+    p.w1_floats = weight_image_floats<DIM>(0, ns, Cp / ns, kin8 / 8);
+  }
+  // ---- f2
+  p.s2 = ring + (size_t)2 * G * 2 * Cp * Cp * 4 + par2;
+  p.ns2 = Cp;
+  if (2 * B * Cp > 512 || p.s2 > kSmemMax) {
+    p.st2 = true;
+    int ns = (512 / (2 * B)) / 16 * 16;
+    while (ns >= 16 && (Cp % ns || (size_t)kRing * wunit_bytes<DIM>(2 * ns) + ring + par2 > kSmemMax)) ns -= 16;
+    if (ns < 16) return p;
+    p.ns2 = ns;
+    p.s2 = (size_t)kRing * wunit_bytes<DIM>(2 * ns) + ring + par2;
+    p.w2_floats = weight_image_floats<DIM>(1, ns, Cp / ns, Cp / 8);
+  }
+  p.ok = true;
+  return p;
+}
+
+template <int DIM>
+bool fwd_supported(int cin, int c) { return fwd_plan<DIM>(cin, c).ok; }
+
+inline int64_t align32f(int64_t floats) { return (floats + 31) / 32 * 32; }
+
+template <int DIM>
+int64_t fwd_ws_bytes(const csmpn_block_desc& d) {
+  const FwdPlan p = fwd_plan<DIM>(d.c0 + d.c1 + d.c2, d.c);
+  if (!p.ok) return -1;
+  return (align32f(p.w1_floats) + align32f(p.w2_floats)) * 4;
+}
+
+template <int DIM>
+int launch_weight_images(const WPrepArgs& w, int64_t floats, cudaStream_t stream) {
+  const int threads = 256;
+  int64_t blocks = (floats + threads - 1) / threads;
+  if (blocks > 4096) blocks = 4096;
+  tc_weight_images_kernel<DIM><<<(unsigned)blocks, threads, 0, stream>>>(w);
+  CSMPN_LAUNCH_CHECK("tc_weight_images_kernel");
+  return CSMPN_OK;
 }
 
 template <int DIM>
@@ -554,31 +667,49 @@ int launch_fwd(const csmpn_block_desc& d, cudaStream_t stream) {
   if (!a.y2 || !a.y) return CSMPN_ERR_BAD_ARG;
   if (a.in_bpt && (d.mode != 0 || d.c1 || d.c2)) return CSMPN_ERR_BAD_ARG;
   if (a.out_bpt && d.res) return CSMPN_ERR_BAD_ARG;
-  if (!fwd_supported<DIM>(a.cin, a.C)) return CSMPN_ERR_UNSUPPORTED;
+  const FwdPlan p = fwd_plan<DIM>(a.cin, a.C);
+  if (!p.ok) return CSMPN_ERR_UNSUPPORTED;
   if (a.tiles == 0) return CSMPN_OK;
-  const int grid = a.tiles < sm_count_cached() ? a.tiles : sm_count_cached();
-  const size_t s1 = f1_smem<DIM>(a.Cp, a.kin8), s2 = f2_smem<DIM>(a.Cp);
+  a.ns1 = p.ns1; a.ns2 = p.ns2;
   const int mask = d.stage_mask ? d.stage_mask : ~0;
-  if (!(mask & 1)) {
-  } else if (a.in_bpt) {
-    CSMPN_CUDA_TRY(cudaFuncSetAttribute(tc_f1_kernel<DIM, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s1));
-    tc_f1_kernel<DIM, true><<<grid, kThreads, s1, stream>>>(a);
-  } else {
-    CSMPN_CUDA_TRY(cudaFuncSetAttribute(tc_f1_kernel<DIM, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s1));
-    tc_f1_kernel<DIM, false><<<grid, kThreads, s1, stream>>>(a);
-  }
-  if (mask & 1) CSMPN_LAUNCH_CHECK("tc_f1_kernel");
-  if (mask & 2) {
-#ifdef CSMPN_DEBUG_TOOLS
-    if (a.dbg) {
-      CSMPN_CUDA_TRY(cudaFuncSetAttribute(tc_f2_kernel<DIM, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s2));
-      tc_f2_kernel<DIM, true><<<grid, kThreads, s2, stream>>>(a);
-    } else
-#endif
-    {
-      CSMPN_CUDA_TRY(cudaFuncSetAttribute(tc_f2_kernel<DIM, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s2));
-      tc_f2_kernel<DIM, false><<<grid, kThreads, s2, stream>>>(a);
+  if (p.st1 || p.st2) {
+    // streamed weights: the pre-split images live in the caller's forward workspace (csmpn_block_fwd_workspace)
+    if (!d.fwd_ws || d.fwd_ws_bytes < (align32f(p.w1_floats) + align32f(p.w2_floats)) * 4) return CSMPN_ERR_WORKSPACE;
+    if (p.st2 && !d.save_o) return CSMPN_ERR_BAD_ARG;  // the scaling pass of f2 re-reads the product sum from it
+    float* w1img = (float*)d.fwd_ws;
+    float* w2img = w1img + align32f(p.w1_floats);
+    a.wimg1 = w1img; a.wimg2 = w2img;
+    if (p.st1 && (mask & 1)) {
+      WPrepArgs w{d.w1, nullptr, 0, 0, a.C, a.cin, 0, p.ns1, a.Cp / p.ns1, a.kin8 / 8, 0, w1img};
+      int st = launch_weight_images<DIM>(w, p.w1_floats, stream);
+      if (st) return st;
     }
+    if (p.st2 && (mask & 2)) {
+      WPrepArgs w{d.wr, d.wl, 1, 0, a.C, a.C, 0, p.ns2, a.Cp / p.ns2, a.Cp / 8, 0, w2img};
+      int st = launch_weight_images<DIM>(w, p.w2_floats, stream);
+      if (st) return st;
+    }
+  }
+  const int grid = a.tiles < sm_count_cached() ? a.tiles : sm_count_cached();
+  auto run = [&](auto kern, size_t smem_bytes) -> int {
+    CSMPN_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+    kern<<<grid, kThreads, smem_bytes, stream>>>(a);
+    return CSMPN_OK;
+  };
+  if (mask & 1) {
+    int rc = a.in_bpt ? (p.st1 ? run(tc_f1_kernel<DIM, true, true>, p.s1) : run(tc_f1_kernel<DIM, true, false>, p.s1))
+                      : (p.st1 ? run(tc_f1_kernel<DIM, false, true>, p.s1) : run(tc_f1_kernel<DIM, false, false>, p.s1));
+    if (rc) return rc;
+    CSMPN_LAUNCH_CHECK("tc_f1_kernel");
+  }
+  if (mask & 2) {
+    int rc;
+#ifdef CSMPN_DEBUG_TOOLS
+    if (a.dbg && !p.st2) rc = run(tc_f2_kernel<DIM, true, false>, p.s2);
+    else
+#endif
+    rc = p.st2 ? run(tc_f2_kernel<DIM, false, true>, p.s2) : run(tc_f2_kernel<DIM, false, false>, p.s2);
+    if (rc) return rc;
     CSMPN_LAUNCH_CHECK("tc_f2_kernel");
   }
   return CSMPN_OK;
@@ -592,7 +723,20 @@ int tc_block_fwd(int dim, const csmpn_block_desc* d, cudaStream_t stream) {
   return CSMPN_ERR_UNSUPPORTED;
 }
 void tc_set_debug_buffer(long long* p) { tcb::debug_buffer() = p; }
+int64_t tc_block_fwd_workspace(int dim, const csmpn_block_desc* d) {
+  if (dim == 2) return tcb::fwd_ws_bytes<2>(*d);
+  if (dim == 3) return tcb::fwd_ws_bytes<3>(*d);
+  return -1;
+}
 bool tc_block_bwd_supported(int dim, int c_in, int c);  // tc_block_bwd.cu
+int tc_block_bwd_wide(int dim, int c_in, int c);         // tc_block_bwd.cu
+bool tc_block_supported(int dim, int c_in, int c);
+// bit 0: supported, bit 1 / 2: f1 / f2 stream their weights, bit 3: the backward runs the wide plan
+int tc_block_plan(int dim, int c_in, int c) {
+  if (!tc_block_supported(dim, c_in, c)) return 0;
+  tcb::FwdPlan p = dim == 2 ? tcb::fwd_plan<2>(c_in, c) : tcb::fwd_plan<3>(c_in, c);
+  return 1 | (p.st1 ? 2 : 0) | (p.st2 ? 4 : 0) | (tc_block_bwd_wide(dim, c_in, c) ? 8 : 0);
+}
 bool tc_block_supported(int dim, int c_in, int c) {
   if (dim == 2) return tcb::fwd_supported<2>(c_in, c) && tc_block_bwd_supported(2, c_in, c);
   if (dim == 3) return tcb::fwd_supported<3>(c_in, c) && tc_block_bwd_supported(3, c_in, c);

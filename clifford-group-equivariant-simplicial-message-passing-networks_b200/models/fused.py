@@ -35,6 +35,7 @@ class BlockDesc(ctypes.Structure):
         ("engine", c_int32), ("in_bpt", c_int32), ("out_bpt", c_int32), ("stage_mask", c_int32),
         ("save_y2", c_void_p), ("save_x0", c_void_p),
         ("pair_attr", c_int32),
+        ("fwd_ws", c_void_p), ("fwd_ws_bytes", c_int64),
     ]
 
 
@@ -104,11 +105,12 @@ def _block_supported(layer) -> bool:
     if not (isinstance(lin, MVLinear) and lin.subspaces and isinstance(act, MVSiLU) and act.invariant == "mag2"
             and isinstance(sgp, SteerableGeometricProductLayer) and sgp.include_first_order
             and isinstance(sgp.normalization, NormalizationLayer) and isinstance(ln, MVLayerNorm)
-            and lin.out_features <= 128):
+            and lin.out_features <= 256):
         return False
-    # wide blocks whose weights leave room for fewer than 4 rows per shared-memory tile run faster as composed unit kernels
-    # (C = 64, Cl(3,0): 144 ms vs 551 ms per layer step on 1.06 M pairs) than on the SIMT engine's staged-weights mode
-    return _fits_fused(lin.algebra.dim, lin.in_features, lin.out_features)
+    # wide blocks whose weights leave room for fewer than 4 rows per shared-memory tile of the SIMT engine run on the
+    # tensor-core engine with streamed weights (csmpn_block_tc_plan); what neither engine takes is composed from unit kernels
+    dim = lin.algebra.dim
+    return _fits_fused(dim, lin.in_features, lin.out_features) or (dim in (2, 3) and tc_supported(dim, lin.in_features, lin.out_features))
 
 
 _FITS: dict = {}
@@ -316,8 +318,18 @@ class TcBlockFn(torch.autograd.Function):
         d.engine, d.in_bpt, d.out_bpt = 1, int(in_bpt), int(out_bpt)
         d.save_y2 = y2.data_ptr()
         d.save_x0 = None if x0 is None else x0.data_ptr()
+        nws = lib().csmpn_block_fwd_workspace(dim, ctypes.byref(d))
+        if nws < 0:
+            raise _lib.CsmpnError("tensor-core block forward: unsupported configuration")
+        wsf = scratch_o = None
+        if nws > 0:  # wide block: pre-split weight images streamed with the K chunks
+            wsf = workspace(nws, dev)
+            d.fwd_ws, d.fwd_ws_bytes = wsf.data_ptr(), nws
+            if saves is None:  # the scaling pass of the second kernel re-reads the product sum from this tensor
+                scratch_o = bpt_empty(dim, rows, c, dev)
+                d.save_o = scratch_o.data_ptr()
         check(lib().csmpn_block_fwd(dim, ctypes.byref(d), stream_ptr(dev)), "block_fwd (tensor-core)")
-        _record("fwd", dim, d, keep=[srcs, params, y, resc, saves, y2, x0])
+        _record("fwd", dim, d, keep=[srcs, params, y, resc, saves, y2, x0, wsf, scratch_o])
         if need_grad:
             ctx.save_for_backward(*[t for t in srcs if t is not None], *[t for t in params if t is not None], *saves, y2,
                                   *([] if x0 is None else [x0]))
@@ -504,9 +516,11 @@ def _block_uses_tc(algebra, layer, need_grad, rows=None) -> bool:
     lin = layer[0]
     if algebra.dim not in (2, 3) or (need_grad and not TC_BACKWARD_READY):
         return False
-    if rows is not None and rows < tc_min_rows():
+    if not tc_supported(algebra.dim, lin.in_features, lin.out_features):
         return False
-    return tc_supported(algebra.dim, lin.in_features, lin.out_features)
+    if not _fits_fused(algebra.dim, lin.in_features, lin.out_features):
+        return True  # wide block: the SIMT engine cannot hold it, whatever the row count
+    return rows is None or rows >= tc_min_rows()
 
 
 def block_forward(algebra, layer, x, p1=None, p2=None, res=None, mode=0, sgraph=None, bpt_rows=None, out_bpt=False,
@@ -615,7 +629,8 @@ def _kernel_stages(d: BlockDesc, g, B: int):
                 ("tc_f2", "linear_right/left + normalisation + weighted GP + MVLayerNorm (+residual)", 2, 4 * T + y_out, 3 * rows * 4 * B * C * C)]
     gy = T if g.gy_bpt else ref(C)
     gx = 0 if not g.grad_x else (Tin if g.gx_bpt else ref(cin))
-    fused_silu = os.environ.get("CSMPN_TC_FUSE_SILU", "1") != "0" and cp <= 64
+    wide = bool(lib().csmpn_block_tc_plan(B.bit_length() - 1, cin, C) & 8)
+    fused_silu = os.environ.get("CSMPN_TC_FUSE_SILU", "1") != "0" and cp <= 64 and not wide
     mid = ([("tc_bgemm", "dy2 = dy2p + d WL + dxr WR, MVSiLU adjoint in the epilogue -> dy1", 2, 5 * T, 3 * rows * 4 * B * C * C)]
            if fused_silu else
            [("tc_bgemm", "dy2 = dy2p + d WL + dxr WR", 2, 4 * T, 3 * rows * 4 * B * C * C), ("tc_b3", "MVSiLU adjoint", 4, 3 * T, 0)])

@@ -199,6 +199,9 @@ typedef struct csmpn_block_desc {
                                            table = p1 [n_nodes, c1/2, B] (per-simplex attributes, e.g. the simplex-type
                                            embedding of md17_cssmpnn.py:122-133) instead of a materialised [E, c1, B]
                                            edge_attr read through eid; its gradient: csmpn_scatter_pair_sorted */
+  void* fwd_ws;                         /* engine 1, wide blocks (csmpn_block_fwd_workspace > 0): device scratch of the
+                                           forward for the pre-split weight images streamed with the K chunks */
+  int64_t fwd_ws_bytes;
 } csmpn_block_desc;
 
 /* gradients produced by csmpn_block_bwd (all overwritten; parameter gradients reduced deterministically) */
@@ -212,8 +215,15 @@ typedef struct csmpn_block_grads {
 } csmpn_block_grads;
 
 int csmpn_block_fwd(int dim, const csmpn_block_desc* desc, csmpn_stream_t stream);
+/* device bytes csmpn_block_fwd needs in desc->fwd_ws (0 for every block whose weights stay resident in shared memory;
+ * -1 if engine 1 does not handle the shape) */
+int64_t csmpn_block_fwd_workspace(int dim, const csmpn_block_desc* desc);
 /* 1 if the tensor-core engine handles a block of this shape (c_in input channels, width c) in algebra dimension dim */
 int csmpn_block_tc_supported(int dim, int c_in, int c);
+/* how engine 1 runs such a block: bit 0 = supported; bit 1 / bit 2 = the first / second forward kernel streams its weights
+ * with the K chunks (wide blocks: Cl(3,0) with c >= 64, ...) instead of keeping them resident in shared memory; bit 3 =
+ * the backward runs the wide plan (streamed GEMM weights, slab-wise weight-gradient launches, separate MVSiLU adjoint) */
+int csmpn_block_tc_plan(int dim, int c_in, int c);
 /* > 0 (the rows per shared-memory tile) if engine 0 keeps the block's weights resident in shared memory (forward and
  * backward), 0 if it would stage them per GEMM; with fewer than 8 rows per tile or staged weights the unit kernels
  * (csmpn_mvlinear_*, csmpn_mvsilu_*, csmpn_wgp_*, ...) composed by the host are the faster path for that shape */

@@ -66,7 +66,7 @@ def test_tc_engine_is_selected():
 
     assert fused.tc_supported(3, 38, 32) and fused.tc_supported(3, 67, 32) and fused.tc_supported(2, 46, 40)
     assert not fused.tc_supported(5, 28, 28)  # Cl(5,0): 32 blades do not fit the TMEM accumulator budget
-    assert not fused.tc_supported(3, 64, 64)
+    assert fused.tc_supported(3, 64, 64)  # wide block: streamed weights
 
 
 @pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
@@ -331,3 +331,61 @@ def test_silu_adjoint_folded_into_gemm_matches_separate_kernel(case, monkeypatch
     assert out["launches0"] == out["launches1"] + 4  # one kernel less per block
     for what, a, b in zip(["gh"] + names, out["1"], out["0"]):
         assert_close(a, b, 2e-6, f"{name} {what} fused vs separate MVSiLU adjoint")
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# wide blocks: weights streamed with the K chunks (csmpn_block_tc_plan bits 1-3), hidden widths 64 / 128 / 256
+WIDE = [
+    # name, metric, C, T, complexes, simplices/complex, pairs/complex, aggr
+    ("cl3_c64", (1, 1, 1), 64, 3, 4, 87, 527, "sum"),
+    ("cl3_c128", (1, 1, 1), 128, 3, 2, 87, 527, "mean"),
+    ("cl3_c256", (1, 1, 1), 256, 3, 1, 60, 300, "sum"),
+    ("cl2_c128", (1, 1), 128, 3, 3, 41, 345, "sum"),
+    ("cl2_c64", (1, 1), 64, 3, 3, 41, 345, "mean"),
+    ("cl3_c64_multi_tile", (1, 1, 1), 64, 3, 40, 87, 527, "sum"),   # 165 tiles of pairs: two tiles on some CTAs
+]
+
+
+def test_wide_plans():
+    from csmpn_b200 import _lib
+
+    plan = _lib.lib().csmpn_block_tc_plan
+    assert plan(3, 38, 32) == 1 and plan(2, 46, 40) == 1          # resident weights
+    for c in (64, 128, 256):
+        assert plan(3, c + 6, c) == 0b1111 and plan(3, 2 * c + 3, c) == 0b1111 and plan(3, c, c) == 0b1111
+    assert plan(2, 134, 128) == 0b1111
+    assert plan(5, 28, 28) == 0 and plan(3, 102, 96) == 0         # Cl(5,0) and non-slab widths stay off the engine
+
+
+@pytest.mark.parametrize("case", WIDE, ids=[c[0] for c in WIDE])
+def test_wide_block_forward_backward_vs_oracle(case):
+    """EGCL at hidden widths 64 / 128 / 256 on the tensor-core engine (streamed weights, channel passes, slab-wise
+    weight-gradient launches): forward and every gradient against the CPU oracle"""
+    name, metric, C, T, ncx, n, e, aggr = case
+    CliffordAlgebra, M = _mods()
+    ralg, params, h, ei, ea, na, cot = _inputs(case)
+    hr, nar = h.clone().requires_grad_(), na.clone().requires_grad_()
+    pr = {k: v.clone().requires_grad_() for k, v in params.items()}
+    yr = R.egcl(ralg, hr, ei, torch.cat([nar[ei[0]], nar[ei[1]]], 1), nar, pr, aggr=aggr)
+    names = list(pr)
+    gr = torch.autograd.grad(yr, [hr, nar] + [pr[k] for k in names], cot)
+
+    from csmpn_b200 import _lib
+    from csmpn_b200.models import fused
+
+    alg = CliffordAlgebra(metric).to(DEV)
+    m = M.EGCL(alg, C, C, C, edge_attr_features=2 * T, node_attr_features=T, aggr=aggr).to(DEV)
+    _load(m, params)
+    assert all(fused._block_uses_tc(alg, b, True, 1) for b in list(m.edge_model.layers) + list(m.node_model.layers))
+    hd, nad = h.to(DEV).requires_grad_(), na.to(DEV).requires_grad_()
+    n0 = _lib.lib().csmpn_launch_count()
+    y = m(hd, ei.to(DEV), M.PairedNodeAttr(nad), nad)
+    pd = dict(m.named_parameters())
+    got = torch.autograd.grad(y, [hd, nad] + [pd[k] for k in names], cot.to(DEV))
+    assert _lib.lib().csmpn_launch_count() - n0 > 40
+    assert_close(y, yr, 1e-5, f"{name} fwd")
+    for what, a, b in zip(["gh", "gnode_attr"] + names, got, gr):
+        assert_close(a, b, 1e-4, f"{name} {what}")
+    with torch.no_grad():   # inference path: no saved tensors, the product sum goes through a scratch tensor
+        y2 = m(h.to(DEV), ei.to(DEV), M.PairedNodeAttr(na.to(DEV)), na.to(DEV))
+    assert torch.equal(y2, y.detach())
