@@ -644,7 +644,7 @@ def run_ours(args):
     if rank == 0:
         sampler.start()
     main = layer_leg(args.workload, ncx, C, dev, world, rank, args.steps, args.warmup, lib, use_graph=not args.no_graph,
-                     hbm_peak=hbm_peak, peak_src=peak_src)
+                     with_e2e=not args.no_e2e, with_roofline=not args.no_roofline, hbm_peak=hbm_peak, peak_src=peak_src)
     clocks = sampler.stop() if rank == 0 else None  # sampled over the e2e and layer-step timed regions of the headline workload
     others = {}
     if args.workload == "md17" and not args.complexes and not args.hidden and not args.only:
@@ -658,7 +658,8 @@ def run_ours(args):
     lifting = lifting_leg(dev, hbm_peak) if (rank == 0 and not args.only) else None
 
     if rank == 0:
-        roof = main.pop("roofline")
+        roof = main.pop("roofline", None) or {"bound": "hbm", "achieved": None, "peak": hbm_peak, "unit": "GB/s", "frac": None,
+                                              "traffic": None, "kernel": "not timed (--no-roofline)", "peak_source": peak_src}
         lr = main.pop("layer_roofline")
         lr["note"] = ("the whole layer step (`value`) against SURVEY 8d's fused-minimum bytes / FLOPs; the tensor-core engine runs a block "
                       "as several kernels whose intermediates cross L2/HBM (per-kernel figures under roofline.kernels)")
@@ -676,10 +677,11 @@ def run_ours(args):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": main["ms_per_step"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": desc, "aggr": aggr, "hidden": C, "complexes_per_step_per_gpu": ncx, "simplices_per_gpu": main["simplices_per_gpu"],
-                       "pairs_per_gpu": main["pairs_per_gpu"], "l2": "flushed between timed steps (256 MiB write)",
+                       "pairs_per_gpu": main["pairs_per_gpu"], "simplices_processed_in_timed_region": main["simplices_all_gpus"] * args.steps,
+                       "l2": "flushed between timed steps (256 MiB write)",
                        "parallelism": f"dp{world}" if world > 1 else "single", "path": fused_path_name(), "launch": glaunch,
                        "edge_attr": "PairedNodeAttr(node_attr): node_attr[src] | node_attr[dst] gathered inside the message kernel"},
-            "e2e": {"value": main["e2e_value"], "unit": "simplices/s", "h2d_bytes_per_step": main["h2d_bytes_per_step"],
+            "e2e": None if args.no_e2e else {"value": main["e2e_value"], "unit": "simplices/s", "h2d_bytes_per_step": main["h2d_bytes_per_step"],
                     "d2h_bytes_per_step": main["d2h_bytes_per_step"], "ms_per_step": main["e2e_ms_per_step"],
                     "regions_ms_per_step": main["e2e_regions_ms_per_step"],
                     "how": "median of 3 regions of K steps, each timed as one region; per step: pinned H2D of h, edge_index, node_attr "
@@ -712,6 +714,8 @@ def main():
     ap.add_argument("--hidden", type=int, default=0, help="hidden width C (default: the workload's)")
     ap.add_argument("--no-train", action="store_true", help="skip the full-model train-step leg")
     ap.add_argument("--no-graph", action="store_true", help="launch the layer step eagerly instead of replaying CUDA graphs")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (sweep runs: 10^6-simplex batches)")
+    ap.add_argument("--no-roofline", action="store_true", help="skip the per-kernel timing table")
     ap.add_argument("--only", action="store_true", help="only the named workload's layer legs (no motion/NBA side runs, no lifting leg)")
     args = ap.parse_args()
     if args.impl == "reference":
