@@ -14,6 +14,7 @@
 //
 // The elementwise kernels keep one channel per thread for the whole kernel (warp = 4 channels x 8 rows), so every
 // per-channel parameter gradient is a register accumulator and every BPT access of a warp is one 128-byte line.
+#include <utility>
 #include <vector>
 
 #include "tc_block.cuh"
@@ -1019,7 +1020,14 @@ int launch_bwd(const csmpn_block_desc& d, const csmpn_block_grads& g, void* work
   if (!d.save_y1 || !d.save_y2 || !d.save_xr || !d.save_o) return CSMPN_ERR_BAD_ARG;
   const float* x0 = d.in_bpt ? d.p0 : d.save_x0;
   if (!x0) return CSMPN_ERR_BAD_ARG;
-  if (p.tiles == 0) return CSMPN_OK;
+  if (p.tiles == 0) {  // no rows: every parameter gradient is zero (the header promises they are all overwritten)
+    const size_t c = d.c, cin = p.cin;
+    const std::pair<float*, size_t> outs[] = {{g.g_w1, c * cin * G}, {d.has_b1 ? g.g_b1 : nullptr, c}, {g.g_sa, c * G}, {g.g_sb, c * G},
+                                              {g.g_wr, c * c * G}, {g.g_na, c * G}, {g.g_wl, c * c * G}, {g.g_bl, c}, {g.g_wp, c * P}, {g.g_la, c}};
+    for (const auto& o : outs)
+      if (o.first) CSMPN_CUDA_TRY(cudaMemsetAsync(o.first, 0, o.second * sizeof(float), stream));
+    return CSMPN_OK;
+  }
   float* ws = (float*)workspace;
   const int C = d.c, Cp = p.Cp;
   // ---- B1

@@ -6,6 +6,7 @@ allocates nothing) and calls one or two C entry points on the current CUDA strea
 from __future__ import annotations
 
 import math
+import os
 
 import torch
 
@@ -192,6 +193,11 @@ class CSRGraph:
             raise ValueError("edge_index must be an int64 tensor of shape [2, E]")
         self.n_nodes = int(n_nodes)
         self.n_pairs = int(edge_index.shape[1])
+        if os.environ.get("CSMPN_CHECK_INDICES") == "1" and self.n_pairs:
+            # PyG raises IndexError for simplex ids outside [0, n_nodes); the kernels trust them (one host sync to check)
+            lo, hi = int(edge_index.min()), int(edge_index.max())
+            if lo < 0 or hi >= int(n_nodes):
+                raise IndexError(f"edge_index holds simplex ids in [{lo}, {hi}] but the graph has {int(n_nodes)} simplices")
         ei = edge_index.contiguous()
         self.edge_index = ei
         self.src = ei[0]
