@@ -705,7 +705,7 @@ def bench_layer_kernels(layer, d, graph, hbm_peak, peak_src, traffic=None, iters
     dom = classes[dom_name]
     return {
         "bound": "hbm", "achieved": dom["hbm_gbs"], "peak": hbm_peak, "unit": "GB/s", "frac": dom["hbm_frac"],
-        "traffic": dom["traffic"], "peak_source": peak_src,
+        "traffic": None if not dom["traffic"] else dom["traffic"] / dom["launches"], "peak_source": peak_src,
         "kernel": "%s (%d launches per layer step, %.0f %% of the layer's summed kernel time)" % (dom_name, dom["launches"], 100 * dom["share_of_layer_kernel_time"]),
         "launch_ms": dom["ms"] / dom["launches"], "algorithmic_bytes_per_launch": dom["bytes"] / dom["launches"],
         "how": "every kernel of one layer step launched alone (csmpn_block_desc.stage_mask) between CUDA events on the launching "
