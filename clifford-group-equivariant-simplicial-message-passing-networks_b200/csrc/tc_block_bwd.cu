@@ -635,6 +635,237 @@ __global__ void __launch_bounds__(kThreads, 1) tc_bgemm_kernel(GemmArgs a) {
 }
 
 // =====================================================================================================================
+// The same GEMM with an OVERLAPPED epilogue (resident weights, one pass, B * n16 <= 256 TMEM columns): accumulators
+// alternate between two TMEM buffers by tile and the epilogue of tile t-1 runs as channel-group units between the chunks
+// of tile t's K loop (see tc_f1db_kernel).  Warp 0 issues; warps 1-15 convert; warps 4-15 own the epilogue (lane quadrant
+// warp & 3, channel groups (warp >> 2) - 1, + 3, ...).  Bit-identical outputs; the SILU parameter-gradient partials are
+// summed in a different (still fixed) order than in tc_bgemm_kernel.
+template <int DIM, bool SILU>
+__global__ void __launch_bounds__(kThreads, 1) tc_bgemmdb_kernel(GemmArgs a) {
+  using A = Alg<DIM>;
+  constexpr int B = A::B, G = A::G, NPS = 2 * G + 1;
+  constexpr int kUnits = 6;  // channel groups per epilogue warp: n16 / 4 / 3 <= 6 (n16 <= 64)
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int tid = threadIdx.x, warp = uniform_warp_idx(), lane = tid & 31;
+  const uint32_t img = (uint32_t)a.n16 * a.kmax * 4;
+  const uint32_t set_bytes = G * 2 * img;
+  uint8_t* wimg = smem + (kRing + 1) * B * kPS;
+  const int nsets = a.src[1] ? 2 : 1;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(wimg + (size_t)nsets * set_bytes);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kPipeBars);
+  float* sa_s = reinterpret_cast<float*>(tmem_slot + 4);
+  float* sb_s = sa_s + a.n16 * G;
+  Pipe p;
+  p.init(smem, bars, B * kPS);
+  if (SILU) {
+    for (int i = tid; i < a.n16 * G; i += kThreads) {
+      sa_s[i] = (i < a.C * G) ? a.sa[i] : 0.f;
+      sb_s[i] = (i < a.C * G) ? a.sb[i] : 0.f;
+    }
+  }
+  float acc[kUnits][2];
+#pragma unroll
+  for (int u = 0; u < kUnits; ++u) { acc[u][0] = 0.f; acc[u][1] = 0.f; }
+  for (int s = 0; s < nsets; ++s) stage_weight_images<DIM, true>(wimg + (size_t)s * set_bytes, img, a.w[s], a.wk[s], a.wn, a.n16, a.kmax);
+  const int Np = a.n16;
+  const uint32_t bufcols = (uint32_t)B * Np;  // <= 256 (host)
+  const uint32_t need = 2 * bufcols;
+  const uint32_t tcols = need <= 32 ? 32 : need <= 64 ? 64 : need <= 128 ? 128 : need <= 256 ? 256 : 512;
+  if (warp == 0) tmem_alloc(tmem_slot, tcols);
+  fence_async_smem();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tbase = *tmem_slot;
+  const int nk = a.nk[0] + a.nk[1];
+  const int my_tiles = (a.tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int total_chunks = my_tiles * nk;
+  const uint32_t idesc = idesc_tf32(kTile, Np, false, false);
+  auto issue = [&](int qq) {
+    const int64_t tile = (int64_t)blockIdx.x + (int64_t)(qq / nk) * gridDim.x;
+    const int kc = qq % nk;
+    const int s = kc < a.nk[0] ? 0 : 1;
+    issue_chunk_load<B>(p, qq, a.src[s], a.cp[s], tile, s ? kc - a.nk[0] : kc);
+  };
+  const uint32_t lane_base = (warp & 3) * 32;
+  const int r = lane_base + lane;
+  const bool wide_ok = aligned32(a.out);
+  const int n_c4 = Np >> 2;
+
+  auto epilogue_unit = [&](int64_t tile, int c4, uint32_t tb) {
+    const int64_t row0 = tile * kTile;
+    const bool row_ok = row0 + r < a.rows;
+    float v[B][4];
+#pragma unroll
+    for (int b = 0; b < B; ++b) tmem_ld4(tmem_at(tb, lane_base, b * Np + c4 * 4), v[b]);
+    if (a.addend) {
+      float4 ad[B];
+#pragma unroll
+      for (int b = 0; b < B; ++b) ad[b] = *reinterpret_cast<const float4*>(a.addend + bpt_off(B, a.n16, tile, b, c4, r));
+      tmem_wait_ld();
+#pragma unroll
+      for (int b = 0; b < B; ++b) {
+        v[b][0] += ad[b].x; v[b][1] += ad[b].y; v[b][2] += ad[b].z; v[b][3] += ad[b].w;
+      }
+    } else {
+      tmem_wait_ld();
+    }
+    if constexpr (SILU) {
+      const int u = c4 / 3;
+#pragma unroll
+      for (int pr = 0; pr < 2; ++pr) {
+        float2 y1v[B];
+#pragma unroll
+        for (int b = 0; b < B; ++b)
+          y1v[b] = *reinterpret_cast<const float2*>(a.y1 + bpt_off(B, a.n16, tile, b, c4, r) + 2 * pr);
+        float vals[16], t0 = 0.f, t1 = 0.f;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) vals[i] = 0.f;
+#pragma unroll
+        for (int jj = 0; jj < 2; ++jj) {
+          const int j = 2 * pr + jj, ch = c4 * 4 + j;
+          float y1[B], dy[B], sg[G], inv[G], tg[G], ds[G];
+#pragma unroll
+          for (int b = 0; b < B; ++b) {
+            y1[b] = jj == 0 ? y1v[b].x : y1v[b].y;
+            dy[b] = v[b][j];
+          }
+          const float* sa = sa_s + ch * G;
+          silu_gates<DIM>(y1, sa, sb_s + ch * G, sg, inv);
+#pragma unroll
+          for (int g = 0; g < G; ++g) tg[g] = 0.f;
+#pragma unroll
+          for (int b = 0; b < B; ++b) tg[A::grade_of(b)] = fmaf(dy[b], y1[b], tg[A::grade_of(b)]);
+          const bool ok = row_ok && ch < a.C;
+          float gv[NPS];
+#pragma unroll
+          for (int g = 0; g < G; ++g) {
+            ds[g] = ok ? tg[g] * sg[g] * (1.f - sg[g]) : 0.f;
+            gv[g] = ds[g] * inv[g];
+            gv[G + g] = ds[g];
+          }
+#pragma unroll
+          for (int b = 0; b < B; ++b) {
+            const int g = A::grade_of(b);
+            const float dinv = (g == 0) ? 1.f : 2.f * y1[b];
+            v[b][j] = ok ? fmaf(sg[g], dy[b], ds[g] * sa[g] * dinv) : 0.f;
+          }
+          gv[2 * G] = v[0][j];
+#pragma unroll
+          for (int k = 0; k < NPS; ++k) {
+            const int idx = jj * NPS + k;
+            if (idx < 16) vals[idx] = gv[k];
+            else if (idx == 16) t0 = gv[k];
+            else t1 = gv[k];
+          }
+        }
+        const float s16 = warp_transpose_reduce16(vals, lane);
+        t0 = warp_sum(t0);
+        t1 = warp_sum(t1);
+        const float mine = lane < 16 ? s16 : lane == 16 ? t0 : lane == 17 ? t1 : 0.f;
+#pragma unroll
+        for (int k = 0; k < kUnits; ++k) {
+          if (k == u) acc[k][pr] += mine;
+        }
+      }
+    }
+    if (a.out_bpt) {
+#pragma unroll
+      for (int b = 0; b < B; ++b) {
+        float4 x = make_float4(v[b][0], v[b][1], v[b][2], v[b][3]);
+        if (!row_ok) x = make_float4(0.f, 0.f, 0.f, 0.f);
+        *reinterpret_cast<float4*>(a.out + bpt_off(B, a.n16, tile, b, c4, r)) = x;
+      }
+    } else if (row_ok) {
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        const int n = c4 * 4 + jj;
+        if (n >= a.wn) continue;
+        float* dst = a.out + ((size_t)(row0 + r) * a.wn + n) * B;
+        if constexpr (B == 8) {
+          if (wide_ok) {
+            float w8[8];
+#pragma unroll
+            for (int b = 0; b < 8; ++b) w8[b] = v[b][jj];
+            st_global_v8(dst, w8);
+            continue;
+          }
+        }
+#pragma unroll
+        for (int h = 0; h < B / 4; ++h)
+          *reinterpret_cast<float4*>(dst + 4 * h) = make_float4(v[4 * h][jj], v[4 * h + 1][jj], v[4 * h + 2][jj], v[4 * h + 3][jj]);
+      }
+    }
+  };
+  int64_t pend_tile = -1;
+  int pend_c4 = 0, pend_q = 0;
+  uint32_t pend_tb = 0;
+  bool pend_ready = false;
+  auto epilogue_step = [&]() {
+    if (warp < 4 || pend_tile < 0) return;
+    if (!pend_ready) {
+      mbar_wait(&p.slot_bar[pend_q % kRing], (pend_q / kRing) & 1);
+      fence_after_sync();
+      pend_ready = true;
+    }
+    if (pend_c4 < n_c4) {
+      epilogue_unit(pend_tile, pend_c4, pend_tb);
+      pend_c4 += 3;
+    }
+    if (pend_c4 >= n_c4) { pend_tile = -1; fence_before_sync(); }
+  };
+
+  int q = 0, loaded = 0;
+  if (warp == 0) for (; loaded < kRing - 1 && loaded < total_chunks; ++loaded) issue(loaded);
+  for (int t = 0; t < my_tiles; ++t) {
+    const int64_t tile = (int64_t)blockIdx.x + (int64_t)t * gridDim.x;
+    const uint32_t tb = tbase + (uint32_t)(t & 1) * bufcols;
+    for (int kc = 0; kc < nk; ++kc, ++q) {
+      if (warp == 0) {  // issuer
+        p.wait_full(q);
+        if (loaded == q + kRing - 1 && loaded < total_chunks) {
+          if (q >= 1) mbar_wait(&p.slot_bar[(q - 1) % kRing], ((q - 1) / kRing) & 1);
+          issue(loaded);
+          ++loaded;
+        }
+        const int s = kc < a.nk[0] ? 0 : 1;
+        issue_chunk_mma<DIM>(p, q, tb, Np, kc > 0, wimg, img, s, 1, set_bytes, a.n16, s ? kc - a.nk[0] : kc, 0, idesc);
+      } else {
+        mbar_wait(&p.load_bar[q % kRing], (q / kRing) & 1);
+        split_chunk<B>(p, q);
+        epilogue_step();
+      }
+    }
+    while (warp >= 4 && pend_tile >= 0) epilogue_step();
+    pend_tile = tile; pend_c4 = (warp >> 2) - 1; pend_q = q - 1; pend_tb = tb; pend_ready = false;
+  }
+  while (warp >= 4 && pend_tile >= 0) epilogue_step();
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tbase, tcols);
+  if constexpr (SILU) {
+    float* red = reinterpret_cast<float*>(p.lo);  // [16 warps][kUnits][2 pairs][18]; 16 * 6 * 2 * 18 * 4 B = 13.8 KB <= the lo slot
+#pragma unroll
+    for (int u = 0; u < kUnits; ++u) {
+#pragma unroll
+      for (int pr = 0; pr < 2; ++pr) {
+        float* dst = red + ((warp * kUnits + u) * 2 + pr) * 18;
+        if (lane < 18) dst[lane] = acc[u][pr];
+      }
+    }
+    __syncthreads();
+    for (int e = tid; e < a.C * NPS; e += kThreads) {
+      const int ch = e / NPS, k = e - ch * NPS;
+      const int c4 = ch >> 2, j = ch & 3, g3 = c4 % 3, u = c4 / 3, pr = j >> 1, idx = (j & 1) * NPS + k;
+      float sum = 0.f;
+#pragma unroll
+      for (int q4 = 0; q4 < 4; ++q4) sum += red[((((g3 + 1) * 4 + q4) * kUnits + u) * 2 + pr) * 18 + idx];
+      a.partial[((size_t)blockIdx.x * a.C + ch) * NPS + k] = sum;
+    }
+  }
+}
+
+// =====================================================================================================================
 // weight-gradient GEMM:  D_g[m, n] += sum_{tiles, blades b of grade g, rows r} Acat[r, m, b] * Bsrc[r, n, b]
 // Acat = channels of a0 followed by the channels of a1 (BPT, cpa each); operands MN-major (K = rows).
 struct DwArgs {
@@ -1077,6 +1308,13 @@ int launch_bwd(const csmpn_block_desc& d, const csmpn_block_grads& g, void* work
   CSMPN_CUDA_TRY(cudaFuncSetAttribute(tc_bgemm_kernel<DIM, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
   CSMPN_CUDA_TRY(cudaFuncSetAttribute(tc_bgemm_kernel<DIM, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
   CSMPN_CUDA_TRY(cudaFuncSetAttribute(tc_bgemm_kernel<DIM, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
+  CSMPN_CUDA_TRY(cudaFuncSetAttribute(tc_bgemmdb_kernel<DIM, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
+  CSMPN_CUDA_TRY(cudaFuncSetAttribute(tc_bgemmdb_kernel<DIM, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax));
+  // the overlapped-epilogue GEMM needs two accumulator buffers in TMEM and at most 6 channel groups per epilogue warp
+  auto overlap_ok = [&](int n16) {
+    const char* e = getenv("CSMPN_TC_OVERLAP");
+    return !(e && e[0] == '0') && 2 * B * n16 <= 512 && n16 <= 64;
+  };
   auto prep = [&](const WPrepArgs& w, int64_t floats) -> int {
     int64_t blocks = (floats + 255) / 256;
     if (blocks > 4096) blocks = 4096;
@@ -1093,8 +1331,14 @@ int launch_bwd(const csmpn_block_desc& d, const csmpn_block_grads& g, void* work
       tc_bgemm_kernel<DIM, false, true><<<grid, kThreads, gemm_smem_streamed<DIM>(p.np), stream>>>(ga);
     } else {
       const size_t sm = gemm_smem<DIM>(2, ga.n16, ga.kmax, fuse_silu);
-      if (fuse_silu) tc_bgemm_kernel<DIM, true, false><<<grid, kThreads, sm, stream>>>(ga);
-      else tc_bgemm_kernel<DIM, false, false><<<grid, kThreads, sm, stream>>>(ga);
+      if (overlap_ok(ga.n16)) {  // two accumulator buffers fit: epilogue overlapped with the next tile's K loop
+        if (fuse_silu) tc_bgemmdb_kernel<DIM, true><<<grid, kThreads, sm, stream>>>(ga);
+        else tc_bgemmdb_kernel<DIM, false><<<grid, kThreads, sm, stream>>>(ga);
+      } else if (fuse_silu) {
+        tc_bgemm_kernel<DIM, true, false><<<grid, kThreads, sm, stream>>>(ga);
+      } else {
+        tc_bgemm_kernel<DIM, false, false><<<grid, kThreads, sm, stream>>>(ga);
+      }
     }
     CSMPN_LAUNCH_CHECK("tc_bgemm_kernel(dy2)");
   }
@@ -1127,6 +1371,8 @@ int launch_bwd(const csmpn_block_desc& d, const csmpn_block_grads& g, void* work
       if (rc) return rc;
       ga.wimg = img_gx; ga.np = p.np;
       tc_bgemm_kernel<DIM, false, true><<<grid, kThreads, gemm_smem_streamed<DIM>(p.np), stream>>>(ga);
+    } else if (overlap_ok(ga.n16)) {
+      tc_bgemmdb_kernel<DIM, false><<<grid, kThreads, gemm_smem<DIM>(1, ga.n16, ga.kmax), stream>>>(ga);
     } else {
       tc_bgemm_kernel<DIM, false, false><<<grid, kThreads, gemm_smem<DIM>(1, ga.n16, ga.kmax), stream>>>(ga);
     }

@@ -322,6 +322,154 @@ __global__ void __launch_bounds__(kThreads, 1) tc_f1_kernel(FwdArgs a) {
 }
 
 // =====================================================================================================================
+// F1 with OVERLAPPED epilogue (resident weights, B * Cp <= 256 TMEM columns): two accumulator buffers alternate by tile,
+// and the epilogue of tile t-1 (TMEM -> bias -> y1 store -> MVSiLU -> y2 store) is cut into channel-group units that the
+// converter warps run BETWEEN the chunks of tile t's K loop.  Loads, MMAs, the elementwise pass and the store drain of
+// neighbouring tiles then overlap instead of running back to back (the plain kernel above spends two thirds of a tile in
+// the epilogue and its drain with the tensor pipe and the copy engine idle).
+// Roles: warp 0 issues copies and MMAs only; warps 1-15 convert / gather; warps 4-15 also own the epilogue: lane quadrant
+// warp & 3, channel groups (warp >> 2) - 1, + 3, ...  Same arithmetic as tc_f1_kernel: results are bit-identical.
+template <int DIM, bool BPT_IN>
+__global__ void __launch_bounds__(kThreads, 1) tc_f1db_kernel(FwdArgs a) {
+  using A = Alg<DIM>;
+  constexpr int B = A::B, G = A::G;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int tid = threadIdx.x, warp = uniform_warp_idx(), lane = tid & 31;
+  const int C = a.C, Cp = a.Cp, nk = a.kin8 / 8;
+  const uint32_t img = (uint32_t)a.kin8 * Cp * 4;
+  uint8_t* wimg = smem + (kRing + 1) * B * kPS;
+  float* b1_s = reinterpret_cast<float*>(wimg + (size_t)G * 2 * img);
+  float* sa_s = b1_s + Cp;
+  float* sb_s = sa_s + Cp * G;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sb_s + Cp * G);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kPipeBars);
+  Pipe p;
+  p.init(smem, bars, B * kPS);
+
+  stage_weight_images<DIM, false>(wimg, img, a.w1, C, a.cin, Cp, a.kin8);
+  for (int i = tid; i < Cp; i += kThreads) b1_s[i] = (i < C && a.has_b1) ? a.b1[i] : 0.f;
+  for (int i = tid; i < Cp * G; i += kThreads) {
+    sa_s[i] = (i < C * G) ? a.sa[i] : 0.f;
+    sb_s[i] = (i < C * G) ? a.sb[i] : 0.f;
+  }
+  const uint32_t bufcols = (uint32_t)B * Cp;  // <= 256 (host)
+  const uint32_t need = 2 * bufcols;
+  const uint32_t tcols = need <= 32 ? 32 : need <= 64 ? 64 : need <= 128 ? 128 : need <= 256 ? 256 : 512;
+  if (warp == 0) tmem_alloc(tmem_slot, tcols);
+  fence_async_smem();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tbase = *tmem_slot;
+  const uint32_t idesc = idesc_tf32(kTile, Cp, false, false);
+  const int my_tiles = (a.tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int total_chunks = my_tiles * nk;
+  auto tile_of = [&](int q) { return (int64_t)blockIdx.x + (int64_t)(q / nk) * gridDim.x; };
+  const int r = (warp & 3) * 32 + lane;
+  const int n_c4 = Cp >> 2;
+
+  // one epilogue unit: channel group c4 of `tile`, accumulators at tb
+  auto epilogue_unit = [&](int64_t tile, int c4, uint32_t tb) {
+    const bool row_ok = tile * kTile + r < a.rows;
+    float v[B][4];
+#pragma unroll
+    for (int b = 0; b < B; ++b) tmem_ld4(tmem_at(tb, (warp & 3) * 32, b * Cp + c4 * 4), v[b]);
+    tmem_wait_ld();
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int ch = c4 * 4 + j;
+      float y1[B];
+      const bool ok = row_ok && ch < C;
+#pragma unroll
+      for (int b = 0; b < B; ++b) y1[b] = ok ? v[b][j] : 0.f;
+      if (ok) y1[0] += b1_s[ch];
+#pragma unroll
+      for (int b = 0; b < B; ++b) v[b][j] = y1[b];
+    }
+    if (a.save_y1) {
+#pragma unroll
+      for (int b = 0; b < B; ++b)
+        *reinterpret_cast<float4*>(a.save_y1 + bpt_off(B, Cp, tile, b, c4, r)) = make_float4(v[b][0], v[b][1], v[b][2], v[b][3]);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int ch = c4 * 4 + j;
+      float y1[B], sg[G], inv[G];
+#pragma unroll
+      for (int b = 0; b < B; ++b) y1[b] = v[b][j];
+      silu_gates<DIM>(y1, sa_s + ch * G, sb_s + ch * G, sg, inv);
+#pragma unroll
+      for (int b = 0; b < B; ++b) v[b][j] = y1[b] * sg[A::grade_of(b)];
+    }
+#pragma unroll
+    for (int b = 0; b < B; ++b)
+      *reinterpret_cast<float4*>(a.y2 + bpt_off(B, Cp, tile, b, c4, r)) = make_float4(v[b][0], v[b][1], v[b][2], v[b][3]);
+  };
+  // pending epilogue of this warp: tile, next channel group, accumulator buffer, last chunk of that tile
+  int64_t pend_tile = -1;
+  int pend_c4 = 0, pend_q = 0;
+  uint32_t pend_tb = 0;
+  bool pend_ready = false;
+  auto epilogue_step = [&]() {  // at most one unit
+    if (warp < 4 || pend_tile < 0) return;
+    if (!pend_ready) {  // the MMAs of the pending tile have completed (its last chunk released its slot)
+      mbar_wait(&p.slot_bar[pend_q % kRing], (pend_q / kRing) & 1);
+      fence_after_sync();
+      pend_ready = true;
+    }
+    if (pend_c4 < n_c4) {
+      epilogue_unit(pend_tile, pend_c4, pend_tb);
+      pend_c4 += 3;
+    }
+    if (pend_c4 >= n_c4) { pend_tile = -1; fence_before_sync(); }
+  };
+
+  int q = 0, loaded = 0;
+  float4 gv[BPT_IN ? 1 : ApiItems<DIM>::N];
+  if (!BPT_IN && warp != 0 && total_chunks > 0) gather_chunk_api<DIM>(a, tile_of(0) * kTile, 0, gv);
+  if (BPT_IN && warp == 0) {
+    for (; loaded < kRing - 1 && loaded < total_chunks; ++loaded)
+      issue_chunk_load<B>(p, loaded, a.p0, a.in_cp, tile_of(loaded), loaded % nk);
+  }
+  for (int t = 0; t < my_tiles; ++t) {
+    const int64_t tile = (int64_t)blockIdx.x + (int64_t)t * gridDim.x;
+    const uint32_t tb = tbase + (uint32_t)(t & 1) * bufcols;
+    for (int kc = 0; kc < nk; ++kc, ++q) {
+      if (warp == 0) {  // issuer
+        p.wait_full(q);
+        if (BPT_IN && loaded == q + kRing - 1 && loaded < total_chunks) {
+          if (q >= 1) mbar_wait(&p.slot_bar[(q - 1) % kRing], ((q - 1) / kRing) & 1);
+          issue_chunk_load<B>(p, loaded, a.p0, a.in_cp, tile_of(loaded), loaded % nk);
+          ++loaded;
+        }
+        // buffer t & 1 was read by the epilogue of tile t-2: every epilogue warp finished it before its conv_done of
+        // this tile's first chunk (full_bar observed above), so the first MMA may overwrite it
+        issue_chunk_mma<DIM>(p, q, tb, Cp, kc > 0, wimg, img, 0, 1, 0, Cp, kc, 0, idesc);
+      } else {
+        if (BPT_IN) {
+          mbar_wait(&p.load_bar[q % kRing], (q / kRing) & 1);
+          split_chunk<B>(p, q);
+        } else {
+          if (q >= kRing) mbar_wait(&p.slot_bar[q % kRing], ((q - kRing) / kRing) & 1);
+          store_chunk_api<DIM>(p, q, gv, a.save_x0, round_up(a.kin8, 16), tile, kc);
+          p.conv_done(q);
+          if (q + 1 < total_chunks) gather_chunk_api<DIM>(a, tile_of(q + 1) * kTile, (q + 1) % nk, gv);
+          if (a.save_x0 && kc == nk - 1 && (a.kin8 & 8)) zero_chunk_bpt<B>(a.save_x0, round_up(a.kin8, 16), tile, nk);
+        }
+        epilogue_step();  // one unit of the previous tile between two chunks of this one
+      }
+    }
+    // the previous tile's epilogue must be finished before this warp signals the next tile's first chunk
+    while (warp >= 4 && pend_tile >= 0) epilogue_step();
+    pend_tile = tile; pend_c4 = (warp >> 2) - 1; pend_q = q - 1; pend_tb = tb; pend_ready = false;
+  }
+  while (warp >= 4 && pend_tile >= 0) epilogue_step();
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tbase, tcols);
+}
+
+// =====================================================================================================================
 // F2: linear_right / linear_left + normalisation + weighted geometric product + MVLayerNorm (+ residual)
 // The two linears share ONE MMA per (blade, split term): the weight images hold linear_right in plane rows [0, NS) and
 // linear_left in rows [NS, 2 NS), so the instruction shape is 128 x 2 NS x 8 and the A operand (the activations, the
@@ -626,6 +774,11 @@ template <int DIM>
 bool fwd_supported(int cin, int c) { return fwd_plan<DIM>(cin, c).ok; }
 
 inline int64_t align32f(int64_t floats) { return (floats + 31) / 32 * 32; }
+// CSMPN_TC_OVERLAP=0 selects the plain kernels (epilogue after the K loop); read per call so a test can compare both
+inline bool overlap_enabled() {
+  const char* e = getenv("CSMPN_TC_OVERLAP");
+  return !(e && e[0] == '0');
+}
 
 template <int DIM>
 int64_t fwd_ws_bytes(const csmpn_block_desc& d) {
@@ -697,8 +850,11 @@ int launch_fwd(const csmpn_block_desc& d, cudaStream_t stream) {
     return CSMPN_OK;
   };
   if (mask & 1) {
-    int rc = a.in_bpt ? (p.st1 ? run(tc_f1_kernel<DIM, true, true>, p.s1) : run(tc_f1_kernel<DIM, true, false>, p.s1))
-                      : (p.st1 ? run(tc_f1_kernel<DIM, false, true>, p.s1) : run(tc_f1_kernel<DIM, false, false>, p.s1));
+    // resident weights and accumulators of at most half of TMEM: the overlapped-epilogue kernel (CSMPN_TC_OVERLAP=0: plain)
+    const bool overlap = !p.st1 && 2 * B * a.Cp <= 512 && overlap_enabled();
+    int rc = overlap ? (a.in_bpt ? run(tc_f1db_kernel<DIM, true>, p.s1) : run(tc_f1db_kernel<DIM, false>, p.s1))
+             : a.in_bpt ? (p.st1 ? run(tc_f1_kernel<DIM, true, true>, p.s1) : run(tc_f1_kernel<DIM, true, false>, p.s1))
+                        : (p.st1 ? run(tc_f1_kernel<DIM, false, true>, p.s1) : run(tc_f1_kernel<DIM, false, false>, p.s1));
     if (rc) return rc;
     CSMPN_LAUNCH_CHECK("tc_f1_kernel");
   }

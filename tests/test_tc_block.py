@@ -389,3 +389,28 @@ def test_wide_block_forward_backward_vs_oracle(case):
     with torch.no_grad():   # inference path: no saved tensors, the product sum goes through a scratch tensor
         y2 = m(h.to(DEV), ei.to(DEV), M.PairedNodeAttr(na.to(DEV)), na.to(DEV))
     assert torch.equal(y2, y.detach())
+
+
+@pytest.mark.parametrize("case", [CASES[0], CASES[1], CASES[2], CASES[3], CASES[4]], ids=["motion", "md17", "nba", "odd_c", "tiny"])
+def test_overlapped_epilogue_kernels_match_plain_kernels(case, monkeypatch):
+    """tc_f1db / tc_bgemmdb (two TMEM accumulator buffers, epilogue of tile t-1 interleaved with the K loop of tile t) against
+    the plain kernels (CSMPN_TC_OVERLAP=0): same arithmetic, so the layer output is bit-identical; the MVSiLU parameter
+    gradients are summed in another fixed order"""
+    name, metric, C, T, ncx, n, e, aggr = case
+    CliffordAlgebra, M = _mods()
+    ralg, params, h, ei, ea, na, cot = _inputs(case)
+    alg = CliffordAlgebra(metric).to(DEV)
+    m = M.EGCL(alg, C, C, C, edge_attr_features=2 * T, node_attr_features=T, aggr=aggr).to(DEV)
+    _load(m, params)
+    names = [k for k, _ in m.named_parameters()]
+    plist = [p for _, p in m.named_parameters()]
+    out = {}
+    for ov in ("1", "0"):
+        monkeypatch.setenv("CSMPN_TC_OVERLAP", ov)
+        hd = h.to(DEV).requires_grad_()
+        y = m(hd, ei.to(DEV), ea.to(DEV), na.to(DEV))
+        out[ov] = (y.detach().clone(), torch.autograd.grad(y, [hd] + plist, cot.to(DEV)))
+        torch.cuda.synchronize()
+    assert torch.equal(out["1"][0], out["0"][0])
+    for what, a, b in zip(["gh"] + names, out["1"][1], out["0"][1]):
+        assert_close(a, b, 2e-6, f"{name} {what} overlapped vs plain")
