@@ -640,6 +640,13 @@ def run_ours(args):
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
 
+    if args.train_only:  # diagnostics: the train leg alone, on a fresh allocator
+        train = train_leg(dev, world, rank, max(3, args.steps // 2), 3, lib, graphed=not args.no_graph)
+        if rank == 0:
+            print(json.dumps({"train": train}))
+        if world > 1:
+            dist.destroy_process_group()
+        return
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -716,6 +723,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="launch the layer step eagerly instead of replaying CUDA graphs")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (sweep runs: 10^6-simplex batches)")
     ap.add_argument("--no-roofline", action="store_true", help="skip the per-kernel timing table")
+    ap.add_argument("--train-only", action="store_true", help="only the full-model train-step leg")
     ap.add_argument("--only", action="store_true", help="only the named workload's layer legs (no motion/NBA side runs, no lifting leg)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -68,8 +68,33 @@ struct ApiItems {
   }
 };
 
+// A thread's items keep their rows from chunk to chunk of a tile, so the gather indices of those rows (receiver, sender,
+// position of the pair in the caller's order) are fetched ONCE per tile: the per-chunk gathers then start with the data
+// loads instead of a dependent index load (the K loop of the gathering kernel is latency-bound on exactly that chain).
 template <int DIM>
-__device__ __forceinline__ void gather_chunk_api(const FwdArgs& a, int64_t row0, int kc, float4* v) {
+struct GatherIdx {
+  int32_t d[ApiItems<DIM>::N], s[ApiItems<DIM>::N], e[ApiItems<DIM>::N];
+};
+template <int DIM>
+__device__ __forceinline__ void load_gather_idx(const FwdArgs& a, int64_t row0, GatherIdx<DIM>& gi) {
+  constexpr int N = ApiItems<DIM>::N, TOT = ApiItems<DIM>::TOT;
+  if (a.mode != 1) return;
+  const int ct = (int)threadIdx.x - 32;
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    const int it = ct + i * kConv;
+    int r, cl, h;
+    ApiItems<DIM>::decode(it, r, cl, h);
+    const int64_t R = row0 + r;
+    const bool ok = it < TOT && R < a.rows;
+    gi.d[i] = ok ? a.dst[R] : 0;
+    gi.s[i] = ok ? a.src[R] : 0;
+    gi.e[i] = (ok && a.c1 > 0 && !a.pair_attr) ? a.eid[R] : 0;
+  }
+}
+
+template <int DIM>
+__device__ __forceinline__ void gather_chunk_api(const FwdArgs& a, int64_t row0, int kc, float4* v, const GatherIdx<DIM>& gi) {
   constexpr int B = Alg<DIM>::B, H = ApiItems<DIM>::H, PPR = ApiItems<DIM>::PPR, N = ApiItems<DIM>::N, TOT = ApiItems<DIM>::TOT;
   const int ct = (int)threadIdx.x - 32;
 #pragma unroll
@@ -83,16 +108,16 @@ __device__ __forceinline__ void gather_chunk_api(const FwdArgs& a, int64_t row0,
     if (it < TOT && R < a.rows && c < a.cin) {
       if (a.mode == 1) {
         if (c < a.c0) {
-          const int64_t d = a.dst[R], s = a.src[R];
+          const int64_t d = gi.d[i], s = gi.s[i];
           const float4 x = __ldg(reinterpret_cast<const float4*>(a.p0 + (d * a.c0 + c) * B + 4 * h));
           const float4 z = __ldg(reinterpret_cast<const float4*>(a.p0 + (s * a.c0 + c) * B + 4 * h));
           v[i] = make_float4(x.x - z.x, x.y - z.y, x.z - z.z, x.w - z.w);
         } else if (a.pair_attr) {  // (table[src] | table[dst]), table = p1 [n_nodes, c1/2, B]
           const int k = c - a.c0, half = a.c1 >> 1;
-          const int64_t n = k < half ? a.src[R] : a.dst[R];
+          const int64_t n = k < half ? gi.s[i] : gi.d[i];
           v[i] = __ldg(reinterpret_cast<const float4*>(a.p1 + (n * half + (k < half ? k : k - half)) * B + 4 * h));
         } else {
-          const int64_t e = a.eid[R];
+          const int64_t e = gi.e[i];
           v[i] = __ldg(reinterpret_cast<const float4*>(a.p1 + (e * a.c1 + (c - a.c0)) * B + 4 * h));
         }
       } else {
@@ -229,7 +254,11 @@ __global__ void __launch_bounds__(kThreads, 1) tc_f1_kernel(FwdArgs a) {
   int q = 0;       // chunk sequence number of this CTA; chunk q lives in raw slot q % kRing
   int loaded = 0;  // warp 0: chunks whose bulk copies have been issued
   float4 gv[BPT_IN ? 1 : ApiItems<DIM>::N];  // gathered items of the NEXT chunk to stage (API-layout input)
-  if (!BPT_IN && warp != 0 && total_chunks > 0) gather_chunk_api<DIM>(a, tile_of(0) * kTile, 0, gv);
+  GatherIdx<DIM> gi;
+  if (!BPT_IN && warp != 0 && total_chunks > 0) {
+    load_gather_idx<DIM>(a, tile_of(0) * kTile, gi);
+    gather_chunk_api<DIM>(a, tile_of(0) * kTile, 0, gv, gi);
+  }
   if (LOADS && warp == 0) {
     for (; loaded < kRing - 1 && loaded < total_chunks; ++loaded) load(loaded);
   }
@@ -262,7 +291,10 @@ __global__ void __launch_bounds__(kThreads, 1) tc_f1_kernel(FwdArgs a) {
           float* x0 = ps == 0 ? a.save_x0 : nullptr;
           store_chunk_api<DIM>(p, q, gv, x0, round_up(a.kin8, 16), tile, kc);
           p.conv_done(q);
-          if (q + 1 < total_chunks) gather_chunk_api<DIM>(a, tile_of(q + 1) * kTile, (q + 1) % nk, gv);
+          if (q + 1 < total_chunks) {
+            if ((q + 1) % per_tile == 0) load_gather_idx<DIM>(a, tile_of(q + 1) * kTile, gi);  // first chunk of the next tile
+            gather_chunk_api<DIM>(a, tile_of(q + 1) * kTile, (q + 1) % nk, gv, gi);
+          }
           if (x0 && kc == nk - 1 && (a.kin8 & 8)) zero_chunk_bpt<B>(x0, round_up(a.kin8, 16), tile, nk);
         }
       }
@@ -426,7 +458,11 @@ __global__ void __launch_bounds__(kThreads, 1) tc_f1db_kernel(FwdArgs a) {
 
   int q = 0, loaded = 0;
   float4 gv[BPT_IN ? 1 : ApiItems<DIM>::N];
-  if (!BPT_IN && warp != 0 && total_chunks > 0) gather_chunk_api<DIM>(a, tile_of(0) * kTile, 0, gv);
+  GatherIdx<DIM> gi;
+  if (!BPT_IN && warp != 0 && total_chunks > 0) {
+    load_gather_idx<DIM>(a, tile_of(0) * kTile, gi);
+    gather_chunk_api<DIM>(a, tile_of(0) * kTile, 0, gv, gi);
+  }
   if (BPT_IN && warp == 0) {
     for (; loaded < kRing - 1 && loaded < total_chunks; ++loaded)
       issue_chunk_load<B>(p, loaded, a.p0, a.in_cp, tile_of(loaded), loaded % nk);
@@ -453,7 +489,10 @@ __global__ void __launch_bounds__(kThreads, 1) tc_f1db_kernel(FwdArgs a) {
           if (q >= kRing) mbar_wait(&p.slot_bar[q % kRing], ((q - kRing) / kRing) & 1);
           store_chunk_api<DIM>(p, q, gv, a.save_x0, round_up(a.kin8, 16), tile, kc);
           p.conv_done(q);
-          if (q + 1 < total_chunks) gather_chunk_api<DIM>(a, tile_of(q + 1) * kTile, (q + 1) % nk, gv);
+          if (q + 1 < total_chunks) {
+            if ((q + 1) % nk == 0) load_gather_idx<DIM>(a, tile_of(q + 1) * kTile, gi);  // first chunk of the next tile
+            gather_chunk_api<DIM>(a, tile_of(q + 1) * kTile, (q + 1) % nk, gv, gi);
+          }
           if (a.save_x0 && kc == nk - 1 && (a.kin8 & 8)) zero_chunk_bpt<B>(a.save_x0, round_up(a.kin8, 16), tile, nk);
         }
         epilogue_step();  // one unit of the previous tile between two chunks of this one
