@@ -15,8 +15,8 @@ import os
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-CLASSES = (("tc_f1_kernel", "tc_f1"), ("tc_f2_kernel", "tc_f2"), ("tc_b1_kernel", "tc_b1"), ("tc_bgemm_kernel", "tc_bgemm"),
-           ("tc_b3_kernel", "tc_b3"), ("tc_dw_kernel", "tc_dw"), ("tc_final_kernel", "tc_final"), ("tc_weight_images", "tc_weight_images"),
+CLASSES = (("tc_f1", "tc_f1"), ("tc_f2", "tc_f2"), ("tc_b1", "tc_b1"), ("tc_bgemm", "tc_bgemm"),
+           ("tc_b3", "tc_b3"), ("tc_dw", "tc_dw"), ("tc_final", "tc_final"), ("tc_weight_images", "tc_weight_images"),
            ("block_fwd_kernel", "block_fwd (fp32 simt)"), ("block_bwd", "block_bwd (fp32 simt)"), ("segment_", "segment reduce / expand"),
            ("scatter_", "scatter (grad_h, table grads)"), ("add3_rows", "add3_rows"))
 
@@ -39,7 +39,8 @@ def main():
         d = dict(zip(hdr, r))
         val = float(d["Metric Value"].replace(",", ""))
         unit = d.get("Metric Unit", "")
-        scale = {"Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "byte": 1.0, "usecond": 1.0, "msecond": 1e3, "nsecond": 1e-3, "second": 1e6}.get(unit, 1.0)
+        scale = {"Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "byte": 1.0, "usecond": 1.0, "us": 1.0, "msecond": 1e3, "ms": 1e3,
+                 "nsecond": 1e-3, "ns": 1e-3, "second": 1e6, "s": 1e6}.get(unit, 1.0)
         k = per.setdefault(d["ID"], {"name": d["Kernel Name"], "dram": 0.0, "us": 0.0})
         if d["Metric Name"].startswith("dram__bytes"):
             k["dram"] += val * scale
