@@ -1043,7 +1043,8 @@ inline int check_desc(int dim, const csmpn_block_desc* d) {
   if (!d) return CSMPN_ERR_BAD_ARG;
   if (dim != 2 && dim != 3 && dim != 5) return CSMPN_ERR_UNSUPPORTED;
   if (d->rows < 0 || d->c <= 0 || d->c0 <= 0 || d->c1 < 0 || d->c2 < 0) return CSMPN_ERR_BAD_ARG;
-  if (d->mode != 0 && d->mode != 1) return CSMPN_ERR_BAD_ARG;
+  if (d->mode == 2 && d->engine != 1) return CSMPN_ERR_UNSUPPORTED;  // the vertex-table gather lives in the tensor-core engine
+  if (d->mode != 0 && d->mode != 1 && d->mode != 2) return CSMPN_ERR_BAD_ARG;
   if (!d->p0 || (d->c1 > 0 && !d->p1) || (d->c2 > 0 && !d->p2)) return CSMPN_ERR_BAD_ARG;
   if (d->mode == 1 && (!d->src || !d->dst || (d->c1 > 0 && !d->eid && !d->pair_attr) || d->c2 != 0)) return CSMPN_ERR_BAD_ARG;
   if (d->pair_attr && (d->mode != 1 || (d->c1 & 1))) return CSMPN_ERR_BAD_ARG;

@@ -24,6 +24,7 @@ struct FwdArgs {
   int cin, kin8;  // input channels of the first linear, padded to a multiple of 8
   int in_bpt, in_cp;
   int mode, c0, c1, c2, pair_attr;
+  int vt_k, vt_fp;  // mode 2 (vertex-table gather): vertices per row, channels per (feature type, vertex)
   const float *p0, *p1, *p2;
   const int32_t *src, *dst, *eid;
   const float *w1, *b1, *sa, *sb, *wr, *na, *wl, *bl, *wp, *la;
@@ -78,7 +79,7 @@ struct GatherIdx {
 template <int DIM>
 __device__ __forceinline__ void load_gather_idx(const FwdArgs& a, int64_t row0, GatherIdx<DIM>& gi) {
   constexpr int N = ApiItems<DIM>::N, TOT = ApiItems<DIM>::TOT;
-  if (a.mode != 1) return;
+  if (a.mode == 0) return;
   const int ct = (int)threadIdx.x - 32;
 #pragma unroll
   for (int i = 0; i < N; ++i) {
@@ -87,9 +88,15 @@ __device__ __forceinline__ void load_gather_idx(const FwdArgs& a, int64_t row0, 
     ApiItems<DIM>::decode(it, r, cl, h);
     const int64_t R = row0 + r;
     const bool ok = it < TOT && R < a.rows;
-    gi.d[i] = ok ? a.dst[R] : 0;
-    gi.s[i] = ok ? a.src[R] : 0;
-    gi.e[i] = (ok && a.c1 > 0 && !a.pair_attr) ? a.eid[R] : 0;
+    if (a.mode == 2) {  // the (up to three) table rows of this row's vertices, in the row's vertex order
+      gi.d[i] = ok ? a.src[R * a.vt_k] : 0;
+      gi.s[i] = (ok && a.vt_k > 1) ? a.src[R * a.vt_k + 1] : 0;
+      gi.e[i] = (ok && a.vt_k > 2) ? a.src[R * a.vt_k + 2] : 0;
+    } else {
+      gi.d[i] = ok ? a.dst[R] : 0;
+      gi.s[i] = ok ? a.src[R] : 0;
+      gi.e[i] = (ok && a.c1 > 0 && !a.pair_attr) ? a.eid[R] : 0;
+    }
   }
 }
 
@@ -106,7 +113,12 @@ __device__ __forceinline__ void gather_chunk_api(const FwdArgs& a, int64_t row0,
     const int64_t R = row0 + r;
     v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (it < TOT && R < a.rows && c < a.cin) {
-      if (a.mode == 1) {
+      if (a.mode == 2) {
+        // channel c = (type t, vertex slot j, feature f): c = (t * k + j) * fp + f  ->  table[vertex_j][t * fp + f]
+        const int kf = a.vt_k * a.vt_fp, t = c / kf, j = (c - t * kf) / a.vt_fp, f = c - t * kf - j * a.vt_fp;
+        const int64_t vrow = j == 0 ? gi.d[i] : j == 1 ? gi.s[i] : gi.e[i];
+        v[i] = __ldg(reinterpret_cast<const float4*>(a.p0 + (vrow * (a.c0 / a.vt_k) + t * a.vt_fp + f) * B + 4 * h));
+      } else if (a.mode == 1) {
         if (c < a.c0) {
           const int64_t d = gi.d[i], s = gi.s[i];
           const float4 x = __ldg(reinterpret_cast<const float4*>(a.p0 + (d * a.c0 + c) * B + 4 * h));
@@ -850,6 +862,7 @@ int launch_fwd(const csmpn_block_desc& d, cudaStream_t stream) {
   a.in_bpt = d.in_bpt;
   a.in_cp = round_up(a.cin, 16);
   a.mode = d.mode; a.c0 = d.c0; a.c1 = d.c1; a.c2 = d.c2; a.pair_attr = d.pair_attr;
+  a.vt_k = d.vt_k; a.vt_fp = d.vt_fp;
   a.p0 = d.p0; a.p1 = d.p1; a.p2 = d.p2;
   a.src = d.src; a.dst = d.dst; a.eid = d.eid;
   a.w1 = d.w1; a.b1 = d.b1; a.sa = d.sa; a.sb = d.sb; a.wr = d.wr; a.na = d.na; a.wl = d.wl; a.bl = d.bl; a.wp = d.wp; a.la = d.la;
@@ -858,6 +871,7 @@ int launch_fwd(const csmpn_block_desc& d, cudaStream_t stream) {
   a.dbg = debug_buffer();
   if (!a.y2 || !a.y) return CSMPN_ERR_BAD_ARG;
   if (a.in_bpt && (d.mode != 0 || d.c1 || d.c2)) return CSMPN_ERR_BAD_ARG;
+  if (d.mode == 2 && (d.vt_k < 1 || d.vt_k > 3 || d.vt_fp < 1 || d.c0 % (d.vt_k * d.vt_fp) || d.c1 || d.c2 || !d.src)) return CSMPN_ERR_BAD_ARG;
   if (a.out_bpt && d.res) return CSMPN_ERR_BAD_ARG;
   const FwdPlan p = fwd_plan<DIM>(a.cin, a.C);
   if (!p.ok) return CSMPN_ERR_UNSUPPORTED;

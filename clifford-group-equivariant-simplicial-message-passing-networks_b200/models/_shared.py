@@ -123,16 +123,47 @@ class SharedSimplicialBase(nn.Module):
         rows = self.simplex_rows(graph)
         n_out = out_channels if out_channels is not None else self.num_hidden
         x = torch.zeros((graph.x_ind.shape[0], n_out, B), device=graph.x_ind.device)
+        table = [None]  # per-vertex feature table of THIS forward (values change from step to step: never cached on the batch)
         for d in range(self.max_dim + 1):
             idx = rows[d]
             if idx.numel() == 0:
                 continue
             orders = vertex_orders(d + 1, idx.device)
             verts = simplex_vertices[idx, : d + 1][:, orders].reshape(-1, d + 1)          # [n_d * (d+1)!, d+1]
-            emb = self.cl_feature_embedding[d](self.vertex_features(graph, verts))
+            emb = self._embed_fused(graph, verts, d, table) if d > 0 else None
+            if emb is None:
+                emb = self.cl_feature_embedding[d](self.vertex_features(graph, verts))
             emb = emb.reshape(idx.shape[0], math.factorial(d + 1), -1, B).sum(dim=1)
             x = x.index_copy(0, idx, emb)
         return x
+
+    def _embed_fused(self, graph, verts, d, table_slot):
+        """permute-embed without the permuted rows: one per-vertex feature table (the features of every vertex ONCE, in the
+        channel order vertex_features uses for a single vertex) + the vertex ids of every (simplex, order) row; the first
+        block of cl_feature_embedding[d] gathers its (type, vertex slot, feature) channels itself (fused.embed_rows_forward)"""
+        from . import fused
+        from .cegnn_utils import CEMLP
+
+        emb_mod = self.cl_feature_embedding[d]
+        if not (isinstance(emb_mod, CEMLP) and fused.enabled(self.algebra) and self.algebra.dim in (2, 3)):
+            return None
+        rows0 = self.simplex_rows(graph)[0]
+        if table_slot[0] is None:
+            table_slot[0] = self.vertex_features(graph, rows0.unsqueeze(1))       # [V, types * fp, B], k = 1
+        table = table_slot[0]
+        fp = table.shape[1] // self.vertex_feature_types
+        # vertex ids are rows of the collated simplex axis; the table is indexed by position among the vertices
+        vpos = getattr(graph, "_csmpn_vertex_pos", None)
+        if vpos is None:
+            vpos = torch.zeros(graph.x_ind.shape[0], dtype=torch.int32, device=rows0.device)
+            vpos[rows0] = torch.arange(rows0.shape[0], dtype=torch.int32, device=rows0.device)
+            try:
+                graph._csmpn_vertex_pos = vpos   # structure only (like simplex_rows): safe to keep on the batch
+            except Exception:
+                pass
+        return fused.embed_rows_forward(self.algebra, list(emb_mod.layers), table, vpos[verts], fp)
+
+    vertex_feature_types = 1   # feature types concatenated by vertex_features (md17: pos | vel | charge = 3)
 
     def grade1(self, t):
         """[..., dim] vectors -> grade-1 multivectors"""

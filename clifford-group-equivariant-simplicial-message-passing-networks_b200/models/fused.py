@@ -35,6 +35,7 @@ class BlockDesc(ctypes.Structure):
         ("engine", c_int32), ("in_bpt", c_int32), ("out_bpt", c_int32), ("stage_mask", c_int32),
         ("save_y2", c_void_p), ("save_x0", c_void_p),
         ("pair_attr", c_int32),
+        ("vt_k", c_int32), ("vt_fp", c_int32),
         ("fwd_ws", c_void_p), ("fwd_ws_bytes", c_int64),
     ]
 
@@ -301,11 +302,14 @@ class TcBlockFn(torch.autograd.Function):
         pair = bool(cfg.get("pair_attr")) and not in_bpt
         if pair:
             chans[1] *= 2  # p1 is the per-simplex table: every pair sees table[src] | table[dst]
+        vt = cfg.get("vertex_table") if mode == 2 else None  # (vertex ids int32 [rows, k], channels per (type, vertex))
+        if vt is not None:
+            chans = [srcs[0].shape[1] * vt[0].shape[1], 0, 0]  # p0 is the per-vertex table [V, types * fp, B]
         c = w1.shape[0]
         cin = sum(chans)
         if cin != w1.shape[1]:
             raise ValueError(f"tensor-core block: input channels {chans} do not match weight {tuple(w1.shape)}")
-        rows = cfg["rows"] if in_bpt else (sgraph.csr.n_pairs if mode == 1 else srcs[0].shape[0])
+        rows = cfg["rows"] if in_bpt else (sgraph.csr.n_pairs if mode == 1 else (vt[0].shape[0] if vt is not None else srcs[0].shape[0]))
         params = tuple(None if t is None else f32c(t) for t in (w1, b1, sa, sb, wr, na, wl, bl, wp, la))
         dev = srcs[0].device
         y = bpt_empty(dim, rows, c, dev) if out_bpt else torch.empty((rows, c, B), dtype=torch.float32, device=dev)
@@ -318,6 +322,8 @@ class TcBlockFn(torch.autograd.Function):
         d.engine, d.in_bpt, d.out_bpt = 1, int(in_bpt), int(out_bpt)
         d.save_y2 = y2.data_ptr()
         d.save_x0 = None if x0 is None else x0.data_ptr()
+        if vt is not None:
+            d.src, d.vt_k, d.vt_fp = vt[0].data_ptr(), vt[0].shape[1], vt[1]
         nws = lib().csmpn_block_fwd_workspace(dim, ctypes.byref(d))
         if nws < 0:
             raise _lib.CsmpnError("tensor-core block forward: unsupported configuration")
@@ -335,7 +341,7 @@ class TcBlockFn(torch.autograd.Function):
                                   *([] if x0 is None else [x0]))
             ctx.meta = (dim, mode, sgraph, chans, c, rows, [t is not None for t in srcs], [t is not None for t in params],
                         res is not None, [None if t is None else t.shape for t in (w1, b1, sa, sb, wr, na, wl, bl, wp, la)],
-                        [None if t is None else t.shape for t in (p0, p1, p2)], in_bpt, out_bpt, x0 is not None, pair)
+                        [None if t is None else t.shape for t in (p0, p1, p2)], in_bpt, out_bpt, x0 is not None, pair, vt)
         return y
 
     @staticmethod
@@ -344,7 +350,7 @@ class TcBlockFn(torch.autograd.Function):
 
 
 def _tc_block_backward(ctx, gy):
-    (dim, mode, sgraph, chans, c, rows, src_mask, par_mask, has_res, pshapes, sshapes, in_bpt, out_bpt, has_x0, pair) = ctx.meta
+    (dim, mode, sgraph, chans, c, rows, src_mask, par_mask, has_res, pshapes, sshapes, in_bpt, out_bpt, has_x0, pair, vt) = ctx.meta
     saved = list(ctx.saved_tensors)
     srcs = [saved.pop(0) if m else None for m in src_mask]
     params = [saved.pop(0) if m else None for m in par_mask]
@@ -358,10 +364,16 @@ def _tc_block_backward(ctx, gy):
     d.engine, d.in_bpt, d.out_bpt = 1, int(in_bpt), int(out_bpt)
     d.save_y2 = y2.data_ptr()
     d.save_x0 = None if x0 is None else x0.data_ptr()
-    gx = bpt_empty(dim, rows, cin, dev) if in_bpt else torch.empty((rows, cin, B), dtype=torch.float32, device=dev)
+    if vt is not None:
+        if ctx.needs_input_grad[1]:
+            raise _lib.CsmpnError("the vertex-table gather (mode 2) has no gradient w.r.t. the table: its rows are input data")
+        d.src, d.vt_k, d.vt_fp = vt[0].data_ptr(), vt[0].shape[1], vt[1]
+        gx = None  # no grad_x GEMM at all
+    else:
+        gx = bpt_empty(dim, rows, cin, dev) if in_bpt else torch.empty((rows, cin, B), dtype=torch.float32, device=dev)
     pg = [None if t is None else torch.empty_like(t) for t in params]
     g = BlockGrads()
-    g.grad_y, g.grad_x = gy.data_ptr(), gx.data_ptr()
+    g.grad_y, g.grad_x = gy.data_ptr(), None if gx is None else gx.data_ptr()
     g.gy_bpt, g.gx_bpt = int(out_bpt), int(in_bpt)
     names = ("g_w1", "g_b1", "g_sa", "g_sb", "g_wr", "g_na", "g_wl", "g_bl", "g_wp", "g_la")
     for n, t in zip(names, pg):
@@ -377,7 +389,9 @@ def _tc_block_backward(ctx, gy):
         check(lib().csmpn_block_bwd(dim, ctypes.byref(d), ctypes.byref(g), ptr(ws), ws.numel(), stream_ptr(dev)),
               "block_bwd (tensor-core)")
     gsrc = [None, None, None]
-    if in_bpt:
+    if vt is not None:
+        pass
+    elif in_bpt:
         gsrc[0] = gx
     elif mode == 0:
         off = 0
@@ -395,7 +409,7 @@ def _tc_block_backward(ctx, gy):
         gsrc[0] = gh
         if srcs[1] is not None and ctx.needs_input_grad[2]:
             gsrc[1] = _extra_channel_grad(gx, cin, chans, B, sgraph, srcs[1], rows, pair, dev)
-    if not in_bpt:
+    if not in_bpt and vt is None:
         gsrc = [None if t is None else t.reshape(s) for t, s in zip(gsrc, sshapes)]
     gres = gy if has_res else None
     pgr = [None if t is None else t.reshape(s) for t, s in zip(pg, pshapes)]
@@ -542,6 +556,29 @@ def block_forward(algebra, layer, x, p1=None, p2=None, res=None, mode=0, sgraph=
         cfg.update(in_bpt=in_bpt, out_bpt=out_bpt, rows=bpt_rows, c_in=layer[0].in_features)
         return TcBlockFn.apply(cfg, x, p1, p2, res, *params)
     return FusedBlockFn.apply(cfg, x, p1, p2, res, *params)
+
+
+def embed_rows_forward(algebra, blocks, table, vertex_rows, fp):
+    """The permute-embed step of ``embed_simplicial_complex`` (md17_cssmpnn.py:85-120) for one simplex dimension, without
+    materialising the permuted feature rows: ``table`` [V, types * fp, B] holds every vertex' features once, ``vertex_rows``
+    int32 [rows, k] the table rows of the k vertices of each (simplex, vertex order) row.  The first block of the CEMLP
+    gathers its input channels ``(type, vertex slot, feature)`` itself (csmpn_block_desc mode 2); returns [rows, C, B], or
+    None when these blocks do not run on the tensor-core engine (the caller then builds the rows with torch indexing)."""
+    rows = vertex_rows.shape[0]
+    need_grad = _need_grad(*[t for b in blocks for t in _block_params(b)])
+    k = vertex_rows.shape[1]
+    lin = blocks[0][0]
+    if (not all(_block_supported(b) for b in blocks) or lin.in_features != table.shape[1] * k or table.requires_grad
+            or not _chain_uses_tc(algebra, blocks, need_grad, rows)):
+        return None
+    cfg = {"dim": algebra.dim, "mode": 2, "sgraph": None, "need_grad": need_grad, "pair_attr": False,
+           "vertex_table": (vertex_rows.contiguous(), int(fp)), "in_bpt": False, "out_bpt": len(blocks) > 1, "rows": None,
+           "c_in": lin.in_features}
+    u = TcBlockFn.apply(cfg, f32c(table), None, None, None, *_block_params(blocks[0]))
+    for i, blk in enumerate(blocks[1:]):
+        last = i == len(blocks) - 2
+        u = block_forward(algebra, blk, u, bpt_rows=rows, out_bpt=not last)
+    return u
 
 
 def _chain_uses_tc(algebra, blocks, need_grad, rows) -> bool:

@@ -43,6 +43,8 @@ class HullsCliffordSharedSimplicialMPNN(SharedSimplicialBase):
             h = layer(h, edges, node_attr=node_attr, edge_attr=edge_attr)
         return self.projection(h)
 
+    vertex_feature_types = 1
+
     def vertex_features(self, graph, verts):
         return self.grade1(graph.input[verts])
 

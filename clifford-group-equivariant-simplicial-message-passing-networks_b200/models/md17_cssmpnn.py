@@ -35,6 +35,8 @@ class CliffordSharedSimplicialMPNN_md17(SharedSimplicialBase):
     def _setup_metrics(self):
         return MetricCollection({"loss": Loss(), "ade_loss": Loss(), "fde_loss": Loss()})
 
+    vertex_feature_types = 3
+
     def vertex_features(self, graph, verts):
         rows, k = verts.shape
         pos = self.grade1(graph.pos[verts].reshape(rows, -1, 3))         # k * frames channels, vertex-major

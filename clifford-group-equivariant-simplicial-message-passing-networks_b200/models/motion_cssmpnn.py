@@ -34,6 +34,8 @@ class MotionCliffordSharedSimplicialMPNN(SharedSimplicialBase):
     def _setup_metrics(self):
         return MetricCollection({"loss": Loss()})
 
+    vertex_feature_types = 2
+
     def vertex_features(self, graph, verts):
         return torch.cat((self.grade1(graph.pos[verts]), self.grade1(graph.vel[verts])), dim=1)
 

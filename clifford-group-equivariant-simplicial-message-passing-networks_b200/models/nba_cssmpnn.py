@@ -39,6 +39,8 @@ class NBACliffordSharedSimplicialMPNN(SharedSimplicialBase):
     def _setup_metrics(self):
         return MetricCollection({"loss": Loss(), "ade_loss": Loss(), "fde_loss": Loss()})
 
+    vertex_feature_types = 2
+
     def vertex_features(self, graph, verts):
         rows = verts.shape[0]
         pos = self.grade1(graph.pos[verts].reshape(rows, -1, 2))

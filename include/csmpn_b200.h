@@ -159,6 +159,7 @@ int csmpn_segment_expand(const float* grad_out, const int64_t* dst, const int32_
  *   mode 0 (concat):  [ p0[r, 0:c0] | p1[r, 0:c1] | p2[r, 0:c2] ]                (p1 / p2 may be NULL with c = 0)
  *   mode 1 (gather):  [ p0[dst[r], 0:c0] - p0[src[r], 0:c0] | p1[eid[r], 0:c1] ]  rows = adjacency pairs in
  *                     receiver-sorted order; src/dst/eid are int32 [rows] (eid = original pair id)
+ *   mode 2 (vertex-table gather, engine 1): the (d+1)!-permutation rows of embed_simplicial_complex, see vt_k / vt_fp
  * Forward output y[r, 0:c] (+ res[r] when res != NULL).  When save_* are non-NULL the forward also stores the three
  * [rows, c, B] intermediates the backward needs (pre-SiLU y1, pre-normalisation right input xr, pre-LayerNorm o).  */
 typedef struct csmpn_block_desc {
@@ -199,6 +200,12 @@ typedef struct csmpn_block_desc {
                                            table = p1 [n_nodes, c1/2, B] (per-simplex attributes, e.g. the simplex-type
                                            embedding of md17_cssmpnn.py:122-133) instead of a materialised [E, c1, B]
                                            edge_attr read through eid; its gradient: csmpn_scatter_pair_sorted */
+  int32_t vt_k, vt_fp;                  /* mode 2 (engine 1): "permute-embed" gather of embed_simplicial_complex
+                                           (md17_cssmpnn.py:85-120): row r is one vertex ORDER of a simplex, src[r * vt_k + j]
+                                           = row of its j-th vertex in the per-vertex feature table p0 [V, c0 / vt_k, B];
+                                           input channel (t * vt_k + j) * vt_fp + f of the row = table channel t * vt_fp + f of
+                                           vertex j (feature type t, vt_fp channels per type) -- the reference's
+                                           cat(pos[verts], vel[verts], ...) layout, never materialised */
   void* fwd_ws;                         /* engine 1, wide blocks (csmpn_block_fwd_workspace > 0): device scratch of the
                                            forward for the pre-split weight images streamed with the K chunks */
   int64_t fwd_ws_bytes;
