@@ -264,13 +264,18 @@ def test_fused_permute_embed_equals_materialised_rows(gold, name, monkeypatch):
             g.pos = g.loc
         calls = []
         orig = fused.embed_rows_forward
-        monkeypatch.setattr(fused, "embed_rows_forward", lambda *a, **k: (calls.append(1), orig(*a, **k))[1])
+        def counted(*a, **k):
+            r = orig(*a, **k)
+            calls.append(r is not None)
+            return r
+
+        monkeypatch.setattr(fused, "embed_rows_forward", counted)
         x = m.embed_simplicial_complex(g)
         params = [p for e in m.cl_feature_embedding for p in e.parameters()]
         grads = torch.autograd.grad(x.square().sum(), params)
         monkeypatch.setattr(fused, "embed_rows_forward", orig)
-        out[tc] = (x.detach(), grads, len(calls))
-    assert out["1"][2] >= 1  # the fused path ran for at least one simplex dimension
+        out[tc] = (x.detach(), grads, sum(calls))
+    assert out["1"][2] >= 1 and out["0"][2] == 0  # the fused path ran for at least one simplex dimension / never without the engine
     assert_close(out["1"][0], out["0"][0], 1e-5, f"{name} embedding")
     for a, c in zip(out["1"][1], out["0"][1]):
         assert_close(a, c, 1e-4, f"{name} embedding parameter gradient")
