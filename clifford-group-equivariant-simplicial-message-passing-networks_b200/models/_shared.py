@@ -145,8 +145,10 @@ class SharedSimplicialBase(nn.Module):
         from .cegnn_utils import CEMLP
 
         emb_mod = self.cl_feature_embedding[d]
-        if not (isinstance(emb_mod, CEMLP) and fused.enabled(self.algebra) and self.algebra.dim in (2, 3)):
+        mlps = [emb_mod] if isinstance(emb_mod, CEMLP) else (list(emb_mod) if isinstance(emb_mod, nn.Sequential) else [])
+        if not (mlps and all(isinstance(m, CEMLP) for m in mlps) and fused.enabled(self.algebra) and self.algebra.dim in (2, 3)):
             return None
+        blocks = [blk for m in mlps for blk in m.layers]   # nba: two CEMLPs in a row for the triangles (nba_cssmpnn.py:57-60)
         rows0 = self.simplex_rows(graph)[0]
         if table_slot[0] is None:
             table_slot[0] = self.vertex_features(graph, rows0.unsqueeze(1))       # [V, types * fp, B], k = 1
@@ -161,7 +163,7 @@ class SharedSimplicialBase(nn.Module):
                 graph._csmpn_vertex_pos = vpos   # structure only (like simplex_rows): safe to keep on the batch
             except Exception:
                 pass
-        return fused.embed_rows_forward(self.algebra, list(emb_mod.layers), table, vpos[verts], fp)
+        return fused.embed_rows_forward(self.algebra, blocks, table, vpos[verts], fp)
 
     vertex_feature_types = 1   # feature types concatenated by vertex_features (md17: pos | vel | charge = 3)
 
