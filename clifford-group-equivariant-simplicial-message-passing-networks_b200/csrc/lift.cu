@@ -25,27 +25,39 @@
 namespace csmpn {
 
 constexpr int kLiftWarps = 4;      // complexes per CTA
-constexpr int kMaxV = 32;          // vertices per complex (one adjacency bit mask per vertex)
-constexpr int kMaxE = 496;         // 32 choose 2
+constexpr int kMaxV = 32;          // vertices per complex of the one-word kernels (one 32-bit adjacency mask per vertex)
+constexpr int kMaxV2 = 64;         // ... of the two-word kernels (uint64 masks), selected by csmpn_lift_desc.max_vertices > 32
 
 constexpr int kMotionV = 31, kMotionE = 12, kMotionT = 4, kMotionFixedPairs = 96;
 __constant__ uint8_t c_motion_edges[kMotionE][2] = {{6, 7}, {7, 8}, {6, 8}, {1, 2}, {2, 3}, {1, 3}, {24, 25}, {25, 26},
                                                     {24, 26}, {22, 23}, {21, 22}, {21, 23}};
 __constant__ uint8_t c_motion_tris[kMotionT][3] = {{6, 7, 8}, {1, 2, 3}, {24, 25, 26}, {21, 22, 23}};
 
-struct LiftWarp {
-  uint32_t adj[kMaxV];        // neighbour mask of every vertex
-  uint32_t adj0[kMaxV];       // clique modes with filters: the unfiltered graph (triangle candidates are ITS 3-cliques)
-  uint32_t cof[kMaxE];        // per edge (a,b): every x such that {a,b,x} is a triangle of the complex
-  uint16_t ebase[kMaxV + 1];  // number of edges whose smaller vertex is < a
-  uint16_t tbase[kMaxE + 1];  // number of triangles whose smallest edge (p,q) precedes edge e
-  uint16_t cbase[kMaxE + 1];  // number of (triangle, edge) incidences of the edges preceding e
-  uint8_t ea[kMaxE], eb[kMaxE];
+// M = mask word (uint32_t: up to 32 vertices, uint64_t: up to 64), KV = vertex capacity
+template <typename M, int KV>
+struct LiftWarpT {
+  static constexpr int KE = KV * (KV - 1) / 2;
+  M adj[KV];                  // neighbour mask of every vertex
+  M adj0[KV];                 // clique modes with filters: the unfiltered graph (triangle candidates are ITS 3-cliques)
+  M cof[KE];                  // per edge (a,b): every x such that {a,b,x} is a triangle of the complex
+  uint16_t ebase[KV + 1];     // number of edges whose smaller vertex is < a
+  uint32_t tbase[KE + 1];     // number of triangles whose smallest edge (p,q) precedes edge e
+  uint32_t cbase[KE + 1];     // number of (triangle, edge) incidences of the edges preceding e
+  uint8_t ea[KE], eb[KE];
   int n, n_e, n_t;
 };
 
-__device__ __forceinline__ uint32_t bits_above(int v) { return v >= 31 ? 0u : ~((2u << v) - 1u); }  // {v+1 .. 31}
-__device__ __forceinline__ uint32_t bits_below(int v) { return (1u << v) - 1u; }                    // {0 .. v-1}
+template <typename M> __device__ __forceinline__ M bit_of(int v) { return (M)1 << v; }
+template <typename M> __device__ __forceinline__ M bits_above(int v) {  // {v+1 .. capacity-1}
+  return v >= (int)(8 * sizeof(M)) - 1 ? (M)0 : ~((((M)2) << v) - (M)1);
+}
+template <typename M> __device__ __forceinline__ M bits_below(int v) { return (((M)1) << v) - (M)1; }  // {0 .. v-1}
+__device__ __forceinline__ int popc(uint32_t m) { return __popc(m); }
+__device__ __forceinline__ int popc(uint64_t m) { return __popcll(m); }
+__device__ __forceinline__ int ffs0(uint32_t m) { return __ffs(m) - 1; }
+__device__ __forceinline__ int ffs0(uint64_t m) { return __ffsll((long long)m) - 1; }
+__device__ __forceinline__ void atomic_or(uint32_t* p, uint32_t v) { atomicOr(p, v); }
+__device__ __forceinline__ void atomic_or(uint64_t* p, uint64_t v) { atomicOr(reinterpret_cast<unsigned long long*>(p), (unsigned long long)v); }
 
 __device__ __forceinline__ bool clique_like(int mode) { return mode == CSMPN_LIFT_CLIQUE || mode == CSMPN_LIFT_KNN; }
 
@@ -108,65 +120,72 @@ __device__ __forceinline__ void frozenset_order(const int* v, int k, float* out)
 }
 
 // index of the edge (u, w), u < w, in lexicographic order
-__device__ __forceinline__ int edge_index_of(const LiftWarp& s, int u, int w) {
-  return s.ebase[u] + __popc(s.adj[u] & bits_above(u) & bits_below(w));
+template <typename M, int KV>
+__device__ __forceinline__ int edge_index_of(const LiftWarpT<M, KV>& s, int u, int w) {
+  return s.ebase[u] + popc((M)(s.adj[u] & bits_above<M>(u) & bits_below<M>(w)));
 }
 
-// Build the adjacency masks, the lexicographic edge list and the triangle tables of complex `c` (one warp).
-__device__ void lift_build(LiftWarp& s, const csmpn_lift_desc& d, int c, int lane) {
+// Build the adjacency masks, the lexicographic edge list and the triangle tables of complex `c` (one warp; vertex v is
+// handled by lane v % 32).
+template <typename M, int KV>
+__device__ void lift_build(LiftWarpT<M, KV>& s, const csmpn_lift_desc& d, int c, int lane) {
   const int v0 = d.vptr[c], n = d.vptr[c + 1] - v0;
   if (lane == 0) s.n = n;
-  uint32_t mine = 0;
   if (d.mode == CSMPN_LIFT_RIPS) {
     // gudhi RipsComplex: Euclidean distance in double over the float32 coordinates, edge iff dist <= max_edge_length
-    if (lane < n) {
-      for (int j = 0; j < n; ++j) {
-        if (j == lane) continue;
-        double acc = 0.0;
-        for (int k = 0; k < d.point_dim; ++k) {
-          const double diff = __dsub_rn((double)d.points[(int64_t)(v0 + lane) * d.point_dim + k],
-                                        (double)d.points[(int64_t)(v0 + j) * d.point_dim + k]);
-          acc = __dadd_rn(acc, __dmul_rn(diff, diff));
+    for (int v = lane; v < KV; v += 32) {
+      M mine = 0;
+      if (v < n) {
+        for (int j = 0; j < n; ++j) {
+          if (j == v) continue;
+          double acc = 0.0;
+          for (int k = 0; k < d.point_dim; ++k) {
+            const double diff = __dsub_rn((double)d.points[(int64_t)(v0 + v) * d.point_dim + k],
+                                          (double)d.points[(int64_t)(v0 + j) * d.point_dim + k]);
+            acc = __dadd_rn(acc, __dmul_rn(diff, diff));
+          }
+          if (sqrt(acc) <= d.max_edge_length) mine |= bit_of<M>(j);
         }
-        if (sqrt(acc) <= d.max_edge_length) mine |= 1u << j;
       }
+      s.adj[v] = mine;
     }
-    s.adj[lane] = mine;
   } else if (clique_like(d.mode)) {
-    s.adj[lane] = 0;
+    for (int v = lane; v < KV; v += 32) s.adj[v] = 0;
     __syncwarp();
     if (d.mode == CSMPN_LIFT_CLIQUE) {
       const int64_t p0 = d.pptr[c], p1 = d.pptr[c + 1];
       for (int64_t p = p0 + lane; p < p1; p += 32) {
         const int a = (int)d.pairs[p], b = (int)d.pairs[d.n_pairs + p];
         if (a != b && a >= 0 && b >= 0 && a < n && b < n) {
-          atomicOr(&s.adj[a], 1u << b);
-          atomicOr(&s.adj[b], 1u << a);
+          atomic_or(&s.adj[a], bit_of<M>(b));
+          atomic_or(&s.adj[b], bit_of<M>(a));
         }
       }
-    } else if (lane < n) {
+    } else {
       // knn_graph(points, k) (csmpn/data/md17.py:64, nba.py:48; torch_cluster): every vertex is joined to its k nearest
       // other vertices, nearest first, ties to the smaller index; the lift only uses the UNDIRECTED edge set
       // (nx.Graph, utils.py:171-172).  Distances in double over the fp32 coordinates.
-      uint32_t taken = 1u << lane;
-      const int kk = d.knn_k < n - 1 ? d.knn_k : n - 1;
-      for (int t = 0; t < kk; ++t) {
-        double best = 0.0;
-        int bj = -1;
-        for (int j = 0; j < n; ++j) {
-          if (taken >> j & 1u) continue;
-          double acc = 0.0;
-          for (int k = 0; k < d.point_dim; ++k) {
-            const double diff = __dsub_rn((double)d.points[(int64_t)(v0 + lane) * d.point_dim + k],
-                                          (double)d.points[(int64_t)(v0 + j) * d.point_dim + k]);
-            acc = __dadd_rn(acc, __dmul_rn(diff, diff));
+      for (int v = lane; v < n; v += 32) {
+        M taken = bit_of<M>(v);
+        const int kk = d.knn_k < n - 1 ? d.knn_k : n - 1;
+        for (int t = 0; t < kk; ++t) {
+          double best = 0.0;
+          int bj = -1;
+          for (int j = 0; j < n; ++j) {
+            if ((taken >> j) & 1) continue;
+            double acc = 0.0;
+            for (int k = 0; k < d.point_dim; ++k) {
+              const double diff = __dsub_rn((double)d.points[(int64_t)(v0 + v) * d.point_dim + k],
+                                            (double)d.points[(int64_t)(v0 + j) * d.point_dim + k]);
+              acc = __dadd_rn(acc, __dmul_rn(diff, diff));
+            }
+            const double dist = sqrt(acc);
+            if (bj < 0 || dist < best) { best = dist; bj = j; }
           }
-          const double dist = sqrt(acc);
-          if (bj < 0 || dist < best) { best = dist; bj = j; }
+          taken |= bit_of<M>(bj);
+          atomic_or(&s.adj[v], bit_of<M>(bj));
+          atomic_or(&s.adj[bj], bit_of<M>(v));
         }
-        taken |= 1u << bj;
-        atomicOr(&s.adj[lane], 1u << bj);
-        atomicOr(&s.adj[bj], 1u << lane);
       }
     }
     __syncwarp();
@@ -174,63 +193,77 @@ __device__ void lift_build(LiftWarp& s, const csmpn_lift_desc& d, int c, int lan
       // utils.py:181-200: an edge of the graph enters the complex iff its length is <= edge_th OR it is a face of a kept
       // triangle (SimplexTree.insert adds all faces); a 3-clique of the graph is kept iff its area is <= tri_th
       const float* P = d.points + (int64_t)v0 * d.point_dim;
-      const uint32_t a0 = lane < n ? s.adj[lane] : 0u;
-      s.adj0[lane] = a0;
+      for (int v = lane; v < KV; v += 32) s.adj0[v] = v < n ? s.adj[v] : (M)0;
       __syncwarp();
-      uint32_t keep = 0;
-      uint32_t m = a0;
-      while (m) {
-        const int b = __ffs(m) - 1;
-        m &= m - 1;
-        bool k = lift_edge_len(P, d.point_dim, lane, b) <= d.edge_th;
-        if (!k && d.max_dim >= 2) {
-          uint32_t t = a0 & s.adj0[b];
-          while (t && !k) {
-            const int x = __ffs(t) - 1;
-            t &= t - 1;
-            k = lift_tri_area_sorted(P, d.point_dim, lane, b, x) <= d.tri_th;
+      M keepv[KV / 32];
+#pragma unroll
+      for (int i = 0; i < KV / 32; ++i) {
+        const int v = lane + 32 * i;
+        M keep = 0;
+        M m = v < n ? s.adj0[v] : (M)0;
+        while (m) {
+          const int b = ffs0(m);
+          m &= m - 1;
+          bool k = lift_edge_len(P, d.point_dim, v, b) <= d.edge_th;
+          if (!k && d.max_dim >= 2) {
+            M t = s.adj0[v] & s.adj0[b];
+            while (t && !k) {
+              const int x = ffs0(t);
+              t &= t - 1;
+              k = lift_tri_area_sorted(P, d.point_dim, v, b, x) <= d.tri_th;
+            }
           }
+          if (k) keep |= bit_of<M>(b);
         }
-        if (k) keep |= 1u << b;
+        keepv[i] = keep;
       }
       __syncwarp();
-      s.adj[lane] = keep;
+#pragma unroll
+      for (int i = 0; i < KV / 32; ++i) s.adj[lane + 32 * i] = keepv[i];
     }
   } else {  // CSMPN_LIFT_FACETS: two vertices are joined iff some facet holds both
-    if (lane < n) {
-      for (int f = d.fptr[c]; f < d.fptr[c + 1]; ++f) {
-        uint32_t m = 0;
-        for (int k = 0; k < d.facet_size; ++k) m |= 1u << (int)d.facets[(int64_t)f * d.facet_size + k];
-        if (m >> lane & 1u) mine |= m;
+    for (int v = lane; v < KV; v += 32) {
+      M mine = 0;
+      if (v < n) {
+        for (int f = d.fptr[c]; f < d.fptr[c + 1]; ++f) {
+          M m = 0;
+          for (int k = 0; k < d.facet_size; ++k) m |= bit_of<M>((int)d.facets[(int64_t)f * d.facet_size + k]);
+          if ((m >> v) & 1) mine |= m;
+        }
+        mine &= ~bit_of<M>(v);
       }
-      mine &= ~(1u << lane);
+      s.adj[v] = mine;
     }
-    s.adj[lane] = mine;
   }
   __syncwarp();
-  // edges, lexicographic: vertex a owns the edges (a, b > a)
-  const uint32_t up = lane < n ? (s.adj[lane] & bits_above(lane)) : 0u;
-  int n_e;
-  const int eb0 = warp_excl_scan(__popc(up), lane, &n_e);
-  s.ebase[lane] = (uint16_t)eb0;
-  if (lane == 0) { s.ebase[kMaxV] = (uint16_t)n_e; s.n_e = n_e; }
-  {
-    uint32_t m = up;
+  // edges, lexicographic: vertex a owns the edges (a, b > a); vertices in rounds of 32 (ascending)
+  int ecarry = 0;
+#pragma unroll
+  for (int i = 0; i < KV / 32; ++i) {
+    const int v = lane + 32 * i;
+    const M up = v < n ? (M)(s.adj[v] & bits_above<M>(v)) : (M)0;
+    int tot;
+    const int eb0 = ecarry + warp_excl_scan(popc(up), lane, &tot);
+    s.ebase[v] = (uint16_t)eb0;
+    M m = up;
     int e = eb0;
     while (m) {
-      const int b = __ffs(m) - 1;
+      const int b = ffs0(m);
       m &= m - 1;
-      s.ea[e] = (uint8_t)lane;
+      s.ea[e] = (uint8_t)v;
       s.eb[e] = (uint8_t)b;
       ++e;
     }
+    ecarry += tot;
   }
+  const int n_e = ecarry;
+  if (lane == 0) { s.ebase[KV] = (uint16_t)n_e; s.n_e = n_e; }
   __syncwarp();
   // triangles: clique complexes close every 3-clique; the facet mode only keeps triples inside one facet
   int tcarry = 0, ccarry = 0;
   for (int e0 = 0; e0 < n_e; e0 += 32) {
     const int e = e0 + lane;
-    uint32_t cand = 0;
+    M cand = 0;
     int a = 0, b = 0;
     if (e < n_e) {
       a = s.ea[e];
@@ -238,20 +271,20 @@ __device__ void lift_build(LiftWarp& s, const csmpn_lift_desc& d, int c, int lan
       cand = s.adj[a] & s.adj[b];
       if (clique_like(d.mode) && d.use_filters) {  // 3-cliques of the UNFILTERED graph whose area passes tri_th
         const float* P = d.points + (int64_t)d.vptr[c] * d.point_dim;
-        uint32_t t = s.adj0[a] & s.adj0[b], keep = 0;
+        M t = s.adj0[a] & s.adj0[b], keep = 0;
         while (t) {
-          const int x = __ffs(t) - 1;
+          const int x = ffs0(t);
           t &= t - 1;
-          if (lift_tri_area_sorted(P, d.point_dim, a, b, x) <= d.tri_th) keep |= 1u << x;
+          if (lift_tri_area_sorted(P, d.point_dim, a, b, x) <= d.tri_th) keep |= bit_of<M>(x);
         }
         cand = keep;
       }
       if (d.mode == CSMPN_LIFT_FACETS) {
-        uint32_t keep = 0;
+        M keep = 0;
         for (int f = d.fptr[c]; f < d.fptr[c + 1]; ++f) {
-          uint32_t m = 0;
-          for (int k = 0; k < d.facet_size; ++k) m |= 1u << (int)d.facets[(int64_t)f * d.facet_size + k];
-          if ((m >> a & 1u) && (m >> b & 1u)) keep |= m;
+          M m = 0;
+          for (int k = 0; k < d.facet_size; ++k) m |= bit_of<M>((int)d.facets[(int64_t)f * d.facet_size + k]);
+          if (((m >> a) & 1) && ((m >> b) & 1)) keep |= m;
         }
         cand &= keep;
       }
@@ -259,18 +292,18 @@ __device__ void lift_build(LiftWarp& s, const csmpn_lift_desc& d, int c, int lan
       s.cof[e] = cand;
     }
     int tt, ct;
-    const int tb = warp_excl_scan(__popc(cand & bits_above(b)), lane, &tt);
-    const int cb = warp_excl_scan(__popc(cand), lane, &ct);
+    const int tb = warp_excl_scan(popc((M)(cand & bits_above<M>(b))), lane, &tt);
+    const int cb = warp_excl_scan(popc(cand), lane, &ct);
     if (e < n_e) {
-      s.tbase[e] = (uint16_t)(tcarry + tb);
-      s.cbase[e] = (uint16_t)(ccarry + cb);
+      s.tbase[e] = (uint32_t)(tcarry + tb);
+      s.cbase[e] = (uint32_t)(ccarry + cb);
     }
     tcarry += tt;
     ccarry += ct;
   }
   if (lane == 0) {
-    s.tbase[n_e] = (uint16_t)tcarry;
-    s.cbase[n_e] = (uint16_t)ccarry;
+    s.tbase[n_e] = (uint32_t)tcarry;
+    s.cbase[n_e] = (uint32_t)ccarry;
     s.n_t = tcarry;
   }
   __syncwarp();
@@ -282,11 +315,12 @@ __device__ __forceinline__ int64_t pairs_of(int mode, int n, int n_e, int n_t) {
   return p;
 }
 
-__global__ void __launch_bounds__(32 * kLiftWarps) lift_count_kernel(csmpn_lift_desc d, int32_t* __restrict__ counts,
-                                                                      int32_t* __restrict__ bad) {
-  __shared__ LiftWarp sm[kLiftWarps];
+template <typename M, int KV, int WARPS>
+__global__ void __launch_bounds__(32 * WARPS) lift_count_kernel(csmpn_lift_desc d, int32_t* __restrict__ counts,
+                                                                 int32_t* __restrict__ bad) {
+  __shared__ LiftWarpT<M, KV> sm[WARPS];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int c = blockIdx.x * kLiftWarps + w;
+  const int c = blockIdx.x * WARPS + w;
   if (c >= d.n_complexes) return;
   if (d.mode == CSMPN_LIFT_MOTION) {
     if (lane == 0) {
@@ -297,11 +331,11 @@ __global__ void __launch_bounds__(32 * kLiftWarps) lift_count_kernel(csmpn_lift_
     return;
   }
   const int n = d.vptr[c + 1] - d.vptr[c];
-  if (n > kMaxV || n < 0) {
+  if (n > KV || n < 0) {
     if (lane == 0) { *bad = 1; counts[2 * c] = 0; counts[2 * c + 1] = 0; }
     return;
   }
-  lift_build(sm[w], d, c, lane);
+  lift_build<M, KV>(sm[w], d, c, lane);
   if (lane == 0) {
     counts[2 * c] = sm[w].n_e;
     counts[2 * c + 1] = sm[w].n_t;
@@ -365,11 +399,12 @@ __device__ __forceinline__ void put_pair(const LiftOut& o, int64_t pos, int64_t 
   o.dst[pos] = b;
 }
 
-__global__ void __launch_bounds__(32 * kLiftWarps) lift_fill_kernel(csmpn_lift_desc d, const int64_t* __restrict__ node_ptr,
-                                                                     const int64_t* __restrict__ pair_ptr, LiftOut o) {
-  __shared__ LiftWarp sm[kLiftWarps];
+template <typename M, int KV, int WARPS>
+__global__ void __launch_bounds__(32 * WARPS) lift_fill_kernel(csmpn_lift_desc d, const int64_t* __restrict__ node_ptr,
+                                                                const int64_t* __restrict__ pair_ptr, LiftOut o) {
+  __shared__ LiftWarpT<M, KV> sm[WARPS];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int c = blockIdx.x * kLiftWarps + w;
+  const int c = blockIdx.x * WARPS + w;
   if (c >= d.n_complexes) return;
   const int64_t nb = node_ptr[c];
   int64_t pp = pair_ptr[c];
@@ -404,15 +439,15 @@ __global__ void __launch_bounds__(32 * kLiftWarps) lift_fill_kernel(csmpn_lift_d
     }
     return;
   }
-  LiftWarp& s = sm[w];
-  lift_build(s, d, c, lane);
+  LiftWarpT<M, KV>& s = sm[w];
+  lift_build<M, KV>(s, d, c, lane);
   const int n = s.n, n_e = s.n_e, n_t = s.n_t;
   const int64_t E0 = nb + n, T0 = nb + n + n_e;
   // ---- simplices: x_ind, node_types, batch
-  if (lane < n) {
-    o.x_ind[(nb + lane) * 3] = (float)lane; o.x_ind[(nb + lane) * 3 + 1] = 0.f; o.x_ind[(nb + lane) * 3 + 2] = 0.f;
-    o.node_types[nb + lane] = 0;
-    o.batch[nb + lane] = c;
+  for (int v = lane; v < n; v += 32) {
+    o.x_ind[(nb + v) * 3] = (float)v; o.x_ind[(nb + v) * 3 + 1] = 0.f; o.x_ind[(nb + v) * 3 + 2] = 0.f;
+    o.node_types[nb + v] = 0;
+    o.batch[nb + v] = c;
   }
   for (int e = lane; e < n_e; e += 32) {
     int v[2] = {s.ea[e], s.eb[e]};
@@ -422,26 +457,38 @@ __global__ void __launch_bounds__(32 * kLiftWarps) lift_fill_kernel(csmpn_lift_d
     o.node_types[E0 + e] = 1;
     o.batch[E0 + e] = c;
   }
-  // ---- block 0_0: upper adjacency through the shared edge ...
+  // ---- block 0_0: upper adjacency through the shared edge (receivers in ascending order, rounds of 32 vertices) ...
   {
-    const uint32_t m0 = lane < n ? s.adj[lane] : 0u;
-    int tot;
-    int pos = warp_excl_scan(__popc(m0), lane, &tot);
-    uint32_t m = m0;
-    while (m) {
-      const int u = __ffs(m) - 1;
-      m &= m - 1;
-      put_pair(o, pp + pos++, nb + u, nb + lane);
+    int carry = 0;
+#pragma unroll
+    for (int i = 0; i < KV / 32; ++i) {
+      const int v = lane + 32 * i;
+      const M m0 = v < n ? s.adj[v] : (M)0;
+      int tot;
+      int pos = carry + warp_excl_scan(popc(m0), lane, &tot);
+      M m = m0;
+      while (m) {
+        const int u = ffs0(m);
+        m &= m - 1;
+        put_pair(o, pp + pos++, nb + u, nb + v);
+      }
+      carry += tot;
     }
-    pp += tot;  // = 2 n_e
+    pp += carry;  // = 2 n_e
     if (!clique_like(d.mode)) {  // ... plus the extra pairs of generate_adjacencies_single (utils.py:90-96)
-      const uint32_t up = m0 & bits_above(lane);
-      int tot2;
-      int q = warp_excl_scan(lane < n ? (n - 1) - __popc(up) : 0, lane, &tot2);
-      if (lane < n)
-        for (int j = 0; j < n; ++j)
-          if (j != lane && !(up >> j & 1u)) put_pair(o, pp + q++, nb + lane, nb + j);
-      pp += tot2;
+      int carry2 = 0;
+#pragma unroll
+      for (int i = 0; i < KV / 32; ++i) {
+        const int v = lane + 32 * i;
+        const M up = v < n ? (M)(s.adj[v] & bits_above<M>(v)) : (M)0;
+        int tot2;
+        int q = carry2 + warp_excl_scan(v < n ? (n - 1) - popc(up) : 0, lane, &tot2);
+        if (v < n)
+          for (int j = 0; j < n; ++j)
+            if (j != v && !((up >> j) & 1)) put_pair(o, pp + q++, nb + v, nb + j);
+        carry2 += tot2;
+      }
+      pp += carry2;
     }
   }
   // ---- blocks 0_1 and 1_0
@@ -456,10 +503,10 @@ __global__ void __launch_bounds__(32 * kLiftWarps) lift_fill_kernel(csmpn_lift_d
   // ---- block 1_1: edges that share a triangle
   for (int e = lane; e < n_e; e += 32) {
     const int a = s.ea[e], b = s.eb[e];
-    uint32_t m = s.cof[e];
+    M m = s.cof[e];
     int64_t pos = pp + 2ll * s.cbase[e];
     while (m) {
-      const int x = __ffs(m) - 1;
+      const int x = ffs0(m);
       m &= m - 1;
       // sorted triple (p, q, r); faces in gudhi boundary order (p,q), (p,r), (q,r) without e itself
       if (x < a) {          // (x, a, b): faces (x,a), (x,b), [a,b]
@@ -478,10 +525,10 @@ __global__ void __launch_bounds__(32 * kLiftWarps) lift_fill_kernel(csmpn_lift_d
   // ---- triangles: x_ind rows and blocks 1_2, 2_1
   for (int e = lane; e < n_e; e += 32) {
     const int p = s.ea[e], q = s.eb[e];
-    uint32_t m = s.cof[e] & bits_above(q);
-    int t = s.tbase[e];
+    M m = s.cof[e] & bits_above<M>(q);
+    int64_t t = s.tbase[e];
     while (m) {
-      const int r = __ffs(m) - 1;
+      const int r = ffs0(m);
       m &= m - 1;
       const int64_t f0 = E0 + e, f1 = E0 + edge_index_of(s, p, r), f2 = E0 + edge_index_of(s, q, r);
       put_pair(o, pp + 3 * t, f0, T0 + t);
@@ -516,12 +563,13 @@ inline int check_lift_desc(const csmpn_lift_desc* d) {
       if (!d->points || d->point_dim <= 0 || d->knn_k < 1) return CSMPN_ERR_BAD_ARG;
       break;
     case CSMPN_LIFT_FACETS:
-      if (!d->fptr || !d->facets || d->facet_size < 2 || d->facet_size > kMaxV) return CSMPN_ERR_BAD_ARG;
+      if (!d->fptr || !d->facets || d->facet_size < 2 || d->facet_size > kMaxV2) return CSMPN_ERR_BAD_ARG;
       break;
     default:
       return CSMPN_ERR_BAD_ARG;
   }
   if (d->max_dim < 1 || d->max_dim > 2) return CSMPN_ERR_UNSUPPORTED;
+  if (d->max_vertices < 0 || d->max_vertices > kMaxV2) return CSMPN_ERR_UNSUPPORTED;
   return CSMPN_OK;
 }
 
@@ -539,8 +587,12 @@ int csmpn_lift_count(const csmpn_lift_desc* desc, int32_t* counts, int64_t* node
   cudaStream_t s = (cudaStream_t)stream;
   CSMPN_CUDA_TRY(cudaMemsetAsync(status, 0, sizeof(int32_t), s));
   if (desc->n_complexes > 0) {
-    const int grid = (desc->n_complexes + kLiftWarps - 1) / kLiftWarps;
-    lift_count_kernel<<<grid, 32 * kLiftWarps, 0, s>>>(*desc, counts, status);
+    if (desc->max_vertices > kMaxV) {  // two-word masks, one complex per CTA (37 KB of tables per complex)
+      lift_count_kernel<uint64_t, kMaxV2, 1><<<desc->n_complexes, 32, 0, s>>>(*desc, counts, status);
+    } else {
+      const int grid = (desc->n_complexes + kLiftWarps - 1) / kLiftWarps;
+      lift_count_kernel<uint32_t, kMaxV, kLiftWarps><<<grid, 32 * kLiftWarps, 0, s>>>(*desc, counts, status);
+    }
     CSMPN_LAUNCH_CHECK("lift_count");
   }
   lift_scan_kernel<<<1, 1024, 0, s>>>(*desc, counts, node_ptr, pair_ptr);
@@ -556,8 +608,12 @@ int csmpn_lift_fill(const csmpn_lift_desc* desc, const int64_t* node_ptr, const 
   if (n_pairs_total > 0 && !edge_index) return CSMPN_ERR_BAD_ARG;
   if (desc->n_complexes == 0) return CSMPN_OK;
   LiftOut o{edge_index, edge_index + n_pairs_total, x_ind, node_types, batch};
-  const int grid = (desc->n_complexes + kLiftWarps - 1) / kLiftWarps;
-  lift_fill_kernel<<<grid, 32 * kLiftWarps, 0, (cudaStream_t)stream>>>(*desc, node_ptr, pair_ptr, o);
+  if (desc->max_vertices > kMaxV) {
+    lift_fill_kernel<uint64_t, kMaxV2, 1><<<desc->n_complexes, 32, 0, (cudaStream_t)stream>>>(*desc, node_ptr, pair_ptr, o);
+  } else {
+    const int grid = (desc->n_complexes + kLiftWarps - 1) / kLiftWarps;
+    lift_fill_kernel<uint32_t, kMaxV, kLiftWarps><<<grid, 32 * kLiftWarps, 0, (cudaStream_t)stream>>>(*desc, node_ptr, pair_ptr, o);
+  }
   CSMPN_LAUNCH_CHECK("lift_fill");
   return CSMPN_OK;
 }

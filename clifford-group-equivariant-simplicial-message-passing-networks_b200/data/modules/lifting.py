@@ -14,13 +14,13 @@ import torch
 from ..._lib import CsmpnError, check, lib, ptr, require_cuda, stream_ptr
 
 LIFT_RIPS, LIFT_CLIQUE, LIFT_FACETS, LIFT_MOTION, LIFT_KNN = 0, 1, 2, 3, 4
-MAX_VERTICES = 32
+MAX_VERTICES = 64  # 33..64 vertices run the two-word-mask kernels (one complex per CTA)
 
 
 class LiftDesc(ctypes.Structure):
     _fields_ = [
         ("mode", c_int32), ("n_complexes", c_int32), ("max_dim", c_int32), ("point_dim", c_int32),
-        ("facet_size", c_int32), ("reserved", c_int32),
+        ("facet_size", c_int32), ("max_vertices", c_int32),
         ("max_edge_length", c_double), ("n_pairs", c_int64),
         ("vptr", c_void_p), ("points", c_void_p), ("pairs", c_void_p), ("pptr", c_void_p), ("facets", c_void_p),
         ("fptr", c_void_p),
@@ -94,6 +94,7 @@ def lift_batch(mode: int, n_vertices, *, points=None, max_edge_length=0.0, pairs
 
     d = LiftDesc()
     d.mode, d.n_complexes, d.max_dim = mode, ncx, dim
+    d.max_vertices = int(nv.max()) if ncx else 0  # > 32 selects the two-word-mask kernels
     vptr = make_ptr(nv)
     d.vptr = vptr.data_ptr()
     keep = [vptr]

@@ -304,7 +304,9 @@ enum csmpn_lift_mode {
 };
 
 typedef struct csmpn_lift_desc {
-  int32_t mode, n_complexes, max_dim, point_dim, facet_size, reserved;
+  int32_t mode, n_complexes, max_dim, point_dim, facet_size;
+  int32_t max_vertices;  /* largest vertex count of a complex in the batch (0: at most 32).  <= 32: one 32-bit adjacency mask
+                            per vertex, four complexes per CTA; 33..64: 64-bit masks, one complex per CTA; more: unsupported */
   double max_edge_length;
   int64_t n_pairs;
   const int32_t* vptr;
@@ -322,7 +324,7 @@ typedef struct csmpn_lift_desc {
 
 /* Pass 1: counts [n_complexes, 2] = (edges, triangles) of every complex; node_ptr / pair_ptr [n_complexes+1] =
  * exclusive prefix sums of simplices / adjacency pairs (last entry = batch totals, which the caller reads back to
- * size the outputs); *status (device int32) is set non-zero if a complex has more than 32 vertices.               */
+ * size the outputs); *status (device int32) is set non-zero if a complex has more vertices than max_vertices allows (32 or 64).               */
 int csmpn_lift_count(const csmpn_lift_desc* desc, int32_t* counts, int64_t* node_ptr, int64_t* pair_ptr, int32_t* status,
                      csmpn_stream_t stream);
 /* Pass 2: edge_index [2, n_pairs_total] int64 (global ids), x_ind [N, 3] fp32 (local vertex ids, CPython frozenset

@@ -277,3 +277,54 @@ def test_gpu_transform_api_with_filters(gold_filtered):
     assert x_dict[1].shape[0] == int((g["node_types"] == 1).sum()) and x_dict[2].shape[0] == int((g["node_types"] == 2).sum())
     a = torch.tensor([[0.0, 0.0, 0.0]]); b = torch.tensor([[1.0, 0.0, 0.0]]); c = torch.tensor([[0.0, 2.0, 0.0]])
     assert float(U.triangle_area(a, b, c)) == 1.0
+
+
+@pytest.mark.gpu
+def test_gpu_lift_33_to_64_vertices_vs_oracle():
+    """complexes with more than 32 vertices run the two-word-mask kernels (64-bit adjacency masks, one complex per CTA):
+    Rips, clique (from pairs and with the in-kernel kNN graph) and facet lifts of mixed-size batches, bit-exact to the oracle"""
+    from scipy.spatial import ConvexHull
+
+    from csmpn_b200.data.modules import lifting as G
+
+    dev = torch.device("cuda:0")
+    gen = torch.Generator().manual_seed(77)
+    sizes = [33, 64, 5, 40, 32, 57]
+    pts = [torch.randn(n, 3, generator=gen) for n in sizes]
+    # Rips at a radius that gives a sparse-to-medium complex
+    parts = [L.merge_ref(*L.rips_lift_ref(p.tolist(), 2, 0.9)) for p in pts]
+    ei, x_ind, nt = _collate_ref(parts)
+    lb = G.lift_batch(G.LIFT_RIPS, sizes, points=torch.cat(pts).to(dev), max_edge_length=0.9)
+    assert torch.equal(lb.edge_index.cpu(), ei) and torch.equal(lb.x_ind.cpu(), x_ind) and torch.equal(lb.node_types.cpu(), nt)
+    # clique complexes of kNN graphs: pairs path and in-kernel kNN
+    pairs = [L.knn_graph(p, 4) for p in pts]
+    parts = [L.merge_ref(*L.clique_lift_ref(n, e)) for n, e in zip(sizes, pairs)]
+    ei, x_ind, nt = _collate_ref(parts)
+    a = G.lift_batch(G.LIFT_CLIQUE, sizes, pairs=torch.cat(pairs, 1).to(dev), pairs_per_complex=[e.shape[1] for e in pairs])
+    b = G.lift_batch(G.LIFT_KNN, sizes, points=torch.cat(pts).to(dev), knn_k=4)
+    for lb in (a, b):
+        assert torch.equal(lb.edge_index.cpu(), ei) and torch.equal(lb.x_ind.cpu(), x_ind) and torch.equal(lb.node_types.cpu(), nt)
+    # facets: faces of the convex hull triangles of 40 and 64 points in R^3
+    fsizes = [40, 64]
+    fpts = [torch.randn(n, 3, generator=gen) for n in fsizes]
+    facets = [torch.as_tensor(ConvexHull(p.numpy()).simplices).long() for p in fpts]
+    parts = [L.merge_ref(*L.hull_faces_lift_ref(n, f.tolist(), 2)) for n, f in zip(fsizes, facets)]
+    ei, x_ind, nt = _collate_ref(parts)
+    lb = G.lift_batch(G.LIFT_FACETS, fsizes, facets=torch.cat(facets).to(dev), facets_per_complex=[f.shape[0] for f in facets])
+    assert torch.equal(lb.edge_index.cpu(), ei) and torch.equal(lb.x_ind.cpu(), x_ind) and torch.equal(lb.node_types.cpu(), nt)
+    with pytest.raises(ValueError):
+        G.lift_batch(G.LIFT_RIPS, [65], points=torch.randn(65, 3).to(dev), max_edge_length=1.0)
+
+
+@pytest.mark.gpu
+def test_gpu_lift_full_64_vertex_complex_counts():
+    """complete complex on 64 vertices: 2 016 edges, 41 664 triangles, closed-form block sizes"""
+    from csmpn_b200.data.modules import lifting as G
+
+    dev = torch.device("cuda:0")
+    n, ne, nt = 64, 2016, 41664
+    lb = G.lift_batch(G.LIFT_RIPS, [n], points=torch.randn(n, 2).to(dev), max_edge_length=1e9)
+    assert lb.x_ind.shape[0] == n + ne + nt
+    assert lb.edge_index.shape[1] == 6 * ne + 12 * nt + n * (n - 1) - ne
+    assert int((lb.node_types == 2).sum()) == nt
+    assert int(lb.edge_index.max()) == n + ne + nt - 1 and int(lb.edge_index.min()) == 0
