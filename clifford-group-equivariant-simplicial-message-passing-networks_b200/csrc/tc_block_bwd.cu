@@ -429,18 +429,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_bgemm_kernel(GemmArgs a) {
 #pragma unroll
     for (int pr = 0; pr < 2; ++pr) acc[it][pr] = 0.f;
   }
-  if (!ST) {
-    for (int s = 0; s < nsets; ++s) stage_weight_images<DIM, true>(wimg + (size_t)s * set_bytes, img, a.w[s], a.wk[s], a.wn, a.n16, a.kmax);
-  }
   const int npass = (a.n16 + nmax - 1) / nmax;
-  const uint32_t need = (uint32_t)B * (a.n16 < nmax ? a.n16 : nmax);
-  const uint32_t tcols = need <= 32 ? 32 : need <= 64 ? 64 : need <= 128 ? 128 : need <= 256 ? 256 : 512;
-  if (warp == 0) tmem_alloc(tmem_slot, tcols);
-  fence_async_smem();
-  fence_before_sync();
-  __syncthreads();
-  fence_after_sync();
-  const uint32_t tbase = *tmem_slot;
   const int nk = a.nk[0] + a.nk[1];
   const int per_tile = npass * nk;
   const int my_tiles = (a.tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
@@ -457,7 +446,18 @@ __global__ void __launch_bounds__(kThreads, 1) tc_bgemm_kernel(GemmArgs a) {
     }
   };
   int q = 0, loaded = 0;
-  if (warp == 0) for (; loaded < kRing - 1 && loaded < total_chunks; ++loaded) issue(loaded);
+  if (warp == 0) for (; loaded < kRing - 1 && loaded < total_chunks; ++loaded) issue(loaded);  // before the weights are staged
+  if (!ST) {
+    for (int s = 0; s < nsets; ++s) stage_weight_images<DIM, true>(wimg + (size_t)s * set_bytes, img, a.w[s], a.wk[s], a.wn, a.n16, a.kmax);
+  }
+  const uint32_t need = (uint32_t)B * (a.n16 < nmax ? a.n16 : nmax);
+  const uint32_t tcols = need <= 32 ? 32 : need <= 64 ? 64 : need <= 128 ? 128 : need <= 256 ? 256 : 512;
+  if (warp == 0) tmem_alloc(tmem_slot, tcols);
+  fence_async_smem();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tbase = *tmem_slot;
   const uint32_t lane_base = (warp & 3) * 32;
   const bool wide_ok = aligned32(a.out);
   for (int t = 0; t < my_tiles; ++t) {
@@ -666,6 +666,17 @@ __global__ void __launch_bounds__(kThreads, 1) tc_bgemmdb_kernel(GemmArgs a) {
   float acc[kUnits][2];
 #pragma unroll
   for (int u = 0; u < kUnits; ++u) { acc[u][0] = 0.f; acc[u][1] = 0.f; }
+  const int nk = a.nk[0] + a.nk[1];
+  const int my_tiles = (a.tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int total_chunks = my_tiles * nk;
+  auto issue = [&](int qq) {
+    const int64_t tile = (int64_t)blockIdx.x + (int64_t)(qq / nk) * gridDim.x;
+    const int kc = qq % nk;
+    const int s = kc < a.nk[0] ? 0 : 1;
+    issue_chunk_load<B>(p, qq, a.src[s], a.cp[s], tile, s ? kc - a.nk[0] : kc);
+  };
+  int q = 0, loaded = 0;
+  if (warp == 0) for (; loaded < kRing - 1 && loaded < total_chunks; ++loaded) issue(loaded);  // before the weights are staged
   for (int s = 0; s < nsets; ++s) stage_weight_images<DIM, true>(wimg + (size_t)s * set_bytes, img, a.w[s], a.wk[s], a.wn, a.n16, a.kmax);
   const int Np = a.n16;
   const uint32_t bufcols = (uint32_t)B * Np;  // <= 256 (host)
@@ -677,16 +688,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_bgemmdb_kernel(GemmArgs a) {
   __syncthreads();
   fence_after_sync();
   const uint32_t tbase = *tmem_slot;
-  const int nk = a.nk[0] + a.nk[1];
-  const int my_tiles = (a.tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-  const int total_chunks = my_tiles * nk;
   const uint32_t idesc = idesc_tf32(kTile, Np, false, false);
-  auto issue = [&](int qq) {
-    const int64_t tile = (int64_t)blockIdx.x + (int64_t)(qq / nk) * gridDim.x;
-    const int kc = qq % nk;
-    const int s = kc < a.nk[0] ? 0 : 1;
-    issue_chunk_load<B>(p, qq, a.src[s], a.cp[s], tile, s ? kc - a.nk[0] : kc);
-  };
   const uint32_t lane_base = (warp & 3) * 32;
   const int r = lane_base + lane;
   const bool wide_ok = aligned32(a.out);
@@ -815,8 +817,6 @@ __global__ void __launch_bounds__(kThreads, 1) tc_bgemmdb_kernel(GemmArgs a) {
     if (pend_c4 >= n_c4) { pend_tile = -1; fence_before_sync(); }
   };
 
-  int q = 0, loaded = 0;
-  if (warp == 0) for (; loaded < kRing - 1 && loaded < total_chunks; ++loaded) issue(loaded);
   for (int t = 0; t < my_tiles; ++t) {
     const int64_t tile = (int64_t)blockIdx.x + (int64_t)t * gridDim.x;
     const uint32_t tb = tbase + (uint32_t)(t & 1) * bufcols;

@@ -234,6 +234,32 @@ __global__ void __launch_bounds__(kThreads, 1) tc_f1_kernel(FwdArgs a) {
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kPipeBars);
   Pipe p;
   p.init(smem, bars, half);
+  const int my_tiles = (a.tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int per_tile = npass * nk;
+  const int total_chunks = my_tiles * per_tile;
+  auto tile_of = [&](int q) { return (int64_t)blockIdx.x + (int64_t)(q / per_tile) * gridDim.x; };
+  auto load = [&](int qq) {  // copies of chunk qq of this CTA (all lanes of warp 0)
+    if constexpr (ST) {
+      const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(a.wimg1) + (size_t)(qq % per_tile) * wunit;
+      issue_chunk_load_w<B>(p, qq, BPT_IN ? a.p0 : nullptr, a.in_cp, tile_of(qq), qq % nk, wsrc, wunit);
+    } else {
+      issue_chunk_load<B>(p, qq, a.p0, a.in_cp, tile_of(qq), qq % nk);
+    }
+  };
+  // The first chunks are requested BEFORE the weights are staged (bulk copies by the thread that initialised the
+  // barriers; register gathers by the converters): with one to three tiles per CTA the prologue is a visible part of
+  // the kernel and these latencies overlap it.
+  int q = 0;       // chunk sequence number of this CTA; chunk q lives in raw slot q % kRing
+  int loaded = 0;  // warp 0: chunks whose bulk copies have been issued
+  float4 gv[BPT_IN ? 1 : ApiItems<DIM>::N];  // gathered items of the NEXT chunk to stage (API-layout input)
+  GatherIdx<DIM> gi;
+  if (!BPT_IN && warp != 0 && total_chunks > 0) {
+    load_gather_idx<DIM>(a, tile_of(0) * kTile, gi);
+    gather_chunk_api<DIM>(a, tile_of(0) * kTile, 0, gv, gi);
+  }
+  if (LOADS && warp == 0) {
+    for (; loaded < kRing - 1 && loaded < total_chunks; ++loaded) load(loaded);
+  }
 
   if (!ST) stage_weight_images<DIM, false>(wimg, img, a.w1, C, a.cin, Cp, a.kin8);
   for (int i = tid; i < Cp; i += kThreads) b1_s[i] = (i < C && a.has_b1) ? a.b1[i] : 0.f;
@@ -250,30 +276,6 @@ __global__ void __launch_bounds__(kThreads, 1) tc_f1_kernel(FwdArgs a) {
   fence_after_sync();
   const uint32_t tbase = *tmem_slot;
   const uint32_t idesc = idesc_tf32(kTile, NS, false, false);
-  const int my_tiles = (a.tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-  const int per_tile = npass * nk;
-  const int total_chunks = my_tiles * per_tile;
-  auto tile_of = [&](int q) { return (int64_t)blockIdx.x + (int64_t)(q / per_tile) * gridDim.x; };
-  auto load = [&](int qq) {  // copies of chunk qq of this CTA (all lanes of warp 0)
-    if constexpr (ST) {
-      const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(a.wimg1) + (size_t)(qq % per_tile) * wunit;
-      issue_chunk_load_w<B>(p, qq, BPT_IN ? a.p0 : nullptr, a.in_cp, tile_of(qq), qq % nk, wsrc, wunit);
-    } else {
-      issue_chunk_load<B>(p, qq, a.p0, a.in_cp, tile_of(qq), qq % nk);
-    }
-  };
-
-  int q = 0;       // chunk sequence number of this CTA; chunk q lives in raw slot q % kRing
-  int loaded = 0;  // warp 0: chunks whose bulk copies have been issued
-  float4 gv[BPT_IN ? 1 : ApiItems<DIM>::N];  // gathered items of the NEXT chunk to stage (API-layout input)
-  GatherIdx<DIM> gi;
-  if (!BPT_IN && warp != 0 && total_chunks > 0) {
-    load_gather_idx<DIM>(a, tile_of(0) * kTile, gi);
-    gather_chunk_api<DIM>(a, tile_of(0) * kTile, 0, gv, gi);
-  }
-  if (LOADS && warp == 0) {
-    for (; loaded < kRing - 1 && loaded < total_chunks; ++loaded) load(loaded);
-  }
   for (int t = 0; t < my_tiles; ++t) {
     const int64_t tile = (int64_t)blockIdx.x + (int64_t)t * gridDim.x;
     const int64_t row0 = tile * kTile;
@@ -389,6 +391,21 @@ __global__ void __launch_bounds__(kThreads, 1) tc_f1db_kernel(FwdArgs a) {
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kPipeBars);
   Pipe p;
   p.init(smem, bars, B * kPS);
+  const int my_tiles = (a.tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int total_chunks = my_tiles * nk;
+  auto tile_of = [&](int q) { return (int64_t)blockIdx.x + (int64_t)(q / nk) * gridDim.x; };
+  // first chunks requested before the weights are staged (see tc_f1_kernel)
+  int q = 0, loaded = 0;
+  float4 gv[BPT_IN ? 1 : ApiItems<DIM>::N];
+  GatherIdx<DIM> gi;
+  if (!BPT_IN && warp != 0 && total_chunks > 0) {
+    load_gather_idx<DIM>(a, tile_of(0) * kTile, gi);
+    gather_chunk_api<DIM>(a, tile_of(0) * kTile, 0, gv, gi);
+  }
+  if (BPT_IN && warp == 0) {
+    for (; loaded < kRing - 1 && loaded < total_chunks; ++loaded)
+      issue_chunk_load<B>(p, loaded, a.p0, a.in_cp, tile_of(loaded), loaded % nk);
+  }
 
   stage_weight_images<DIM, false>(wimg, img, a.w1, C, a.cin, Cp, a.kin8);
   for (int i = tid; i < Cp; i += kThreads) b1_s[i] = (i < C && a.has_b1) ? a.b1[i] : 0.f;
@@ -406,9 +423,6 @@ __global__ void __launch_bounds__(kThreads, 1) tc_f1db_kernel(FwdArgs a) {
   fence_after_sync();
   const uint32_t tbase = *tmem_slot;
   const uint32_t idesc = idesc_tf32(kTile, Cp, false, false);
-  const int my_tiles = (a.tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-  const int total_chunks = my_tiles * nk;
-  auto tile_of = [&](int q) { return (int64_t)blockIdx.x + (int64_t)(q / nk) * gridDim.x; };
   const int r = (warp & 3) * 32 + lane;
   const int n_c4 = Cp >> 2;
 
@@ -468,17 +482,6 @@ __global__ void __launch_bounds__(kThreads, 1) tc_f1db_kernel(FwdArgs a) {
     if (pend_c4 >= n_c4) { pend_tile = -1; fence_before_sync(); }
   };
 
-  int q = 0, loaded = 0;
-  float4 gv[BPT_IN ? 1 : ApiItems<DIM>::N];
-  GatherIdx<DIM> gi;
-  if (!BPT_IN && warp != 0 && total_chunks > 0) {
-    load_gather_idx<DIM>(a, tile_of(0) * kTile, gi);
-    gather_chunk_api<DIM>(a, tile_of(0) * kTile, 0, gv, gi);
-  }
-  if (BPT_IN && warp == 0) {
-    for (; loaded < kRing - 1 && loaded < total_chunks; ++loaded)
-      issue_chunk_load<B>(p, loaded, a.p0, a.in_cp, tile_of(loaded), loaded % nk);
-  }
   for (int t = 0; t < my_tiles; ++t) {
     const int64_t tile = (int64_t)blockIdx.x + (int64_t)t * gridDim.x;
     const uint32_t tb = tbase + (uint32_t)(t & 1) * bufcols;
@@ -552,6 +555,22 @@ __global__ void __launch_bounds__(kThreads, 1) tc_f2_kernel(FwdArgs a) {
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kPipeBars);
   Pipe p;
   p.init(smem, bars, half);
+  const int my_tiles = (a.tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int per_tile = npass * nk;
+  const int total_chunks = my_tiles * per_tile;
+  auto tile_of = [&](int q) { return (int64_t)blockIdx.x + (int64_t)(q / per_tile) * gridDim.x; };
+  auto load = [&](int qq) {
+    if constexpr (ST) {
+      const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(a.wimg2) + (size_t)(qq % per_tile) * wunit;
+      issue_chunk_load_w<B>(p, qq, a.y2, Cp, tile_of(qq), qq % nk, wsrc, wunit);
+    } else {
+      issue_chunk_load<B>(p, qq, a.y2, Cp, tile_of(qq), qq % nk);
+    }
+  };
+  int q = 0, loaded = 0;
+  if (warp == 0) {  // first chunks requested before the weights are staged (see tc_f1_kernel)
+    for (; loaded < kRing - 1 && loaded < total_chunks; ++loaded) load(loaded);
+  }
 
   if (!ST) {
     stage_weight_images<DIM, false>(wimg, img, a.wr, C, C, 2 * Cp, Cp, 0, true);
@@ -572,28 +591,12 @@ __global__ void __launch_bounds__(kThreads, 1) tc_f2_kernel(FwdArgs a) {
   fence_after_sync();
   const uint32_t tbase = *tmem_slot;
   const uint32_t idesc = idesc_tf32(kTile, 2 * NS, false, false);
-  const int my_tiles = (a.tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-  const int per_tile = npass * nk;
-  const int total_chunks = my_tiles * per_tile;
-  auto tile_of = [&](int q) { return (int64_t)blockIdx.x + (int64_t)(q / per_tile) * gridDim.x; };
-  auto load = [&](int qq) {
-    if constexpr (ST) {
-      const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(a.wimg2) + (size_t)(qq % per_tile) * wunit;
-      issue_chunk_load_w<B>(p, qq, a.y2, Cp, tile_of(qq), qq % nk, wsrc, wunit);
-    } else {
-      issue_chunk_load<B>(p, qq, a.y2, Cp, tile_of(qq), qq % nk);
-    }
-  };
   const uint32_t col_r = 0, col_l = NS, bcols = 2 * NS;  // column of (blade b, channel c of the pass): b * bcols + col_{r,l} + c
   const bool wide_ok = aligned32(a.y) && (!a.res || aligned32(a.res));
   const uint32_t lane_base = (warp & 3) * 32;
 
-  int q = 0, loaded = 0;
   [[maybe_unused]] int dbg_n = 0;
   TSTAMP(1);
-  if (warp == 0) {
-    for (; loaded < kRing - 1 && loaded < total_chunks; ++loaded) load(loaded);
-  }
   for (int t = 0; t < my_tiles; ++t) {
     const int64_t tile = (int64_t)blockIdx.x + (int64_t)t * gridDim.x;
     const int64_t row0 = tile * kTile;
