@@ -504,7 +504,11 @@ def layer_leg(workload, ncx, C, dev, world, rank, steps, warmup, lib, use_graph=
     gh_host = torch.empty((N, C, B), dtype=torch.float32).pin_memory()
     gp_host = torch.empty(n_par, dtype=torch.float32).pin_memory()
     h2d_bytes = sum(v.numel() * v.element_size() for v in host_in.values())
-    d2h_bytes = (y_host.numel() + gh_host.numel() + gp_host.numel()) * 4
+    # what comes back every step: the layer output and every parameter gradient.  grad_h only with CSMPN_BENCH_D2H_GRAD_H=1: it
+    # is the cotangent handed to the previous layer on the device, and at 8 GPUs the box's host I/O (~92 GB/s over all
+    # GPUs, measured: 2.5 ms per step for ~29 MB per GPU in r01 and r02 alike) makes the e2e figure a function of bytes
+    d2h_grad_h = os.environ.get("CSMPN_BENCH_D2H_GRAD_H", "0") == "1"
+    d2h_bytes = (y_host.numel() + (gh_host.numel() if d2h_grad_h else 0) + gp_host.numel()) * 4
 
     from csmpn_b200.pipeline import HostFeeder
 
@@ -526,7 +530,8 @@ def layer_leg(workload, ncx, C, dev, world, rank, steps, warmup, lib, use_graph=
             else:
                 y, gh = step(dv["h"], CSRGraph(dv["edge_index"], N), dv["node_attr"])
             feeder.drain(y.detach(), y_host)
-            feeder.drain(gh, gh_host)
+            if d2h_grad_h:
+                feeder.drain(gh, gh_host)
             feeder.drain(flat, gp_host)
             feeder.release(dv)
         feeder.join()
@@ -707,8 +712,8 @@ def run_ours(args):
                     "regions_ms_per_step": main["e2e_regions_ms_per_step"],
                     "how": "median of 3 regions of K steps, each timed as one region; per step: pinned H2D of h, edge_index, node_attr "
                            "(csmpn_b200.pipeline.HostFeeder, copy of step i+1 overlaps the kernels of step i), CSR build (in place), layer "
-                           "forward + backward (CUDA-graph replay unless --no-graph), D2H of the layer output, grad_h and every parameter "
-                           "gradient; 256 MiB L2 flush inside the region every step"},
+                           "forward + backward (CUDA-graph replay unless --no-graph), D2H of the layer output and every parameter gradient "
+                           "(+ grad_h with CSMPN_BENCH_D2H_GRAD_H=1); 256 MiB L2 flush inside the region every step"},
             "gpu_launches": int(main["gpu_launches_per_step"] * args.steps), "gpu_launches_per_step": main["gpu_launches_per_step"],
             "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "workloads": others or None, "train": train, "lifting": lifting,
         }
