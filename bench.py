@@ -499,11 +499,27 @@ def layer_leg(workload, ncx, C, dev, world, rank, steps, warmup, lib, use_graph=
         return y, grads[0]
 
     # host-resident inputs (pinned) for the end-to-end leg
-    host_in = {k: b[k].pin_memory() for k in ("h", "edge_index", "node_attr")}
+    # ONE pinned staging buffer holding h | edge_index | node_attr back to back: one H2D copy per step instead of three
+    segs = [("h", b["h"]), ("edge_index", b["edge_index"]), ("node_attr", b["node_attr"])]
+    offs, total_b = {}, 0
+    for k, t in segs:
+        offs[k] = total_b
+        total_b += (t.numel() * t.element_size() + 255) // 256 * 256
+    blob_host = torch.empty(total_b, dtype=torch.uint8).pin_memory()
+    for k, t in segs:
+        blob_host[offs[k]: offs[k] + t.numel() * t.element_size()].view(t.dtype).view(t.shape).copy_(t)
+    host_in = {"blob": blob_host}
+
+    def unpack(dv):
+        out = {}
+        for k, t in segs:
+            out[k] = dv["blob"][offs[k]: offs[k] + t.numel() * t.element_size()].view(t.dtype).view(t.shape)
+        return out
+
     y_host = torch.empty((N, C, B), dtype=torch.float32).pin_memory()
     gh_host = torch.empty((N, C, B), dtype=torch.float32).pin_memory()
     gp_host = torch.empty(n_par, dtype=torch.float32).pin_memory()
-    h2d_bytes = sum(v.numel() * v.element_size() for v in host_in.values())
+    h2d_bytes = sum(t.numel() * t.element_size() for _, t in segs)
     # what comes back every step: the layer output and every parameter gradient.  grad_h only with CSMPN_BENCH_D2H_GRAD_H=1: it
     # is the cotangent handed to the previous layer on the device, and at 8 GPUs the box's host I/O (~92 GB/s over all
     # GPUs, measured: 2.5 ms per step for ~29 MB per GPU in r01 and r02 alike) makes the e2e figure a function of bytes
@@ -524,11 +540,12 @@ def layer_leg(workload, ncx, C, dev, world, rank, steps, warmup, lib, use_graph=
             if i + 1 < n_steps:
                 feeder.submit(host_in)
             flush.fill_(1.0)  # L2 flush, inside the timed region
+            x = unpack(dv)
             if glayer is not None:  # batches of a fixed shape: CSR rebuilt in place, layer replayed from CUDA graphs
-                glayer.set_graph(dv["edge_index"])
-                y, gh = step(dv["h"], None, dv["node_attr"])
+                glayer.set_graph(x["edge_index"])
+                y, gh = step(x["h"], None, x["node_attr"])
             else:
-                y, gh = step(dv["h"], CSRGraph(dv["edge_index"], N), dv["node_attr"])
+                y, gh = step(x["h"], CSRGraph(x["edge_index"], N), x["node_attr"])
             feeder.drain(y.detach(), y_host)
             if d2h_grad_h:
                 feeder.drain(gh, gh_host)
@@ -710,7 +727,7 @@ def run_ours(args):
             "e2e": None if args.no_e2e else {"value": main["e2e_value"], "unit": "simplices/s", "h2d_bytes_per_step": main["h2d_bytes_per_step"],
                     "d2h_bytes_per_step": main["d2h_bytes_per_step"], "ms_per_step": main["e2e_ms_per_step"],
                     "regions_ms_per_step": main["e2e_regions_ms_per_step"],
-                    "how": "median of 3 regions of K steps, each timed as one region; per step: pinned H2D of h, edge_index, node_attr "
+                    "how": "median of 3 regions of K steps, each timed as one region; per step: ONE pinned H2D copy of h | edge_index | node_attr "
                            "(csmpn_b200.pipeline.HostFeeder, copy of step i+1 overlaps the kernels of step i), CSR build (in place), layer "
                            "forward + backward (CUDA-graph replay unless --no-graph), D2H of the layer output and every parameter gradient "
                            "(+ grad_h with CSMPN_BENCH_D2H_GRAD_H=1); 256 MiB L2 flush inside the region every step"},

@@ -223,18 +223,36 @@ class CSRGraph:
         if tuple(edge_index.shape) != tuple(self.edge_index.shape) or edge_index.dtype != torch.int64:
             raise ValueError("CSRGraph.rebuild_: edge_index must keep its shape [2, E] and dtype int64")
         self.edge_index.copy_(edge_index)
+        # The dozen small launches of the rebuild (two counting sorts, sorted views, inverse permutation) are captured
+        # once and replayed as ONE graph launch: a host-fed loop calls this every step, and with eight ranks per box the
+        # per-launch driver cost, not the kernels, is what the step pays for (CSMPN_CSR_GRAPH=0: eager launches).
+        sg = getattr(self, "_sorted", None)
+        g = getattr(self, "_rebuild_graph", None)
+        if g is not None and self._rebuild_sorted is sg:
+            g.replay()
+            return self
+        if getattr(self, "_rebuild_ws", None) is None:
+            self._rebuild_ws = workspace(lib().csmpn_csr_workspace(self.n_pairs, self.n_nodes), self.edge_index.device)
+        self._build_all(sg)
+        if os.environ.get("CSMPN_CSR_GRAPH", "1") != "0" and not torch.cuda.is_current_stream_capturing():
+            torch.cuda.synchronize(self.edge_index.device)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                self._build_all(sg)
+            self._rebuild_graph, self._rebuild_sorted = graph, sg
+        return self
+
+    def _build_all(self, sg):
         dev = self.edge_index.device
         E, N = self.n_pairs, self.n_nodes
-        ws = workspace(lib().csmpn_csr_workspace(E, N), dev)
+        ws = self._rebuild_ws
         s = stream_ptr(dev)
         check(lib().csmpn_csr_build(ptr(self.dst), E, N, ptr(self.rowptr_dst), ptr(self.perm_dst), ptr(ws), ws.numel(), s),
               "csr_build(dst)")
         check(lib().csmpn_csr_build(ptr(self.src), E, N, ptr(self.rowptr_src), ptr(self.perm_src), ptr(ws), ws.numel(), s),
               "csr_build(src)")
-        sg = getattr(self, "_sorted", None)
         if sg is not None:
             sg.refresh_()
-        return self
 
 
 _CSR_CACHE: dict = {}
