@@ -80,33 +80,112 @@ __device__ __forceinline__ float mv_sumsq(const float* x) {
   return Q;
 }
 
-// Stage a [c_out, c_in, G] weight (global, reference layout) as 2*G operand images in shared memory:
+// Stage [c_out, c_in, G] weights (global, reference layout) as 2*G operand images each in shared memory:
 //   image (g, hl) = plane with R = rows_p rows;  TRANS == false: row = output channel, column = input channel
 //                                                TRANS == true : row = input channel,  column = output channel
 // hl = 0: TF32-exact high part, hl = 1: remainder.  Rows/columns beyond the real sizes are zero.
-// row0: first plane row of this weight (two weights can share one image set: rows [0, n) and [n, 2n)); zero: clear the
-// image set first (only the first weight staged into a set does).
-template <int DIM, bool TRANS>
-__device__ __forceinline__ void stage_weight_images(uint8_t* img0, uint32_t img_bytes, const float* __restrict__ w, int c_out,
-                                                    int c_in, int rows_p, int cols_p, int row0 = 0, bool zero = true) {
-  constexpr int G = Alg<DIM>::G;
-  if (zero) {
-    for (uint32_t i = threadIdx.x; i < G * 2 * (img_bytes >> 4); i += blockDim.x)
-      reinterpret_cast<float4*>(img0)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-  }
+// A job = one weight: its image set (img0), its first plane row (two weights can share one image set: rows [0, n) and
+// [n, 2n)).  [zero_base, zero_base + zero_bytes) -- all image sets of the call, contiguous -- is cleared first.
+// The prologue of every GEMM kernel runs this once per CTA, and a one-tile-per-CTA launch (every per-simplex block) pays
+// for it in full: the global loads are therefore issued in batches of 8 per thread, the first batch BEFORE the zero
+// fill and the barrier, so that one L2/HBM latency is exposed per batch instead of one per element (the element-wise loop
+// took 8-9 us of a 22 us single-tile kernel, profiles/r02_f2_timeline_prologue.log).
+struct WJob {
+  uint8_t* img0;
+  const float* w;
+  int c_out, c_in, row0;
+};
+// Work unit = one 8-row x 4-column block of a weight's image plane, one warp per unit: lane = (row % 8) * 4 + column % 4,
+// so the 32 stores of one (grade, hi/lo) image are 128 contiguous bytes (conflict-free) and a lane's G grades of one
+// (output, input) pair are one 16-byte load when G == 4.  Units of up to two weights are walked in one flat index space,
+// four units per warp in flight.
+template <int DIM, bool TRANS, int NJ>
+__device__ __forceinline__ void stage_weight_jobs(const WJob (&j)[NJ], int njobs, uint32_t img_bytes, int rows_p, int cols_p,
+                                                  uint8_t* zero_base, uint32_t zero_bytes) {
+  static_assert(NJ == 1 || NJ == 2, "one or two weights per call");
+  constexpr int G = Alg<DIM>::G, U = 4;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int rl = lane >> 2, cl = lane & 3;
+  // job fields are selected with ?: (dynamic indexing of the job array would put it in local memory)
+  const WJob& j0 = j[0];
+  const WJob& j1 = j[NJ - 1];
+  const bool two = NJ == 2 && njobs > 1;
+  const int R0 = TRANS ? j0.c_in : j0.c_out, C0 = TRANS ? j0.c_out : j0.c_in;
+  const int R1 = TRANS ? j1.c_in : j1.c_out, C1 = TRANS ? j1.c_out : j1.c_in;
+  const int ncb0 = (C0 + 3) >> 2, ncb1 = (C1 + 3) >> 2;
+  const int nb0 = ((R0 + 7) >> 3) * ncb0, nb1 = two ? ((R1 + 7) >> 3) * ncb1 : 0;
+  const int total = nb0 + nb1;
+  // unit -> (second job?, row, column, valid)
+  auto decode = [&](int wb, bool& sj, int& row, int& col) -> bool {
+    if (wb >= total) return false;
+    sj = wb >= nb0;
+    if (sj) wb -= nb0;
+    const int ncb = sj ? ncb1 : ncb0;
+    const int rb = wb / ncb, cb = wb - rb * ncb;
+    row = rb * 8 + rl;
+    col = cb * 4 + cl;
+    return row < (sj ? R1 : R0) && col < (sj ? C1 : C0);
+  };
+  auto fetch = [&](int wb, float* v) {
+#pragma unroll
+    for (int g = 0; g < G; ++g) v[g] = 0.f;
+    bool sj;
+    int row, col;
+    if (!decode(wb, sj, row, col)) return;
+    const int o = TRANS ? col : row, i = TRANS ? row : col;
+    const float* src = (sj ? j1.w : j0.w) + ((size_t)o * (sj ? j1.c_in : j0.c_in) + i) * G;
+    if (G == 4 && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+      const float4 x = __ldg(reinterpret_cast<const float4*>(src));
+      v[0] = x.x; v[1] = x.y; v[2] = x.z; v[G - 1] = x.w;
+    } else {
+#pragma unroll
+      for (int g = 0; g < G; ++g) v[g] = __ldg(src + g);
+    }
+  };
+  auto put = [&](int wb, const float* v) {
+    bool sj;
+    int row, col;
+    if (!decode(wb, sj, row, col)) return;
+    const int r = (sj ? j1.row0 : j0.row0) + row;
+    if (r >= rows_p || col >= cols_p) return;
+    uint8_t* dst = (sj ? j1.img0 : j0.img0) + plane_off(rows_p, r, col);
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      const float hi = tf32_hi(v[g]);
+      *reinterpret_cast<float*>(dst + (size_t)(g * 2 + 0) * img_bytes) = hi;
+      *reinterpret_cast<float*>(dst + (size_t)(g * 2 + 1) * img_bytes) = v[g] - hi;
+    }
+  };
+  float x[U][G];
+#pragma unroll
+  for (int u = 0; u < U; ++u) fetch(warp + u * nwarps, x[u]);  // in flight across the zero fill and the barrier
+  for (uint32_t i = threadIdx.x; i < (zero_bytes >> 4); i += blockDim.x)
+    reinterpret_cast<float4*>(zero_base)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   __syncthreads();
-  const int total = c_out * c_in * G;
-  for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
-    const int g = idx % G, i = (idx / G) % c_in, o = idx / (G * c_in);
-    const float x = w[idx];
-    const float hi = tf32_hi(x);
-    const int r = row0 + (TRANS ? i : o), c = TRANS ? o : i;
-    if (r < rows_p && c < cols_p) {
-      const uint32_t off = plane_off(rows_p, r, c);
-      *reinterpret_cast<float*>(img0 + (size_t)(g * 2 + 0) * img_bytes + off) = hi;
-      *reinterpret_cast<float*>(img0 + (size_t)(g * 2 + 1) * img_bytes + off) = x - hi;
+  for (int base = 0; base < total; base += U * nwarps) {
+    float nx[U][G];
+    const int nbase = base + U * nwarps;
+    if (nbase < total) {
+#pragma unroll
+      for (int u = 0; u < U; ++u) fetch(nbase + warp + u * nwarps, nx[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) put(base + warp + u * nwarps, x[u]);
+    if (nbase < total) {
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+#pragma unroll
+        for (int g = 0; g < G; ++g) x[u][g] = nx[u][g];
+      }
     }
   }
+}
+// one weight into its own image set (cleared first)
+template <int DIM, bool TRANS>
+__device__ __forceinline__ void stage_weight_images(uint8_t* img0, uint32_t img_bytes, const float* __restrict__ w, int c_out,
+                                                    int c_in, int rows_p, int cols_p) {
+  const WJob j[1] = {{img0, w, c_out, c_in, 0}};
+  stage_weight_jobs<DIM, TRANS, 1>(j, 1, img_bytes, rows_p, cols_p, img0, (uint32_t)Alg<DIM>::G * 2u * img_bytes);
 }
 
 // A-operand descriptors of blade b in a chunk buffer half

@@ -447,12 +447,15 @@ __global__ void __launch_bounds__(kThreads, 1) tc_bgemm_kernel(GemmArgs a) {
   };
   int q = 0, loaded = 0;
   if (warp == 0) for (; loaded < kRing - 1 && loaded < total_chunks; ++loaded) issue(loaded);  // before the weights are staged
-  if (!ST) {
-    for (int s = 0; s < nsets; ++s) stage_weight_images<DIM, true>(wimg + (size_t)s * set_bytes, img, a.w[s], a.wk[s], a.wn, a.n16, a.kmax);
-  }
   const uint32_t need = (uint32_t)B * (a.n16 < nmax ? a.n16 : nmax);
   const uint32_t tcols = need <= 32 ? 32 : need <= 64 ? 64 : need <= 128 ? 128 : need <= 256 ? 256 : 512;
   if (warp == 0) tmem_alloc(tmem_slot, tcols);
+  if (!ST) {
+    {
+    const WJob wj[2] = {{wimg, a.w[0], a.wk[0], a.wn, 0}, {wimg + set_bytes, a.w[nsets - 1], a.wk[nsets - 1], a.wn, 0}};
+    stage_weight_jobs<DIM, true, 2>(wj, nsets, img, a.n16, a.kmax, wimg, (uint32_t)nsets * set_bytes);
+  }
+  }
   fence_async_smem();
   fence_before_sync();
   __syncthreads();
@@ -677,12 +680,15 @@ __global__ void __launch_bounds__(kThreads, 1) tc_bgemmdb_kernel(GemmArgs a) {
   };
   int q = 0, loaded = 0;
   if (warp == 0) for (; loaded < kRing - 1 && loaded < total_chunks; ++loaded) issue(loaded);  // before the weights are staged
-  for (int s = 0; s < nsets; ++s) stage_weight_images<DIM, true>(wimg + (size_t)s * set_bytes, img, a.w[s], a.wk[s], a.wn, a.n16, a.kmax);
   const int Np = a.n16;
   const uint32_t bufcols = (uint32_t)B * Np;  // <= 256 (host)
   const uint32_t need = 2 * bufcols;
   const uint32_t tcols = need <= 32 ? 32 : need <= 64 ? 64 : need <= 128 ? 128 : need <= 256 ? 256 : 512;
   if (warp == 0) tmem_alloc(tmem_slot, tcols);
+  {
+    const WJob wj[2] = {{wimg, a.w[0], a.wk[0], a.wn, 0}, {wimg + set_bytes, a.w[nsets - 1], a.wk[nsets - 1], a.wn, 0}};
+    stage_weight_jobs<DIM, true, 2>(wj, nsets, img, a.n16, a.kmax, wimg, (uint32_t)nsets * set_bytes);
+  }
   fence_async_smem();
   fence_before_sync();
   __syncthreads();

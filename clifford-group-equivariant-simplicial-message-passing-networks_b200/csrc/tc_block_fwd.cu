@@ -261,15 +261,21 @@ __global__ void __launch_bounds__(kThreads, 1) tc_f1_kernel(FwdArgs a) {
     for (; loaded < kRing - 1 && loaded < total_chunks; ++loaded) load(loaded);
   }
 
-  if (!ST) stage_weight_images<DIM, false>(wimg, img, a.w1, C, a.cin, Cp, a.kin8);
-  for (int i = tid; i < Cp; i += kThreads) b1_s[i] = (i < C && a.has_b1) ? a.b1[i] : 0.f;
-  for (int i = tid; i < Cp * G; i += kThreads) {
-    sa_s[i] = (i < C * G) ? a.sa[i] : 0.f;
-    sb_s[i] = (i < C * G) ? a.sb[i] : 0.f;
-  }
   const uint32_t need = (uint32_t)B * NS;
   const uint32_t tcols = need <= 32 ? 32 : need <= 64 ? 64 : need <= 128 ? 128 : need <= 256 ? 256 : 512;
   if (warp == 0) tmem_alloc(tmem_slot, tcols);
+  // small parameters requested before the weights are staged (see tc_f2_kernel)
+  const float pf_b1 = (tid < C && a.has_b1) ? __ldg(a.b1 + tid) : 0.f;
+  const float pf_sa = tid < C * G ? __ldg(a.sa + tid) : 0.f;
+  const float pf_sb = tid < C * G ? __ldg(a.sb + tid) : 0.f;
+  if (!ST) stage_weight_images<DIM, false>(wimg, img, a.w1, C, a.cin, Cp, a.kin8);
+  if (tid < Cp) b1_s[tid] = pf_b1;
+  for (int i = tid + kThreads; i < Cp; i += kThreads) b1_s[i] = (i < C && a.has_b1) ? a.b1[i] : 0.f;
+  if (tid < Cp * G) { sa_s[tid] = pf_sa; sb_s[tid] = pf_sb; }
+  for (int i = tid + kThreads; i < Cp * G; i += kThreads) {
+    sa_s[i] = (i < C * G) ? a.sa[i] : 0.f;
+    sb_s[i] = (i < C * G) ? a.sb[i] : 0.f;
+  }
   fence_async_smem();
   fence_before_sync();
   __syncthreads();
@@ -407,16 +413,22 @@ __global__ void __launch_bounds__(kThreads, 1) tc_f1db_kernel(FwdArgs a) {
       issue_chunk_load<B>(p, loaded, a.p0, a.in_cp, tile_of(loaded), loaded % nk);
   }
 
-  stage_weight_images<DIM, false>(wimg, img, a.w1, C, a.cin, Cp, a.kin8);
-  for (int i = tid; i < Cp; i += kThreads) b1_s[i] = (i < C && a.has_b1) ? a.b1[i] : 0.f;
-  for (int i = tid; i < Cp * G; i += kThreads) {
-    sa_s[i] = (i < C * G) ? a.sa[i] : 0.f;
-    sb_s[i] = (i < C * G) ? a.sb[i] : 0.f;
-  }
   const uint32_t bufcols = (uint32_t)B * Cp;  // <= 256 (host)
   const uint32_t need = 2 * bufcols;
   const uint32_t tcols = need <= 32 ? 32 : need <= 64 ? 64 : need <= 128 ? 128 : need <= 256 ? 256 : 512;
   if (warp == 0) tmem_alloc(tmem_slot, tcols);
+  // small parameters requested before the weights are staged (see tc_f2_kernel)
+  const float pf_b1 = (tid < C && a.has_b1) ? __ldg(a.b1 + tid) : 0.f;
+  const float pf_sa = tid < C * G ? __ldg(a.sa + tid) : 0.f;
+  const float pf_sb = tid < C * G ? __ldg(a.sb + tid) : 0.f;
+  stage_weight_images<DIM, false>(wimg, img, a.w1, C, a.cin, Cp, a.kin8);
+  if (tid < Cp) b1_s[tid] = pf_b1;
+  for (int i = tid + kThreads; i < Cp; i += kThreads) b1_s[i] = (i < C && a.has_b1) ? a.b1[i] : 0.f;
+  if (tid < Cp * G) { sa_s[tid] = pf_sa; sb_s[tid] = pf_sb; }
+  for (int i = tid + kThreads; i < Cp * G; i += kThreads) {
+    sa_s[i] = (i < C * G) ? a.sa[i] : 0.f;
+    sb_s[i] = (i < C * G) ? a.sb[i] : 0.f;
+  }
   fence_async_smem();
   fence_before_sync();
   __syncthreads();
@@ -538,6 +550,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_f2_kernel(FwdArgs a) {
   constexpr int B = A::B, G = A::G, P = A::P;
   extern __shared__ __align__(1024) uint8_t smem[];
   const int tid = threadIdx.x, warp = uniform_warp_idx(), lane = tid & 31;
+  [[maybe_unused]] int dbg_n = 0;
+  TSTAMP(2);
   const int C = a.C, Cp = a.Cp, nk = Cp / 8;
   const int NS = ST ? a.ns2 : Cp;                      // output channels per pass
   const int npass = ST ? Cp / NS : 1;
@@ -572,19 +586,32 @@ __global__ void __launch_bounds__(kThreads, 1) tc_f2_kernel(FwdArgs a) {
     for (; loaded < kRing - 1 && loaded < total_chunks; ++loaded) load(loaded);
   }
 
-  if (!ST) {
-    stage_weight_images<DIM, false>(wimg, img, a.wr, C, C, 2 * Cp, Cp, 0, true);
-    stage_weight_images<DIM, false>(wimg, img, a.wl, C, C, 2 * Cp, Cp, Cp, false);
-  }
-  for (int i = tid; i < Cp * G; i += kThreads) sn_s[i] = (i < C * G) ? sigmoidf_(a.na[i]) : 0.f;
-  for (int i = tid; i < Cp * P; i += kThreads) wv_s[i] = (i < C * P) ? a.wp[i] : 0.f;
-  for (int i = tid; i < Cp; i += kThreads) {
-    bl_s[i] = (i < C) ? a.bl[i] : 0.f;
-    la_s[i] = (i < C) ? a.la[i] : 0.f;
-  }
+  TSTAMP(3);
   const uint32_t need = 2 * B * NS;
   const uint32_t tcols = need <= 32 ? 32 : need <= 64 ? 64 : need <= 128 ? 128 : need <= 256 ? 256 : 512;
   if (warp == 0) tmem_alloc(tmem_slot, tcols);
+  // the first elements of the small per-channel parameters are requested before the weights are staged (one exposed
+  // latency for the whole prologue instead of one per loop)
+  const float pf_na = tid < C * G ? __ldg(a.na + tid) : 0.f;
+  const float pf_wp0 = tid < C * P ? __ldg(a.wp + tid) : 0.f;
+  const float pf_wp1 = tid + kThreads < C * P ? __ldg(a.wp + tid + kThreads) : 0.f;
+  const float pf_bl = tid < C ? __ldg(a.bl + tid) : 0.f;
+  const float pf_la = tid < C ? __ldg(a.la + tid) : 0.f;
+  if (!ST) {
+    const WJob wj[2] = {{wimg, a.wr, C, C, 0}, {wimg, a.wl, C, C, Cp}};  // right | left stacked along the image rows
+    stage_weight_jobs<DIM, false, 2>(wj, 2, img, 2 * Cp, Cp, wimg, (uint32_t)G * 2u * img);
+  }
+  TSTAMP(4);
+  if (tid < Cp * G) sn_s[tid] = tid < C * G ? sigmoidf_(pf_na) : 0.f;
+  for (int i = tid + kThreads; i < Cp * G; i += kThreads) sn_s[i] = (i < C * G) ? sigmoidf_(a.na[i]) : 0.f;
+  if (tid < Cp * P) wv_s[tid] = pf_wp0;
+  if (tid + kThreads < Cp * P) wv_s[tid + kThreads] = pf_wp1;
+  for (int i = tid + 2 * kThreads; i < Cp * P; i += kThreads) wv_s[i] = (i < C * P) ? a.wp[i] : 0.f;
+  if (tid < Cp) { bl_s[tid] = pf_bl; la_s[tid] = pf_la; }
+  for (int i = tid + kThreads; i < Cp; i += kThreads) {
+    bl_s[i] = (i < C) ? a.bl[i] : 0.f;
+    la_s[i] = (i < C) ? a.la[i] : 0.f;
+  }
   fence_async_smem();
   fence_before_sync();
   __syncthreads();
@@ -595,7 +622,6 @@ __global__ void __launch_bounds__(kThreads, 1) tc_f2_kernel(FwdArgs a) {
   const bool wide_ok = aligned32(a.y) && (!a.res || aligned32(a.res));
   const uint32_t lane_base = (warp & 3) * 32;
 
-  [[maybe_unused]] int dbg_n = 0;
   TSTAMP(1);
   for (int t = 0; t < my_tiles; ++t) {
     const int64_t tile = (int64_t)blockIdx.x + (int64_t)t * gridDim.x;
@@ -766,6 +792,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_f2_kernel(FwdArgs a) {
   fence_before_sync();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tbase, tcols);
+  TSTAMP(5);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
