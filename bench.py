@@ -390,6 +390,40 @@ def train_leg(dev, world, rank, steps, warmup, lib, graphed=True):
                      "simplices_per_step_per_gpu": [min(sizes), max(sizes)],
                      "what": "different batch every step: pinned H2D of raw samples, GPU lifting, CSR build, forward, zero_grad, backward, "
                              "flat-bucket all-reduce, fused Adam, cosine schedule; eager launches"}
+    # ---- (c) the same stream replayed from ONE CUDA graph: every batch padded to a bucket of simplex / pair counts
+    if graphed:
+        from csmpn_b200.data.padding import make_bucket
+        from csmpn_b200.train_step import StreamGraphedStep
+
+        lifted = [lift.lift(gs, device=dev) for gs in pool]
+        bucket = make_bucket([b.sizes for b in lifted])  # a pass over the sampler's batches fixes the bucket
+        sstep = StreamGraphedStep(model, opt, lifted[0], bucket)
+        del lifted
+
+        from csmpn_b200.pipeline import LiftPrefetcher
+
+        pre = LiftPrefetcher(lambda samples: lift.lift(samples, device=dev), dev)
+        pre.submit(pool[0])
+
+        def stream_graphed_step(i):
+            sstep.load(pre.take())   # batch i -> the graph's static tensors (padded in place), CSR rebuilt in place
+            pre.consumed()
+            loss, _ = sstep.run(i)   # one graph replay ...
+            pre.submit(pool[(i + 1) % n_pool])  # ... under which the host lifts batch i + 1 on a side stream
+            sched.step()
+            return loss
+
+        for i in range(warmup):
+            stream_graphed_step(i)
+        ms_sg = _timed_region(stream_graphed_step, steps, dev, world)
+        out["stream_graphed"] = {"value": ncx * world / (ms_sg * 1e-3), "ms_per_step": ms_sg,
+                                 "bucket": {"simplices": bucket.simplices, "edges": bucket.edges, "triangles": bucket.triangles,
+                                            "pairs": bucket.pairs, "dummy_vertices": bucket.n_dummy_vertices},
+                                 "what": "different batch every step: pinned H2D of raw samples + GPU lifting of batch i+1 on a side stream under "
+                                         "step i (csmpn_b200.pipeline.LiftPrefetcher), in-place padding to one "
+                                         "bucket of simplex / pair counts (one dummy complex, masked out of the loss), CSR rebuilt in "
+                                         "place, then ONE graph replay: " + sstep.describe()}
+        del sstep
     # ---- (a) fixed structure, graph replay
     loc0 = batch.loc.clone()
     batch.loc = loc0

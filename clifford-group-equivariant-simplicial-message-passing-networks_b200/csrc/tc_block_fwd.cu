@@ -384,6 +384,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_f1_kernel(FwdArgs a) {
 template <int DIM, bool BPT_IN>
 __global__ void __launch_bounds__(kThreads, 1) tc_f1db_kernel(FwdArgs a) {
   using A = Alg<DIM>;
+  [[maybe_unused]] constexpr bool TL = true;  // timeline stamps (diagnostics build only, when a.dbg is set)
+  [[maybe_unused]] int dbg_n = 0;
   constexpr int B = A::B, G = A::G;
   extern __shared__ __align__(1024) uint8_t smem[];
   const int tid = threadIdx.x, warp = uniform_warp_idx(), lane = tid & 31;
@@ -499,7 +501,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc_f1db_kernel(FwdArgs a) {
     const uint32_t tb = tbase + (uint32_t)(t & 1) * bufcols;
     for (int kc = 0; kc < nk; ++kc, ++q) {
       if (warp == 0) {  // issuer
+        TSTAMP(36);
         p.wait_full(q);
+        TSTAMP(37);
         if (BPT_IN && loaded == q + kRing - 1 && loaded < total_chunks) {
           if (q >= 1) mbar_wait(&p.slot_bar[(q - 1) % kRing], ((q - 1) / kRing) & 1);
           issue_chunk_load<B>(p, loaded, a.p0, a.in_cp, tile_of(loaded), loaded % nk);
@@ -508,21 +512,28 @@ __global__ void __launch_bounds__(kThreads, 1) tc_f1db_kernel(FwdArgs a) {
         // buffer t & 1 was read by the epilogue of tile t-2: every epilogue warp finished it before its conv_done of
         // this tile's first chunk (full_bar observed above), so the first MMA may overwrite it
         issue_chunk_mma<DIM>(p, q, tb, Cp, kc > 0, wimg, img, 0, 1, 0, Cp, kc, 0, idesc);
+        TSTAMP(38);
       } else {
         if (BPT_IN) {
           mbar_wait(&p.load_bar[q % kRing], (q / kRing) & 1);
           split_chunk<B>(p, q);
         } else {
+          TSTAMP(30);
           if (q >= kRing) mbar_wait(&p.slot_bar[q % kRing], ((q - kRing) / kRing) & 1);
+          TSTAMP(31);
           store_chunk_api<DIM>(p, q, gv, a.save_x0, round_up(a.kin8, 16), tile, kc);
+          TSTAMP(32);
           p.conv_done(q);
+          TSTAMP(33);
           if (q + 1 < total_chunks) {
             if ((q + 1) % nk == 0) load_gather_idx<DIM>(a, tile_of(q + 1) * kTile, gi);  // first chunk of the next tile
             gather_chunk_api<DIM>(a, tile_of(q + 1) * kTile, (q + 1) % nk, gv, gi);
           }
           if (a.save_x0 && kc == nk - 1 && (a.kin8 & 8)) zero_chunk_bpt<B>(a.save_x0, round_up(a.kin8, 16), tile, nk);
+          TSTAMP(34);
         }
         epilogue_step();  // one unit of the previous tile between two chunks of this one
+        TSTAMP(35);
       }
     }
     // the previous tile's epilogue must be finished before this warp signals the next tile's first chunk
@@ -932,6 +943,10 @@ int launch_fwd(const csmpn_block_desc& d, cudaStream_t stream) {
     kern<<<grid, kThreads, smem_bytes, stream>>>(a);
     return CSMPN_OK;
   };
+  long long* const dbg_buf = a.dbg;  // diagnostics build: CSMPN_DBG_KERNEL=f1 records the first kernel, default the second
+  const char* dbg_k = getenv("CSMPN_DBG_KERNEL");
+  const bool dbg_f1 = dbg_k && dbg_k[0] == 'f' && dbg_k[1] == '1';
+  a.dbg = dbg_f1 ? dbg_buf : nullptr;
   if (mask & 1) {
     // resident weights and accumulators of at most half of TMEM: the overlapped-epilogue kernel (CSMPN_TC_OVERLAP=0: plain)
     const bool overlap = !p.st1 && 2 * B * a.Cp <= 512 && overlap_enabled();
@@ -941,6 +956,7 @@ int launch_fwd(const csmpn_block_desc& d, cudaStream_t stream) {
     if (rc) return rc;
     CSMPN_LAUNCH_CHECK("tc_f1_kernel");
   }
+  a.dbg = dbg_f1 ? nullptr : dbg_buf;
   if (mask & 2) {
     int rc;
 #ifdef CSMPN_DEBUG_TOOLS

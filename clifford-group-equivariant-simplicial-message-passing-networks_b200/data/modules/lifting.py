@@ -147,8 +147,10 @@ def lift_batch(mode: int, n_vertices, *, points=None, max_edge_length=0.0, pairs
     status = torch.empty(1, dtype=torch.int32, device=device)
     s = stream_ptr(device)
     check(lib().csmpn_lift_count(ctypes.byref(d), ptr(counts), ptr(node_ptr), ptr(pair_ptr), ptr(status), s), "lift_count")
-    totals = torch.stack([node_ptr[-1], pair_ptr[-1], status[0].long()]).cpu()  # the one host sync: output sizes
-    n_total, e_total, bad = (int(v) for v in totals)
+    # the one host sync: output sizes (+ the per-dimension totals, which shape-padded batches need: data/padding.py)
+    csum = counts.long().sum(0) if ncx else torch.zeros(2, dtype=torch.int64, device=device)
+    totals = torch.stack([node_ptr[-1], pair_ptr[-1], status[0].long(), csum[0], csum[1]]).cpu()
+    n_total, e_total, bad, n_edges_total, n_tris_total = (int(v) for v in totals)
     if bad:
         raise ValueError("lift_batch: a complex has an unsupported vertex count")
     edge_index = torch.empty((2, e_total), dtype=torch.int64, device=device)
@@ -160,6 +162,8 @@ def lift_batch(mode: int, n_vertices, *, points=None, max_edge_length=0.0, pairs
     out = LiftedBatch(edge_index=edge_index, x_ind=x_ind, node_types=node_types, batch=batch, node_ptr=node_ptr,
                       pair_ptr=pair_ptr, counts=counts, n_vertices=vptr[1:] - vptr[:-1], mode=mode, _keep=keep)
     out.n_vertices_host = nv
+    out.sizes = {"vertices": int(nv.sum()) if ncx else 0, "edges": n_edges_total, "triangles": n_tris_total, "pairs": e_total,
+                 "simplices": n_total, "complexes": ncx}
     out._counts_host = None
     return out
 

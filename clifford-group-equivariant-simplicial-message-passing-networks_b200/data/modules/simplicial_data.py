@@ -159,6 +159,7 @@ def _collate(lb, graphs, label):
     out = Data(edge_index=lb.edge_index, x_ind=lb.x_ind, node_types=lb.node_types, batch=lb.batch, ptr=lb.node_ptr,
                x_ind_batch=lb.batch, x_ind_ptr=lb.node_ptr, node_types_batch=lb.batch, node_types_ptr=lb.node_ptr,
                num_graphs=len(graphs))
+    out.sizes = dict(lb.sizes)   # host ints: vertices / edges / triangles / pairs / simplices / complexes of this batch
     dev = lb.edge_index.device
     for name in _VERTEX_FEATURES[label]:
         if all(hasattr(g, name) for g in graphs):

@@ -85,8 +85,25 @@ class SharedSimplicialBase(nn.Module):
     learned_type_embedding = True
 
     # ---- per-batch index cache (one nonzero per simplex dimension, reused by every step of the forward) ----------
+    def begin_forward(self, graph):
+        """Shape-padded batches (data/padding.py) are overwritten in place from step to step and replayed from ONE CUDA graph:
+        their index caches must be recomputed by every forward (inside the captured graph), never carried over."""
+        if getattr(graph, "_csmpn_dynamic", False):
+            graph._csmpn_rows = None
+            graph._csmpn_vertex_pos = None
+
     def simplex_rows(self, graph):
         cached = getattr(graph, "_csmpn_rows", None)
+        if cached is None and getattr(graph, "_csmpn_dynamic", False):
+            # fixed counts per dimension (host ints): a stable sort groups the rows by dimension, no nonzero / host sync
+            order = torch.argsort(graph.node_types, stable=True)
+            cached, off = [], 0
+            for d in range(self.max_dim + 1):
+                n_d = int(graph.pad_counts[d]) if d < len(graph.pad_counts) else 0
+                cached.append(order[off: off + n_d])
+                off += n_d
+            graph._csmpn_rows = cached
+            return cached
         if cached is None:
             cached = [torch.nonzero(graph.node_types == d).squeeze(1) for d in range(self.max_dim + 1)]
             try:

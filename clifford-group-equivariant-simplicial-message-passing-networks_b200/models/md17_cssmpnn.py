@@ -55,7 +55,9 @@ class CliffordSharedSimplicialMPNN_md17(SharedSimplicialBase):
         return per_graph[graph.x_ind_batch]
 
     def forward(self, graph, step, mode):
+        self.begin_forward(graph)
         batch_size = graph.ptr.shape[0] - 1
+        n_real = int(getattr(graph, "n_real_graphs", batch_size))  # shape-padded batches end with one dummy complex
         num_frames = graph.loc.shape[1]
         rows0 = self.simplex_rows(graph)[0]
         loc_node = graph.loc[rows0]
@@ -72,6 +74,8 @@ class CliffordSharedSimplicialMPNN_md17(SharedSimplicialBase):
         fde_loss = torch.sqrt(F.mse_loss(loc_pred[:, -1, :], targets[:, -1, :], reduction="none").sum(dim=-1)
                               ).reshape(batch_size, -1).mean(dim=-1)
         loss = sq.reshape(batch_size, -1, 3).sum(-1).mean(-1)
+        if n_real != batch_size:
+            loss, ade_loss, fde_loss = loss[:n_real], ade_loss[:n_real], fde_loss[:n_real]
         return loss.mean(), {"loss": loss, "ade_loss": ade_loss, "fde_loss": fde_loss}
 
     def __str__(self):

@@ -79,3 +79,46 @@ class HostFeeder:
         cur = torch.cuda.current_stream(self.device)
         cur.wait_stream(self.copy_stream)
         cur.wait_stream(self.drain_stream)
+
+
+class LiftPrefetcher:
+    """Lifts (pinned H2D of the raw samples + GPU lifting + collation) batch i+1 on a side stream while step i computes.
+
+    The lifter needs one host sync for its output sizes; on the compute stream that sync would wait for the whole previous
+    step.  On a side stream it only waits for the lifting kernels, so the host prepares batch i+1 under the kernels of step i.
+
+    >>> pre = LiftPrefetcher(lambda samples: transform.lift(samples, device=dev), dev)
+    >>> pre.submit(samples(0))
+    >>> for i in range(steps):
+    ...     b = pre.take()                 # compute stream waits for the lifting of batch i
+    ...     step.load(b); pre.consumed()   # batch i has been copied into the step's static tensors
+    ...     pre.submit(samples(i + 1))     # overlaps step.run()
+    ...     step.run()
+    """
+
+    def __init__(self, lift_fn, device):
+        self.lift_fn = lift_fn
+        self.device = torch.device(device)
+        self.side = torch.cuda.Stream(self.device)
+        self._next = None
+        self._consumed = None
+
+    def submit(self, samples):
+        if self._consumed is not None:   # the memory of an earlier batch may be recycled: its readers come first
+            self.side.wait_event(self._consumed)
+        with torch.cuda.stream(self.side):
+            b = self.lift_fn(samples)
+            ev = torch.cuda.Event()
+            ev.record(self.side)
+        self._next = (b, ev)
+
+    def take(self):
+        b, ev = self._next
+        self._next = None
+        torch.cuda.current_stream(self.device).wait_event(ev)
+        return b
+
+    def consumed(self):
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.device))
+        self._consumed = ev

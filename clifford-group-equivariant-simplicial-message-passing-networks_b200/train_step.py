@@ -220,6 +220,42 @@ class GraphedDataParallelStep(DataParallelStep):
         return self.loss, self.out
 
 
+class StreamGraphedStep(GraphedDataParallelStep):
+    """The graphed step for a stream of DIFFERENT batches (MD17 / NBA complexes change from sample to sample; SURVEY 8f-4,
+    engineer/trainer/trainer.py:204-227 feeds a new batch every step).
+
+    Every batch is padded to one ``Bucket`` of simplex / pair counts with a dummy complex (data/padding.py) that neither
+    talks to the real complexes nor enters the loss, so ONE captured graph -- forward + backward (+ all-reduce + Adam) --
+    serves every step.  Per step, eagerly: the lifted batch is written into the graph's static tensors (``pad_to_bucket``
+    in place), the CSR of its pairs is rebuilt in place (one small graph replay), then the step graph is replayed.  A batch
+    that overflows the bucket raises ``BucketOverflow``: build a new step with a larger bucket (``make_bucket``)."""
+
+    def __init__(self, model, optimizer, first_batch, bucket, **kw):
+        from .data.padding import pad_to_bucket
+
+        self.bucket_shape = bucket
+        padded = pad_to_bucket(first_batch, bucket)
+        super().__init__(model, optimizer, padded, **kw)
+
+    def load(self, batch):
+        """write ``batch`` (a collated lift) into the graph's static tensors, padded to the bucket, and rebuild its CSR"""
+        from .data.padding import pad_to_bucket
+
+        self._rebind()
+        pad_to_bucket(batch, self.bucket_shape, out=self.batch)      # in place: the graph's static tensors keep their addresses
+        self._csr.rebuild_(self.batch.edge_index)                     # counting sorts + sorted views, replayed from a small graph
+
+    def run(self, step: int = 0):
+        return super().__call__(None, step)
+
+    def __call__(self, batch, step: int = 0):
+        self.load(batch)
+        return self.run(step)
+
+    def describe(self):
+        return super().describe().replace("(GraphedDataParallelStep)", "(StreamGraphedStep: shape-padded batches, CSR rebuilt in place)")
+
+
 class CosineAnnealingLR(torch.optim.lr_scheduler.LRScheduler):
     """The reference's schedule (engineer/schedulers/cosine.py:10-46; built in csmpn/md17.py:26-36 with
     warmup = steps / 64, decay = steps / 4): half-cosine warm-up over ``warmup_steps``, flat at the base rate for

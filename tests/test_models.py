@@ -279,3 +279,87 @@ def test_fused_permute_embed_equals_materialised_rows(gold, name, monkeypatch):
     assert_close(out["1"][0], out["0"][0], 1e-5, f"{name} embedding")
     for a, c in zip(out["1"][1], out["0"][1]):
         assert_close(a, c, 1e-4, f"{name} embedding parameter gradient")
+
+
+# ---------------------------------------------------------------------------------------------- shape-padded stream
+def _md17_samples(n, seed):
+    import bench
+
+    return bench.make_md17_graphs(n, seed, "cpu")
+
+
+@pytest.mark.gpu
+def test_padded_batch_leaves_loss_and_gradients_unchanged():
+    """data/padding.py: one dummy complex absorbs the difference to the bucket sizes.  The md17 model on the padded batch gives
+    the loss, the per-sample losses and every parameter gradient of the unpadded batch (dummy simplices only talk to
+    dummy simplices and are masked out of the loss)."""
+    from csmpn_b200.data.modules.simplicial_data import SimplicialTransform
+    from csmpn_b200.data.padding import BucketOverflow, make_bucket, pad_to_bucket
+
+    dev = torch.device("cuda:0")
+    lift = SimplicialTransform(dim=2, dis=2.5, label="md17", molecule_type="aspirin")
+    b = lift.lift(_md17_samples(12, 5), device=dev)
+    torch.manual_seed(0)
+    m = model_class("md17")().to(dev)
+    loss, out = m(b, 0, "train")
+    g_ref = torch.autograd.grad(loss, list(m.parameters()))
+    bucket = make_bucket([b.sizes], margin=1.1)
+    assert bucket.edges > b.sizes["edges"] and bucket.triangles > b.sizes["triangles"] and bucket.pairs > b.sizes["pairs"]
+    pb = pad_to_bucket(b, bucket)
+    assert pb.x_ind.shape[0] == bucket.simplices and pb.edge_index.shape[1] == bucket.pairs
+    assert [int((pb.node_types == d).sum()) for d in range(3)] == list(bucket.counts())
+    loss_p, out_p = m(pb, 0, "train")
+    g_p = torch.autograd.grad(loss_p, list(m.parameters()))
+    assert_close(loss_p, loss, FWD_TOL, "loss of the padded batch")
+    assert out_p["loss"].shape == out["loss"].shape
+    assert_close(out_p["loss"], out["loss"], FWD_TOL, "per-sample losses of the padded batch")
+    for (n, _), a, r in zip(m.named_parameters(), g_p, g_ref):
+        assert torch.isfinite(a).all(), n
+        assert_close(a, r, GRAD_TOL, f"grad {n} (padded batch)")
+    small = make_bucket([{**b.sizes, "edges": b.sizes["edges"] - 70}], margin=1.0, multiple=1)
+    with pytest.raises(BucketOverflow):
+        pad_to_bucket(b, small)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("optim", ["adam", "sgd"])
+def test_padded_stream_step_follows_eager_on_different_batches(optim):
+    """StreamGraphedStep: ONE captured graph (forward + backward [+ Adam]) replayed on three DIFFERENT md17 batches (different
+    simplex and pair counts) tracks the eager DataParallelStep on the same batches.  adam: the optimizer step is inside the
+    graph, losses of the three steps agree (Adam turns fp32 noise of near-zero gradients into +-lr, so the parameters are
+    compared under plain SGD, where they must agree to the gradient tolerance)."""
+    from csmpn_b200.data.modules.simplicial_data import SimplicialTransform
+    from csmpn_b200.data.padding import make_bucket
+    from csmpn_b200.train_step import DataParallelStep, StreamGraphedStep
+
+    dev = torch.device("cuda:0")
+    lift = SimplicialTransform(dim=2, dis=2.5, label="md17", molecule_type="aspirin")
+    pools = [_md17_samples(10, 100 + k) for k in range(4)]
+    sizes = [lift.lift(p, device=dev).sizes for p in pools]
+    assert len({(s["simplices"], s["pairs"]) for s in sizes}) > 1, "the batches should differ in size"
+    results = []
+    for graphed in (False, True):
+        torch.manual_seed(0)
+        m = model_class("md17")().to(dev)
+        if optim == "sgd":
+            opt = torch.optim.SGD(m.parameters(), lr=1e-2)
+        elif graphed:
+            opt = torch.optim.Adam(m.parameters(), lr=torch.tensor(1e-3, device=dev), fused=True, capturable=True)
+        else:
+            opt = torch.optim.Adam(m.parameters(), lr=1e-3)
+        if graphed:
+            step = StreamGraphedStep(m, opt, lift.lift(pools[0], device=dev), make_bucket(sizes))
+            assert step.captured_optimizer == (optim == "adam")
+        else:
+            step = DataParallelStep(m, opt)
+        losses = []
+        for k in (1, 2, 3):
+            loss, _ = step(lift.lift(pools[k], device=dev), k)
+            losses.append(float(loss.detach()))
+        results.append((losses, [p.detach().clone() for p in m.parameters()]))
+    (l0, p0), (l1, p1) = results
+    for a, b in zip(l0, l1):
+        assert abs(a - b) <= 1e-5 * max(1.0, abs(a)), (l0, l1)
+    if optim == "sgd":
+        for a, b in zip(p0, p1):
+            assert_close(b, a, GRAD_TOL, "parameters after 3 SGD steps on different batches")

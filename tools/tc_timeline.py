@@ -14,7 +14,7 @@ os.environ["CSMPN_TC"] = "1"
 os.environ["CSMPN_TC_MIN_ROWS"] = "0"
 import bench  # noqa: E402
 
-NAMES = {2: "kernel entry", 3: "first loads issued", 4: "weights staged", 5: "kernel exit", 1: "start", 10: "chunk top", 11: "load landed", 12: "lo free", 13: "split done", 14: "chunk full", 15: "mma issued",
+NAMES = {30: "conv top", 31: "slot free", 32: "chunk stored", 33: "conv_done", 34: "next gather issued", 35: "epilogue step done", 36: "issuer top", 37: "chunk full(f1)", 38: "mma issued(f1)", 2: "kernel entry", 3: "first loads issued", 4: "weights staged", 5: "kernel exit", 1: "start", 10: "chunk top", 11: "load landed", 12: "lo free", 13: "split done", 14: "chunk full", 15: "mma issued",
          16: "load issued", 20: "K loop end", 21: "all MMAs done", 22: "pass1 done", 23: "rowsum barrier", 24: "tile end"}
 
 
