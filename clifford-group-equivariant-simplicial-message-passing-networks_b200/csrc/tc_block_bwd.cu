@@ -29,6 +29,8 @@ struct EwArgs {
   int tiles, C, Cp;
   const float* gy;  // grad_y: BPT [Cp] or reference layout [rows, C, B]
   int gy_bpt;
+  const int32_t* gy_rows;  // reference layout only: block row r reads grad_y row gy_rows[r] (NULL: r) ...
+  int64_t gy_stride;       // ... at this row pitch in floats (the aggregation's adjoint folded into the gather)
   const float *o, *xr, *y2, *y1, *dy2;
   const float *la, *wp, *na, *sa, *sb;
   float *d, *dxr, *dy2p, *dy1;
@@ -134,7 +136,9 @@ __global__ void __launch_bounds__(CP * 8, CP <= 32 ? 2 : 1) tc_b1_kernel(EwArgs 
     } else {
       float* dst = stage_of(s, 1) + lane;  // reference layout: every thread fetches its own multivector
       if (chx < C && tile * kTile + r < a.rows) {
-        const float* src = a.gy + ((size_t)(tile * kTile + r) * C + chx) * B;
+        // the row indices of a tile are 512 contiguous bytes: L1 hits after the first touch of each line
+        const int64_t grow = a.gy_rows ? (int64_t)__ldg(a.gy_rows + tile * kTile + r) : tile * kTile + r;
+        const float* src = a.gy + (size_t)grow * a.gy_stride + (size_t)chx * B;
 #pragma unroll
         for (int b = 0; b < B; ++b) cp_async4(dst + b * 32, src + b);
       } else {
@@ -1272,6 +1276,8 @@ int launch_bwd(const csmpn_block_desc& d, const csmpn_block_grads& g, void* work
   memset(&e, 0, sizeof(e));
   e.rows = d.rows; e.tiles = p.tiles; e.C = C; e.Cp = Cp;
   e.gy = g.grad_y; e.gy_bpt = g.gy_bpt;
+  e.gy_rows = g.gy_bpt ? nullptr : g.gy_rows;
+  e.gy_stride = (!g.gy_bpt && g.gy_row_stride > 0) ? g.gy_row_stride : (int64_t)C * Alg<DIM>::B;
   e.o = d.save_o; e.xr = d.save_xr; e.y2 = d.save_y2; e.y1 = d.save_y1;
   e.la = d.la; e.wp = d.wp; e.na = d.na; e.sa = d.sa; e.sb = d.sb;
   e.d = ws + p.o_d; e.dxr = ws + p.o_dxr; e.dy2p = ws + p.o_dy2p; e.dy2 = ws + p.o_dy2; e.dy1 = ws + p.o_dy1;

@@ -46,6 +46,7 @@ class BlockGrads(ctypes.Structure):
         ("g_w1", c_void_p), ("g_b1", c_void_p), ("g_sa", c_void_p), ("g_sb", c_void_p), ("g_wr", c_void_p),
         ("g_na", c_void_p), ("g_wl", c_void_p), ("g_bl", c_void_p), ("g_wp", c_void_p), ("g_la", c_void_p),
         ("gy_bpt", c_int32), ("gx_bpt", c_int32),
+        ("gy_rows", c_void_p), ("gy_row_stride", ctypes.c_int64),
     ]
 
 
@@ -336,6 +337,16 @@ class TcBlockFn(torch.autograd.Function):
                 d.save_o = scratch_o.data_ptr()
         check(lib().csmpn_block_fwd(dim, ctypes.byref(d), stream_ptr(dev)), "block_fwd (tensor-core)")
         _record("fwd", dim, d, keep=[srcs, params, y, resc, saves, y2, x0, wsf, scratch_o])
+        red = cfg.get("reduce")   # (SortedGraph, mean): return the per-receiver aggregate of the rows instead of the rows
+        if red is not None:
+            csr = red[0].csr
+            agg = torch.empty((csr.n_nodes, c, B), dtype=torch.float32, device=dev)
+            check(lib().csmpn_segment_reduce_sorted(ptr(y), ptr(csr.rowptr_dst), ptr(agg), csr.n_nodes, c * B, int(red[1]),
+                                                    stream_ptr(dev)), "segment_reduce_sorted")
+            ctx.reduce = red
+            y = agg
+        else:
+            ctx.reduce = None
         if need_grad:
             ctx.save_for_backward(*[t for t in srcs if t is not None], *[t for t in params if t is not None], *saves, y2,
                                   *([] if x0 is None else [x0]))
@@ -356,9 +367,24 @@ def _tc_block_backward(ctx, gy):
     params = [saved.pop(0) if m else None for m in par_mask]
     y1, xr, o, y2 = saved[:4]
     x0 = saved[4] if has_x0 else None
-    gy = f32c(gy)
-    dev = gy.device
     B = 1 << dim
+    red = getattr(ctx, "reduce", None)
+    gy_rows, gy_stride = None, 0
+    if red is not None:
+        # gy is the cotangent of the AGGREGATE [n_nodes, c, B]: row r of the block reads row dst_sorted[r] of it (the adjoint
+        # of the segment sum folded into the first backward kernel; no [pairs, c, B] expansion).  A channel slice of a
+        # wider gradient (the update block hands back grad_x[:, c:2c]) is read in place through its row pitch.
+        rsg, mean = red
+        if mean:
+            deg = (rsg.csr.rowptr_dst[1:] - rsg.csr.rowptr_dst[:-1]).clamp(min=1).to(torch.float32)
+            gy = gy.to(torch.float32) / deg.reshape(-1, 1, 1)
+        if not (gy.dtype == torch.float32 and gy.dim() == 3 and gy.stride(2) == 1 and gy.stride(1) == B
+                and gy.stride(0) % 4 == 0 and gy.data_ptr() % 16 == 0):
+            gy = f32c(gy)
+        gy_rows, gy_stride = rsg.dst_sorted, int(gy.stride(0))
+    else:
+        gy = f32c(gy)
+    dev = gy.device
     cin = sum(chans)
     d = _fill_desc(dim, mode, srcs, chans, rows, c, params, sgraph, gy, None, (y1, xr, o), pair)
     d.engine, d.in_bpt, d.out_bpt = 1, int(in_bpt), int(out_bpt)
@@ -375,6 +401,8 @@ def _tc_block_backward(ctx, gy):
     g = BlockGrads()
     g.grad_y, g.grad_x = gy.data_ptr(), None if gx is None else gx.data_ptr()
     g.gy_bpt, g.gx_bpt = int(out_bpt), int(in_bpt)
+    if gy_rows is not None:
+        g.gy_rows, g.gy_row_stride = gy_rows.data_ptr(), gy_stride
     names = ("g_w1", "g_b1", "g_sa", "g_sb", "g_wr", "g_na", "g_wl", "g_bl", "g_wp", "g_la")
     for n, t in zip(names, pg):
         setattr(g, n, None if t is None else t.data_ptr())
@@ -538,13 +566,15 @@ def _block_uses_tc(algebra, layer, need_grad, rows=None) -> bool:
 
 
 def block_forward(algebra, layer, x, p1=None, p2=None, res=None, mode=0, sgraph=None, bpt_rows=None, out_bpt=False,
-                  pair_attr=False):
+                  pair_attr=False, reduce=None):
     """Run one CEMLP block (nn.Sequential of the four sub-layers) through the fused kernels.
 
     bpt_rows: x is a BPT tensor (output of a previous tensor-core block) holding that many rows.
     out_bpt:  return a BPT tensor (only honoured on the tensor-core engine; the caller checks with is_bpt)."""
     in_bpt = bpt_rows is not None
     if not in_bpt and (not _block_supported(layer) or (x is not None and x.dim() != 3)):
+        if reduce is not None:
+            raise ValueError("block_forward(reduce=...) needs a block the fused kernels support")
         y = x if p1 is None else torch.cat([t for t in (x, p1, p2) if t is not None], dim=1)
         y = layer(y)
         return y if res is None else res + y
@@ -554,8 +584,17 @@ def block_forward(algebra, layer, x, p1=None, p2=None, res=None, mode=0, sgraph=
     rows_now = bpt_rows if in_bpt else (sgraph.csr.n_pairs if mode == 1 else x.shape[0])
     if in_bpt or _block_uses_tc(algebra, layer, need_grad, rows_now):
         cfg.update(in_bpt=in_bpt, out_bpt=out_bpt, rows=bpt_rows, c_in=layer[0].in_features)
-        return TcBlockFn.apply(cfg, x, p1, p2, res, *params)
-    return FusedBlockFn.apply(cfg, x, p1, p2, res, *params)
+        if reduce is not None and not out_bpt and res is None:
+            cfg["reduce"] = reduce   # the block returns the aggregate; its backward gathers the aggregate's cotangent
+            return TcBlockFn.apply(cfg, x, p1, p2, res, *params)
+        y = TcBlockFn.apply(cfg, x, p1, p2, res, *params)
+    else:
+        y = FusedBlockFn.apply(cfg, x, p1, p2, res, *params)
+    if reduce is not None:
+        B = algebra.n_blades
+        n_pairs = reduce[0].csr.n_pairs
+        return SegmentReduceSortedFn.apply(y.reshape(n_pairs, -1), reduce[0], reduce[1]).reshape(reduce[0].csr.n_nodes, -1, B)
+    return y
 
 
 def embed_rows_forward(algebra, blocks, table, vertex_rows, fp):
@@ -585,15 +624,18 @@ def _chain_uses_tc(algebra, blocks, need_grad, rows) -> bool:
     return all(_block_supported(b) for b in blocks) and all(_block_uses_tc(algebra, b, need_grad, rows) for b in blocks)
 
 
-def mlp_forward(algebra, blocks, x, p1=None, p2=None, res=None, mode=0, sgraph=None, rows=None, pair_attr=False):
-    """A CEMLP (list of blocks): on the tensor-core engine the tensors between blocks stay in the BPT layout."""
+def mlp_forward(algebra, blocks, x, p1=None, p2=None, res=None, mode=0, sgraph=None, rows=None, pair_attr=False, reduce=None):
+    """A CEMLP (list of blocks): on the tensor-core engine the tensors between blocks stay in the BPT layout.
+    reduce = (SortedGraph, mean): the rows are messages in receiver-sorted order and the CEMLP returns their per-receiver
+    aggregate [n_nodes, C, B] (the last block folds the aggregation's adjoint into its backward on the tensor-core engine)."""
     need_grad = _need_grad(x, p1, p2, res, *[t for b in blocks for t in _block_params(b)])
     tc = len(blocks) > 1 and _chain_uses_tc(algebra, blocks, need_grad, rows)
     u = block_forward(algebra, blocks[0], x, p1, p2, res if len(blocks) == 1 else None, mode=mode, sgraph=sgraph, out_bpt=tc,
-                      pair_attr=pair_attr)
+                      pair_attr=pair_attr, reduce=reduce if len(blocks) == 1 else None)
     for k, blk in enumerate(blocks[1:]):
         last = k == len(blocks) - 2
-        u = block_forward(algebra, blk, u, res=res if last else None, bpt_rows=rows if tc else None, out_bpt=tc and not last)
+        u = block_forward(algebra, blk, u, res=res if last else None, bpt_rows=rows if tc else None, out_bpt=tc and not last,
+                          reduce=reduce if last else None)
     return u
 
 
@@ -620,9 +662,8 @@ def egcl_forward(egcl, h, edge_index, edge_attr=None, node_attr=None):
     else:
         h_msg = h_upd = h_res = h
     if csr.n_pairs > 0:
-        m = mlp_forward(alg, blocks_e, h_msg, edge_attr.node_attr if pair else edge_attr, None, None, mode=1, sgraph=sg,
-                        rows=csr.n_pairs, pair_attr=pair)
-        agg = SegmentReduceSortedFn.apply(m.reshape(csr.n_pairs, -1), sg, egcl.aggr == "mean").reshape(N, -1, B)
+        agg = mlp_forward(alg, blocks_e, h_msg, edge_attr.node_attr if pair else edge_attr, None, None, mode=1, sgraph=sg,
+                          rows=csr.n_pairs, pair_attr=pair, reduce=(sg, egcl.aggr == "mean"))
     else:
         agg = h.new_zeros((N, egcl.out_features, B))
     return mlp_forward(alg, blocks_n, h_upd, agg, node_attr, h_res if egcl.residual else None, rows=N)

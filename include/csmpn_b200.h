@@ -219,6 +219,12 @@ typedef struct csmpn_block_grads {
   float *g_w1, *g_b1, *g_sa, *g_sb, *g_wr, *g_na, *g_wl, *g_bl, *g_wp, *g_la;
   /* engine 1 only: grad_y is a BPT [c] tensor / grad_x is written as a BPT [c_in] tensor (grad_x may be NULL) */
   int32_t gy_bpt, gx_bpt;
+  /* engine 1 only, reference-layout grad_y: row r of the block reads grad_y row gy_rows[r] (NULL: row r) at a row pitch of
+   * gy_row_stride floats (0: c * B).  This is the adjoint of the aggregation folded into the block: the cotangent of the
+   * messages of receiver i is the cotangent of its aggregate (cegnn_utils.py:262-275 through PyG's scatter), so the
+   * [pairs, c, B] expansion of the [simplices, c, B] gradient is never written. */
+  const int32_t* gy_rows;
+  int64_t gy_row_stride;
 } csmpn_block_grads;
 
 int csmpn_block_fwd(int dim, const csmpn_block_desc* desc, csmpn_stream_t stream);
