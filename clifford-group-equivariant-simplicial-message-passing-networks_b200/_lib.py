@@ -66,6 +66,7 @@ def _declare(lib):
         "csmpn_block_bwd": (c_int, [i32, P, P, P, i64, P]),
         "csmpn_csr_sorted_indices": (c_int, [P, P, P, P, P, i64, P]),
         "csmpn_csr_rank": (c_int, [P, P, i64, P]),
+        "csmpn_csr_build_pair": (c_int, [P, P, i64, i64, P, P, P, P, P, P, P, P, i64, P]),
         "csmpn_segment_reduce_sorted": (c_int, [P, P, P, i64, i64, i32, P]),
         "csmpn_segment_expand_sorted": (c_int, [P, P, P, P, i64, i64, i32, P]),
         "csmpn_scatter_diff_sorted": (c_int, [P, i64, P, P, P, P, P, i64, i64, i32, P]),

@@ -143,6 +143,120 @@ __global__ void csr_sort_segments_kernel(const int32_t* __restrict__ rowptr, int
 }
 
 // ---------------------------------------------------------------------------------------------------
+// Both CSRs of a batch (by receiver and by sender) + the receiver-sorted views in SIX launches instead of sixteen: every
+// kernel handles both key arrays (blockIdx.y), the three-step scan collapses into one CTA per array while the counters fit
+// its registers (n_nodes <= 64 k: every configuration BASELINE.json names), and the sorted views and the inverse
+// permutation come from one kernel.  The chain is latency-bound (a few microseconds per launch even replayed from a CUDA
+// graph) and every host-fed step pays for it.  (A one-CTA-per-array variant with shared-memory counters was slower than
+// the sixteen launches: 103 vs 65 us at md17 size, 1.0 ms at NBA size -- profiles/r02_csr_rebuild.log.)
+struct CsrPair {
+  const int64_t* keys[2];   // [0] receivers (edge_index[1]), [1] senders (edge_index[0])
+  int32_t* rowptr[2];
+  int32_t* perm[2];
+  int32_t* cursor[2];       // workspace: counts, then running cursors
+};
+
+__global__ void csr_count2_kernel(CsrPair a, int64_t n_pairs, int64_t n_nodes) {
+  const int w = blockIdx.y;
+  const int64_t* __restrict__ keys = a.keys[w];
+  int32_t* __restrict__ counts = a.cursor[w];
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n_pairs; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t k = keys[e];
+    if (k >= 0 && k < n_nodes) atomicAdd(&counts[k], 1);
+  }
+}
+
+constexpr int kScan1Threads = 1024, kScan1Per = 64;  // one CTA scans up to 64 k counters (a contiguous chunk per thread)
+__global__ void __launch_bounds__(kScan1Threads) csr_scan2_kernel(CsrPair a, int n_nodes) {
+  __shared__ int32_t warp_sums[kScan1Threads / 32];
+  const int w = blockIdx.x;
+  int32_t* __restrict__ cursor = a.cursor[w];
+  int32_t* __restrict__ rowptr = a.rowptr[w];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int per = (n_nodes + kScan1Threads - 1) / kScan1Threads;  // <= kScan1Per (host)
+  const int b0 = min(tid * per, n_nodes), b1 = min(b0 + per, n_nodes);
+  int32_t run = 0;
+#pragma unroll 8
+  for (int i = b0; i < b1; ++i) run += cursor[i];
+  int32_t inc = run;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const int32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+  if (lane == 31) warp_sums[wid] = inc;
+  __syncthreads();
+  if (wid == 0) {
+    const int32_t ws = warp_sums[lane];
+    int32_t wi = ws;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int32_t t = __shfl_up_sync(0xffffffffu, wi, o); if (lane >= o) wi += t; }
+    warp_sums[lane] = wi - ws;
+  }
+  __syncthreads();
+  int32_t off = warp_sums[wid] + inc - run;
+#pragma unroll 8
+  for (int i = b0; i < b1; ++i) {  // second read of the thread's own chunk: L1 hits
+    const int32_t c = cursor[i];
+    rowptr[i] = off; cursor[i] = off;
+    off += c;
+  }
+  if (tid == kScan1Threads - 1) rowptr[n_nodes] = off;
+}
+
+__global__ void csr_fill2_kernel(CsrPair a, int64_t n_pairs, int64_t n_nodes) {
+  const int w = blockIdx.y;
+  const int64_t* __restrict__ keys = a.keys[w];
+  int32_t* __restrict__ cursor = a.cursor[w];
+  int32_t* __restrict__ perm = a.perm[w];
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n_pairs; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t k = keys[e];
+    if (k < 0 || k >= n_nodes) continue;
+    perm[atomicAdd(&cursor[k], 1)] = (int32_t)e;
+  }
+}
+
+__device__ __forceinline__ void sort_segment(int32_t* a, int d);
+__global__ void csr_sort2_kernel(CsrPair a, int64_t n_nodes) {
+  const int w = blockIdx.y;
+  const int32_t* __restrict__ rowptr = a.rowptr[w];
+  for (int64_t n = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; n < n_nodes; n += (int64_t)gridDim.x * blockDim.x) {
+    const int32_t b = rowptr[n], e = rowptr[n + 1];
+    sort_segment(a.perm[w] + b, e - b);
+  }
+}
+
+__device__ __forceinline__ void sort_segment(int32_t* a, int d) {
+  if (d <= 1) return;
+  if (d <= 24) {
+    for (int i = 1; i < d; ++i) {
+      int32_t v = a[i]; int j = i - 1;
+      while (j >= 0 && a[j] > v) { a[j + 1] = a[j]; --j; }
+      a[j + 1] = v;
+    }
+    return;
+  }
+  for (int start = d / 2 - 1; start >= 0; --start) {  // heapsort
+    int root = start; int32_t v = a[root];
+    while (true) {
+      int child = 2 * root + 1; if (child >= d) break;
+      if (child + 1 < d && a[child + 1] > a[child]) ++child;
+      if (a[child] <= v) break;
+      a[root] = a[child]; root = child;
+    }
+    a[root] = v;
+  }
+  for (int end = d - 1; end > 0; --end) {
+    int32_t v = a[end]; a[end] = a[0];
+    int root = 0;
+    while (true) {
+      int child = 2 * root + 1; if (child >= end) break;
+      if (child + 1 < end && a[child + 1] > a[child]) ++child;
+      if (a[child] <= v) break;
+      a[root] = a[child]; root = child;
+    }
+    a[root] = v;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
 template <int V>
 __global__ void gather_diff_kernel(const float* __restrict__ h, const int64_t* __restrict__ src,
                                    const int64_t* __restrict__ dst, float* __restrict__ out, int64_t n_pairs,
@@ -456,6 +570,41 @@ int csmpn_segment_expand(const float* grad_out, const int64_t* dst, const int32_
   cudaStream_t s = (cudaStream_t)stream;
   CSMPN_VEC_DISPATCH(width, segment_expand_kernel, n_pairs * width, grad_out, dst, rowptr, grad_msg, n_pairs, width, mean);
   CSMPN_LAUNCH_CHECK("segment_expand");
+  return CSMPN_OK;
+}
+
+int csmpn_csr_build_pair(const int64_t* src, const int64_t* dst, int64_t n_pairs, int64_t n_nodes, int32_t* rowptr_dst,
+                         int32_t* perm_dst, int32_t* rowptr_src, int32_t* perm_src, int32_t* src_sorted, int32_t* dst_sorted,
+                         int32_t* rank, void* workspace, int64_t workspace_bytes, csmpn_stream_t stream) {
+  if (n_pairs < 0 || n_nodes < 0 || !rowptr_dst || !rowptr_src) return CSMPN_ERR_BAD_ARG;
+  if (n_pairs > 0 && (!src || !dst || !perm_dst || !perm_src)) return CSMPN_ERR_BAD_ARG;
+  if ((src_sorted == nullptr) != (dst_sorted == nullptr)) return CSMPN_ERR_BAD_ARG;
+  if (n_nodes > (int64_t)kScan1Threads * kScan1Per || n_pairs >= ((int64_t)1 << 31)) return CSMPN_ERR_UNSUPPORTED;  // -> csmpn_csr_build
+  const int64_t half = (n_nodes + 4) / 4 * 4;  // int32 counters per key array
+  if (!workspace || workspace_bytes < 2 * half * (int64_t)sizeof(int32_t)) return CSMPN_ERR_WORKSPACE;
+  cudaStream_t s = (cudaStream_t)stream;
+  CsrPair a;
+  a.keys[0] = dst; a.keys[1] = src;
+  a.rowptr[0] = rowptr_dst; a.rowptr[1] = rowptr_src;
+  a.perm[0] = perm_dst; a.perm[1] = perm_src;
+  a.cursor[0] = (int32_t*)workspace; a.cursor[1] = (int32_t*)workspace + half;
+  CSMPN_CUDA_TRY(cudaMemsetAsync(workspace, 0, (size_t)(2 * half) * sizeof(int32_t), s));
+  if (n_pairs > 0) {
+    csr_count2_kernel<<<dim3(grid_for(n_pairs, 256), 2), 256, 0, s>>>(a, n_pairs, n_nodes);
+    CSMPN_LAUNCH_CHECK("csr_count2");
+  }
+  csr_scan2_kernel<<<2, kScan1Threads, 0, s>>>(a, (int)n_nodes);
+  CSMPN_LAUNCH_CHECK("csr_scan2");
+  if (n_pairs > 0) {
+    csr_fill2_kernel<<<dim3(grid_for(n_pairs, 256), 2), 256, 0, s>>>(a, n_pairs, n_nodes);
+    CSMPN_LAUNCH_CHECK("csr_fill2");
+    csr_sort2_kernel<<<dim3(grid_for(n_nodes, 128), 2), 128, 0, s>>>(a, n_nodes);
+    CSMPN_LAUNCH_CHECK("csr_sort2");
+    if (src_sorted) {
+      sorted_indices_kernel<<<grid_for(n_pairs, 256), 256, 0, s>>>(src, dst, perm_dst, src_sorted, dst_sorted, rank, n_pairs);
+      CSMPN_LAUNCH_CHECK("csr_sorted_indices");
+    }
+  }
   return CSMPN_OK;
 }
 

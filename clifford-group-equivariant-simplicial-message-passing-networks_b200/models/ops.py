@@ -208,12 +208,8 @@ class CSRGraph:
         self.perm_dst = torch.empty(max(E, 1), dtype=torch.int32, device=dev)
         self.rowptr_src = torch.empty(N + 1, dtype=torch.int32, device=dev)
         self.perm_src = torch.empty(max(E, 1), dtype=torch.int32, device=dev)
-        ws = workspace(lib().csmpn_csr_workspace(E, N), dev)
-        s = stream_ptr(dev)
-        check(lib().csmpn_csr_build(ptr(self.dst), E, N, ptr(self.rowptr_dst), ptr(self.perm_dst), ptr(ws), ws.numel(), s),
-              "csr_build(dst)")
-        check(lib().csmpn_csr_build(ptr(self.src), E, N, ptr(self.rowptr_src), ptr(self.perm_src), ptr(ws), ws.numel(), s),
-              "csr_build(src)")
+        self._rebuild_ws = None
+        self._build_all(None)
         self._key = (edge_index.data_ptr(), tuple(edge_index.shape), edge_index._version, N)
 
     def rebuild_(self, edge_index: torch.Tensor):
@@ -231,8 +227,6 @@ class CSRGraph:
         if g is not None and self._rebuild_sorted is sg:
             g.replay()
             return self
-        if getattr(self, "_rebuild_ws", None) is None:
-            self._rebuild_ws = workspace(lib().csmpn_csr_workspace(self.n_pairs, self.n_nodes), self.edge_index.device)
         self._build_all(sg)
         if os.environ.get("CSMPN_CSR_GRAPH", "1") != "0" and not torch.cuda.is_current_stream_capturing():
             torch.cuda.synchronize(self.edge_index.device)
@@ -243,10 +237,23 @@ class CSRGraph:
         return self
 
     def _build_all(self, sg):
+        """both CSRs (+ the sorted views of ``sg``): six launches for batches of up to 65 536 simplices (csmpn_csr_build_pair,
+        CSMPN_CSR_SMALL=0 disables it), else the sixteen of the general path."""
         dev = self.edge_index.device
         E, N = self.n_pairs, self.n_nodes
-        ws = self._rebuild_ws
         s = stream_ptr(dev)
+        if getattr(self, "_rebuild_ws", None) is None:
+            self._rebuild_ws = workspace(2 * lib().csmpn_csr_workspace(E, N), dev)
+        ws = self._rebuild_ws
+        if os.environ.get("CSMPN_CSR_SMALL", "1") != "0":
+            st = lib().csmpn_csr_build_pair(ptr(self.src), ptr(self.dst), E, N, ptr(self.rowptr_dst), ptr(self.perm_dst),
+                                            ptr(self.rowptr_src), ptr(self.perm_src),
+                                            None if sg is None else ptr(sg.src_sorted), None if sg is None else ptr(sg.dst_sorted),
+                                            None if sg is None else ptr(sg.rank), ptr(ws), ws.numel(), s)
+            if st == 0:
+                return
+            if st != -3:  # anything but "too many simplices for the one-CTA scan"
+                check(st, "csr_build_pair")
         check(lib().csmpn_csr_build(ptr(self.dst), E, N, ptr(self.rowptr_dst), ptr(self.perm_dst), ptr(ws), ws.numel(), s),
               "csr_build(dst)")
         check(lib().csmpn_csr_build(ptr(self.src), E, N, ptr(self.rowptr_src), ptr(self.perm_src), ptr(ws), ws.numel(), s),

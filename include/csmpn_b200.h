@@ -254,6 +254,15 @@ int csmpn_csr_sorted_indices(const int64_t* src, const int64_t* dst, const int32
                              int32_t* dst_sorted, int64_t n_pairs, csmpn_stream_t stream);
 /* rank[perm[p]] = p : position of every original pair in the sorted order (inverse permutation) */
 int csmpn_csr_rank(const int32_t* perm, int32_t* rank, int64_t n_pairs, csmpn_stream_t stream);
+/* Both CSRs of a batch (by receiver and by sender), the receiver-sorted int32 views (src_sorted / dst_sorted, may both be
+ * NULL) and the inverse permutation rank[pair] = position in receiver order (may be NULL) in SIX launches: every kernel
+ * handles both key arrays and the scan is one CTA per array.  Same results as csmpn_csr_build x 2 +
+ * csmpn_csr_sorted_indices + csmpn_csr_rank (16 launches).  workspace: csmpn_csr_workspace(E, n_nodes) x 2 bytes.
+ * CSMPN_ERR_UNSUPPORTED when n_nodes > 65 536 (the one-CTA scan): use the calls above.
+ * Out-of-range simplex ids are skipped, as in csmpn_csr_build (PyG would raise; validate with CSMPN_CHECK_INDICES=1). */
+int csmpn_csr_build_pair(const int64_t* src, const int64_t* dst, int64_t n_pairs, int64_t n_nodes, int32_t* rowptr_dst,
+                         int32_t* perm_dst, int32_t* rowptr_src, int32_t* perm_src, int32_t* src_sorted, int32_t* dst_sorted,
+                         int32_t* rank, void* workspace, int64_t workspace_bytes, csmpn_stream_t stream);
 /* segment reduce over CONTIGUOUS rows (messages already in receiver-sorted order):
  *   out[n,:] = sum_{p in [rowptr[n], rowptr[n+1])} msg[p,:]   (/ max(deg,1) when mean)                        */
 int csmpn_segment_reduce_sorted(const float* msg, const int32_t* rowptr, float* out, int64_t n_nodes, int64_t width,

@@ -285,19 +285,42 @@ def test_egcl_empty_and_ragged(path):
             assert_close(y, yr, 1e-5, f"ragged {aggr} E={ei.shape[1]}")
 
 
-def test_csr_is_stable_sort():
+@pytest.mark.parametrize("small", ["1", "0"])
+def test_csr_is_stable_sort(small, monkeypatch):
+    """both builders -- the single-launch two-CTA kernel (csmpn_csr_build_pair) and the multi-launch path -- give the stable
+    counting sort: rowptr = exclusive counts, perm = argsort(key, stable); the sorted views and the inverse permutation
+    follow the receiver order; rebuild_ in place gives the same for new pairs."""
+    from csmpn_b200.models import fused
     from csmpn_b200.models.ops import CSRGraph
 
+    monkeypatch.setenv("CSMPN_CSR_SMALL", small)
     gen = torch.Generator().manual_seed(2)
-    for N, E in ((1, 0), (7, 1), (50, 1000), (5000, 30000), (3, 5000)):
-        ei = torch.randint(0, N, (2, E), generator=gen)
-        g = CSRGraph(ei.to(DEV), N)
+
+    def verify(g, ei, N, E):
         for key, rowptr, perm in ((ei[1], g.rowptr_dst, g.perm_dst), (ei[0], g.rowptr_src, g.perm_src)):
             order = torch.argsort(key, stable=True)
             counts = torch.bincount(key, minlength=N)
             ref_ptr = torch.cat([torch.zeros(1, dtype=torch.long), counts.cumsum(0)])
             assert torch.equal(rowptr.cpu().long(), ref_ptr)
             assert torch.equal(perm.cpu().long()[:E], order)
+        if E:
+            sg = fused.sorted_graph(g)
+            order = torch.argsort(ei[1], stable=True)
+            assert torch.equal(sg.src_sorted.cpu().long()[:E], ei[0][order])
+            assert torch.equal(sg.dst_sorted.cpu().long()[:E], ei[1][order])
+            assert torch.equal(sg.rank.cpu().long()[:E][order], torch.arange(E))
+
+    for N, E in ((1, 0), (7, 1), (50, 1000), (5000, 30000), (3, 5000), (1031, 4097), (40000, 100000), (60000, 90000)):
+        ei = torch.randint(0, N, (2, E), generator=gen)
+        g = CSRGraph(ei.to(DEV), N)
+        verify(g, ei, N, E)
+        if E:
+            ei2 = torch.randint(0, N, (2, E), generator=gen)
+            g.rebuild_(ei2.to(DEV))   # first call builds eagerly and captures, second call replays the captured rebuild
+            verify(g, ei2, N, E)
+            ei3 = torch.randint(0, N, (2, E), generator=gen)
+            g.rebuild_(ei3.to(DEV))
+            verify(g, ei3, N, E)
 
 
 def test_equivariance_with_correct_inverse():
