@@ -132,7 +132,9 @@ def pad_to_bucket(batch: Data, bucket: Bucket, out: Data | None = None) -> Data:
     for key in VERTEX_ALIGNED:
         if hasattr(batch, key) and torch.is_tensor(getattr(batch, key)):
             t = getattr(batch, key)
-            put(key, t, t.new_zeros((nvd,) + tuple(t.shape[1:])))
+            # rows per complex: one per vertex (md17: 21 atoms), or fewer (nba: the 10 players of 11 vertices have targets)
+            per = t.shape[0] // B if (B and t.shape[0] % B == 0) else nvd
+            put(key, t, t.new_zeros((per,) + tuple(t.shape[1:])))
     for key in GRAPH_ALIGNED:
         if hasattr(batch, key) and torch.is_tensor(getattr(batch, key)):
             t = getattr(batch, key)

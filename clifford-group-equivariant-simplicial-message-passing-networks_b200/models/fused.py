@@ -549,9 +549,10 @@ TC_BACKWARD_READY = True
 
 def tc_min_rows() -> int:
     """Rows below which a block stays on the FP32 SIMT engine: the tensor-core engine runs a block as several
-    persistent kernels over 128-row tiles; below ~64 tiles the SIMT engine's 16-row tiles use the GPU better
-    (motion-shaped batch, 4 700 simplices: 0.935 ms on SIMT node blocks vs 0.966 ms on tensor-core ones)."""
-    return int(os.environ.get("CSMPN_TC_MIN_ROWS", "8192"))  # 64 tiles; see DESIGN.md 4.4 for the measurements behind it
+    persistent kernels over 128-row tiles, each paying its prologue once per CTA.  With the batched weight staging
+    (tc_block.cuh) the cross-over is near 32 tiles: motion-shaped batch, 4 700 simplices = 37 tiles per node block:
+    0.796 ms with tensor-core node blocks vs 0.814 ms with SIMT ones (r01 prologues: 0.966 vs 0.935 ms)."""
+    return int(os.environ.get("CSMPN_TC_MIN_ROWS", "4096"))  # 32 tiles; see DESIGN.md 4.4 for the measurements behind it
 
 
 def _block_uses_tc(algebra, layer, need_grad, rows=None) -> bool:

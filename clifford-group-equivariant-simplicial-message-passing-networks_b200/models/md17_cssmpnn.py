@@ -69,13 +69,16 @@ class CliffordSharedSimplicialMPNN_md17(SharedSimplicialBase):
         pred = self.projection(x[rows0])[..., 1:4]
         loc_pred = loc_node + pred
         targets = graph.y
+        if n_real != batch_size:
+            # the dummy complex (last rows) leaves BEFORE the losses: sqrt has no gradient at its all-zero prediction
+            v_real = loc_pred.shape[0] // batch_size * n_real
+            loc_pred, targets = loc_pred[:v_real], targets[:v_real]
+            batch_size = n_real
         sq = F.mse_loss(loc_pred.reshape(-1, 3), targets.reshape(-1, 3), reduction="none")
         ade_loss = torch.sqrt(sq.sum(dim=-1)).reshape(batch_size, -1, num_frames).mean(dim=-1).mean(dim=-1)
         fde_loss = torch.sqrt(F.mse_loss(loc_pred[:, -1, :], targets[:, -1, :], reduction="none").sum(dim=-1)
                               ).reshape(batch_size, -1).mean(dim=-1)
         loss = sq.reshape(batch_size, -1, 3).sum(-1).mean(-1)
-        if n_real != batch_size:
-            loss, ade_loss, fde_loss = loss[:n_real], ade_loss[:n_real], fde_loss[:n_real]
         return loss.mean(), {"loss": loss, "ade_loss": ade_loss, "fde_loss": fde_loss}
 
     def __str__(self):

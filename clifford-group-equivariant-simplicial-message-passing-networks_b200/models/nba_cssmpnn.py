@@ -51,7 +51,9 @@ class NBACliffordSharedSimplicialMPNN(SharedSimplicialBase):
         return self.feature_embedding(torch.cat((x, node_attr), dim=1))
 
     def forward(self, graph, step, mode):
+        self.begin_forward(graph)
         batch_size = graph.ptr.shape[0] - 1
+        n_real = int(getattr(graph, "n_real_graphs", batch_size))  # shape-padded batches end with one dummy complex
         num_frames = graph.pos.shape[1]
         d = self.algebra.dim
         node_attr, edge_attr = self.embed_simplex_types(graph)
@@ -60,8 +62,14 @@ class NBACliffordSharedSimplicialMPNN(SharedSimplicialBase):
         x = self.run_layers(x, graph, edge_attr, node_attr)
         out = self.projection(x[self.simplex_rows(graph)[0]])
         loc_pred = out[..., 1:3].reshape(batch_size, self.vertices_per_complex, num_frames * 4, -1)[:, :-1, ...]
-        loc_pred = loc_pred.reshape(-1, self.num_out, d)
         targets = graph.y
+        if n_real != batch_size:
+            # the dummy complex leaves BEFORE the losses: its prediction is exactly zero (zero vectors in, zero vectors out,
+            # by equivariance) and sqrt has no gradient there
+            loc_pred = loc_pred[:n_real]
+            targets = targets[: n_real * (self.vertices_per_complex - 1)]
+            batch_size = n_real
+        loc_pred = loc_pred.reshape(-1, self.num_out, d)
         ade_loss = torch.sqrt(F.mse_loss(loc_pred.reshape(-1, d), targets.reshape(-1, d), reduction="none").sum(dim=-1)
                               ).reshape(batch_size, -1, num_frames).mean(dim=-1).mean(dim=-1)
         fde_loss = torch.sqrt(F.mse_loss(loc_pred[:, -1, :], targets[:, -1, :], reduction="none").sum(dim=-1)

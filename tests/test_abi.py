@@ -97,7 +97,7 @@ def test_host_side_modules_import_without_gpu():
         importlib.import_module(name)
     from csmpn_b200.models import fused
 
-    assert fused.tc_min_rows() == 8192 and fused.fork_max_rows() > 1 << 30
+    assert fused.tc_min_rows() == 4096 and fused.fork_max_rows() > 1 << 30
 
 
 def test_bench_accounting_matches_survey_formulas():

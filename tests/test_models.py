@@ -363,3 +363,34 @@ def test_padded_stream_step_follows_eager_on_different_batches(optim):
     if optim == "sgd":
         for a, b in zip(p0, p1):
             assert_close(b, a, GRAD_TOL, "parameters after 3 SGD steps on different batches")
+
+
+@pytest.mark.gpu
+def test_padded_nba_batch_leaves_loss_and_gradients_unchanged(gold):
+    """the same for the NBA model (Cl(2,0), Rips complexes, targets for all vertices but the last of each complex)"""
+    from csmpn_b200.data.modules.simplicial_data import Data, SimplicialTransform
+    from csmpn_b200.data.padding import make_bucket, pad_to_bucket
+
+    dev = torch.device("cuda:0")
+    fx = gold["nba"]
+    b = fx["batch"]
+    graphs = []
+    for c in range(3):
+        lo = int(b["ptr"][c])
+        pos, vel = b["pos"][lo:lo + 6], b["vel"][lo:lo + 6]
+        graphs.append(Data(pos=pos.to(dev), vel=vel.to(dev), init_pos=pos[:, 0].to(dev), y=b["y"][5 * c:5 * c + 5].to(dev)))
+    g = SimplicialTransform(dim=2, dis=1e4, label="nba").lift(graphs, device=dev)
+    m = model_class("nba")(**fx["kwargs"]).to(dev)
+    m.load_state_dict(fx["state_dict"], strict=False)
+    loss, out = m(g, 0, "train")
+    g_ref = torch.autograd.grad(loss, [p for p in m.parameters() if p.requires_grad], allow_unused=True)
+    pb = pad_to_bucket(g, make_bucket([g.sizes], margin=1.2, multiple=8))
+    assert pb.y.shape[0] == g.y.shape[0] + 5 and pb.x_ind.shape[0] > g.x_ind.shape[0]
+    loss_p, out_p = m(pb, 0, "train")
+    g_p = torch.autograd.grad(loss_p, [p for p in m.parameters() if p.requires_grad], allow_unused=True)
+    assert_close(loss_p, loss, FWD_TOL, "nba loss of the padded batch")
+    assert_close(out_p["loss"], out["loss"], FWD_TOL, "nba per-sample losses of the padded batch")
+    for a, r in zip(g_p, g_ref):
+        assert (a is None) == (r is None)
+        if a is not None:
+            assert_close(a, r, GRAD_TOL, "nba grad (padded batch)")
