@@ -518,10 +518,10 @@ def layer_leg(workload, ncx, C, dev, world, rank, steps, warmup, lib, use_graph=
     glayer = None
     flat = torch.empty(n_par, device=dev)
 
-    def step(h, graph_, node_attr, pack=True):
+    def step(h, graph_, node_attr, pack=True, gl=None):
         hh = h.detach().requires_grad_()
         if glayer is not None:
-            y = glayer(hh, None, node_attr)
+            y = (gl or glayer)(hh, None, node_attr)
         else:
             y = layer(hh, graph_, PairedNodeAttr(node_attr), node_attr)
         grads = torch.autograd.grad(y, [hh] + params, d["cot"])
@@ -562,7 +562,10 @@ def layer_leg(workload, ncx, C, dev, world, rank, steps, warmup, lib, use_graph=
 
     from csmpn_b200.pipeline import HostFeeder
 
-    feeder = HostFeeder(dev)
+    # graphed runs: one captured layer per feeder slot, each with its own CSR buffers -- the CSR of batch i+1 is rebuilt on the
+    # copy stream right after its H2D copy (HostFeeder.prepare), under the kernels of step i, instead of in front of step i+1
+    glayers = []
+    feeder = HostFeeder(dev, prepare=(lambda k, bufs: glayers[k].set_graph(unpack(bufs)["edge_index"])) if use_graph else None)
 
     def run_e2e(n_steps):
         """n_steps layer steps from HOST buffers through the public API: every step copies its inputs from pinned host
@@ -575,9 +578,8 @@ def layer_leg(workload, ncx, C, dev, world, rank, steps, warmup, lib, use_graph=
                 feeder.submit(host_in)
             flush.fill_(1.0)  # L2 flush, inside the timed region
             x = unpack(dv)
-            if glayer is not None:  # batches of a fixed shape: CSR rebuilt in place, layer replayed from CUDA graphs
-                glayer.set_graph(x["edge_index"])
-                y, gh = step(x["h"], None, x["node_attr"])
+            if glayer is not None:  # batches of a fixed shape: CSR rebuilt in place (by the feeder), layer replayed from CUDA graphs
+                y, gh = step(x["h"], None, x["node_attr"], gl=glayers[dv["_index"]])
             else:
                 y, gh = step(x["h"], CSRGraph(x["edge_index"], N), x["node_attr"])
             feeder.drain(y.detach(), y_host)
@@ -621,6 +623,9 @@ def layer_leg(workload, ncx, C, dev, world, rank, steps, warmup, lib, use_graph=
         from csmpn_b200.graphs import GraphedEGCL
 
         glayer = GraphedEGCL(layer, graph, d["h"], PairedNodeAttr(d["node_attr"]), d["node_attr"])
+        if with_e2e:  # the e2e leg's per-slot layers (own CSR buffers each; same parameters)
+            glayers.extend(GraphedEGCL(layer, d["edge_index"].clone(), d["h"], PairedNodeAttr(d["node_attr"]), d["node_attr"])
+                           for _ in range(len(feeder.slots)))
     res = {"workload": desc, "aggr": aggr, "hidden": C, "complexes_per_step_per_gpu": ncx, "simplices_per_gpu": N, "pairs_per_gpu": E,
            "gpu_launches_per_step": int(launches_per_step)}
     if with_e2e:
@@ -651,6 +656,7 @@ def layer_leg(workload, ncx, C, dev, world, rank, steps, warmup, lib, use_graph=
             res["roofline"] = {"bound": "hbm", "achieved": None, "peak": hbm_peak, "unit": "GB/s", "frac": None, "traffic": None,
                                "kernel": f"unavailable: {e}", "peak_source": peak_src}
     del glayer
+    glayers.clear()
     return res
 
 
@@ -762,7 +768,7 @@ def run_ours(args):
                     "d2h_bytes_per_step": main["d2h_bytes_per_step"], "ms_per_step": main["e2e_ms_per_step"],
                     "regions_ms_per_step": main["e2e_regions_ms_per_step"],
                     "how": "median of 3 regions of K steps, each timed as one region; per step: ONE pinned H2D copy of h | edge_index | node_attr "
-                           "(csmpn_b200.pipeline.HostFeeder, copy of step i+1 overlaps the kernels of step i), CSR build (in place), layer "
+                           "(csmpn_b200.pipeline.HostFeeder, copy AND in-place CSR rebuild of step i+1 overlap the kernels of step i), layer "
                            "forward + backward (CUDA-graph replay unless --no-graph), D2H of the layer output and every parameter gradient "
                            "(+ grad_h with CSMPN_BENCH_D2H_GRAD_H=1); 256 MiB L2 flush inside the region every step"},
             "gpu_launches": int(main["gpu_launches_per_step"] * args.steps), "gpu_launches_per_step": main["gpu_launches_per_step"],

@@ -26,11 +26,15 @@ class HostFeeder:
     >>> feeder.join()                                    # compute stream waits for all outstanding copies
     """
 
-    def __init__(self, device, slots: int = 2):
+    def __init__(self, device, slots: int = 2, prepare=None):
+        """prepare(slot_index, device_tensors): optional per-batch preprocessing that only depends on the copied inputs
+        (e.g. the CSR of the batch's pairs, built into per-slot buffers); it runs on the copy stream right after the copies,
+        i.e. under the kernels of the previous step, and the slot only becomes ready once it has finished."""
         self.device = torch.device(device)
         self.copy_stream = torch.cuda.Stream(self.device)
         self.drain_stream = torch.cuda.Stream(self.device)
-        self.slots = [dict(bufs=None, ready=None, free=None) for _ in range(slots)]
+        self.prepare = prepare
+        self.slots = [dict(bufs=None, ready=None, free=None, index=i) for i in range(slots)]
         self._submitted = 0
         self._taken = 0
         self._drain_done = None
@@ -46,6 +50,8 @@ class HostFeeder:
                 slot["bufs"] = {k: torch.empty(v.shape, dtype=v.dtype, device=self.device) for k, v in host.items()}
             for k, v in host.items():
                 slot["bufs"][k].copy_(v, non_blocking=True)
+            if self.prepare is not None:
+                self.prepare(slot["index"], slot["bufs"])
             ev = torch.cuda.Event()
             ev.record(self.copy_stream)
             slot["ready"] = ev
@@ -56,6 +62,7 @@ class HostFeeder:
         torch.cuda.current_stream(self.device).wait_event(slot["ready"])
         out = dict(slot["bufs"])
         out["_slot"] = slot
+        out["_index"] = slot["index"]
         return out
 
     def release(self, dev: dict):
