@@ -394,3 +394,47 @@ def test_padded_nba_batch_leaves_loss_and_gradients_unchanged(gold):
         assert (a is None) == (r is None)
         if a is not None:
             assert_close(a, r, GRAD_TOL, "nba grad (padded batch)")
+
+
+@pytest.mark.gpu
+def test_padded_stream_step_nba_follows_eager(gold):
+    """the NBA model (Cl(2,0), Rips complexes whose edge / triangle counts change with the positions) trained from ONE graph
+    on different batches: same losses and, under SGD, the same parameters as the eager step"""
+    from csmpn_b200.data.modules.simplicial_data import Data, SimplicialTransform
+    from csmpn_b200.data.padding import make_bucket
+    from csmpn_b200.train_step import DataParallelStep, StreamGraphedStep
+
+    dev = torch.device("cuda:0")
+    fx = gold["nba"]
+    frames = fx["batch"]["pos"].shape[1]
+    lift = SimplicialTransform(dim=2, dis=1.6, label="nba")
+
+    def samples(seed, n=4):
+        g = torch.Generator().manual_seed(seed)
+        out = []
+        for _ in range(n):
+            pos = torch.randn(6, frames, 2, generator=g)
+            out.append(Data(pos=pos.to(dev), vel=torch.randn(6, frames, 2, generator=g).to(dev), init_pos=pos[:, 0].to(dev),
+                            y=torch.randn(5, fx["batch"]["y"].shape[1], 2, generator=g).to(dev)))
+        return out
+
+    pools = [samples(500 + k) for k in range(4)]
+    sizes = [lift.lift(p, device=dev).sizes for p in pools]
+    assert len({(s["simplices"], s["pairs"]) for s in sizes}) > 1, "the batches should differ in size"
+    results = []
+    for graphed in (False, True):
+        m = model_class("nba")(**fx["kwargs"]).to(dev)
+        m.load_state_dict(fx["state_dict"], strict=False)
+        opt = torch.optim.SGD(m.parameters(), lr=1e-2)
+        step = StreamGraphedStep(m, opt, lift.lift(pools[0], device=dev), make_bucket(sizes, multiple=8)) if graphed \
+            else DataParallelStep(m, opt)
+        losses = []
+        for k in (1, 2, 3):
+            loss, _ = step(lift.lift(pools[k], device=dev), k)
+            losses.append(float(loss.detach()))
+        results.append((losses, [p.detach().clone() for p in m.parameters()]))
+    (l0, p0), (l1, p1) = results
+    for a, b in zip(l0, l1):
+        assert abs(a - b) <= 1e-5 * max(1.0, abs(a)), (l0, l1)
+    for a, b in zip(p0, p1):
+        assert_close(b, a, GRAD_TOL, "nba parameters after 3 SGD steps on different batches")
