@@ -533,8 +533,15 @@ def layer_leg(workload, ncx, C, dev, world, rank, steps, warmup, lib, use_graph=
         return y, grads[0]
 
     # host-resident inputs (pinned) for the end-to-end leg
-    # ONE pinned staging buffer holding h | edge_index | node_attr back to back: one H2D copy per step instead of three
-    segs = [("h", b["h"]), ("edge_index", b["edge_index"]), ("node_attr", b["node_attr"])]
+    # ONE pinned staging buffer holding h | edge_index | node_attr back to back: one H2D copy per step instead of three.
+    # Wire format: the pair list as int32 (simplex ids of a batch fit easily) and, when node_attr only carries scalars -- the
+    # simplex-type embedding of the models, md17_cssmpnn.py:122-129 -- its grade-0 part [N, T]; both are widened on the device
+    # into per-slot int64 [2, E] / [N, T, B] tensors by the feeder (copy stream), so the layer is called with the reference's
+    # argument types.  At 8 GPUs the step time of this leg is set by the bytes that cross the host link.
+    compact_attr = bool((b["node_attr"][..., 1:] == 0).all()) and os.environ.get("CSMPN_BENCH_WIRE", "compact") == "compact"
+    segs = [("h", b["h"]),
+            ("edge_index", b["edge_index"].to(torch.int32) if compact_attr else b["edge_index"]),
+            ("node_attr", b["node_attr"][..., 0].contiguous() if compact_attr else b["node_attr"])]
     offs, total_b = {}, 0
     for k, t in segs:
         offs[k] = total_b
@@ -565,7 +572,23 @@ def layer_leg(workload, ncx, C, dev, world, rank, steps, warmup, lib, use_graph=
     # graphed runs: one captured layer per feeder slot, each with its own CSR buffers -- the CSR of batch i+1 is rebuilt on the
     # copy stream right after its H2D copy (HostFeeder.prepare), under the kernels of step i, instead of in front of step i+1
     glayers = []
-    feeder = HostFeeder(dev, prepare=(lambda k, bufs: glayers[k].set_graph(unpack(bufs)["edge_index"])) if use_graph else None)
+    n_slots = 2
+    ei_dev = [torch.empty((2, E), dtype=torch.int64, device=dev) for _ in range(n_slots)]
+    na_dev = [torch.zeros((N, T_TYPES, B), dtype=torch.float32, device=dev) for _ in range(n_slots)]
+
+    def prepare(k, bufs):
+        """on the copy stream, right after the H2D copy of slot k: widen the wire format, rebuild the slot's CSR in place"""
+        x = unpack(bufs)
+        if compact_attr:
+            ei_dev[k].copy_(x["edge_index"])
+            na_dev[k][..., 0].copy_(x["node_attr"])
+        else:
+            ei_dev[k], na_dev[k] = x["edge_index"], x["node_attr"]
+        if use_graph and glayers:
+            glayers[k].set_graph(ei_dev[k])
+
+    feeder = HostFeeder(dev, slots=n_slots, prepare=prepare)
+    drained = [None] * n_slots
 
     def run_e2e(n_steps):
         """n_steps layer steps from HOST buffers through the public API: every step copies its inputs from pinned host
@@ -577,23 +600,35 @@ def layer_leg(workload, ncx, C, dev, world, rank, steps, warmup, lib, use_graph=
             if i + 1 < n_steps:
                 feeder.submit(host_in)
             flush.fill_(1.0)  # L2 flush, inside the timed region
-            x = unpack(dv)
-            if glayer is not None:  # batches of a fixed shape: CSR rebuilt in place (by the feeder), layer replayed from CUDA graphs
-                y, gh = step(x["h"], None, x["node_attr"], gl=glayers[dv["_index"]])
+            x, k = unpack(dv), dv["_index"]
+            if drained[k] is not None:  # the graph's static outputs of this slot: their last D2H copies must have left
+                torch.cuda.current_stream(dev).wait_event(drained[k])
+            if glayer is not None:
+                # batches of a fixed shape: ONE graph replay per step (forward + backward + gradient pack) that reads the
+                # feeder's device buffers directly; the CSR was rebuilt in place by the feeder
+                y, gh, gflat = glayers[k]()
+                if world > 1:
+                    dist.all_reduce(gflat)
+                    gflat.div_(world)
             else:
-                y, gh = step(x["h"], CSRGraph(x["edge_index"], N), x["node_attr"])
-            feeder.drain(y.detach(), y_host)
+                y, gh = step(x["h"], CSRGraph(ei_dev[k], N), na_dev[k])
+                gflat = flat
+            feeder.drain(y, y_host)
             if d2h_grad_h:
                 feeder.drain(gh, gh_host)
-            feeder.drain(flat, gp_host)
+            feeder.drain(gflat, gp_host)
+            drained[k] = feeder._drain_done
             feeder.release(dv)
         feeder.join()
 
     def timed_e2e(steps, warmup, regions=3):
         run_e2e(warmup)
         out = []
+        host = []
         for _ in range(regions):
             out.append(_timed_block(lambda: run_e2e(steps), dev, world))
+            host.append(_timed_block.host_ms / steps)
+        timed_e2e.host_ms_per_step = statistics.median(host)
         return statistics.median(out), out
 
     def timed(steps, warmup):
@@ -623,15 +658,27 @@ def layer_leg(workload, ncx, C, dev, world, rank, steps, warmup, lib, use_graph=
         from csmpn_b200.graphs import GraphedEGCL
 
         glayer = GraphedEGCL(layer, graph, d["h"], PairedNodeAttr(d["node_attr"]), d["node_attr"])
-        if with_e2e:  # the e2e leg's per-slot layers (own CSR buffers each; same parameters)
-            glayers.extend(GraphedEGCL(layer, d["edge_index"].clone(), d["h"], PairedNodeAttr(d["node_attr"]), d["node_attr"])
-                           for _ in range(len(feeder.slots)))
+        if with_e2e:
+            # the e2e leg: one whole-step graph per feeder slot, reading that slot's device buffers (own CSR buffers each, same
+            # parameters).  Two submits create the slots' device buffers (their addresses then stay fixed).
+            from csmpn_b200.graphs import GraphedLayerStep
+
+            for _ in range(n_slots):
+                feeder.submit(host_in)
+            torch.cuda.synchronize()
+            for k in range(n_slots):
+                x = unpack(feeder.slots[k]["bufs"])
+                glayers.append(GraphedLayerStep(layer, ei_dev[k], x["h"], na_dev[k], d["cot"]))
+            for _ in range(n_slots):   # hand the two submitted batches back: the timed loops start from an empty feeder
+                feeder.release(feeder.next())
+            feeder.join()
     res = {"workload": desc, "aggr": aggr, "hidden": C, "complexes_per_step_per_gpu": ncx, "simplices_per_gpu": N, "pairs_per_gpu": E,
            "gpu_launches_per_step": int(launches_per_step)}
     if with_e2e:
         e2e_ms, regions = timed_e2e(steps, max(3, warmup // 2))
         res["e2e_ms_per_step"] = e2e_ms / steps
         res["e2e_regions_ms_per_step"] = [r / steps for r in regions]
+        res["e2e_host_enqueue_ms_per_step"] = timed_e2e.host_ms_per_step
         res["h2d_bytes_per_step"], res["d2h_bytes_per_step"] = h2d_bytes, d2h_bytes
     total_ms = timed(steps, warmup)
     res["ms_per_step"] = total_ms / steps
@@ -677,7 +724,9 @@ def _timed_block(fn, dev, world):
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
+    h0 = time.perf_counter()
     fn()
+    _timed_block.host_ms = (time.perf_counter() - h0) * 1e3  # wall time the host needed to ENQUEUE the region (before the sync)
     e1.record()
     torch.cuda.synchronize()
     t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
@@ -767,9 +816,10 @@ def run_ours(args):
             "e2e": None if args.no_e2e else {"value": main["e2e_value"], "unit": "simplices/s", "h2d_bytes_per_step": main["h2d_bytes_per_step"],
                     "d2h_bytes_per_step": main["d2h_bytes_per_step"], "ms_per_step": main["e2e_ms_per_step"],
                     "regions_ms_per_step": main["e2e_regions_ms_per_step"],
-                    "how": "median of 3 regions of K steps, each timed as one region; per step: ONE pinned H2D copy of h | edge_index | node_attr "
+                    "host_enqueue_ms_per_step": main["e2e_host_enqueue_ms_per_step"],
+                    "how": "median of 3 regions of K steps, each timed as one region; per step: ONE pinned H2D copy of h | edge_index (int32 on the wire) | node_attr (its scalar part on the wire; both widened on the device to the reference's int64 [2, E] / [N, T, B]) "
                            "(csmpn_b200.pipeline.HostFeeder, copy AND in-place CSR rebuild of step i+1 overlap the kernels of step i), layer "
-                           "forward + backward (CUDA-graph replay unless --no-graph), D2H of the layer output and every parameter gradient "
+                           "forward + backward + gradient pack as ONE CUDA-graph replay reading the feeder's device buffers (csmpn_b200.graphs.GraphedLayerStep; eager with --no-graph), D2H of the layer output and every parameter gradient "
                            "(+ grad_h with CSMPN_BENCH_D2H_GRAD_H=1); 256 MiB L2 flush inside the region every step"},
             "gpu_launches": int(main["gpu_launches_per_step"] * args.steps), "gpu_launches_per_step": main["gpu_launches_per_step"],
             "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "workloads": others or None, "train": train, "lifting": lifting,

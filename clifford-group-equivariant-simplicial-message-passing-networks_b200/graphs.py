@@ -80,3 +80,51 @@ class GraphedEGCL:
         if self.paired:  # edge_attr (a PairedNodeAttr or None) is implied by node_attr
             return self.fn(h, node_attr)
         return self.fn(h, edge_attr, node_attr)
+
+
+class GraphedLayerStep:
+    """Forward + backward + gradient pack of one EGCL layer as ONE CUDA graph over STATIC tensors.
+
+    ``h``, ``node_attr`` and ``cot`` are the tensors the graph reads: a host feeder copies every new batch straight into them
+    (no per-call copy into graph-private buffers as with ``torch.cuda.make_graphed_callables``) and a step is a single
+    ``replay()`` -- a dozen host calls per step instead of ~40, which is what eight feeder processes on one host need.
+    ``set_graph(edge_index)`` rebuilds the CSR of new pairs in place (same counts).  Outputs (static as well): ``y``,
+    ``grad_h`` and ``flat`` (every parameter gradient, packed in ``layer.parameters()`` order)."""
+
+    def __init__(self, layer: nn.Module, edge_index: torch.Tensor, h: torch.Tensor, node_attr: torch.Tensor, cot: torch.Tensor,
+                 warmup: int = 3):
+        from .models.cegnn_utils import PairedNodeAttr
+
+        if not h.is_cuda:
+            raise ValueError("GraphedLayerStep needs CUDA tensors")
+        self.h, self.node_attr, self.cot = h, node_attr, cot
+        self.csr = CSRGraph(edge_index.clone(), h.shape[0])
+        self.params = list(layer.parameters())
+        self.flat = torch.empty(sum(p.numel() for p in self.params), dtype=torch.float32, device=h.device)
+        views = list(self.flat.split([p.numel() for p in self.params]))
+
+        def run():
+            hh = self.h.detach().requires_grad_()
+            y = layer(hh, self.csr, PairedNodeAttr(self.node_attr), self.node_attr)
+            grads = torch.autograd.grad(y, [hh] + self.params, self.cot)
+            torch._foreach_copy_(views, [g.reshape(-1) for g in grads[1:]])
+            return y.detach(), grads[0]
+
+        cur = torch.cuda.current_stream(h.device)
+        side = torch.cuda.Stream(h.device)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            for _ in range(warmup):   # builds the lazily created helper structures (sorted views of the CSR, workspaces)
+                run()
+        cur.wait_stream(side)
+        torch.cuda.synchronize(h.device)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.y, self.grad_h = run()
+
+    def set_graph(self, edge_index: torch.Tensor):
+        self.csr.rebuild_(edge_index)
+
+    def __call__(self):
+        self.graph.replay()
+        return self.y, self.grad_h, self.flat

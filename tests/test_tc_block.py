@@ -169,6 +169,36 @@ def test_graphed_layer_matches_eager():
             assert torch.equal(a, b)
 
 
+def test_graphed_layer_step_matches_eager():
+    """csmpn_b200.graphs.GraphedLayerStep: forward + backward + gradient pack as ONE graph over static tensors (what the host-fed
+    leg of bench.py replays): new VALUES written into the static tensors and a new pair structure rebuilt in place give the
+    output, grad_h and every parameter gradient of the eager step, bit for bit."""
+    from csmpn_b200.graphs import GraphedLayerStep
+    from csmpn_b200.models.cegnn_utils import PairedNodeAttr
+    from csmpn_b200.models.ops import CSRGraph
+
+    case = CASES[0]
+    name, metric, C, T, ncx, n, e, aggr = case
+    CliffordAlgebra, M = _mods()
+    ralg, params, h, ei, ea, na, cot = _inputs(case)
+    alg = CliffordAlgebra(metric).to(DEV)
+    m = M.EGCL(alg, C, C, C, edge_attr_features=2 * T, node_attr_features=T, aggr=aggr).to(DEV)
+    _load(m, params)
+    plist = list(m.parameters())
+    h_s, na_s, cot_s = h.to(DEV).clone(), na.to(DEV).clone(), cot.to(DEV).clone()
+    g = GraphedLayerStep(m, ei.to(DEV), h_s, na_s, cot_s)
+    ei2 = _graph(ncx, n, e, torch.Generator().manual_seed(99))
+    for scale, pairs in ((1.0, ei), (-0.41, ei), (0.7, ei2)):
+        h_s.copy_(h.to(DEV) * scale)          # the feeder writes new values into the static tensors
+        g.set_graph(pairs.to(DEV))
+        y, gh, flat = g()
+        h1 = (h.to(DEV) * scale).requires_grad_()
+        ye = m(h1, CSRGraph(pairs.to(DEV), h.shape[0]), PairedNodeAttr(na.to(DEV)), na.to(DEV))
+        ge = torch.autograd.grad(ye, [h1] + plist, cot.to(DEV))
+        assert torch.equal(y, ye) and torch.equal(gh, ge[0])
+        assert torch.equal(flat, torch.cat([t.reshape(-1) for t in ge[1:]]))
+
+
 def test_graphed_layer_new_structure_same_shape():
     """GraphedEGCL.set_graph: a different complex structure with the same counts is rebuilt in place (CSR + sorted views)
     and the replayed graphs follow it."""
