@@ -518,12 +518,10 @@ def layer_leg(workload, ncx, C, dev, world, rank, steps, warmup, lib, use_graph=
     glayer = None
     flat = torch.empty(n_par, device=dev)
 
-    def step(h, graph_, node_attr, pack=True, gl=None):
+    def step(h, graph_, node_attr, pack=True):
+        """one EAGER layer step (forward + backward through autograd); the graphed runs replay GraphedLayerStep instead"""
         hh = h.detach().requires_grad_()
-        if glayer is not None:
-            y = (gl or glayer)(hh, None, node_attr)
-        else:
-            y = layer(hh, graph_, PairedNodeAttr(node_attr), node_attr)
+        y = layer(hh, graph_, PairedNodeAttr(node_attr), node_attr)
         grads = torch.autograd.grad(y, [hh] + params, d["cot"])
         if pack or world > 1:  # one flat gradient buffer: the all-reduce bucket / the D2H payload of the e2e leg
             torch._foreach_copy_(list(flat.split([p.numel() for p in params])), [g.reshape(-1) for g in grads[1:]])
@@ -631,9 +629,25 @@ def layer_leg(workload, ncx, C, dev, world, rank, steps, warmup, lib, use_graph=
         timed_e2e.host_ms_per_step = statistics.median(host)
         return statistics.median(out), out
 
+    gstep = None
+    if use_graph:
+        # `value`: inputs resident -> the step is ONE replay of the whole-step graph on the resident tensors (no per-call copies
+        # into graph-private buffers); the gradient pack is part of it only where it is used (the all-reduce bucket, N > 1)
+        from csmpn_b200.graphs import GraphedLayerStep
+
+        gstep = GraphedLayerStep(layer, d["edge_index"], d["h"], d["node_attr"], d["cot"], pack=world > 1)
+
+    def resident_step():
+        if gstep is None:
+            return step(d["h"], graph, d["node_attr"], pack=False)
+        _, _, gflat = gstep()
+        if world > 1:
+            dist.all_reduce(gflat)
+            gflat.div_(world)
+
     def timed(steps, warmup):
         for _ in range(warmup):
-            step(d["h"], graph, d["node_attr"], pack=False)
+            resident_step()
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
@@ -643,7 +657,7 @@ def layer_leg(workload, ncx, C, dev, world, rank, steps, warmup, lib, use_graph=
             flush.fill_(1.0)  # L2 flush (256 MiB > 126 MB L2), outside the timed events
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            step(d["h"], graph, d["node_attr"], pack=False)
+            resident_step()
             e1.record()
             evs.append((e0, e1))
         torch.cuda.synchronize()
@@ -655,9 +669,7 @@ def layer_leg(workload, ncx, C, dev, world, rank, steps, warmup, lib, use_graph=
         return float(t.item())
 
     if use_graph:
-        from csmpn_b200.graphs import GraphedEGCL
-
-        glayer = GraphedEGCL(layer, graph, d["h"], PairedNodeAttr(d["node_attr"]), d["node_attr"])
+        glayer = gstep  # (flag for the host-fed leg below: graphed)
         if with_e2e:
             # the e2e leg: one whole-step graph per feeder slot, reading that slot's device buffers (own CSR buffers each, same
             # parameters).  Two submits create the slots' device buffers (their addresses then stay fixed).
@@ -803,7 +815,8 @@ def run_ours(args):
             cores = os.cpu_count() or 1
             cpu = {"value": cN / cms, "unit": "simplices/s", "cores": cores, "kind": kind,
                    "sample": f"the same {ncx} complexes ({cN} simplices, {cE} pairs), median of 3 steps after 1 warm-up, {_cpu_what(kind, cores)}"}
-        glaunch = "CUDA-graph replay of the layer forward and backward (csmpn_b200.graphs.GraphedEGCL)" if not args.no_graph else "eager"
+        glaunch = ("ONE CUDA-graph replay per step: layer forward + backward on the resident tensors (csmpn_b200.graphs.GraphedLayerStep)"
+                   if not args.no_graph else "eager")
         line = {
             "metric": "simplices/sec fwd+bwd per CSMPN layer", "value": main["value"], "unit": "simplices/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": main["ms_per_step"], "higher_is_better": True,

@@ -89,10 +89,11 @@ class GraphedLayerStep:
     (no per-call copy into graph-private buffers as with ``torch.cuda.make_graphed_callables``) and a step is a single
     ``replay()`` -- a dozen host calls per step instead of ~40, which is what eight feeder processes on one host need.
     ``set_graph(edge_index)`` rebuilds the CSR of new pairs in place (same counts).  Outputs (static as well): ``y``,
-    ``grad_h`` and ``flat`` (every parameter gradient, packed in ``layer.parameters()`` order)."""
+    ``grad_h`` and ``flat`` (every parameter gradient, packed in ``layer.parameters()`` order; ``pack=False``: left in
+    ``param_grads``, one tensor per parameter)."""
 
     def __init__(self, layer: nn.Module, edge_index: torch.Tensor, h: torch.Tensor, node_attr: torch.Tensor, cot: torch.Tensor,
-                 warmup: int = 3):
+                 warmup: int = 3, pack: bool = True):
         from .models.cegnn_utils import PairedNodeAttr
 
         if not h.is_cuda:
@@ -107,7 +108,10 @@ class GraphedLayerStep:
             hh = self.h.detach().requires_grad_()
             y = layer(hh, self.csr, PairedNodeAttr(self.node_attr), self.node_attr)
             grads = torch.autograd.grad(y, [hh] + self.params, self.cot)
-            torch._foreach_copy_(views, [g.reshape(-1) for g in grads[1:]])
+            if pack:
+                torch._foreach_copy_(views, [g.reshape(-1) for g in grads[1:]])
+            else:
+                self.param_grads = list(grads[1:])  # static tensors as well (the graph's pool)
             return y.detach(), grads[0]
 
         cur = torch.cuda.current_stream(h.device)
