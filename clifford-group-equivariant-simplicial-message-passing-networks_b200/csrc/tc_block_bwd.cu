@@ -1154,10 +1154,13 @@ size_t gemm_smem(int nsets, int n16, int kmax, bool silu = false) {
   constexpr int B = Alg<DIM>::B, G = Alg<DIM>::G;
   return (size_t)(kRing + 1) * B * kPS + (size_t)nsets * G * 2 * n16 * kmax * 4 + 128 + (silu ? (size_t)2 * n16 * G * 4 : 0);
 }
-// CSMPN_TC_FUSE_SILU=0 keeps the MVSiLU adjoint as its own kernel (tests compare the two paths)
+// CSMPN_TC_FUSE_SILU=1 folds the MVSiLU adjoint into the epilogue of the dy2 GEMM (tests compare the two paths).  Default
+// since the prologue rework: its own kernel.  The fused epilogue saves two tensor passes, but it runs in the GEMM kernel's
+// one 16-warp CTA per SM, whose per-SM chain bounds the kernel; the streaming elementwise kernel (two 8-warp CTAs per SM,
+// cp.async stages) does the same work at 0.7 of the HBM roof: layer 1.130 -> 1.111 ms, motion 0.774 -> 0.739, NBA 3.14 -> 3.10.
 inline bool fuse_silu_adjoint() {
   const char* e = getenv("CSMPN_TC_FUSE_SILU");  // read per call: a test toggles it within one process
-  return !(e && e[0] == '0');
+  return e && e[0] == '1';
 }
 template <int DIM>
 size_t dw_smem(int M, int na4, int cpb) {

@@ -709,7 +709,7 @@ def _kernel_stages(d: BlockDesc, g, B: int):
     gy = T if g.gy_bpt else ref(C)
     gx = 0 if not g.grad_x else (Tin if g.gx_bpt else ref(cin))
     wide = bool(lib().csmpn_block_tc_plan(B.bit_length() - 1, cin, C) & 8)
-    fused_silu = os.environ.get("CSMPN_TC_FUSE_SILU", "1") != "0" and cp <= 64 and not wide
+    fused_silu = os.environ.get("CSMPN_TC_FUSE_SILU", "0") == "1" and cp <= 64 and not wide
     mid = ([("tc_bgemm", "dy2 = dy2p + d WL + dxr WR, MVSiLU adjoint in the epilogue -> dy1", 2, 5 * T, 3 * rows * 4 * B * C * C)]
            if fused_silu else
            [("tc_bgemm", "dy2 = dy2p + d WL + dxr WR", 2, 4 * T, 3 * rows * 4 * B * C * C), ("tc_b3", "MVSiLU adjoint", 4, 3 * T, 0)])
