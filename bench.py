@@ -615,7 +615,7 @@ def layer_leg(workload, ncx, C, dev, world, rank, steps, warmup, lib, use_graph=
             if d2h_grad_h:
                 feeder.drain(gh, gh_host)
             feeder.drain(gflat, gp_host)
-            drained[k] = feeder._drain_done
+            drained[k] = feeder.last_drain_event
             feeder.release(dv)
         feeder.join()
 

@@ -82,6 +82,12 @@ class HostFeeder:
             done.record(self.drain_stream)
             self._drain_done = done
 
+    @property
+    def last_drain_event(self):
+        """event recorded after the most recent ``drain`` copy (None before the first): a producer that overwrites the
+        drained tensor in place (e.g. a CUDA graph's static output) waits for it first"""
+        return self._drain_done
+
     def join(self):
         cur = torch.cuda.current_stream(self.device)
         cur.wait_stream(self.copy_stream)
