@@ -1,5 +1,5 @@
 import os, subprocess, time, torch
-print(subprocess.run("nvidia-smi topo -m; lscpu | grep -i 'numa\|^CPU(s)\|Model name'; cat /sys/fs/cgroup/cpuset.cpus.effective 2>/dev/null; nproc; cat /proc/self/status | grep -i 'Cpus_allowed_list\|Mems_allowed_list'", shell=True, capture_output=True, text=True).stdout)
+print(subprocess.run(r"nvidia-smi topo -m; lscpu | grep -i 'numa\|^CPU(s)\|Model name'; cat /sys/fs/cgroup/cpuset.cpus.effective 2>/dev/null; nproc; cat /proc/self/status | grep -i 'Cpus_allowed_list\|Mems_allowed_list'", shell=True, capture_output=True, text=True).stdout)
 dev = torch.device("cuda:0")
 def bw(tag):
     x = torch.empty(64 * 1024 * 1024 // 4).pin_memory()
