@@ -107,3 +107,39 @@ def test_bench_accounting_matches_survey_formulas():
     flops, nbytes = bench.layer_flops_bytes(1000, 6000, 32, 8)
     assert abs(nbytes / 1000 - 23.6e3) / 23.6e3 < 0.02
     assert abs(flops / 1000 - 2.63e6) / 2.63e6 < 0.02
+
+
+def test_struct_layouts_match_the_header(tmp_path):
+    """The ctypes mirrors of the three C structs (csmpn_block_desc, csmpn_block_grads, csmpn_lift_desc) have the header's
+    size and the header's offset for every field: a C program compiled from include/csmpn_b200.h prints them (gcc; no GPU)."""
+    import ctypes
+    import shutil
+    import subprocess
+
+    from csmpn_b200.data.modules.lifting import LiftDesc
+    from csmpn_b200.models.fused import BlockDesc, BlockGrads
+
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    structs = {"csmpn_block_desc": BlockDesc, "csmpn_block_grads": BlockGrads, "csmpn_lift_desc": LiftDesc}
+    lines = ["#include <stddef.h>", "#include <stdio.h>", '#include "csmpn_b200.h"', "int main(void) {"]
+    for cname, cls in structs.items():
+        lines.append(f'  printf("{cname} size %zu\\n", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'  printf("{cname} {fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ["  return 0;", "}"]
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    inc = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include")
+    subprocess.run([gcc, "-std=c11", "-I", inc, str(src), "-o", str(exe)], check=True, capture_output=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split("\n")
+    seen = 0
+    for line in filter(None, out):
+        cname, fname, val = line.split()
+        cls = structs[cname]
+        want = ctypes.sizeof(cls) if fname == "size" else getattr(cls, fname).offset
+        assert int(val) == want, f"{cname}.{fname}: header {val}, ctypes {want}"
+        seen += 1
+    assert seen == sum(len(c._fields_) + 1 for c in structs.values())
