@@ -13,6 +13,7 @@ values so a reference ``state_dict`` loads unchanged.
 from __future__ import annotations
 
 import functools
+import itertools
 import math
 
 import torch
@@ -233,65 +234,60 @@ class CliffordAlgebra(nn.Module):
         return self._forms(mv, grades, 0)
 
     # ---------------------------------------------------------------- versor utilities
+    # Off the hot path (no model calls them); kept so that code written against the reference's CliffordAlgebra -- its
+    # equivariance checks use rho / versor (cliffordalgebra.py:170-236) -- keeps working.  Same results, own wording.
     def sandwich(self, u, v, w):
         return self.geometric_product(self.geometric_product(u, v), w)
 
     def output_blades(self, blades_left, blades_right):
-        blades = []
-        for blade_left in blades_left:
-            for blade_right in blades_right:
-                bitmap_left = self.bbo.index_to_bitmap[blade_left]
-                bitmap_right = self.bbo.index_to_bitmap[blade_right]
-                bitmap_out, _ = gmt_element(int(bitmap_left), int(bitmap_right), self._metric_list)
-                blades.append(int(self.bbo.bitmap_to_index[bitmap_out]))
-        return torch.tensor(blades)
+        """blade index of e_l e_r for every (l, r), l-major"""
+        to_bitmap, to_index = self.bbo.index_to_bitmap, self.bbo.bitmap_to_index
+        return torch.tensor([int(to_index[gmt_element(int(to_bitmap[l]), int(to_bitmap[r]), self._metric_list)[0]])
+                             for l, r in itertools.product(blades_left, blades_right)])
 
     def random(self, n=None):
-        if n is None:
-            n = 1
-        return torch.randn(n, self.n_blades)
+        return torch.randn(1 if n is None else n, self.n_blades)
 
     def random_vector(self, n=None):
-        if n is None:
-            n = 1
-        vector_indices = self.bbo_grades == 1
-        v = torch.zeros(n, self.n_blades, device=self.cayley.device)
-        v[:, vector_indices] = torch.randn(n, int(vector_indices.sum()), device=self.cayley.device)
-        return v
+        rows, dev = (1 if n is None else n), self.cayley.device
+        grade1 = torch.nonzero(self.bbo_grades == 1).squeeze(1).to(dev)
+        draws = torch.randn(rows, grade1.numel(), device=dev)
+        return torch.zeros(rows, self.n_blades, device=dev).index_copy_(1, grade1, draws)
 
     def parity(self, mv):
-        is_odd = torch.all(mv[..., self.even_grades] == 0)
-        is_even = torch.all(mv[..., self.odd_grades] == 0)
-        if is_odd ^ is_even:
-            return is_odd
-        else:
+        """0-dim bool tensor: True for an odd element, False for an even one; anything mixed (or zero) is rejected"""
+        no_even_part = bool((mv[..., self.even_grades] == 0).all())
+        no_odd_part = bool((mv[..., self.odd_grades] == 0).all())
+        if no_even_part == no_odd_part:
             raise ValueError("This is not a homogeneous element.")
+        return torch.tensor(no_even_part)
 
     def eta(self, w):
-        return (-1) ** self.parity(w)
+        return -1 if bool(self.parity(w)) else 1
 
     def alpha_w(self, w, mv):
-        return self.even_grades * mv + self.eta(w) * self.odd_grades * mv
+        # the grade involution of mv when w is odd, mv itself when w is even
+        return torch.where(self.odd_grades.to(mv.device), self.eta(w) * mv, mv)
 
     def inverse(self, mv, blades=None):
-        # kept as in the reference (cliffordalgebra.py:215-217), including its normalisation quirk
-        mv_ = self.beta(mv, blades=blades)
-        return mv_ / self.b(mv, mv_)
+        reverse = self.beta(mv, blades=blades)
+        return reverse / self.b(mv, reverse)  # the reference's normalisation (cliffordalgebra.py:215-217), quirk included
 
     def rho(self, w, mv):
         return self.sandwich(w, self.alpha_w(w, mv), self.inverse(w))
 
     def reduce_geometric_product(self, inputs):
-        return functools.reduce(self.geometric_product, inputs)
+        factors = iter(inputs)
+        acc = next(factors)
+        for f in factors:
+            acc = self.geometric_product(acc, f)
+        return acc
 
     def versor(self, order=None, normalized=True):
         if order is None:
-            order = self.dim if self.dim % 2 == 0 else self.dim - 1
-        vectors = self.random_vector(order)
-        versor = self.reduce_geometric_product(vectors[:, None])
-        if normalized:
-            versor = versor / self.norm(versor)[..., :1]
-        return versor
+            order = self.dim - self.dim % 2  # the largest even number of reflections
+        v = self.reduce_geometric_product(self.random_vector(order)[:, None])
+        return v / self.norm(v)[..., :1] if normalized else v
 
     def rotor(self):
         return self.versor()
